@@ -1,0 +1,245 @@
+// gsr_common.cuh -- host/device math shared by every kernel of the rasteriser.
+//
+// Everything that decides WHICH pixels a Gaussian touches lives here as
+// __host__ __device__ functions so that the CPU test hooks (gsr_hostcheck.cu) can
+// run the very same code against the oracle without a GPU.
+//
+// Reference semantics restated here (GSASR tree):
+//   pixel coordinate rule + inclusive dmax test   utils/gs_cuda_dmax/gs.cu:39-50, 124-132
+//   conic coefficients                            utils/gs_cuda_dmax/gs.cu:33-36, 106-111
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#define GSR_HD __host__ __device__ __forceinline__
+
+// ---- geometry of the decomposition ---------------------------------------------------
+constexpr int GSR_TILE = 32;          // forward CTA tile, pixels per side
+constexpr int GSR_BIN = 16;           // home-bin side (Gaussians are counting-sorted by bin)
+constexpr int GSR_REGION = 8;         // one warp of the forward kernel owns an 8x8 region
+constexpr int GSR_LARGE_PX = 128;     // half-extent above which a Gaussian goes to the "large" list
+constexpr int GSR_MAX_DIM = 32767;    // bbox corners are stored as int16
+constexpr float GSR_LOG2E = 1.4426950408889634f;
+constexpr float GSR_CULL_PAD_PX = 0.02f;  // slack on every culling bound (pixels)
+
+// Sorted per-Gaussian record consumed by the raster kernels (32 B, two float4 loads).
+//   E(dx,dy) = a*dx*dx + b*dx*dy + c*dy*dy   (log2 units, dx/dy in normalised [-1,1] units)
+//   value    = exp2(E);  contribution = value * (r,g,bl)
+struct __align__(16) GsrRec {
+  float x, y, a, b;
+  float c, r, g, bl;
+};
+
+// Cull box: inclusive integer pixel ranges packed as 4 x 15 bit in a uint2.  Bit 15 of the
+// first half-word carries the "window binds" flag: the dmax window cuts the k-sigma box on at
+// least one side, so pixels outside the box must be excluded EXACTLY (they may carry large
+// values) -- the predicated path of the kernels.
+GSR_HD uint2 gsr_box_pack(int x0, int x1, int y0, int y1, bool binds) {
+  // x0,x1,y0,y1 in [0,32767]; the flag goes to the sign bit of the first half-word.
+  uint32_t lo = (uint32_t)(x0 & 0x7fff) | (binds ? 0x8000u : 0u) | ((uint32_t)(x1 & 0x7fff) << 16);
+  uint32_t hi = (uint32_t)(y0 & 0x7fff) | ((uint32_t)(y1 & 0x7fff) << 16);
+  return make_uint2(lo, hi);
+}
+GSR_HD void gsr_box_unpack(uint2 p, int& x0, int& x1, int& y0, int& y1, bool& binds) {
+  x0 = (int)(p.x & 0x7fffu);
+  binds = (p.x & 0x8000u) != 0;
+  x1 = (int)((p.x >> 16) & 0x7fffu);
+  y0 = (int)(p.y & 0x7fffu);
+  y1 = (int)((p.y >> 16) & 0x7fffu);
+}
+
+// ---- the reference's pixel coordinate rule (gs.cu:39,46): double arithmetic, one rounding
+// to float on assignment.
+GSR_HD float gsr_pix_coord(int i, int n) { return (float)(2.0 * i / (n - 1) - 1.0); }
+
+// The reference's inclusion predicate for one axis (gs.cu:40-43,47-50): fp32 subtraction,
+// skip iff d > dmax || d < -dmax (so NaN d is NOT skipped; we never get here with NaN centres).
+GSR_HD bool gsr_in_window(int i, int n, float ctr, float dmax) {
+  float d = gsr_pix_coord(i, n) - ctr;
+  return !(d > dmax || d < -dmax);
+}
+
+// Inclusive index range [lo,hi] of the pixels of an n-pixel axis that pass gsr_in_window.
+// The predicate is monotone in i, so the set is contiguous; we estimate both ends in double
+// and repair them with the exact predicate (the estimate is off by at most one pixel).
+// Empty range <=> lo > hi.
+GSR_HD void gsr_window_range(int n, float ctr, float dmax, int& lo, int& hi) {
+  if (dmax != dmax || dmax >= 3.0e38f) {  // NaN never skips; +inf never skips
+    lo = 0;
+    hi = n - 1;
+    return;
+  }
+  if (dmax < 0.0f) {  // every finite d fails one of the two comparisons
+    lo = 1;
+    hi = 0;
+    return;
+  }
+  const double s = 0.5 * (double)(n - 1);
+  double flo = ((double)ctr - (double)dmax + 1.0) * s;
+  double fhi = ((double)ctr + (double)dmax + 1.0) * s;
+  flo = fmin(fmax(flo, -2.0), (double)n + 1.0);
+  fhi = fmin(fmax(fhi, -2.0), (double)n + 1.0);
+  int l = (int)ceil(flo) - 1;
+  int h = (int)floor(fhi) + 1;
+  l = l < 0 ? 0 : (l > n ? n : l);
+  h = h > n - 1 ? n - 1 : (h < -1 ? -1 : h);
+  for (int t = 0; t < 4 && l < n && !gsr_in_window(l, n, ctr, dmax); ++t) ++l;
+  if (l < n && !gsr_in_window(l, n, ctr, dmax)) l = n;
+  for (int t = 0; t < 4 && h >= 0 && !gsr_in_window(h, n, ctr, dmax); ++t) --h;
+  if (h >= 0 && !gsr_in_window(h, n, ctr, dmax)) h = -1;
+  lo = l;
+  hi = h;
+}
+
+// ---- per-Gaussian set-up ------------------------------------------------------------------
+struct GsrSetup {
+  bool live;        // false: skipped entirely (invalid parameters or empty cull box)
+  bool large;       // cull box half-extent above GSR_LARGE_PX: goes to the global "large" list
+  bool binds;       // dmax window cuts the k-sigma box (exact predicate needed)
+  int x0, x1, y0, y1;   // cull box, inclusive, clipped to the image
+  int bin_x, bin_y;     // home bin (clamped into the image)
+  int ext_x, ext_y;     // ceil of the distance from the centre to the far box edge (pixels)
+};
+
+GSR_HD bool gsr_finite(float v) { return v == v && fabsf(v) < 3.0e38f; }
+
+// Cull box = exact dmax window  INTERSECT  [c - (k*sigma_px + pad), c + (k*sigma_px + pad)].
+GSR_HD GsrSetup gsr_setup(float sx, float sy, float rho, float x, float y, float cr, float cg,
+                          float cb, int h, int w, float dmax, float ksigma) {
+  GsrSetup o;
+  o.live = false;
+  o.large = false;
+  o.binds = false;
+  o.x0 = o.y0 = 1;
+  o.x1 = o.y1 = 0;
+  o.bin_x = o.bin_y = 0;
+  o.ext_x = o.ext_y = 0;
+  if (!(gsr_finite(sx) && gsr_finite(sy) && gsr_finite(rho) && gsr_finite(x) && gsr_finite(y) &&
+        gsr_finite(cr) && gsr_finite(cg) && gsr_finite(cb)))
+    return o;
+  if (sx == 0.0f || sy == 0.0f || !(fabsf(rho) < 1.0f)) return o;
+
+  int wx0, wx1, wy0, wy1;
+  gsr_window_range(w, x, dmax, wx0, wx1);
+  gsr_window_range(h, y, dmax, wy0, wy1);
+  if (wx0 > wx1 || wy0 > wy1) return o;
+
+  const double hx = 0.5 * (double)(w - 1), hy = 0.5 * (double)(h - 1);
+  const double cx = ((double)x + 1.0) * hx, cy = ((double)y + 1.0) * hy;
+  const double ex = (double)ksigma * fabs((double)sx) * hx + (double)GSR_CULL_PAD_PX;
+  const double ey = (double)ksigma * fabs((double)sy) * hy + (double)GSR_CULL_PAD_PX;
+  const double lim = 1.0e9;
+  int kx0 = (int)ceil(fmin(fmax(cx - ex, -lim), lim));
+  int kx1 = (int)floor(fmin(fmax(cx + ex, -lim), lim));
+  int ky0 = (int)ceil(fmin(fmax(cy - ey, -lim), lim));
+  int ky1 = (int)floor(fmin(fmax(cy + ey, -lim), lim));
+  // "binds": on some side the window is tighter than both the k-sigma box and the image edge.
+  o.binds = (wx0 > (kx0 > 0 ? kx0 : 0)) || (wx1 < (kx1 < w - 1 ? kx1 : w - 1)) ||
+            (wy0 > (ky0 > 0 ? ky0 : 0)) || (wy1 < (ky1 < h - 1 ? ky1 : h - 1));
+  o.x0 = wx0 > kx0 ? wx0 : kx0;
+  o.x1 = wx1 < kx1 ? wx1 : kx1;
+  o.y0 = wy0 > ky0 ? wy0 : ky0;
+  o.y1 = wy1 < ky1 ? wy1 : ky1;
+  if (o.x0 > o.x1 || o.y0 > o.y1) return o;
+  o.live = true;
+
+  double bx = floor(cx / GSR_BIN), by = floor(cy / GSR_BIN);
+  const int nbx = (w + GSR_BIN - 1) / GSR_BIN, nby = (h + GSR_BIN - 1) / GSR_BIN;
+  o.bin_x = (int)fmin(fmax(bx, 0.0), (double)(nbx - 1));
+  o.bin_y = (int)fmin(fmax(by, 0.0), (double)(nby - 1));
+  // Distance from the (clamped-into-image) centre to the far edges of the box: a tile that
+  // overlaps the box lies within this distance of the home bin along each axis.
+  const double ccx = fmin(fmax(cx, 0.0), (double)(w - 1)), ccy = fmin(fmax(cy, 0.0), (double)(h - 1));
+  double dxm = fmax(ccx - (double)o.x0, (double)o.x1 - ccx);
+  double dym = fmax(ccy - (double)o.y0, (double)o.y1 - ccy);
+  o.ext_x = (int)ceil(fmax(dxm, 0.0));
+  o.ext_y = (int)ceil(fmax(dym, 0.0));
+  o.large = (o.ext_x > GSR_LARGE_PX) || (o.ext_y > GSR_LARGE_PX);
+  return o;
+}
+
+// Conic in log2 units (double set-up, rounded once to float):
+//   E = log2(e) * w1 * (w2 dx^2 - 2 rho w3 dx dy + w4 dy^2),  w1 = -0.5/(1-rho^2), w2 = 1/sx^2 ...
+GSR_HD GsrRec gsr_make_rec(float sx, float sy, float rho, float x, float y, float cr, float cg,
+                           float cb) {
+  const double r = (double)rho;
+  const double w1 = -0.5 / (1.0 - r * r) * 1.4426950408889634;
+  const double isx = 1.0 / (double)sx, isy = 1.0 / (double)sy;
+  GsrRec o;
+  o.x = x;
+  o.y = y;
+  o.a = (float)(w1 * isx * isx);
+  o.b = (float)(-2.0 * r * w1 * isx * isy);
+  o.c = (float)(w1 * isy * isy);
+  o.r = cr;
+  o.g = cg;
+  o.bl = cb;
+  return o;
+}
+
+// ---- region mask ----------------------------------------------------------------------------
+// For a GSR_TILE x GSR_TILE tile at pixel origin (tx0,ty0), which of its (TILE/REGION)^2
+// warp regions does the ellipse {E >= ecut}, clipped to the cull box, touch?  Bit
+// (ry*(TILE/REGION) + rx).  Conservative (never misses a pixel with E >= ecut inside the
+// box); pixels it drops carry exp2(E) < exp2(ecut).
+//
+// Per band of REGION rows: the ellipse's x-interval at row dy is centred on m(dy) = -b/(2a)*dy
+// with half-width sqrt((ecut - c' dy^2)/a), c' = c - b^2/(4a); over a band we take the hull of
+// the two end-row centres widened by the largest half-width in the band.
+GSR_HD uint32_t gsr_region_mask(const GsrRec& g, int bx0, int bx1, int by0, int by1, int tx0,
+                                int ty0, int h, int w, float ecut) {
+  constexpr int NR = GSR_TILE / GSR_REGION;
+  const float hxs = 0.5f * (float)(w - 1), hys = 0.5f * (float)(h - 1);
+  const float gx = 1.0f / hxs, gy = 1.0f / hys;  // normalised units per pixel
+  const float cx = (g.x + 1.0f) * hxs, cy = (g.y + 1.0f) * hys;
+  // conic in pixel units
+  const float a = g.a * gx * gx, b = g.b * gx * gy, c = g.c * gy * gy;
+  const float inv_a = 1.0f / a;                 // a < 0
+  const float kappa = -0.5f * b * inv_a;        // ridge slope dx/dy
+  const float cp = c + 0.5f * kappa * b;        // c - b^2/(4a)  (<= 0)
+  uint32_t mask = 0;
+  const int cx0 = bx0 > tx0 ? bx0 : tx0;
+  const int cx1 = bx1 < tx0 + GSR_TILE - 1 ? bx1 : tx0 + GSR_TILE - 1;
+  if (cx0 > cx1) return 0;
+#pragma unroll
+  for (int ry = 0; ry < NR; ++ry) {
+    int ya = ty0 + ry * GSR_REGION, yb = ya + GSR_REGION - 1;
+    ya = ya > by0 ? ya : by0;
+    yb = yb < by1 ? yb : by1;
+    if (ya > yb) continue;
+    const float da = (float)ya - cy, db = (float)yb - cy;
+    // row offset in the band closest to the centre row
+    float t = da > 0.0f ? da : (db < 0.0f ? db : 0.0f);
+    // shrink |t| by the pad so rounding of cy can only widen the band
+    t = t > 0.0f ? fmaxf(t - GSR_CULL_PAD_PX, 0.0f) : fminf(t + GSR_CULL_PAD_PX, 0.0f);
+    float w2 = (ecut - cp * t * t) * inv_a;
+    if (!(w2 >= 0.0f)) {
+      if (w2 < 0.0f) continue;   // band entirely outside the ellipse
+      w2 = 3.0e38f;              // NaN/inf from a degenerate conic: do not cull
+    }
+    const float hw = sqrtf(w2) + GSR_CULL_PAD_PX + 1.0e-6f * fabsf(cx);  // fp32 slack on cx
+    const float ma = cx + kappa * da, mb = cx + kappa * db;
+    float lo = fminf(ma, mb) - hw, hi = fmaxf(ma, mb) + hw;
+    if (!(lo == lo) || !(hi == hi)) {
+      lo = -3.0e38f;
+      hi = 3.0e38f;
+    }
+    lo = fmaxf(lo, (float)cx0);
+    hi = fminf(hi, (float)cx1);
+    int xl = (int)ceilf(lo), xh = (int)floorf(hi);
+    if (xl > xh) continue;
+    int r0 = (xl - tx0) / GSR_REGION, r1 = (xh - tx0) / GSR_REGION;
+    uint32_t bits = ((2u << r1) - 1u) & ~((1u << r0) - 1u);
+    mask |= bits << (ry * NR);
+  }
+  return mask;
+}
+
+// Default and exact k-sigma handling shared by host API and kernels.
+GSR_HD float gsr_effective_ksigma(float ksigma) {
+  if (!(ksigma == ksigma) || ksigma <= 0.0f) return 5.0f;       // GSR_DEFAULT_KSIGMA
+  if (ksigma > 13.25f) return 13.25f;                            // GSR_EXACT_KSIGMA
+  return ksigma;
+}
+GSR_HD float gsr_ecut(float ksigma_eff) { return -0.5f * ksigma_eff * ksigma_eff * GSR_LOG2E; }

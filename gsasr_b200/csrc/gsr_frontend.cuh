@@ -1,0 +1,76 @@
+// gsr_frontend.cuh -- fused front end of the render path: raw head output -> raster inputs.
+//
+// Restates utils/gaussian_splatting.py:174-180 (activations) and :121-123 (unit / coordinate
+// mapping of rendering_cuda_dmax) as one elementwise kernel, and its chain rule as another.
+// The arithmetic follows what PyTorch executes on the INFERENCE path (inference_paper.py:113-131:
+// sr_size and scale_modify are CPU tensors, so CUDA tensor / CPU-scalar divisions run as a
+// multiplication by the fp32 reciprocal); every operation is individually rounded (no FMA
+// contraction) so the mapped parameters agree with the unfused path to the last bit or one ulp.
+#pragma once
+#include "gsr_common.cuh"
+
+__device__ __forceinline__ float gsr_sigmoid(float x) {
+  return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+}
+
+// raw (s,9) = (sx, sy, rho, alpha, r, g, b, mu_x, mu_y)
+//   sigmas (s,3) = (sy/step*2/(w-1), sx/step*2/(h-1), rho)      NOTE the x/y swap (:121)
+//   coords (s,2) = ((mu*2-1) + 1 - 1/n) * n / (n-1) - 1          (:122-123)
+//   colors (s,3) = sigmoid(rgb) * sigmoid(alpha)                 (:177-180)
+__global__ void __launch_bounds__(256)
+gsr_map_kernel(const float* __restrict__ raw, float* __restrict__ sigmas,
+               float* __restrict__ coords, float* __restrict__ colors, int s, int h, int w,
+               float step) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s) return;
+  const float* p = raw + 9 * (size_t)i;
+  const float inv_step = __fdiv_rn(1.0f, step);
+  const float inv_w1 = __fdiv_rn(1.0f, (float)(w - 1)), inv_h1 = __fdiv_rn(1.0f, (float)(h - 1));
+  const float inv_w = __fdiv_rn(1.0f, (float)w), inv_h = __fdiv_rn(1.0f, (float)h);
+  const float sgx = __fadd_rn(__fmul_rn(0.99999f, gsr_sigmoid(__ldg(p + 0))), 1e-6f);
+  const float sgy = __fadd_rn(__fmul_rn(0.99999f, gsr_sigmoid(__ldg(p + 1))), 1e-6f);
+  const float rho = __fmul_rn(0.999999f, tanhf(__ldg(p + 2)));
+  const float alpha = gsr_sigmoid(__ldg(p + 3));
+  sigmas[3 * (size_t)i + 0] = __fmul_rn(__fmul_rn(__fmul_rn(sgy, inv_step), 2.0f), inv_w1);
+  sigmas[3 * (size_t)i + 1] = __fmul_rn(__fmul_rn(__fmul_rn(sgx, inv_step), 2.0f), inv_h1);
+  sigmas[3 * (size_t)i + 2] = rho;
+  const float mx = __fsub_rn(__fmul_rn(__ldg(p + 7), 2.0f), 1.0f);
+  const float my = __fsub_rn(__fmul_rn(__ldg(p + 8), 2.0f), 1.0f);
+  coords[2 * (size_t)i + 0] = __fsub_rn(
+      __fmul_rn(__fmul_rn(__fsub_rn(__fadd_rn(mx, 1.0f), inv_w), (float)w), inv_w1), 1.0f);
+  coords[2 * (size_t)i + 1] = __fsub_rn(
+      __fmul_rn(__fmul_rn(__fsub_rn(__fadd_rn(my, 1.0f), inv_h), (float)h), inv_h1), 1.0f);
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    colors[3 * (size_t)i + c] = __fmul_rn(gsr_sigmoid(__ldg(p + 4 + c)), alpha);
+}
+
+// Chain rule of gsr_map_kernel: (d/dsigmas, d/dcoords, d/dcolors) -> d/draw (s,9), written.
+__global__ void __launch_bounds__(256)
+gsr_unmap_kernel(const float* __restrict__ raw, const float* __restrict__ g_sigmas,
+                 const float* __restrict__ g_coords, const float* __restrict__ g_colors,
+                 float* __restrict__ g_raw, int s, int h, int w, float step) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s) return;
+  const float* p = raw + 9 * (size_t)i;
+  float* o = g_raw + 9 * (size_t)i;
+  const float kx = 2.0f / (step * (float)(w - 1)), ky = 2.0f / (step * (float)(h - 1));
+  const float s0 = gsr_sigmoid(__ldg(p + 0)), s1 = gsr_sigmoid(__ldg(p + 1));
+  const float th = tanhf(__ldg(p + 2));
+  const float al = gsr_sigmoid(__ldg(p + 3));
+  // sigmas[.,0] = sigma_y * kx (from raw column 1); sigmas[.,1] = sigma_x * ky (raw column 0)
+  o[0] = g_sigmas[3 * (size_t)i + 1] * ky * 0.99999f * s0 * (1.0f - s0);
+  o[1] = g_sigmas[3 * (size_t)i + 0] * kx * 0.99999f * s1 * (1.0f - s1);
+  o[2] = g_sigmas[3 * (size_t)i + 2] * 0.999999f * (1.0f - th * th);
+  float ga = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float sc = gsr_sigmoid(__ldg(p + 4 + c));
+    const float gc = g_colors[3 * (size_t)i + c];
+    o[4 + c] = gc * al * sc * (1.0f - sc);
+    ga = fmaf(gc, sc, ga);
+  }
+  o[3] = ga * al * (1.0f - al);
+  o[7] = g_coords[2 * (size_t)i + 0] * 2.0f * (float)w / (float)(w - 1);
+  o[8] = g_coords[2 * (size_t)i + 1] * 2.0f * (float)h / (float)(h - 1);
+}

@@ -1,0 +1,296 @@
+// gsraster.cu -- the C ABI of libgsraster.so (see include/gsraster.h for the contract and the
+// reference interfaces each entry point replaces).  One translation unit: set-up pipeline,
+// forward and backward raster kernels, fused front end, and CPU test hooks.
+#include "../../include/gsraster.h"
+#include "gsr_backward.cuh"
+#include "gsr_frontend.cuh"
+
+static thread_local int g_last_cuda_error = 0;
+
+#define GSR_CUDA(call)                                  \
+  do {                                                  \
+    cudaError_t e__ = (call);                           \
+    if (e__ != cudaSuccess) {                           \
+      g_last_cuda_error = (int)e__;                     \
+      (void)cudaGetLastError();                         \
+      return GSR_ERR_CUDA;                              \
+    }                                                   \
+  } while (0)
+
+extern "C" int gsr_version(void) { return GSR_VERSION; }
+
+extern "C" const char* gsr_status_string(int status) {
+  switch (status) {
+    case GSR_OK: return "ok";
+    case GSR_ERR_NULL_POINTER: return "null pointer argument";
+    case GSR_ERR_BAD_SHAPE: return "bad shape: need s >= 0 and 2 <= h, w <= 32767";
+    case GSR_ERR_BAD_CHANNELS: return "bad channel count: the rasteriser supports c == 3 only";
+    case GSR_ERR_WORKSPACE: return "workspace missing, misaligned (256 B) or too small";
+    case GSR_ERR_BAD_ARGUMENT: return "bad argument";
+    case GSR_ERR_CUDA: return "CUDA runtime error (see gsr_last_cuda_error)";
+    default: return "unknown status";
+  }
+}
+
+extern "C" int gsr_last_cuda_error(void) { return g_last_cuda_error; }
+
+static bool gsr_dims_ok(int s, int h, int w) {
+  return s >= 0 && h >= 2 && w >= 2 && h <= GSR_MAX_DIM && w <= GSR_MAX_DIM;
+}
+
+extern "C" size_t gsr_workspace_bytes(int s, int h, int w) {
+  if (!gsr_dims_ok(s, h, w)) return 0;
+  return gsr_carve(nullptr, s, h, w).bytes;
+}
+
+static int gsr_check_ws(void* workspace, size_t bytes, size_t need) {
+  if (!workspace || ((uintptr_t)workspace & 255u) || bytes < need) return GSR_ERR_WORKSPACE;
+  return GSR_OK;
+}
+
+// K1..K3.  Leaves the sorted arrays in ws.
+static int gsr_run_prepass(const float* sigmas, const float* coords, const float* colors, int s,
+                           int h, int w, float dmax, float keff, const GsrWorkspace& ws,
+                           cudaStream_t st) {
+  GSR_CUDA(cudaMemsetAsync(ws.bin_count, 0, ((size_t)ws.nb + 1 + 8) * sizeof(int), st));
+  int n = s > w ? s : w;
+  n = n > h ? n : h;
+  gsr_bin_kernel<<<(n + 255) / 256, 256, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff, ws);
+  gsr_scan_kernel<<<1, 1024, 0, st>>>(ws.bin_count, ws.bin_off, ws.nb + 1);
+  if (s > 0) gsr_scatter_kernel<<<(s + 255) / 256, 256, 0, st>>>(sigmas, coords, colors, s, ws);
+  GSR_CUDA(cudaGetLastError());
+  return GSR_OK;
+}
+
+static int gsr_launch_forward(const GsrWorkspace& ws, float* img, int h, int w, float keff,
+                              uint32_t flags, cudaStream_t st) {
+  GsrFwdArgs a;
+  a.rec = ws.rec;
+  a.box = ws.box;
+  a.bin_off = ws.bin_off;
+  a.stats = ws.stats;
+  a.px_tab = ws.px_tab;
+  a.py_tab = ws.py_tab;
+  a.img = img;
+  a.h = h;
+  a.w = w;
+  a.nbx = ws.nbx;
+  a.nby = ws.nby;
+  a.nb = ws.nb;
+  a.ecut = gsr_ecut(keff);
+  a.flags = flags;
+  GSR_CUDA(cudaFuncSetAttribute(gsr_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(GsrFwdSmem)));
+  dim3 grid((w + GSR_TILE - 1) / GSR_TILE, (h + GSR_TILE - 1) / GSR_TILE);
+  gsr_forward_kernel<<<grid, GSR_FWD_THREADS, sizeof(GsrFwdSmem), st>>>(a);
+  GSR_CUDA(cudaGetLastError());
+  return GSR_OK;
+}
+
+static int gsr_launch_backward(const GsrWorkspace& ws, const float* sigmas, const float* grads,
+                               float* gs, float* gc, float* gk, int s, int h, int w,
+                               uint32_t flags, cudaStream_t st) {
+  if (s == 0) return GSR_OK;
+  GsrBwdArgs a;
+  a.rec = ws.rec;
+  a.box = ws.box;
+  a.ids = ws.ids;
+  a.bin_off = ws.bin_off;
+  a.px_tab = ws.px_tab;
+  a.py_tab = ws.py_tab;
+  a.grads = grads;
+  a.sigmas = sigmas;
+  a.g_sigmas = gs;
+  a.g_coords = gc;
+  a.g_colors = gk;
+  a.h = h;
+  a.w = w;
+  a.nb = ws.nb;
+  a.flags = flags;
+  gsr_backward_kernel<<<(s + GSR_BWD_WARPS - 1) / GSR_BWD_WARPS, GSR_BWD_THREADS, 0, st>>>(a);
+  GSR_CUDA(cudaGetLastError());
+  return GSR_OK;
+}
+
+extern "C" int gsr_forward(const float* sigmas, const float* coords, const float* colors,
+                           float* img, int s, int h, int w, int c, float dmax, float ksigma,
+                           uint32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
+  if (c != 3) return GSR_ERR_BAD_CHANNELS;
+  if (!gsr_dims_ok(s, h, w)) return GSR_ERR_BAD_SHAPE;
+  if (!img || (s > 0 && (!sigmas || !coords || !colors))) return GSR_ERR_NULL_POINTER;
+  const GsrWorkspace ws = gsr_carve(workspace, s, h, w);
+  int rc = gsr_check_ws(workspace, workspace_bytes, ws.bytes);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float keff = gsr_effective_ksigma(ksigma);
+  rc = gsr_run_prepass(sigmas, coords, colors, s, h, w, dmax, keff, ws, st);
+  if (rc) return rc;
+  return gsr_launch_forward(ws, img, h, w, keff, flags, st);
+}
+
+extern "C" int gsr_backward(const float* sigmas, const float* coords, const float* colors,
+                            const float* grads, float* grads_sigmas, float* grads_coords,
+                            float* grads_colors, int s, int h, int w, int c, float dmax,
+                            float ksigma, uint32_t flags, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  if (c != 3) return GSR_ERR_BAD_CHANNELS;
+  if (!gsr_dims_ok(s, h, w)) return GSR_ERR_BAD_SHAPE;
+  if (!grads || (s > 0 && (!sigmas || !coords || !colors || !grads_sigmas || !grads_coords ||
+                           !grads_colors)))
+    return GSR_ERR_NULL_POINTER;
+  const GsrWorkspace ws = gsr_carve(workspace, s, h, w);
+  int rc = gsr_check_ws(workspace, workspace_bytes, ws.bytes);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const float keff = gsr_effective_ksigma(ksigma);
+  rc = gsr_run_prepass(sigmas, coords, colors, s, h, w, dmax, keff, ws, st);
+  if (rc) return rc;
+  return gsr_launch_backward(ws, sigmas, grads, grads_sigmas, grads_coords, grads_colors, s, h, w,
+                             flags, st);
+}
+
+// ---- ragged batches -------------------------------------------------------------------------
+extern "C" size_t gsr_workspace_bytes_batch(const gsr_sample* samples, int n) {
+  if (!samples || n < 0) return 0;
+  size_t total = 0;
+  for (int i = 0; i < n; ++i) {
+    const size_t b = gsr_workspace_bytes(samples[i].s, samples[i].h, samples[i].w);
+    if (b == 0) return 0;
+    total += b;
+  }
+  return total;
+}
+
+extern "C" int gsr_forward_batch(const gsr_sample* samples, int n, float ksigma, uint32_t flags,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (n < 0) return GSR_ERR_BAD_ARGUMENT;
+  if (n > 0 && !samples) return GSR_ERR_NULL_POINTER;
+  const size_t need = gsr_workspace_bytes_batch(samples, n);
+  if (n > 0 && need == 0) return GSR_ERR_BAD_SHAPE;
+  int rc = n > 0 ? gsr_check_ws(workspace, workspace_bytes, need) : GSR_OK;
+  if (rc) return rc;
+  char* base = (char*)workspace;
+  for (int i = 0; i < n; ++i) {
+    const gsr_sample& sm = samples[i];
+    const size_t b = gsr_workspace_bytes(sm.s, sm.h, sm.w);
+    rc = gsr_forward(sm.sigmas, sm.coords, sm.colors, sm.img, sm.s, sm.h, sm.w, 3, sm.dmax, ksigma,
+                     flags, base, b, stream);
+    if (rc) return rc;
+    base += b;
+  }
+  return GSR_OK;
+}
+
+extern "C" int gsr_backward_batch(const gsr_sample* samples, int n, float ksigma, uint32_t flags,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  if (n < 0) return GSR_ERR_BAD_ARGUMENT;
+  if (n > 0 && !samples) return GSR_ERR_NULL_POINTER;
+  const size_t need = gsr_workspace_bytes_batch(samples, n);
+  if (n > 0 && need == 0) return GSR_ERR_BAD_SHAPE;
+  int rc = n > 0 ? gsr_check_ws(workspace, workspace_bytes, need) : GSR_OK;
+  if (rc) return rc;
+  char* base = (char*)workspace;
+  for (int i = 0; i < n; ++i) {
+    const gsr_sample& sm = samples[i];
+    const size_t b = gsr_workspace_bytes(sm.s, sm.h, sm.w);
+    rc = gsr_backward(sm.sigmas, sm.coords, sm.colors, sm.grads, sm.grads_sigmas, sm.grads_coords,
+                      sm.grads_colors, sm.s, sm.h, sm.w, 3, sm.dmax, ksigma, flags, base, b, stream);
+    if (rc) return rc;
+    base += b;
+  }
+  return GSR_OK;
+}
+
+// ---- fused front end --------------------------------------------------------------------------
+extern "C" int gsr_frontend_forward(const float* raw, float* mapped, float* img_chw, int s, int h,
+                                    int w, float step_size, float dmax, float ksigma,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  if (!gsr_dims_ok(s, h, w)) return GSR_ERR_BAD_SHAPE;
+  if (!img_chw || (s > 0 && (!raw || !mapped))) return GSR_ERR_NULL_POINTER;
+  if (!(step_size > 0.0f)) return GSR_ERR_BAD_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s > 0) {
+    gsr_map_kernel<<<(s + 255) / 256, 256, 0, st>>>(raw, mapped, mapped + 3 * (size_t)s,
+                                                    mapped + 5 * (size_t)s, s, h, w, step_size);
+    GSR_CUDA(cudaGetLastError());
+  }
+  return gsr_forward(mapped, mapped + 3 * (size_t)s, mapped + 5 * (size_t)s, img_chw, s, h, w, 3,
+                     dmax, ksigma, GSR_FLAG_OVERWRITE | GSR_FLAG_CHW, workspace, workspace_bytes,
+                     stream);
+}
+
+extern "C" int gsr_frontend_backward(const float* raw, const float* mapped, const float* grads_chw,
+                                     float* grad_raw, int s, int h, int w, float step_size,
+                                     float dmax, float ksigma, void* workspace,
+                                     size_t workspace_bytes, void* stream) {
+  if (!gsr_dims_ok(s, h, w)) return GSR_ERR_BAD_SHAPE;
+  if (!grads_chw || (s > 0 && (!raw || !mapped || !grad_raw))) return GSR_ERR_NULL_POINTER;
+  if (!(step_size > 0.0f)) return GSR_ERR_BAD_ARGUMENT;
+  if (s == 0) return GSR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  // grad_raw doubles as the accumulation buffer for the mapped-parameter gradients:
+  // [0,3s) d/dsigmas, [3s,5s) d/dcoords, [5s,8s) d/dcolors, then rewritten in place per row.
+  // The (s,9) output has 9s floats, the mapped gradients need 8s: they are staged at the END
+  // of the workspace instead, so the chain-rule kernel can write grad_raw freely.
+  const size_t need = gsr_workspace_bytes(s, h, w);
+  const size_t stage = gsr_align_up((size_t)s * 8 * sizeof(float), 256);
+  if (!workspace || ((uintptr_t)workspace & 255u) || workspace_bytes < need + stage)
+    return GSR_ERR_WORKSPACE;
+  float* gm = (float*)((char*)workspace + need);
+  GSR_CUDA(cudaMemsetAsync(gm, 0, (size_t)s * 8 * sizeof(float), st));
+  int rc = gsr_backward(mapped, mapped + 3 * (size_t)s, mapped + 5 * (size_t)s, grads_chw, gm,
+                        gm + 3 * (size_t)s, gm + 5 * (size_t)s, s, h, w, 3, dmax, ksigma,
+                        GSR_FLAG_CHW, workspace, need, stream);
+  if (rc) return rc;
+  gsr_unmap_kernel<<<(s + 255) / 256, 256, 0, st>>>(raw, gm, gm + 3 * (size_t)s, gm + 5 * (size_t)s,
+                                                    grad_raw, s, h, w, step_size);
+  GSR_CUDA(cudaGetLastError());
+  return GSR_OK;
+}
+
+// ---- CPU test hooks (no GPU needed): run the shared host/device culling code on the host ----
+extern "C" void gsr_host_setup(const float* sigmas, const float* coords, const float* colors,
+                               int s, int h, int w, float dmax, float ksigma, int* out /* s x 9 */) {
+  const float keff = gsr_effective_ksigma(ksigma);
+  for (int i = 0; i < s; ++i) {
+    GsrSetup st = gsr_setup(sigmas[3 * i], sigmas[3 * i + 1], sigmas[3 * i + 2], coords[2 * i],
+                            coords[2 * i + 1], colors[3 * i], colors[3 * i + 1], colors[3 * i + 2],
+                            h, w, dmax, keff);
+    int* o = out + 9 * (size_t)i;
+    o[0] = st.live;
+    o[1] = st.x0;
+    o[2] = st.x1;
+    o[3] = st.y0;
+    o[4] = st.y1;
+    o[5] = st.binds;
+    o[6] = st.large;
+    o[7] = st.bin_y * ((w + GSR_BIN - 1) / GSR_BIN) + st.bin_x;
+    o[8] = st.ext_x > st.ext_y ? st.ext_x : st.ext_y;
+  }
+}
+
+extern "C" void gsr_host_window_range(int n, float ctr, float dmax, int* lo, int* hi) {
+  gsr_window_range(n, ctr, dmax, *lo, *hi);
+}
+
+// Region mask of Gaussian i for the tile at (tx0, ty0); 0 if the Gaussian is not live.
+extern "C" unsigned gsr_host_region_mask(const float* sigmas, const float* coords,
+                                         const float* colors, int i, int h, int w, float dmax,
+                                         float ksigma, int tx0, int ty0) {
+  const float keff = gsr_effective_ksigma(ksigma);
+  GsrSetup st = gsr_setup(sigmas[3 * i], sigmas[3 * i + 1], sigmas[3 * i + 2], coords[2 * i],
+                          coords[2 * i + 1], colors[3 * i], colors[3 * i + 1], colors[3 * i + 2], h,
+                          w, dmax, keff);
+  if (!st.live) return 0;
+  if (st.x1 < tx0 || st.x0 >= tx0 + GSR_TILE || st.y1 < ty0 || st.y0 >= ty0 + GSR_TILE) return 0;
+  GsrRec r = gsr_make_rec(sigmas[3 * i], sigmas[3 * i + 1], sigmas[3 * i + 2], coords[2 * i],
+                          coords[2 * i + 1], colors[3 * i], colors[3 * i + 1], colors[3 * i + 2]);
+  return gsr_region_mask(r, st.x0, st.x1, st.y0, st.y1, tx0, ty0, h, w, gsr_ecut(keff));
+}
+
+extern "C" void gsr_host_geometry(int* tile, int* bin, int* region, int* large_px) {
+  *tile = GSR_TILE;
+  *bin = GSR_BIN;
+  *region = GSR_REGION;
+  *large_px = GSR_LARGE_PX;
+}

@@ -1,0 +1,242 @@
+"""Mirror of the render front end, utils/gaussian_splatting.py (GSASR): same function names,
+same arguments, same (3, H, W) float32 result.
+
+    generate_2D_gaussian_splatting_step(sr_size, gs_parameters, scale, scale_modify, ...)   :158-217
+    generate_2D_gaussian_splatting_step_buffer(..., buffer_size=4000000)                    :219-265
+    rendering_cuda_dmax / rendering_cuda / *_buffer                                          :86-155
+
+The activations (:174-180) and the unit / coordinate mapping (:121-123) are executed with the
+very same torch expressions as the reference, so the tensors handed to the rasteriser are
+bit-identical to the reference's.  What changes is below that line: the B200 kernels write the
+(3,H,W) image directly (no zero-fill, no permute().contiguous() pass), and the `_buffer`
+variants differentiate correctly (the reference drops the gradient of all but the last chunk,
+gswrapper.py:44).  ``fused=True`` additionally replaces the ~15 elementwise torch kernels by the
+library's fused front end (gsr_frontend_forward / _backward; parity 1e-4, not bitwise).
+
+``cuda_rendering=False`` selected the reference's PyTorch resampling renderer (rendering_python,
+:11-84), a different algorithm that is not part of this library: it raises here.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from . import gscuda as _gs
+
+__all__ = [
+    "generate_2D_gaussian_splatting_step", "generate_2D_gaussian_splatting_step_buffer",
+    "rendering_cuda", "rendering_cuda_buffer", "rendering_cuda_dmax", "rendering_cuda_dmax_buffer",
+    "map_gaussians", "render_chw",
+]
+
+_CHW = _lib.GSR_FLAG_CHW
+_OVER = _lib.GSR_FLAG_OVERWRITE
+
+
+class _RenderCHW(Function):
+    """(sigmas, coords, colors) -> (3,H,W); Gaussians optionally processed in chunks of buffer_size."""
+
+    @staticmethod
+    def forward(ctx, sigmas, coords, colors, h, w, dmax, buffer_size):
+        sigmas, coords, colors = sigmas.contiguous(), coords.contiguous(), colors.contiguous()
+        ctx.save_for_backward(sigmas, coords, colors)
+        ctx.meta = (int(h), int(w), float(dmax), buffer_size)
+        h, w = int(h), int(w)
+        out = torch.empty(3, h, w, device=sigmas.device, dtype=torch.float32)
+        n = sigmas.shape[0]
+        step = n if not buffer_size else int(buffer_size)
+        first = True
+        for a in range(0, max(n, 1), max(step, 1)):
+            b = min(a + step, n)
+            _gs.gs_render(sigmas[a:b], coords[a:b], colors[a:b], out, b - a, h, w, 3, dmax,
+                          flags=_CHW | (_OVER if first else 0))
+            first = False
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad):
+        sigmas, coords, colors = ctx.saved_tensors
+        h, w, dmax, buffer_size = ctx.meta
+        grad = grad.contiguous()
+        gs, gc, gk = torch.zeros_like(sigmas), torch.zeros_like(coords), torch.zeros_like(colors)
+        n = sigmas.shape[0]
+        step = n if not buffer_size else int(buffer_size)
+        for a in range(0, n, max(step, 1)):
+            b = min(a + step, n)
+            _gs.gs_render_backward(sigmas[a:b], coords[a:b], colors[a:b], grad, gs[a:b], gc[a:b],
+                                   gk[a:b], b - a, h, w, 3, dmax, flags=_CHW)
+        return gs, gc, gk, None, None, None, None
+
+
+def render_chw(sigmas, coords, colors, h, w, dmax=float("inf"), buffer_size=None):
+    """Differentiable render straight into a (3,h,w) image."""
+    return _RenderCHW.apply(sigmas, coords, colors, h, w, dmax, buffer_size)
+
+
+def map_gaussians(sigma_x, sigma_y, rho, coords, sr_size, step_size):
+    """Unit / coordinate mapping of rendering_cuda_dmax (:121-123), same expressions.
+    NOTE the x/y swap: the head's sigma_x is the vertical std.  ``coords`` is modified in place,
+    as in the reference."""
+    sigmas = torch.cat([sigma_y / step_size * 2 / (sr_size[1] - 1),
+                        sigma_x / step_size * 2 / (sr_size[0] - 1), rho], dim=-1).contiguous()
+    coords[:, 0] = (coords[:, 0] + 1 - 1 / sr_size[1]) * sr_size[1] / (sr_size[1] - 1) - 1.0
+    coords[:, 1] = (coords[:, 1] + 1 - 1 / sr_size[0]) * sr_size[0] / (sr_size[0] - 1) - 1.0
+    return sigmas, coords
+
+
+def rendering_cuda_dmax(sigma_x, sigma_y, rho, coords, colours_with_alpha, sr_size, step_size, device,
+                        dmax=1):
+    sigmas, coords = map_gaussians(sigma_x, sigma_y, rho, coords, sr_size, step_size)
+    return render_chw(sigmas, coords, colours_with_alpha, int(sr_size[0]), int(sr_size[1]), dmax)
+
+
+def rendering_cuda(sigma_x, sigma_y, rho, coords, colours_with_alpha, sr_size, step_size, device):
+    sigmas, coords = map_gaussians(sigma_x, sigma_y, rho, coords, sr_size, step_size)
+    return render_chw(sigmas, coords, colours_with_alpha, int(sr_size[0]), int(sr_size[1]))
+
+
+def rendering_cuda_dmax_buffer(sigma_x, sigma_y, rho, coords, colours_with_alpha, sr_size, step_size,
+                               device, dmax=1, buffer_size=1000000):
+    sigmas, coords = map_gaussians(sigma_x, sigma_y, rho, coords, sr_size, step_size)
+    return render_chw(sigmas, coords, colours_with_alpha, int(sr_size[0]), int(sr_size[1]), dmax,
+                      buffer_size)
+
+
+def rendering_cuda_buffer(sigma_x, sigma_y, rho, coords, colours_with_alpha, sr_size, step_size, device,
+                          buffer_size=1000000):
+    sigmas, coords = map_gaussians(sigma_x, sigma_y, rho, coords, sr_size, step_size)
+    return render_chw(sigmas, coords, colours_with_alpha, int(sr_size[0]), int(sr_size[1]),
+                      float("inf"), buffer_size)
+
+
+class _FusedFrontend(Function):
+    """raw (N,9) -> (3,H,W) through gsr_frontend_forward / gsr_frontend_backward."""
+
+    @staticmethod
+    def forward(ctx, raw, h, w, step_size, dmax):
+        L = _lib.load()
+        raw = raw.contiguous().float()
+        n = raw.shape[0]
+        mapped = torch.empty(max(n, 1) * 8, device=raw.device, dtype=torch.float32)
+        out = torch.empty(3, h, w, device=raw.device, dtype=torch.float32)
+        with torch.cuda.device(raw.device):
+            ws = _gs.workspace(n, h, w, raw.device)
+            rc = L.gsr_frontend_forward(raw.data_ptr(), mapped.data_ptr(), out.data_ptr(), n, h, w,
+                                        float(step_size), float(dmax), float(_gs.get_ksigma()),
+                                        ws.data_ptr(), ws.numel(),
+                                        torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc)
+        ctx.save_for_backward(raw, mapped)
+        ctx.meta = (h, w, float(step_size), float(dmax))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad):
+        L = _lib.load()
+        raw, mapped = ctx.saved_tensors
+        h, w, step_size, dmax = ctx.meta
+        n = raw.shape[0]
+        grad = grad.contiguous()
+        g_raw = torch.zeros_like(raw)
+        if n:
+            with torch.cuda.device(raw.device):
+                need = L.gsr_workspace_bytes(n, h, w) + (n * 32 + 255) // 256 * 256
+                ws = torch.empty(need, dtype=torch.uint8, device=raw.device)
+                rc = L.gsr_frontend_backward(raw.data_ptr(), mapped.data_ptr(), grad.data_ptr(),
+                                             g_raw.data_ptr(), n, h, w, step_size, dmax,
+                                             float(_gs.get_ksigma()), ws.data_ptr(), ws.numel(),
+                                             torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc)
+        return g_raw, None, None, None, None
+
+
+def _prepare(gs_parameters, scale, scale_modify, default_step_size, mode):
+    # set step_size according to scale factor (:164-171)
+    if mode == 'scale':
+        final_scale = scale
+    elif mode == 'scale_modify':
+        assert scale_modify[0] == scale_modify[1], f"scale_modify is not the same-{scale_modify}"
+        final_scale = scale_modify[0]
+    else:
+        raise ValueError(f"mode-{mode} must be scale or scale_modify")
+    step_size = default_step_size / final_scale
+    # prepare gaussian properties (:174-180)
+    sigma_x = 0.99999 * torch.sigmoid(gs_parameters[:, 0:1]) + 1e-6
+    sigma_y = 0.99999 * torch.sigmoid(gs_parameters[:, 1:2]) + 1e-6
+    rho = 0.999999 * torch.tanh(gs_parameters[:, 2:3])
+    alpha = torch.sigmoid(gs_parameters[:, 3:4])
+    colours = torch.sigmoid(gs_parameters[:, 4:7])
+    coords = (gs_parameters[:, 7:9] * 2 - 1)
+    colours_with_alpha = colours * alpha
+    return step_size, sigma_x, sigma_y, rho, coords, colours_with_alpha
+
+
+def _resolve_dmax(if_dmax, dmax_mode, dmax, sr_size):
+    if not if_dmax:
+        return float("inf")
+    if dmax_mode == 'dynamic':  # (:203-204)
+        return float((dmax + 2) / min(sr_size[0], sr_size[1]))
+    if dmax_mode == 'fix':
+        return float(dmax)
+    raise ValueError(f"dmax_mode-{dmax_mode} must be fix or dynamic")
+
+
+def _no_python_renderer():
+    raise NotImplementedError(
+        "cuda_rendering=False selects the reference's PyTorch resampling renderer "
+        "(utils/gaussian_splatting.py:11-84), which this library does not provide; "
+        "the B200 rasteriser has no CPU path")
+
+
+def _sample(final_image, sample_coords):
+    if sample_coords is not None:  # (:214-216)
+        sample_RGB_values = [final_image[:, coord[0], coord[1]] for coord in sample_coords]
+        final_image = torch.stack(sample_RGB_values, dim=1)
+    return final_image
+
+
+def generate_2D_gaussian_splatting_step(sr_size, gs_parameters, scale, scale_modify,
+                                        sample_coords=None, default_step_size=1.2,
+                                        cuda_rendering=True, mode='scale_modify',
+                                        if_dmax=True, dmax_mode='fix', dmax=25, fused=False):
+    if not cuda_rendering:
+        _no_python_renderer()
+    if fused:
+        step_size = float(default_step_size / (scale if mode == 'scale' else scale_modify[0]))
+        final_image = _FusedFrontend.apply(gs_parameters, int(sr_size[0]), int(sr_size[1]), step_size,
+                                           _resolve_dmax(if_dmax, dmax_mode, dmax, sr_size))
+        return _sample(final_image, sample_coords)
+    step_size, sigma_x, sigma_y, rho, coords, colours_with_alpha = _prepare(
+        gs_parameters, scale, scale_modify, default_step_size, mode)
+    if if_dmax:
+        final_image = rendering_cuda_dmax(sigma_x, sigma_y, rho, coords, colours_with_alpha, sr_size,
+                                          step_size, dmax=_resolve_dmax(True, dmax_mode, dmax, sr_size),
+                                          device=sigma_x.device)
+    else:
+        final_image = rendering_cuda(sigma_x, sigma_y, rho, coords, colours_with_alpha, sr_size,
+                                     step_size, device=sigma_x.device)
+    return _sample(final_image, sample_coords)
+
+
+def generate_2D_gaussian_splatting_step_buffer(sr_size, gs_parameters, scale, scale_modify,
+                                               sample_coords=None, default_step_size=1.2,
+                                               cuda_rendering=True, mode='scale_modify',
+                                               if_dmax=True, dmax_mode='fix', dmax=25,
+                                               buffer_size=4000000):
+    if not cuda_rendering:
+        _no_python_renderer()
+    step_size, sigma_x, sigma_y, rho, coords, colours_with_alpha = _prepare(
+        gs_parameters, scale, scale_modify, default_step_size, mode)
+    if if_dmax:
+        final_image = rendering_cuda_dmax_buffer(sigma_x, sigma_y, rho, coords, colours_with_alpha,
+                                                 sr_size, step_size,
+                                                 dmax=_resolve_dmax(True, dmax_mode, dmax, sr_size),
+                                                 device=sigma_x.device, buffer_size=buffer_size)
+    else:
+        final_image = rendering_cuda_buffer(sigma_x, sigma_y, rho, coords, colours_with_alpha, sr_size,
+                                            step_size, device=sigma_x.device, buffer_size=buffer_size)
+    return _sample(final_image, sample_coords)

@@ -1,0 +1,114 @@
+"""Drop-in for the reference's pybind module ``gscuda`` (built by setup_gscuda.py:6-21 from
+utils/gs_cuda_dmax/{gswrapper.cpp,gs.cu}).
+
+Same two functions, same positional signatures and in-place accumulate semantics:
+
+    gs_render(sigmas, coords, colors, rendered_img, s, h, w, c, dmax)            gswrapper.cpp:9-35
+    gs_render_backward(sigmas, coords, colors, grads, grads_sigmas, grads_coords,
+                       grads_colors, s, h, w, c, dmax)                           gswrapper.cpp:37-73
+
+The window-less forms of utils/gs_cuda/gswrapper.cpp:9-34,36-71 (no ``dmax`` argument) are
+accepted too and mean ``dmax = +inf``.  Like the reference, tensors must be CUDA and contiguous
+(``RuntimeError`` otherwise, same wording as TORCH_CHECK); unlike it, dtype, shapes and c == 3 are
+validated as well, and the kernels run on the CURRENT torch stream instead of the legacy default
+stream.  Calls are asynchronous.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _lib
+
+__all__ = ["gs_render", "gs_render_backward", "set_ksigma", "get_ksigma"]
+
+_ksigma = float(os.environ.get("GSR_KSIGMA", "0"))  # 0 -> library default (GSR_DEFAULT_KSIGMA)
+
+
+def set_ksigma(k: float) -> None:
+    """Truncation radius in sigmas: contributions with Mahalanobis distance > k are dropped
+    (each < exp(-k^2/2)*|colour|).  0 = library default (5); float('inf') = exact mode."""
+    global _ksigma
+    _ksigma = float(k)
+
+
+def get_ksigma() -> float:
+    return _ksigma
+
+
+def _check_input(t, name: str) -> None:
+    # wording follows CHECK_CUDA / CHECK_CONTIGUOUS of gswrapper.cpp:5-7
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32")
+
+
+def _check_shape(t, shape, name: str) -> None:
+    if tuple(t.shape) != tuple(shape):
+        raise RuntimeError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+
+
+def workspace(s: int, h: int, w: int, device) -> torch.Tensor:
+    """Scratch for one call, from torch's caching allocator (stream-ordered reuse)."""
+    n = _lib.load().gsr_workspace_bytes(int(s), int(h), int(w))
+    if n == 0:
+        raise RuntimeError(f"libgsraster: bad sizes s={s}, h={h}, w={w} (need s>=0, 2<=h,w<=32767)")
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def _ptr(t):
+    return t.data_ptr() if t.numel() else None
+
+
+def gs_render(sigmas, coords, colors, rendered_img, s, h, w, c, dmax=float("inf"), *,
+              ksigma=None, flags=0, workspace_buf=None):
+    L = _lib.load()
+    for t, n in ((sigmas, "sigmas"), (coords, "coords"), (colors, "colors"), (rendered_img, "rendered_img")):
+        _check_input(t, n)
+    s, h, w, c = int(s), int(h), int(w), int(c)
+    if c != 3:
+        raise RuntimeError("libgsraster: c must be 3 (the reference forward hard-codes 3 channels)")
+    _check_shape(sigmas, (s, 3), "sigmas")
+    _check_shape(coords, (s, 2), "coords")
+    _check_shape(colors, (s, 3), "colors")
+    if rendered_img.numel() != h * w * c:
+        raise RuntimeError("rendered_img must have h*w*c elements")
+    with torch.cuda.device(sigmas.device):
+        ws = workspace_buf if workspace_buf is not None else workspace(s, h, w, sigmas.device)
+        rc = L.gsr_forward(_ptr(sigmas), _ptr(coords), _ptr(colors), rendered_img.data_ptr(), s, h, w, c,
+                           float(dmax), float(_ksigma if ksigma is None else ksigma), int(flags),
+                           ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)
+
+
+def gs_render_backward(sigmas, coords, colors, grads, grads_sigmas, grads_coords, grads_colors,
+                       s, h, w, c, dmax=float("inf"), *, ksigma=None, flags=0, workspace_buf=None):
+    L = _lib.load()
+    for t, n in ((sigmas, "sigmas"), (coords, "coords"), (colors, "colors"), (grads, "grads"),
+                 (grads_sigmas, "grads_sigmas"), (grads_coords, "grads_coords"),
+                 (grads_colors, "grads_colors")):
+        _check_input(t, n)
+    s, h, w, c = int(s), int(h), int(w), int(c)
+    if c != 3:
+        raise RuntimeError("libgsraster: c must be 3")
+    _check_shape(sigmas, (s, 3), "sigmas")
+    _check_shape(coords, (s, 2), "coords")
+    _check_shape(colors, (s, 3), "colors")
+    _check_shape(grads_sigmas, (s, 3), "grads_sigmas")
+    _check_shape(grads_coords, (s, 2), "grads_coords")
+    _check_shape(grads_colors, (s, 3), "grads_colors")
+    if grads.numel() != h * w * c:
+        raise RuntimeError("grads must have h*w*c elements")
+    with torch.cuda.device(sigmas.device):
+        ws = workspace_buf if workspace_buf is not None else workspace(s, h, w, sigmas.device)
+        rc = L.gsr_backward(_ptr(sigmas), _ptr(coords), _ptr(colors), grads.data_ptr(),
+                            _ptr(grads_sigmas), _ptr(grads_coords), _ptr(grads_colors), s, h, w, c,
+                            float(dmax), float(_ksigma if ksigma is None else ksigma), int(flags),
+                            ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)

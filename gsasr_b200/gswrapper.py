@@ -1,0 +1,50 @@
+"""Mirror of utils/gs_cuda_dmax/gswrapper.py:22-53 (and of utils/gs_cuda/gswrapper.py:19-48):
+the autograd boundary of the render path, same names, same argument meaning.
+
+    GSCUDA.apply(sigmas, coords, colors, rendered_img, dmax) -> rendered_img (same tensor)
+    gaussiansplatting_render(sigmas, coords, colors, image_size, dmax=100) -> (h, w, c)
+
+As in the reference no gradient flows to ``rendered_img`` and backward is once-differentiable.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import gscuda as GSWrapper
+
+
+class GSCUDA(Function):
+    @staticmethod
+    def forward(ctx, sigmas, coords, colors, rendered_img, dmax=float("inf")):
+        ctx.save_for_backward(sigmas, coords, colors)
+        ctx.dmax = dmax
+        h, w, c = rendered_img.shape
+        s = sigmas.shape[0]
+        GSWrapper.gs_render(sigmas, coords, colors, rendered_img, s, h, w, c, dmax)
+        return rendered_img
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        sigmas, coords, colors = ctx.saved_tensors
+        dmax = ctx.dmax
+        h, w, c = grad_output.shape
+        s = sigmas.shape[0]
+        grads_sigmas = torch.zeros_like(sigmas)
+        grads_coords = torch.zeros_like(coords)
+        grads_colors = torch.zeros_like(colors)
+        GSWrapper.gs_render_backward(sigmas, coords, colors, grad_output.contiguous(), grads_sigmas,
+                                     grads_coords, grads_colors, s, h, w, c, dmax)
+        return (grads_sigmas, grads_coords, grads_colors, None, None)
+
+
+def gaussiansplatting_render(sigmas, coords, colors, image_size, dmax=100):
+    sigmas = sigmas.contiguous()  # (gs num, 3)
+    coords = coords.contiguous()  # (gs num, 2)
+    colors = colors.contiguous()  # (gs num, c)
+    h, w = image_size[:2]
+    c = colors.shape[-1]
+    rendered_img = torch.zeros(h, w, c, device=colors.device, dtype=torch.float32)
+    return GSCUDA.apply(sigmas, coords, colors, rendered_img, dmax)

@@ -1,0 +1,132 @@
+/*
+ * gsraster.h -- C ABI of the B200-native 2-D Gaussian rasteriser (libgsraster.so).
+ *
+ * This is the drop-in boundary for GSASR's render path.  Every entry point below
+ * replaces one piece of the reference's native interface (paths relative to the
+ * GSASR tree):
+ *
+ *   gsr_forward           <-  _gs_render            utils/gs_cuda_dmax/gs.h:2-12, gs.cu:67-83
+ *                             gs_render (pybind)    utils/gs_cuda_dmax/gswrapper.cpp:9-35
+ *                             (and the window-less  utils/gs_cuda/gs.h, gs.cu:64-79 with dmax=+inf)
+ *   gsr_backward          <-  _gs_render_backward   utils/gs_cuda_dmax/gs.h:14-27, gs.cu:167-186
+ *                             gs_render_backward    utils/gs_cuda_dmax/gswrapper.cpp:37-73
+ *   gsr_forward_batch /   <-  the per-sample Python loop that calls the two functions above B times
+ *   gsr_backward_batch        TrainTestGSASR/basicsr/models/gsasr_model.py:191-233
+ *   gsr_frontend_forward  <-  activations + unit mapping + render + HWC->CHW transpose
+ *                             utils/gaussian_splatting.py:119-131,158-217
+ *   gsr_frontend_backward <-  autograd of the same chain down to the raw (N,9) head output
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless named *_host;
+ *   - fp32, contiguous, layouts as in the reference: sigmas (s,3) = (sigma_x, sigma_y, rho),
+ *     coords (s,2) = (x, y) on the align_corners=True [-1,1] grid, colors (s,3),
+ *     image / grads (h,w,3) HWC;
+ *   - the library never allocates or frees device memory, never synchronises the device and
+ *     never throws: scratch comes from the caller (`workspace`, sized by gsr_workspace_bytes),
+ *     work is enqueued on `stream` (a cudaStream_t / CUstream; NULL = legacy default stream,
+ *     which is what the reference launches on), and the return value is a gsr_status;
+ *   - re-entrant: no global mutable state; concurrent calls need distinct workspaces.
+ *
+ * Semantics that are identical to the reference:
+ *   - pixel (wi,hi) of Gaussian g is evaluated iff  |px(wi)-x| <= dmax  and  |py(hi)-y| <= dmax
+ *     with px(i) = (float)(2.0*i/(n-1) - 1.0) and the subtraction in fp32 (gs.cu:39-50,124-132):
+ *     the inclusion set is bit-identical;
+ *   - forward ACCUMULATES into `img` (gs.cu:58-60), backward ACCUMULATES into the three
+ *     gradient arrays (gs.cu:152-159) -- callers pre-zero them (gswrapper.py:40-43);
+ *   - no normalisation constant, no alpha compositing: img += sum_g color_g * exp(-q_g/2).
+ *
+ * Semantics that are new (documented deviations):
+ *   - `ksigma`: contributions with Mahalanobis distance^2 > ksigma^2 are dropped (each is
+ *     < exp(-ksigma^2/2) * |color|).  ksigma <= 0 selects GSR_DEFAULT_KSIGMA; ksigma = +inf
+ *     selects the exact mode, which drops only terms that are exactly 0 in flushed fp32
+ *     (ksigma is capped at GSR_EXACT_KSIGMA because exp2 of anything below -126 flushes to 0);
+ *   - Gaussians with non-finite parameters, sigma == 0 or |rho| >= 1 are skipped (the reference
+ *     renders NaN/Inf for them);
+ *   - c must be 3 (the reference's forward hard-codes 3 channels, gs.cu:29-31,58-60);
+ *     h, w must be in [2, 32767] (the reference divides by (n-1)).
+ */
+#ifndef GSRASTER_H_
+#define GSRASTER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSR_VERSION 100
+
+#define GSR_DEFAULT_KSIGMA 5.0f
+#define GSR_EXACT_KSIGMA 13.25f
+
+typedef enum gsr_status {
+  GSR_OK = 0,
+  GSR_ERR_NULL_POINTER = 1,
+  GSR_ERR_BAD_SHAPE = 2,       /* s < 0, h/w outside [2,32767] */
+  GSR_ERR_BAD_CHANNELS = 3,    /* c != 3 */
+  GSR_ERR_WORKSPACE = 4,       /* workspace NULL, misaligned (256 B) or too small */
+  GSR_ERR_BAD_ARGUMENT = 5,
+  GSR_ERR_CUDA = 6             /* a CUDA runtime call failed; see gsr_last_cuda_error() */
+} gsr_status;
+
+/* flags */
+#define GSR_FLAG_OVERWRITE 0x1u /* forward: img = sum instead of img += sum (skips the read) */
+#define GSR_FLAG_CHW 0x2u       /* forward: img is (3,h,w); backward: grads is (3,h,w)       */
+
+int gsr_version(void);
+const char* gsr_status_string(int status);
+/* Last CUDA error code observed by the calling thread inside this library (0 = none). */
+int gsr_last_cuda_error(void);
+
+/* Scratch bytes needed by gsr_forward / gsr_backward for s Gaussians on an h x w image.
+ * Depends on sizes only (never on data), so it can be called once and cached. 0 on bad sizes. */
+size_t gsr_workspace_bytes(int s, int h, int w);
+
+int gsr_forward(const float* sigmas, const float* coords, const float* colors, float* img,
+                int s, int h, int w, int c, float dmax, float ksigma, uint32_t flags,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+int gsr_backward(const float* sigmas, const float* coords, const float* colors,
+                 const float* grads, float* grads_sigmas, float* grads_coords,
+                 float* grads_colors, int s, int h, int w, int c, float dmax, float ksigma,
+                 uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
+
+/* One sample of a ragged batch (heterogeneous h, w, dmax -- the training loop's shape,
+ * gsasr_model.py:191-233).  Pointers are device pointers; the descriptor array is HOST memory. */
+typedef struct gsr_sample {
+  const float* sigmas;
+  const float* coords;
+  const float* colors;
+  float* img;                 /* forward: output;  backward: unused (may be NULL)    */
+  const float* grads;         /* backward: dL/dimg; forward: unused (may be NULL)    */
+  float* grads_sigmas;        /* backward outputs; forward: unused                   */
+  float* grads_coords;
+  float* grads_colors;
+  int s, h, w;
+  float dmax;
+} gsr_sample;
+
+size_t gsr_workspace_bytes_batch(const gsr_sample* samples_host, int n);
+int gsr_forward_batch(const gsr_sample* samples_host, int n, float ksigma, uint32_t flags,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int gsr_backward_batch(const gsr_sample* samples_host, int n, float ksigma, uint32_t flags,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Fused front end: raw head output (s,9) = (sx, sy, rho, alpha, r, g, b, mu_x, mu_y) ->
+ * activations (gaussian_splatting.py:174-180) -> unit/coordinate mapping (:121-123) ->
+ * render -> (3,h,w) image, written (not accumulated).  step_size = default_step_size / scale.
+ * The mapped (sigmas, coords, colors) are also written to `mapped` (s*8 floats, layout
+ * [sigmas (s,3) | coords (s,2) | colors (s,3)]) because the backward needs them. */
+int gsr_frontend_forward(const float* raw_params, float* mapped, float* img_chw, int s, int h,
+                         int w, float step_size, float dmax, float ksigma, void* workspace,
+                         size_t workspace_bytes, void* stream);
+/* grads_chw (3,h,w) -> grad_raw (s,9), written (not accumulated). */
+int gsr_frontend_backward(const float* raw_params, const float* mapped, const float* grads_chw,
+                          float* grad_raw, int s, int h, int w, float step_size, float dmax,
+                          float ksigma, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSRASTER_H_ */

@@ -1,0 +1,25 @@
+/*
+ * gsraster_test.h -- CPU test hooks exported by libgsraster.so.  They run the library's shared
+ * host/device culling code (gsasr_b200/csrc/gsr_common.cuh) on the HOST so that the CPU test
+ * suite can check it against the oracle without a GPU.  Not part of the product API.
+ */
+#ifndef GSRASTER_TEST_H_
+#define GSRASTER_TEST_H_
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* out is (s,9) int32: live, x0, x1, y0, y1 (inclusive cull box), binds, large, home bin, extent */
+void gsr_host_setup(const float* sigmas, const float* coords, const float* colors, int s, int h,
+                    int w, float dmax, float ksigma, int* out);
+/* inclusive pixel range of the reference's dmax window on an n-pixel axis (gs.cu:39-50) */
+void gsr_host_window_range(int n, float ctr, float dmax, int* lo, int* hi);
+/* 16-bit mask of the 8x8 regions of the 32x32 tile at (tx0,ty0) that Gaussian i may touch */
+unsigned gsr_host_region_mask(const float* sigmas, const float* coords, const float* colors, int i,
+                              int h, int w, float dmax, float ksigma, int tx0, int ty0);
+void gsr_host_geometry(int* tile, int* bin, int* region, int* large_px);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,70 @@
+"""CPU emulation of the forward kernel's CULLING semantics, built from the library's own host
+hooks (include/gsraster_test.h): which (Gaussian, pixel) pairs the sm_100a kernel evaluates.
+Values are computed in float64 from fp32-rounded dx, dy, so any difference against the oracle is
+due to culling (k-sigma truncation, region masks), never to arithmetic.  Test infrastructure."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from gsasr_b200 import _lib
+
+
+def pix_coords(n):
+    return (2.0 * np.arange(n, dtype=np.float64) / (n - 1) - 1.0).astype(np.float32)
+
+
+def host_setup(sigmas, coords, colors, h, w, dmax, ksigma):
+    L = _lib.load()
+    s = sigmas.shape[0]
+    out = np.zeros((max(s, 1), 9), dtype=np.int32)
+    L.gsr_host_setup(sigmas.ctypes.data, coords.ctypes.data, colors.ctypes.data, s, h, w,
+                     float(dmax), float(ksigma), out.ctypes.data)
+    return out[:s]
+
+
+def geometry():
+    L = _lib.load()
+    v = [ctypes.c_int() for _ in range(4)]
+    L.gsr_host_geometry(*[ctypes.byref(x) for x in v])
+    return tuple(x.value for x in v)
+
+
+def emulate_forward(sigmas, coords, colors, h, w, dmax, ksigma):
+    """Returns (img float64 (h,w,3), pairs evaluated, pairs inside the reference window)."""
+    L = _lib.load()
+    sigmas = np.ascontiguousarray(sigmas, np.float32)
+    coords = np.ascontiguousarray(coords, np.float32)
+    colors = np.ascontiguousarray(colors, np.float32)
+    TILE, BIN, REG, _ = geometry()
+    NR = TILE // REG
+    st = host_setup(sigmas, coords, colors, h, w, dmax, ksigma)
+    px, py = pix_coords(w), pix_coords(h)
+    img = np.zeros((h, w, 3))
+    npairs = 0
+    for g in np.nonzero(st[:, 0])[0]:
+        _, x0, x1, y0, y1, binds, _, _, _ = st[g]
+        sx, sy, rho = (float(v) for v in sigmas[g])
+        w1 = -0.5 / (1.0 - rho * rho)
+        for ty in range(y0 // TILE, y1 // TILE + 1):
+            for tx in range(x0 // TILE, x1 // TILE + 1):
+                m = L.gsr_host_region_mask(sigmas.ctypes.data, coords.ctypes.data, colors.ctypes.data,
+                                           int(g), h, w, float(dmax), float(ksigma), tx * TILE, ty * TILE)
+                for r in range(NR * NR):
+                    if not (m >> r) & 1:
+                        continue
+                    ry, rx = divmod(r, NR)
+                    xa, ya = tx * TILE + rx * REG, ty * TILE + ry * REG
+                    xb, yb = min(xa + REG, w), min(ya + REG, h)
+                    if binds:  # exact predicate: only pixels of the cull box
+                        xa, xb, ya, yb = max(xa, x0), min(xb, x1 + 1), max(ya, y0), min(yb, y1 + 1)
+                    if xa >= xb or ya >= yb:
+                        continue
+                    dx = (px[xa:xb] - coords[g, 0]).astype(np.float64)[None, :]
+                    dy = (py[ya:yb] - coords[g, 1]).astype(np.float64)[:, None]
+                    q = dx * dx / (sx * sx) - 2 * rho * dx * dy / (sx * sy) + dy * dy / (sy * sy)
+                    v = np.exp(w1 * q)
+                    img[ya:yb, xa:xb, :] += v[:, :, None] * colors[g].astype(np.float64)[None, None, :]
+                    npairs += v.size
+    return img, npairs
