@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of the render path (BASELINE.json):
+
+    metric   HR megapixels/sec rasterized (fwd) at x4, 2M Gaussians; % HBM roofline
+    workload "HL": 512x1024 LR -> x4 = 2048x4096 HR (8.39 MP), 2,097,152 synthetic Gaussians
+             (seeded raw head tensor, model-like sigma, the reference's own activation/mapping),
+             dmax 0.1, library-default k-sigma truncation.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload HL]
+
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1).  The path has no
+exchange step, so at N GPUs every rank rasterises its own image of the same shape (weak scaling,
+no collective in the timed region); `value` is the whole-job MP/s: N * MP / max-over-ranks time.
+
+A step is one forward pass of the hot path (set-up + raster kernels) with the Gaussian tensors
+and the image resident in HBM.  `e2e` is the same metric through the plugin call a GSASR user
+makes (gscuda.gs_render) from pinned HOST buffers, host<->device copies inside the timed region.
+`roofline` is for the dominant kernel (gsr_forward_kernel), timed with CUDA events on the launch
+stream via the split-phase C ABI.  `cpu_baseline` / `--impl reference` time the CPU restatement
+of the reference algorithm (oracle/, OpenMP over all host cores) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "HR megapixels/sec rasterized (fwd) at x4, 2M Gaussians"
+UNIT = "MP/s"
+DMAX = 0.1
+KERNELS_PER_STEP = 5  # gsr_table, gsr_bin, gsr_scan, gsr_scatter, gsr_forward
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_sample(cfg_name: str, seconds: float = 12.0, threads: int | None = None):
+    """Times the CPU restatement of the reference algorithm (oracle/gs_oracle.c, fp32 mode, dmax
+    window semantics, all host cores) on the first M Gaussians of the workload; M is grown until
+    one call takes ~`seconds`.  Returns (MP/s extrapolated to the whole workload, cores, text)."""
+    from gsasr_b200 import fields
+    from oracle import oracle
+
+    oracle.build()
+    if threads:
+        oracle.set_num_threads(threads)
+    cores = oracle.num_threads()
+    _, s, c, k, h, w = fields.make(cfg_name, 0)
+    s, c, k = s.numpy(), c.numpy(), k.numpy()
+    n = s.shape[0]
+    m, t = min(n, 256 * cores), 0.0
+    while True:
+        t0 = time.perf_counter()
+        oracle.forward(s[:m], c[:m], k[:m], h, w, DMAX, mode=1)
+        t = time.perf_counter() - t0
+        if t >= 0.5 * seconds or m >= n:
+            break
+        m = min(n, max(m + 1, int(m * min(8.0, seconds / max(t, 1e-3)))))
+    mps = (h * w / 1e6) / (t * n / m)
+    return mps, cores, (f"first {m} of {n} Gaussians of {cfg_name} ({h}x{w}, dmax {DMAX}) rendered in {t:.2f} s by "
+                        f"oracle/gs_oracle.c (fp32 mode, OpenMP {cores} threads); MP/s = MP / (t * {n}/{m})"), t
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    vals = []
+    sample = ""
+    cores = 1
+    for i in range(args.warmup + args.steps):
+        mps, cores, sample, t = cpu_sample(args.workload, seconds=max(2.0, 40.0 / (args.warmup + args.steps)))
+        if i >= args.warmup:
+            vals.append((mps, t))
+    value = sum(v for v, _ in vals) / len(vals)
+    from gsasr_b200 import fields
+    cfg = fields.CONFIGS[args.workload]
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * (cfg.hr[0] * cfg.hr[1] / 1e6) / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference's own implementation of this path is CUDA-only (gs_cuda_dmax); its CPU arm is the "
+                "oracle port of that algorithm timed on the host cores; ms_per_step is extrapolated to the whole image",
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(name):
+    from gsasr_b200 import fields
+    cfg = fields.CONFIGS[name]
+    h, w = cfg.hr
+    return {"workload": name, "lr": [cfg.lr_h, cfg.lr_w], "scale": cfg.scale, "hr": [h, w],
+            "gaussians": cfg.n, "dmax": DMAX, "sigma": "model-like: 0.99999*sigmoid(N(0,1))+1e-6",
+            "ksigma": "library default (5)",
+            "l2": "per-step working set (params 67 MB + image 101 MB + workspace 126 MB) exceeds the 126 MB L2"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="HL")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from gsasr_b200 import _lib, fields, gscuda
+    from gsasr_b200 import build as gbuild
+
+    gbuild.build()
+    L = _lib.load()  # raises if the CUDA library is missing: there is no fallback
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = fields.CONFIGS[args.workload]
+    _, s, c, k, h, w = fields.make(cfg, seed=rank)  # every rank its own image (weak scaling)
+    n = s.shape[0]
+    mp_img = h * w / 1e6
+    s_h, c_h, k_h = (t.pin_memory() for t in (s, c, k))
+    sd, cd, kd = s_h.to(dev), c_h.to(dev), k_h.to(dev)
+    img = torch.zeros(h, w, 3, device=dev)
+    ws = gscuda.workspace(n, h, w, dev)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    def step():
+        _lib.check(L.gsr_forward(sd.data_ptr(), cd.data_ptr(), kd.data_ptr(), img.data_ptr(), n, h, w, 3,
+                                 DMAX, 0.0, _lib.GSR_FLAG_OVERWRITE, ws.data_ptr(), ws.numel(), sptr))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: exactly K steps, device-timed, max over ranks ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * mp_img / (ms_step * 1e-3)
+
+    # ---- dominant kernel, timed alone with events through the split-phase ABI ----
+    kern_ms = []
+    for _ in range(min(args.steps, 30)):
+        _lib.check(L.gsr_prepare(sd.data_ptr(), cd.data_ptr(), kd.data_ptr(), n, h, w, DMAX, 0.0, ws.data_ptr(),
+                                 ws.numel(), sptr))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.check(L.gsr_forward_prepared(img.data_ptr(), n, h, w, 0.0, _lib.GSR_FLAG_OVERWRITE, ws.data_ptr(),
+                                          ws.numel(), sptr))
+        b.record()
+        torch.cuda.synchronize()
+        kern_ms.append(a.elapsed_time(b))
+    kern_ms = sum(kern_ms) / len(kern_ms)
+    alg_bytes = 32 * n + 12 * h * w
+    peak, peak_src = peaks()
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+
+    # ---- end to end through the plugin call, host buffers ----
+    out_h = torch.empty(h, w, 3, dtype=torch.float32).pin_memory()
+    def e2e_step():
+        a, b, cc = s_h.to(dev, non_blocking=True), c_h.to(dev, non_blocking=True), k_h.to(dev, non_blocking=True)
+        o = torch.zeros(h, w, 3, device=dev)
+        gscuda.gs_render(a, b, cc, o, n, h, w, 3, DMAX)
+        out_h.copy_(o, non_blocking=True)
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    ksteps = max(5, min(args.steps, 20))
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(ksteps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / ksteps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * mp_img / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload),
+            "clocks": clocks, "gpu_launches": KERNELS_PER_STEP * args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 12 * h * w},
+            "roofline": {"bound": "hbm", "kernel": "gsr_forward_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                         "algorithmic_bytes": alg_bytes, "kernel_ms": kern_ms,
+                         "kernel_share_of_step": kern_ms / ms_step, "traffic": TRAFFIC.get(args.workload),
+                         "note": "the kernel is bound by the MUFU.EX2 / FP32 issue pipes, not by HBM: see DESIGN.md"},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            mps, cores, sample, _ = cpu_sample(args.workload)
+            out["cpu_baseline"] = {"value": mps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of gsr_forward_kernel per launch, from the
+# `ncu --set full` capture summarised under profiles/ (bytes); None where not captured.
+TRAFFIC = {"HL": None}
+
+if __name__ == "__main__":
+    main()

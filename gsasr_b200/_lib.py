@@ -38,6 +38,9 @@ SIGNATURES = {
     "gsr_workspace_bytes": (_sz, [_i, _i, _i]),
     "gsr_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _u32, _vp, _sz, _vp]),
     "gsr_backward": (_i, [_vp] * 7 + [_i, _i, _i, _i, _f, _f, _u32, _vp, _sz, _vp]),
+    "gsr_prepare": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _sz, _vp]),
+    "gsr_forward_prepared": (_i, [_vp, _i, _i, _i, _f, _u32, _vp, _sz, _vp]),
+    "gsr_backward_prepared": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _u32, _vp, _sz, _vp]),
     "gsr_workspace_bytes_batch": (_sz, [ctypes.POINTER(GsrSample), _i]),
     "gsr_forward_batch": (_i, [ctypes.POINTER(GsrSample), _i, _f, _u32, _vp, _sz, _vp]),
     "gsr_backward_batch": (_i, [ctypes.POINTER(GsrSample), _i, _f, _u32, _vp, _sz, _vp]),

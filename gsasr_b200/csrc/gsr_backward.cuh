@@ -2,10 +2,18 @@
 //
 // Replaces _gs_render_backward_cuda (utils/gs_cuda_dmax/gs.cu:85-165; utils/gs_cuda/gs.cu:82-178).
 // The reference walks ALL h*w pixels per Gaussian with 24 global read-modify-writes per
-// in-window pixel.  Here one warp owns one Gaussian (taken in home-bin order, so neighbouring
-// warps read neighbouring parts of the gradient image), sweeps only the Gaussian's cull box in
-// 8x4 pixel patches, accumulates eight sums in registers, reduces them with warp shuffles and
-// issues ONE plain read-modify-write per output value: no atomics, deterministic.
+// in-window pixel.  Here the work is Gaussian-centric but tile-staged:
+//
+//   * one CTA per 32x32 "super tile" (2x2 home bins).  It stages the gradient image of the tile
+//     plus a halo (the reach of the Gaussians, capped at GSR_BWD_HALO) into shared memory as
+//     three planes whose row stride is 8 mod 32 words, so that an 8x4 pixel patch is read
+//     without bank conflicts;
+//   * the Gaussians homed in the tile are dealt to the 16 warps; a warp sweeps one Gaussian's
+//     cull box in 8x4 patches (lane = pixel), accumulates eight sums in registers, reduces them
+//     with shuffles and lane 0 issues ONE plain read-modify-write per output value:
+//     no atomics, deterministic;
+//   * Gaussians whose box leaves the staged window, and the "large" list (extra CTAs at the end
+//     of the grid), read the gradient image through L1/L2 instead.
 //
 // Gradient algebra (gs.cu:139-159) refactored into moments: with u = v * sum_c g_c col_c,
 //   Sx = sum u dx, Sy = sum u dy, Sxx = sum u dx^2, Sxy = sum u dx dy, Syy = sum u dy^2
@@ -16,14 +24,29 @@
 #pragma once
 #include "gsr_forward.cuh"
 
-constexpr int GSR_BWD_THREADS = 256;
+constexpr int GSR_BWD_THREADS = 512;
 constexpr int GSR_BWD_WARPS = GSR_BWD_THREADS / 32;
+constexpr int GSR_BWD_TILE = 32;                       // super tile side (multiple of GSR_BIN)
+constexpr int GSR_BWD_HALO = 24;                       // staged halo cap, pixels
+constexpr int GSR_BWD_RW = GSR_BWD_TILE + 2 * GSR_BWD_HALO;   // staged window side (80)
+constexpr int GSR_BWD_RS = 104;                        // plane row stride in words: >= RW, == 8 mod 32
+constexpr int GSR_BWD_PLANE = GSR_BWD_RW * GSR_BWD_RS; // words per plane
+constexpr int GSR_BWD_LARGE_CHUNK = 64;                // large-list Gaussians per extra CTA
+static_assert(GSR_BWD_RS % 32 == 8 && GSR_BWD_RS >= GSR_BWD_RW, "conflict-free patch reads");
+static_assert(GSR_BWD_TILE % GSR_BIN == 0, "super tile is made of whole bins");
+
+struct GsrBwdSmem {
+  float plane[3 * GSR_BWD_PLANE];
+  float px[GSR_BWD_RW];
+  float py[GSR_BWD_RW];
+};
 
 struct GsrBwdArgs {
   const GsrRec* rec;
   const uint2* box;
   const int* ids;
   const int* bin_off;
+  const int* stats;
   const float* px_tab;
   const float* py_tab;
   const float* grads;
@@ -31,7 +54,8 @@ struct GsrBwdArgs {
   float* g_sigmas;
   float* g_coords;
   float* g_colors;
-  int h, w, nb;
+  int h, w, nbx, nby, nb;
+  int tiles_x, tiles_y;
   uint32_t flags;
 };
 
@@ -41,97 +65,217 @@ __device__ __forceinline__ float gsr_warp_sum(float v) {
   return v;
 }
 
-__global__ void __launch_bounds__(GSR_BWD_THREADS) gsr_backward_kernel(GsrBwdArgs p) {
-  const int lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * GSR_BWD_WARPS + (threadIdx.x >> 5);
-  const int n_live = __ldg(p.bin_off + p.nb + 1);
-  if (gw >= n_live) return;
+struct GsrBwdAcc {
+  float cr, cg, cb, sx, sy, sxx, sxy, syy;
+};
 
-  const float4* rp = reinterpret_cast<const float4*>(p.rec + gw);
-  const float4 a0 = __ldg(rp), a1 = __ldg(rp + 1);
-  int bx0, bx1, by0, by1;
-  bool binds;
-  gsr_box_unpack(__ldg(p.box + gw), bx0, bx1, by0, by1, binds);
+// One pixel's contribution.  v must already be 0 for lanes outside the cull box.
+__device__ __forceinline__ void gsr_bwd_accum(GsrBwdAcc& a, float v, float g0, float g1, float g2,
+                                              float dx, float dy, const float4& a1) {
+  a.cr = fmaf(v, g0, a.cr);
+  a.cg = fmaf(v, g1, a.cg);
+  a.cb = fmaf(v, g2, a.cb);
+  const float G = fmaf(g0, a1.y, fmaf(g1, a1.z, g2 * a1.w));
+  const float u = v * G;
+  const float ux = u * dx, uy = u * dy;
+  a.sx += ux;
+  a.sy += uy;
+  a.sxx = fmaf(ux, dx, a.sxx);
+  a.sxy = fmaf(ux, dy, a.sxy);
+  a.syy = fmaf(uy, dy, a.syy);
+}
 
-  const bool chw = (p.flags & 2u) != 0;
-  const size_t plane = (size_t)p.h * p.w;
-  const int lx = lane & 7, ly = lane >> 3;
-  float cr = 0.f, cg = 0.f, cb = 0.f, sx_ = 0.f, sy_ = 0.f, sxx = 0.f, sxy = 0.f, syy = 0.f;
-
+// Sweep of one Gaussian's cull box with gradients read from the staged planes.
+__device__ __forceinline__ void gsr_bwd_sweep_smem(GsrBwdAcc& acc, const GsrBwdSmem& sm,
+                                                   const float4& a0, const float4& a1, int bx0,
+                                                   int bx1, int by0, int by1, int sx0, int sy0,
+                                                   int lx, int ly) {
   for (int yb = by0; yb <= by1; yb += 4) {
     const int y = yb + ly;
+    const int yc = min(y, by1) - sy0;  // lanes past the box re-read its last row (v = 0 there)
     const bool yok = y <= by1;
-    const float py = __ldg(p.py_tab + min(y, p.h - 1));
-    const float dy = py - a0.y;
+    const float dy = sm.py[yc] - a0.y;
+    const float t1 = a0.w * dy;
+    const float t0 = a1.x * dy * dy;
+    const float* row = sm.plane + yc * GSR_BWD_RS;
+    for (int xb = bx0; xb <= bx1; xb += 8) {
+      const int x = xb + lx;
+      const int xc = min(x, bx1) - sx0;
+      const bool ok = yok && x <= bx1;
+      const float dx = sm.px[xc] - a0.x;
+      const float e = fmaf(dx, fmaf(a0.z, dx, t1), t0);
+      const float g0 = row[xc];
+      const float g1 = row[xc + GSR_BWD_PLANE];
+      const float g2 = row[xc + 2 * GSR_BWD_PLANE];
+      const float v = ok ? gsr_ex2(e) : 0.f;
+      gsr_bwd_accum(acc, v, g0, g1, g2, dx, dy, a1);
+    }
+  }
+}
+
+// Same sweep with gradients read from global memory (through L1/L2).
+__device__ __forceinline__ void gsr_bwd_sweep_gmem(GsrBwdAcc& acc, const GsrBwdArgs& p,
+                                                   const float4& a0, const float4& a1, int bx0,
+                                                   int bx1, int by0, int by1, int lx, int ly) {
+  const bool chw = (p.flags & 2u) != 0;
+  const size_t plane = (size_t)p.h * p.w;
+  for (int yb = by0; yb <= by1; yb += 4) {
+    const int y = yb + ly;
+    const int yc = min(y, by1);
+    const bool yok = y <= by1;
+    const float dy = __ldg(p.py_tab + yc) - a0.y;
     const float t1 = a0.w * dy;
     const float t0 = a1.x * dy * dy;
     for (int xb = bx0; xb <= bx1; xb += 8) {
       const int x = xb + lx;
+      const int xc = min(x, bx1);
       const bool ok = yok && x <= bx1;
-      const float px = __ldg(p.px_tab + min(x, p.w - 1));
-      const float dx = px - a0.x;
+      const float dx = __ldg(p.px_tab + xc) - a0.x;
       const float e = fmaf(dx, fmaf(a0.z, dx, t1), t0);
-      float g0 = 0.f, g1 = 0.f, g2 = 0.f;
-      if (ok) {
-        if (chw) {
-          const float* gp = p.grads + (size_t)y * p.w + x;
-          g0 = __ldg(gp);
-          g1 = __ldg(gp + plane);
-          g2 = __ldg(gp + 2 * plane);
-        } else {
-          const float* gp = p.grads + ((size_t)y * p.w + x) * 3;
-          g0 = __ldg(gp);
-          g1 = __ldg(gp + 1);
-          g2 = __ldg(gp + 2);
-        }
+      float g0, g1, g2;
+      if (chw) {
+        const float* gp = p.grads + (size_t)yc * p.w + xc;
+        g0 = __ldg(gp);
+        g1 = __ldg(gp + plane);
+        g2 = __ldg(gp + 2 * plane);
+      } else {
+        const float* gp = p.grads + ((size_t)yc * p.w + xc) * 3;
+        g0 = __ldg(gp);
+        g1 = __ldg(gp + 1);
+        g2 = __ldg(gp + 2);
       }
       const float v = ok ? gsr_ex2(e) : 0.f;
-      cr = fmaf(v, g0, cr);
-      cg = fmaf(v, g1, cg);
-      cb = fmaf(v, g2, cb);
-      const float G = fmaf(g0, a1.y, fmaf(g1, a1.z, g2 * a1.w));
-      const float u = v * G;
-      const float ux = u * dx, uy = u * dy;
-      sx_ += ux;
-      sy_ += uy;
-      sxx = fmaf(ux, dx, sxx);
-      sxy = fmaf(ux, dy, sxy);
-      syy = fmaf(uy, dy, syy);
+      gsr_bwd_accum(acc, v, g0, g1, g2, dx, dy, a1);
     }
   }
-  cr = gsr_warp_sum(cr);
-  cg = gsr_warp_sum(cg);
-  cb = gsr_warp_sum(cb);
-  sx_ = gsr_warp_sum(sx_);
-  sy_ = gsr_warp_sum(sy_);
-  sxx = gsr_warp_sum(sxx);
-  sxy = gsr_warp_sum(sxy);
-  syy = gsr_warp_sum(syy);
+}
 
-  if (lane == 0) {
-    const int id = __ldg(p.ids + gw);
-    const double sgx = (double)__ldg(p.sigmas + 3 * (size_t)id + 0);
-    const double sgy = (double)__ldg(p.sigmas + 3 * (size_t)id + 1);
-    const double rho = (double)__ldg(p.sigmas + 3 * (size_t)id + 2);
-    const double w1 = -0.5 / (1.0 - rho * rho);
-    const double w2 = 1.0 / (sgx * sgx), w3 = 1.0 / (sgx * sgy), w4 = 1.0 / (sgy * sgy);
-    const double Sx = sx_, Sy = sy_, Sxx = sxx, Sxy = sxy, Syy = syy;
-    const double gx = 2.0 * w1 * (-w2 * Sx + rho * w3 * Sy);
-    const double gy = 2.0 * w1 * (-w4 * Sy + rho * w3 * Sx);
-    const double gsx = 2.0 * w1 / sgx * (rho * w3 * Sxy - w2 * Sxx);
-    const double gsy = 2.0 * w1 / sgy * (rho * w3 * Sxy - w4 * Syy);
-    const double D = w2 * Sxx - 2.0 * rho * w3 * Sxy + w4 * Syy;
-    const double grho = -2.0 * w1 * (2.0 * w1 * rho * D + w3 * Sxy);
-    float* os = p.g_sigmas + 3 * (size_t)id;
-    float* oc = p.g_coords + 2 * (size_t)id;
-    float* ok = p.g_colors + 3 * (size_t)id;
-    os[0] += (float)gsx;
-    os[1] += (float)gsy;
-    os[2] += (float)grho;
-    oc[0] += (float)gx;
-    oc[1] += (float)gy;
-    ok[0] += cr;
-    ok[1] += cg;
-    ok[2] += cb;
+// Warp-reduce the eight sums and let lane 0 apply the chain rule and accumulate the outputs.
+__device__ __forceinline__ void gsr_bwd_finish(GsrBwdAcc acc, const GsrBwdArgs& p, int gi, int lane) {
+  acc.cr = gsr_warp_sum(acc.cr);
+  acc.cg = gsr_warp_sum(acc.cg);
+  acc.cb = gsr_warp_sum(acc.cb);
+  acc.sx = gsr_warp_sum(acc.sx);
+  acc.sy = gsr_warp_sum(acc.sy);
+  acc.sxx = gsr_warp_sum(acc.sxx);
+  acc.sxy = gsr_warp_sum(acc.sxy);
+  acc.syy = gsr_warp_sum(acc.syy);
+  if (lane != 0) return;
+  const int id = __ldg(p.ids + gi);
+  const double sgx = (double)__ldg(p.sigmas + 3 * (size_t)id + 0);
+  const double sgy = (double)__ldg(p.sigmas + 3 * (size_t)id + 1);
+  const double rho = (double)__ldg(p.sigmas + 3 * (size_t)id + 2);
+  const double w1 = -0.5 / (1.0 - rho * rho);
+  const double w2 = 1.0 / (sgx * sgx), w3 = 1.0 / (sgx * sgy), w4 = 1.0 / (sgy * sgy);
+  const double Sx = acc.sx, Sy = acc.sy, Sxx = acc.sxx, Sxy = acc.sxy, Syy = acc.syy;
+  const double gx = 2.0 * w1 * (-w2 * Sx + rho * w3 * Sy);
+  const double gy = 2.0 * w1 * (-w4 * Sy + rho * w3 * Sx);
+  const double gsx = 2.0 * w1 / sgx * (rho * w3 * Sxy - w2 * Sxx);
+  const double gsy = 2.0 * w1 / sgy * (rho * w3 * Sxy - w4 * Syy);
+  const double D = w2 * Sxx - 2.0 * rho * w3 * Sxy + w4 * Syy;
+  const double grho = -2.0 * w1 * (2.0 * w1 * rho * D + w3 * Sxy);
+  float* os = p.g_sigmas + 3 * (size_t)id;
+  float* oc = p.g_coords + 2 * (size_t)id;
+  float* ok = p.g_colors + 3 * (size_t)id;
+  os[0] += (float)gsx;
+  os[1] += (float)gsy;
+  os[2] += (float)grho;
+  oc[0] += (float)gx;
+  oc[1] += (float)gy;
+  ok[0] += acc.cr;
+  ok[1] += acc.cg;
+  ok[2] += acc.cb;
+}
+
+__global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwdArgs p) {
+  extern __shared__ __align__(16) unsigned char gsr_smem_raw[];
+  GsrBwdSmem& sm = *reinterpret_cast<GsrBwdSmem*>(gsr_smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lx = lane & 7, ly = lane >> 3;
+  const int ntiles = p.tiles_x * p.tiles_y;
+
+  if ((int)blockIdx.x >= ntiles) {
+    // ---- "large" list: no staging, one chunk per CTA ----
+    const int l0 = __ldg(p.bin_off + p.nb), l1 = __ldg(p.bin_off + p.nb + 1);
+    const int c0 = l0 + ((int)blockIdx.x - ntiles) * GSR_BWD_LARGE_CHUNK;
+    const int c1 = min(c0 + GSR_BWD_LARGE_CHUNK, l1);
+    for (int gi = c0 + warp; gi < c1; gi += GSR_BWD_WARPS) {
+      const float4* rp = reinterpret_cast<const float4*>(p.rec + gi);
+      const float4 a0 = __ldg(rp), a1 = __ldg(rp + 1);
+      int bx0, bx1, by0, by1;
+      bool binds;
+      gsr_box_unpack(__ldg(p.box + gi), bx0, bx1, by0, by1, binds);
+      GsrBwdAcc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      gsr_bwd_sweep_gmem(acc, p, a0, a1, bx0, bx1, by0, by1, lx, ly);
+      gsr_bwd_finish(acc, p, gi, lane);
+    }
+    return;
+  }
+
+  const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
+  const int tx0 = tx * GSR_BWD_TILE, ty0 = ty * GSR_BWD_TILE;
+  // Gaussians homed in this tile: one contiguous run per bin row.
+  constexpr int BPT = GSR_BWD_TILE / GSR_BIN;
+  const int bx_lo = tx * BPT, bx_hi = min(bx_lo + BPT, p.nbx);
+  int run_s[BPT], run_n[BPT], ntot = 0;
+#pragma unroll
+  for (int r = 0; r < BPT; ++r) {
+    const int by = ty * BPT + r;
+    run_s[r] = 0;
+    run_n[r] = 0;
+    if (by < p.nby) {
+      run_s[r] = __ldg(p.bin_off + by * p.nbx + bx_lo);
+      run_n[r] = __ldg(p.bin_off + by * p.nbx + bx_hi) - run_s[r];
+    }
+    ntot += run_n[r];
+  }
+  if (ntot == 0) return;
+
+  // ---- stage the gradient window ----
+  const int hx = min(__ldg(p.stats + 0), GSR_BWD_HALO), hy = min(__ldg(p.stats + 1), GSR_BWD_HALO);
+  const int sx0 = max(tx0 - hx, 0), sx1 = min(tx0 + GSR_BWD_TILE - 1 + hx, p.w - 1);
+  const int sy0 = max(ty0 - hy, 0), sy1 = min(ty0 + GSR_BWD_TILE - 1 + hy, p.h - 1);
+  const int rw = sx1 - sx0 + 1, rh = sy1 - sy0 + 1;
+  if (tid < rw) sm.px[tid] = __ldg(p.px_tab + sx0 + tid);
+  if (tid >= 128 && tid - 128 < rh) sm.py[tid - 128] = __ldg(p.py_tab + sy0 + tid - 128);
+  if (p.flags & 2u) {  // CHW source: plane by plane
+    const size_t gplane = (size_t)p.h * p.w;
+    for (int r = warp; r < 3 * rh; r += GSR_BWD_WARPS) {
+      const int c = r / rh, yi = r - c * rh;
+      const float* src = p.grads + c * gplane + (size_t)(sy0 + yi) * p.w + sx0;
+      float* dst = sm.plane + c * GSR_BWD_PLANE + yi * GSR_BWD_RS;
+      for (int e = lane; e < rw; e += 32) dst[e] = __ldg(src + e);
+    }
+  } else {  // HWC source: a row of the window is 3*rw contiguous floats
+    for (int yi = warp; yi < rh; yi += GSR_BWD_WARPS) {
+      const float* src = p.grads + ((size_t)(sy0 + yi) * p.w + sx0) * 3;
+      float* dst = sm.plane + yi * GSR_BWD_RS;
+      for (int e = lane; e < 3 * rw; e += 32) {
+        const int x = e / 3, c = e - 3 * x;
+        dst[c * GSR_BWD_PLANE + x] = __ldg(src + e);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- one Gaussian per warp at a time ----
+  for (int k = warp; k < ntot; k += GSR_BWD_WARPS) {
+    int gi = 0, kk = k;
+#pragma unroll
+    for (int r = 0; r < BPT; ++r) {
+      if (kk >= 0 && kk < run_n[r]) gi = run_s[r] + kk;
+      kk = kk < run_n[r] ? -1 : kk - run_n[r];
+    }
+    const float4* rp = reinterpret_cast<const float4*>(p.rec + gi);
+    const float4 a0 = __ldg(rp), a1 = __ldg(rp + 1);
+    int bx0, bx1, by0, by1;
+    bool binds;
+    gsr_box_unpack(__ldg(p.box + gi), bx0, bx1, by0, by1, binds);
+    GsrBwdAcc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (bx0 >= sx0 && bx1 <= sx1 && by0 >= sy0 && by1 <= sy1)
+      gsr_bwd_sweep_smem(acc, sm, a0, a1, bx0, bx1, by0, by1, sx0, sy0, lx, ly);
+    else
+      gsr_bwd_sweep_gmem(acc, p, a0, a1, bx0, bx1, by0, by1, lx, ly);
+    gsr_bwd_finish(acc, p, gi, lane);
   }
 }

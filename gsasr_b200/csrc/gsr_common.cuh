@@ -55,8 +55,10 @@ GSR_HD float gsr_pix_coord(int i, int n) { return (float)(2.0 * i / (n - 1) - 1.
 
 // The reference's inclusion predicate for one axis (gs.cu:40-43,47-50): fp32 subtraction,
 // skip iff d > dmax || d < -dmax (so NaN d is NOT skipped; we never get here with NaN centres).
-GSR_HD bool gsr_in_window(int i, int n, float ctr, float dmax) {
-  float d = gsr_pix_coord(i, n) - ctr;
+// `tab` is the table of gsr_pix_coord values of the axis (device: filled by gsr_table_kernel);
+// NULL evaluates the rule directly.
+GSR_HD bool gsr_in_window(int i, int n, float ctr, float dmax, const float* tab = nullptr) {
+  float d = (tab ? tab[i] : gsr_pix_coord(i, n)) - ctr;
   return !(d > dmax || d < -dmax);
 }
 
@@ -64,7 +66,8 @@ GSR_HD bool gsr_in_window(int i, int n, float ctr, float dmax) {
 // The predicate is monotone in i, so the set is contiguous; we estimate both ends in double
 // and repair them with the exact predicate (the estimate is off by at most one pixel).
 // Empty range <=> lo > hi.
-GSR_HD void gsr_window_range(int n, float ctr, float dmax, int& lo, int& hi) {
+GSR_HD void gsr_window_range(int n, float ctr, float dmax, int& lo, int& hi,
+                             const float* tab = nullptr) {
   if (dmax != dmax || dmax >= 3.0e38f) {  // NaN never skips; +inf never skips
     lo = 0;
     hi = n - 1;
@@ -84,10 +87,10 @@ GSR_HD void gsr_window_range(int n, float ctr, float dmax, int& lo, int& hi) {
   int h = (int)floor(fhi) + 1;
   l = l < 0 ? 0 : (l > n ? n : l);
   h = h > n - 1 ? n - 1 : (h < -1 ? -1 : h);
-  for (int t = 0; t < 4 && l < n && !gsr_in_window(l, n, ctr, dmax); ++t) ++l;
-  if (l < n && !gsr_in_window(l, n, ctr, dmax)) l = n;
-  for (int t = 0; t < 4 && h >= 0 && !gsr_in_window(h, n, ctr, dmax); ++t) --h;
-  if (h >= 0 && !gsr_in_window(h, n, ctr, dmax)) h = -1;
+  for (int t = 0; t < 4 && l < n && !gsr_in_window(l, n, ctr, dmax, tab); ++t) ++l;
+  if (l < n && !gsr_in_window(l, n, ctr, dmax, tab)) l = n;
+  for (int t = 0; t < 4 && h >= 0 && !gsr_in_window(h, n, ctr, dmax, tab); ++t) --h;
+  if (h >= 0 && !gsr_in_window(h, n, ctr, dmax, tab)) h = -1;
   lo = l;
   hi = h;
 }
@@ -106,7 +109,8 @@ GSR_HD bool gsr_finite(float v) { return v == v && fabsf(v) < 3.0e38f; }
 
 // Cull box = exact dmax window  INTERSECT  [c - (k*sigma_px + pad), c + (k*sigma_px + pad)].
 GSR_HD GsrSetup gsr_setup(float sx, float sy, float rho, float x, float y, float cr, float cg,
-                          float cb, int h, int w, float dmax, float ksigma) {
+                          float cb, int h, int w, float dmax, float ksigma,
+                          const float* px_tab = nullptr, const float* py_tab = nullptr) {
   GsrSetup o;
   o.live = false;
   o.large = false;
@@ -121,8 +125,8 @@ GSR_HD GsrSetup gsr_setup(float sx, float sy, float rho, float x, float y, float
   if (sx == 0.0f || sy == 0.0f || !(fabsf(rho) < 1.0f)) return o;
 
   int wx0, wx1, wy0, wy1;
-  gsr_window_range(w, x, dmax, wx0, wx1);
-  gsr_window_range(h, y, dmax, wy0, wy1);
+  gsr_window_range(w, x, dmax, wx0, wx1, px_tab);
+  gsr_window_range(h, y, dmax, wy0, wy1, py_tab);
   if (wx0 > wx1 || wy0 > wy1) return o;
 
   const double hx = 0.5 * (double)(w - 1), hy = 0.5 * (double)(h - 1);

@@ -5,40 +5,59 @@
 // Here the image is cut into 32x32 tiles, one CTA per tile, 16 warps each owning an 8x8 region
 // (two horizontally adjacent pixels per lane, accumulated in registers, written once).
 //
-// Per CTA:
-//   stage A  (one thread per candidate)  candidates are the Gaussians of the home bins within
-//            reach of the tile -- contiguous runs of the sorted arrays, one run per bin row --
-//            plus the "large" list.  Cull box vs tile, then an ellipse-vs-region mask
-//            (gsr_region_mask).  Survivors are copied to shared memory and their slot is
-//            appended to the list of every region they touch.
-//   stage C  (one warp per region)  walk the region's list; per Gaussian 2 LDS.128 (broadcast),
-//            then per pixel: 1 FADD + 2 FFMA + MUFU.EX2 + 3 FFMA.
-// The bound is the MUFU pipe (16 ex2/clk/SM): see DESIGN.md.
+// Per CTA, in rounds of at most GSR_FWD_CAP candidates:
+//   stage A  (warp-private, no CTA barrier inside)
+//     pass 1  every warp takes a contiguous slice of the round's candidates -- Gaussians of the
+//             home bins within reach of the tile (contiguous runs of the sorted arrays, one run
+//             per bin row) plus the "large" list -- four per lane, tests cull box vs tile and
+//             streams the 32 B records of the hits into its private shared-memory segment with
+//             cp.async (LDGSTS; no register staging);
+//     pass 2  one lane per hit: ellipse-vs-region mask (gsr_region_mask); hits that touch at
+//             least one region are appended to the CTA-wide scan list (one atomic per warp).
+//   stage C  (one warp per region)  ballot-scan the list 32 entries at a time; per Gaussian that
+//            touches the region: 2 LDS.128 (broadcast), then per pixel 1 FADD + 2 FFMA +
+//            MUFU.EX2 + 3 FFMA.  Gaussians whose dmax window binds take a second, predicated loop.
+// The bound is the MUFU pipe (16 ex2/clk/SM) and FP32 issue: see DESIGN.md.
 #pragma once
 #include "gsr_prepass.cuh"
 
 constexpr int GSR_FWD_THREADS = 512;
 constexpr int GSR_FWD_WARPS = GSR_FWD_THREADS / 32;
-constexpr int GSR_FWD_CAP = 1024;  // survivor slots per flush
+constexpr int GSR_FWD_CAP = 2048;                          // candidate slots per round
+constexpr int GSR_FWD_SEG = GSR_FWD_CAP / GSR_FWD_WARPS;   // slots per warp segment (128)
+constexpr int GSR_FWD_PER_LANE = GSR_FWD_SEG / 32;         // candidates per lane per round (4)
 constexpr int GSR_FWD_MAXRUNS = 2 * ((GSR_LARGE_PX + GSR_BIN - 1) / GSR_BIN) + GSR_TILE / GSR_BIN + 2;
 static_assert(GSR_FWD_WARPS == (GSR_TILE / GSR_REGION) * (GSR_TILE / GSR_REGION), "one warp per region");
 static_assert(GSR_FWD_MAXRUNS <= 32, "run table is built by one warp");
 
 struct GsrFwdSmem {
-  float4 rec[GSR_FWD_CAP * 2];
-  uint2 box[GSR_FWD_CAP];
-  uint16_t list[GSR_FWD_WARPS][GSR_FWD_CAP];
-  int list_n[GSR_FWD_WARPS];
+  float4 rec[GSR_FWD_CAP * 2];   // 64 KB  records, addressed by slot
+  uint2 box[GSR_FWD_CAP];        // 16 KB  packed cull boxes, addressed by slot
+  uint32_t list[GSR_FWD_CAP];    //  8 KB  scan list: region mask | binds<<16 | slot<<17
   int run_start[GSR_FWD_MAXRUNS];
   int run_prefix[GSR_FWD_MAXRUNS + 1];
-  int wcnt[2][GSR_FWD_WARPS];
   int nruns;
+  int nlist[2];  // alternates between rounds
 };
 
 __device__ __forceinline__ float gsr_ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+__device__ __forceinline__ uint32_t gsr_smem_addr(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ float4 gsr_lds128(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void gsr_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void gsr_cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 struct GsrFwdArgs {
@@ -102,6 +121,7 @@ __global__ void __launch_bounds__(GSR_FWD_THREADS, 2) gsr_forward_kernel(GsrFwdA
   constexpr int NR = GSR_TILE / GSR_REGION;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx0 = blockIdx.x * GSR_TILE, ty0 = blockIdx.y * GSR_TILE;
+  const unsigned lt_mask = (1u << lane) - 1u;
 
   // this thread's two pixels
   const int wi0 = tx0 + (warp % NR) * GSR_REGION + (lane & 3) * 2;
@@ -114,107 +134,145 @@ __global__ void __launch_bounds__(GSR_FWD_THREADS, 2) gsr_forward_kernel(GsrFwdA
   if (warp == 0)
     gsr_build_runs(p.bin_off, p.stats, p.nbx, p.nby, p.nb, tx0, tx0 + GSR_TILE - 1, ty0,
                    ty0 + GSR_TILE - 1, lane, sm.run_start, sm.run_prefix, &sm.nruns);
-  if (tid < GSR_FWD_WARPS) sm.list_n[tid] = 0;
+  if (tid == 0) sm.nlist[0] = sm.nlist[1] = 0;
   __syncthreads();
-  int nsurv = 0;  // survivors waiting in shared memory (same value in every thread)
   const int nruns = sm.nruns;
   const int total = sm.run_prefix[nruns];
+  // balanced rounds: each at most GSR_FWD_CAP candidates, split evenly over the warps
+  const int nrounds = (total + GSR_FWD_CAP - 1) / GSR_FWD_CAP;
+  const int per_warp = nrounds ? ((total + nrounds - 1) / nrounds + GSR_FWD_WARPS - 1) / GSR_FWD_WARPS : 0;
+  const int per_round = per_warp * GSR_FWD_WARPS;
 
-  for (int base = 0; base < total; base += GSR_FWD_THREADS) {
-    // ---------------- stage A: cull one candidate per thread ----------------
-    const int cnd = base + tid;
-    uint32_t mask = 0;
-    uint2 pb = make_uint2(0, 0);
-    float4 q0, q1;
-    if (cnd < total) {
-      int r = 0;
-      while (cnd >= sm.run_prefix[r + 1]) ++r;
-      const int idx = sm.run_start[r] + (cnd - sm.run_prefix[r]);
-      pb = __ldg(p.box + idx);
+  const uint32_t rec_s = gsr_smem_addr(sm.rec);
+  const int seg0 = warp * GSR_FWD_SEG;
+
+  for (int round = 0; round < nrounds; ++round) {
+    // ---------------- stage A, pass 1: cull box vs tile, stream hits into the segment ----------
+    // 32-candidate groups are dealt round-robin to the warps, so that the hits (and with them the
+    // expensive pass 2) spread evenly however the runs are laid out.
+    const int rbase = round * per_round;
+    const int rend = min(rbase + per_round, total);
+    uint2 pb[GSR_FWD_PER_LANE];
+    int gidx[GSR_FWD_PER_LANE];
+#pragma unroll
+    for (int k = 0; k < GSR_FWD_PER_LANE; ++k) {
+      const int cnd = rbase + (k * GSR_FWD_WARPS + warp) * 32 + lane;
+      gidx[k] = -1;
+      pb[k] = make_uint2(0, 0);
+      if (cnd < rend) {
+        int r = 0;
+        while (cnd >= sm.run_prefix[r + 1]) ++r;
+        gidx[k] = sm.run_start[r] + (cnd - sm.run_prefix[r]);
+        pb[k] = __ldg(p.box + gidx[k]);
+      }
+    }
+    int n1 = 0;
+#pragma unroll
+    for (int k = 0; k < GSR_FWD_PER_LANE; ++k) {
       int bx0, bx1, by0, by1;
       bool binds;
-      gsr_box_unpack(pb, bx0, bx1, by0, by1, binds);
-      if (bx1 >= tx0 && bx0 < tx0 + GSR_TILE && by1 >= ty0 && by0 < ty0 + GSR_TILE) {
-        const float4* rp = reinterpret_cast<const float4*>(p.rec + idx);
-        q0 = __ldg(rp);
-        q1 = __ldg(rp + 1);
+      gsr_box_unpack(pb[k], bx0, bx1, by0, by1, binds);
+      const bool hit = gidx[k] >= 0 && bx1 >= tx0 && bx0 < tx0 + GSR_TILE && by1 >= ty0 &&
+                       by0 < ty0 + GSR_TILE;
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int slot = seg0 + n1 + __popc(bal & lt_mask);
+        const float4* src = reinterpret_cast<const float4*>(p.rec + gidx[k]);
+        gsr_cp_async16(rec_s + slot * 32, src);
+        gsr_cp_async16(rec_s + slot * 32 + 16, src + 1);
+        sm.box[slot] = pb[k];
+      }
+      n1 += __popc(bal);
+    }
+    gsr_cp_async_wait_all();
+    __syncwarp();
+    // ---------------- stage A, pass 2: region masks, append to the scan list -------------------
+    for (int j = 0; j < n1; j += 32) {
+      const int slot = seg0 + j + lane;
+      uint32_t entry = 0;
+      if (j + lane < n1) {
+        const float4 q0 = sm.rec[2 * slot], q1 = sm.rec[2 * slot + 1];
         GsrRec g;
         g.x = q0.x; g.y = q0.y; g.a = q0.z; g.b = q0.w;
         g.c = q1.x; g.r = q1.y; g.g = q1.z; g.bl = q1.w;
-        mask = gsr_region_mask(g, bx0, bx1, by0, by1, tx0, ty0, p.h, p.w, p.ecut);
+        int bx0, bx1, by0, by1;
+        bool binds;
+        gsr_box_unpack(sm.box[slot], bx0, bx1, by0, by1, binds);
+        const uint32_t m = gsr_region_mask(g, bx0, bx1, by0, by1, tx0, ty0, p.h, p.w, p.ecut);
+        if (m) entry = m | (binds ? 0x10000u : 0u) | ((uint32_t)slot << 17);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, entry != 0);
+      if (bal) {
+        int base = 0;
+        const int leader = __ffs(bal) - 1;
+        if (lane == leader) base = atomicAdd(&sm.nlist[round & 1], __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (entry) sm.list[base + __popc(bal & lt_mask)] = entry;
       }
     }
-    // Deterministic slot assignment: per-warp survivor counts -> block prefix.  The count
-    // buffers alternate between chunks, so one barrier per chunk is enough.
-    const unsigned bal = __ballot_sync(0xffffffffu, mask != 0);
-    int* wcnt = sm.wcnt[(base / GSR_FWD_THREADS) & 1];
-    if (lane == 0) wcnt[warp] = __popc(bal);
-    __syncthreads();
-    {
-      const int mine = lane < GSR_FWD_WARPS ? wcnt[lane] : 0;
-      int incl = mine;
-#pragma unroll
-      for (int d = 1; d < GSR_FWD_WARPS; d <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-      }
-      const int before = __shfl_sync(0xffffffffu, incl - mine, warp);
-      const int chunk_total = __shfl_sync(0xffffffffu, incl, GSR_FWD_WARPS - 1);
-      if (mask) {
-        const int slot = nsurv + before + __popc(bal & ((1u << lane) - 1u));
-        sm.rec[2 * slot] = q0;
-        sm.rec[2 * slot + 1] = q1;
-        sm.box[slot] = pb;
-        const uint16_t entry = (uint16_t)(slot | ((pb.x & 0x8000u) ? 0x8000 : 0));
-        while (mask) {
-          const int rg = __ffs(mask) - 1;
-          mask &= mask - 1;
-          const int pos = atomicAdd(&sm.list_n[rg], 1);
-          sm.list[rg][pos] = entry;
-        }
-      }
-      nsurv += chunk_total;
-    }
-    const bool last = base + GSR_FWD_THREADS >= total;
-    if (!last && nsurv + GSR_FWD_THREADS <= GSR_FWD_CAP) continue;
     __syncthreads();
 
-    // ---------------- stage C: every warp walks its region's list ----------------
-    const int n = sm.list_n[warp];
-    const uint16_t* mylist = sm.list[warp];
-#pragma unroll 2
-    for (int i = 0; i < n; ++i) {
-      const uint32_t entry = mylist[i];
-      const int slot = entry & 0x3ff;
-      const float4 a0 = sm.rec[2 * slot];
-      const float4 a1 = sm.rec[2 * slot + 1];
-      const float dy = py - a0.y;
-      const float t1 = a0.w * dy;
-      const float t0 = a1.x * dy * dy;
-      const float dx0 = px0 - a0.x;
-      const float dx1 = px1 - a0.x;
-      const float e0 = fmaf(dx0, fmaf(a0.z, dx0, t1), t0);
-      const float e1 = fmaf(dx1, fmaf(a0.z, dx1, t1), t0);
-      float v0 = gsr_ex2(e0);
-      float v1 = gsr_ex2(e1);
-      if (entry & 0x8000u) {  // dmax window cuts this Gaussian: exact inclusion test
+    // ---------------- stage C: every warp scans the list for its region ------------------------
+    const int nlist = sm.nlist[round & 1];
+    if (tid == 0) sm.nlist[(round + 1) & 1] = 0;  // free since the end of the previous round
+    for (int j = 0; j < nlist; j += 32) {
+      const uint32_t e = (j + lane < nlist) ? sm.list[j + lane] : 0u;
+      const bool mine = (e >> warp) & 1u;
+      unsigned fast = __ballot_sync(0xffffffffu, mine && !(e & 0x10000u));
+      unsigned slow = __ballot_sync(0xffffffffu, mine && (e & 0x10000u));
+      while (fast) {
+        const int src = __ffs(fast) - 1;
+        fast &= fast - 1;
+        const uint32_t es = __shfl_sync(0xffffffffu, e, src);
+        const uint32_t addr = rec_s + ((es >> 17) << 5);
+        const float4 a0 = gsr_lds128(addr);
+        const float4 a1 = gsr_lds128(addr + 16);
+        const float dy = py - a0.y;
+        const float t1 = a0.w * dy;
+        const float t0 = a1.x * dy * dy;
+        const float dx0 = px0 - a0.x;
+        const float dx1 = px1 - a0.x;
+        const float e0 = fmaf(dx0, fmaf(a0.z, dx0, t1), t0);
+        const float e1 = fmaf(dx1, fmaf(a0.z, dx1, t1), t0);
+        const float v0 = gsr_ex2(e0);
+        const float v1 = gsr_ex2(e1);
+        r0 = fmaf(v0, a1.y, r0);
+        g0 = fmaf(v0, a1.z, g0);
+        b0 = fmaf(v0, a1.w, b0);
+        r1 = fmaf(v1, a1.y, r1);
+        g1 = fmaf(v1, a1.z, g1);
+        b1 = fmaf(v1, a1.w, b1);
+      }
+      while (slow) {  // dmax window cuts this Gaussian: exact inclusion test per pixel
+        const int src = __ffs(slow) - 1;
+        slow &= slow - 1;
+        const uint32_t es = __shfl_sync(0xffffffffu, e, src);
+        const int slot = (int)(es >> 17);
+        const uint32_t addr = rec_s + (slot << 5);
+        const float4 a0 = gsr_lds128(addr);
+        const float4 a1 = gsr_lds128(addr + 16);
         int bx0, bx1, by0, by1;
         bool binds;
         gsr_box_unpack(sm.box[slot], bx0, bx1, by0, by1, binds);
         const bool iny = hi >= by0 && hi <= by1;
-        if (!(iny && wi0 >= bx0 && wi0 <= bx1)) v0 = 0.f;
-        if (!(iny && wi0 + 1 >= bx0 && wi0 + 1 <= bx1)) v1 = 0.f;
+        const float dy = py - a0.y;
+        const float t1 = a0.w * dy;
+        const float t0 = a1.x * dy * dy;
+        const float dx0 = px0 - a0.x;
+        const float dx1 = px1 - a0.x;
+        const float e0 = fmaf(dx0, fmaf(a0.z, dx0, t1), t0);
+        const float e1 = fmaf(dx1, fmaf(a0.z, dx1, t1), t0);
+        const float v0 = (iny && wi0 >= bx0 && wi0 <= bx1) ? gsr_ex2(e0) : 0.f;
+        const float v1 = (iny && wi0 + 1 >= bx0 && wi0 + 1 <= bx1) ? gsr_ex2(e1) : 0.f;
+        r0 = fmaf(v0, a1.y, r0);
+        g0 = fmaf(v0, a1.z, g0);
+        b0 = fmaf(v0, a1.w, b0);
+        r1 = fmaf(v1, a1.y, r1);
+        g1 = fmaf(v1, a1.z, g1);
+        b1 = fmaf(v1, a1.w, b1);
       }
-      r0 = fmaf(v0, a1.y, r0);
-      g0 = fmaf(v0, a1.z, g0);
-      b0 = fmaf(v0, a1.w, b0);
-      r1 = fmaf(v1, a1.y, r1);
-      g1 = fmaf(v1, a1.z, g1);
-      b1 = fmaf(v1, a1.w, b1);
     }
-    __syncthreads();
-    if (tid < GSR_FWD_WARPS) sm.list_n[tid] = 0;
-    nsurv = 0;
+    __syncthreads();  // segments and list are reused by the next round
   }
 
   // ---------------- write-out ----------------

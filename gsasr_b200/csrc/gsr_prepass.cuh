@@ -64,9 +64,6 @@ gsr_bin_kernel(const float* __restrict__ sigmas, const float* __restrict__ coord
                const float* __restrict__ colors, int s, int h, int w, float dmax, float ksigma,
                GsrWorkspace ws) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  // coordinate tables: the reference's rule, evaluated once per axis entry
-  if (i < w) ws.px_tab[i] = gsr_pix_coord(i, w);
-  if (i < h) ws.py_tab[i] = gsr_pix_coord(i, h);
   if (i >= s) return;
   const float sx = __ldg(sigmas + 3 * (size_t)i + 0);
   const float sy = __ldg(sigmas + 3 * (size_t)i + 1);
@@ -76,7 +73,7 @@ gsr_bin_kernel(const float* __restrict__ sigmas, const float* __restrict__ coord
   const float cr = __ldg(colors + 3 * (size_t)i + 0);
   const float cg = __ldg(colors + 3 * (size_t)i + 1);
   const float cb = __ldg(colors + 3 * (size_t)i + 2);
-  GsrSetup st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, h, w, dmax, ksigma);
+  GsrSetup st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, h, w, dmax, ksigma, ws.px_tab, ws.py_tab);
   if (st.live) {
     const GsrRec r = gsr_make_rec(sx, sy, rho, x, y, cr, cg, cb);
     if (!(gsr_finite(r.a) && gsr_finite(r.b) && gsr_finite(r.c))) st.live = false;
@@ -85,13 +82,26 @@ gsr_bin_kernel(const float* __restrict__ sigmas, const float* __restrict__ coord
   if (st.live) {
     key = st.large ? ws.nb : st.bin_y * ws.nbx + st.bin_x;
     rank = atomicAdd(ws.bin_count + key, 1);
-    if (!st.large) {
-      atomicMax(ws.stats + 0, st.ext_x);
-      atomicMax(ws.stats + 1, st.ext_y);
-    }
     ws.box_tmp[i] = gsr_box_pack(st.x0, st.x1, st.y0, st.y1, st.binds);
   }
   ws.keyrank[i] = make_int2(key, rank);
+  // reach statistics: one atomic per warp, and only while the maximum still grows
+  const bool small = st.live && !st.large;
+  const unsigned act = __activemask();
+  const int ex = __reduce_max_sync(act, small ? st.ext_x : 0);
+  const int ey = __reduce_max_sync(act, small ? st.ext_y : 0);
+  if ((threadIdx.x & 31) == (__ffs(act) - 1)) {
+    if (ex > *(volatile int*)(ws.stats + 0)) atomicMax(ws.stats + 0, ex);
+    if (ey > *(volatile int*)(ws.stats + 1)) atomicMax(ws.stats + 1, ey);
+  }
+}
+
+// Pixel coordinate tables: the reference's rule (gs.cu:39,46), evaluated once per axis entry.
+__global__ void __launch_bounds__(256) gsr_table_kernel(float* __restrict__ px_tab,
+                                                        float* __restrict__ py_tab, int h, int w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < w) px_tab[i] = gsr_pix_coord(i, w);
+  if (i < h) py_tab[i] = gsr_pix_coord(i, h);
 }
 
 // Exclusive scan of n = nb + 1 counters into n + 1 offsets; one CTA of 1024 threads.

@@ -53,9 +53,10 @@ static int gsr_run_prepass(const float* sigmas, const float* coords, const float
                            int h, int w, float dmax, float keff, const GsrWorkspace& ws,
                            cudaStream_t st) {
   GSR_CUDA(cudaMemsetAsync(ws.bin_count, 0, ((size_t)ws.nb + 1 + 8) * sizeof(int), st));
-  int n = s > w ? s : w;
-  n = n > h ? n : h;
-  gsr_bin_kernel<<<(n + 255) / 256, 256, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff, ws);
+  const int n = w > h ? w : h;
+  gsr_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws.px_tab, ws.py_tab, h, w);
+  if (s > 0)
+    gsr_bin_kernel<<<(s + 255) / 256, 256, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff, ws);
   gsr_scan_kernel<<<1, 1024, 0, st>>>(ws.bin_count, ws.bin_off, ws.nb + 1);
   if (s > 0) gsr_scatter_kernel<<<(s + 255) / 256, 256, 0, st>>>(sigmas, coords, colors, s, ws);
   GSR_CUDA(cudaGetLastError());
@@ -96,6 +97,7 @@ static int gsr_launch_backward(const GsrWorkspace& ws, const float* sigmas, cons
   a.box = ws.box;
   a.ids = ws.ids;
   a.bin_off = ws.bin_off;
+  a.stats = ws.stats;
   a.px_tab = ws.px_tab;
   a.py_tab = ws.py_tab;
   a.grads = grads;
@@ -105,9 +107,16 @@ static int gsr_launch_backward(const GsrWorkspace& ws, const float* sigmas, cons
   a.g_colors = gk;
   a.h = h;
   a.w = w;
+  a.nbx = ws.nbx;
+  a.nby = ws.nby;
   a.nb = ws.nb;
+  a.tiles_x = (w + GSR_BWD_TILE - 1) / GSR_BWD_TILE;
+  a.tiles_y = (h + GSR_BWD_TILE - 1) / GSR_BWD_TILE;
   a.flags = flags;
-  gsr_backward_kernel<<<(s + GSR_BWD_WARPS - 1) / GSR_BWD_WARPS, GSR_BWD_THREADS, 0, st>>>(a);
+  GSR_CUDA(cudaFuncSetAttribute(gsr_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(GsrBwdSmem)));
+  const int grid = a.tiles_x * a.tiles_y + (s + GSR_BWD_LARGE_CHUNK - 1) / GSR_BWD_LARGE_CHUNK;
+  gsr_backward_kernel<<<grid, GSR_BWD_THREADS, sizeof(GsrBwdSmem), st>>>(a);
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
 }
@@ -147,6 +156,43 @@ extern "C" int gsr_backward(const float* sigmas, const float* coords, const floa
   if (rc) return rc;
   return gsr_launch_backward(ws, sigmas, grads, grads_sigmas, grads_coords, grads_colors, s, h, w,
                              flags, st);
+}
+
+// ---- split-phase form ---------------------------------------------------------------------------
+extern "C" int gsr_prepare(const float* sigmas, const float* coords, const float* colors, int s,
+                           int h, int w, float dmax, float ksigma, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  if (!gsr_dims_ok(s, h, w)) return GSR_ERR_BAD_SHAPE;
+  if (s > 0 && (!sigmas || !coords || !colors)) return GSR_ERR_NULL_POINTER;
+  const GsrWorkspace ws = gsr_carve(workspace, s, h, w);
+  int rc = gsr_check_ws(workspace, workspace_bytes, ws.bytes);
+  if (rc) return rc;
+  return gsr_run_prepass(sigmas, coords, colors, s, h, w, dmax, gsr_effective_ksigma(ksigma), ws,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int gsr_forward_prepared(float* img, int s, int h, int w, float ksigma, uint32_t flags,
+                                    void* workspace, size_t workspace_bytes, void* stream) {
+  if (!gsr_dims_ok(s, h, w)) return GSR_ERR_BAD_SHAPE;
+  if (!img) return GSR_ERR_NULL_POINTER;
+  const GsrWorkspace ws = gsr_carve(workspace, s, h, w);
+  int rc = gsr_check_ws(workspace, workspace_bytes, ws.bytes);
+  if (rc) return rc;
+  return gsr_launch_forward(ws, img, h, w, gsr_effective_ksigma(ksigma), flags, (cudaStream_t)stream);
+}
+
+extern "C" int gsr_backward_prepared(const float* sigmas, const float* grads, float* grads_sigmas,
+                                     float* grads_coords, float* grads_colors, int s, int h, int w,
+                                     uint32_t flags, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+  if (!gsr_dims_ok(s, h, w)) return GSR_ERR_BAD_SHAPE;
+  if (!grads || (s > 0 && (!sigmas || !grads_sigmas || !grads_coords || !grads_colors)))
+    return GSR_ERR_NULL_POINTER;
+  const GsrWorkspace ws = gsr_carve(workspace, s, h, w);
+  int rc = gsr_check_ws(workspace, workspace_bytes, ws.bytes);
+  if (rc) return rc;
+  return gsr_launch_backward(ws, sigmas, grads, grads_sigmas, grads_coords, grads_colors, s, h, w,
+                             flags, (cudaStream_t)stream);
 }
 
 // ---- ragged batches -------------------------------------------------------------------------

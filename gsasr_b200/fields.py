@@ -66,9 +66,11 @@ def raw_field(gh: int, gw: int, seed: int = 0, compact: bool = False) -> torch.T
 
 def map_field(p: torch.Tensor, h: int, w: int, scale: float, default_step_size: float = 1.2):
     """raw (N,9) -> (sigmas (N,3), coords (N,2), colors (N,3)) with the reference's own expressions
-    (utils/gaussian_splatting.py:174-180, 121-123; sr_size as CPU int64 tensor, as inference does)."""
+    (utils/gaussian_splatting.py:174-180, 121-123; sr_size / scale_modify as CPU tensors, as
+    inference_paper.py:113-131 passes them)."""
     sr_size = torch.tensor([h, w])
-    step_size = default_step_size / scale
+    scale_modify = torch.tensor([scale, scale])  # inference_paper.py:125
+    step_size = default_step_size / scale_modify[0]
     sigma_x = 0.99999 * torch.sigmoid(p[:, 0:1]) + 1e-6
     sigma_y = 0.99999 * torch.sigmoid(p[:, 1:2]) + 1e-6
     rho = 0.999999 * torch.tanh(p[:, 2:3])

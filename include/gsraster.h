@@ -92,6 +92,20 @@ int gsr_backward(const float* sigmas, const float* coords, const float* colors,
                  float* grads_colors, int s, int h, int w, int c, float dmax, float ksigma,
                  uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Split-phase form.  gsr_forward == gsr_prepare + gsr_forward_prepared, gsr_backward ==
+ * gsr_prepare + gsr_backward_prepared.  gsr_prepare runs the O(N) set-up (cull boxes, counting
+ * sort by home bin) and leaves it in `workspace`; as long as the workspace is untouched and
+ * (s, h, w, dmax, ksigma) are the same, any number of raster passes can reuse it -- a training
+ * step prepares once and runs forward and backward (GSCUDA.forward / .backward,
+ * gswrapper.py:25-44, see the same Gaussians). */
+int gsr_prepare(const float* sigmas, const float* coords, const float* colors, int s, int h, int w,
+                float dmax, float ksigma, void* workspace, size_t workspace_bytes, void* stream);
+int gsr_forward_prepared(float* img, int s, int h, int w, float ksigma, uint32_t flags,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int gsr_backward_prepared(const float* sigmas, const float* grads, float* grads_sigmas,
+                          float* grads_coords, float* grads_colors, int s, int h, int w,
+                          uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
+
 /* One sample of a ragged batch (heterogeneous h, w, dmax -- the training loop's shape,
  * gsasr_model.py:191-233).  Pointers are device pointers; the descriptor array is HOST memory. */
 typedef struct gsr_sample {

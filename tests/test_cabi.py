@@ -1,0 +1,115 @@
+"""The C-ABI library: loads, exports every declared symbol, validates arguments (no GPU work)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from gsasr_b200 import _lib
+
+
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gsr_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported():
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared("gsraster.h") + _declared("gsraster_test.h")
+    assert "gsr_forward" in names and "gsr_backward" in names and len(names) >= 14
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/ but not exported by libgsraster.so"
+    # and the ctypes table covers the whole public header
+    assert set(_declared("gsraster.h")) == set(_lib.SIGNATURES)
+    assert set(_declared("gsraster_test.h")) == set(_lib.TEST_SIGNATURES)
+
+
+def test_no_cpu_fallback_symbols():
+    """The product library must not link the oracle."""
+    out = os.popen(f"nm -D {_lib.LIB_PATH}").read()
+    assert "gso_" not in out
+
+
+def test_version_and_strings():
+    L = _lib.load()
+    assert L.gsr_version() == 100
+    assert L.gsr_status_string(0) == b"ok"
+    for code in range(1, 7):
+        assert len(L.gsr_status_string(code)) > 3
+
+
+def test_workspace_bytes():
+    L = _lib.load()
+    a = L.gsr_workspace_bytes(1000, 64, 64)
+    b = L.gsr_workspace_bytes(2000, 64, 64)
+    c = L.gsr_workspace_bytes(1000, 1024, 1024)
+    assert 0 < a < b and a < c
+    assert L.gsr_workspace_bytes(0, 64, 64) > 0
+    for bad in ((-1, 64, 64), (10, 1, 64), (10, 64, 1), (10, 40000, 64), (10, 64, 40000)):
+        assert L.gsr_workspace_bytes(*bad) == 0
+    # bounded by sizes alone: ~52 B per Gaussian + ~8 B per 16x16 bin
+    assert L.gsr_workspace_bytes(2097152, 2048, 4096) < 160 * 2**20
+
+
+def test_argument_validation_without_gpu():
+    L = _lib.load()
+    fake = ctypes.c_void_p(256)  # never dereferenced: validation fails first
+    ws = ctypes.c_void_p(4096)
+    f = L.gsr_forward
+    assert f(fake, fake, fake, fake, 10, 64, 64, 4, 0.1, 0.0, 0, ws, 1 << 30, None) == 3      # c != 3
+    assert f(fake, fake, fake, fake, 10, 1, 64, 3, 0.1, 0.0, 0, ws, 1 << 30, None) == 2       # h < 2
+    assert f(fake, fake, fake, fake, -1, 64, 64, 3, 0.1, 0.0, 0, ws, 1 << 30, None) == 2      # s < 0
+    assert f(fake, fake, fake, None, 10, 64, 64, 3, 0.1, 0.0, 0, ws, 1 << 30, None) == 1      # img NULL
+    assert f(None, fake, fake, fake, 10, 64, 64, 3, 0.1, 0.0, 0, ws, 1 << 30, None) == 1      # sigmas NULL
+    assert f(fake, fake, fake, fake, 10, 64, 64, 3, 0.1, 0.0, 0, None, 1 << 30, None) == 4    # no workspace
+    assert f(fake, fake, fake, fake, 10, 64, 64, 3, 0.1, 0.0, 0, ws, 16, None) == 4           # too small
+    assert f(fake, fake, fake, fake, 10, 64, 64, 3, 0.1, 0.0, 0, ctypes.c_void_p(4100), 1 << 30, None) == 4  # misaligned
+    b = L.gsr_backward
+    assert b(fake, fake, fake, fake, fake, fake, fake, 10, 64, 64, 2, 0.1, 0.0, 0, ws, 1 << 30, None) == 3
+    assert b(fake, fake, fake, None, fake, fake, fake, 10, 64, 64, 3, 0.1, 0.0, 0, ws, 1 << 30, None) == 1
+    assert L.gsr_frontend_forward(fake, fake, fake, 10, 64, 64, 0.0, 0.1, 0.0, ws, 1 << 30, None) == 5  # step<=0
+    assert L.gsr_forward_batch(None, 2, 0.0, 0, ws, 1 << 30, None) == 1
+    assert L.gsr_forward_batch(None, -1, 0.0, 0, ws, 1 << 30, None) == 5
+    assert L.gsr_forward_batch(None, 0, 0.0, 0, None, 0, None) == 0
+
+
+def test_batch_workspace_is_sum_of_samples():
+    L = _lib.load()
+    arr = (_lib.GsrSample * 3)()
+    dims = [(100, 48, 48), (5000, 190, 130), (0, 64, 64)]
+    for a, (s, h, w) in zip(arr, dims):
+        a.s, a.h, a.w, a.dmax = s, h, w, 0.5
+    assert L.gsr_workspace_bytes_batch(arr, 3) == sum(L.gsr_workspace_bytes(*d) for d in dims)
+    arr[1].h = 1
+    assert L.gsr_workspace_bytes_batch(arr, 3) == 0
+
+
+def test_python_wrapper_rejects_cpu_tensors_like_the_reference():
+    """CHECK_CUDA / CHECK_CONTIGUOUS wording of gswrapper.cpp:5-7."""
+    import torch
+
+    from gsasr_b200 import gscuda
+
+    s = torch.rand(4, 3)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        gscuda.gs_render(s, torch.rand(4, 2), torch.rand(4, 3), torch.zeros(8, 8, 3), 4, 8, 8, 3, 0.5)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        gscuda.gs_render_backward(s, torch.rand(4, 2), torch.rand(4, 3), torch.zeros(8, 8, 3), s, s, s, 4, 8, 8, 3, 0.5)
+
+
+def test_top_level_gscuda_module_has_reference_surface():
+    import gscuda  # what utils/gs_cuda_dmax/gswrapper.py:19 imports
+
+    assert callable(gscuda.gs_render) and callable(gscuda.gs_render_backward)
+
+
+def test_frontend_rejects_python_renderer():
+    import torch
+
+    from gsasr_b200.gaussian_splatting import generate_2D_gaussian_splatting_step
+
+    with pytest.raises(NotImplementedError):
+        generate_2D_gaussian_splatting_step(torch.tensor([8, 8]), torch.zeros(4, 9), 2.0,
+                                            torch.tensor([2.0, 2.0]), cuda_rendering=False)

@@ -1,0 +1,115 @@
+"""The library's culling code (gsr_common.cuh), run on the HOST through the test hooks, against
+the oracle: exact dmax inclusion set, cull boxes, region masks, k-sigma truncation error."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import emulate
+from gsasr_b200 import _lib, fields
+from oracle import oracle
+
+
+def _window(n, ctr, dmax):
+    L = _lib.load()
+    lo, hi = ctypes.c_int(), ctypes.c_int()
+    L.gsr_host_window_range(n, ctypes.c_float(ctr), ctypes.c_float(dmax), ctypes.byref(lo), ctypes.byref(hi))
+    return lo.value, hi.value
+
+
+@pytest.mark.parametrize("n", [2, 3, 10, 128, 1023, 4096])
+def test_window_range_is_the_reference_inclusion_set(n):
+    rng = np.random.default_rng(n)
+    ctrs = np.concatenate([rng.uniform(-1.3, 1.3, 300), oracle_px(n)[rng.integers(0, n, 100)]]).astype(np.float32)
+    for dmax in (0.0, 1e-4, 0.05, 0.1, 0.5, 2.5, np.float32(2.0 / (n - 1)), np.inf):
+        want = oracle.ranges(np.stack([ctrs, ctrs], 1), n, n, dmax)
+        for c, r in zip(ctrs, want):
+            lo, hi = _window(n, float(c), float(dmax))
+            if r[1] < r[0]:
+                assert hi < lo
+            else:
+                assert (lo, hi) == (r[0], r[1]), (n, c, dmax)
+
+
+def oracle_px(n):
+    return emulate.pix_coords(n)
+
+
+def test_window_range_special_dmax():
+    assert _window(16, 0.0, float("nan")) == (0, 15)   # NaN never skips (gs.cu:41)
+    lo, hi = _window(16, 0.0, -0.5)
+    assert hi < lo                                       # negative dmax skips everything
+    assert _window(16, 5.0, float("inf")) == (0, 15)
+
+
+def _random_field(rng, s, sig_lo, sig_hi):
+    sig = np.stack([rng.uniform(sig_lo, sig_hi, s), rng.uniform(sig_lo, sig_hi, s),
+                    np.tanh(rng.normal(0, 1.2, s)) * 0.999999], 1).astype(np.float32)
+    xy = rng.uniform(-1.15, 1.15, (s, 2)).astype(np.float32)
+    col = rng.uniform(0, 1, (s, 3)).astype(np.float32)
+    return sig, xy, col
+
+
+@pytest.mark.parametrize("h,w,dmax", [(40, 72, 0.2), (97, 33, 0.08), (64, 64, np.inf), (50, 50, 0.5)])
+def test_exact_mode_reproduces_the_inclusion_set(h, w, dmax):
+    """ksigma=inf: every (Gaussian,pixel) pair of the reference with a non-flushed value is kept."""
+    rng = np.random.default_rng(h * w)
+    sig, xy, col = _random_field(rng, 150, 0.01, 0.4)
+    ref = oracle.forward(sig, xy, col, h, w, dmax)
+    img, _ = emulate.emulate_forward(sig, xy, col, h, w, dmax, float("inf"))
+    assert np.abs(img - ref).max() < 1e-12
+    st = emulate.host_setup(sig, xy, col, h, w, dmax, float("inf"))
+    rr = oracle.ranges(xy, h, w, dmax)
+    live = st[:, 0] == 1
+    # cull box is inside the window, and equal to it wherever the window binds on all sides
+    assert np.all(st[live, 1] >= rr[live, 0]) and np.all(st[live, 2] <= rr[live, 1])
+    assert np.all(st[live, 3] >= rr[live, 2]) and np.all(st[live, 4] <= rr[live, 3])
+
+
+@pytest.mark.parametrize("cfg,dmax", [("C1", 0.1), ("C1", 0.05)])
+def test_default_ksigma_error_budget(cfg, dmax):
+    """Default k-sigma truncation stays a decade below the 1e-4 parity tolerance."""
+    _, s, c, k, h, w = fields.make(cfg)
+    s, c, k = s.numpy(), c.numpy(), k.numpy()
+    ref = oracle.forward(s, c, k, h, w, dmax)
+    img, _ = emulate.emulate_forward(s, c, k, h, w, dmax, 0.0)
+    assert np.abs(img - ref).max() < 1e-5
+
+
+def test_degenerate_gaussians_are_skipped_or_kept_consistently():
+    h, w = 48, 80
+    sig = np.array([[0.1, 0.1, 0.0], [0.0, 0.1, 0.0], [0.1, 0.1, 1.0], [np.nan, 0.1, 0.0],
+                    [1e-9, 1e-9, 0.0], [5.0, 5.0, 0.3], [0.1, -0.2, 0.5]], np.float32)
+    xy = np.array([[0, 0], [0, 0], [0, 0], [0, 0], [0.0, 0.0], [0.2, -0.3], [3.0, 0.1]], np.float32)
+    col = np.ones((7, 3), np.float32)
+    st = emulate.host_setup(sig, xy, col, h, w, 0.3, 0.0)
+    assert st[:, 0].tolist() == [1, 0, 0, 0, 0, 1, 0]   # sigma=0, |rho|=1, NaN dropped; tiny off-grid
+                                                        # and far-outside Gaussians have empty boxes
+    keep = [0, 5]
+    ref = oracle.forward(sig[keep], xy[keep], col[keep], h, w, 0.3)
+    img, _ = emulate.emulate_forward(sig, xy, col, h, w, 0.3, 0.0)
+    assert np.abs(img - ref).max() < 1e-5
+
+
+def test_negative_sigma_matches_reference_formula():
+    h, w = 32, 32
+    sig = np.array([[0.2, -0.3, 0.6]], np.float32)
+    xy = np.array([[0.1, -0.2]], np.float32)
+    col = np.array([[1.0, 0.5, 0.25]], np.float32)
+    ref = oracle.forward(sig, xy, col, h, w, 10.0)
+    img, _ = emulate.emulate_forward(sig, xy, col, h, w, 10.0, float("inf"))
+    assert np.abs(img - ref).max() < 1e-12
+
+
+def test_large_class_and_bins():
+    tile, bin_, region, large = emulate.geometry()
+    assert tile % region == 0 and tile % bin_ == 0
+    h, w = 600, 900
+    sig = np.array([[0.5, 0.5, 0.0], [0.002, 0.002, 0.0]], np.float32)
+    xy = np.array([[0.0, 0.0], [-1.0, 1.0]], np.float32)
+    col = np.ones((2, 3), np.float32)
+    st = emulate.host_setup(sig, xy, col, h, w, 10.0, 0.0)
+    assert st[0, 6] == 1 and st[0, 8] > large     # wide Gaussian -> large list
+    assert st[1, 6] == 0
+    nbx = (w + bin_ - 1) // bin_
+    assert st[1, 7] == ((h - 1) // bin_) * nbx + 0  # bottom-left corner bin
