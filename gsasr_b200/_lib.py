@@ -6,7 +6,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgsraster.so")
+LIB_PATH = os.environ.get("GSR_LIB_PATH") or os.path.join(HERE, "libgsraster.so")
 
 GSR_FLAG_OVERWRITE = 0x1
 GSR_FLAG_CHW = 0x2
@@ -53,7 +53,7 @@ TEST_SIGNATURES = {
     "gsr_host_setup": (None, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
     "gsr_host_window_range": (None, [_i, _f, _f, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "gsr_host_region_mask": (ctypes.c_uint, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _i]),
-    "gsr_host_geometry": (None, [ctypes.POINTER(_i)] * 4),
+    "gsr_host_geometry": (None, [ctypes.POINTER(_i)] * 5),
 }
 
 _lib = None

@@ -54,6 +54,15 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(defines, out_path: str) -> str:
+    """Tuning aid: the same library with -D overrides of the geometry (gsr_common.cuh), written to
+    out_path; select it at run time with GSR_LIB_PATH=out_path."""
+    cmd = [nvcc_path()] + [f for f in NVCC_FLAGS if f != "-v" and f != "-Xptxas"] + [f"-D{d}" for d in defines]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out_path]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    return out_path
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile libgsraster.so for sm_100a; returns its path."""
     if not force and not is_stale():

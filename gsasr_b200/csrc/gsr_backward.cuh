@@ -85,28 +85,36 @@ __device__ __forceinline__ void gsr_bwd_accum(GsrBwdAcc& a, float v, float g0, f
   a.syy = fmaf(uy, dy, a.syy);
 }
 
-// Sweep of one Gaussian's cull box with gradients read from the staged planes.
-__device__ __forceinline__ void gsr_bwd_sweep_smem(GsrBwdAcc& acc, const GsrBwdSmem& sm,
-                                                   const float4& a0, const float4& a1, int bx0,
-                                                   int bx1, int by0, int by1, int sx0, int sy0,
-                                                   int lx, int ly) {
+// Sweep of one Gaussian's cull box with gradients read from the staged planes (explicit 32-bit
+// shared addresses, plane offsets as immediates).
+template <int OFF>
+__device__ __forceinline__ float gsr_lds32(uint32_t addr) {
+  float v;
+  asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
+
+__device__ __forceinline__ void gsr_bwd_sweep_smem(GsrBwdAcc& acc, uint32_t plane_s, uint32_t px_s,
+                                                   uint32_t py_s, const float4& a0, const float4& a1,
+                                                   int bx0, int bx1, int by0, int by1, int sx0,
+                                                   int sy0, int lx, int ly) {
+  const int xlim = bx1 - sx0;
   for (int yb = by0; yb <= by1; yb += 4) {
     const int y = yb + ly;
     const int yc = min(y, by1) - sy0;  // lanes past the box re-read its last row (v = 0 there)
     const bool yok = y <= by1;
-    const float dy = sm.py[yc] - a0.y;
+    const float dy = gsr_lds32<0>(py_s + yc * 4) - a0.y;
     const float t1 = a0.w * dy;
     const float t0 = a1.x * dy * dy;
-    const float* row = sm.plane + yc * GSR_BWD_RS;
-    for (int xb = bx0; xb <= bx1; xb += 8) {
-      const int x = xb + lx;
-      const int xc = min(x, bx1) - sx0;
-      const bool ok = yok && x <= bx1;
-      const float dx = sm.px[xc] - a0.x;
+    const uint32_t row = plane_s + yc * (GSR_BWD_RS * 4);
+    for (int xi = bx0 - sx0 + lx; xi - lx <= xlim; xi += 8) {
+      const uint32_t off = (uint32_t)min(xi, xlim) * 4u;
+      const bool ok = yok && xi <= xlim;
+      const float dx = gsr_lds32<0>(px_s + off) - a0.x;
       const float e = fmaf(dx, fmaf(a0.z, dx, t1), t0);
-      const float g0 = row[xc];
-      const float g1 = row[xc + GSR_BWD_PLANE];
-      const float g2 = row[xc + 2 * GSR_BWD_PLANE];
+      const float g0 = gsr_lds32<0>(row + off);
+      const float g1 = gsr_lds32<GSR_BWD_PLANE * 4>(row + off);
+      const float g2 = gsr_lds32<2 * GSR_BWD_PLANE * 4>(row + off);
       const float v = ok ? gsr_ex2(e) : 0.f;
       gsr_bwd_accum(acc, v, g0, g1, g2, dx, dy, a1);
     }
@@ -150,41 +158,62 @@ __device__ __forceinline__ void gsr_bwd_sweep_gmem(GsrBwdAcc& acc, const GsrBwdA
   }
 }
 
-// Warp-reduce the eight sums and let lane 0 apply the chain rule and accumulate the outputs.
-__device__ __forceinline__ void gsr_bwd_finish(GsrBwdAcc acc, const GsrBwdArgs& p, int gi, int lane) {
-  acc.cr = gsr_warp_sum(acc.cr);
-  acc.cg = gsr_warp_sum(acc.cg);
-  acc.cb = gsr_warp_sum(acc.cb);
-  acc.sx = gsr_warp_sum(acc.sx);
-  acc.sy = gsr_warp_sum(acc.sy);
-  acc.sxx = gsr_warp_sum(acc.sxx);
-  acc.sxy = gsr_warp_sum(acc.sxy);
-  acc.syy = gsr_warp_sum(acc.syy);
+// Warp-reduce the eight sums (recursive halving: 9 shuffles instead of 40, then 8 to collect) and
+// let lane 0 apply the chain rule and accumulate the outputs.  The chain rule is written in
+// terms of the raster conic (a, b, c) = log2(e) * w1 * (w2, -2 rho w3, w4):
+//   d/dx   = -(2 a Sx + b Sy) / L           d/dy   = -(2 c Sy + b Sx) / L
+//   d/dsx  = -(b Sxy + 2 a Sxx) / (L sx)    d/dsy  = -(b Sxy + 2 c Syy) / (L sy)
+//   d/drho = (2 rho Q / L + Sxy / (sx sy)) / (1 - rho^2),   Q = a Sxx + b Sxy + c Syy
+// (Q cancels strongly for |rho| -> 1 and is formed in double.)
+__device__ __forceinline__ void gsr_bwd_finish(const GsrBwdAcc& acc, const GsrBwdArgs& p, int gi,
+                                               int lane, const float4& a0, const float4& a1) {
+  float v[8] = {acc.cr, acc.cg, acc.cb, acc.sx, acc.sy, acc.sxx, acc.sxy, acc.syy};
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float w4[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b4 ? v[i] : v[i + 4], keep = b4 ? v[i + 4] : v[i];
+    w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  float w2[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b3 ? w4[i] : w4[i + 2], keep = b3 ? w4[i + 2] : w4[i];
+    w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  float x = (b2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? w2[0] : w2[1], 4);
+  x += __shfl_xor_sync(0xffffffffu, x, 2);
+  x += __shfl_xor_sync(0xffffffffu, x, 1);
+  // value k now lives in the lanes with (bit4,bit3,bit2) = (k>>2&1, k>>1&1, k&1)
+  float t[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) t[k] = __shfl_sync(0xffffffffu, x, ((k >> 2) & 1) * 16 + ((k >> 1) & 1) * 8 + (k & 1) * 4);
   if (lane != 0) return;
   const int id = __ldg(p.ids + gi);
-  const double sgx = (double)__ldg(p.sigmas + 3 * (size_t)id + 0);
-  const double sgy = (double)__ldg(p.sigmas + 3 * (size_t)id + 1);
-  const double rho = (double)__ldg(p.sigmas + 3 * (size_t)id + 2);
-  const double w1 = -0.5 / (1.0 - rho * rho);
-  const double w2 = 1.0 / (sgx * sgx), w3 = 1.0 / (sgx * sgy), w4 = 1.0 / (sgy * sgy);
-  const double Sx = acc.sx, Sy = acc.sy, Sxx = acc.sxx, Sxy = acc.sxy, Syy = acc.syy;
-  const double gx = 2.0 * w1 * (-w2 * Sx + rho * w3 * Sy);
-  const double gy = 2.0 * w1 * (-w4 * Sy + rho * w3 * Sx);
-  const double gsx = 2.0 * w1 / sgx * (rho * w3 * Sxy - w2 * Sxx);
-  const double gsy = 2.0 * w1 / sgy * (rho * w3 * Sxy - w4 * Syy);
-  const double D = w2 * Sxx - 2.0 * rho * w3 * Sxy + w4 * Syy;
-  const double grho = -2.0 * w1 * (2.0 * w1 * rho * D + w3 * Sxy);
+  const float sgx = __ldg(p.sigmas + 3 * (size_t)id + 0);
+  const float sgy = __ldg(p.sigmas + 3 * (size_t)id + 1);
+  const float rho = __ldg(p.sigmas + 3 * (size_t)id + 2);
+  const float Sx = t[3], Sy = t[4], Sxx = t[5], Sxy = t[6], Syy = t[7];
+  const float a = a0.z, b = a0.w, c = a1.x;
+  const float iL = 0.6931471805599453f;  // 1 / log2(e)
+  const float gx = -(2.0f * a * Sx + b * Sy) * iL;
+  const float gy = -(2.0f * c * Sy + b * Sx) * iL;
+  const float gsx = -(b * Sxy + 2.0f * a * Sxx) * iL / sgx;
+  const float gsy = -(b * Sxy + 2.0f * c * Syy) * iL / sgy;
+  const double Q = (double)a * Sxx + (double)b * Sxy + (double)c * Syy;
+  const float grho = (float)((2.0 * (double)rho * Q * (double)iL + (double)Sxy / ((double)sgx * sgy)) /
+                             (1.0 - (double)rho * rho));
   float* os = p.g_sigmas + 3 * (size_t)id;
   float* oc = p.g_coords + 2 * (size_t)id;
   float* ok = p.g_colors + 3 * (size_t)id;
-  os[0] += (float)gsx;
-  os[1] += (float)gsy;
-  os[2] += (float)grho;
-  oc[0] += (float)gx;
-  oc[1] += (float)gy;
-  ok[0] += acc.cr;
-  ok[1] += acc.cg;
-  ok[2] += acc.cb;
+  os[0] += gsx;
+  os[1] += gsy;
+  os[2] += grho;
+  oc[0] += gx;
+  oc[1] += gy;
+  ok[0] += t[0];
+  ok[1] += t[1];
+  ok[2] += t[2];
 }
 
 __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwdArgs p) {
@@ -207,7 +236,7 @@ __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwd
       gsr_box_unpack(__ldg(p.box + gi), bx0, bx1, by0, by1, binds);
       GsrBwdAcc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       gsr_bwd_sweep_gmem(acc, p, a0, a1, bx0, bx1, by0, by1, lx, ly);
-      gsr_bwd_finish(acc, p, gi, lane);
+      gsr_bwd_finish(acc, p, gi, lane, a0, a1);
     }
     return;
   }
@@ -258,6 +287,7 @@ __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwd
   }
   __syncthreads();
 
+  const uint32_t plane_s = gsr_smem_addr(sm.plane), px_s = gsr_smem_addr(sm.px), py_s = gsr_smem_addr(sm.py);
   // ---- one Gaussian per warp at a time ----
   for (int k = warp; k < ntot; k += GSR_BWD_WARPS) {
     int gi = 0, kk = k;
@@ -273,9 +303,9 @@ __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwd
     gsr_box_unpack(__ldg(p.box + gi), bx0, bx1, by0, by1, binds);
     GsrBwdAcc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (bx0 >= sx0 && bx1 <= sx1 && by0 >= sy0 && by1 <= sy1)
-      gsr_bwd_sweep_smem(acc, sm, a0, a1, bx0, bx1, by0, by1, sx0, sy0, lx, ly);
+      gsr_bwd_sweep_smem(acc, plane_s, px_s, py_s, a0, a1, bx0, bx1, by0, by1, sx0, sy0, lx, ly);
     else
       gsr_bwd_sweep_gmem(acc, p, a0, a1, bx0, bx1, by0, by1, lx, ly);
-    gsr_bwd_finish(acc, p, gi, lane);
+    gsr_bwd_finish(acc, p, gi, lane, a0, a1);
   }
 }

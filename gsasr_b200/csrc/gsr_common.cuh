@@ -15,10 +15,26 @@
 #define GSR_HD __host__ __device__ __forceinline__
 
 // ---- geometry of the decomposition ---------------------------------------------------
-constexpr int GSR_TILE = 32;          // forward CTA tile, pixels per side
-constexpr int GSR_BIN = 16;           // home-bin side (Gaussians are counting-sorted by bin)
-constexpr int GSR_REGION = 8;         // one warp of the forward kernel owns an 8x8 region
-constexpr int GSR_LARGE_PX = 128;     // half-extent above which a Gaussian goes to the "large" list
+// (overridable at compile time for tuning sweeps: -DGSR_CFG_TILE_W=.. etc.)
+#ifndef GSR_CFG_TILE_W
+#define GSR_CFG_TILE_W 32
+#endif
+#ifndef GSR_CFG_TILE_H
+#define GSR_CFG_TILE_H 16
+#endif
+#ifndef GSR_CFG_BIN
+#define GSR_CFG_BIN 8
+#endif
+#ifndef GSR_CFG_LARGE_PX
+#define GSR_CFG_LARGE_PX 96
+#endif
+constexpr int GSR_TILE_W = GSR_CFG_TILE_W;  // forward CTA tile, pixels
+constexpr int GSR_TILE_H = GSR_CFG_TILE_H;
+constexpr int GSR_BIN = GSR_CFG_BIN;        // home-bin side (Gaussians are counting-sorted by bin)
+constexpr int GSR_REGION = 8;               // one warp of the forward kernel owns an 8x8 region
+constexpr int GSR_NRX = GSR_TILE_W / GSR_REGION, GSR_NRY = GSR_TILE_H / GSR_REGION;
+constexpr int GSR_LARGE_PX = GSR_CFG_LARGE_PX;  // half-extent above which a Gaussian goes to the "large" list
+static_assert(GSR_NRX * GSR_NRY <= 16, "region mask is 16 bits");
 constexpr int GSR_MAX_DIM = 32767;    // bbox corners are stored as int16
 constexpr float GSR_LOG2E = 1.4426950408889634f;
 constexpr float GSR_CULL_PAD_PX = 0.02f;  // slack on every culling bound (pixels)
@@ -183,9 +199,9 @@ GSR_HD GsrRec gsr_make_rec(float sx, float sy, float rho, float x, float y, floa
 }
 
 // ---- region mask ----------------------------------------------------------------------------
-// For a GSR_TILE x GSR_TILE tile at pixel origin (tx0,ty0), which of its (TILE/REGION)^2
+// For a GSR_TILE_W x GSR_TILE_H tile at pixel origin (tx0,ty0), which of its GSR_NRX x GSR_NRY
 // warp regions does the ellipse {E >= ecut}, clipped to the cull box, touch?  Bit
-// (ry*(TILE/REGION) + rx).  Conservative (never misses a pixel with E >= ecut inside the
+// (ry*GSR_NRX + rx).  Conservative (never misses a pixel with E >= ecut inside the
 // box); pixels it drops carry exp2(E) < exp2(ecut).
 //
 // Per band of REGION rows: the ellipse's x-interval at row dy is centred on m(dy) = -b/(2a)*dy
@@ -193,7 +209,7 @@ GSR_HD GsrRec gsr_make_rec(float sx, float sy, float rho, float x, float y, floa
 // the two end-row centres widened by the largest half-width in the band.
 GSR_HD uint32_t gsr_region_mask(const GsrRec& g, int bx0, int bx1, int by0, int by1, int tx0,
                                 int ty0, int h, int w, float ecut) {
-  constexpr int NR = GSR_TILE / GSR_REGION;
+  constexpr int NR = GSR_NRX;
   const float hxs = 0.5f * (float)(w - 1), hys = 0.5f * (float)(h - 1);
   const float gx = 1.0f / hxs, gy = 1.0f / hys;  // normalised units per pixel
   const float cx = (g.x + 1.0f) * hxs, cy = (g.y + 1.0f) * hys;
@@ -204,10 +220,10 @@ GSR_HD uint32_t gsr_region_mask(const GsrRec& g, int bx0, int bx1, int by0, int 
   const float cp = c + 0.5f * kappa * b;        // c - b^2/(4a)  (<= 0)
   uint32_t mask = 0;
   const int cx0 = bx0 > tx0 ? bx0 : tx0;
-  const int cx1 = bx1 < tx0 + GSR_TILE - 1 ? bx1 : tx0 + GSR_TILE - 1;
+  const int cx1 = bx1 < tx0 + GSR_TILE_W - 1 ? bx1 : tx0 + GSR_TILE_W - 1;
   if (cx0 > cx1) return 0;
 #pragma unroll
-  for (int ry = 0; ry < NR; ++ry) {
+  for (int ry = 0; ry < GSR_NRY; ++ry) {
     int ya = ty0 + ry * GSR_REGION, yb = ya + GSR_REGION - 1;
     ya = ya > by0 ? ya : by0;
     yb = yb < by1 ? yb : by1;

@@ -21,19 +21,29 @@
 #pragma once
 #include "gsr_prepass.cuh"
 
-constexpr int GSR_FWD_THREADS = 512;
+constexpr int GSR_FWD_THREADS = 32 * GSR_NRX * GSR_NRY;
 constexpr int GSR_FWD_WARPS = GSR_FWD_THREADS / 32;
-constexpr int GSR_FWD_CAP = 2048;                          // candidate slots per round
+#ifndef GSR_CFG_MIN_CTAS
+#define GSR_CFG_MIN_CTAS 3
+#endif
+#ifndef GSR_CFG_PER_LANE
+#define GSR_CFG_PER_LANE 6
+#endif
+constexpr int GSR_FWD_CAP = 32 * GSR_CFG_PER_LANE * GSR_NRX * GSR_NRY;                        // candidate slots per round
 constexpr int GSR_FWD_SEG = GSR_FWD_CAP / GSR_FWD_WARPS;   // slots per warp segment (128)
 constexpr int GSR_FWD_PER_LANE = GSR_FWD_SEG / 32;         // candidates per lane per round (4)
-constexpr int GSR_FWD_MAXRUNS = 2 * ((GSR_LARGE_PX + GSR_BIN - 1) / GSR_BIN) + GSR_TILE / GSR_BIN + 2;
-static_assert(GSR_FWD_WARPS == (GSR_TILE / GSR_REGION) * (GSR_TILE / GSR_REGION), "one warp per region");
+constexpr int GSR_FWD_LCAP = 32;   // entries per (producer warp, region) list per round; the rest
+                                   // (and window-binding Gaussians) go to the scan list
+constexpr int GSR_FWD_MAXRUNS = 2 * ((GSR_LARGE_PX + GSR_BIN - 1) / GSR_BIN) + GSR_TILE_H / GSR_BIN + 2;
+static_assert(GSR_FWD_WARPS == GSR_NRX * GSR_NRY, "one warp per region");
 static_assert(GSR_FWD_MAXRUNS <= 32, "run table is built by one warp");
 
 struct GsrFwdSmem {
   float4 rec[GSR_FWD_CAP * 2];   // 64 KB  records, addressed by slot
   uint2 box[GSR_FWD_CAP];        // 16 KB  packed cull boxes, addressed by slot
-  uint32_t list[GSR_FWD_CAP];    //  8 KB  scan list: region mask | binds<<16 | slot<<17
+  uint32_t list[GSR_FWD_CAP];    //  8 KB  overflow scan list: region mask | binds<<16 | slot<<17
+  uint16_t lfast[GSR_FWD_WARPS][GSR_FWD_WARPS][GSR_FWD_LCAP];  // [producer warp][region] slot lists
+  uint8_t lcnt[GSR_FWD_WARPS][GSR_FWD_WARPS];                  // their lengths, rewritten every round
   int run_start[GSR_FWD_MAXRUNS];
   int run_prefix[GSR_FWD_MAXRUNS + 1];
   int nruns;
@@ -115,12 +125,12 @@ __device__ __forceinline__ void gsr_build_runs(const int* __restrict__ bin_off,
   }
 }
 
-__global__ void __launch_bounds__(GSR_FWD_THREADS, 2) gsr_forward_kernel(GsrFwdArgs p) {
+__global__ void __launch_bounds__(GSR_FWD_THREADS, GSR_CFG_MIN_CTAS) gsr_forward_kernel(GsrFwdArgs p) {
   extern __shared__ __align__(16) unsigned char gsr_smem_raw[];
   GsrFwdSmem& sm = *reinterpret_cast<GsrFwdSmem*>(gsr_smem_raw);
-  constexpr int NR = GSR_TILE / GSR_REGION;
+  constexpr int NR = GSR_NRX;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tx0 = blockIdx.x * GSR_TILE, ty0 = blockIdx.y * GSR_TILE;
+  const int tx0 = blockIdx.x * GSR_TILE_W, ty0 = blockIdx.y * GSR_TILE_H;
   const unsigned lt_mask = (1u << lane) - 1u;
 
   // this thread's two pixels
@@ -132,8 +142,8 @@ __global__ void __launch_bounds__(GSR_FWD_THREADS, 2) gsr_forward_kernel(GsrFwdA
   float r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
 
   if (warp == 0)
-    gsr_build_runs(p.bin_off, p.stats, p.nbx, p.nby, p.nb, tx0, tx0 + GSR_TILE - 1, ty0,
-                   ty0 + GSR_TILE - 1, lane, sm.run_start, sm.run_prefix, &sm.nruns);
+    gsr_build_runs(p.bin_off, p.stats, p.nbx, p.nby, p.nb, tx0, tx0 + GSR_TILE_W - 1, ty0,
+                   ty0 + GSR_TILE_H - 1, lane, sm.run_start, sm.run_prefix, &sm.nruns);
   if (tid == 0) sm.nlist[0] = sm.nlist[1] = 0;
   __syncthreads();
   const int nruns = sm.nruns;
@@ -154,13 +164,13 @@ __global__ void __launch_bounds__(GSR_FWD_THREADS, 2) gsr_forward_kernel(GsrFwdA
     const int rend = min(rbase + per_round, total);
     uint2 pb[GSR_FWD_PER_LANE];
     int gidx[GSR_FWD_PER_LANE];
+    int r = 0;  // run of the current candidate: candidates grow with k, so the search resumes
 #pragma unroll
     for (int k = 0; k < GSR_FWD_PER_LANE; ++k) {
       const int cnd = rbase + (k * GSR_FWD_WARPS + warp) * 32 + lane;
       gidx[k] = -1;
       pb[k] = make_uint2(0, 0);
       if (cnd < rend) {
-        int r = 0;
         while (cnd >= sm.run_prefix[r + 1]) ++r;
         gidx[k] = sm.run_start[r] + (cnd - sm.run_prefix[r]);
         pb[k] = __ldg(p.box + gidx[k]);
@@ -172,8 +182,8 @@ __global__ void __launch_bounds__(GSR_FWD_THREADS, 2) gsr_forward_kernel(GsrFwdA
       int bx0, bx1, by0, by1;
       bool binds;
       gsr_box_unpack(pb[k], bx0, bx1, by0, by1, binds);
-      const bool hit = gidx[k] >= 0 && bx1 >= tx0 && bx0 < tx0 + GSR_TILE && by1 >= ty0 &&
-                       by0 < ty0 + GSR_TILE;
+      const bool hit = gidx[k] >= 0 && bx1 >= tx0 && bx0 < tx0 + GSR_TILE_W && by1 >= ty0 &&
+                       by0 < ty0 + GSR_TILE_H;
       const unsigned bal = __ballot_sync(0xffffffffu, hit);
       if (hit) {
         const int slot = seg0 + n1 + __popc(bal & lt_mask);
@@ -186,90 +196,94 @@ __global__ void __launch_bounds__(GSR_FWD_THREADS, 2) gsr_forward_kernel(GsrFwdA
     }
     gsr_cp_async_wait_all();
     __syncwarp();
-    // ---------------- stage A, pass 2: region masks, append to the scan list -------------------
+    // ---------------- stage A, pass 2: region masks, append to the region lists ---------------
+    int cnt[GSR_FWD_WARPS];
+#pragma unroll
+    for (int rg = 0; rg < GSR_FWD_WARPS; ++rg) cnt[rg] = 0;
     for (int j = 0; j < n1; j += 32) {
       const int slot = seg0 + j + lane;
-      uint32_t entry = 0;
+      uint32_t m = 0;
+      bool binds = false;
       if (j + lane < n1) {
         const float4 q0 = sm.rec[2 * slot], q1 = sm.rec[2 * slot + 1];
         GsrRec g;
         g.x = q0.x; g.y = q0.y; g.a = q0.z; g.b = q0.w;
         g.c = q1.x; g.r = q1.y; g.g = q1.z; g.bl = q1.w;
         int bx0, bx1, by0, by1;
-        bool binds;
         gsr_box_unpack(sm.box[slot], bx0, bx1, by0, by1, binds);
-        const uint32_t m = gsr_region_mask(g, bx0, bx1, by0, by1, tx0, ty0, p.h, p.w, p.ecut);
-        if (m) entry = m | (binds ? 0x10000u : 0u) | ((uint32_t)slot << 17);
+        m = gsr_region_mask(g, bx0, bx1, by0, by1, tx0, ty0, p.h, p.w, p.ecut);
       }
-      const unsigned bal = __ballot_sync(0xffffffffu, entry != 0);
+      // Append to this warp's private list of every region touched (no atomics: the ranks come
+      // from ballots).  Window-binding Gaussians and entries that do not fit go to the CTA-wide
+      // scan list instead.
+      uint32_t ovf = binds ? m : 0u;
+#pragma unroll
+      for (int rg = 0; rg < GSR_FWD_WARPS; ++rg) {
+        const bool bit = ((m >> rg) & 1u) && !binds;
+        const unsigned bal = __ballot_sync(0xffffffffu, bit);
+        if (bit) {
+          const int pos = cnt[rg] + __popc(bal & lt_mask);
+          if (pos < GSR_FWD_LCAP) sm.lfast[warp][rg][pos] = (uint16_t)slot; else ovf |= 1u << rg;
+        }
+        cnt[rg] += __popc(bal);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, ovf != 0);
       if (bal) {
         int base = 0;
         const int leader = __ffs(bal) - 1;
         if (lane == leader) base = atomicAdd(&sm.nlist[round & 1], __popc(bal));
         base = __shfl_sync(0xffffffffu, base, leader);
-        if (entry) sm.list[base + __popc(bal & lt_mask)] = entry;
+        if (ovf) sm.list[base + __popc(bal & lt_mask)] = ovf | (binds ? 0x10000u : 0u) | ((uint32_t)slot << 17);
       }
     }
+#pragma unroll
+    for (int rg = 0; rg < GSR_FWD_WARPS; ++rg)
+      if (lane == rg) sm.lcnt[warp][rg] = (uint8_t)min(cnt[rg], GSR_FWD_LCAP);
     __syncthreads();
 
-    // ---------------- stage C: every warp scans the list for its region ------------------------
-    const int nlist = sm.nlist[round & 1];
+    // ---------------- stage C: every warp walks its region's lists -----------------------------
+    auto eval = [&](uint32_t addr, const bool in0, const bool in1) {
+      const float4 a0 = gsr_lds128(addr);
+      const float4 a1 = gsr_lds128(addr + 16);
+      const float dy = py - a0.y;
+      const float t1 = a0.w * dy;
+      const float t0 = a1.x * dy * dy;
+      const float dx0 = px0 - a0.x;
+      const float dx1 = px1 - a0.x;
+      const float e0 = fmaf(dx0, fmaf(a0.z, dx0, t1), t0);
+      const float e1 = fmaf(dx1, fmaf(a0.z, dx1, t1), t0);
+      const float v0 = in0 ? gsr_ex2(e0) : 0.f;
+      const float v1 = in1 ? gsr_ex2(e1) : 0.f;
+      r0 = fmaf(v0, a1.y, r0);
+      g0 = fmaf(v0, a1.z, g0);
+      b0 = fmaf(v0, a1.w, b0);
+      r1 = fmaf(v1, a1.y, r1);
+      g1 = fmaf(v1, a1.z, g1);
+      b1 = fmaf(v1, a1.w, b1);
+    };
+    auto eval_slow = [&](int slot) {  // dmax window cuts this Gaussian: exact inclusion per pixel
+      int bx0, bx1, by0, by1;
+      bool binds;
+      gsr_box_unpack(sm.box[slot], bx0, bx1, by0, by1, binds);
+      const bool iny = hi >= by0 && hi <= by1;
+      eval(rec_s + (slot << 5), iny && wi0 >= bx0 && wi0 <= bx1, iny && wi0 + 1 >= bx0 && wi0 + 1 <= bx1);
+    };
+    for (int pw = 0; pw < GSR_FWD_WARPS; ++pw) {  // the list each producer warp left for this region
+      const int nf = sm.lcnt[pw][warp];
+      const uint16_t* lf = sm.lfast[pw][warp];
+#pragma unroll 2
+      for (int i = 0; i < nf; ++i) eval(rec_s + ((uint32_t)lf[i] << 5), true, true);
+    }
+    const int nlist = sm.nlist[round & 1];  // overflow entries (normally none)
     if (tid == 0) sm.nlist[(round + 1) & 1] = 0;  // free since the end of the previous round
     for (int j = 0; j < nlist; j += 32) {
       const uint32_t e = (j + lane < nlist) ? sm.list[j + lane] : 0u;
-      const bool mine = (e >> warp) & 1u;
-      unsigned fast = __ballot_sync(0xffffffffu, mine && !(e & 0x10000u));
-      unsigned slow = __ballot_sync(0xffffffffu, mine && (e & 0x10000u));
-      while (fast) {
-        const int src = __ffs(fast) - 1;
-        fast &= fast - 1;
+      unsigned mine = __ballot_sync(0xffffffffu, (e >> warp) & 1u);
+      while (mine) {
+        const int src = __ffs(mine) - 1;
+        mine &= mine - 1;
         const uint32_t es = __shfl_sync(0xffffffffu, e, src);
-        const uint32_t addr = rec_s + ((es >> 17) << 5);
-        const float4 a0 = gsr_lds128(addr);
-        const float4 a1 = gsr_lds128(addr + 16);
-        const float dy = py - a0.y;
-        const float t1 = a0.w * dy;
-        const float t0 = a1.x * dy * dy;
-        const float dx0 = px0 - a0.x;
-        const float dx1 = px1 - a0.x;
-        const float e0 = fmaf(dx0, fmaf(a0.z, dx0, t1), t0);
-        const float e1 = fmaf(dx1, fmaf(a0.z, dx1, t1), t0);
-        const float v0 = gsr_ex2(e0);
-        const float v1 = gsr_ex2(e1);
-        r0 = fmaf(v0, a1.y, r0);
-        g0 = fmaf(v0, a1.z, g0);
-        b0 = fmaf(v0, a1.w, b0);
-        r1 = fmaf(v1, a1.y, r1);
-        g1 = fmaf(v1, a1.z, g1);
-        b1 = fmaf(v1, a1.w, b1);
-      }
-      while (slow) {  // dmax window cuts this Gaussian: exact inclusion test per pixel
-        const int src = __ffs(slow) - 1;
-        slow &= slow - 1;
-        const uint32_t es = __shfl_sync(0xffffffffu, e, src);
-        const int slot = (int)(es >> 17);
-        const uint32_t addr = rec_s + (slot << 5);
-        const float4 a0 = gsr_lds128(addr);
-        const float4 a1 = gsr_lds128(addr + 16);
-        int bx0, bx1, by0, by1;
-        bool binds;
-        gsr_box_unpack(sm.box[slot], bx0, bx1, by0, by1, binds);
-        const bool iny = hi >= by0 && hi <= by1;
-        const float dy = py - a0.y;
-        const float t1 = a0.w * dy;
-        const float t0 = a1.x * dy * dy;
-        const float dx0 = px0 - a0.x;
-        const float dx1 = px1 - a0.x;
-        const float e0 = fmaf(dx0, fmaf(a0.z, dx0, t1), t0);
-        const float e1 = fmaf(dx1, fmaf(a0.z, dx1, t1), t0);
-        const float v0 = (iny && wi0 >= bx0 && wi0 <= bx1) ? gsr_ex2(e0) : 0.f;
-        const float v1 = (iny && wi0 + 1 >= bx0 && wi0 + 1 <= bx1) ? gsr_ex2(e1) : 0.f;
-        r0 = fmaf(v0, a1.y, r0);
-        g0 = fmaf(v0, a1.z, g0);
-        b0 = fmaf(v0, a1.w, b0);
-        r1 = fmaf(v1, a1.y, r1);
-        g1 = fmaf(v1, a1.z, g1);
-        b1 = fmaf(v1, a1.w, b1);
+        if (es & 0x10000u) eval_slow((int)(es >> 17)); else eval(rec_s + ((es >> 17) << 5), true, true);
       }
     }
     __syncthreads();  // segments and list are reused by the next round

@@ -3,7 +3,8 @@
 //   K1 gsr_bin_kernel     per Gaussian: exact dmax window /\ k-sigma box -> cull box, home bin,
 //                         rank inside the bin (atomic), global reach statistics; also fills the
 //                         pixel coordinate tables (the reference's double-precision rule).
-//   K2 gsr_scan_kernel    exclusive scan of the bin histogram (single CTA).
+//   K2 gsr_scan_kernel    exclusive scan of the bin histogram (decoupled look-back, one CTA per
+//                         4096 bins).
 //   K3 gsr_scatter_kernel counting-sort scatter: writes the 32 B raster record, the packed
 //                         cull box and the original index at offset[bin] + rank.
 //
@@ -14,8 +15,11 @@
 #include "gsr_common.cuh"
 
 struct GsrWorkspace {
-  int* bin_count;   // nb + 1        (zeroed per call, contiguous with stats)
+  int* bin_count;   // nb + 1        (zeroed per call, contiguous with stats and scan_state)
   int* stats;       // 8 ints        [0] max ext_x (small), [1] max ext_y (small)
+  int* scan_state;  // 2 * nscan     per scan CTA: [2b] = ready flag, [2b+1] = CTA total
+  int nscan;        // CTAs of the scan kernel
+  size_t zero_bytes;  // bytes of the block cleared per call
   int* bin_off;     // nb + 2        exclusive offsets; [nb] = start of large, [nb+1] = n_live
   float* px_tab;    // w
   float* py_tab;    // h
@@ -27,6 +31,8 @@ struct GsrWorkspace {
   int nbx, nby, nb;
   size_t bytes;
 };
+
+constexpr int GSR_SCAN_CHUNK = 4096;  // counters per scan CTA (1024 threads x 4)
 
 static inline size_t gsr_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -44,9 +50,12 @@ static inline GsrWorkspace gsr_carve(void* base, int s, int h, int w) {
     return (void*)r;
   };
   const size_t sn = (size_t)(s > 0 ? s : 1);
-  // bin_count and stats must be contiguous: they are cleared by one memset.
-  ws.bin_count = (int*)take(((size_t)ws.nb + 1 + 8) * sizeof(int));
+  // bin_count, stats and scan_state are contiguous: they are cleared by one memset.
+  ws.nscan = (ws.nb + 1 + GSR_SCAN_CHUNK - 1) / GSR_SCAN_CHUNK;
+  ws.zero_bytes = ((size_t)ws.nb + 1 + 8 + 2 * (size_t)ws.nscan) * sizeof(int);
+  ws.bin_count = (int*)take(ws.zero_bytes);
   ws.stats = ws.bin_count ? ws.bin_count + ws.nb + 1 : nullptr;
+  ws.scan_state = ws.bin_count ? ws.stats + 8 : nullptr;
   ws.bin_off = (int*)take(((size_t)ws.nb + 2) * sizeof(int));
   ws.px_tab = (float*)take((size_t)w * sizeof(float));
   ws.py_tab = (float*)take((size_t)h * sizeof(float));
@@ -104,52 +113,76 @@ __global__ void __launch_bounds__(256) gsr_table_kernel(float* __restrict__ px_t
   if (i < h) py_tab[i] = gsr_pix_coord(i, h);
 }
 
-// Exclusive scan of n = nb + 1 counters into n + 1 offsets; one CTA of 1024 threads.
-__global__ void __launch_bounds__(1024) gsr_scan_kernel(const int* __restrict__ count,
-                                                        int* __restrict__ off, int n) {
-  __shared__ int warp_sums[32];
-  __shared__ int carry_s;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) carry_s = 0;
-  __syncthreads();
-  // process in slabs of 1024*4 elements so that loads stay coalesced (int4 per thread)
-  for (int base = 0; base < n; base += 4096) {
-    const int i0 = base + tid * 4;
-    int v[4];
+// Exclusive scan of n = nb + 1 counters into n + 1 offsets.  One CTA of 1024 threads per
+// GSR_SCAN_CHUNK counters; CTAs publish their totals (state[2b+1], then flag state[2b]) and sum
+// the totals of their predecessors (decoupled look-back: totals do not depend on anything, so
+// every flag is raised as soon as its CTA has been scheduled; CTAs are dispatched in index order,
+// so a waiting CTA never starves the ones it waits for).  `state` is zero on entry.
+__device__ __forceinline__ int gsr_block_sum_1024(int v, int* warp_sums) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? count[i0 + k] : 0;
-    const int local = v[0] + v[1] + v[2] + v[3];
-    int incl = local;
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  if (lane == 0) warp_sums[warp] = v;
+  __syncthreads();
+  int t = warp_sums[lane];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+  __syncthreads();
+  return t;
+}
+
+__global__ void __launch_bounds__(1024) gsr_scan_kernel(const int* __restrict__ count,
+                                                        int* __restrict__ off, int n,
+                                                        int* state) {
+  __shared__ int warp_sums[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
+  const int i0 = b * GSR_SCAN_CHUNK + tid * 4;
+  int v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] = (i0 + k < n) ? count[i0 + k] : 0;
+  const int local = v[0] + v[1] + v[2] + v[3];
+  // inclusive scan of the thread sums inside the CTA
+  int incl = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int ws = warp_sums[lane], wi = ws;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += t;
+      int t = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += t;
     }
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      int ws = warp_sums[lane];
-      int wi = ws;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, wi, d);
-        if (lane >= d) wi += t;
-      }
-      warp_sums[lane] = wi - ws;  // exclusive prefix of the warp totals
+    warp_sums[lane] = wi - ws;  // exclusive prefix of the warp totals
+    if (lane == 31) {           // wi = CTA total: publish it
+      *(volatile int*)(state + 2 * b + 1) = wi;
+      __threadfence();
+      *(volatile int*)(state + 2 * b) = 1;
     }
-    __syncthreads();
-    const int carry = carry_s;
-    int run = carry + warp_sums[warp] + incl - local;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (i0 + k < n) off[i0 + k] = run;
-      run += v[k];
-    }
-    __syncthreads();
-    if (tid == 1023) carry_s = run;
-    __syncthreads();
   }
-  if (tid == 0) off[n] = carry_s;
+  __syncthreads();
+  const int in_cta = warp_sums[warp] + incl - local;
+  __syncthreads();
+  // look back: sum the totals of CTAs 0 .. b-1
+  int carry = 0;
+  for (int j = tid; j < b; j += 1024) {
+    while (*(volatile int*)(state + 2 * j) == 0) {
+    }
+    __threadfence();
+    carry += *(volatile int*)(state + 2 * j + 1);
+  }
+  carry = gsr_block_sum_1024(carry, warp_sums);
+  int run = carry + in_cta;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (i0 + k < n) off[i0 + k] = run;
+    run += v[k];
+  }
+  if (b == gridDim.x - 1 && tid == 1023) off[n] = run;
 }
 
 __global__ void __launch_bounds__(256)

@@ -52,12 +52,12 @@ static int gsr_check_ws(void* workspace, size_t bytes, size_t need) {
 static int gsr_run_prepass(const float* sigmas, const float* coords, const float* colors, int s,
                            int h, int w, float dmax, float keff, const GsrWorkspace& ws,
                            cudaStream_t st) {
-  GSR_CUDA(cudaMemsetAsync(ws.bin_count, 0, ((size_t)ws.nb + 1 + 8) * sizeof(int), st));
+  GSR_CUDA(cudaMemsetAsync(ws.bin_count, 0, ws.zero_bytes, st));
   const int n = w > h ? w : h;
   gsr_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws.px_tab, ws.py_tab, h, w);
   if (s > 0)
     gsr_bin_kernel<<<(s + 255) / 256, 256, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff, ws);
-  gsr_scan_kernel<<<1, 1024, 0, st>>>(ws.bin_count, ws.bin_off, ws.nb + 1);
+  gsr_scan_kernel<<<ws.nscan, 1024, 0, st>>>(ws.bin_count, ws.bin_off, ws.nb + 1, ws.scan_state);
   if (s > 0) gsr_scatter_kernel<<<(s + 255) / 256, 256, 0, st>>>(sigmas, coords, colors, s, ws);
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
@@ -82,7 +82,7 @@ static int gsr_launch_forward(const GsrWorkspace& ws, float* img, int h, int w, 
   a.flags = flags;
   GSR_CUDA(cudaFuncSetAttribute(gsr_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(GsrFwdSmem)));
-  dim3 grid((w + GSR_TILE - 1) / GSR_TILE, (h + GSR_TILE - 1) / GSR_TILE);
+  dim3 grid((w + GSR_TILE_W - 1) / GSR_TILE_W, (h + GSR_TILE_H - 1) / GSR_TILE_H);
   gsr_forward_kernel<<<grid, GSR_FWD_THREADS, sizeof(GsrFwdSmem), st>>>(a);
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
@@ -328,14 +328,15 @@ extern "C" unsigned gsr_host_region_mask(const float* sigmas, const float* coord
                           coords[2 * i + 1], colors[3 * i], colors[3 * i + 1], colors[3 * i + 2], h,
                           w, dmax, keff);
   if (!st.live) return 0;
-  if (st.x1 < tx0 || st.x0 >= tx0 + GSR_TILE || st.y1 < ty0 || st.y0 >= ty0 + GSR_TILE) return 0;
+  if (st.x1 < tx0 || st.x0 >= tx0 + GSR_TILE_W || st.y1 < ty0 || st.y0 >= ty0 + GSR_TILE_H) return 0;
   GsrRec r = gsr_make_rec(sigmas[3 * i], sigmas[3 * i + 1], sigmas[3 * i + 2], coords[2 * i],
                           coords[2 * i + 1], colors[3 * i], colors[3 * i + 1], colors[3 * i + 2]);
   return gsr_region_mask(r, st.x0, st.x1, st.y0, st.y1, tx0, ty0, h, w, gsr_ecut(keff));
 }
 
-extern "C" void gsr_host_geometry(int* tile, int* bin, int* region, int* large_px) {
-  *tile = GSR_TILE;
+extern "C" void gsr_host_geometry(int* tile_w, int* tile_h, int* bin, int* region, int* large_px) {
+  *tile_w = GSR_TILE_W;
+  *tile_h = GSR_TILE_H;
   *bin = GSR_BIN;
   *region = GSR_REGION;
   *large_px = GSR_LARGE_PX;

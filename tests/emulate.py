@@ -26,7 +26,7 @@ def host_setup(sigmas, coords, colors, h, w, dmax, ksigma):
 
 def geometry():
     L = _lib.load()
-    v = [ctypes.c_int() for _ in range(4)]
+    v = [ctypes.c_int() for _ in range(5)]
     L.gsr_host_geometry(*[ctypes.byref(x) for x in v])
     return tuple(x.value for x in v)
 
@@ -37,8 +37,8 @@ def emulate_forward(sigmas, coords, colors, h, w, dmax, ksigma):
     sigmas = np.ascontiguousarray(sigmas, np.float32)
     coords = np.ascontiguousarray(coords, np.float32)
     colors = np.ascontiguousarray(colors, np.float32)
-    TILE, BIN, REG, _ = geometry()
-    NR = TILE // REG
+    TW, TH, BIN, REG, _ = geometry()
+    NRX, NRY = TW // REG, TH // REG
     st = host_setup(sigmas, coords, colors, h, w, dmax, ksigma)
     px, py = pix_coords(w), pix_coords(h)
     img = np.zeros((h, w, 3))
@@ -47,15 +47,15 @@ def emulate_forward(sigmas, coords, colors, h, w, dmax, ksigma):
         _, x0, x1, y0, y1, binds, _, _, _ = st[g]
         sx, sy, rho = (float(v) for v in sigmas[g])
         w1 = -0.5 / (1.0 - rho * rho)
-        for ty in range(y0 // TILE, y1 // TILE + 1):
-            for tx in range(x0 // TILE, x1 // TILE + 1):
+        for ty in range(y0 // TH, y1 // TH + 1):
+            for tx in range(x0 // TW, x1 // TW + 1):
                 m = L.gsr_host_region_mask(sigmas.ctypes.data, coords.ctypes.data, colors.ctypes.data,
-                                           int(g), h, w, float(dmax), float(ksigma), tx * TILE, ty * TILE)
-                for r in range(NR * NR):
+                                           int(g), h, w, float(dmax), float(ksigma), tx * TW, ty * TH)
+                for r in range(NRX * NRY):
                     if not (m >> r) & 1:
                         continue
-                    ry, rx = divmod(r, NR)
-                    xa, ya = tx * TILE + rx * REG, ty * TILE + ry * REG
+                    ry, rx = divmod(r, NRX)
+                    xa, ya = tx * TW + rx * REG, ty * TH + ry * REG
                     xb, yb = min(xa + REG, w), min(ya + REG, h)
                     if binds:  # exact predicate: only pixels of the cull box
                         xa, xb, ya, yb = max(xa, x0), min(xb, x1 + 1), max(ya, y0), min(yb, y1 + 1)

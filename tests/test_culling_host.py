@@ -102,8 +102,8 @@ def test_negative_sigma_matches_reference_formula():
 
 
 def test_large_class_and_bins():
-    tile, bin_, region, large = emulate.geometry()
-    assert tile % region == 0 and tile % bin_ == 0
+    tile_w, tile_h, bin_, region, large = emulate.geometry()
+    assert tile_w % region == 0 and tile_h % region == 0
     h, w = 600, 900
     sig = np.array([[0.5, 0.5, 0.0], [0.002, 0.002, 0.0]], np.float32)
     xy = np.array([[0.0, 0.0], [-1.0, 1.0]], np.float32)
