@@ -293,7 +293,7 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of gsr_forward_kernel per launch, from the
 # `ncu --set full` capture summarised under profiles/ (bytes); None where not captured.
-TRAFFIC = {"HL": None}
+TRAFFIC = {"HL": 241.0e6}  # profiles/r01_fwd_HL_*_ncu_full.txt: 185.2 MB read + 55.8 MB written
 
 if __name__ == "__main__":
     main()
