@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 METRIC = "HR megapixels/sec rasterized (fwd) at x4, 2M Gaussians"
 UNIT = "MP/s"
 DMAX = 0.1
-KERNELS_PER_STEP = 5  # gsr_table, gsr_bin, gsr_scan, gsr_scatter, gsr_forward
+KERNELS_PER_STEP = 9  # table, tile_count, scan, tile_fill, forward_list + the guarded fallback (bin, scan, scatter, forward_bins)
 
 
 def peaks():
@@ -277,7 +277,7 @@ def main():
             "clocks": clocks, "gpu_launches": KERNELS_PER_STEP * args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 12 * h * w},
-            "roofline": {"bound": "hbm", "kernel": "gsr_forward_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "gsr_forward_list_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes": alg_bytes, "kernel_ms": kern_ms,
                          "kernel_share_of_step": kern_ms / ms_step, "traffic": TRAFFIC.get(args.workload),

@@ -140,11 +140,6 @@ GSR_HD GsrSetup gsr_setup(float sx, float sy, float rho, float x, float y, float
     return o;
   if (sx == 0.0f || sy == 0.0f || !(fabsf(rho) < 1.0f)) return o;
 
-  int wx0, wx1, wy0, wy1;
-  gsr_window_range(w, x, dmax, wx0, wx1, px_tab);
-  gsr_window_range(h, y, dmax, wy0, wy1, py_tab);
-  if (wx0 > wx1 || wy0 > wy1) return o;
-
   const double hx = 0.5 * (double)(w - 1), hy = 0.5 * (double)(h - 1);
   const double cx = ((double)x + 1.0) * hx, cy = ((double)y + 1.0) * hy;
   const double ex = (double)ksigma * fabs((double)sx) * hx + (double)GSR_CULL_PAD_PX;
@@ -154,6 +149,25 @@ GSR_HD GsrSetup gsr_setup(float sx, float sy, float rho, float x, float y, float
   int kx1 = (int)floor(fmin(fmax(cx + ex, -lim), lim));
   int ky0 = (int)ceil(fmin(fmax(cy - ey, -lim), lim));
   int ky1 = (int)floor(fmin(fmax(cy + ey, -lim), lim));
+
+  // Exact dmax window.  When the k-sigma box lies at least two pixels inside the window estimate
+  // (the estimate is within one pixel of the truth) the window cannot bind and the exact repair
+  // with the reference's predicate is skipped: the window is then only known to contain the box.
+  int wx0, wx1, wy0, wy1;
+  const double dmx = (dmax != dmax || dmax >= 3.0e38f) ? 1.0e9 : (double)dmax;
+  if (dmx >= 0.0 && kx0 - 2.0 > (cx - dmx * hx) && kx1 + 2.0 < (cx + dmx * hx)) {
+    wx0 = kx0 < 0 ? 0 : kx0;
+    wx1 = kx1 > w - 1 ? w - 1 : kx1;
+  } else {
+    gsr_window_range(w, x, dmax, wx0, wx1, px_tab);
+  }
+  if (dmx >= 0.0 && ky0 - 2.0 > (cy - dmx * hy) && ky1 + 2.0 < (cy + dmx * hy)) {
+    wy0 = ky0 < 0 ? 0 : ky0;
+    wy1 = ky1 > h - 1 ? h - 1 : ky1;
+  } else {
+    gsr_window_range(h, y, dmax, wy0, wy1, py_tab);
+  }
+  if (wx0 > wx1 || wy0 > wy1) return o;
   // "binds": on some side the window is tighter than both the k-sigma box and the image edge.
   o.binds = (wx0 > (kx0 > 0 ? kx0 : 0)) || (wx1 < (kx1 < w - 1 ? kx1 : w - 1)) ||
             (wy0 > (ky0 > 0 ? ky0 : 0)) || (wy1 < (ky1 < h - 1 ? ky1 : h - 1));
@@ -207,17 +221,57 @@ GSR_HD GsrRec gsr_make_rec(float sx, float sy, float rho, float x, float y, floa
 // Per band of REGION rows: the ellipse's x-interval at row dy is centred on m(dy) = -b/(2a)*dy
 // with half-width sqrt((ecut - c' dy^2)/a), c' = c - b^2/(4a); over a band we take the hull of
 // the two end-row centres widened by the largest half-width in the band.
-GSR_HD uint32_t gsr_region_mask(const GsrRec& g, int bx0, int bx1, int by0, int by1, int tx0,
-                                int ty0, int h, int w, float ecut) {
-  constexpr int NR = GSR_NRX;
+struct GsrEllipse {
+  float cx, cy;     // centre, pixels
+  float inv_a;      // 1 / (conic a in pixel units), < 0
+  float kappa;      // ridge slope dx/dy
+  float cp;         // c - b^2/(4a) in pixel units, <= 0
+};
+
+GSR_HD GsrEllipse gsr_ellipse(const GsrRec& g, int h, int w) {
   const float hxs = 0.5f * (float)(w - 1), hys = 0.5f * (float)(h - 1);
   const float gx = 1.0f / hxs, gy = 1.0f / hys;  // normalised units per pixel
-  const float cx = (g.x + 1.0f) * hxs, cy = (g.y + 1.0f) * hys;
-  // conic in pixel units
-  const float a = g.a * gx * gx, b = g.b * gx * gy, c = g.c * gy * gy;
-  const float inv_a = 1.0f / a;                 // a < 0
-  const float kappa = -0.5f * b * inv_a;        // ridge slope dx/dy
-  const float cp = c + 0.5f * kappa * b;        // c - b^2/(4a)  (<= 0)
+  GsrEllipse e;
+  e.cx = (g.x + 1.0f) * hxs;
+  e.cy = (g.y + 1.0f) * hys;
+  const float a = g.a * gx * gx, b = g.b * gx * gy, c = g.c * gy * gy;  // conic in pixel units
+  e.inv_a = 1.0f / a;
+  e.kappa = -0.5f * b * e.inv_a;
+  e.cp = c + 0.5f * e.kappa * b;
+  return e;
+}
+
+// Conservative pixel x-range [xl, xh] of {E >= ecut} over the rows ya..yb (inclusive, already
+// clipped to the cull box), clipped to [cx0, cx1].  Returns false if the band is empty.
+GSR_HD bool gsr_band_xrange(const GsrEllipse& e, float ecut, int ya, int yb, int cx0, int cx1,
+                            int& xl, int& xh) {
+  const float da = (float)ya - e.cy, db = (float)yb - e.cy;
+  // row offset in the band closest to the centre row, shrunk by the pad so that rounding of cy
+  // can only widen the band
+  float t = da > 0.0f ? da : (db < 0.0f ? db : 0.0f);
+  t = t > 0.0f ? fmaxf(t - GSR_CULL_PAD_PX, 0.0f) : fminf(t + GSR_CULL_PAD_PX, 0.0f);
+  float w2 = (ecut - e.cp * t * t) * e.inv_a;
+  if (!(w2 >= 0.0f)) {
+    if (w2 < 0.0f) return false;  // band entirely outside the ellipse
+    w2 = 3.0e38f;                 // NaN/inf from a degenerate conic: do not cull
+  }
+  const float hw = sqrtf(w2) + GSR_CULL_PAD_PX + 1.0e-6f * fabsf(e.cx);  // fp32 slack on cx
+  const float ma = e.cx + e.kappa * da, mb = e.cx + e.kappa * db;
+  float lo = fminf(ma, mb) - hw, hi = fmaxf(ma, mb) + hw;
+  if (!(lo == lo) || !(hi == hi)) {
+    lo = -3.0e38f;
+    hi = 3.0e38f;
+  }
+  lo = fmaxf(lo, (float)cx0);
+  hi = fminf(hi, (float)cx1);
+  xl = (int)ceilf(lo);
+  xh = (int)floorf(hi);
+  return xl <= xh;
+}
+
+GSR_HD uint32_t gsr_region_mask(const GsrRec& g, int bx0, int bx1, int by0, int by1, int tx0,
+                                int ty0, int h, int w, float ecut) {
+  const GsrEllipse e = gsr_ellipse(g, h, w);
   uint32_t mask = 0;
   const int cx0 = bx0 > tx0 ? bx0 : tx0;
   const int cx1 = bx1 < tx0 + GSR_TILE_W - 1 ? bx1 : tx0 + GSR_TILE_W - 1;
@@ -228,30 +282,11 @@ GSR_HD uint32_t gsr_region_mask(const GsrRec& g, int bx0, int bx1, int by0, int 
     ya = ya > by0 ? ya : by0;
     yb = yb < by1 ? yb : by1;
     if (ya > yb) continue;
-    const float da = (float)ya - cy, db = (float)yb - cy;
-    // row offset in the band closest to the centre row
-    float t = da > 0.0f ? da : (db < 0.0f ? db : 0.0f);
-    // shrink |t| by the pad so rounding of cy can only widen the band
-    t = t > 0.0f ? fmaxf(t - GSR_CULL_PAD_PX, 0.0f) : fminf(t + GSR_CULL_PAD_PX, 0.0f);
-    float w2 = (ecut - cp * t * t) * inv_a;
-    if (!(w2 >= 0.0f)) {
-      if (w2 < 0.0f) continue;   // band entirely outside the ellipse
-      w2 = 3.0e38f;              // NaN/inf from a degenerate conic: do not cull
-    }
-    const float hw = sqrtf(w2) + GSR_CULL_PAD_PX + 1.0e-6f * fabsf(cx);  // fp32 slack on cx
-    const float ma = cx + kappa * da, mb = cx + kappa * db;
-    float lo = fminf(ma, mb) - hw, hi = fmaxf(ma, mb) + hw;
-    if (!(lo == lo) || !(hi == hi)) {
-      lo = -3.0e38f;
-      hi = 3.0e38f;
-    }
-    lo = fmaxf(lo, (float)cx0);
-    hi = fminf(hi, (float)cx1);
-    int xl = (int)ceilf(lo), xh = (int)floorf(hi);
-    if (xl > xh) continue;
-    int r0 = (xl - tx0) / GSR_REGION, r1 = (xh - tx0) / GSR_REGION;
-    uint32_t bits = ((2u << r1) - 1u) & ~((1u << r0) - 1u);
-    mask |= bits << (ry * NR);
+    int xl, xh;
+    if (!gsr_band_xrange(e, ecut, ya, yb, cx0, cx1, xl, xh)) continue;
+    const int r0 = (xl - tx0) / GSR_REGION, r1 = (xh - tx0) / GSR_REGION;
+    const uint32_t bits = ((2u << r1) - 1u) & ~((1u << r0) - 1u);
+    mask |= bits << (ry * GSR_NRX);
   }
   return mask;
 }

@@ -55,6 +55,33 @@ __device__ __forceinline__ float gsr_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Packed FP32x2 arithmetic (sm_100: FFMA2 / FADD2, one issue slot for two lanes of work; ptxas uses
+// the scalar-broadcast operand form when both halves of a pair are the same register).
+typedef unsigned long long gsr_f2;
+__device__ __forceinline__ gsr_f2 gsr_pk(float lo, float hi) {
+  gsr_f2 r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void gsr_upk(gsr_f2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ gsr_f2 gsr_fma2(gsr_f2 a, gsr_f2 b, gsr_f2 c) {
+  gsr_f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ gsr_f2 gsr_add2(gsr_f2 a, gsr_f2 b) {
+  gsr_f2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// One Gaussian against this lane's two pixels: 1 FADD + 3 FMUL (row terms), FADD2 (dx pair),
+// 2 FFMA2 (exponent pair), 2 MUFU.EX2, 3 FFMA2 (colour accumulate).  px2 = {px0, px1}.
+__device__ __forceinline__ void gsr_eval_pair(uint32_t addr, gsr_f2 px2, float py, bool in0, bool in1,
+                                              gsr_f2& accr, gsr_f2& accg, gsr_f2& accb);
+
 __device__ __forceinline__ uint32_t gsr_smem_addr(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -70,6 +97,25 @@ __device__ __forceinline__ void gsr_cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
+__device__ __forceinline__ void gsr_eval_pair(uint32_t addr, gsr_f2 px2, float py, bool in0, bool in1,
+                                              gsr_f2& accr, gsr_f2& accg, gsr_f2& accb) {
+  const float4 a0 = gsr_lds128(addr);       // x, y, a, b
+  const float4 a1 = gsr_lds128(addr + 16);  // c, r, g, bl
+  const float dy = py - a0.y;
+  const float t1 = a0.w * dy;
+  const float t0 = a1.x * dy * dy;
+  const gsr_f2 dx2 = gsr_add2(px2, gsr_pk(-a0.x, -a0.x));
+  const gsr_f2 e2 = gsr_fma2(dx2, gsr_fma2(gsr_pk(a0.z, a0.z), dx2, gsr_pk(t1, t1)), gsr_pk(t0, t0));
+  float e0, e1;
+  gsr_upk(e2, e0, e1);
+  const float v0 = in0 ? gsr_ex2(e0) : 0.f;
+  const float v1 = in1 ? gsr_ex2(e1) : 0.f;
+  const gsr_f2 v2 = gsr_pk(v0, v1);
+  accr = gsr_fma2(v2, gsr_pk(a1.y, a1.y), accr);
+  accg = gsr_fma2(v2, gsr_pk(a1.z, a1.z), accg);
+  accb = gsr_fma2(v2, gsr_pk(a1.w, a1.w), accb);
+}
+
 struct GsrFwdArgs {
   const GsrRec* rec;
   const uint2* box;
@@ -81,6 +127,14 @@ struct GsrFwdArgs {
   int h, w, nbx, nby, nb;
   float ecut;
   uint32_t flags;
+  const int* guard;  // run only if *guard == want (nullptr: always)
+  int want;
+  // tile-list path
+  const int* tile_off;
+  const uint2* entries;
+  const GsrRec* rec_in;
+  const uint2* box_in;
+  int ntx;
 };
 
 // Builds the table of candidate runs for a pixel rectangle [x0,x1]x[y0,y1] (inclusive):
@@ -125,13 +179,52 @@ __device__ __forceinline__ void gsr_build_runs(const int* __restrict__ bin_off,
   }
 }
 
-__global__ void __launch_bounds__(GSR_FWD_THREADS, GSR_CFG_MIN_CTAS) gsr_forward_kernel(GsrFwdArgs p) {
+// One write (or read-modify-write: the reference accumulates into rendered_img) per pixel.
+__device__ __forceinline__ void gsr_fwd_writeout(const GsrFwdArgs& p, int hi, int wi0, float r0,
+                                                 float g0, float b0, float r1, float g1, float b1) {
+  if (hi < p.h) {
+    const bool over = (p.flags & 1u) != 0;
+    if (p.flags & 2u) {  // CHW
+      const size_t plane = (size_t)p.h * p.w;
+      float* o = p.img + (size_t)hi * p.w + wi0;
+      if (wi0 < p.w) {
+        o[0] = over ? r0 : o[0] + r0;
+        o[plane] = over ? g0 : o[plane] + g0;
+        o[2 * plane] = over ? b0 : o[2 * plane] + b0;
+      }
+      if (wi0 + 1 < p.w) {
+        o[1] = over ? r1 : o[1] + r1;
+        o[plane + 1] = over ? g1 : o[plane + 1] + g1;
+        o[2 * plane + 1] = over ? b1 : o[2 * plane + 1] + b1;
+      }
+    } else {  // HWC: 6 contiguous floats per lane
+      float* o = p.img + ((size_t)hi * p.w + wi0) * 3;
+      if (wi0 < p.w) {
+        o[0] = over ? r0 : o[0] + r0;
+        o[1] = over ? g0 : o[1] + g0;
+        o[2] = over ? b0 : o[2] + b0;
+      }
+      if (wi0 + 1 < p.w) {
+        o[3] = over ? r1 : o[3] + r1;
+        o[4] = over ? g1 : o[4] + g1;
+        o[5] = over ? b1 : o[5] + b1;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GSR_FWD_THREADS, GSR_CFG_MIN_CTAS) gsr_forward_bins_kernel(GsrFwdArgs p) {
+  if (gsr_guard_skip(p.guard, p.want)) return;
   extern __shared__ __align__(16) unsigned char gsr_smem_raw[];
   GsrFwdSmem& sm = *reinterpret_cast<GsrFwdSmem*>(gsr_smem_raw);
   constexpr int NR = GSR_NRX;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tx0 = blockIdx.x * GSR_TILE_W, ty0 = blockIdx.y * GSR_TILE_H;
   const unsigned lt_mask = (1u << lane) - 1u;
+  // persistent over tiles: the grid is capped so that a guarded no-op launch stays cheap
+  const int ntx_ = (p.w + GSR_TILE_W - 1) / GSR_TILE_W, nty_ = (p.h + GSR_TILE_H - 1) / GSR_TILE_H;
+  for (int tile = blockIdx.x; tile < ntx_ * nty_; tile += gridDim.x) {
+  const int tx0 = (tile % ntx_) * GSR_TILE_W, ty0 = (tile / ntx_) * GSR_TILE_H;
+  __syncthreads();  // shared memory of the previous tile is free
 
   // this thread's two pixels
   const int wi0 = tx0 + (warp % NR) * GSR_REGION + (lane & 3) * 2;
@@ -139,7 +232,8 @@ __global__ void __launch_bounds__(GSR_FWD_THREADS, GSR_CFG_MIN_CTAS) gsr_forward
   const float px0 = __ldg(p.px_tab + min(wi0, p.w - 1));
   const float px1 = __ldg(p.px_tab + min(wi0 + 1, p.w - 1));
   const float py = __ldg(p.py_tab + min(hi, p.h - 1));
-  float r0 = 0.f, g0 = 0.f, b0 = 0.f, r1 = 0.f, g1 = 0.f, b1 = 0.f;
+  gsr_f2 accr = gsr_pk(0.f, 0.f), accg = gsr_pk(0.f, 0.f), accb = gsr_pk(0.f, 0.f);
+  const gsr_f2 px2 = gsr_pk(px0, px1);
 
   if (warp == 0)
     gsr_build_runs(p.bin_off, p.stats, p.nbx, p.nby, p.nb, tx0, tx0 + GSR_TILE_W - 1, ty0,
@@ -243,23 +337,7 @@ __global__ void __launch_bounds__(GSR_FWD_THREADS, GSR_CFG_MIN_CTAS) gsr_forward
 
     // ---------------- stage C: every warp walks its region's lists -----------------------------
     auto eval = [&](uint32_t addr, const bool in0, const bool in1) {
-      const float4 a0 = gsr_lds128(addr);
-      const float4 a1 = gsr_lds128(addr + 16);
-      const float dy = py - a0.y;
-      const float t1 = a0.w * dy;
-      const float t0 = a1.x * dy * dy;
-      const float dx0 = px0 - a0.x;
-      const float dx1 = px1 - a0.x;
-      const float e0 = fmaf(dx0, fmaf(a0.z, dx0, t1), t0);
-      const float e1 = fmaf(dx1, fmaf(a0.z, dx1, t1), t0);
-      const float v0 = in0 ? gsr_ex2(e0) : 0.f;
-      const float v1 = in1 ? gsr_ex2(e1) : 0.f;
-      r0 = fmaf(v0, a1.y, r0);
-      g0 = fmaf(v0, a1.z, g0);
-      b0 = fmaf(v0, a1.w, b0);
-      r1 = fmaf(v1, a1.y, r1);
-      g1 = fmaf(v1, a1.z, g1);
-      b1 = fmaf(v1, a1.w, b1);
+      gsr_eval_pair(addr, px2, py, in0, in1, accr, accg, accb);
     };
     auto eval_slow = [&](int slot) {  // dmax window cuts this Gaussian: exact inclusion per pixel
       int bx0, bx1, by0, by1;
@@ -289,34 +367,130 @@ __global__ void __launch_bounds__(GSR_FWD_THREADS, GSR_CFG_MIN_CTAS) gsr_forward
     __syncthreads();  // segments and list are reused by the next round
   }
 
-  // ---------------- write-out ----------------
-  if (hi < p.h) {
-    const bool over = (p.flags & 1u) != 0;
-    if (p.flags & 2u) {  // CHW
-      const size_t plane = (size_t)p.h * p.w;
-      float* o = p.img + (size_t)hi * p.w + wi0;
-      if (wi0 < p.w) {
-        o[0] = over ? r0 : o[0] + r0;
-        o[plane] = over ? g0 : o[plane] + g0;
-        o[2 * plane] = over ? b0 : o[2 * plane] + b0;
+  {
+    float r0, r1, g0, g1, b0, b1;
+    gsr_upk(accr, r0, r1);
+    gsr_upk(accg, g0, g1);
+    gsr_upk(accb, b0, b1);
+    gsr_fwd_writeout(p, hi, wi0, r0, g0, b0, r1, g1, b1);
+  }
+  }  // tile loop
+}
+
+// ---- tile-list forward kernel (the fast path) ---------------------------------------------------
+// One CTA per 32x16 tile, one warp per 8x8 region, two pixels per lane.  The tile's entries
+// {Gaussian index, region mask} were produced by the set-up pipeline; per round of
+// GSR_FL_CHUNK entries every lane takes GSR_FL_PER_LANE of them, gathers the 32-byte records
+// (and, for window-binding Gaussians, the cull boxes) into shared memory with cp.async and
+// appends the slot to its warp's list for every region of the mask (ranks from ballots, no
+// atomics).  After one barrier each warp walks the lists left for its region.
+constexpr int GSR_FL_THREADS = 32 * GSR_NRX * GSR_NRY;
+constexpr int GSR_FL_WARPS = GSR_FL_THREADS / 32;
+#ifndef GSR_CFG_FL_PER_LANE
+#define GSR_CFG_FL_PER_LANE 2
+#endif
+constexpr int GSR_FL_PER_LANE = GSR_CFG_FL_PER_LANE;
+constexpr int GSR_FL_PER_WARP = 32 * GSR_FL_PER_LANE;
+constexpr int GSR_FL_CHUNK = GSR_FL_THREADS * GSR_FL_PER_LANE;
+#ifndef GSR_CFG_FL_MIN_CTAS
+#define GSR_CFG_FL_MIN_CTAS 4
+#endif
+
+struct GsrFwdListSmem {
+  float4 rec[GSR_FL_CHUNK * 2];
+  uint2 box[GSR_FL_CHUNK];
+  uint16_t lfast[GSR_FL_WARPS][GSR_FL_WARPS][GSR_FL_PER_WARP];  // [producer warp][region]
+  uint16_t lslow[GSR_FL_WARPS][GSR_FL_WARPS][GSR_FL_PER_WARP];
+  uint8_t nfast[GSR_FL_WARPS][GSR_FL_WARPS];
+  uint8_t nslow[GSR_FL_WARPS][GSR_FL_WARPS];
+};
+
+__global__ void __launch_bounds__(GSR_FL_THREADS, GSR_CFG_FL_MIN_CTAS) gsr_forward_list_kernel(GsrFwdArgs p) {
+  if (gsr_guard_skip(p.guard, p.want)) return;
+  __shared__ GsrFwdListSmem sm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx0 = blockIdx.x * GSR_TILE_W, ty0 = blockIdx.y * GSR_TILE_H;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int wi0 = tx0 + (warp % GSR_NRX) * GSR_REGION + (lane & 3) * 2;
+  const int hi = ty0 + (warp / GSR_NRX) * GSR_REGION + (lane >> 2);
+  const float px0 = __ldg(p.px_tab + min(wi0, p.w - 1));
+  const float px1 = __ldg(p.px_tab + min(wi0 + 1, p.w - 1));
+  const float py = __ldg(p.py_tab + min(hi, p.h - 1));
+  gsr_f2 accr = gsr_pk(0.f, 0.f), accg = gsr_pk(0.f, 0.f), accb = gsr_pk(0.f, 0.f);
+  const gsr_f2 px2 = gsr_pk(px0, px1);
+  const int tile = blockIdx.y * p.ntx + blockIdx.x;
+  const int e_begin = __ldg(p.tile_off + tile), e_end = __ldg(p.tile_off + tile + 1);
+  const uint32_t rec_s = gsr_smem_addr(sm.rec);
+  const uint32_t box_s = gsr_smem_addr(sm.box);
+
+  auto eval = [&](uint32_t addr, const bool in0, const bool in1) {
+    gsr_eval_pair(addr, px2, py, in0, in1, accr, accg, accb);
+  };
+
+  for (int e0 = e_begin; e0 < e_end; e0 += GSR_FL_CHUNK) {
+    // ---- stage A: gather records, build the region lists ----
+    int cf[GSR_FL_WARPS], cs[GSR_FL_WARPS];
+#pragma unroll
+    for (int rg = 0; rg < GSR_FL_WARPS; ++rg) cf[rg] = cs[rg] = 0;
+#pragma unroll
+    for (int k = 0; k < GSR_FL_PER_LANE; ++k) {
+      const int slot = warp * GSR_FL_PER_WARP + k * 32 + lane;
+      uint32_t m = 0;
+      bool binds = false;
+      if (e0 + slot < e_end) {
+        const uint2 en = __ldg(p.entries + e0 + slot);
+        m = en.y & 0xffffu;
+        binds = (en.y & 0x10000u) != 0;
+        const float4* src = reinterpret_cast<const float4*>(p.rec_in + en.x);
+        gsr_cp_async16(rec_s + slot * 32, src);
+        gsr_cp_async16(rec_s + slot * 32 + 16, src + 1);
+        if (binds) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(box_s + slot * 8), "l"(p.box_in + en.x) : "memory");
       }
-      if (wi0 + 1 < p.w) {
-        o[1] = over ? r1 : o[1] + r1;
-        o[plane + 1] = over ? g1 : o[plane + 1] + g1;
-        o[2 * plane + 1] = over ? b1 : o[2 * plane + 1] + b1;
-      }
-    } else {  // HWC: 6 contiguous floats per lane
-      float* o = p.img + ((size_t)hi * p.w + wi0) * 3;
-      if (wi0 < p.w) {
-        o[0] = over ? r0 : o[0] + r0;
-        o[1] = over ? g0 : o[1] + g0;
-        o[2] = over ? b0 : o[2] + b0;
-      }
-      if (wi0 + 1 < p.w) {
-        o[3] = over ? r1 : o[3] + r1;
-        o[4] = over ? g1 : o[4] + g1;
-        o[5] = over ? b1 : o[5] + b1;
+#pragma unroll
+      for (int rg = 0; rg < GSR_FL_WARPS; ++rg) {
+        const bool bit = (m >> rg) & 1u;
+        const unsigned balf = __ballot_sync(0xffffffffu, bit && !binds);
+        const unsigned bals = __ballot_sync(0xffffffffu, bit && binds);
+        if (bit) {
+          if (!binds) sm.lfast[warp][rg][cf[rg] + __popc(balf & lt_mask)] = (uint16_t)slot;
+          else sm.lslow[warp][rg][cs[rg] + __popc(bals & lt_mask)] = (uint16_t)slot;
+        }
+        cf[rg] += __popc(balf);
+        cs[rg] += __popc(bals);
       }
     }
+#pragma unroll
+    for (int rg = 0; rg < GSR_FL_WARPS; ++rg)
+      if (lane == rg) {
+        sm.nfast[warp][rg] = (uint8_t)cf[rg];
+        sm.nslow[warp][rg] = (uint8_t)cs[rg];
+      }
+    gsr_cp_async_wait_all();
+    __syncthreads();
+    // ---- stage C: walk the lists every producer warp left for this region ----
+    for (int pw = 0; pw < GSR_FL_WARPS; ++pw) {
+      const int nf = sm.nfast[pw][warp];
+      const uint16_t* lf = sm.lfast[pw][warp];
+#pragma unroll 2
+      for (int i = 0; i < nf; ++i) eval(rec_s + ((uint32_t)lf[i] << 5), true, true);
+      const int ns = sm.nslow[pw][warp];
+      const uint16_t* ls = sm.lslow[pw][warp];
+      for (int i = 0; i < ns; ++i) {  // dmax window cuts this Gaussian: exact inclusion per pixel
+        const int slot = ls[i];
+        int bx0, bx1, by0, by1;
+        bool binds;
+        gsr_box_unpack(sm.box[slot], bx0, bx1, by0, by1, binds);
+        const bool iny = hi >= by0 && hi <= by1;
+        eval(rec_s + (slot << 5), iny && wi0 >= bx0 && wi0 <= bx1, iny && wi0 + 1 >= bx0 && wi0 + 1 <= bx1);
+      }
+    }
+    __syncthreads();
+  }
+  {
+    float r0, r1, g0, g1, b0, b1;
+    gsr_upk(accr, r0, r1);
+    gsr_upk(accg, g0, g1);
+    gsr_upk(accb, b0, b1);
+    gsr_fwd_writeout(p, hi, wi0, r0, g0, b0, r1, g1, b1);
   }
 }

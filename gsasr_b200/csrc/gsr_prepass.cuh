@@ -1,34 +1,57 @@
-// gsr_prepass.cuh -- O(N) set-up pipeline shared by forward and backward:
+// gsr_prepass.cuh -- O(N) set-up pipelines shared by forward and backward.
 //
-//   K1 gsr_bin_kernel     per Gaussian: exact dmax window /\ k-sigma box -> cull box, home bin,
-//                         rank inside the bin (atomic), global reach statistics; also fills the
-//                         pixel coordinate tables (the reference's double-precision rule).
-//   K2 gsr_scan_kernel    exclusive scan of the bin histogram (decoupled look-back, one CTA per
-//                         4096 bins).
-//   K3 gsr_scatter_kernel counting-sort scatter: writes the 32 B raster record, the packed
-//                         cull box and the original index at offset[bin] + rank.
+// Tile-list pipeline (forward fast path):
+//   T1 gsr_tile_count_kernel  per Gaussian: exact dmax window /\ k-sigma box -> cull box, raster
+//                             record (written in input order), and for every 32x16 tile the box
+//                             touches the ellipse-vs-region mask; one RED per (Gaussian,tile) pair.
+//   T2 gsr_scan_kernel        exclusive scan of the tile histogram; raises the overflow flag when
+//                             the pairs do not fit the entry capacity (8 per Gaussian).
+//   T3 gsr_tile_fill_kernel   recomputes the masks and writes the 8-byte entries {index, mask}
+//                             at cursor[tile]++.
+//   The forward kernel then streams each tile's entries and gathers the 32-byte records.
 //
-// After K3 the Gaussians of one home bin are contiguous, bins are row-major, and the
-// "large" Gaussians (cull box half-extent > GSR_LARGE_PX) form one extra bin at the end.
-// Memory is bounded by sizes alone (no data-dependent list lengths, no host sync).
+// Home-bin pipeline (backward; forward fallback when the tile lists overflow their capacity):
+//   K1 gsr_bin_kernel     per Gaussian: cull box, home bin, rank inside the bin (atomic), reach.
+//   K2 gsr_scan_kernel    exclusive scan of the bin histogram.
+//   K3 gsr_scatter_kernel counting-sort scatter: 32 B record, packed cull box, original index at
+//                         offset[bin] + rank.  Bins are row-major; Gaussians whose cull box reaches
+//                         further than GSR_LARGE_PX form one extra bin at the end.
+//
+// Memory is bounded by sizes alone (no data-dependent allocation, no host sync): the choice between
+// the two forward paths is made ON THE DEVICE through stats[GSR_STAT_OVERFLOW]; kernels of the path
+// not taken return at once (`guard`).
 #pragma once
 #include "gsr_common.cuh"
 
+constexpr int GSR_STAT_EXT_X = 0, GSR_STAT_EXT_Y = 1, GSR_STAT_OVERFLOW = 2, GSR_STAT_ENTRIES = 3;
+constexpr int GSR_ENTRIES_PER_GAUSSIAN = 8;  // tile-entry capacity = 8 * N + 256
+
 struct GsrWorkspace {
-  int* bin_count;   // nb + 1        (zeroed per call, contiguous with stats and scan_state)
-  int* stats;       // 8 ints        [0] max ext_x (small), [1] max ext_y (small)
-  int* scan_state;  // 2 * nscan     per scan CTA: [2b] = ready flag, [2b+1] = CTA total
-  int nscan;        // CTAs of the scan kernel
-  size_t zero_bytes;  // bytes of the block cleared per call
-  int* bin_off;     // nb + 2        exclusive offsets; [nb] = start of large, [nb+1] = n_live
-  float* px_tab;    // w
-  float* py_tab;    // h
-  uint2* box_tmp;   // s   (unsorted)
-  int2* keyrank;    // s   (unsorted)  key = bin id, -1 = skipped
-  GsrRec* rec;      // s   (sorted)
-  uint2* box;       // s   (sorted)
-  int* ids;         // s   (sorted -> original index)
-  int nbx, nby, nb;
+  // ---- one block, cleared per call ----
+  int* bin_count;    // nb + 1
+  int* stats;        // 8 ints, see GSR_STAT_*
+  int* scan_state;   // 2 * nscan     look-back state of the bin scan
+  int* tile_count;   // nt
+  int* tscan_state;  // 2 * ntscan    look-back state of the tile scan
+  size_t zero_bytes;
+  // ---- tile-list pipeline ----
+  int* tile_off;     // nt + 1   exclusive offsets
+  int* tile_cur;     // nt + 1   fill cursors (copy of the offsets)
+  GsrRec* rec_in;    // s        records, input order
+  uint2* box_in;     // s        packed cull boxes, input order (x0 > x1: skipped Gaussian)
+  uint2* entries;    // ecap     {Gaussian index, region mask | binds << 16}
+  int ntx, nty, nt, ntscan, ecap;
+  // ---- home-bin pipeline ----
+  int* bin_off;      // nb + 2   exclusive offsets; [nb] = start of large, [nb+1] = n_live
+  uint2* box_tmp;    // s   (unsorted)
+  int2* keyrank;     // s   (unsorted)  key = bin id, -1 = skipped
+  GsrRec* rec;       // s   (sorted)
+  uint2* box;        // s   (sorted)
+  int* ids;          // s   (sorted -> original index)
+  int nbx, nby, nb, nscan;
+  // ---- both ----
+  float* px_tab;     // w
+  float* py_tab;     // h
   size_t bytes;
 };
 
@@ -42,6 +65,9 @@ static inline GsrWorkspace gsr_carve(void* base, int s, int h, int w) {
   ws.nbx = (w + GSR_BIN - 1) / GSR_BIN;
   ws.nby = (h + GSR_BIN - 1) / GSR_BIN;
   ws.nb = ws.nbx * ws.nby;
+  ws.ntx = (w + GSR_TILE_W - 1) / GSR_TILE_W;
+  ws.nty = (h + GSR_TILE_H - 1) / GSR_TILE_H;
+  ws.nt = ws.ntx * ws.nty;
   size_t off = 0;
   char* p = (char*)base;
   auto take = [&](size_t bytes) {
@@ -50,12 +76,21 @@ static inline GsrWorkspace gsr_carve(void* base, int s, int h, int w) {
     return (void*)r;
   };
   const size_t sn = (size_t)(s > 0 ? s : 1);
-  // bin_count, stats and scan_state are contiguous: they are cleared by one memset.
   ws.nscan = (ws.nb + 1 + GSR_SCAN_CHUNK - 1) / GSR_SCAN_CHUNK;
-  ws.zero_bytes = ((size_t)ws.nb + 1 + 8 + 2 * (size_t)ws.nscan) * sizeof(int);
+  ws.ntscan = (ws.nt + GSR_SCAN_CHUNK - 1) / GSR_SCAN_CHUNK;
+  ws.zero_bytes = ((size_t)ws.nb + 1 + 8 + 2 * (size_t)ws.nscan + (size_t)ws.nt + 2 * (size_t)ws.ntscan) * sizeof(int);
   ws.bin_count = (int*)take(ws.zero_bytes);
   ws.stats = ws.bin_count ? ws.bin_count + ws.nb + 1 : nullptr;
   ws.scan_state = ws.bin_count ? ws.stats + 8 : nullptr;
+  ws.tile_count = ws.bin_count ? ws.scan_state + 2 * ws.nscan : nullptr;
+  ws.tscan_state = ws.bin_count ? ws.tile_count + ws.nt : nullptr;
+  ws.tile_off = (int*)take(((size_t)ws.nt + 1) * sizeof(int));
+  ws.tile_cur = (int*)take(((size_t)ws.nt + 1) * sizeof(int));
+  ws.rec_in = (GsrRec*)take(sn * sizeof(GsrRec));
+  ws.box_in = (uint2*)take(sn * sizeof(uint2));
+  const size_t ecap = (size_t)GSR_ENTRIES_PER_GAUSSIAN * (size_t)(s > 0 ? s : 0) + 256;
+  ws.ecap = (int)(ecap > 0x7fffff00u ? 0x7fffff00u : ecap);
+  ws.entries = (uint2*)take((size_t)ws.ecap * sizeof(uint2));
   ws.bin_off = (int*)take(((size_t)ws.nb + 2) * sizeof(int));
   ws.px_tab = (float*)take((size_t)w * sizeof(float));
   ws.py_tab = (float*)take((size_t)h * sizeof(float));
@@ -68,12 +103,15 @@ static inline GsrWorkspace gsr_carve(void* base, int s, int h, int w) {
   return ws;
 }
 
-__global__ void __launch_bounds__(256)
-gsr_bin_kernel(const float* __restrict__ sigmas, const float* __restrict__ coords,
-               const float* __restrict__ colors, int s, int h, int w, float dmax, float ksigma,
-               GsrWorkspace ws) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= s) return;
+// A kernel of the path not taken returns at once: guard == nullptr means "always run".
+__device__ __forceinline__ bool gsr_guard_skip(const int* guard, int want) {
+  return guard != nullptr && *(const volatile int*)guard != want;
+}
+
+__device__ __forceinline__ void gsr_bin_one(const float* __restrict__ sigmas,
+                                            const float* __restrict__ coords,
+                                            const float* __restrict__ colors, int i, int h, int w,
+                                            float dmax, float ksigma, const GsrWorkspace& ws) {
   const float sx = __ldg(sigmas + 3 * (size_t)i + 0);
   const float sy = __ldg(sigmas + 3 * (size_t)i + 1);
   const float rho = __ldg(sigmas + 3 * (size_t)i + 2);
@@ -100,9 +138,19 @@ gsr_bin_kernel(const float* __restrict__ sigmas, const float* __restrict__ coord
   const int ex = __reduce_max_sync(act, small ? st.ext_x : 0);
   const int ey = __reduce_max_sync(act, small ? st.ext_y : 0);
   if ((threadIdx.x & 31) == (__ffs(act) - 1)) {
-    if (ex > *(volatile int*)(ws.stats + 0)) atomicMax(ws.stats + 0, ex);
-    if (ey > *(volatile int*)(ws.stats + 1)) atomicMax(ws.stats + 1, ey);
+    if (ex > *(volatile int*)(ws.stats + 0)) atomicMax(ws.stats + GSR_STAT_EXT_X, ex);
+    if (ey > *(volatile int*)(ws.stats + 1)) atomicMax(ws.stats + GSR_STAT_EXT_Y, ey);
   }
+}
+
+// Grid-stride: a guarded launch of the path not taken uses a small grid and costs ~2 us.
+__global__ void __launch_bounds__(256)
+gsr_bin_kernel(const float* __restrict__ sigmas, const float* __restrict__ coords,
+               const float* __restrict__ colors, int s, int h, int w, float dmax, float ksigma,
+               GsrWorkspace ws, const int* guard, int want) {
+  if (gsr_guard_skip(guard, want)) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s; i += gridDim.x * blockDim.x)
+    gsr_bin_one(sigmas, coords, colors, i, h, w, dmax, ksigma, ws);
 }
 
 // Pixel coordinate tables: the reference's rule (gs.cu:39,46), evaluated once per axis entry.
@@ -131,9 +179,14 @@ __device__ __forceinline__ int gsr_block_sum_1024(int v, int* warp_sums) {
   return t;
 }
 
+// Optional extras: `cur` receives a copy of the offsets (fill cursors); when cap >= 0 the last CTA
+// stores the grand total in stats[GSR_STAT_ENTRIES] and raises stats[GSR_STAT_OVERFLOW] if it
+// exceeds cap.
 __global__ void __launch_bounds__(1024) gsr_scan_kernel(const int* __restrict__ count,
-                                                        int* __restrict__ off, int n,
-                                                        int* state) {
+                                                        int* __restrict__ off, int* __restrict__ cur,
+                                                        int n, int* state, int cap, int* stats,
+                                                        const int* guard, int want) {
+  if (gsr_guard_skip(guard, want)) return;
   __shared__ int warp_sums[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
   const int i0 = b * GSR_SCAN_CHUNK + tid * 4;
@@ -179,17 +232,25 @@ __global__ void __launch_bounds__(1024) gsr_scan_kernel(const int* __restrict__ 
   int run = carry + in_cta;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    if (i0 + k < n) off[i0 + k] = run;
+    if (i0 + k < n) {
+      off[i0 + k] = run;
+      if (cur) cur[i0 + k] = run;
+    }
     run += v[k];
   }
-  if (b == gridDim.x - 1 && tid == 1023) off[n] = run;
+  if (b == gridDim.x - 1 && tid == 1023) {
+    off[n] = run;
+    if (cap >= 0) {
+      stats[GSR_STAT_ENTRIES] = run;
+      if (run > cap) stats[GSR_STAT_OVERFLOW] = 1;
+    }
+  }
 }
 
-__global__ void __launch_bounds__(256)
-gsr_scatter_kernel(const float* __restrict__ sigmas, const float* __restrict__ coords,
-                   const float* __restrict__ colors, int s, GsrWorkspace ws) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= s) return;
+__device__ __forceinline__ void gsr_scatter_one(const float* __restrict__ sigmas,
+                                                const float* __restrict__ coords,
+                                                const float* __restrict__ colors, int i,
+                                                const GsrWorkspace& ws) {
   const int2 kr = ws.keyrank[i];
   if (kr.x < 0) return;
   const int dst = __ldg(ws.bin_off + kr.x) + kr.y;
@@ -207,4 +268,190 @@ gsr_scatter_kernel(const float* __restrict__ sigmas, const float* __restrict__ c
   dr[1] = make_float4(r.c, r.r, r.g, r.bl);
   ws.box[dst] = ws.box_tmp[i];
   ws.ids[dst] = i;
+}
+
+__global__ void __launch_bounds__(256)
+gsr_scatter_kernel(const float* __restrict__ sigmas, const float* __restrict__ coords,
+                   const float* __restrict__ colors, int s, GsrWorkspace ws, const int* guard,
+                   int want) {
+  if (gsr_guard_skip(guard, want)) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s; i += gridDim.x * blockDim.x)
+    gsr_scatter_one(sigmas, coords, colors, i, ws);
+}
+
+// ---- tile-list pipeline -------------------------------------------------------------------------
+// Calls f(tile id, region mask) for every tile whose regions the Gaussian's ellipse touches.
+// Same masks as gsr_region_mask, but the x-range of every 8-row band is computed once per tile
+// ROW and shared by the tiles of that row.
+template <class F>
+__device__ __forceinline__ void gsr_for_each_tile(const GsrRec& r, int x0, int x1, int y0, int y1,
+                                                  int h, int w, int ntx, float ecut, F&& f) {
+  const GsrEllipse e = gsr_ellipse(r, h, w);
+  const int tx0 = x0 / GSR_TILE_W, tx1 = x1 / GSR_TILE_W;
+  const int ty0 = y0 / GSR_TILE_H, ty1 = y1 / GSR_TILE_H;
+  for (int ty = ty0; ty <= ty1; ++ty) {
+    int xl[GSR_NRY], xh[GSR_NRY];
+    bool any = false;
+#pragma unroll
+    for (int ry = 0; ry < GSR_NRY; ++ry) {
+      int ya = ty * GSR_TILE_H + ry * GSR_REGION, yb = ya + GSR_REGION - 1;
+      ya = ya > y0 ? ya : y0;
+      yb = yb < y1 ? yb : y1;
+      const bool ok = ya <= yb && gsr_band_xrange(e, ecut, ya, yb, x0, x1, xl[ry], xh[ry]);
+      if (!ok) {
+        xl[ry] = 1;
+        xh[ry] = 0;
+      }
+      any |= ok;
+    }
+    if (!any) continue;
+    for (int tx = tx0; tx <= tx1; ++tx) {
+      const int ox = tx * GSR_TILE_W;
+      uint32_t m = 0;
+#pragma unroll
+      for (int ry = 0; ry < GSR_NRY; ++ry) {
+        const int lo = xl[ry] > ox ? xl[ry] : ox;
+        const int hi = xh[ry] < ox + GSR_TILE_W - 1 ? xh[ry] : ox + GSR_TILE_W - 1;
+        if (lo <= hi) {
+          const int r0 = (lo - ox) / GSR_REGION, r1 = (hi - ox) / GSR_REGION;
+          m |= (((2u << r1) - 1u) & ~((1u << r0) - 1u)) << (ry * GSR_NRX);
+        }
+      }
+      if (m) f(ty * ntx + tx, m);
+    }
+  }
+}
+
+// Warp-cooperative form: the 32 Gaussians of a warp are consecutive in the input, which for a
+// fea2gs field means spatially adjacent (utils/fea2gs.py:553-563), so their tile sets overlap
+// heavily.  The warp walks the UNION of the lanes' tile rectangles; per tile every lane computes
+// its mask and `coop(tile, mask, ballot of lanes with a non-empty mask)` is called once -- one
+// atomic per (warp, tile) instead of one per (Gaussian, tile), and coalesced entry writes.  If the
+// union is large (incoherent input) every lane walks its own tiles and `single(tile, mask)` is
+// called instead.  All 32 lanes must call this function (dead lanes pass live = false).
+constexpr int GSR_COOP_MAX_TILES = 96;
+
+template <class FC, class FS>
+__device__ __forceinline__ void gsr_warp_tiles(bool live, const GsrRec& r, int x0, int x1, int y0,
+                                               int y1, int h, int w, int ntx, float ecut, FC&& coop,
+                                               FS&& single) {
+  const unsigned full = 0xffffffffu;
+  const int tx0 = live ? x0 / GSR_TILE_W : 0x3fffffff, tx1 = live ? x1 / GSR_TILE_W : -1;
+  const int ty0 = live ? y0 / GSR_TILE_H : 0x3fffffff, ty1 = live ? y1 / GSR_TILE_H : -1;
+  const int ux0 = __reduce_min_sync(full, tx0), ux1 = __reduce_max_sync(full, tx1);
+  const int uy0 = __reduce_min_sync(full, ty0), uy1 = __reduce_max_sync(full, ty1);
+  if (ux1 < ux0 || uy1 < uy0) return;  // no live lane
+  if ((long long)(ux1 - ux0 + 1) * (uy1 - uy0 + 1) > GSR_COOP_MAX_TILES) {
+    if (live) gsr_for_each_tile(r, x0, x1, y0, y1, h, w, ntx, ecut, single);
+    return;
+  }
+  GsrEllipse e;
+  if (live) e = gsr_ellipse(r, h, w);
+  for (int ty = uy0; ty <= uy1; ++ty) {
+    int xl[GSR_NRY], xh[GSR_NRY];
+    const bool in_row = live && ty >= ty0 && ty <= ty1;
+#pragma unroll
+    for (int ry = 0; ry < GSR_NRY; ++ry) {
+      int ya = ty * GSR_TILE_H + ry * GSR_REGION, yb = ya + GSR_REGION - 1;
+      ya = ya > y0 ? ya : y0;
+      yb = yb < y1 ? yb : y1;
+      const bool ok = in_row && ya <= yb && gsr_band_xrange(e, ecut, ya, yb, x0, x1, xl[ry], xh[ry]);
+      if (!ok) {
+        xl[ry] = 1;
+        xh[ry] = 0;
+      }
+    }
+    for (int tx = ux0; tx <= ux1; ++tx) {
+      const int ox = tx * GSR_TILE_W;
+      uint32_t m = 0;
+#pragma unroll
+      for (int ry = 0; ry < GSR_NRY; ++ry) {
+        const int lo = xl[ry] > ox ? xl[ry] : ox;
+        const int hi = xh[ry] < ox + GSR_TILE_W - 1 ? xh[ry] : ox + GSR_TILE_W - 1;
+        if (lo <= hi) {
+          const int r0 = (lo - ox) / GSR_REGION, r1 = (hi - ox) / GSR_REGION;
+          m |= (((2u << r1) - 1u) & ~((1u << r0) - 1u)) << (ry * GSR_NRX);
+        }
+      }
+      const unsigned bal = __ballot_sync(full, m != 0);
+      if (bal) coop(ty * ntx + tx, m, bal);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gsr_tile_count_kernel(const float* __restrict__ sigmas, const float* __restrict__ coords,
+                      const float* __restrict__ colors, int s, int h, int w, float dmax,
+                      float ksigma, float ecut, GsrWorkspace ws) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // the grid covers s rounded up to 32
+  const int lane = threadIdx.x & 31;
+  GsrSetup st;
+  st.live = false;
+  st.x0 = st.y0 = 1;
+  st.x1 = st.y1 = 0;
+  GsrRec r;
+  r.x = r.y = r.a = r.b = r.c = r.r = r.g = r.bl = 0.f;
+  if (i < s) {
+    const float sx = __ldg(sigmas + 3 * (size_t)i + 0);
+    const float sy = __ldg(sigmas + 3 * (size_t)i + 1);
+    const float rho = __ldg(sigmas + 3 * (size_t)i + 2);
+    const float x = __ldg(coords + 2 * (size_t)i + 0);
+    const float y = __ldg(coords + 2 * (size_t)i + 1);
+    const float cr = __ldg(colors + 3 * (size_t)i + 0);
+    const float cg = __ldg(colors + 3 * (size_t)i + 1);
+    const float cb = __ldg(colors + 3 * (size_t)i + 2);
+    st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, h, w, dmax, ksigma, ws.px_tab, ws.py_tab);
+    if (st.live) {
+      r = gsr_make_rec(sx, sy, rho, x, y, cr, cg, cb);
+      if (!(gsr_finite(r.a) && gsr_finite(r.b) && gsr_finite(r.c))) st.live = false;
+    }
+    if (st.live) {
+      float4* dr = reinterpret_cast<float4*>(ws.rec_in + i);
+      dr[0] = make_float4(r.x, r.y, r.a, r.b);
+      dr[1] = make_float4(r.c, r.r, r.g, r.bl);
+      ws.box_in[i] = gsr_box_pack(st.x0, st.x1, st.y0, st.y1, st.binds);
+    } else {
+      ws.box_in[i] = gsr_box_pack(1, 0, 1, 0, false);  // empty: skipped by the fill kernel
+    }
+  }
+  int* cnt = ws.tile_count;
+  gsr_warp_tiles(st.live, r, st.x0, st.x1, st.y0, st.y1, h, w, ws.ntx, ecut,
+                 [&](int t, uint32_t, unsigned bal) {
+                   if (lane == __ffs(bal) - 1) atomicAdd(cnt + t, __popc(bal));
+                 },
+                 [&](int t, uint32_t) { atomicAdd(cnt + t, 1); });
+}
+
+__global__ void __launch_bounds__(256)
+gsr_tile_fill_kernel(int s, int h, int w, float ecut, GsrWorkspace ws, const int* guard, int want) {
+  if (gsr_guard_skip(guard, want)) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int x0 = 1, x1 = 0, y0 = 1, y1 = 0;
+  bool binds = false;
+  GsrRec r;
+  r.x = r.y = r.a = r.b = r.c = r.r = r.g = r.bl = 0.f;
+  if (i < s) gsr_box_unpack(ws.box_in[i], x0, x1, y0, y1, binds);
+  const bool live = x0 <= x1;
+  if (live) {
+    const float4* rp = reinterpret_cast<const float4*>(ws.rec_in + i);
+    const float4 q0 = rp[0], q1 = rp[1];
+    r.x = q0.x; r.y = q0.y; r.a = q0.z; r.b = q0.w;
+    r.c = q1.x; r.r = q1.y; r.g = q1.z; r.bl = q1.w;
+  }
+  int* cur = ws.tile_cur;
+  uint2* ent = ws.entries;
+  const uint32_t fl = binds ? 0x10000u : 0u;
+  gsr_warp_tiles(live, r, x0, x1, y0, y1, h, w, ws.ntx, ecut,
+                 [&](int t, uint32_t m, unsigned bal) {
+                   const int leader = __ffs(bal) - 1;
+                   int base = 0;
+                   if (lane == leader) base = atomicAdd(cur + t, __popc(bal));
+                   base = __shfl_sync(0xffffffffu, base, leader);
+                   if (m) ent[base + __popc(bal & ((1u << lane) - 1u))] = make_uint2((uint32_t)i, m | fl);
+                 },
+                 [&](int t, uint32_t m) {
+                   const int slot = atomicAdd(cur + t, 1);
+                   ent[slot] = make_uint2((uint32_t)i, m | fl);
+                 });
 }

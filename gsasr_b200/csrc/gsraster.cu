@@ -48,23 +48,48 @@ static int gsr_check_ws(void* workspace, size_t bytes, size_t need) {
   return GSR_OK;
 }
 
-// K1..K3.  Leaves the sorted arrays in ws.
-static int gsr_run_prepass(const float* sigmas, const float* coords, const float* colors, int s,
-                           int h, int w, float dmax, float keff, const GsrWorkspace& ws,
-                           cudaStream_t st) {
+static int gsr_clear_and_tables(int h, int w, const GsrWorkspace& ws, cudaStream_t st) {
   GSR_CUDA(cudaMemsetAsync(ws.bin_count, 0, ws.zero_bytes, st));
   const int n = w > h ? w : h;
   gsr_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws.px_tab, ws.py_tab, h, w);
-  if (s > 0)
-    gsr_bin_kernel<<<(s + 255) / 256, 256, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff, ws);
-  gsr_scan_kernel<<<ws.nscan, 1024, 0, st>>>(ws.bin_count, ws.bin_off, ws.nb + 1, ws.scan_state);
-  if (s > 0) gsr_scatter_kernel<<<(s + 255) / 256, 256, 0, st>>>(sigmas, coords, colors, s, ws);
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
 }
 
-static int gsr_launch_forward(const GsrWorkspace& ws, float* img, int h, int w, float keff,
-                              uint32_t flags, cudaStream_t st) {
+// Home-bin pipeline K1..K3 (leaves the sorted arrays in ws).  guard/want: see gsr_guard_skip.
+static int gsr_run_bins(const float* sigmas, const float* coords, const float* colors, int s,
+                        int h, int w, float dmax, float keff, const GsrWorkspace& ws,
+                        const int* guard, int want, cudaStream_t st) {
+  // guarded (fallback) launches use a small grid-stride grid: the no-op case must stay cheap
+  const int gs_grid = guard ? (s + 255) / 256 < 592 ? (s + 255) / 256 : 592 : (s + 255) / 256;
+  if (s > 0)
+    gsr_bin_kernel<<<gs_grid, 256, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff, ws, guard, want);
+  gsr_scan_kernel<<<ws.nscan, 1024, 0, st>>>(ws.bin_count, ws.bin_off, nullptr, ws.nb + 1,
+                                             ws.scan_state, -1, ws.stats, guard, want);
+  if (s > 0)
+    gsr_scatter_kernel<<<gs_grid, 256, 0, st>>>(sigmas, coords, colors, s, ws, guard, want);
+  GSR_CUDA(cudaGetLastError());
+  return GSR_OK;
+}
+
+// Tile-list pipeline T1..T3.  Raises stats[GSR_STAT_OVERFLOW] when the entries do not fit.
+static int gsr_run_tiles(const float* sigmas, const float* coords, const float* colors, int s,
+                         int h, int w, float dmax, float keff, const GsrWorkspace& ws,
+                         cudaStream_t st) {
+  const float ecut = gsr_ecut(keff);
+  if (s > 0)
+    gsr_tile_count_kernel<<<(s + 255) / 256, 256, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff,
+                                                           ecut, ws);
+  gsr_scan_kernel<<<ws.ntscan, 1024, 0, st>>>(ws.tile_count, ws.tile_off, ws.tile_cur, ws.nt,
+                                              ws.tscan_state, ws.ecap, ws.stats, nullptr, 0);
+  if (s > 0)
+    gsr_tile_fill_kernel<<<(s + 255) / 256, 256, 0, st>>>(s, h, w, ecut, ws, ws.stats + GSR_STAT_OVERFLOW, 0);
+  GSR_CUDA(cudaGetLastError());
+  return GSR_OK;
+}
+
+static GsrFwdArgs gsr_fwd_args(const GsrWorkspace& ws, float* img, int h, int w, float keff,
+                               uint32_t flags) {
   GsrFwdArgs a;
   a.rec = ws.rec;
   a.box = ws.box;
@@ -80,12 +105,55 @@ static int gsr_launch_forward(const GsrWorkspace& ws, float* img, int h, int w, 
   a.nb = ws.nb;
   a.ecut = gsr_ecut(keff);
   a.flags = flags;
-  GSR_CUDA(cudaFuncSetAttribute(gsr_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(GsrFwdSmem)));
-  dim3 grid((w + GSR_TILE_W - 1) / GSR_TILE_W, (h + GSR_TILE_H - 1) / GSR_TILE_H);
-  gsr_forward_kernel<<<grid, GSR_FWD_THREADS, sizeof(GsrFwdSmem), st>>>(a);
+  a.guard = ws.stats + GSR_STAT_OVERFLOW;
+  a.want = 0;
+  a.tile_off = ws.tile_off;
+  a.entries = ws.entries;
+  a.rec_in = ws.rec_in;
+  a.box_in = ws.box_in;
+  a.ntx = ws.ntx;
+  return a;
+}
+
+// Raster over the tile lists (runs when the lists fit) ...
+static int gsr_launch_forward_list(const GsrWorkspace& ws, float* img, int h, int w, float keff,
+                                   uint32_t flags, cudaStream_t st) {
+  GsrFwdArgs a = gsr_fwd_args(ws, img, h, w, keff, flags);
+  a.want = 0;
+  dim3 grid(ws.ntx, ws.nty);
+  gsr_forward_list_kernel<<<grid, GSR_FL_THREADS, 0, st>>>(a);
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
+}
+
+// ... or over the home bins (runs when they overflowed).
+static int gsr_launch_forward_bins(const GsrWorkspace& ws, float* img, int h, int w, float keff,
+                                   uint32_t flags, cudaStream_t st) {
+  GsrFwdArgs a = gsr_fwd_args(ws, img, h, w, keff, flags);
+  a.want = 1;
+  GSR_CUDA(cudaFuncSetAttribute(gsr_forward_bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(GsrFwdSmem)));
+  const int ntiles = ((w + GSR_TILE_W - 1) / GSR_TILE_W) * ((h + GSR_TILE_H - 1) / GSR_TILE_H);
+  const int grid = ntiles < 148 * GSR_CFG_MIN_CTAS ? ntiles : 148 * GSR_CFG_MIN_CTAS;
+  gsr_forward_bins_kernel<<<grid, GSR_FWD_THREADS, sizeof(GsrFwdSmem), st>>>(a);
+  GSR_CUDA(cudaGetLastError());
+  return GSR_OK;
+}
+
+// Whole forward set-up: tile lists, plus the guarded home-bin fallback.
+static int gsr_prepare_forward(const float* sigmas, const float* coords, const float* colors, int s,
+                               int h, int w, float dmax, float keff, const GsrWorkspace& ws,
+                               cudaStream_t st) {
+  int rc = gsr_run_tiles(sigmas, coords, colors, s, h, w, dmax, keff, ws, st);
+  if (rc) return rc;
+  return gsr_run_bins(sigmas, coords, colors, s, h, w, dmax, keff, ws, ws.stats + GSR_STAT_OVERFLOW, 1, st);
+}
+
+static int gsr_raster_forward(const GsrWorkspace& ws, float* img, int h, int w, float keff,
+                              uint32_t flags, cudaStream_t st) {
+  int rc = gsr_launch_forward_list(ws, img, h, w, keff, flags, st);
+  if (rc) return rc;
+  return gsr_launch_forward_bins(ws, img, h, w, keff, flags, st);
 }
 
 static int gsr_launch_backward(const GsrWorkspace& ws, const float* sigmas, const float* grads,
@@ -132,9 +200,11 @@ extern "C" int gsr_forward(const float* sigmas, const float* coords, const float
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const float keff = gsr_effective_ksigma(ksigma);
-  rc = gsr_run_prepass(sigmas, coords, colors, s, h, w, dmax, keff, ws, st);
+  rc = gsr_clear_and_tables(h, w, ws, st);
   if (rc) return rc;
-  return gsr_launch_forward(ws, img, h, w, keff, flags, st);
+  rc = gsr_prepare_forward(sigmas, coords, colors, s, h, w, dmax, keff, ws, st);
+  if (rc) return rc;
+  return gsr_raster_forward(ws, img, h, w, keff, flags, st);
 }
 
 extern "C" int gsr_backward(const float* sigmas, const float* coords, const float* colors,
@@ -152,7 +222,9 @@ extern "C" int gsr_backward(const float* sigmas, const float* coords, const floa
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const float keff = gsr_effective_ksigma(ksigma);
-  rc = gsr_run_prepass(sigmas, coords, colors, s, h, w, dmax, keff, ws, st);
+  rc = gsr_clear_and_tables(h, w, ws, st);
+  if (rc) return rc;
+  rc = gsr_run_bins(sigmas, coords, colors, s, h, w, dmax, keff, ws, nullptr, 0, st);
   if (rc) return rc;
   return gsr_launch_backward(ws, sigmas, grads, grads_sigmas, grads_coords, grads_colors, s, h, w,
                              flags, st);
@@ -167,8 +239,13 @@ extern "C" int gsr_prepare(const float* sigmas, const float* coords, const float
   const GsrWorkspace ws = gsr_carve(workspace, s, h, w);
   int rc = gsr_check_ws(workspace, workspace_bytes, ws.bytes);
   if (rc) return rc;
-  return gsr_run_prepass(sigmas, coords, colors, s, h, w, dmax, gsr_effective_ksigma(ksigma), ws,
-                         (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float keff = gsr_effective_ksigma(ksigma);
+  rc = gsr_clear_and_tables(h, w, ws, st);
+  if (rc) return rc;
+  rc = gsr_run_tiles(sigmas, coords, colors, s, h, w, dmax, keff, ws, st);
+  if (rc) return rc;
+  return gsr_run_bins(sigmas, coords, colors, s, h, w, dmax, keff, ws, nullptr, 0, st);
 }
 
 extern "C" int gsr_forward_prepared(float* img, int s, int h, int w, float ksigma, uint32_t flags,
@@ -178,7 +255,7 @@ extern "C" int gsr_forward_prepared(float* img, int s, int h, int w, float ksigm
   const GsrWorkspace ws = gsr_carve(workspace, s, h, w);
   int rc = gsr_check_ws(workspace, workspace_bytes, ws.bytes);
   if (rc) return rc;
-  return gsr_launch_forward(ws, img, h, w, gsr_effective_ksigma(ksigma), flags, (cudaStream_t)stream);
+  return gsr_raster_forward(ws, img, h, w, gsr_effective_ksigma(ksigma), flags, (cudaStream_t)stream);
 }
 
 extern "C" int gsr_backward_prepared(const float* sigmas, const float* grads, float* grads_sigmas,
