@@ -24,7 +24,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -49,94 +48,123 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled every 20 ms (NVML) while the timed region runs."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.mx, self._stop, self._thr = index, [], set(), None, False, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self._stop:
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(
+                            pynvml, "nvmlDeviceGetCurrentClocksEventReasons") else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        for bit, name in self.BAD.items():
+                            if r & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    time.sleep(0.02)
+
+            self._thr = threading.Thread(target=loop, daemon=True)
+            self._thr.start()
+        except Exception as exc:  # no NVML: report that, do not fake numbers
+            self.reasons.add(f"nvml unavailable: {exc}")
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        self._stop = True
+        if self._thr is not None:
+            self._thr.join(timeout=1.0)
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
-def cpu_sample(cfg_name: str, seconds: float = 12.0, threads: int | None = None):
-    """Times the CPU restatement of the reference algorithm (oracle/gs_oracle.c, fp32 mode, dmax
-    window semantics, all host cores) on the first M Gaussians of the workload; M is grown until
-    one call takes ~`seconds`.  Returns (MP/s extrapolated to the whole workload, cores, text)."""
-    from gsasr_b200 import fields
-    from oracle import oracle
+class CpuPort:
+    """The CPU restatement of the reference algorithm (oracle/gs_oracle.c, fp32 mode, dmax window
+    semantics, OpenMP over all host cores) on an evenly strided sample of the workload's Gaussians."""
 
-    oracle.build()
-    if threads:
-        oracle.set_num_threads(threads)
-    cores = oracle.num_threads()
-    _, s, c, k, h, w = fields.make(cfg_name, 0)
-    s, c, k = s.numpy(), c.numpy(), k.numpy()
-    n = s.shape[0]
-    import numpy as np
+    def __init__(self, cfg_name: str, threads: int | None = None):
+        import numpy as np
 
-    m, t = min(n, 64 * cores), 0.0
-    while True:
-        idx = np.linspace(0, n - 1, m).astype(np.int64)  # evenly strided: every image row band gets work
+        from gsasr_b200 import fields
+        from oracle import oracle
+
+        oracle.build()
+        if threads:
+            oracle.set_num_threads(threads)
+        self.oracle, self.np, self.name = oracle, np, cfg_name
+        self.cores = oracle.num_threads()
+        _, s, c, k, self.h, self.w = fields.make(cfg_name, 0)
+        self.s, self.c, self.k = s.numpy(), c.numpy(), k.numpy()
+        self.n = self.s.shape[0]
+
+    def run(self, m: int) -> float:
+        idx = self.np.linspace(0, self.n - 1, m).astype(self.np.int64)  # every row band gets work
         t0 = time.perf_counter()
-        oracle.forward(s[idx], c[idx], k[idx], h, w, DMAX, mode=1)
-        t = time.perf_counter() - t0
-        if t >= 0.4 * seconds or m >= n:
-            break
-        m = min(n, max(m + 1, int(m * min(6.0, 0.8 * seconds / max(t, 1e-3)))))
-    mps = (h * w / 1e6) / (t * n / m)
-    return mps, cores, (f"{m} of {n} Gaussians of {cfg_name} (evenly strided; {h}x{w}, dmax {DMAX}) rendered in {t:.2f} s "
-                        f"by oracle/gs_oracle.c (fp32 mode, OpenMP {cores} threads); MP/s = MP / (t * {n}/{m})"), t
+        self.oracle.forward(self.s[idx], self.c[idx], self.k[idx], self.h, self.w, DMAX, mode=1)
+        return time.perf_counter() - t0
+
+    def calibrate(self, seconds: float) -> int:
+        """Sample size whose render takes about `seconds`."""
+        m = min(self.n, 32 * self.cores)
+        while True:
+            t = self.run(m)
+            if t >= 0.3 * seconds or m >= self.n:
+                return max(1, min(self.n, int(m * seconds / max(t, 1e-4))))
+            m = min(self.n, max(m + 1, int(m * min(8.0, 0.8 * seconds / max(t, 1e-4)))))
+
+    def mps(self, m: int, t: float) -> float:
+        return (self.h * self.w / 1e6) / (t * self.n / m)
+
+    def describe(self, m: int, t: float) -> str:
+        return (f"{m} of {self.n} Gaussians of {self.name} (evenly strided; {self.h}x{self.w}, dmax {DMAX}) rendered in "
+                f"{t:.2f} s by oracle/gs_oracle.c (fp32 mode, OpenMP {self.cores} threads); MP/s = MP / (t * {self.n}/{m})")
+
+
+def cpu_sample(cfg_name: str, seconds: float = 12.0):
+    port = CpuPort(cfg_name)
+    m = port.calibrate(seconds)
+    t = port.run(m)
+    return port.mps(m, t), port.cores, port.describe(m, t), t
 
 
 def run_reference(args, rank):
+    """--impl reference: every step renders the same bounded sample; the whole run is sized to ~90 s."""
     if rank != 0:
         return
-    vals = []
-    sample = ""
-    cores = 1
-    for i in range(args.warmup + args.steps):
-        mps, cores, sample, t = cpu_sample(args.workload, seconds=max(2.0, 40.0 / (args.warmup + args.steps)))
+    port = CpuPort(args.workload)
+    total = args.warmup + args.steps
+    m = port.calibrate(max(0.05, 90.0 / max(total, 1)))
+    ts = []
+    for i in range(total):
+        t = port.run(m)
         if i >= args.warmup:
-            vals.append((mps, t))
-    value = sum(v for v, _ in vals) / len(vals)
-    from gsasr_b200 import fields
-    cfg = fields.CONFIGS[args.workload]
+            ts.append(t)
+    t = sum(ts) / len(ts)
+    value = port.mps(m, t)
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * (cfg.hr[0] * cfg.hr[1] / 1e6) / value, "higher_is_better": True,
+        "ms_per_step": 1e3 * t, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.workload),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": port.cores, "kind": "port",
+                         "sample": port.describe(m, t)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference's own implementation of this path is CUDA-only (gs_cuda_dmax); its CPU arm is the "
-                "oracle port of that algorithm timed on the host cores; ms_per_step is extrapolated to the whole image",
+                "oracle port of that algorithm on the host cores; a step renders the bounded sample described in "
+                "cpu_baseline.sample and value extrapolates it to the whole image",
     }
     print(json.dumps(out), flush=True)
 
@@ -154,8 +182,8 @@ def workload_config(name):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="HL")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -392,6 +392,13 @@ constexpr int GSR_FL_WARPS = GSR_FL_THREADS / 32;
 constexpr int GSR_FL_PER_LANE = GSR_CFG_FL_PER_LANE;
 constexpr int GSR_FL_PER_WARP = 32 * GSR_FL_PER_LANE;
 constexpr int GSR_FL_CHUNK = GSR_FL_THREADS * GSR_FL_PER_LANE;
+#ifndef GSR_CFG_FL_UNROLL
+#define GSR_CFG_FL_UNROLL 4
+#endif
+constexpr int GSR_FL_UNROLL = GSR_CFG_FL_UNROLL;
+#ifndef GSR_CFG_FL_UNROLL
+#define GSR_CFG_FL_UNROLL 2
+#endif
 #ifndef GSR_CFG_FL_MIN_CTAS
 #define GSR_CFG_FL_MIN_CTAS 4
 #endif
@@ -471,7 +478,7 @@ __global__ void __launch_bounds__(GSR_FL_THREADS, GSR_CFG_FL_MIN_CTAS) gsr_forwa
     for (int pw = 0; pw < GSR_FL_WARPS; ++pw) {
       const int nf = sm.nfast[pw][warp];
       const uint16_t* lf = sm.lfast[pw][warp];
-#pragma unroll 2
+#pragma unroll GSR_FL_UNROLL
       for (int i = 0; i < nf; ++i) eval(rec_s + ((uint32_t)lf[i] << 5), true, true);
       const int ns = sm.nslow[pw][warp];
       const uint16_t* ls = sm.lslow[pw][warp];

@@ -6,13 +6,13 @@ import os, subprocess, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "variants")
-B8 = ["GSR_CFG_BIN=8", "GSR_CFG_LARGE_PX=96"]
 VARIANTS = {
-    "t32x16_bin8": ["GSR_CFG_TILE_H=16"] + B8,
-    "t32x16_bin8_pl6": ["GSR_CFG_TILE_H=16", "GSR_CFG_PER_LANE=6", "GSR_CFG_MIN_CTAS=3"] + B8,
-    "t32x16_bin8_pl8": ["GSR_CFG_TILE_H=16", "GSR_CFG_PER_LANE=8", "GSR_CFG_MIN_CTAS=2"] + B8,
-    "t32x32_bin8_pl3": ["GSR_CFG_PER_LANE=3"] + B8,
-    "t32x32_bin8_pl2": ["GSR_CFG_PER_LANE=2"] + B8,
+    "u2": [],
+    "u4": ["GSR_CFG_FL_UNROLL=4"],
+    "u3": ["GSR_CFG_FL_UNROLL=3"],
+    "pl1": ["GSR_CFG_FL_PER_LANE=1"],
+    "c5_u2": ["GSR_CFG_FL_MIN_CTAS=5"],
+    "c3_u4": ["GSR_CFG_FL_MIN_CTAS=3", "GSR_CFG_FL_UNROLL=4"],
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
