@@ -1,0 +1,135 @@
+"""Mirror of utils/split_and_joint_image.py:98-232 (tiled inference, `--tile_process`), with the
+tiles sharded over the ranks of a process group.
+
+    split_and_joint_image(lq, scale_factor, split_size, overlap_size, model_g, model_fea2gs,
+                          scale_modify, crop_size=2, default_step_size=1.2, mode='scale_modify',
+                          cuda_rendering=True, if_dmax=False, dmax_mode='fix', dmax=25)
+
+Same arguments, same (B, C, H_pad, W_pad) result.  The reference runs encoder -> head -> render
+for every LR tile sequentially on one GPU (:127-151) and pastes the SR tiles in row-major order,
+later tiles overwriting earlier ones except for the first `crop_size` rows/columns of every
+non-first tile (:166-225).  Tiles are independent, so with torch.distributed initialised each rank
+processes a contiguous block of tiles on its own GPU and the finished tiles are gathered to
+`gather_to` (NCCL over NVLink) where the stitching rules are applied; without a process group this
+is the reference's sequential loop on the B200 rasteriser.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List
+
+import torch
+import torch.nn.functional as F
+
+from .sharding import render_units_sharded
+
+
+@dataclass(frozen=True)
+class TilePlan:
+    tiles_h: int
+    tiles_w: int
+    pad_h: int
+    pad_w: int
+    split: int
+    overlap: int
+    split_sr: int
+    overlap_sr: int
+
+    @property
+    def n(self):
+        return self.tiles_h * self.tiles_w
+
+    @property
+    def stride(self):
+        return self.split - self.overlap
+
+    @property
+    def sr_h(self):
+        return (self.tiles_h - 1) * (self.split_sr - self.overlap_sr) + self.split_sr
+
+    @property
+    def sr_w(self):
+        return (self.tiles_w - 1) * (self.split_sr - self.overlap_sr) + self.split_sr
+
+
+def plan_tiles(h_lq: int, w_lq: int, scale_factor: float, split_size: int, overlap_size: int) -> TilePlan:
+    """Tile geometry of :108-125,153-163."""
+    assert overlap_size > 0 and overlap_size < split_size // 2, "overlap size is wrong"
+    stride = split_size - overlap_size
+    th = math.ceil((h_lq - overlap_size) / stride)
+    tw = math.ceil((w_lq - overlap_size) / stride)
+    pad_h = th * stride + overlap_size - h_lq
+    pad_w = tw * stride + overlap_size - w_lq
+    assert pad_h < h_lq, f"pad_h_lq-{pad_h} should be smaller than h_lq-{h_lq}, please decrease the split_size-{split_size}"
+    assert pad_w < w_lq, f"pad_w_lq-{pad_w} should be smaller than w_lq-{w_lq}, please decrease the split_size-{split_size}"
+    return TilePlan(th, tw, pad_h, pad_w, split_size, overlap_size, math.ceil(split_size * scale_factor),
+                    math.ceil(overlap_size * scale_factor))
+
+
+def _paste_rule(plan: TilePlan, hn: int, wn: int, crop: int, integer_scale: bool):
+    """(rows to skip, columns to skip) at the top/left of tile (hn, wn) when it is pasted.
+    Integer scales: every non-first row/column of tiles skips `crop` (:213-225).  Non-integer
+    scales follow the reference's case table (:168-205), in which an interior tile in the LAST
+    column (or LAST row) skips only its columns (or only its rows)."""
+    if integer_scale:
+        return (crop if hn else 0), (crop if wn else 0)
+    last_h, last_w = hn == plan.tiles_h - 1, wn == plan.tiles_w - 1
+    if hn == 0:
+        return 0, (crop if wn else 0)
+    if wn == 0:
+        return crop, 0
+    if last_w and not last_h:
+        return 0, crop
+    if last_h and not last_w:
+        return crop, 0
+    return crop, crop
+
+
+def stitch_tiles(tiles: List[torch.Tensor], plan: TilePlan, batch: int, channels: int, scale_factor: float,
+                 crop_size: int) -> torch.Tensor:
+    """Paste the (1,C,S,S) SR tiles (row-major) into the padded SR canvas (:160-227)."""
+    s, step = plan.split_sr, plan.split_sr - plan.overlap_sr
+    for t in tiles:
+        assert t.shape[-2] == s and t.shape[-1] == s, f"tile {tuple(t.shape)} is not {s}x{s}"
+    canvas = torch.zeros(batch, channels, plan.sr_h, plan.sr_w, device=tiles[0].device)
+    integer_scale = scale_factor == int(scale_factor)
+    idx = 0
+    for hn in range(plan.tiles_h):
+        for wn in range(plan.tiles_w):
+            top, left = _paste_rule(plan, hn, wn, crop_size, integer_scale)
+            y0, x0 = hn * step, wn * step
+            y1, x1 = min(y0 + s, plan.sr_h), min(x0 + s, plan.sr_w)
+            canvas[:, :, y0 + top:y1, x0 + left:x1] = tiles[idx][:, :, top:y1 - y0, left:x1 - x0]
+            idx += 1
+    return canvas
+
+
+def split_and_joint_image(lq, scale_factor, split_size, overlap_size, model_g, model_fea2gs, scale_modify,
+                          crop_size=2, default_step_size=1.2, mode='scale_modify', cuda_rendering=True,
+                          if_dmax=False, dmax_mode='fix', dmax=25, *, render_fn=None, gather_to=0, group=None):
+    """Returns the stitched (B,C,H_pad,W_pad) SR image on rank `gather_to` (every rank when it is
+    None or when torch.distributed is not initialised); None on the other ranks."""
+    if render_fn is None:
+        from .gaussian_splatting import generate_2D_gaussian_splatting_step as render_fn
+    h_lq, w_lq = lq.shape[-2:]
+    plan = plan_tiles(h_lq, w_lq, scale_factor, split_size, overlap_size)
+    lq_pad = F.pad(input=lq, pad=(0, plan.pad_w, 0, plan.pad_h), mode='reflect')
+
+    def render_tile(i: int) -> torch.Tensor:
+        hn, wn = divmod(i, plan.tiles_w)
+        y, x = hn * plan.stride, wn * plan.stride
+        tile = lq_pad[:, :, y:y + split_size, x:x + split_size]
+        feat = model_g(tile)
+        scale_vector = scale_modify[0].unsqueeze(0).to(feat.device)
+        gs_parameters = model_fea2gs(feat, scale_vector)[0, :]
+        out = render_fn(sr_size=torch.tensor([plan.split_sr, plan.split_sr]), gs_parameters=gs_parameters,
+                        scale=scale_factor, sample_coords=None, scale_modify=scale_modify,
+                        default_step_size=default_step_size, mode=mode, cuda_rendering=cuda_rendering,
+                        if_dmax=if_dmax, dmax_mode=dmax_mode, dmax=dmax)
+        return out.unsqueeze(0)
+
+    tiles = render_units_sharded(plan.n, render_tile, gather_to=gather_to, group=group)
+    if tiles is None:
+        return None
+    return stitch_tiles(tiles, plan, lq.shape[0], lq.shape[1], scale_factor, crop_size)

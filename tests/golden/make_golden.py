@@ -94,6 +94,28 @@ def frontend_fixture(n_side, scale, seed, dmax, dmax_mode):
     return rec
 
 
+def stitch_fixture(h_lq, w_lq, scale, split, overlap, crop, seed):
+    """The reference's split_and_joint_image (utils/split_and_joint_image.py:98-232) run unmodified
+    on CPU with stub networks and a stub renderer that returns seeded random tiles: pins the tile
+    geometry and every paste rule (integer and non-integer scale branches)."""
+    sys.path.insert(0, REF)
+    import utils.split_and_joint_image as sj
+
+    calls = []
+
+    def fake_render(sr_size, gs_parameters, **kw):
+        g = torch.Generator().manual_seed(1000 * seed + len(calls))
+        calls.append(int(sr_size[0]))
+        return torch.rand(3, int(sr_size[0]), int(sr_size[1]), generator=g)
+
+    sj.generate_2D_gaussian_splatting_step = fake_render
+    lq = torch.rand(1, 3, h_lq, w_lq, generator=torch.Generator().manual_seed(seed))
+    out = sj.split_and_joint_image(lq, scale, split, overlap, lambda t: t, lambda f, s: torch.zeros(1, 4, 9),
+                                   torch.tensor([scale, scale]), crop_size=crop)
+    return dict(out=out.numpy(), h_lq=h_lq, w_lq=w_lq, scale=np.float32(scale), split=split, overlap=overlap,
+                crop=crop, seed=seed, n_tiles=len(calls))
+
+
 def main():
     cd = load_check(os.path.join(REF, "utils/gs_cuda_dmax/check.py"))
     cp = load_check(os.path.join(REF, "utils/gs_cuda/check.py"))
@@ -104,6 +126,9 @@ def main():
     np.savez(os.path.join(OUT, "check_dmax_narrow.npz"), **run_check(cd, 24, (37, 45), 0.2, 7, 0.15))
     np.savez(os.path.join(OUT, "frontend_x4_fix.npz"), **frontend_fixture(16, 4.0, 0, 0.1, 'fix'))
     np.savez(os.path.join(OUT, "frontend_x2p5_dynamic.npz"), **frontend_fixture(12, 2.5, 1, 25, 'dynamic'))
+    np.savez(os.path.join(OUT, "stitch_x4.npz"), **stitch_fixture(40, 52, 4.0, 16, 4, 2, 0))
+    np.savez(os.path.join(OUT, "stitch_x2p5.npz"), **stitch_fixture(37, 45, 2.5, 14, 3, 2, 1))
+    np.savez(os.path.join(OUT, "stitch_x3p3.npz"), **stitch_fixture(50, 31, 3.3, 12, 2, 3, 2))
     print("wrote", sorted(f for f in os.listdir(OUT) if f.endswith(".npz")))
 
 
