@@ -47,7 +47,7 @@ def render_units_sharded(n_units: int, render_unit: Callable[[int], torch.Tensor
     backend = dist.get_backend(group)
     if backend == "nccl":
         device = torch.device("cuda", torch.cuda.current_device())
-    shapes = torch.zeros(n_units, 4, dtype=torch.int64, device=device)
+    shapes = torch.zeros(n_units, 9, dtype=torch.int64, device=device)  # [ndim, up to 8 extents]
     for i, t in mine.items():
         shapes[i, 0] = t.dim()
         shapes[i, 1:1 + t.dim()] = torch.tensor(list(t.shape), dtype=torch.int64)
