@@ -90,6 +90,11 @@ __device__ __forceinline__ float4 gsr_lds128(uint32_t addr) {
   asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint32_t gsr_lds_u16(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void gsr_cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -130,7 +135,8 @@ struct GsrFwdArgs {
   const int* guard;  // run only if *guard == want (nullptr: always)
   int want;
   // tile-list path
-  const int* tile_off;
+  const int* tile_count;
+  int tile_cap;
   const uint2* entries;
   const GsrRec* rec_in;
   const uint2* box_in;
@@ -426,7 +432,8 @@ __global__ void __launch_bounds__(GSR_FL_THREADS, GSR_CFG_FL_MIN_CTAS) gsr_forwa
   gsr_f2 accr = gsr_pk(0.f, 0.f), accg = gsr_pk(0.f, 0.f), accb = gsr_pk(0.f, 0.f);
   const gsr_f2 px2 = gsr_pk(px0, px1);
   const int tile = blockIdx.y * p.ntx + blockIdx.x;
-  const int e_begin = __ldg(p.tile_off + tile), e_end = __ldg(p.tile_off + tile + 1);
+  const uint2* tile_entries = p.entries + (size_t)tile * p.tile_cap;  // this tile's bucket
+  const int e_begin = 0, e_end = min(__ldg(p.tile_count + tile), p.tile_cap);
   const uint32_t rec_s = gsr_smem_addr(sm.rec);
   const uint32_t box_s = gsr_smem_addr(sm.box);
 
@@ -445,7 +452,7 @@ __global__ void __launch_bounds__(GSR_FL_THREADS, GSR_CFG_FL_MIN_CTAS) gsr_forwa
       uint32_t m = 0;
       bool binds = false;
       if (e0 + slot < e_end) {
-        const uint2 en = __ldg(p.entries + e0 + slot);
+        const uint2 en = __ldg(tile_entries + e0 + slot);
         m = en.y & 0xffffu;
         binds = (en.y & 0x10000u) != 0;
         const float4* src = reinterpret_cast<const float4*>(p.rec_in + en.x);
@@ -459,7 +466,7 @@ __global__ void __launch_bounds__(GSR_FL_THREADS, GSR_CFG_FL_MIN_CTAS) gsr_forwa
         const unsigned balf = __ballot_sync(0xffffffffu, bit && !binds);
         const unsigned bals = __ballot_sync(0xffffffffu, bit && binds);
         if (bit) {
-          if (!binds) sm.lfast[warp][rg][cf[rg] + __popc(balf & lt_mask)] = (uint16_t)slot;
+          if (!binds) sm.lfast[warp][rg][cf[rg] + __popc(balf & lt_mask)] = (uint16_t)(slot * 32);
           else sm.lslow[warp][rg][cs[rg] + __popc(bals & lt_mask)] = (uint16_t)slot;
         }
         cf[rg] += __popc(balf);
@@ -477,9 +484,9 @@ __global__ void __launch_bounds__(GSR_FL_THREADS, GSR_CFG_FL_MIN_CTAS) gsr_forwa
     // ---- stage C: walk the lists every producer warp left for this region ----
     for (int pw = 0; pw < GSR_FL_WARPS; ++pw) {
       const int nf = sm.nfast[pw][warp];
-      const uint16_t* lf = sm.lfast[pw][warp];
+      const uint32_t lf = gsr_smem_addr(sm.lfast[pw][warp]);  // byte offsets of the records
 #pragma unroll GSR_FL_UNROLL
-      for (int i = 0; i < nf; ++i) eval(rec_s + ((uint32_t)lf[i] << 5), true, true);
+      for (int i = 0; i < nf; ++i) eval(rec_s + gsr_lds_u16(lf + 2 * i), true, true);
       const int ns = sm.nslow[pw][warp];
       const uint16_t* ls = sm.lslow[pw][warp];
       for (int i = 0; i < ns; ++i) {  // dmax window cuts this Gaussian: exact inclusion per pixel

@@ -1,14 +1,15 @@
 // gsr_prepass.cuh -- O(N) set-up pipelines shared by forward and backward.
 //
-// Tile-list pipeline (forward fast path):
-//   T1 gsr_tile_count_kernel  per Gaussian: exact dmax window /\ k-sigma box -> cull box, raster
-//                             record (written in input order), and for every 32x16 tile the box
-//                             touches the ellipse-vs-region mask; one RED per (Gaussian,tile) pair.
-//   T2 gsr_scan_kernel        exclusive scan of the tile histogram; raises the overflow flag when
-//                             the pairs do not fit the entry capacity (8 per Gaussian).
-//   T3 gsr_tile_fill_kernel   recomputes the masks and writes the 8-byte entries {index, mask}
-//                             at cursor[tile]++.
-//   The forward kernel then streams each tile's entries and gathers the 32-byte records.
+// Tile-list pipeline (forward fast path), ONE pass over the Gaussians:
+//   T1 gsr_tile_build_kernel  per Gaussian: exact dmax window /\ k-sigma box -> cull box, raster
+//                             record (written in input order), and for every 32x16 tile whose
+//                             8x8 regions the ellipse touches an 8-byte entry {index, region mask}
+//                             appended to the tile's bucket (warp-cooperative: one atomic per
+//                             (warp, tile), coalesced entry writes).
+//   Every tile owns a fixed-capacity bucket (8 N / tiles + 64 entries: GSASR emits its Gaussians on
+//   a regular grid, utils/fea2gs.py:553-563, so the load per tile is uniform); an entry that does
+//   not fit raises the overflow flag and the forward falls back to the home-bin pipeline.
+//   The forward kernel then streams each tile's bucket and gathers the 32-byte records.
 //
 // Home-bin pipeline (backward; forward fallback when the tile lists overflow their capacity):
 //   K1 gsr_bin_kernel     per Gaussian: cull box, home bin, rank inside the bin (atomic), reach.
@@ -24,23 +25,20 @@
 #include "gsr_common.cuh"
 
 constexpr int GSR_STAT_EXT_X = 0, GSR_STAT_EXT_Y = 1, GSR_STAT_OVERFLOW = 2, GSR_STAT_ENTRIES = 3;
-constexpr int GSR_ENTRIES_PER_GAUSSIAN = 8;  // tile-entry capacity = 8 * N + 256
+constexpr int GSR_ENTRIES_PER_GAUSSIAN = 8;  // bucket capacity per tile = 8 * N / tiles + 64
 
 struct GsrWorkspace {
   // ---- one block, cleared per call ----
   int* bin_count;    // nb + 1
   int* stats;        // 8 ints, see GSR_STAT_*
   int* scan_state;   // 2 * nscan     look-back state of the bin scan
-  int* tile_count;   // nt
-  int* tscan_state;  // 2 * ntscan    look-back state of the tile scan
+  int* tile_count;   // nt        entries appended to each tile's bucket (may exceed tile_cap)
   size_t zero_bytes;
   // ---- tile-list pipeline ----
-  int* tile_off;     // nt + 1   exclusive offsets
-  int* tile_cur;     // nt + 1   fill cursors (copy of the offsets)
   GsrRec* rec_in;    // s        records, input order
-  uint2* box_in;     // s        packed cull boxes, input order (x0 > x1: skipped Gaussian)
-  uint2* entries;    // ecap     {Gaussian index, region mask | binds << 16}
-  int ntx, nty, nt, ntscan, ecap;
+  uint2* box_in;     // s        packed cull boxes, input order (only read for window-binding ones)
+  uint2* entries;    // nt * tile_cap   {Gaussian index, region mask | binds << 16}
+  int ntx, nty, nt, tile_cap;
   // ---- home-bin pipeline ----
   int* bin_off;      // nb + 2   exclusive offsets; [nb] = start of large, [nb+1] = n_live
   uint2* box_tmp;    // s   (unsorted)
@@ -77,20 +75,16 @@ static inline GsrWorkspace gsr_carve(void* base, int s, int h, int w) {
   };
   const size_t sn = (size_t)(s > 0 ? s : 1);
   ws.nscan = (ws.nb + 1 + GSR_SCAN_CHUNK - 1) / GSR_SCAN_CHUNK;
-  ws.ntscan = (ws.nt + GSR_SCAN_CHUNK - 1) / GSR_SCAN_CHUNK;
-  ws.zero_bytes = ((size_t)ws.nb + 1 + 8 + 2 * (size_t)ws.nscan + (size_t)ws.nt + 2 * (size_t)ws.ntscan) * sizeof(int);
+  ws.zero_bytes = ((size_t)ws.nb + 1 + 8 + 2 * (size_t)ws.nscan + (size_t)ws.nt) * sizeof(int);
   ws.bin_count = (int*)take(ws.zero_bytes);
   ws.stats = ws.bin_count ? ws.bin_count + ws.nb + 1 : nullptr;
   ws.scan_state = ws.bin_count ? ws.stats + 8 : nullptr;
   ws.tile_count = ws.bin_count ? ws.scan_state + 2 * ws.nscan : nullptr;
-  ws.tscan_state = ws.bin_count ? ws.tile_count + ws.nt : nullptr;
-  ws.tile_off = (int*)take(((size_t)ws.nt + 1) * sizeof(int));
-  ws.tile_cur = (int*)take(((size_t)ws.nt + 1) * sizeof(int));
   ws.rec_in = (GsrRec*)take(sn * sizeof(GsrRec));
   ws.box_in = (uint2*)take(sn * sizeof(uint2));
-  const size_t ecap = (size_t)GSR_ENTRIES_PER_GAUSSIAN * (size_t)(s > 0 ? s : 0) + 256;
-  ws.ecap = (int)(ecap > 0x7fffff00u ? 0x7fffff00u : ecap);
-  ws.entries = (uint2*)take((size_t)ws.ecap * sizeof(uint2));
+  const size_t per_tile = ((size_t)GSR_ENTRIES_PER_GAUSSIAN * (size_t)(s > 0 ? s : 0) + ws.nt - 1) / ws.nt + 64;
+  ws.tile_cap = (int)(per_tile > 0x3fffffffu ? 0x3fffffffu : per_tile);
+  ws.entries = (uint2*)take((size_t)ws.nt * (size_t)ws.tile_cap * sizeof(uint2));
   ws.bin_off = (int*)take(((size_t)ws.nb + 2) * sizeof(int));
   ws.px_tab = (float*)take((size_t)w * sizeof(float));
   ws.py_tab = (float*)take((size_t)h * sizeof(float));
@@ -380,13 +374,14 @@ __device__ __forceinline__ void gsr_warp_tiles(bool live, const GsrRec& r, int x
 }
 
 __global__ void __launch_bounds__(256)
-gsr_tile_count_kernel(const float* __restrict__ sigmas, const float* __restrict__ coords,
+gsr_tile_build_kernel(const float* __restrict__ sigmas, const float* __restrict__ coords,
                       const float* __restrict__ colors, int s, int h, int w, float dmax,
                       float ksigma, float ecut, GsrWorkspace ws) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // the grid covers s rounded up to 32
   const int lane = threadIdx.x & 31;
   GsrSetup st;
   st.live = false;
+  st.binds = false;
   st.x0 = st.y0 = 1;
   st.x1 = st.y1 = 0;
   GsrRec r;
@@ -409,49 +404,29 @@ gsr_tile_count_kernel(const float* __restrict__ sigmas, const float* __restrict_
       float4* dr = reinterpret_cast<float4*>(ws.rec_in + i);
       dr[0] = make_float4(r.x, r.y, r.a, r.b);
       dr[1] = make_float4(r.c, r.r, r.g, r.bl);
-      ws.box_in[i] = gsr_box_pack(st.x0, st.x1, st.y0, st.y1, st.binds);
-    } else {
-      ws.box_in[i] = gsr_box_pack(1, 0, 1, 0, false);  // empty: skipped by the fill kernel
+      if (st.binds) ws.box_in[i] = gsr_box_pack(st.x0, st.x1, st.y0, st.y1, true);
     }
   }
   int* cnt = ws.tile_count;
-  gsr_warp_tiles(st.live, r, st.x0, st.x1, st.y0, st.y1, h, w, ws.ntx, ecut,
-                 [&](int t, uint32_t, unsigned bal) {
-                   if (lane == __ffs(bal) - 1) atomicAdd(cnt + t, __popc(bal));
-                 },
-                 [&](int t, uint32_t) { atomicAdd(cnt + t, 1); });
-}
-
-__global__ void __launch_bounds__(256)
-gsr_tile_fill_kernel(int s, int h, int w, float ecut, GsrWorkspace ws, const int* guard, int want) {
-  if (gsr_guard_skip(guard, want)) return;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  int x0 = 1, x1 = 0, y0 = 1, y1 = 0;
-  bool binds = false;
-  GsrRec r;
-  r.x = r.y = r.a = r.b = r.c = r.r = r.g = r.bl = 0.f;
-  if (i < s) gsr_box_unpack(ws.box_in[i], x0, x1, y0, y1, binds);
-  const bool live = x0 <= x1;
-  if (live) {
-    const float4* rp = reinterpret_cast<const float4*>(ws.rec_in + i);
-    const float4 q0 = rp[0], q1 = rp[1];
-    r.x = q0.x; r.y = q0.y; r.a = q0.z; r.b = q0.w;
-    r.c = q1.x; r.r = q1.y; r.g = q1.z; r.bl = q1.w;
-  }
-  int* cur = ws.tile_cur;
   uint2* ent = ws.entries;
-  const uint32_t fl = binds ? 0x10000u : 0u;
-  gsr_warp_tiles(live, r, x0, x1, y0, y1, h, w, ws.ntx, ecut,
+  const int cap = ws.tile_cap;
+  int* overflow = ws.stats + GSR_STAT_OVERFLOW;
+  const uint32_t fl = st.binds ? 0x10000u : 0u;
+  gsr_warp_tiles(st.live, r, st.x0, st.x1, st.y0, st.y1, h, w, ws.ntx, ecut,
                  [&](int t, uint32_t m, unsigned bal) {
                    const int leader = __ffs(bal) - 1;
                    int base = 0;
-                   if (lane == leader) base = atomicAdd(cur + t, __popc(bal));
+                   if (lane == leader) base = atomicAdd(cnt + t, __popc(bal));
                    base = __shfl_sync(0xffffffffu, base, leader);
-                   if (m) ent[base + __popc(bal & ((1u << lane) - 1u))] = make_uint2((uint32_t)i, m | fl);
+                   if (m) {
+                     const int pos = base + __popc(bal & ((1u << lane) - 1u));
+                     if (pos < cap) ent[(size_t)t * cap + pos] = make_uint2((uint32_t)i, m | fl);
+                     else *overflow = 1;
+                   }
                  },
                  [&](int t, uint32_t m) {
-                   const int slot = atomicAdd(cur + t, 1);
-                   ent[slot] = make_uint2((uint32_t)i, m | fl);
+                   const int pos = atomicAdd(cnt + t, 1);
+                   if (pos < cap) ent[(size_t)t * cap + pos] = make_uint2((uint32_t)i, m | fl);
+                   else *overflow = 1;
                  });
 }

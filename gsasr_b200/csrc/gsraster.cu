@@ -72,18 +72,13 @@ static int gsr_run_bins(const float* sigmas, const float* coords, const float* c
   return GSR_OK;
 }
 
-// Tile-list pipeline T1..T3.  Raises stats[GSR_STAT_OVERFLOW] when the entries do not fit.
+// Tile-list pipeline (one kernel).  Raises stats[GSR_STAT_OVERFLOW] when a bucket overflows.
 static int gsr_run_tiles(const float* sigmas, const float* coords, const float* colors, int s,
                          int h, int w, float dmax, float keff, const GsrWorkspace& ws,
                          cudaStream_t st) {
-  const float ecut = gsr_ecut(keff);
   if (s > 0)
-    gsr_tile_count_kernel<<<(s + 255) / 256, 256, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff,
-                                                           ecut, ws);
-  gsr_scan_kernel<<<ws.ntscan, 1024, 0, st>>>(ws.tile_count, ws.tile_off, ws.tile_cur, ws.nt,
-                                              ws.tscan_state, ws.ecap, ws.stats, nullptr, 0);
-  if (s > 0)
-    gsr_tile_fill_kernel<<<(s + 255) / 256, 256, 0, st>>>(s, h, w, ecut, ws, ws.stats + GSR_STAT_OVERFLOW, 0);
+    gsr_tile_build_kernel<<<(s + 255) / 256, 256, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff,
+                                                           gsr_ecut(keff), ws);
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
 }
@@ -107,7 +102,8 @@ static GsrFwdArgs gsr_fwd_args(const GsrWorkspace& ws, float* img, int h, int w,
   a.flags = flags;
   a.guard = ws.stats + GSR_STAT_OVERFLOW;
   a.want = 0;
-  a.tile_off = ws.tile_off;
+  a.tile_count = ws.tile_count;
+  a.tile_cap = ws.tile_cap;
   a.entries = ws.entries;
   a.rec_in = ws.rec_in;
   a.box_in = ws.box_in;
