@@ -316,31 +316,49 @@ __device__ __forceinline__ void gsr_for_each_tile(const GsrRec& r, int x0, int x
   }
 }
 
-// Warp-cooperative form: the 32 Gaussians of a warp are consecutive in the input, which for a
-// fea2gs field means spatially adjacent (utils/fea2gs.py:553-563), so their tile sets overlap
-// heavily.  The warp walks the UNION of the lanes' tile rectangles; per tile every lane computes
-// its mask and `coop(tile, mask, ballot of lanes with a non-empty mask)` is called once -- one
-// atomic per (warp, tile) instead of one per (Gaussian, tile), and coalesced entry writes.  If the
-// union is large (incoherent input) every lane walks its own tiles and `single(tile, mask)` is
-// called instead.  All 32 lanes must call this function (dead lanes pass live = false).
-constexpr int GSR_COOP_MAX_TILES = 96;
+// Warp-cooperative bucket append.  The 32 Gaussians of a warp are consecutive in the input, which
+// for a fea2gs field means spatially adjacent (utils/fea2gs.py:553-563), so their tile sets overlap
+// heavily.  The warp walks the UNION of the lanes' tile rectangles (at most GSR_COOP_MAX_TILES
+// tiles) in three phases:
+//   1. per tile every lane computes its region mask; non-empty tiles are staged in shared memory
+//      (tile id, ballot, the lanes' masks);
+//   2. lane j reserves the slots of staged tile j with ONE atomicAdd -- all reservations of the
+//      warp are in flight together, so the atomic round trip is paid once per warp;
+//   3. per staged tile the lanes with a non-empty mask write their entries, contiguously.
+// If the union is larger (incoherent input) every lane walks its own tiles with one atomic each.
+// All 32 lanes must call this function (dead lanes pass live = false).
+constexpr int GSR_COOP_MAX_TILES = 24;
 
-template <class FC, class FS>
-__device__ __forceinline__ void gsr_warp_tiles(bool live, const GsrRec& r, int x0, int x1, int y0,
-                                               int y1, int h, int w, int ntx, float ecut, FC&& coop,
-                                               FS&& single) {
+struct GsrCoopStage {
+  int tile[GSR_COOP_MAX_TILES];
+  unsigned ballot[GSR_COOP_MAX_TILES];
+  uint16_t mask[GSR_COOP_MAX_TILES][32];
+};
+
+__device__ __forceinline__ void gsr_warp_append(GsrCoopStage& sg, bool live, const GsrRec& r, int gi,
+                                                uint32_t fl, int x0, int x1, int y0, int y1, int h,
+                                                int w, int ntx, float ecut, int* __restrict__ cnt,
+                                                uint2* __restrict__ ent, int cap, int* overflow) {
   const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
   const int tx0 = live ? x0 / GSR_TILE_W : 0x3fffffff, tx1 = live ? x1 / GSR_TILE_W : -1;
   const int ty0 = live ? y0 / GSR_TILE_H : 0x3fffffff, ty1 = live ? y1 / GSR_TILE_H : -1;
   const int ux0 = __reduce_min_sync(full, tx0), ux1 = __reduce_max_sync(full, tx1);
   const int uy0 = __reduce_min_sync(full, ty0), uy1 = __reduce_max_sync(full, ty1);
   if (ux1 < ux0 || uy1 < uy0) return;  // no live lane
   if ((long long)(ux1 - ux0 + 1) * (uy1 - uy0 + 1) > GSR_COOP_MAX_TILES) {
-    if (live) gsr_for_each_tile(r, x0, x1, y0, y1, h, w, ntx, ecut, single);
+    if (live)
+      gsr_for_each_tile(r, x0, x1, y0, y1, h, w, ntx, ecut, [&](int t, uint32_t m) {
+        const int pos = atomicAdd(cnt + t, 1);
+        if (pos < cap) ent[(size_t)t * cap + pos] = make_uint2((uint32_t)gi, m | fl);
+        else *overflow = 1;
+      });
     return;
   }
+  // ---- phase 1: masks of every tile of the union ----
   GsrEllipse e;
   if (live) e = gsr_ellipse(r, h, w);
+  int nj = 0;
   for (int ty = uy0; ty <= uy1; ++ty) {
     int xl[GSR_NRY], xh[GSR_NRY];
     const bool in_row = live && ty >= ty0 && ty <= ty1;
@@ -368,9 +386,32 @@ __device__ __forceinline__ void gsr_warp_tiles(bool live, const GsrRec& r, int x
         }
       }
       const unsigned bal = __ballot_sync(full, m != 0);
-      if (bal) coop(ty * ntx + tx, m, bal);
+      if (bal) {
+        if (lane == 0) {
+          sg.tile[nj] = ty * ntx + tx;
+          sg.ballot[nj] = bal;
+        }
+        sg.mask[nj][lane] = (uint16_t)m;
+        ++nj;
+      }
     }
   }
+  __syncwarp();
+  // ---- phase 2: one reservation per staged tile, all in flight together ----
+  int base = 0;
+  if (lane < nj) base = atomicAdd(cnt + sg.tile[lane], __popc(sg.ballot[lane]));
+  // ---- phase 3: write the entries ----
+  for (int j = 0; j < nj; ++j) {
+    const int b = __shfl_sync(full, base, j);
+    const unsigned bal = sg.ballot[j];
+    const uint32_t m = sg.mask[j][lane];
+    if (m) {
+      const int pos = b + __popc(bal & ((1u << lane) - 1u));
+      if (pos < cap) ent[(size_t)sg.tile[j] * cap + pos] = make_uint2((uint32_t)gi, m | fl);
+      else *overflow = 1;
+    }
+  }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(256)
@@ -407,26 +448,8 @@ gsr_tile_build_kernel(const float* __restrict__ sigmas, const float* __restrict_
       if (st.binds) ws.box_in[i] = gsr_box_pack(st.x0, st.x1, st.y0, st.y1, true);
     }
   }
-  int* cnt = ws.tile_count;
-  uint2* ent = ws.entries;
-  const int cap = ws.tile_cap;
-  int* overflow = ws.stats + GSR_STAT_OVERFLOW;
-  const uint32_t fl = st.binds ? 0x10000u : 0u;
-  gsr_warp_tiles(st.live, r, st.x0, st.x1, st.y0, st.y1, h, w, ws.ntx, ecut,
-                 [&](int t, uint32_t m, unsigned bal) {
-                   const int leader = __ffs(bal) - 1;
-                   int base = 0;
-                   if (lane == leader) base = atomicAdd(cnt + t, __popc(bal));
-                   base = __shfl_sync(0xffffffffu, base, leader);
-                   if (m) {
-                     const int pos = base + __popc(bal & ((1u << lane) - 1u));
-                     if (pos < cap) ent[(size_t)t * cap + pos] = make_uint2((uint32_t)i, m | fl);
-                     else *overflow = 1;
-                   }
-                 },
-                 [&](int t, uint32_t m) {
-                   const int pos = atomicAdd(cnt + t, 1);
-                   if (pos < cap) ent[(size_t)t * cap + pos] = make_uint2((uint32_t)i, m | fl);
-                   else *overflow = 1;
-                 });
+  __shared__ GsrCoopStage stage[8];  // one per warp of the CTA
+  gsr_warp_append(stage[threadIdx.x >> 5], st.live, r, i, st.binds ? 0x10000u : 0u, st.x0, st.x1, st.y0,
+                  st.y1, h, w, ws.ntx, ecut, ws.tile_count, ws.entries, ws.tile_cap,
+                  ws.stats + GSR_STAT_OVERFLOW);
 }
