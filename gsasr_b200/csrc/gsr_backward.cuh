@@ -35,10 +35,14 @@ constexpr int GSR_BWD_LARGE_CHUNK = 64;                // large-list Gaussians p
 static_assert(GSR_BWD_RS % 32 == 8 && GSR_BWD_RS >= GSR_BWD_RW, "conflict-free patch reads");
 static_assert(GSR_BWD_TILE % GSR_BIN == 0, "super tile is made of whole bins");
 
+constexpr int GSR_BWD_BATCH = 16;  // Gaussians a warp reduces before one lane-parallel chain rule
+
 struct GsrBwdSmem {
   float plane[3 * GSR_BWD_PLANE];
   float px[GSR_BWD_RW];
   float py[GSR_BWD_RW];
+  float tot[GSR_BWD_WARPS][GSR_BWD_BATCH][8];  // reduced sums of the current batch
+  int tot_gi[GSR_BWD_WARPS][GSR_BWD_BATCH];    // sorted index of the Gaussians of the batch
 };
 
 struct GsrBwdArgs {
@@ -165,8 +169,9 @@ __device__ __forceinline__ void gsr_bwd_sweep_gmem(GsrBwdAcc& acc, const GsrBwdA
 //   d/dsx  = -(b Sxy + 2 a Sxx) / (L sx)    d/dsy  = -(b Sxy + 2 c Syy) / (L sy)
 //   d/drho = (2 rho Q / L + Sxy / (sx sy)) / (1 - rho^2),   Q = a Sxx + b Sxy + c Syy
 // (Q cancels strongly for |rho| -> 1 and is formed in double.)
-__device__ __forceinline__ void gsr_bwd_finish(const GsrBwdAcc& acc, const GsrBwdArgs& p, int gi,
-                                               int lane, const float4& a0, const float4& a1) {
+// Recursive-halving reduction of the eight sums: afterwards total k lives in the lanes whose
+// (bit4, bit3, bit2) = (k>>2&1, k>>1&1, k&1); lanes 0,4,...,28 store one total each.
+__device__ __forceinline__ void gsr_bwd_reduce_store(const GsrBwdAcc& acc, int lane, float* dst8) {
   float v[8] = {acc.cr, acc.cg, acc.cb, acc.sx, acc.sy, acc.sxx, acc.sxy, acc.syy};
   const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
   float w4[4];
@@ -184,11 +189,14 @@ __device__ __forceinline__ void gsr_bwd_finish(const GsrBwdAcc& acc, const GsrBw
   float x = (b2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? w2[0] : w2[1], 4);
   x += __shfl_xor_sync(0xffffffffu, x, 2);
   x += __shfl_xor_sync(0xffffffffu, x, 1);
-  // value k now lives in the lanes with (bit4,bit3,bit2) = (k>>2&1, k>>1&1, k&1)
-  float t[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) t[k] = __shfl_sync(0xffffffffu, x, ((k >> 2) & 1) * 16 + ((k >> 1) & 1) * 8 + (k & 1) * 4);
-  if (lane != 0) return;
+  if ((lane & 3) == 0) dst8[(b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0)] = x;
+}
+
+// Chain rule for ONE Gaussian (executed lane-parallel: one lane per Gaussian of a batch) and the
+// single read-modify-write per output value.
+__device__ __forceinline__ void gsr_bwd_chain(const float* t, const GsrBwdArgs& p, int gi) {
+  const float4* rp = reinterpret_cast<const float4*>(p.rec + gi);
+  const float4 a0 = __ldg(rp), a1 = __ldg(rp + 1);
   const int id = __ldg(p.ids + gi);
   const float sgx = __ldg(p.sigmas + 3 * (size_t)id + 0);
   const float sgy = __ldg(p.sigmas + 3 * (size_t)id + 1);
@@ -228,15 +236,25 @@ __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwd
     const int l0 = __ldg(p.bin_off + p.nb), l1 = __ldg(p.bin_off + p.nb + 1);
     const int c0 = l0 + ((int)blockIdx.x - ntiles) * GSR_BWD_LARGE_CHUNK;
     const int c1 = min(c0 + GSR_BWD_LARGE_CHUNK, l1);
-    for (int gi = c0 + warp; gi < c1; gi += GSR_BWD_WARPS) {
-      const float4* rp = reinterpret_cast<const float4*>(p.rec + gi);
-      const float4 a0 = __ldg(rp), a1 = __ldg(rp + 1);
-      int bx0, bx1, by0, by1;
-      bool binds;
-      gsr_box_unpack(__ldg(p.box + gi), bx0, bx1, by0, by1, binds);
-      GsrBwdAcc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      gsr_bwd_sweep_gmem(acc, p, a0, a1, bx0, bx1, by0, by1, lx, ly);
-      gsr_bwd_finish(acc, p, gi, lane, a0, a1);
+    for (int g0 = c0 + warp; g0 < c1; g0 += GSR_BWD_WARPS * GSR_BWD_BATCH) {
+      int nb = 0;
+      for (int j = 0; j < GSR_BWD_BATCH; ++j) {
+        const int gi = g0 + j * GSR_BWD_WARPS;
+        if (gi >= c1) break;
+        const float4* rp = reinterpret_cast<const float4*>(p.rec + gi);
+        const float4 a0 = __ldg(rp), a1 = __ldg(rp + 1);
+        int bx0, bx1, by0, by1;
+        bool binds;
+        gsr_box_unpack(__ldg(p.box + gi), bx0, bx1, by0, by1, binds);
+        GsrBwdAcc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        gsr_bwd_sweep_gmem(acc, p, a0, a1, bx0, bx1, by0, by1, lx, ly);
+        gsr_bwd_reduce_store(acc, lane, sm.tot[warp][j]);
+        if (lane == 0) sm.tot_gi[warp][j] = gi;
+        ++nb;
+      }
+      __syncwarp();
+      if (lane < nb) gsr_bwd_chain(sm.tot[warp][lane], p, sm.tot_gi[warp][lane]);
+      __syncwarp();
     }
     return;
   }
@@ -288,24 +306,34 @@ __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwd
   __syncthreads();
 
   const uint32_t plane_s = gsr_smem_addr(sm.plane), px_s = gsr_smem_addr(sm.px), py_s = gsr_smem_addr(sm.py);
-  // ---- one Gaussian per warp at a time ----
-  for (int k = warp; k < ntot; k += GSR_BWD_WARPS) {
-    int gi = 0, kk = k;
+  // ---- one Gaussian per warp at a time, chain rule once per batch ----
+  for (int k0 = warp; k0 < ntot; k0 += GSR_BWD_WARPS * GSR_BWD_BATCH) {
+    int nb = 0;
+    for (int j = 0; j < GSR_BWD_BATCH; ++j) {
+      const int k = k0 + j * GSR_BWD_WARPS;
+      if (k >= ntot) break;
+      int gi = 0, kk = k;
 #pragma unroll
-    for (int r = 0; r < BPT; ++r) {
-      if (kk >= 0 && kk < run_n[r]) gi = run_s[r] + kk;
-      kk = kk < run_n[r] ? -1 : kk - run_n[r];
+      for (int r = 0; r < BPT; ++r) {
+        if (kk >= 0 && kk < run_n[r]) gi = run_s[r] + kk;
+        kk = kk < run_n[r] ? -1 : kk - run_n[r];
+      }
+      const float4* rp = reinterpret_cast<const float4*>(p.rec + gi);
+      const float4 a0 = __ldg(rp), a1 = __ldg(rp + 1);
+      int bx0, bx1, by0, by1;
+      bool binds;
+      gsr_box_unpack(__ldg(p.box + gi), bx0, bx1, by0, by1, binds);
+      GsrBwdAcc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (bx0 >= sx0 && bx1 <= sx1 && by0 >= sy0 && by1 <= sy1)
+        gsr_bwd_sweep_smem(acc, plane_s, px_s, py_s, a0, a1, bx0, bx1, by0, by1, sx0, sy0, lx, ly);
+      else
+        gsr_bwd_sweep_gmem(acc, p, a0, a1, bx0, bx1, by0, by1, lx, ly);
+      gsr_bwd_reduce_store(acc, lane, sm.tot[warp][j]);
+      if (lane == 0) sm.tot_gi[warp][j] = gi;
+      ++nb;
     }
-    const float4* rp = reinterpret_cast<const float4*>(p.rec + gi);
-    const float4 a0 = __ldg(rp), a1 = __ldg(rp + 1);
-    int bx0, bx1, by0, by1;
-    bool binds;
-    gsr_box_unpack(__ldg(p.box + gi), bx0, bx1, by0, by1, binds);
-    GsrBwdAcc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (bx0 >= sx0 && bx1 <= sx1 && by0 >= sy0 && by1 <= sy1)
-      gsr_bwd_sweep_smem(acc, plane_s, px_s, py_s, a0, a1, bx0, bx1, by0, by1, sx0, sy0, lx, ly);
-    else
-      gsr_bwd_sweep_gmem(acc, p, a0, a1, bx0, bx1, by0, by1, lx, ly);
-    gsr_bwd_finish(acc, p, gi, lane, a0, a1);
+    __syncwarp();
+    if (lane < nb) gsr_bwd_chain(sm.tot[warp][lane], p, sm.tot_gi[warp][lane]);
+    __syncwarp();
   }
 }
