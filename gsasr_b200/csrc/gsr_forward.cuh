@@ -134,10 +134,10 @@ struct GsrFwdArgs {
   uint32_t flags;
   const int* guard;  // run only if *guard == want (nullptr: always)
   int want;
-  // tile-list path
-  const int* tile_count;
-  int tile_cap;
-  const uint2* entries;
+  // region-bucket path
+  const int* reg_count;
+  int reg_cap, nrx;
+  const uint32_t* entries;
   const GsrRec* rec_in;
   const uint2* box_in;
   int ntx;
@@ -383,122 +383,95 @@ __global__ void __launch_bounds__(GSR_FWD_THREADS, GSR_CFG_MIN_CTAS) gsr_forward
   }  // tile loop
 }
 
-// ---- tile-list forward kernel (the fast path) ---------------------------------------------------
-// One CTA per 32x16 tile, one warp per 8x8 region, two pixels per lane.  The tile's entries
-// {Gaussian index, region mask} were produced by the set-up pipeline; per round of
-// GSR_FL_CHUNK entries every lane takes GSR_FL_PER_LANE of them, gathers the 32-byte records
-// (and, for window-binding Gaussians, the cull boxes) into shared memory with cp.async and
-// appends the slot to its warp's list for every region of the mask (ranks from ballots, no
-// atomics).  After one barrier each warp walks the lists left for its region.
-constexpr int GSR_FL_THREADS = 32 * GSR_NRX * GSR_NRY;
-constexpr int GSR_FL_WARPS = GSR_FL_THREADS / 32;
-#ifndef GSR_CFG_FL_PER_LANE
-#define GSR_CFG_FL_PER_LANE 2
+// ---- region-bucket forward kernel (the fast path) ------------------------------------------------
+// One warp per 8x8-pixel region (two horizontally adjacent pixels per lane), eight warps = one
+// 32x16 tile per CTA, and NOTHING shared between the warps: no culling, no lists, no CTA barrier.
+// The region's bucket (4-byte Gaussian indices written by gsr_region_build_kernel) is streamed 32
+// entries at a time: lane i gathers record i (32 B, two LDG.128) into registers while the warp
+// evaluates the previous 32 records from its private, double-buffered shared-memory slice
+// (2 broadcast LDS.128 per record).  Per record: FADD + 3 FMUL (row terms), FADD2 (dx pair),
+// 2 FFMA2 (exponent pair), 2 MUFU.EX2, 3 FFMA2 (colour pairs): 15 instructions for 64 pixel
+// evaluations.  Window-binding Gaussians (entry bit 31) also bring their cull box and are
+// evaluated with the exact per-pixel inclusion test.
+constexpr int GSR_FR_THREADS = 32 * GSR_NRX * GSR_NRY;
+constexpr int GSR_FR_WARPS = GSR_FR_THREADS / 32;
+#ifndef GSR_CFG_FR_UNROLL
+#define GSR_CFG_FR_UNROLL 8
 #endif
-constexpr int GSR_FL_PER_LANE = GSR_CFG_FL_PER_LANE;
-constexpr int GSR_FL_PER_WARP = 32 * GSR_FL_PER_LANE;
-constexpr int GSR_FL_CHUNK = GSR_FL_THREADS * GSR_FL_PER_LANE;
-#ifndef GSR_CFG_FL_UNROLL
-#define GSR_CFG_FL_UNROLL 4
+#ifndef GSR_CFG_FR_MIN_CTAS
+#define GSR_CFG_FR_MIN_CTAS 4
 #endif
-constexpr int GSR_FL_UNROLL = GSR_CFG_FL_UNROLL;
-#ifndef GSR_CFG_FL_UNROLL
-#define GSR_CFG_FL_UNROLL 2
-#endif
-#ifndef GSR_CFG_FL_MIN_CTAS
-#define GSR_CFG_FL_MIN_CTAS 4
-#endif
+constexpr int GSR_FR_UNROLL = GSR_CFG_FR_UNROLL;
 
-struct GsrFwdListSmem {
-  float4 rec[GSR_FL_CHUNK * 2];
-  uint2 box[GSR_FL_CHUNK];
-  uint16_t lfast[GSR_FL_WARPS][GSR_FL_WARPS][GSR_FL_PER_WARP];  // [producer warp][region]
-  uint16_t lslow[GSR_FL_WARPS][GSR_FL_WARPS][GSR_FL_PER_WARP];
-  uint8_t nfast[GSR_FL_WARPS][GSR_FL_WARPS];
-  uint8_t nslow[GSR_FL_WARPS][GSR_FL_WARPS];
+struct GsrFwdRegionSmem {
+  float4 rec[GSR_FR_WARPS][2][64];  // per warp, double buffered: 32 records of 2 x float4
+  uint2 box[GSR_FR_WARPS][2][32];
 };
 
-__global__ void __launch_bounds__(GSR_FL_THREADS, GSR_CFG_FL_MIN_CTAS) gsr_forward_list_kernel(GsrFwdArgs p) {
+__global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forward_region_kernel(GsrFwdArgs p) {
   if (gsr_guard_skip(p.guard, p.want)) return;
-  __shared__ GsrFwdListSmem sm;
+  __shared__ GsrFwdRegionSmem sm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tx0 = blockIdx.x * GSR_TILE_W, ty0 = blockIdx.y * GSR_TILE_H;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const int wi0 = tx0 + (warp % GSR_NRX) * GSR_REGION + (lane & 3) * 2;
-  const int hi = ty0 + (warp / GSR_NRX) * GSR_REGION + (lane >> 2);
+  const int rx = blockIdx.x * GSR_NRX + warp % GSR_NRX, ry = blockIdx.y * GSR_NRY + warp / GSR_NRX;
+  const int wi0 = rx * GSR_REGION + (lane & 3) * 2;
+  const int hi = ry * GSR_REGION + (lane >> 2);
   const float px0 = __ldg(p.px_tab + min(wi0, p.w - 1));
   const float px1 = __ldg(p.px_tab + min(wi0 + 1, p.w - 1));
   const float py = __ldg(p.py_tab + min(hi, p.h - 1));
-  gsr_f2 accr = gsr_pk(0.f, 0.f), accg = gsr_pk(0.f, 0.f), accb = gsr_pk(0.f, 0.f);
   const gsr_f2 px2 = gsr_pk(px0, px1);
-  const int tile = blockIdx.y * p.ntx + blockIdx.x;
-  const uint2* tile_entries = p.entries + (size_t)tile * p.tile_cap;  // this tile's bucket
-  const int e_begin = 0, e_end = min(__ldg(p.tile_count + tile), p.tile_cap);
-  const uint32_t rec_s = gsr_smem_addr(sm.rec);
-  const uint32_t box_s = gsr_smem_addr(sm.box);
+  gsr_f2 accr = gsr_pk(0.f, 0.f), accg = gsr_pk(0.f, 0.f), accb = gsr_pk(0.f, 0.f);
 
-  auto eval = [&](uint32_t addr, const bool in0, const bool in1) {
-    gsr_eval_pair(addr, px2, py, in0, in1, accr, accg, accb);
+  const int rid = ry * p.nrx + rx;
+  const int n = min(__ldg(p.reg_count + rid), p.reg_cap);
+  const uint32_t* ent = p.entries + (size_t)rid * p.reg_cap;
+  const uint32_t rec_s = gsr_smem_addr(&sm.rec[warp][0][0]);
+  uint2* box_w = &sm.box[warp][0][0];
+
+  // prefetch the first 32 records into registers
+  float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+  uint2 qb = make_uint2(0, 0);
+  bool qslow = false;
+  auto fetch = [&](int i) {
+    qslow = false;
+    if (i < n) {
+      const uint32_t en = __ldg(ent + i);
+      const uint32_t gi = en & 0x7fffffffu;
+      const float4* src = reinterpret_cast<const float4*>(p.rec_in + gi);
+      q0 = __ldg(src);
+      q1 = __ldg(src + 1);
+      qslow = (en >> 31) != 0;
+      if (qslow) qb = __ldg(p.box_in + gi);
+    }
   };
-
-  for (int e0 = e_begin; e0 < e_end; e0 += GSR_FL_CHUNK) {
-    // ---- stage A: gather records, build the region lists ----
-    int cf[GSR_FL_WARPS], cs[GSR_FL_WARPS];
-#pragma unroll
-    for (int rg = 0; rg < GSR_FL_WARPS; ++rg) cf[rg] = cs[rg] = 0;
-#pragma unroll
-    for (int k = 0; k < GSR_FL_PER_LANE; ++k) {
-      const int slot = warp * GSR_FL_PER_WARP + k * 32 + lane;
-      uint32_t m = 0;
-      bool binds = false;
-      if (e0 + slot < e_end) {
-        const uint2 en = __ldg(tile_entries + e0 + slot);
-        m = en.y & 0xffffu;
-        binds = (en.y & 0x10000u) != 0;
-        const float4* src = reinterpret_cast<const float4*>(p.rec_in + en.x);
-        gsr_cp_async16(rec_s + slot * 32, src);
-        gsr_cp_async16(rec_s + slot * 32 + 16, src + 1);
-        if (binds) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(box_s + slot * 8), "l"(p.box_in + en.x) : "memory");
-      }
-#pragma unroll
-      for (int rg = 0; rg < GSR_FL_WARPS; ++rg) {
-        const bool bit = (m >> rg) & 1u;
-        const unsigned balf = __ballot_sync(0xffffffffu, bit && !binds);
-        const unsigned bals = __ballot_sync(0xffffffffu, bit && binds);
-        if (bit) {
-          if (!binds) sm.lfast[warp][rg][cf[rg] + __popc(balf & lt_mask)] = (uint16_t)(slot * 32);
-          else sm.lslow[warp][rg][cs[rg] + __popc(bals & lt_mask)] = (uint16_t)slot;
+  fetch(lane);
+  int cur = 0;
+  for (int c0 = 0; c0 < n; c0 += 32) {
+    const int cnt = min(32, n - c0);
+    const uint32_t buf = rec_s + cur * (64 * 16);
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(buf + lane * 32), "f"(q0.x), "f"(q0.y), "f"(q0.z), "f"(q0.w) : "memory");
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(buf + lane * 32 + 16), "f"(q1.x), "f"(q1.y), "f"(q1.z), "f"(q1.w) : "memory");
+    if (qslow) box_w[cur * 32 + lane] = qb;
+    const unsigned slow = __ballot_sync(0xffffffffu, qslow);
+    __syncwarp();
+    fetch(c0 + 32 + lane);  // next chunk: in flight while this one is evaluated
+    if (slow == 0) {
+#pragma unroll GSR_FR_UNROLL
+      for (int j = 0; j < cnt; ++j) gsr_eval_pair(buf + j * 32, px2, py, true, true, accr, accg, accb);
+    } else {
+      for (int j = 0; j < cnt; ++j) {
+        if ((slow >> j) & 1u) {  // dmax window cuts this Gaussian: exact inclusion per pixel
+          int bx0, bx1, by0, by1;
+          bool binds;
+          gsr_box_unpack(box_w[cur * 32 + j], bx0, bx1, by0, by1, binds);
+          const bool iny = hi >= by0 && hi <= by1;
+          gsr_eval_pair(buf + j * 32, px2, py, iny && wi0 >= bx0 && wi0 <= bx1,
+                        iny && wi0 + 1 >= bx0 && wi0 + 1 <= bx1, accr, accg, accb);
+        } else {
+          gsr_eval_pair(buf + j * 32, px2, py, true, true, accr, accg, accb);
         }
-        cf[rg] += __popc(balf);
-        cs[rg] += __popc(bals);
       }
     }
-#pragma unroll
-    for (int rg = 0; rg < GSR_FL_WARPS; ++rg)
-      if (lane == rg) {
-        sm.nfast[warp][rg] = (uint8_t)cf[rg];
-        sm.nslow[warp][rg] = (uint8_t)cs[rg];
-      }
-    gsr_cp_async_wait_all();
-    __syncthreads();
-    // ---- stage C: walk the lists every producer warp left for this region ----
-    for (int pw = 0; pw < GSR_FL_WARPS; ++pw) {
-      const int nf = sm.nfast[pw][warp];
-      const uint32_t lf = gsr_smem_addr(sm.lfast[pw][warp]);  // byte offsets of the records
-#pragma unroll GSR_FL_UNROLL
-      for (int i = 0; i < nf; ++i) eval(rec_s + gsr_lds_u16(lf + 2 * i), true, true);
-      const int ns = sm.nslow[pw][warp];
-      const uint16_t* ls = sm.lslow[pw][warp];
-      for (int i = 0; i < ns; ++i) {  // dmax window cuts this Gaussian: exact inclusion per pixel
-        const int slot = ls[i];
-        int bx0, bx1, by0, by1;
-        bool binds;
-        gsr_box_unpack(sm.box[slot], bx0, bx1, by0, by1, binds);
-        const bool iny = hi >= by0 && hi <= by1;
-        eval(rec_s + (slot << 5), iny && wi0 >= bx0 && wi0 <= bx1, iny && wi0 + 1 >= bx0 && wi0 + 1 <= bx1);
-      }
-    }
-    __syncthreads();
+    cur ^= 1;
   }
   {
     float r0, r1, g0, g1, b0, b1;

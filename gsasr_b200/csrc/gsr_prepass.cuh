@@ -1,15 +1,15 @@
 // gsr_prepass.cuh -- O(N) set-up pipelines shared by forward and backward.
 //
-// Tile-list pipeline (forward fast path), ONE pass over the Gaussians:
-//   T1 gsr_tile_build_kernel  per Gaussian: exact dmax window /\ k-sigma box -> cull box, raster
-//                             record (written in input order), and for every 32x16 tile whose
-//                             8x8 regions the ellipse touches an 8-byte entry {index, region mask}
-//                             appended to the tile's bucket (warp-cooperative: one atomic per
-//                             (warp, tile), coalesced entry writes).
-//   Every tile owns a fixed-capacity bucket (8 N / tiles + 64 entries: GSASR emits its Gaussians on
-//   a regular grid, utils/fea2gs.py:553-563, so the load per tile is uniform); an entry that does
-//   not fit raises the overflow flag and the forward falls back to the home-bin pipeline.
-//   The forward kernel then streams each tile's bucket and gathers the 32-byte records.
+// Region-bucket pipeline (forward fast path), ONE pass over the Gaussians:
+//   T1 gsr_region_build_kernel  per Gaussian: exact dmax window /\ k-sigma box -> cull box, raster
+//                               record (written in input order); then for every 8x8-pixel region
+//                               the ellipse touches a 4-byte entry {index | binds << 31} is appended
+//                               to the region's bucket (warp-cooperative: one atomic per
+//                               (warp, region), all reservations of a warp in flight together).
+//   Every region owns a fixed-capacity bucket (16 N / regions + 64 entries: GSASR emits its Gaussians
+//   on a regular grid, utils/fea2gs.py:553-563, so the load per region is uniform); an entry that
+//   does not fit raises the overflow flag and the forward falls back to the home-bin pipeline.
+//   The forward kernel then needs no culling at all: one warp per region streams its bucket.
 //
 // Home-bin pipeline (backward; forward fallback when the tile lists overflow their capacity):
 //   K1 gsr_bin_kernel     per Gaussian: cull box, home bin, rank inside the bin (atomic), reach.
@@ -25,20 +25,20 @@
 #include "gsr_common.cuh"
 
 constexpr int GSR_STAT_EXT_X = 0, GSR_STAT_EXT_Y = 1, GSR_STAT_OVERFLOW = 2, GSR_STAT_ENTRIES = 3;
-constexpr int GSR_ENTRIES_PER_GAUSSIAN = 8;  // bucket capacity per tile = 8 * N / tiles + 64
+constexpr int GSR_ENTRIES_PER_GAUSSIAN = 16;  // bucket capacity per region = 16 * N / regions + 64
 
 struct GsrWorkspace {
   // ---- one block, cleared per call ----
   int* bin_count;    // nb + 1
   int* stats;        // 8 ints, see GSR_STAT_*
   int* scan_state;   // 2 * nscan     look-back state of the bin scan
-  int* tile_count;   // nt        entries appended to each tile's bucket (may exceed tile_cap)
+  int* reg_count;    // nreg      entries appended to each region's bucket (may exceed reg_cap)
   size_t zero_bytes;
   // ---- tile-list pipeline ----
   GsrRec* rec_in;    // s        records, input order
   uint2* box_in;     // s        packed cull boxes, input order (only read for window-binding ones)
-  uint2* entries;    // nt * tile_cap   {Gaussian index, region mask | binds << 16}
-  int ntx, nty, nt, tile_cap;
+  uint32_t* entries; // nreg * reg_cap   Gaussian index | binds << 31
+  int ntx, nty, nrx, nry, nreg, reg_cap;
   // ---- home-bin pipeline ----
   int* bin_off;      // nb + 2   exclusive offsets; [nb] = start of large, [nb+1] = n_live
   uint2* box_tmp;    // s   (unsorted)
@@ -65,7 +65,9 @@ static inline GsrWorkspace gsr_carve(void* base, int s, int h, int w) {
   ws.nb = ws.nbx * ws.nby;
   ws.ntx = (w + GSR_TILE_W - 1) / GSR_TILE_W;
   ws.nty = (h + GSR_TILE_H - 1) / GSR_TILE_H;
-  ws.nt = ws.ntx * ws.nty;
+  ws.nrx = ws.ntx * GSR_NRX;  // region grid padded to whole tiles
+  ws.nry = ws.nty * GSR_NRY;
+  ws.nreg = ws.nrx * ws.nry;
   size_t off = 0;
   char* p = (char*)base;
   auto take = [&](size_t bytes) {
@@ -75,16 +77,16 @@ static inline GsrWorkspace gsr_carve(void* base, int s, int h, int w) {
   };
   const size_t sn = (size_t)(s > 0 ? s : 1);
   ws.nscan = (ws.nb + 1 + GSR_SCAN_CHUNK - 1) / GSR_SCAN_CHUNK;
-  ws.zero_bytes = ((size_t)ws.nb + 1 + 8 + 2 * (size_t)ws.nscan + (size_t)ws.nt) * sizeof(int);
+  ws.zero_bytes = ((size_t)ws.nb + 1 + 8 + 2 * (size_t)ws.nscan + (size_t)ws.nreg) * sizeof(int);
   ws.bin_count = (int*)take(ws.zero_bytes);
   ws.stats = ws.bin_count ? ws.bin_count + ws.nb + 1 : nullptr;
   ws.scan_state = ws.bin_count ? ws.stats + 8 : nullptr;
-  ws.tile_count = ws.bin_count ? ws.scan_state + 2 * ws.nscan : nullptr;
+  ws.reg_count = ws.bin_count ? ws.scan_state + 2 * ws.nscan : nullptr;
   ws.rec_in = (GsrRec*)take(sn * sizeof(GsrRec));
   ws.box_in = (uint2*)take(sn * sizeof(uint2));
-  const size_t per_tile = ((size_t)GSR_ENTRIES_PER_GAUSSIAN * (size_t)(s > 0 ? s : 0) + ws.nt - 1) / ws.nt + 64;
-  ws.tile_cap = (int)(per_tile > 0x3fffffffu ? 0x3fffffffu : per_tile);
-  ws.entries = (uint2*)take((size_t)ws.nt * (size_t)ws.tile_cap * sizeof(uint2));
+  const size_t per_reg = ((size_t)GSR_ENTRIES_PER_GAUSSIAN * (size_t)(s > 0 ? s : 0) + ws.nreg - 1) / ws.nreg + 64;
+  ws.reg_cap = (int)(per_reg > 0x3fffffffu ? 0x3fffffffu : per_reg);
+  ws.entries = (uint32_t*)take((size_t)ws.nreg * (size_t)ws.reg_cap * sizeof(uint32_t));
   ws.bin_off = (int*)take(((size_t)ws.nb + 2) * sizeof(int));
   ws.px_tab = (float*)take((size_t)w * sizeof(float));
   ws.py_tab = (float*)take((size_t)h * sizeof(float));
@@ -317,30 +319,39 @@ __device__ __forceinline__ void gsr_for_each_tile(const GsrRec& r, int x0, int x
 }
 
 // Warp-cooperative bucket append.  The 32 Gaussians of a warp are consecutive in the input, which
-// for a fea2gs field means spatially adjacent (utils/fea2gs.py:553-563), so their tile sets overlap
-// heavily.  The warp walks the UNION of the lanes' tile rectangles (at most GSR_COOP_MAX_TILES
-// tiles) in three phases:
-//   1. per tile every lane computes its region mask; non-empty tiles are staged in shared memory
-//      (tile id, ballot, the lanes' masks);
-//   2. lane j reserves the slots of staged tile j with ONE atomicAdd -- all reservations of the
-//      warp are in flight together, so the atomic round trip is paid once per warp;
-//   3. per staged tile the lanes with a non-empty mask write their entries, contiguously.
-// If the union is larger (incoherent input) every lane walks its own tiles with one atomic each.
-// All 32 lanes must call this function (dead lanes pass live = false).
+// for a fea2gs field means spatially adjacent (utils/fea2gs.py:553-563), so their region sets
+// overlap heavily.  The warp walks the UNION of the lanes' tile rectangles (at most
+// GSR_COOP_MAX_TILES tiles of GSR_NRX x GSR_NRY regions) in three phases:
+//   1. per tile every lane computes its region mask; for non-empty tiles the ballot of every
+//      region (which lanes touch it) is staged in shared memory;
+//   2. the non-empty (tile, region) pairs are compacted;
+//   3. lane = pair: one atomicAdd reserves the pair's slots (32 reservations in flight per
+//      instruction, so the atomic round trip is paid once per warp), then the lane streams the
+//      entries of its pair -- fetched from the owning lanes with shuffles -- into the bucket.
+// If the union is larger (incoherent input) every lane walks its own tiles with one atomic per
+// (Gaussian, region).  All 32 lanes must call this function (dead lanes pass live = false).
 constexpr int GSR_COOP_MAX_TILES = 24;
+constexpr int GSR_RPT = GSR_NRX * GSR_NRY;  // regions per tile (8)
 
 struct GsrCoopStage {
-  int tile[GSR_COOP_MAX_TILES];
-  unsigned ballot[GSR_COOP_MAX_TILES];
-  uint16_t mask[GSR_COOP_MAX_TILES][32];
+  int tile_x[GSR_COOP_MAX_TILES], tile_y[GSR_COOP_MAX_TILES];
+  unsigned ballot[GSR_COOP_MAX_TILES * GSR_RPT];
+  uint16_t pair[GSR_COOP_MAX_TILES * GSR_RPT];  // compacted non-empty (tile, region) pairs
 };
+static_assert(GSR_RPT <= 8, "per-lane tile masks are staged as bytes");
 
-__device__ __forceinline__ void gsr_warp_append(GsrCoopStage& sg, bool live, const GsrRec& r, int gi,
-                                                uint32_t fl, int x0, int x1, int y0, int y1, int h,
-                                                int w, int ntx, float ecut, int* __restrict__ cnt,
-                                                uint2* __restrict__ ent, int cap, int* overflow) {
+__device__ __forceinline__ int gsr_region_id(int tx, int ty, int rg, int nrx) {
+  return (ty * GSR_NRY + rg / GSR_NRX) * nrx + tx * GSR_NRX + rg % GSR_NRX;
+}
+
+__device__ __forceinline__ void gsr_warp_append(GsrCoopStage& sg, bool live, const GsrRec& r,
+                                                uint32_t entry, int x0, int x1, int y0, int y1, int h,
+                                                int w, int ntx, int nrx, float ecut,
+                                                int* __restrict__ cnt, uint32_t* __restrict__ ent,
+                                                int cap, int* overflow) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
   const int tx0 = live ? x0 / GSR_TILE_W : 0x3fffffff, tx1 = live ? x1 / GSR_TILE_W : -1;
   const int ty0 = live ? y0 / GSR_TILE_H : 0x3fffffff, ty1 = live ? y1 / GSR_TILE_H : -1;
   const int ux0 = __reduce_min_sync(full, tx0), ux1 = __reduce_max_sync(full, tx1);
@@ -349,13 +360,19 @@ __device__ __forceinline__ void gsr_warp_append(GsrCoopStage& sg, bool live, con
   if ((long long)(ux1 - ux0 + 1) * (uy1 - uy0 + 1) > GSR_COOP_MAX_TILES) {
     if (live)
       gsr_for_each_tile(r, x0, x1, y0, y1, h, w, ntx, ecut, [&](int t, uint32_t m) {
-        const int pos = atomicAdd(cnt + t, 1);
-        if (pos < cap) ent[(size_t)t * cap + pos] = make_uint2((uint32_t)gi, m | fl);
-        else *overflow = 1;
+        const int tx = t % ntx, ty = t / ntx;
+        while (m) {
+          const int rg = __ffs(m) - 1;
+          m &= m - 1;
+          const int rid = gsr_region_id(tx, ty, rg, nrx);
+          const int pos = atomicAdd(cnt + rid, 1);
+          if (pos < cap) ent[(size_t)rid * cap + pos] = entry;
+          else *overflow = 1;
+        }
       });
     return;
   }
-  // ---- phase 1: masks of every tile of the union ----
+  // ---- phase 1: masks of every tile of the union, ballots of every region ----
   GsrEllipse e;
   if (live) e = gsr_ellipse(r, h, w);
   int nj = 0;
@@ -385,37 +402,63 @@ __device__ __forceinline__ void gsr_warp_append(GsrCoopStage& sg, bool live, con
           m |= (((2u << r1) - 1u) & ~((1u << r0) - 1u)) << (ry * GSR_NRX);
         }
       }
-      const unsigned bal = __ballot_sync(full, m != 0);
-      if (bal) {
+      if (__ballot_sync(full, m != 0)) {
         if (lane == 0) {
-          sg.tile[nj] = ty * ntx + tx;
-          sg.ballot[nj] = bal;
+          sg.tile_x[nj] = tx;
+          sg.tile_y[nj] = ty;
         }
-        sg.mask[nj][lane] = (uint16_t)m;
+#pragma unroll
+        for (int rg = 0; rg < GSR_RPT; ++rg) {
+          const unsigned bal = __ballot_sync(full, (m >> rg) & 1u);
+          if (lane == rg) sg.ballot[nj * GSR_RPT + rg] = bal;
+        }
         ++nj;
       }
     }
   }
   __syncwarp();
-  // ---- phase 2: one reservation per staged tile, all in flight together ----
-  int base = 0;
-  if (lane < nj) base = atomicAdd(cnt + sg.tile[lane], __popc(sg.ballot[lane]));
-  // ---- phase 3: write the entries ----
-  for (int j = 0; j < nj; ++j) {
-    const int b = __shfl_sync(full, base, j);
-    const unsigned bal = sg.ballot[j];
-    const uint32_t m = sg.mask[j][lane];
-    if (m) {
-      const int pos = b + __popc(bal & ((1u << lane) - 1u));
-      if (pos < cap) ent[(size_t)sg.tile[j] * cap + pos] = make_uint2((uint32_t)gi, m | fl);
-      else *overflow = 1;
+  // ---- phase 2: compact the non-empty (tile, region) pairs ----
+  int np = 0;  // number of non-empty pairs (warp-uniform)
+  for (int q0 = 0; q0 < nj * GSR_RPT; q0 += 32) {
+    const int q = q0 + lane;
+    const bool has = q < nj * GSR_RPT && sg.ballot[q] != 0;
+    const unsigned hb = __ballot_sync(full, has);
+    if (has) sg.pair[np + __popc(hb & lt_mask)] = (uint16_t)q;
+    np += __popc(hb);
+  }
+  __syncwarp();
+  // ---- phase 3: lane = pair.  One reservation per pair (32 in flight per instruction), then the
+  //      lane streams the entries of its pair into the region's bucket: the k-th set bit of the
+  //      pair's ballot names the lane whose Gaussian goes to slot base + k. ----
+  for (int p0 = 0; p0 < np; p0 += 32) {
+    const bool act = p0 + lane < np;
+    unsigned bal = 0;
+    uint32_t* dst = ent;
+    int room = 0;
+    if (act) {
+      const int q = sg.pair[p0 + lane];
+      const int j = q / GSR_RPT, rg = q % GSR_RPT;
+      bal = sg.ballot[q];
+      const int rid = gsr_region_id(sg.tile_x[j], sg.tile_y[j], rg, nrx);
+      const int base = atomicAdd(cnt + rid, __popc(bal));
+      dst = ent + (size_t)rid * cap + base;
+      room = cap - base;  // entries that still fit
+      if (room < __popc(bal)) *overflow = 1;
+    }
+    const int iters = __reduce_max_sync(full, __popc(bal));
+    for (int k = 0; k < iters; ++k) {
+      const int src = bal ? __ffs(bal) - 1 : 0;
+      const uint32_t en = __shfl_sync(full, entry, src);
+      if (bal && k < room) dst[k] = en;
+      bal &= bal - 1;
     }
   }
   __syncwarp();
 }
 
+
 __global__ void __launch_bounds__(256)
-gsr_tile_build_kernel(const float* __restrict__ sigmas, const float* __restrict__ coords,
+gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restrict__ coords,
                       const float* __restrict__ colors, int s, int h, int w, float dmax,
                       float ksigma, float ecut, GsrWorkspace ws) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // the grid covers s rounded up to 32
@@ -449,7 +492,7 @@ gsr_tile_build_kernel(const float* __restrict__ sigmas, const float* __restrict_
     }
   }
   __shared__ GsrCoopStage stage[8];  // one per warp of the CTA
-  gsr_warp_append(stage[threadIdx.x >> 5], st.live, r, i, st.binds ? 0x10000u : 0u, st.x0, st.x1, st.y0,
-                  st.y1, h, w, ws.ntx, ecut, ws.tile_count, ws.entries, ws.tile_cap,
+  gsr_warp_append(stage[threadIdx.x >> 5], st.live, r, (uint32_t)i | (st.binds ? 0x80000000u : 0u), st.x0,
+                  st.x1, st.y0, st.y1, h, w, ws.ntx, ws.nrx, ecut, ws.reg_count, ws.entries, ws.reg_cap,
                   ws.stats + GSR_STAT_OVERFLOW);
 }

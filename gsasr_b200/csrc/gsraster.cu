@@ -72,12 +72,12 @@ static int gsr_run_bins(const float* sigmas, const float* coords, const float* c
   return GSR_OK;
 }
 
-// Tile-list pipeline (one kernel).  Raises stats[GSR_STAT_OVERFLOW] when a bucket overflows.
+// Region-bucket pipeline (one kernel).  Raises stats[GSR_STAT_OVERFLOW] when a bucket overflows.
 static int gsr_run_tiles(const float* sigmas, const float* coords, const float* colors, int s,
                          int h, int w, float dmax, float keff, const GsrWorkspace& ws,
                          cudaStream_t st) {
   if (s > 0)
-    gsr_tile_build_kernel<<<(s + 255) / 256, 256, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff,
+    gsr_region_build_kernel<<<(s + 255) / 256, 256, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff,
                                                            gsr_ecut(keff), ws);
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
@@ -102,8 +102,9 @@ static GsrFwdArgs gsr_fwd_args(const GsrWorkspace& ws, float* img, int h, int w,
   a.flags = flags;
   a.guard = ws.stats + GSR_STAT_OVERFLOW;
   a.want = 0;
-  a.tile_count = ws.tile_count;
-  a.tile_cap = ws.tile_cap;
+  a.reg_count = ws.reg_count;
+  a.reg_cap = ws.reg_cap;
+  a.nrx = ws.nrx;
   a.entries = ws.entries;
   a.rec_in = ws.rec_in;
   a.box_in = ws.box_in;
@@ -117,7 +118,7 @@ static int gsr_launch_forward_list(const GsrWorkspace& ws, float* img, int h, in
   GsrFwdArgs a = gsr_fwd_args(ws, img, h, w, keff, flags);
   a.want = 0;
   dim3 grid(ws.ntx, ws.nty);
-  gsr_forward_list_kernel<<<grid, GSR_FL_THREADS, 0, st>>>(a);
+  gsr_forward_region_kernel<<<grid, GSR_FR_THREADS, 0, st>>>(a);
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
 }

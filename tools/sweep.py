@@ -7,12 +7,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "variants")
 VARIANTS = {
-    "u2": [],
-    "u4": ["GSR_CFG_FL_UNROLL=4"],
-    "u3": ["GSR_CFG_FL_UNROLL=3"],
-    "pl1": ["GSR_CFG_FL_PER_LANE=1"],
-    "c5_u2": ["GSR_CFG_FL_MIN_CTAS=5"],
-    "c3_u4": ["GSR_CFG_FL_MIN_CTAS=3", "GSR_CFG_FL_UNROLL=4"],
+    "u4c4": [],
+    "u2c5": ["GSR_CFG_FR_UNROLL=2", "GSR_CFG_FR_MIN_CTAS=5"],
+    "u2c6": ["GSR_CFG_FR_UNROLL=2", "GSR_CFG_FR_MIN_CTAS=6"],
+    "u3c5": ["GSR_CFG_FR_UNROLL=3", "GSR_CFG_FR_MIN_CTAS=5"],
+    "u2c4": ["GSR_CFG_FR_UNROLL=2"],
+    "u8c4": ["GSR_CFG_FR_UNROLL=8"],
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
