@@ -70,22 +70,31 @@ __device__ __forceinline__ float gsr_warp_sum(float v) {
 }
 
 struct GsrBwdAcc {
-  float cr, cg, cb, sx, sy, sxx, sxy, syy;
+  gsr_f2 crg;   // {sum v g_r, sum v g_g}
+  float cb;     // sum v g_b
+  gsr_f2 s1;    // {Sx, Sy}
+  gsr_f2 s2;    // {Sxx, Sxy}
+  float syy;
 };
+__device__ __forceinline__ GsrBwdAcc gsr_bwd_acc_zero() {
+  GsrBwdAcc a;
+  a.crg = a.s1 = a.s2 = gsr_pk(0.f, 0.f);
+  a.cb = a.syy = 0.f;
+  return a;
+}
 
-// One pixel's contribution.  v must already be 0 for lanes outside the cull box.
+// One pixel's contribution (packed FP32x2 where two sums share a factor).  v must already be 0
+// for lanes outside the cull box.
 __device__ __forceinline__ void gsr_bwd_accum(GsrBwdAcc& a, float v, float g0, float g1, float g2,
                                               float dx, float dy, const float4& a1) {
-  a.cr = fmaf(v, g0, a.cr);
-  a.cg = fmaf(v, g1, a.cg);
+  a.crg = gsr_fma2(gsr_pk(v, v), gsr_pk(g0, g1), a.crg);
   a.cb = fmaf(v, g2, a.cb);
   const float G = fmaf(g0, a1.y, fmaf(g1, a1.z, g2 * a1.w));
   const float u = v * G;
+  const gsr_f2 d2 = gsr_pk(dx, dy);
+  a.s1 = gsr_fma2(gsr_pk(u, u), d2, a.s1);
   const float ux = u * dx, uy = u * dy;
-  a.sx += ux;
-  a.sy += uy;
-  a.sxx = fmaf(ux, dx, a.sxx);
-  a.sxy = fmaf(ux, dy, a.sxy);
+  a.s2 = gsr_fma2(gsr_pk(ux, ux), d2, a.s2);
   a.syy = fmaf(uy, dy, a.syy);
 }
 
@@ -172,7 +181,12 @@ __device__ __forceinline__ void gsr_bwd_sweep_gmem(GsrBwdAcc& acc, const GsrBwdA
 // Recursive-halving reduction of the eight sums: afterwards total k lives in the lanes whose
 // (bit4, bit3, bit2) = (k>>2&1, k>>1&1, k&1); lanes 0,4,...,28 store one total each.
 __device__ __forceinline__ void gsr_bwd_reduce_store(const GsrBwdAcc& acc, int lane, float* dst8) {
-  float v[8] = {acc.cr, acc.cg, acc.cb, acc.sx, acc.sy, acc.sxx, acc.sxy, acc.syy};
+  float v[8];
+  gsr_upk(acc.crg, v[0], v[1]);
+  v[2] = acc.cb;
+  gsr_upk(acc.s1, v[3], v[4]);
+  gsr_upk(acc.s2, v[5], v[6]);
+  v[7] = acc.syy;
   const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
   float w4[4];
 #pragma unroll
@@ -246,7 +260,7 @@ __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwd
         int bx0, bx1, by0, by1;
         bool binds;
         gsr_box_unpack(__ldg(p.box + gi), bx0, bx1, by0, by1, binds);
-        GsrBwdAcc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        GsrBwdAcc acc = gsr_bwd_acc_zero();
         gsr_bwd_sweep_gmem(acc, p, a0, a1, bx0, bx1, by0, by1, lx, ly);
         gsr_bwd_reduce_store(acc, lane, sm.tot[warp][j]);
         if (lane == 0) sm.tot_gi[warp][j] = gi;
@@ -323,7 +337,7 @@ __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwd
       int bx0, bx1, by0, by1;
       bool binds;
       gsr_box_unpack(__ldg(p.box + gi), bx0, bx1, by0, by1, binds);
-      GsrBwdAcc acc = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      GsrBwdAcc acc = gsr_bwd_acc_zero();
       if (bx0 >= sx0 && bx1 <= sx1 && by0 >= sy0 && by1 <= sy1)
         gsr_bwd_sweep_smem(acc, plane_s, px_s, py_s, a0, a1, bx0, bx1, by0, by1, sx0, sy0, lx, ly);
       else

@@ -274,3 +274,28 @@ def test_runs_on_the_current_stream():
         gscuda.gs_render(sd, cd, kd, img, sd.shape[0], h, w, 3, 0.1)
     st.synchronize()
     assert torch.allclose(img, want, atol=1e-5)
+
+
+def test_clustered_field_overflows_buckets_and_falls_back():
+    """All Gaussians in one corner: the fixed-capacity region buckets overflow, the device-side flag
+    routes the forward to the home-bin kernel; the result must not change."""
+    rng = np.random.default_rng(21)
+    n, h, w = 20000, 256, 320
+    sig = np.stack([rng.uniform(0.004, 0.02, n), rng.uniform(0.004, 0.02, n), np.tanh(rng.normal(0, 1, n)) * 0.99], 1)
+    xy = np.stack([rng.uniform(-0.95, -0.75, n), rng.uniform(0.7, 0.95, n)], 1)
+    col = rng.uniform(0, 1, (n, 3)) * 0.05
+    ref = oracle.forward(sig, xy, col, h, w, 0.1)
+    out = _render(sig, xy, col, h, w, 0.1).cpu().double().numpy()
+    assert np.abs(out - ref).max() <= FWD_TOL * max(1.0, np.abs(ref).max())
+    g = rng.uniform(-1, 1, (h, w, 3)).astype(np.float32)
+    _assert_grads(_backward(sig, xy, col, g, 0.1), oracle.backward(sig, xy, col, g, 0.1))
+
+
+def test_shuffled_input_takes_the_incoherent_path():
+    """Random input order: the warp-cooperative bucket append sees a large tile union and every lane
+    walks its own tiles; same image."""
+    _, s, c, k, h, w = fields.make("C2", 3)
+    perm = torch.randperm(s.shape[0], generator=torch.Generator().manual_seed(3))
+    a = _render(s, c, k, h, w, 0.1)
+    b = _render(s[perm].contiguous(), c[perm].contiguous(), k[perm].contiguous(), h, w, 0.1)
+    assert float((a - b).abs().max()) <= 2e-5
