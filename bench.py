@@ -15,7 +15,7 @@ no collective in the timed region); `value` is the whole-job MP/s: N * MP / max-
 A step is one forward pass of the hot path (set-up + raster kernels) with the Gaussian tensors
 and the image resident in HBM.  `e2e` is the same metric through the plugin call a GSASR user
 makes (gscuda.gs_render) from pinned HOST buffers, host<->device copies inside the timed region.
-`roofline` is for the dominant kernel (gsr_forward_kernel), timed with CUDA events on the launch
+`roofline` is for the dominant kernel (gsr_forward_region_kernel), timed with CUDA events on the launch
 stream via the split-phase C ABI.  `cpu_baseline` / `--impl reference` time the CPU restatement
 of the reference algorithm (oracle/, OpenMP over all host cores) on a bounded sample.
 """
@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 METRIC = "HR megapixels/sec rasterized (fwd) at x4, 2M Gaussians"
 UNIT = "MP/s"
 DMAX = 0.1
-KERNELS_PER_STEP = 9  # table, tile_count, scan, tile_fill, forward_list + the guarded fallback (bin, scan, scatter, forward_bins)
+KERNELS_PER_STEP = 7  # table, region_build, forward_region + the guarded fallback (bin, scan, scatter, forward_bins)
 
 
 def peaks():
@@ -176,7 +176,7 @@ def workload_config(name):
     return {"workload": name, "lr": [cfg.lr_h, cfg.lr_w], "scale": cfg.scale, "hr": [h, w],
             "gaussians": cfg.n, "dmax": DMAX, "sigma": "model-like: 0.99999*sigmoid(N(0,1))+1e-6",
             "ksigma": "library default (5)",
-            "l2": "per-step working set (params 67 MB + image 101 MB + workspace 126 MB) exceeds the 126 MB L2"}
+            "l2": "per-step working set (params 67 MB + image 101 MB + workspace 330 MB) exceeds the 126 MB L2"}
 
 
 def main():
@@ -305,7 +305,7 @@ def main():
             "clocks": clocks, "gpu_launches": KERNELS_PER_STEP * args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 12 * h * w},
-            "roofline": {"bound": "hbm", "kernel": "gsr_forward_list_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "gsr_forward_region_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes": alg_bytes, "kernel_ms": kern_ms,
                          "kernel_share_of_step": kern_ms / ms_step, "traffic": TRAFFIC.get(args.workload),

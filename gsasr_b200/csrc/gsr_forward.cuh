@@ -187,9 +187,10 @@ __device__ __forceinline__ void gsr_build_runs(const int* __restrict__ bin_off,
 
 // One write (or read-modify-write: the reference accumulates into rendered_img) per pixel.
 __device__ __forceinline__ void gsr_fwd_writeout(const GsrFwdArgs& p, int hi, int wi0, float r0,
-                                                 float g0, float b0, float r1, float g1, float b1) {
+                                                 float g0, float b0, float r1, float g1, float b1,
+                                                 bool force_over = false) {
   if (hi < p.h) {
-    const bool over = (p.flags & 1u) != 0;
+    const bool over = force_over || (p.flags & 1u) != 0;
     if (p.flags & 2u) {  // CHW
       const size_t plane = (size_t)p.h * p.w;
       float* o = p.img + (size_t)hi * p.w + wi0;
@@ -216,6 +217,25 @@ __device__ __forceinline__ void gsr_fwd_writeout(const GsrFwdArgs& p, int hi, in
         o[5] = over ? b1 : o[5] + b1;
       }
     }
+  }
+}
+
+// Accumulate mode (the reference's contract): the old pixel values are fetched at the START of the
+// kernel and seed the accumulators, so their latency hides behind the raster work and the final
+// write is a plain store.
+__device__ __forceinline__ void gsr_fwd_readold(const GsrFwdArgs& p, int hi, int wi0, float& r0,
+                                                float& g0, float& b0, float& r1, float& g1, float& b1) {
+  r0 = g0 = b0 = r1 = g1 = b1 = 0.f;
+  if ((p.flags & 1u) != 0 || hi >= p.h) return;
+  if (p.flags & 2u) {
+    const size_t plane = (size_t)p.h * p.w;
+    const float* o = p.img + (size_t)hi * p.w + wi0;
+    if (wi0 < p.w) { r0 = o[0]; g0 = o[plane]; b0 = o[2 * plane]; }
+    if (wi0 + 1 < p.w) { r1 = o[1]; g1 = o[plane + 1]; b1 = o[2 * plane + 1]; }
+  } else {
+    const float* o = p.img + ((size_t)hi * p.w + wi0) * 3;
+    if (wi0 < p.w) { r0 = o[0]; g0 = o[1]; b0 = o[2]; }
+    if (wi0 + 1 < p.w) { r1 = o[3]; g1 = o[4]; b1 = o[5]; }
   }
 }
 
@@ -419,7 +439,14 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
   const float px1 = __ldg(p.px_tab + min(wi0 + 1, p.w - 1));
   const float py = __ldg(p.py_tab + min(hi, p.h - 1));
   const gsr_f2 px2 = gsr_pk(px0, px1);
-  gsr_f2 accr = gsr_pk(0.f, 0.f), accg = gsr_pk(0.f, 0.f), accb = gsr_pk(0.f, 0.f);
+  gsr_f2 accr, accg, accb;
+  {
+    float r0, r1, g0, g1, b0, b1;
+    gsr_fwd_readold(p, hi, wi0, r0, g0, b0, r1, g1, b1);
+    accr = gsr_pk(r0, r1);
+    accg = gsr_pk(g0, g1);
+    accb = gsr_pk(b0, b1);
+  }
 
   const int rid = ry * p.nrx + rx;
   const int n = min(__ldg(p.reg_count + rid), p.reg_cap);
@@ -478,6 +505,6 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
     gsr_upk(accr, r0, r1);
     gsr_upk(accg, g0, g1);
     gsr_upk(accb, b0, b1);
-    gsr_fwd_writeout(p, hi, wi0, r0, g0, b0, r1, g1, b1);
+    gsr_fwd_writeout(p, hi, wi0, r0, g0, b0, r1, g1, b1, true);
   }
 }

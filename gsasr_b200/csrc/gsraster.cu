@@ -112,8 +112,8 @@ static GsrFwdArgs gsr_fwd_args(const GsrWorkspace& ws, float* img, int h, int w,
   return a;
 }
 
-// Raster over the tile lists (runs when the lists fit) ...
-static int gsr_launch_forward_list(const GsrWorkspace& ws, float* img, int h, int w, float keff,
+// Raster over the region buckets (runs when every bucket fitted) ...
+static int gsr_launch_forward_region(const GsrWorkspace& ws, float* img, int h, int w, float keff,
                                    uint32_t flags, cudaStream_t st) {
   GsrFwdArgs a = gsr_fwd_args(ws, img, h, w, keff, flags);
   a.want = 0;
@@ -148,7 +148,7 @@ static int gsr_prepare_forward(const float* sigmas, const float* coords, const f
 
 static int gsr_raster_forward(const GsrWorkspace& ws, float* img, int h, int w, float keff,
                               uint32_t flags, cudaStream_t st) {
-  int rc = gsr_launch_forward_list(ws, img, h, w, keff, flags, st);
+  int rc = gsr_launch_forward_region(ws, img, h, w, keff, flags, st);
   if (rc) return rc;
   return gsr_launch_forward_bins(ws, img, h, w, keff, flags, st);
 }

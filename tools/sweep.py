@@ -7,12 +7,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "variants")
 VARIANTS = {
-    "u4c4": [],
-    "u2c5": ["GSR_CFG_FR_UNROLL=2", "GSR_CFG_FR_MIN_CTAS=5"],
-    "u2c6": ["GSR_CFG_FR_UNROLL=2", "GSR_CFG_FR_MIN_CTAS=6"],
-    "u3c5": ["GSR_CFG_FR_UNROLL=3", "GSR_CFG_FR_MIN_CTAS=5"],
-    "u2c4": ["GSR_CFG_FR_UNROLL=2"],
-    "u8c4": ["GSR_CFG_FR_UNROLL=8"],
+    "u8c4": [],
+    "u8c3": ["GSR_CFG_FR_MIN_CTAS=3"],
+    "u12c3": ["GSR_CFG_FR_UNROLL=12", "GSR_CFG_FR_MIN_CTAS=3"],
+    "u16c2": ["GSR_CFG_FR_UNROLL=16", "GSR_CFG_FR_MIN_CTAS=2"],
+    "u6c4": ["GSR_CFG_FR_UNROLL=6"],
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
@@ -41,6 +40,12 @@ else:
             a.record(); L.gsr_forward_prepared(img.data_ptr(), n, h, w, 0.0, 1, ws.data_ptr(), ws.numel(), sp); b.record()
             torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
         res[cfg + "_fwd_us"] = round(1e3 * float(np.median(ts[3:])), 1)
+        ts = []
+        for i in range(13):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); L.gsr_forward_prepared(img.data_ptr(), n, h, w, 0.0, 0, ws.data_ptr(), ws.numel(), sp); b.record()
+            torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+        res[cfg + "_fwd_acc_us"] = round(1e3 * float(np.median(ts[3:])), 1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); L.gsr_prepare(sd.data_ptr(), cd.data_ptr(), kd.data_ptr(), n, h, w, 0.1, 0.0, ws.data_ptr(), ws.numel(), sp); b.record()
         torch.cuda.synchronize(); res[cfg + "_prep_us"] = round(1e3 * a.elapsed_time(b), 1)
