@@ -5,7 +5,7 @@
 //                               record (written in input order); then for every 8x8-pixel region
 //                               the ellipse touches a 4-byte entry {index | binds << 31} is appended
 //                               to the region's bucket (warp-cooperative: one atomic per
-//                               (warp, region), all reservations of a warp in flight together).
+//                               (warp, region), 32 reservations in flight together).
 //   Every region owns a fixed-capacity bucket (16 N / regions + 64 entries: GSASR emits its Gaussians
 //   on a regular grid, utils/fea2gs.py:553-563, so the load per region is uniform); an entry that
 //   does not fit raises the overflow flag and the forward falls back to the home-bin pipeline.
@@ -276,186 +276,104 @@ gsr_scatter_kernel(const float* __restrict__ sigmas, const float* __restrict__ c
 }
 
 // ---- tile-list pipeline -------------------------------------------------------------------------
-// Calls f(tile id, region mask) for every tile whose regions the Gaussian's ellipse touches.
-// Same masks as gsr_region_mask, but the x-range of every 8-row band is computed once per tile
-// ROW and shared by the tiles of that row.
-template <class F>
-__device__ __forceinline__ void gsr_for_each_tile(const GsrRec& r, int x0, int x1, int y0, int y1,
-                                                  int h, int w, int ntx, float ecut, F&& f) {
-  const GsrEllipse e = gsr_ellipse(r, h, w);
-  const int tx0 = x0 / GSR_TILE_W, tx1 = x1 / GSR_TILE_W;
-  const int ty0 = y0 / GSR_TILE_H, ty1 = y1 / GSR_TILE_H;
-  for (int ty = ty0; ty <= ty1; ++ty) {
-    int xl[GSR_NRY], xh[GSR_NRY];
-    bool any = false;
-#pragma unroll
-    for (int ry = 0; ry < GSR_NRY; ++ry) {
-      int ya = ty * GSR_TILE_H + ry * GSR_REGION, yb = ya + GSR_REGION - 1;
-      ya = ya > y0 ? ya : y0;
-      yb = yb < y1 ? yb : y1;
-      const bool ok = ya <= yb && gsr_band_xrange(e, ecut, ya, yb, x0, x1, xl[ry], xh[ry]);
-      if (!ok) {
-        xl[ry] = 1;
-        xh[ry] = 0;
-      }
-      any |= ok;
-    }
-    if (!any) continue;
-    for (int tx = tx0; tx <= tx1; ++tx) {
-      const int ox = tx * GSR_TILE_W;
-      uint32_t m = 0;
-#pragma unroll
-      for (int ry = 0; ry < GSR_NRY; ++ry) {
-        const int lo = xl[ry] > ox ? xl[ry] : ox;
-        const int hi = xh[ry] < ox + GSR_TILE_W - 1 ? xh[ry] : ox + GSR_TILE_W - 1;
-        if (lo <= hi) {
-          const int r0 = (lo - ox) / GSR_REGION, r1 = (hi - ox) / GSR_REGION;
-          m |= (((2u << r1) - 1u) & ~((1u << r0) - 1u)) << (ry * GSR_NRX);
-        }
-      }
-      if (m) f(ty * ntx + tx, m);
-    }
+// Warp-cooperative bucket append.  The 32 Gaussians of a warp are consecutive in the input, which
+// for a fea2gs field means spatially adjacent (utils/fea2gs.py:553-563), so their region sets
+// overlap heavily.  Regions are addressed as (band, column): band = 8-row strip of the image.
+//   1. per band of the warp's union every lane computes the column range its ellipse covers
+//      (gsr_band_xrange); per (band, column) of the union one ballot tells which lanes touch the
+//      region, and non-empty pairs are dealt to the lanes, 32 at a time;
+//   2. lane = pair: ONE atomicAdd reserves the pair's slots (32 reservations in flight per
+//      instruction, so the atomic round trip is paid once per batch, not once per pair), then the
+//      lane streams the entries of its pair -- fetched from the owning lanes with shuffles -- into
+//      the region's bucket.
+// If the union is large (incoherent input order) every lane walks its own regions with one atomic
+// per entry.  All 32 lanes must call this function (dead lanes pass live = false).
+constexpr int GSR_COOP_MAX_PAIRS = 256;
+
+__device__ __forceinline__ void gsr_warp_flush_pairs(unsigned bal, int rid, uint32_t entry,
+                                                     int* __restrict__ cnt, uint32_t* __restrict__ ent,
+                                                     int cap, int* overflow) {
+  const unsigned full = 0xffffffffu;
+  uint32_t* dst = ent;
+  int room = 0;
+  if (bal) {
+    const int base = atomicAdd(cnt + rid, __popc(bal));
+    dst = ent + (size_t)rid * cap + base;
+    room = cap - base;  // entries that still fit
+    if (room < __popc(bal)) *overflow = 1;
+  }
+  const int iters = __reduce_max_sync(full, __popc(bal));
+  for (int k = 0; k < iters; ++k) {
+    const int src = bal ? __ffs(bal) - 1 : 0;
+    const uint32_t en = __shfl_sync(full, entry, src);
+    if (bal && k < room) dst[k] = en;
+    bal &= bal - 1;
   }
 }
 
-// Warp-cooperative bucket append.  The 32 Gaussians of a warp are consecutive in the input, which
-// for a fea2gs field means spatially adjacent (utils/fea2gs.py:553-563), so their region sets
-// overlap heavily.  The warp walks the UNION of the lanes' tile rectangles (at most
-// GSR_COOP_MAX_TILES tiles of GSR_NRX x GSR_NRY regions) in three phases:
-//   1. per tile every lane computes its region mask; for non-empty tiles the ballot of every
-//      region (which lanes touch it) is staged in shared memory;
-//   2. the non-empty (tile, region) pairs are compacted;
-//   3. lane = pair: one atomicAdd reserves the pair's slots (32 reservations in flight per
-//      instruction, so the atomic round trip is paid once per warp), then the lane streams the
-//      entries of its pair -- fetched from the owning lanes with shuffles -- into the bucket.
-// If the union is larger (incoherent input) every lane walks its own tiles with one atomic per
-// (Gaussian, region).  All 32 lanes must call this function (dead lanes pass live = false).
-constexpr int GSR_COOP_MAX_TILES = 24;
-constexpr int GSR_RPT = GSR_NRX * GSR_NRY;  // regions per tile (8)
-
-struct GsrCoopStage {
-  int tile_x[GSR_COOP_MAX_TILES], tile_y[GSR_COOP_MAX_TILES];
-  unsigned ballot[GSR_COOP_MAX_TILES * GSR_RPT];
-  uint16_t pair[GSR_COOP_MAX_TILES * GSR_RPT];  // compacted non-empty (tile, region) pairs
-};
-static_assert(GSR_RPT <= 8, "per-lane tile masks are staged as bytes");
-
-__device__ __forceinline__ int gsr_region_id(int tx, int ty, int rg, int nrx) {
-  return (ty * GSR_NRY + rg / GSR_NRX) * nrx + tx * GSR_NRX + rg % GSR_NRX;
-}
-
-__device__ __forceinline__ void gsr_warp_append(GsrCoopStage& sg, bool live, const GsrRec& r,
-                                                uint32_t entry, int x0, int x1, int y0, int y1, int h,
-                                                int w, int ntx, int nrx, float ecut,
-                                                int* __restrict__ cnt, uint32_t* __restrict__ ent,
-                                                int cap, int* overflow) {
+__device__ __forceinline__ void gsr_warp_append(bool live, const GsrRec& r, uint32_t entry, int x0,
+                                                int x1, int y0, int y1, int h, int w, int nrx,
+                                                float ecut, int* __restrict__ cnt,
+                                                uint32_t* __restrict__ ent, int cap, int* overflow) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const int tx0 = live ? x0 / GSR_TILE_W : 0x3fffffff, tx1 = live ? x1 / GSR_TILE_W : -1;
-  const int ty0 = live ? y0 / GSR_TILE_H : 0x3fffffff, ty1 = live ? y1 / GSR_TILE_H : -1;
-  const int ux0 = __reduce_min_sync(full, tx0), ux1 = __reduce_max_sync(full, tx1);
-  const int uy0 = __reduce_min_sync(full, ty0), uy1 = __reduce_max_sync(full, ty1);
-  if (ux1 < ux0 || uy1 < uy0) return;  // no live lane
-  if ((long long)(ux1 - ux0 + 1) * (uy1 - uy0 + 1) > GSR_COOP_MAX_TILES) {
+  const int b0 = live ? y0 / GSR_REGION : 0x3fffffff, b1 = live ? y1 / GSR_REGION : -1;
+  const int c0 = live ? x0 / GSR_REGION : 0x3fffffff, c1 = live ? x1 / GSR_REGION : -1;
+  const int ub0 = __reduce_min_sync(full, b0), ub1 = __reduce_max_sync(full, b1);
+  const int uc0 = __reduce_min_sync(full, c0), uc1 = __reduce_max_sync(full, c1);
+  if (ub1 < ub0 || uc1 < uc0) return;  // no live lane
+  GsrEllipse e;
+  if (live) e = gsr_ellipse(r, h, w);
+  if ((long long)(ub1 - ub0 + 1) * (uc1 - uc0 + 1) > GSR_COOP_MAX_PAIRS) {
     if (live)
-      gsr_for_each_tile(r, x0, x1, y0, y1, h, w, ntx, ecut, [&](int t, uint32_t m) {
-        const int tx = t % ntx, ty = t / ntx;
-        while (m) {
-          const int rg = __ffs(m) - 1;
-          m &= m - 1;
-          const int rid = gsr_region_id(tx, ty, rg, nrx);
+      for (int b = b0; b <= b1; ++b) {
+        int ya = b * GSR_REGION, yb = ya + GSR_REGION - 1, xl, xh;
+        ya = ya > y0 ? ya : y0;
+        yb = yb < y1 ? yb : y1;
+        if (!gsr_band_xrange(e, ecut, ya, yb, x0, x1, xl, xh)) continue;
+        for (int c = xl / GSR_REGION; c <= xh / GSR_REGION; ++c) {
+          const int rid = b * nrx + c;
           const int pos = atomicAdd(cnt + rid, 1);
           if (pos < cap) ent[(size_t)rid * cap + pos] = entry;
           else *overflow = 1;
         }
-      });
+      }
     return;
   }
-  // ---- phase 1: masks of every tile of the union, ballots of every region ----
-  GsrEllipse e;
-  if (live) e = gsr_ellipse(r, h, w);
-  int nj = 0;
-  for (int ty = uy0; ty <= uy1; ++ty) {
-    int xl[GSR_NRY], xh[GSR_NRY];
-    const bool in_row = live && ty >= ty0 && ty <= ty1;
-#pragma unroll
-    for (int ry = 0; ry < GSR_NRY; ++ry) {
-      int ya = ty * GSR_TILE_H + ry * GSR_REGION, yb = ya + GSR_REGION - 1;
+  int slot = 0;  // pairs dealt in the current batch (warp-uniform)
+  unsigned mybal = 0;
+  int myrid = 0;
+  for (int b = ub0; b <= ub1; ++b) {
+    int rc0 = 1, rc1 = 0;  // this lane's column range in band b (empty by default)
+    if (live && b >= b0 && b <= b1) {
+      int ya = b * GSR_REGION, yb = ya + GSR_REGION - 1, xl, xh;
       ya = ya > y0 ? ya : y0;
       yb = yb < y1 ? yb : y1;
-      const bool ok = in_row && ya <= yb && gsr_band_xrange(e, ecut, ya, yb, x0, x1, xl[ry], xh[ry]);
-      if (!ok) {
-        xl[ry] = 1;
-        xh[ry] = 0;
+      if (gsr_band_xrange(e, ecut, ya, yb, x0, x1, xl, xh)) {
+        rc0 = xl / GSR_REGION;
+        rc1 = xh / GSR_REGION;
       }
     }
-    for (int tx = ux0; tx <= ux1; ++tx) {
-      const int ox = tx * GSR_TILE_W;
-      uint32_t m = 0;
-#pragma unroll
-      for (int ry = 0; ry < GSR_NRY; ++ry) {
-        const int lo = xl[ry] > ox ? xl[ry] : ox;
-        const int hi = xh[ry] < ox + GSR_TILE_W - 1 ? xh[ry] : ox + GSR_TILE_W - 1;
-        if (lo <= hi) {
-          const int r0 = (lo - ox) / GSR_REGION, r1 = (hi - ox) / GSR_REGION;
-          m |= (((2u << r1) - 1u) & ~((1u << r0) - 1u)) << (ry * GSR_NRX);
+    // columns that any lane touches in this band
+    const int bc0 = __reduce_min_sync(full, rc0 <= rc1 ? rc0 : 0x3fffffff);
+    const int bc1 = __reduce_max_sync(full, rc0 <= rc1 ? rc1 : -1);
+    for (int c = bc0; c <= bc1; ++c) {
+      const unsigned bal = __ballot_sync(full, rc0 <= c && c <= rc1);
+      if (bal) {
+        if (lane == slot) {
+          mybal = bal;
+          myrid = b * nrx + c;
         }
-      }
-      if (__ballot_sync(full, m != 0)) {
-        if (lane == 0) {
-          sg.tile_x[nj] = tx;
-          sg.tile_y[nj] = ty;
+        if (++slot == 32) {
+          gsr_warp_flush_pairs(mybal, myrid, entry, cnt, ent, cap, overflow);
+          slot = 0;
+          mybal = 0;
         }
-#pragma unroll
-        for (int rg = 0; rg < GSR_RPT; ++rg) {
-          const unsigned bal = __ballot_sync(full, (m >> rg) & 1u);
-          if (lane == rg) sg.ballot[nj * GSR_RPT + rg] = bal;
-        }
-        ++nj;
       }
     }
   }
-  __syncwarp();
-  // ---- phase 2: compact the non-empty (tile, region) pairs ----
-  int np = 0;  // number of non-empty pairs (warp-uniform)
-  for (int q0 = 0; q0 < nj * GSR_RPT; q0 += 32) {
-    const int q = q0 + lane;
-    const bool has = q < nj * GSR_RPT && sg.ballot[q] != 0;
-    const unsigned hb = __ballot_sync(full, has);
-    if (has) sg.pair[np + __popc(hb & lt_mask)] = (uint16_t)q;
-    np += __popc(hb);
-  }
-  __syncwarp();
-  // ---- phase 3: lane = pair.  One reservation per pair (32 in flight per instruction), then the
-  //      lane streams the entries of its pair into the region's bucket: the k-th set bit of the
-  //      pair's ballot names the lane whose Gaussian goes to slot base + k. ----
-  for (int p0 = 0; p0 < np; p0 += 32) {
-    const bool act = p0 + lane < np;
-    unsigned bal = 0;
-    uint32_t* dst = ent;
-    int room = 0;
-    if (act) {
-      const int q = sg.pair[p0 + lane];
-      const int j = q / GSR_RPT, rg = q % GSR_RPT;
-      bal = sg.ballot[q];
-      const int rid = gsr_region_id(sg.tile_x[j], sg.tile_y[j], rg, nrx);
-      const int base = atomicAdd(cnt + rid, __popc(bal));
-      dst = ent + (size_t)rid * cap + base;
-      room = cap - base;  // entries that still fit
-      if (room < __popc(bal)) *overflow = 1;
-    }
-    const int iters = __reduce_max_sync(full, __popc(bal));
-    for (int k = 0; k < iters; ++k) {
-      const int src = bal ? __ffs(bal) - 1 : 0;
-      const uint32_t en = __shfl_sync(full, entry, src);
-      if (bal && k < room) dst[k] = en;
-      bal &= bal - 1;
-    }
-  }
-  __syncwarp();
+  if (slot) gsr_warp_flush_pairs(mybal, myrid, entry, cnt, ent, cap, overflow);
 }
-
 
 __global__ void __launch_bounds__(256)
 gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restrict__ coords,
@@ -491,8 +409,6 @@ gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restric
       if (st.binds) ws.box_in[i] = gsr_box_pack(st.x0, st.x1, st.y0, st.y1, true);
     }
   }
-  __shared__ GsrCoopStage stage[8];  // one per warp of the CTA
-  gsr_warp_append(stage[threadIdx.x >> 5], st.live, r, (uint32_t)i | (st.binds ? 0x80000000u : 0u), st.x0,
-                  st.x1, st.y0, st.y1, h, w, ws.ntx, ws.nrx, ecut, ws.reg_count, ws.entries, ws.reg_cap,
-                  ws.stats + GSR_STAT_OVERFLOW);
+  gsr_warp_append(st.live, r, (uint32_t)i | (st.binds ? 0x80000000u : 0u), st.x0, st.x1, st.y0, st.y1, h,
+                  w, ws.nrx, ecut, ws.reg_count, ws.entries, ws.reg_cap, ws.stats + GSR_STAT_OVERFLOW);
 }
