@@ -6,7 +6,7 @@
 //                               the ellipse touches a 4-byte entry {index | binds << 31} is appended
 //                               to the region's bucket (warp-cooperative: one atomic per
 //                               (warp, region), 32 reservations in flight together).
-//   Every region owns a fixed-capacity bucket (16 N / regions + 64 entries: GSASR emits its Gaussians
+//   Every region owns a fixed-capacity bucket (16 N / regions + 32 entries: GSASR emits its Gaussians
 //   on a regular grid, utils/fea2gs.py:553-563, so the load per region is uniform); an entry that
 //   does not fit raises the overflow flag and the forward falls back to the home-bin pipeline.
 //   The forward kernel then needs no culling at all: one warp per region streams its bucket.
@@ -25,7 +25,7 @@
 #include "gsr_common.cuh"
 
 constexpr int GSR_STAT_EXT_X = 0, GSR_STAT_EXT_Y = 1, GSR_STAT_OVERFLOW = 2, GSR_STAT_ENTRIES = 3;
-constexpr int GSR_ENTRIES_PER_GAUSSIAN = 16;  // bucket capacity per region = 16 * N / regions + 64
+constexpr int GSR_ENTRIES_PER_GAUSSIAN = 16;  // bucket capacity per region = 16 * N / regions + 32
 
 struct GsrWorkspace {
   // ---- one block, cleared per call ----
@@ -84,7 +84,7 @@ static inline GsrWorkspace gsr_carve(void* base, int s, int h, int w) {
   ws.reg_count = ws.bin_count ? ws.scan_state + 2 * ws.nscan : nullptr;
   ws.rec_in = (GsrRec*)take(sn * sizeof(GsrRec));
   ws.box_in = (uint2*)take(sn * sizeof(uint2));
-  const size_t per_reg = ((size_t)GSR_ENTRIES_PER_GAUSSIAN * (size_t)(s > 0 ? s : 0) + ws.nreg - 1) / ws.nreg + 64;
+  const size_t per_reg = ((size_t)GSR_ENTRIES_PER_GAUSSIAN * (size_t)(s > 0 ? s : 0) + ws.nreg - 1) / ws.nreg + 32;
   ws.reg_cap = (int)(per_reg > 0x3fffffffu ? 0x3fffffffu : per_reg);
   ws.entries = (uint32_t*)take((size_t)ws.nreg * (size_t)ws.reg_cap * sizeof(uint32_t));
   ws.bin_off = (int*)take(((size_t)ws.nb + 2) * sizeof(int));
