@@ -136,7 +136,7 @@ struct GsrFwdArgs {
   int want;
   // region-bucket path
   const int* reg_count;
-  int reg_cap, nrx;
+  int reg_cap, nrx, nry;
   const uint32_t* entries;
   const GsrRec* rec_in;
   const uint2* box_in;
@@ -404,107 +404,278 @@ __global__ void __launch_bounds__(GSR_FWD_THREADS, GSR_CFG_MIN_CTAS) gsr_forward
 }
 
 // ---- region-bucket forward kernel (the fast path) ------------------------------------------------
-// One warp per 8x8-pixel region (two horizontally adjacent pixels per lane), eight warps = one
-// 32x16 tile per CTA, and NOTHING shared between the warps: no culling, no lists, no CTA barrier.
-// The region's bucket (4-byte Gaussian indices written by gsr_region_build_kernel) is streamed 32
-// entries at a time: lane i gathers record i (32 B, two LDG.128) into registers while the warp
-// evaluates the previous 32 records from its private, double-buffered shared-memory slice
-// (2 broadcast LDS.128 per record).  Per record: FADD + 3 FMUL (row terms), FADD2 (dx pair),
-// 2 FFMA2 (exponent pair), 2 MUFU.EX2, 3 FFMA2 (colour pairs): 15 instructions for 64 pixel
-// evaluations.  Window-binding Gaussians (entry bit 31) also bring their cull box and are
-// evaluated with the exact per-pixel inclusion test.
-constexpr int GSR_FR_THREADS = 32 * GSR_NRX * GSR_NRY;
-constexpr int GSR_FR_WARPS = GSR_FR_THREADS / 32;
-#ifndef GSR_CFG_FR_UNROLL
-#define GSR_CFG_FR_UNROLL 8
-#endif
+// One HALF-warp per 8x8-pixel region, a 2x2 pixel block per lane (accumulators in registers: six FP32x2
+// pairs), so a warp rasterises two horizontally adjacent regions at once, each half streaming its OWN
+// bucket (4-byte Gaussian indices written by gsr_region_build_kernel): the two halves read different
+// records with the same LDS.128 (one address per quarter-warp phase: conflict-free).  Per iteration --
+// one record per half, 128 pixel evaluations -- the warp issues 2 LDS.128, 2 FADD2 (dx, dy pairs),
+// 3 FMUL2 (row terms), 4 FFMA2 (exponents), 4 MUFU.EX2 and 6 FFMA2 (colour pairs): 21 instructions,
+// against 2 x 15 for the same work with one 1x2 block per lane.  FFMA2/FADD2/FMUL2 issue at full rate on
+// sm_100 (tools/ubench.cu), so the MUFU pipe (8 cycles per warp instruction per sub-partition) is the one
+// bound left: 32 cycles per iteration.
+//
+// Warps are persistent and independent (no CTA barrier, nothing shared between warps): warp g takes the
+// region pairs g, g + W, g + 2W, ...  Buckets are streamed in chunks of 32 entries per half through a
+// private, double-buffered shared-memory slice, two-deep: while chunk k is evaluated the records of chunk
+// k+1 are in flight as cp.async copies (global -> shared, no register staging; past the end of a bucket
+// the copy zero-fills, which makes a null record that adds exactly 0) and the entries of chunk k+2 are in
+// flight as loads whose values are not touched before the next iteration.  The chunk stream is flat over
+// the warp's units -- the bucket lengths of the next two units are requested a unit ahead -- so the
+// count -> entry -> record dependency chain is never waited for after the prologue.  Trip counts are
+// rounded up to a multiple of 4 with null records, so the evaluation loop is made of fully unrolled
+// blocks with immediate shared-memory offsets.  Window-binding Gaussians (entry bit 31) also bring their
+// cull box and are evaluated with the exact per-pixel inclusion test.
+constexpr int GSR_FR_WARPS = 8;
+constexpr int GSR_FR_THREADS = 32 * GSR_FR_WARPS;
+constexpr int GSR_FR_CHUNK = 32;                       // records per half-warp per stage (two per lane)
+constexpr int GSR_FR_HALF_BYTES = GSR_FR_CHUNK * 32;   // one half's records of one stage
+constexpr int GSR_FR_STAGE_BYTES = 2 * GSR_FR_HALF_BYTES;
 #ifndef GSR_CFG_FR_MIN_CTAS
-#define GSR_CFG_FR_MIN_CTAS 4
+#define GSR_CFG_FR_MIN_CTAS 3
 #endif
-constexpr int GSR_FR_UNROLL = GSR_CFG_FR_UNROLL;
+static_assert(GSR_REGION == 8, "a half-warp of 2x2 blocks covers an 8x8 region");
 
 struct GsrFwdRegionSmem {
-  float4 rec[GSR_FR_WARPS][2][64];  // per warp, double buffered: 32 records of 2 x float4
-  uint2 box[GSR_FR_WARPS][2][32];
+  float4 rec[GSR_FR_WARPS][2][2 * GSR_FR_CHUNK * 2];  // per warp, 2 stages x 2 halves x 32 records x 2 float4
+  uint2 box[GSR_FR_WARPS][2][2 * GSR_FR_CHUNK];
 };
+
+__device__ __forceinline__ gsr_f2 gsr_mul2(gsr_f2 a, gsr_f2 b) {
+  gsr_f2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// cp.async with a source size: 0 zero-fills the destination without reading.
+__device__ __forceinline__ void gsr_cp_async16z(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void gsr_cp_async8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+
+// One Gaussian against this lane's 2x2 pixel block.  nx2/ny2 hold the NEGATED pixel coordinates, so
+// d = x + (-px) = -(px - x): the reference's fp32 subtraction with the sign flipped, which the quadratic
+// form does not see (every term is a product of two d's) -- bit-identical exponents, no negation.
+// acc = {R,G,B} x {row 0, row 1}.
+template <bool MASKED>
+__device__ __forceinline__ void gsr_eval_quad(uint32_t addr0, uint32_t addr1, gsr_f2 nx2, gsr_f2 ny2,
+                                              bool m00, bool m01, bool m10, bool m11, gsr_f2& r0,
+                                              gsr_f2& g0, gsr_f2& b0, gsr_f2& r1, gsr_f2& g1, gsr_f2& b1) {
+  const float4 a0 = gsr_lds128(addr0);  // x, y, a, b
+  const float4 a1 = gsr_lds128(addr1);  // c, r, g, bl
+  const gsr_f2 dx2 = gsr_add2(nx2, gsr_pk(a0.x, a0.x));
+  const gsr_f2 dy2 = gsr_add2(ny2, gsr_pk(a0.y, a0.y));
+  const gsr_f2 t1 = gsr_mul2(gsr_pk(a0.w, a0.w), dy2);
+  const gsr_f2 t0 = gsr_mul2(gsr_mul2(gsr_pk(a1.x, a1.x), dy2), dy2);
+  float t1a, t1b, t0a, t0b;
+  gsr_upk(t1, t1a, t1b);
+  gsr_upk(t0, t0a, t0b);
+  const gsr_f2 a2 = gsr_pk(a0.z, a0.z);
+  const gsr_f2 ea = gsr_fma2(dx2, gsr_fma2(a2, dx2, gsr_pk(t1a, t1a)), gsr_pk(t0a, t0a));
+  const gsr_f2 eb = gsr_fma2(dx2, gsr_fma2(a2, dx2, gsr_pk(t1b, t1b)), gsr_pk(t0b, t0b));
+  float e00, e01, e10, e11;
+  gsr_upk(ea, e00, e01);
+  gsr_upk(eb, e10, e11);
+  float v00 = gsr_ex2(e00), v01 = gsr_ex2(e01), v10 = gsr_ex2(e10), v11 = gsr_ex2(e11);
+  if (MASKED) {
+    v00 = m00 ? v00 : 0.f;
+    v01 = m01 ? v01 : 0.f;
+    v10 = m10 ? v10 : 0.f;
+    v11 = m11 ? v11 : 0.f;
+  }
+  const gsr_f2 va = gsr_pk(v00, v01), vb = gsr_pk(v10, v11);
+  const gsr_f2 cr = gsr_pk(a1.y, a1.y), cg = gsr_pk(a1.z, a1.z), cb = gsr_pk(a1.w, a1.w);
+  r0 = gsr_fma2(va, cr, r0);
+  g0 = gsr_fma2(va, cg, g0);
+  b0 = gsr_fma2(va, cb, b0);
+  r1 = gsr_fma2(vb, cr, r1);
+  g1 = gsr_fma2(vb, cg, g1);
+  b1 = gsr_fma2(vb, cb, b1);
+}
+
+// Shared-memory slot of record j of a half: the two float4 of records 4..7, 12..15, ... are swapped, which
+// spreads the lane-per-record staging writes over all banks; the readers' offsets stay immediates.
+__device__ __forceinline__ uint32_t gsr_fr_swz(int j) { return (uint32_t)((j >> 2) & 1) * 16u; }
 
 __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forward_region_kernel(GsrFwdArgs p) {
   if (gsr_guard_skip(p.guard, p.want)) return;
   __shared__ GsrFwdRegionSmem sm;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rx = blockIdx.x * GSR_NRX + warp % GSR_NRX, ry = blockIdx.y * GSR_NRY + warp / GSR_NRX;
-  const int wi0 = rx * GSR_REGION + (lane & 3) * 2;
-  const int hi = ry * GSR_REGION + (lane >> 2);
-  const float px0 = __ldg(p.px_tab + min(wi0, p.w - 1));
-  const float px1 = __ldg(p.px_tab + min(wi0 + 1, p.w - 1));
-  const float py = __ldg(p.py_tab + min(hi, p.h - 1));
-  const gsr_f2 px2 = gsr_pk(px0, px1);
-  gsr_f2 accr, accg, accb;
-  {
-    float r0, r1, g0, g1, b0, b1;
-    gsr_fwd_readold(p, hi, wi0, r0, g0, b0, r1, g1, b1);
-    accr = gsr_pk(r0, r1);
-    accg = gsr_pk(g0, g1);
-    accb = gsr_pk(b0, b1);
-  }
+  constexpr int CH = GSR_FR_CHUNK;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = lane >> 4, l16 = lane & 15;
+  const int npx = p.nrx >> 1;  // region pairs per region row (nrx is a multiple of 4)
+  const int nunits = npx * p.nry;
+  const int nw = gridDim.x * GSR_FR_WARPS;
+  int u = blockIdx.x * GSR_FR_WARPS + warp;  // unit = pair of horizontally adjacent regions
+  if (u >= nunits) return;
+  const uint32_t rec_h = gsr_smem_addr(&sm.rec[warp][0][0]) + half * GSR_FR_HALF_BYTES;  // this half's slice, stage 0
+  const uint32_t box_s = gsr_smem_addr(&sm.box[warp][0][0]);
+  const uint2* box_w = &sm.box[warp][0][0];
+  const bool over = (p.flags & 1u) != 0, chw = (p.flags & 2u) != 0;
 
-  const int rid = ry * p.nrx + rx;
-  const int n = min(__ldg(p.reg_count + rid), p.reg_cap);
-  const uint32_t* ent = p.entries + (size_t)rid * p.reg_cap;
-  const uint32_t rec_s = gsr_smem_addr(&sm.rec[warp][0][0]);
-  uint2* box_w = &sm.box[warp][0][0];
+  // Region of this half in unit v (-1: past the end) and the (raw) length of its bucket.
+  auto region_of = [&](int v) { const int y = v / npx; return v < nunits ? y * p.nrx + (v - y * npx) * 2 + half : -1; };
+  auto count_of = [&](int rid) { return rid >= 0 ? __ldg(p.reg_count + rid) : 0; };  // clamp with reg_cap on use
 
-  // prefetch the first 32 records into registers
-  float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
-  uint2 qb = make_uint2(0, 0);
-  bool qslow = false;
-  auto fetch = [&](int i) {
-    qslow = false;
-    if (i < n) {
-      const uint32_t en = __ldg(ent + i);
-      const uint32_t gi = en & 0x7fffffffu;
-      const float4* src = reinterpret_cast<const float4*>(p.rec_in + gi);
-      q0 = __ldg(src);
-      q1 = __ldg(src + 1);
-      qslow = (en >> 31) != 0;
-      if (qslow) qb = __ldg(p.box_in + gi);
-    }
+  // Entries l16 and l16 + 16 of chunk (rid, c) -- loaded values are not touched before they are consumed
+  // one chunk later; validity is decided from the indices alone, so nothing is waited for here.
+  uint32_t e1a = 0, e1b = 0;
+  bool v1a = false, v1b = false;
+  auto request_entries = [&](int rid, int c, int n) {
+    const int i = c + l16;
+    v1a = i < n;
+    v1b = i + 16 < n;
+    const uint32_t* src = p.entries + (size_t)(rid < 0 ? 0 : rid) * p.reg_cap + i;
+    e1a = v1a ? __ldg(src) : 0u;
+    e1b = v1b ? __ldg(src + 16) : 0u;
   };
-  fetch(lane);
-  int cur = 0;
-  for (int c0 = 0; c0 < n; c0 += 32) {
-    const int cnt = min(32, n - c0);
-    const uint32_t buf = rec_s + cur * (64 * 16);
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(buf + lane * 32), "f"(q0.x), "f"(q0.y), "f"(q0.z), "f"(q0.w) : "memory");
-    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(buf + lane * 32 + 16), "f"(q1.x), "f"(q1.y), "f"(q1.z), "f"(q1.w) : "memory");
-    if (qslow) box_w[cur * 32 + lane] = qb;
-    const unsigned slow = __ballot_sync(0xffffffffu, qslow);
-    __syncwarp();
-    fetch(c0 + 32 + lane);  // next chunk: in flight while this one is evaluated
-    if (slow == 0) {
-#pragma unroll GSR_FR_UNROLL
-      for (int j = 0; j < cnt; ++j) gsr_eval_pair(buf + j * 32, px2, py, true, true, accr, accg, accb);
+  // Records of the requested entries -> stage `st` (cp.async; null records past the end of a bucket).
+  // Returns this lane's two "window binds" flags in bits 0 and 1.
+  auto stage_records = [&](int st) {
+    unsigned fl = 0;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const uint32_t en = t ? e1b : e1a;
+      const bool v = t ? v1b : v1a;
+      const uint32_t gi = v ? (en & 0x7fffffffu) : 0u;
+      const int j = l16 + 16 * t;
+      const char* src = reinterpret_cast<const char*>(p.rec_in + gi);
+      const uint32_t dst = rec_h + st * GSR_FR_STAGE_BYTES + j * 32, sw = gsr_fr_swz(j);
+      gsr_cp_async16z(dst + sw, src, v ? 16u : 0u);
+      gsr_cp_async16z(dst + (sw ^ 16u), src + 16, v ? 16u : 0u);
+      if (v && (en >> 31)) {
+        gsr_cp_async8(box_s + (st * 2 * CH + half * CH + j) * 8, p.box_in + gi);
+        fl |= 1u << t;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    return fl;
+  };
+
+  // Three units in flight: A is evaluated, B and C are known far enough ahead for the two-deep
+  // prefetch to run across unit boundaries.
+  int ridA = region_of(u), ridB = region_of(u + nw), ridC = region_of(u + 2 * nw);
+  int nA = min(count_of(ridA), p.reg_cap), nB = min(count_of(ridB), p.reg_cap), nC = count_of(ridC);
+  int ntripA = max(nA, __shfl_xor_sync(0xffffffffu, nA, 16));  // the longer bucket of the pair
+  int ntripB = max(nB, __shfl_xor_sync(0xffffffffu, nB, 16));
+
+  request_entries(ridA, 0, nA);
+  unsigned fl = stage_records(0);
+  unsigned slow_a = __ballot_sync(0xffffffffu, fl & 1u), slow_b = __ballot_sync(0xffffffffu, fl & 2u);
+  if (CH < ntripA) request_entries(ridA, CH, nA); else request_entries(ridB, 0, nB);
+
+  int cur = 0, c0 = 0;
+  int ry = ridA / p.nrx, rx = ridA - ry * p.nrx;
+  int wi0 = rx * GSR_REGION + (l16 & 3) * 2, hi0 = ry * GSR_REGION + (l16 >> 2) * 2;
+  gsr_f2 nx2 = gsr_pk(-__ldg(p.px_tab + min(wi0, p.w - 1)), -__ldg(p.px_tab + min(wi0 + 1, p.w - 1)));
+  gsr_f2 ny2 = gsr_pk(-__ldg(p.py_tab + min(hi0, p.h - 1)), -__ldg(p.py_tab + min(hi0 + 1, p.h - 1)));
+  gsr_f2 r0 = gsr_pk(0.f, 0.f), g0 = r0, b0 = r0, r1 = r0, g1 = r0, b1 = r0;
+
+  for (;;) {  // one chunk (32 records per half) per iteration, flat over the warp's units
+    const uint32_t buf = rec_h + cur * GSR_FR_STAGE_BYTES;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();  // this chunk's records are visible; the other stage is free
+    // records of the next chunk (their entries were requested one chunk ago) ...
+    fl = stage_records(cur ^ 1);
+    const unsigned slow_an = __ballot_sync(0xffffffffu, fl & 1u), slow_bn = __ballot_sync(0xffffffffu, fl & 2u);
+    // ... and the entries of the chunk after it: (A, c0 + 2 CH), (B, 0), (B, CH) or (C, 0)
+    const bool last = c0 + CH >= ntripA;
+    if (!last) {
+      if (c0 + 2 * CH < ntripA) request_entries(ridA, c0 + 2 * CH, nA); else request_entries(ridB, 0, nB);
     } else {
-      for (int j = 0; j < cnt; ++j) {
-        if ((slow >> j) & 1u) {  // dmax window cuts this Gaussian: exact inclusion per pixel
+      if (CH < ntripB) request_entries(ridB, CH, nB); else request_entries(ridC, 0, min(nC, p.reg_cap));
+    }
+
+    const int trip = min(CH, ntripA - c0);  // <= 0 for an empty pair
+    if ((slow_a | slow_b) == 0) {
+      int j = 0;
+      for (; j + 8 <= trip; j += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t a = buf + j * 32 + k * 32;
+          gsr_eval_quad<false>(a + gsr_fr_swz(k), a + (gsr_fr_swz(k) ^ 16u), nx2, ny2, true, true, true, true,
+                               r0, g0, b0, r1, g1, b1);
+        }
+      }
+      for (; j < trip; j += 4) {  // records past the end of a bucket are null
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t a = buf + j * 32 + k * 32;
+          const uint32_t sw = gsr_fr_swz(j);  // j is a multiple of 4: one swizzle for the block
+          gsr_eval_quad<false>(a + sw, a + (sw ^ 16u), nx2, ny2, true, true, true, true, r0, g0, b0, r1, g1, b1);
+        }
+      }
+    } else {
+      for (int j = 0; j < trip; ++j) {
+        const uint32_t a = buf + j * 32, sw = gsr_fr_swz(j);
+        // record j of this half was staged by lane (half, j & 15) as its entry number j >> 4
+        if ((((j & 16) ? slow_b : slow_a) >> (half * 16 + (j & 15))) & 1u) {  // exact inclusion
           int bx0, bx1, by0, by1;
           bool binds;
-          gsr_box_unpack(box_w[cur * 32 + j], bx0, bx1, by0, by1, binds);
-          const bool iny = hi >= by0 && hi <= by1;
-          gsr_eval_pair(buf + j * 32, px2, py, iny && wi0 >= bx0 && wi0 <= bx1,
-                        iny && wi0 + 1 >= bx0 && wi0 + 1 <= bx1, accr, accg, accb);
+          gsr_box_unpack(box_w[cur * 2 * CH + half * CH + j], bx0, bx1, by0, by1, binds);
+          const bool y0in = hi0 >= by0 && hi0 <= by1, y1in = hi0 + 1 >= by0 && hi0 + 1 <= by1;
+          const bool x0in = wi0 >= bx0 && wi0 <= bx1, x1in = wi0 + 1 >= bx0 && wi0 + 1 <= bx1;
+          gsr_eval_quad<true>(a + sw, a + (sw ^ 16u), nx2, ny2, y0in && x0in, y0in && x1in, y1in && x0in,
+                              y1in && x1in, r0, g0, b0, r1, g1, b1);
         } else {
-          gsr_eval_pair(buf + j * 32, px2, py, true, true, accr, accg, accb);
+          gsr_eval_quad<false>(a + sw, a + (sw ^ 16u), nx2, ny2, true, true, true, true, r0, g0, b0, r1, g1, b1);
         }
       }
     }
     cur ^= 1;
+    c0 += CH;
+    slow_a = slow_an;
+    slow_b = slow_bn;
+    if (!last) continue;
+
+    // ---- unit finished: write out.  Plain stores when the image is overwritten; fire-and-forget
+    // reductions (RED) when the call accumulates into the caller's image (the reference's
+    // contract): no read, no latency.
+    {
+      float v[2][2][3];
+      gsr_upk(r0, v[0][0][0], v[0][1][0]);
+      gsr_upk(g0, v[0][0][1], v[0][1][1]);
+      gsr_upk(b0, v[0][0][2], v[0][1][2]);
+      gsr_upk(r1, v[1][0][0], v[1][1][0]);
+      gsr_upk(g1, v[1][0][1], v[1][1][1]);
+      gsr_upk(b1, v[1][0][2], v[1][1][2]);
+      const size_t plane = (size_t)p.h * p.w;
+#pragma unroll
+      for (int yy = 0; yy < 2; ++yy) {
+#pragma unroll
+        for (int xx = 0; xx < 2; ++xx) {
+          const int hi = hi0 + yy, wi = wi0 + xx;
+          if (hi < p.h && wi < p.w) {
+            const size_t pix = (size_t)hi * p.w + wi;
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+              float* o = chw ? p.img + ch * plane + pix : p.img + pix * 3 + ch;
+              if (over) *o = v[yy][xx][ch];
+              else atomicAdd(o, v[yy][xx][ch]);
+            }
+          }
+        }
+      }
+    }
+    // ---- advance: B becomes A, C becomes B, a new C is requested (consumed one unit from now)
+    u += nw;
+    if (u >= nunits) break;
+    ridA = ridB;
+    nA = nB;
+    ntripA = ntripB;
+    ridB = ridC;
+    nB = min(nC, p.reg_cap);  // requested one unit ago
+    ntripB = max(nB, __shfl_xor_sync(0xffffffffu, nB, 16));
+    ridC = region_of(u + 2 * nw);
+    nC = count_of(ridC);
+    c0 = 0;
+    ry = ridA / p.nrx;
+    rx = ridA - ry * p.nrx;
+    wi0 = rx * GSR_REGION + (l16 & 3) * 2;
+    hi0 = ry * GSR_REGION + (l16 >> 2) * 2;
+    nx2 = gsr_pk(-__ldg(p.px_tab + min(wi0, p.w - 1)), -__ldg(p.px_tab + min(wi0 + 1, p.w - 1)));
+    ny2 = gsr_pk(-__ldg(p.py_tab + min(hi0, p.h - 1)), -__ldg(p.py_tab + min(hi0 + 1, p.h - 1)));
+    r0 = g0 = b0 = r1 = g1 = b1 = gsr_pk(0.f, 0.f);
   }
-  {
-    float r0, r1, g0, g1, b0, b1;
-    gsr_upk(accr, r0, r1);
-    gsr_upk(accg, g0, g1);
-    gsr_upk(accb, b0, b1);
-    gsr_fwd_writeout(p, hi, wi0, r0, g0, b0, r1, g1, b1, true);
-  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");  // nothing may be in flight when the CTA's memory is released
 }

@@ -105,6 +105,7 @@ static GsrFwdArgs gsr_fwd_args(const GsrWorkspace& ws, float* img, int h, int w,
   a.reg_count = ws.reg_count;
   a.reg_cap = ws.reg_cap;
   a.nrx = ws.nrx;
+  a.nry = ws.nry;
   a.entries = ws.entries;
   a.rec_in = ws.rec_in;
   a.box_in = ws.box_in;
@@ -117,8 +118,14 @@ static int gsr_launch_forward_region(const GsrWorkspace& ws, float* img, int h, 
                                    uint32_t flags, cudaStream_t st) {
   GsrFwdArgs a = gsr_fwd_args(ws, img, h, w, keff, flags);
   a.want = 0;
-  dim3 grid(ws.ntx, ws.nty);
-  gsr_forward_region_kernel<<<grid, GSR_FR_THREADS, 0, st>>>(a);
+  // persistent warps: one resident wave, every warp strides over the region pairs
+  int dev = 0, nsm = 0, per_sm = 0;
+  GSR_CUDA(cudaGetDevice(&dev));
+  GSR_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  GSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gsr_forward_region_kernel, GSR_FR_THREADS, 0));
+  const int nunits = (ws.nrx / 2) * ws.nry;
+  const int want = (nunits + GSR_FR_WARPS - 1) / GSR_FR_WARPS, cap = nsm * (per_sm > 0 ? per_sm : 1);
+  gsr_forward_region_kernel<<<want < cap ? want : cap, GSR_FR_THREADS, 0, st>>>(a);
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
 }

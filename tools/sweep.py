@@ -7,11 +7,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "variants")
 VARIANTS = {
-    "u8c4": [],
-    "u8c3": ["GSR_CFG_FR_MIN_CTAS=3"],
-    "u12c3": ["GSR_CFG_FR_UNROLL=12", "GSR_CFG_FR_MIN_CTAS=3"],
-    "u16c2": ["GSR_CFG_FR_UNROLL=16", "GSR_CFG_FR_MIN_CTAS=2"],
-    "u6c4": ["GSR_CFG_FR_UNROLL=6"],
+    "c3": [],
+    "c2": ["GSR_CFG_FR_MIN_CTAS=2"],
+    "c4": ["GSR_CFG_FR_MIN_CTAS=4"],
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build

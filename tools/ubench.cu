@@ -1,0 +1,163 @@
+// ubench.cu -- pipe-throughput microbenchmarks behind the forward kernel's design:
+// how many SM cycles one warp instruction of each kind costs when the SM is saturated with them.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/ubench tools/ubench.cu && tools/ubench
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdint>
+#include <vector>
+#include <algorithm>
+
+constexpr int ITERS = 2048, UNROLL = 8;
+
+enum Kind { FFMA, FFMA2, MUFU, LDS128_SAME, LDS128_HALF, LDS128_QUARTER, LDS128_EIGHTH, LDS128_LANE, LDS64_SAME,
+            LDS32_SAME, SHFL, MIX2x2, MIX1x2, NKIND };
+static const char* kNames[NKIND] = {"ffma", "ffma2", "mufu.ex2", "lds128 one address/warp", "lds128 one address/half-warp",
+                                    "lds128 one address/quarter-warp", "lds128 one address/4 lanes",
+                                    "lds128 lane-distinct (conflict-free)", "lds64 one address/warp",
+                                    "lds32 one address/warp", "shfl.idx",
+                                    "eval 2x2 px/lane (per record-iteration)", "eval 1x2 px/lane (per record-iteration)"};
+
+__device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk(f2 v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { f2 d; asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { f2 d; asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { f2 d; asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(1024) bench(long long* cycles, float* sink, float seed) {
+  __shared__ __align__(16) float sm[4096];
+  for (int i = threadIdx.x; i < 4096; i += blockDim.x) sm[i] = seed * (i & 15) * 1e-3f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const uint32_t base = (uint32_t)__cvta_generic_to_shared(sm);
+  uint32_t addr = base;
+  if (KIND == LDS128_HALF) addr = base + (lane >> 4) * 32;
+  if (KIND == LDS128_QUARTER) addr = base + (lane >> 3) * 32;
+  if (KIND == LDS128_EIGHTH) addr = base + (lane >> 2) * 32;
+  if (KIND == LDS128_LANE) addr = base + lane * 16;
+  float a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+  f2 p0 = pk(a0, a1), p1 = pk(a2, a3), p2 = pk(a4, a5), p3 = pk(a6, a7), p4 = p0, p5 = p1, p6 = p2, p7 = p3;
+  const f2 pc = pk(seed, seed);
+  __syncthreads();
+  const long long t0 = clock64();
+  if (KIND == MIX2x2 || KIND == MIX1x2) {
+    // the forward kernel's inner loop, one record per iteration per (half-)warp
+    const float py0 = seed * lane, py1 = py0 + seed;
+    const f2 px2 = pk(seed * (lane & 3), seed * (lane & 3) + seed), py2 = pk(py0, py1);
+    f2 r0 = pk(0, 0), g0 = r0, b0 = r0, r1 = r0, g1 = r0, b1 = r0;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const uint32_t ad = (KIND == MIX2x2 ? base + (lane >> 4) * 2048 : base) + ((it * UNROLL + u) & 63) * 32;
+        const float4 q0 = lds128(ad), q1 = lds128(ad + 16);  // -x, -y, a, b | c, r, g, bl
+        const f2 dx2 = add2(px2, pk(q0.x, q0.x));
+        if (KIND == MIX2x2) {
+          const f2 dy2 = add2(py2, pk(q0.y, q0.y));
+          const f2 t1 = mul2(pk(q0.w, q0.w), dy2);
+          const f2 t0 = mul2(mul2(pk(q1.x, q1.x), dy2), dy2);
+          float t1l, t1h, t0l, t0h;
+          upk(t1, t1l, t1h);
+          upk(t0, t0l, t0h);
+          const f2 e0 = fma2(dx2, fma2(pk(q0.z, q0.z), dx2, pk(t1l, t1l)), pk(t0l, t0l));
+          const f2 e1 = fma2(dx2, fma2(pk(q0.z, q0.z), dx2, pk(t1h, t1h)), pk(t0h, t0h));
+          float e00, e01, e10, e11;
+          upk(e0, e00, e01);
+          upk(e1, e10, e11);
+          const f2 v0 = pk(ex2(e00), ex2(e01)), v1 = pk(ex2(e10), ex2(e11));
+          r0 = fma2(v0, pk(q1.y, q1.y), r0); g0 = fma2(v0, pk(q1.z, q1.z), g0); b0 = fma2(v0, pk(q1.w, q1.w), b0);
+          r1 = fma2(v1, pk(q1.y, q1.y), r1); g1 = fma2(v1, pk(q1.z, q1.z), g1); b1 = fma2(v1, pk(q1.w, q1.w), b1);
+        } else {
+          const float dy = py0 + q0.y;
+          const float t1 = q0.w * dy, t0 = q1.x * dy * dy;
+          const f2 e0 = fma2(dx2, fma2(pk(q0.z, q0.z), dx2, pk(t1, t1)), pk(t0, t0));
+          float e00, e01;
+          upk(e0, e00, e01);
+          const f2 v0 = pk(ex2(e00), ex2(e01));
+          r0 = fma2(v0, pk(q1.y, q1.y), r0); g0 = fma2(v0, pk(q1.z, q1.z), g0); b0 = fma2(v0, pk(q1.w, q1.w), b0);
+        }
+      }
+    }
+    float x, y;
+    upk(add2(add2(add2(r0, g0), add2(b0, r1)), add2(g1, b1)), x, y);
+    a0 = x + y;
+  } else {
+    for (int it = 0; it < ITERS; ++it) {
+      if (KIND == FFMA) {
+        a0 = fmaf(a0, seed, seed); a1 = fmaf(a1, seed, seed); a2 = fmaf(a2, seed, seed); a3 = fmaf(a3, seed, seed);
+        a4 = fmaf(a4, seed, seed); a5 = fmaf(a5, seed, seed); a6 = fmaf(a6, seed, seed); a7 = fmaf(a7, seed, seed);
+      } else if (KIND == FFMA2) {
+        p0 = fma2(p0, pc, pc); p1 = fma2(p1, pc, pc); p2 = fma2(p2, pc, pc); p3 = fma2(p3, pc, pc);
+        p4 = fma2(p4, pc, pc); p5 = fma2(p5, pc, pc); p6 = fma2(p6, pc, pc); p7 = fma2(p7, pc, pc);
+      } else if (KIND == MUFU) {
+        a0 = ex2(a0); a1 = ex2(a1); a2 = ex2(a2); a3 = ex2(a3); a4 = ex2(a4); a5 = ex2(a5); a6 = ex2(a6); a7 = ex2(a7);
+      } else if (KIND == SHFL) {
+        a0 = __shfl_sync(0xffffffffu, a0, 3); a1 = __shfl_sync(0xffffffffu, a1, 5); a2 = __shfl_sync(0xffffffffu, a2, 7);
+        a3 = __shfl_sync(0xffffffffu, a3, 9); a4 = __shfl_sync(0xffffffffu, a4, 3); a5 = __shfl_sync(0xffffffffu, a5, 5);
+        a6 = __shfl_sync(0xffffffffu, a6, 7); a7 = __shfl_sync(0xffffffffu, a7, 9);
+      } else if (KIND == LDS64_SAME) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          float x, y;
+          asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(x), "=f"(y) : "r"(base + u * 32));
+          a0 += x; a1 += y;
+        }
+      } else if (KIND == LDS32_SAME) {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          float x;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(base + u * 32));
+          a0 += x;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+          const float4 v = lds128(addr + u * 1024);
+          a0 += v.x; a1 += v.w;
+        }
+      }
+    }
+  }
+  const long long t1 = clock64();
+  float x, y;
+  upk(add2(add2(p0, p1), add2(add2(p2, p3), add2(add2(p4, p5), add2(p6, p7)))), x, y);
+  sink[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 + x + y;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int KIND>
+static void run(int warps) {
+  int nsm = 0;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+  long long* cyc;
+  float* sink;
+  cudaMalloc(&cyc, nsm * sizeof(long long));
+  cudaMalloc(&sink, (size_t)nsm * 1024 * sizeof(float));
+  bench<KIND><<<nsm, warps * 32>>>(cyc, sink, 0.f);
+  bench<KIND><<<nsm, warps * 32>>>(cyc, sink, 0.f);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%s: %s\n", kNames[KIND], cudaGetErrorString(e)); return; }
+  std::vector<long long> h(nsm);
+  cudaMemcpy(h.data(), cyc, nsm * sizeof(long long), cudaMemcpyDeviceToHost);
+  std::sort(h.begin(), h.end());
+  const double per = (double)h[nsm / 2] / ((double)ITERS * UNROLL * warps);
+  printf("%-44s warps/SM %2d  SM cycles per warp instruction %.3f  (x4 = per SMSP: %.2f)\n", kNames[KIND], warps, per, per * 4);
+  cudaFree(cyc);
+  cudaFree(sink);
+}
+
+int main() {
+  for (int warps : {16, 32}) {
+    run<FFMA>(warps); run<FFMA2>(warps); run<MUFU>(warps); run<SHFL>(warps);
+    run<LDS128_SAME>(warps); run<LDS128_HALF>(warps); run<LDS128_QUARTER>(warps); run<LDS128_EIGHTH>(warps);
+    run<LDS128_LANE>(warps); run<LDS64_SAME>(warps); run<LDS32_SAME>(warps);
+    run<MIX1x2>(warps); run<MIX2x2>(warps);
+  }
+  return 0;
+}
