@@ -375,40 +375,153 @@ __device__ __forceinline__ void gsr_warp_append(bool live, const GsrRec& r, uint
   if (slot) gsr_warp_flush_pairs(mybal, myrid, entry, cnt, ent, cap, overflow);
 }
 
-__global__ void __launch_bounds__(256)
+// CTA-cooperative bucket append (the common case).  The Gaussians of a CTA are consecutive in the input
+// -- for a fea2gs field a piece of one grid row -- so the regions they touch form a small rectangle
+// (18 x 4 regions for 64 Gaussians at x4).  When it has at most GSR_RB_MAXR regions the CTA collects its
+// entries per region in shared memory (one shared-memory atomic per entry for the slot), reserves each
+// non-empty region's slots in the global bucket with ONE atomicAdd (a thread per region) and copies the
+// short lists out.  A list longer than GSR_RB_LCAP spills its tail straight to the bucket (one global
+// atomic per entry); a CTA whose rectangle is larger (incoherent input order) takes the ballot-based
+// path above.  CTAs are small (two warps: the barriers cost little and many CTAs are in different
+// phases at any time) and persistent: each strides over the chunks of the input and requests the
+// parameters of its next chunk before it processes the current one.
+#ifndef GSR_CFG_RB_THREADS
+#define GSR_CFG_RB_THREADS 64
+#endif
+constexpr int GSR_RB_THREADS = GSR_CFG_RB_THREADS;
+constexpr int GSR_RB_MAXR = 2 * GSR_RB_THREADS;
+constexpr int GSR_RB_LCAP = 16;
+
+struct GsrRegionBuildSmem {
+  int cnt[GSR_RB_MAXR];
+  uint32_t list[GSR_RB_MAXR][GSR_RB_LCAP + 1];  // odd row stride: a thread per region reads conflict-free
+  int red[4][(GSR_RB_THREADS + 31) / 32];
+};
+
+#ifndef GSR_CFG_RB_MIN_CTAS
+#define GSR_CFG_RB_MIN_CTAS (1024 / GSR_CFG_RB_THREADS)
+#endif
+__global__ void __launch_bounds__(GSR_RB_THREADS, GSR_CFG_RB_MIN_CTAS)
 gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restrict__ coords,
                       const float* __restrict__ colors, int s, int h, int w, float dmax,
                       float ksigma, float ecut, GsrWorkspace ws) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // the grid covers s rounded up to 32
-  const int lane = threadIdx.x & 31;
-  GsrSetup st;
-  st.live = false;
-  st.binds = false;
-  st.x0 = st.y0 = 1;
-  st.x1 = st.y1 = 0;
-  GsrRec r;
-  r.x = r.y = r.a = r.b = r.c = r.r = r.g = r.bl = 0.f;
-  if (i < s) {
-    const float sx = __ldg(sigmas + 3 * (size_t)i + 0);
-    const float sy = __ldg(sigmas + 3 * (size_t)i + 1);
-    const float rho = __ldg(sigmas + 3 * (size_t)i + 2);
-    const float x = __ldg(coords + 2 * (size_t)i + 0);
-    const float y = __ldg(coords + 2 * (size_t)i + 1);
-    const float cr = __ldg(colors + 3 * (size_t)i + 0);
-    const float cg = __ldg(colors + 3 * (size_t)i + 1);
-    const float cb = __ldg(colors + 3 * (size_t)i + 2);
-    st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, h, w, dmax, ksigma, ws.px_tab, ws.py_tab);
-    if (st.live) {
-      r = gsr_make_rec(sx, sy, rho, x, y, cr, cg, cb);
-      if (!(gsr_finite(r.a) && gsr_finite(r.b) && gsr_finite(r.c))) st.live = false;
+  __shared__ GsrRegionBuildSmem sm;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned full = 0xffffffffu;
+  int* const overflow = ws.stats + GSR_STAT_OVERFLOW;
+  const int nchunks = (s + GSR_RB_THREADS - 1) / GSR_RB_THREADS;
+
+  float pf[8];
+  auto request = [&](int chunk) {
+    const int i = chunk * GSR_RB_THREADS + tid;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pf[k] = 0.f;
+    if (chunk < nchunks && i < s) {
+      pf[0] = __ldg(sigmas + 3 * (size_t)i + 0);
+      pf[1] = __ldg(sigmas + 3 * (size_t)i + 1);
+      pf[2] = __ldg(sigmas + 3 * (size_t)i + 2);
+      pf[3] = __ldg(coords + 2 * (size_t)i + 0);
+      pf[4] = __ldg(coords + 2 * (size_t)i + 1);
+      pf[5] = __ldg(colors + 3 * (size_t)i + 0);
+      pf[6] = __ldg(colors + 3 * (size_t)i + 1);
+      pf[7] = __ldg(colors + 3 * (size_t)i + 2);
     }
-    if (st.live) {
-      float4* dr = reinterpret_cast<float4*>(ws.rec_in + i);
-      dr[0] = make_float4(r.x, r.y, r.a, r.b);
-      dr[1] = make_float4(r.c, r.r, r.g, r.bl);
-      if (st.binds) ws.box_in[i] = gsr_box_pack(st.x0, st.x1, st.y0, st.y1, true);
+  };
+  request(blockIdx.x);
+
+  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const int i = chunk * GSR_RB_THREADS + tid;
+    const float sx = pf[0], sy = pf[1], rho = pf[2], x = pf[3], y = pf[4], cr = pf[5], cg = pf[6], cb = pf[7];
+    request(chunk + gridDim.x);
+    GsrSetup st;
+    st.live = false;
+    st.binds = false;
+    st.x0 = st.y0 = 1;
+    st.x1 = st.y1 = 0;
+    GsrRec r;
+    r.x = r.y = r.a = r.b = r.c = r.r = r.g = r.bl = 0.f;
+    if (i < s) {
+      st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, h, w, dmax, ksigma, ws.px_tab, ws.py_tab);
+      if (st.live) {
+        r = gsr_make_rec(sx, sy, rho, x, y, cr, cg, cb);
+        if (!(gsr_finite(r.a) && gsr_finite(r.b) && gsr_finite(r.c))) st.live = false;
+      }
+      if (st.live) {
+        float4* dr = reinterpret_cast<float4*>(ws.rec_in + i);
+        dr[0] = make_float4(r.x, r.y, r.a, r.b);
+        dr[1] = make_float4(r.c, r.r, r.g, r.bl);
+        if (st.binds) ws.box_in[i] = gsr_box_pack(st.x0, st.x1, st.y0, st.y1, true);
+      }
     }
+    const uint32_t entry = (uint32_t)i | (st.binds ? 0x80000000u : 0u);
+
+    // ---- the CTA's region rectangle
+    const int b0 = st.live ? st.y0 / GSR_REGION : 0x3fffffff, b1 = st.live ? st.y1 / GSR_REGION : -1;
+    const int c0 = st.live ? st.x0 / GSR_REGION : 0x3fffffff, c1 = st.live ? st.x1 / GSR_REGION : -1;
+    {
+      const int wb0 = __reduce_min_sync(full, b0), wb1 = __reduce_max_sync(full, b1);
+      const int wc0 = __reduce_min_sync(full, c0), wc1 = __reduce_max_sync(full, c1);
+      if (lane == 0) {
+        sm.red[0][warp] = wb0;
+        sm.red[1][warp] = wb1;
+        sm.red[2][warp] = wc0;
+        sm.red[3][warp] = wc1;
+      }
+    }
+    for (int k = tid; k < GSR_RB_MAXR; k += GSR_RB_THREADS) sm.cnt[k] = 0;
+    __syncthreads();
+    int B0 = 0x3fffffff, B1 = -1, C0 = 0x3fffffff, C1 = -1;
+#pragma unroll
+    for (int k = 0; k < (GSR_RB_THREADS + 31) / 32; ++k) {
+      B0 = min(B0, sm.red[0][k]);
+      B1 = max(B1, sm.red[1][k]);
+      C0 = min(C0, sm.red[2][k]);
+      C1 = max(C1, sm.red[3][k]);
+    }
+    const bool any_live = B1 >= B0 && C1 >= C0;  // CTA-uniform
+    const int NC = C1 - C0 + 1, NR = any_live ? NC * (B1 - B0 + 1) : 0;
+    if (any_live && (long long)NC * (B1 - B0 + 1) > GSR_RB_MAXR) {
+      gsr_warp_append(st.live, r, entry, st.x0, st.x1, st.y0, st.y1, h, w, ws.nrx, ecut, ws.reg_count, ws.entries,
+                      ws.reg_cap, overflow);
+    } else if (any_live) {
+      // ---- collect: one shared-memory atomic per (Gaussian, region)
+      if (st.live) {
+        const GsrEllipse e = gsr_ellipse(r, h, w);
+        for (int b = b0; b <= b1; ++b) {
+          int ya = b * GSR_REGION, yb = ya + GSR_REGION - 1, xl, xh;
+          ya = ya > st.y0 ? ya : st.y0;
+          yb = yb < st.y1 ? yb : st.y1;
+          if (!gsr_band_xrange(e, ecut, ya, yb, st.x0, st.x1, xl, xh)) continue;
+          const int row = (b - B0) * NC - C0;
+          for (int c = xl / GSR_REGION; c <= xh / GSR_REGION; ++c) {
+            const int slot = atomicAdd(&sm.cnt[row + c], 1);
+            if (slot < GSR_RB_LCAP) {
+              sm.list[row + c][slot] = entry;
+            } else {  // list full: straight to the bucket
+              const int rid = b * ws.nrx + c;
+              const int pos = atomicAdd(ws.reg_count + rid, 1);
+              if (pos < ws.reg_cap) ws.entries[(size_t)rid * ws.reg_cap + pos] = entry;
+              else *overflow = 1;
+            }
+          }
+        }
+      }
+      __syncthreads();
+      // ---- reserve and copy out: a thread per region of the rectangle -- ONE global atomic for the
+      // region's slots, then its short list goes to the bucket
+      for (int k = tid; k < NR; k += GSR_RB_THREADS) {
+        const int n = min(sm.cnt[k], GSR_RB_LCAP);
+        if (n > 0) {
+          const int rb = k / NC;
+          const int rid = (B0 + rb) * ws.nrx + C0 + (k - rb * NC);
+          const int pos = atomicAdd(ws.reg_count + rid, n);
+          uint32_t* dst = ws.entries + (size_t)rid * ws.reg_cap + pos;
+          const int room = ws.reg_cap - pos;
+          if (room < n) *overflow = 1;
+          for (int j = 0; j < n && j < room; ++j) dst[j] = sm.list[k][j];
+        }
+      }
+    }
+    __syncthreads();  // shared memory is reused by the next chunk
   }
-  gsr_warp_append(st.live, r, (uint32_t)i | (st.binds ? 0x80000000u : 0u), st.x0, st.x1, st.y0, st.y1, h,
-                  w, ws.nrx, ecut, ws.reg_count, ws.entries, ws.reg_cap, ws.stats + GSR_STAT_OVERFLOW);
 }

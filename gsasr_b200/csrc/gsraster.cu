@@ -76,9 +76,16 @@ static int gsr_run_bins(const float* sigmas, const float* coords, const float* c
 static int gsr_run_tiles(const float* sigmas, const float* coords, const float* colors, int s,
                          int h, int w, float dmax, float keff, const GsrWorkspace& ws,
                          cudaStream_t st) {
-  if (s > 0)
-    gsr_region_build_kernel<<<(s + 255) / 256, 256, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff,
-                                                           gsr_ecut(keff), ws);
+  if (s > 0) {
+    // persistent CTAs: one resident wave, every CTA strides over the chunks of the input
+    int dev = 0, nsm = 0, per_sm = 0;
+    GSR_CUDA(cudaGetDevice(&dev));
+    GSR_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+    GSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gsr_region_build_kernel, GSR_RB_THREADS, 0));
+    const int want = (s + GSR_RB_THREADS - 1) / GSR_RB_THREADS, cap = nsm * (per_sm > 0 ? per_sm : 1);
+    gsr_region_build_kernel<<<want < cap ? want : cap, GSR_RB_THREADS, 0, st>>>(sigmas, coords, colors, s, h, w, dmax,
+                                                                               keff, gsr_ecut(keff), ws);
+  }
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
 }

@@ -7,9 +7,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "variants")
 VARIANTS = {
-    "c3": [],
-    "c2": ["GSR_CFG_FR_MIN_CTAS=2"],
-    "c4": ["GSR_CFG_FR_MIN_CTAS=4"],
+    "t64": [],
+    "t32": ["GSR_CFG_RB_THREADS=32"],
+    "t64c12": ["GSR_CFG_RB_MIN_CTAS=12"],
+    "t96": ["GSR_CFG_RB_THREADS=96", "GSR_CFG_RB_MIN_CTAS=10"],
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
@@ -44,6 +45,12 @@ else:
             a.record(); L.gsr_forward_prepared(img.data_ptr(), n, h, w, 0.0, 0, ws.data_ptr(), ws.numel(), sp); b.record()
             torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
         res[cfg + "_fwd_acc_us"] = round(1e3 * float(np.median(ts[3:])), 1)
+        ts = []
+        for i in range(13):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); L.gsr_forward(sd.data_ptr(), cd.data_ptr(), kd.data_ptr(), img.data_ptr(), n, h, w, 3, 0.1, 0.0, 1, ws.data_ptr(), ws.numel(), sp); b.record()
+            torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+        res[cfg + "_full_us"] = round(1e3 * float(np.median(ts[3:])), 1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); L.gsr_prepare(sd.data_ptr(), cd.data_ptr(), kd.data_ptr(), n, h, w, 0.1, 0.0, ws.data_ptr(), ws.numel(), sp); b.record()
         torch.cuda.synchronize(); res[cfg + "_prep_us"] = round(1e3 * a.elapsed_time(b), 1)

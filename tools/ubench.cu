@@ -10,12 +10,14 @@
 constexpr int ITERS = 2048, UNROLL = 8;
 
 enum Kind { FFMA, FFMA2, MUFU, LDS128_SAME, LDS128_HALF, LDS128_QUARTER, LDS128_EIGHTH, LDS128_LANE, LDS64_SAME,
-            LDS32_SAME, SHFL, MIX2x2, MIX1x2, NKIND };
+            LDS32_SAME, SHFL, MIX2x2, MIX1x2, MIX2x2_NOCOL, MIX_MMA, FFMA2_BCAST, NKIND };
 static const char* kNames[NKIND] = {"ffma", "ffma2", "mufu.ex2", "lds128 one address/warp", "lds128 one address/half-warp",
                                     "lds128 one address/quarter-warp", "lds128 one address/4 lanes",
                                     "lds128 lane-distinct (conflict-free)", "lds64 one address/warp",
                                     "lds32 one address/warp", "shfl.idx",
-                                    "eval 2x2 px/lane (per record-iteration)", "eval 1x2 px/lane (per record-iteration)"};
+                                    "eval 2x2 px/lane (per record-iteration)", "eval 1x2 px/lane (per record-iteration)",
+                                    "eval 2x2 px/lane, colour FMAs removed", "eval column/lane + tf32 MMA colours (per 128 evals)",
+                                    "ffma2 scalar-broadcast operands, distinct regs"};
 
 __device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 typedef unsigned long long f2;
@@ -87,6 +89,98 @@ __global__ void __launch_bounds__(1024) bench(long long* cycles, float* sink, fl
     float x, y;
     upk(add2(add2(add2(r0, g0), add2(b0, r1)), add2(g1, b1)), x, y);
     a0 = x + y;
+  } else if (KIND == MIX2x2_NOCOL) {
+    const float py0 = seed * lane, py1 = py0 + seed;
+    const f2 px2 = pk(seed * (lane & 3), seed * (lane & 3) + seed), py2 = pk(py0, py1);
+    f2 r0 = pk(0, 0), r1 = r0;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const uint32_t ad = base + (lane >> 4) * 2048 + ((it * UNROLL + u) & 63) * 32;
+        const float4 q0 = lds128(ad), q1 = lds128(ad + 16);
+        const f2 dx2 = add2(px2, pk(q0.x, q0.x));
+        const f2 dy2 = add2(py2, pk(q0.y, q0.y));
+        const f2 t1 = mul2(pk(q0.w, q0.w), dy2);
+        const f2 t0 = mul2(mul2(pk(q1.x, q1.x), dy2), dy2);
+        float t1l, t1h, t0l, t0h;
+        upk(t1, t1l, t1h);
+        upk(t0, t0l, t0h);
+        const f2 e0 = fma2(dx2, fma2(pk(q0.z, q0.z), dx2, pk(t1l, t1l)), pk(t0l, t0l));
+        const f2 e1 = fma2(dx2, fma2(pk(q0.z, q0.z), dx2, pk(t1h, t1h)), pk(t0h, t0h));
+        float e00, e01, e10, e11;
+        upk(e0, e00, e01);
+        upk(e1, e10, e11);
+        const f2 v0 = pk(ex2(e00), ex2(e01)), v1 = pk(ex2(e10), ex2(e11));
+        r0 = add2(r0, v0);
+        r1 = add2(r1, v1);
+      }
+    }
+    float x, y;
+    upk(add2(r0, r1), x, y);
+    a0 = x + y;
+  } else if (KIND == MIX_MMA) {
+    // warp = one 8x8 region; lane (g = lane >> 2, t = lane & 3) evaluates records t and t + 4 of each
+    // group of 8 at pixel column g, rows 0..7; colours accumulate on the tensor cores (tf32 hi/lo split).
+    const int g = lane >> 2, t = lane & 3;
+    const float nx = seed * g;
+    f2 ny2[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) ny2[m] = pk(seed * (2 * m), seed * (2 * m + 1));
+    float c[4][4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) c[m][0] = c[m][1] = c[m][2] = c[m][3] = 0.f;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+      for (int u = 0; u < UNROLL / 4; ++u) {  // one group of 8 records = 512 evals = 4 "record-iterations" of 128
+        const uint32_t ad = base + (((it * 2 + u) & 7) * 8 + t) * 32;
+        uint32_t hi[2][8];
+        float lo[2][8];
+        uint32_t bf[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const float4 q0 = lds128(ad + r * 128), q1 = lds128(ad + r * 128 + 16);
+          const float dx = q0.x + nx;
+          const float A = q0.z * dx * dx, Bx = q0.w * dx;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const f2 dy2 = add2(ny2[m], pk(q0.y, q0.y));
+            const f2 e2 = fma2(dy2, fma2(pk(q1.x, q1.x), dy2, pk(Bx, Bx)), pk(A, A));
+            float e0, e1;
+            upk(e2, e0, e1);
+            const float v0 = ex2(e0), v1 = ex2(e1);
+            hi[r][2 * m] = __float_as_uint(v0) & 0xffffe000u;
+            hi[r][2 * m + 1] = __float_as_uint(v1) & 0xffffe000u;
+            float l0, l1;
+            upk(add2(pk(v0, v1), pk(-__uint_as_float(hi[r][2 * m]), -__uint_as_float(hi[r][2 * m + 1]))), l0, l1);
+            lo[r][2 * m] = l0;
+            lo[r][2 * m + 1] = l1;
+          }
+          // B fragment: channel g >> 1 of this record, hi (g even) or lo (g odd) part
+          float col;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(col) : "r"(ad + r * 128 + 20 + (g >> 1) * 4));
+          const uint32_t ch = __float_as_uint(col) & 0xffffe000u;
+          bf[r] = g >= 6 ? 0u : ((g & 1) ? __float_as_uint(col - __uint_as_float(ch)) : ch);
+        }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(c[m][0]), "+f"(c[m][1]), "+f"(c[m][2]), "+f"(c[m][3])
+                       : "r"(hi[0][2 * m]), "r"(hi[0][2 * m + 1]), "r"(hi[1][2 * m]), "r"(hi[1][2 * m + 1]), "r"(bf[0]), "r"(bf[1]));
+          asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                       : "+f"(c[m][0]), "+f"(c[m][1]), "+f"(c[m][2]), "+f"(c[m][3])
+                       : "r"(__float_as_uint(lo[0][2 * m])), "r"(__float_as_uint(lo[0][2 * m + 1])), "r"(__float_as_uint(lo[1][2 * m])),
+                         "r"(__float_as_uint(lo[1][2 * m + 1])), "r"(bf[0]), "r"(bf[1]));
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) a0 += c[m][0] + c[m][1] + c[m][2] + c[m][3];
+  } else if (KIND == FFMA2_BCAST) {
+    const f2 qa = pk(seed, seed + 1), qb = pk(seed + 2, seed + 3);
+    for (int it = 0; it < ITERS; ++it) {
+      p0 = fma2(qa, pk(a0, a0), p0); p1 = fma2(qb, pk(a1, a1), p1); p2 = fma2(qa, pk(a2, a2), p2); p3 = fma2(qb, pk(a3, a3), p3);
+      p4 = fma2(qa, pk(a4, a4), p4); p5 = fma2(qb, pk(a5, a5), p5); p6 = fma2(qa, pk(a6, a6), p6); p7 = fma2(qb, pk(a7, a7), p7);
+    }
   } else {
     for (int it = 0; it < ITERS; ++it) {
       if (KIND == FFMA) {
@@ -153,11 +247,11 @@ static void run(int warps) {
 }
 
 int main() {
-  for (int warps : {16, 32}) {
+  for (int warps : {16, 24, 32}) {
     run<FFMA>(warps); run<FFMA2>(warps); run<MUFU>(warps); run<SHFL>(warps);
     run<LDS128_SAME>(warps); run<LDS128_HALF>(warps); run<LDS128_QUARTER>(warps); run<LDS128_EIGHTH>(warps);
     run<LDS128_LANE>(warps); run<LDS64_SAME>(warps); run<LDS32_SAME>(warps);
-    run<MIX1x2>(warps); run<MIX2x2>(warps);
+    run<MIX1x2>(warps); run<MIX2x2>(warps); run<MIX2x2_NOCOL>(warps); run<MIX_MMA>(warps); run<FFMA2_BCAST>(warps);
   }
   return 0;
 }
