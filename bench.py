@@ -330,7 +330,7 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of gsr_forward_kernel per launch, from the
 # `ncu --set full` capture summarised under profiles/ (bytes); None where not captured.
-TRAFFIC = {"HL": 198.6e6}  # profiles/r01_fwd_region_HL_ncu_full.txt: 134.6 MB read + 64.0 MB written
+TRAFFIC = {"HL": 216.8e6}  # profiles/r01_fwd_halfwarp_HL_ncu_full.txt: 150.0 MB read + 66.8 MB written
 
 if __name__ == "__main__":
     main()
