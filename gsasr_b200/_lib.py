@@ -38,6 +38,8 @@ SIGNATURES = {
     "gsr_workspace_bytes": (_sz, [_i, _i, _i]),
     "gsr_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _u32, _vp, _sz, _vp]),
     "gsr_backward": (_i, [_vp] * 7 + [_i, _i, _i, _i, _f, _f, _u32, _vp, _sz, _vp]),
+    "gsr_forward_band": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _u32, _vp, _sz, _vp]),
+    "gsr_backward_band": (_i, [_vp] * 7 + [_i, _i, _i, _i, _i, _i, _f, _f, _u32, _vp, _sz, _vp]),
     "gsr_prepare": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _sz, _vp]),
     "gsr_forward_prepared": (_i, [_vp, _i, _i, _i, _f, _u32, _vp, _sz, _vp]),
     "gsr_backward_prepared": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _u32, _vp, _sz, _vp]),
@@ -51,6 +53,7 @@ SIGNATURES = {
 # CPU test hooks (include/gsraster_test.h)
 TEST_SIGNATURES = {
     "gsr_host_setup": (None, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp]),
+    "gsr_host_setup_band": (None, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp]),
     "gsr_host_window_range": (None, [_i, _f, _f, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "gsr_host_region_mask": (ctypes.c_uint, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _i]),
     "gsr_host_geometry": (None, [ctypes.POINTER(_i)] * 5),

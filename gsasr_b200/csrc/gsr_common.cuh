@@ -73,8 +73,9 @@ GSR_HD float gsr_pix_coord(int i, int n) { return (float)(2.0 * i / (n - 1) - 1.
 // skip iff d > dmax || d < -dmax (so NaN d is NOT skipped; we never get here with NaN centres).
 // `tab` is the table of gsr_pix_coord values of the axis (device: filled by gsr_table_kernel);
 // NULL evaluates the rule directly.
-GSR_HD bool gsr_in_window(int i, int n, float ctr, float dmax, const float* tab = nullptr) {
-  float d = (tab ? tab[i] : gsr_pix_coord(i, n)) - ctr;
+// A band view (rows [off, off+cnt) of the n-pixel axis) has a table of its own rows only: tab[i - off].
+GSR_HD bool gsr_in_window(int i, int n, float ctr, float dmax, const float* tab = nullptr, int off = 0) {
+  float d = (tab ? tab[i - off] : gsr_pix_coord(i, n)) - ctr;
   return !(d > dmax || d < -dmax);
 }
 
@@ -83,10 +84,13 @@ GSR_HD bool gsr_in_window(int i, int n, float ctr, float dmax, const float* tab 
 // and repair them with the exact predicate (the estimate is off by at most one pixel).
 // Empty range <=> lo > hi.
 GSR_HD void gsr_window_range(int n, float ctr, float dmax, int& lo, int& hi,
-                             const float* tab = nullptr) {
+                             const float* tab = nullptr, int off = 0, int cnt = -1) {
+  // [off, off + cnt): the part of the axis that is rendered (a row band; the whole axis by default)
+  if (cnt < 0) cnt = n;
+  const int end = off + cnt;
   if (dmax != dmax || dmax >= 3.0e38f) {  // NaN never skips; +inf never skips
-    lo = 0;
-    hi = n - 1;
+    lo = off;
+    hi = end - 1;
     return;
   }
   if (dmax < 0.0f) {  // every finite d fails one of the two comparisons
@@ -97,16 +101,16 @@ GSR_HD void gsr_window_range(int n, float ctr, float dmax, int& lo, int& hi,
   const double s = 0.5 * (double)(n - 1);
   double flo = ((double)ctr - (double)dmax + 1.0) * s;
   double fhi = ((double)ctr + (double)dmax + 1.0) * s;
-  flo = fmin(fmax(flo, -2.0), (double)n + 1.0);
-  fhi = fmin(fmax(fhi, -2.0), (double)n + 1.0);
+  flo = fmin(fmax(flo, (double)off - 2.0), (double)end + 1.0);
+  fhi = fmin(fmax(fhi, (double)off - 2.0), (double)end + 1.0);
   int l = (int)ceil(flo) - 1;
   int h = (int)floor(fhi) + 1;
-  l = l < 0 ? 0 : (l > n ? n : l);
-  h = h > n - 1 ? n - 1 : (h < -1 ? -1 : h);
-  for (int t = 0; t < 4 && l < n && !gsr_in_window(l, n, ctr, dmax, tab); ++t) ++l;
-  if (l < n && !gsr_in_window(l, n, ctr, dmax, tab)) l = n;
-  for (int t = 0; t < 4 && h >= 0 && !gsr_in_window(h, n, ctr, dmax, tab); ++t) --h;
-  if (h >= 0 && !gsr_in_window(h, n, ctr, dmax, tab)) h = -1;
+  l = l < off ? off : (l > end ? end : l);
+  h = h > end - 1 ? end - 1 : (h < off - 1 ? off - 1 : h);
+  for (int t = 0; t < 4 && l < end && !gsr_in_window(l, n, ctr, dmax, tab, off); ++t) ++l;
+  if (l < end && !gsr_in_window(l, n, ctr, dmax, tab, off)) l = end;
+  for (int t = 0; t < 4 && h >= off && !gsr_in_window(h, n, ctr, dmax, tab, off); ++t) --h;
+  if (h >= off && !gsr_in_window(h, n, ctr, dmax, tab, off)) h = off - 1;
   lo = l;
   hi = h;
 }
@@ -124,9 +128,18 @@ struct GsrSetup {
 GSR_HD bool gsr_finite(float v) { return v == v && fabsf(v) < 3.0e38f; }
 
 // Cull box = exact dmax window  INTERSECT  [c - (k*sigma_px + pad), c + (k*sigma_px + pad)].
+// The image may be a ROW BAND of a taller one: rows [row0, row0 + h) of an hf-row image (hf = 0: the
+// image is whole).  Pixel coordinates, windows and boxes are then those of the full image, cut to the
+// band; band edges behave like image edges.  Everything returned is in band-local rows.
 GSR_HD GsrSetup gsr_setup(float sx, float sy, float rho, float x, float y, float cr, float cg,
                           float cb, int h, int w, float dmax, float ksigma,
-                          const float* px_tab = nullptr, const float* py_tab = nullptr) {
+                          const float* px_tab = nullptr, const float* py_tab = nullptr, int hf = 0,
+                          int row0 = 0) {
+  if (hf <= 0) {
+    hf = h;
+    row0 = 0;
+  }
+  const int rend = row0 + h - 1;  // last row of the band, full-image coordinates
   GsrSetup o;
   o.live = false;
   o.large = false;
@@ -140,7 +153,7 @@ GSR_HD GsrSetup gsr_setup(float sx, float sy, float rho, float x, float y, float
     return o;
   if (sx == 0.0f || sy == 0.0f || !(fabsf(rho) < 1.0f)) return o;
 
-  const double hx = 0.5 * (double)(w - 1), hy = 0.5 * (double)(h - 1);
+  const double hx = 0.5 * (double)(w - 1), hy = 0.5 * (double)(hf - 1);
   const double cx = ((double)x + 1.0) * hx, cy = ((double)y + 1.0) * hy;
   const double ex = (double)ksigma * fabs((double)sx) * hx + (double)GSR_CULL_PAD_PX;
   const double ey = (double)ksigma * fabs((double)sy) * hy + (double)GSR_CULL_PAD_PX;
@@ -162,29 +175,30 @@ GSR_HD GsrSetup gsr_setup(float sx, float sy, float rho, float x, float y, float
     gsr_window_range(w, x, dmax, wx0, wx1, px_tab);
   }
   if (dmx >= 0.0 && ky0 - 2.0 > (cy - dmx * hy) && ky1 + 2.0 < (cy + dmx * hy)) {
-    wy0 = ky0 < 0 ? 0 : ky0;
-    wy1 = ky1 > h - 1 ? h - 1 : ky1;
+    wy0 = ky0 < row0 ? row0 : ky0;
+    wy1 = ky1 > rend ? rend : ky1;
   } else {
-    gsr_window_range(h, y, dmax, wy0, wy1, py_tab);
+    gsr_window_range(hf, y, dmax, wy0, wy1, py_tab, row0, h);
   }
   if (wx0 > wx1 || wy0 > wy1) return o;
   // "binds": on some side the window is tighter than both the k-sigma box and the image edge.
   o.binds = (wx0 > (kx0 > 0 ? kx0 : 0)) || (wx1 < (kx1 < w - 1 ? kx1 : w - 1)) ||
-            (wy0 > (ky0 > 0 ? ky0 : 0)) || (wy1 < (ky1 < h - 1 ? ky1 : h - 1));
+            (wy0 > (ky0 > row0 ? ky0 : row0)) || (wy1 < (ky1 < rend ? ky1 : rend));
   o.x0 = wx0 > kx0 ? wx0 : kx0;
   o.x1 = wx1 < kx1 ? wx1 : kx1;
-  o.y0 = wy0 > ky0 ? wy0 : ky0;
-  o.y1 = wy1 < ky1 ? wy1 : ky1;
+  o.y0 = (wy0 > ky0 ? wy0 : ky0) - row0;  // band-local from here on
+  o.y1 = (wy1 < ky1 ? wy1 : ky1) - row0;
   if (o.x0 > o.x1 || o.y0 > o.y1) return o;
   o.live = true;
 
-  double bx = floor(cx / GSR_BIN), by = floor(cy / GSR_BIN);
+  const double cyl = cy - (double)row0;
+  double bx = floor(cx / GSR_BIN), by = floor(cyl / GSR_BIN);
   const int nbx = (w + GSR_BIN - 1) / GSR_BIN, nby = (h + GSR_BIN - 1) / GSR_BIN;
   o.bin_x = (int)fmin(fmax(bx, 0.0), (double)(nbx - 1));
   o.bin_y = (int)fmin(fmax(by, 0.0), (double)(nby - 1));
   // Distance from the (clamped-into-image) centre to the far edges of the box: a tile that
   // overlaps the box lies within this distance of the home bin along each axis.
-  const double ccx = fmin(fmax(cx, 0.0), (double)(w - 1)), ccy = fmin(fmax(cy, 0.0), (double)(h - 1));
+  const double ccx = fmin(fmax(cx, 0.0), (double)(w - 1)), ccy = fmin(fmax(cyl, 0.0), (double)(h - 1));
   double dxm = fmax(ccx - (double)o.x0, (double)o.x1 - ccx);
   double dym = fmax(ccy - (double)o.y0, (double)o.y1 - ccy);
   o.ext_x = (int)ceil(fmax(dxm, 0.0));
@@ -228,12 +242,12 @@ struct GsrEllipse {
   float cp;         // c - b^2/(4a) in pixel units, <= 0
 };
 
-GSR_HD GsrEllipse gsr_ellipse(const GsrRec& g, int h, int w) {
-  const float hxs = 0.5f * (float)(w - 1), hys = 0.5f * (float)(h - 1);
+GSR_HD GsrEllipse gsr_ellipse(const GsrRec& g, int h, int w, int hf = 0, int row0 = 0) {
+  const float hxs = 0.5f * (float)(w - 1), hys = 0.5f * (float)((hf > 0 ? hf : h) - 1);
   const float gx = 1.0f / hxs, gy = 1.0f / hys;  // normalised units per pixel
   GsrEllipse e;
   e.cx = (g.x + 1.0f) * hxs;
-  e.cy = (g.y + 1.0f) * hys;
+  e.cy = (g.y + 1.0f) * hys - (float)(hf > 0 ? row0 : 0);  // band-local rows
   const float a = g.a * gx * gx, b = g.b * gx * gy, c = g.c * gy * gy;  // conic in pixel units
   e.inv_a = 1.0f / a;
   e.kappa = -0.5f * b * e.inv_a;
@@ -270,8 +284,8 @@ GSR_HD bool gsr_band_xrange(const GsrEllipse& e, float ecut, int ya, int yb, int
 }
 
 GSR_HD uint32_t gsr_region_mask(const GsrRec& g, int bx0, int bx1, int by0, int by1, int tx0,
-                                int ty0, int h, int w, float ecut) {
-  const GsrEllipse e = gsr_ellipse(g, h, w);
+                                int ty0, int h, int w, float ecut, int hf = 0, int row0 = 0) {
+  const GsrEllipse e = gsr_ellipse(g, h, w, hf, row0);
   uint32_t mask = 0;
   const int cx0 = bx0 > tx0 ? bx0 : tx0;
   const int cx1 = bx1 < tx0 + GSR_TILE_W - 1 ? bx1 : tx0 + GSR_TILE_W - 1;

@@ -51,6 +51,7 @@ struct GsrWorkspace {
   float* px_tab;     // w
   float* py_tab;     // h
   size_t bytes;
+  int hf, row0;      // row-band view: the image is rows [row0, row0 + h) of an hf-row image (hf = 0: whole)
 };
 
 constexpr int GSR_SCAN_CHUNK = 4096;  // counters per scan CTA (1024 threads x 4)
@@ -96,6 +97,8 @@ static inline GsrWorkspace gsr_carve(void* base, int s, int h, int w) {
   ws.box = (uint2*)take(sn * sizeof(uint2));
   ws.ids = (int*)take(sn * sizeof(int));
   ws.bytes = off;
+  ws.hf = 0;
+  ws.row0 = 0;
   return ws;
 }
 
@@ -116,7 +119,7 @@ __device__ __forceinline__ void gsr_bin_one(const float* __restrict__ sigmas,
   const float cr = __ldg(colors + 3 * (size_t)i + 0);
   const float cg = __ldg(colors + 3 * (size_t)i + 1);
   const float cb = __ldg(colors + 3 * (size_t)i + 2);
-  GsrSetup st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, h, w, dmax, ksigma, ws.px_tab, ws.py_tab);
+  GsrSetup st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, h, w, dmax, ksigma, ws.px_tab, ws.py_tab, ws.hf, ws.row0);
   if (st.live) {
     const GsrRec r = gsr_make_rec(sx, sy, rho, x, y, cr, cg, cb);
     if (!(gsr_finite(r.a) && gsr_finite(r.b) && gsr_finite(r.c))) st.live = false;
@@ -151,10 +154,11 @@ gsr_bin_kernel(const float* __restrict__ sigmas, const float* __restrict__ coord
 
 // Pixel coordinate tables: the reference's rule (gs.cu:39,46), evaluated once per axis entry.
 __global__ void __launch_bounds__(256) gsr_table_kernel(float* __restrict__ px_tab,
-                                                        float* __restrict__ py_tab, int h, int w) {
+                                                        float* __restrict__ py_tab, int h, int w,
+                                                        int hf, int row0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < w) px_tab[i] = gsr_pix_coord(i, w);
-  if (i < h) py_tab[i] = gsr_pix_coord(i, h);
+  if (i < h) py_tab[i] = hf > 0 ? gsr_pix_coord(i + row0, hf) : gsr_pix_coord(i, h);
 }
 
 // Exclusive scan of n = nb + 1 counters into n + 1 offsets.  One CTA of 1024 threads per
@@ -314,7 +318,8 @@ __device__ __forceinline__ void gsr_warp_flush_pairs(unsigned bal, int rid, uint
 __device__ __forceinline__ void gsr_warp_append(bool live, const GsrRec& r, uint32_t entry, int x0,
                                                 int x1, int y0, int y1, int h, int w, int nrx,
                                                 float ecut, int* __restrict__ cnt,
-                                                uint32_t* __restrict__ ent, int cap, int* overflow) {
+                                                uint32_t* __restrict__ ent, int cap, int* overflow,
+                                                int hf = 0, int row0 = 0) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int b0 = live ? y0 / GSR_REGION : 0x3fffffff, b1 = live ? y1 / GSR_REGION : -1;
@@ -323,7 +328,7 @@ __device__ __forceinline__ void gsr_warp_append(bool live, const GsrRec& r, uint
   const int uc0 = __reduce_min_sync(full, c0), uc1 = __reduce_max_sync(full, c1);
   if (ub1 < ub0 || uc1 < uc0) return;  // no live lane
   GsrEllipse e;
-  if (live) e = gsr_ellipse(r, h, w);
+  if (live) e = gsr_ellipse(r, h, w, hf, row0);
   if ((long long)(ub1 - ub0 + 1) * (uc1 - uc0 + 1) > GSR_COOP_MAX_PAIRS) {
     if (live)
       for (int b = b0; b <= b1; ++b) {
@@ -441,7 +446,7 @@ gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restric
     GsrRec r;
     r.x = r.y = r.a = r.b = r.c = r.r = r.g = r.bl = 0.f;
     if (i < s) {
-      st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, h, w, dmax, ksigma, ws.px_tab, ws.py_tab);
+      st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, h, w, dmax, ksigma, ws.px_tab, ws.py_tab, ws.hf, ws.row0);
       if (st.live) {
         r = gsr_make_rec(sx, sy, rho, x, y, cr, cg, cb);
         if (!(gsr_finite(r.a) && gsr_finite(r.b) && gsr_finite(r.c))) st.live = false;
@@ -482,11 +487,11 @@ gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restric
     const int NC = C1 - C0 + 1, NR = any_live ? NC * (B1 - B0 + 1) : 0;
     if (any_live && (long long)NC * (B1 - B0 + 1) > GSR_RB_MAXR) {
       gsr_warp_append(st.live, r, entry, st.x0, st.x1, st.y0, st.y1, h, w, ws.nrx, ecut, ws.reg_count, ws.entries,
-                      ws.reg_cap, overflow);
+                      ws.reg_cap, overflow, ws.hf, ws.row0);
     } else if (any_live) {
       // ---- collect: one shared-memory atomic per (Gaussian, region)
       if (st.live) {
-        const GsrEllipse e = gsr_ellipse(r, h, w);
+        const GsrEllipse e = gsr_ellipse(r, h, w, ws.hf, ws.row0);
         for (int b = b0; b <= b1; ++b) {
           int ya = b * GSR_REGION, yb = ya + GSR_REGION - 1, xl, xh;
           ya = ya > st.y0 ? ya : st.y0;

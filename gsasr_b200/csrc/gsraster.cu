@@ -51,7 +51,7 @@ static int gsr_check_ws(void* workspace, size_t bytes, size_t need) {
 static int gsr_clear_and_tables(int h, int w, const GsrWorkspace& ws, cudaStream_t st) {
   GSR_CUDA(cudaMemsetAsync(ws.bin_count, 0, ws.zero_bytes, st));
   const int n = w > h ? w : h;
-  gsr_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws.px_tab, ws.py_tab, h, w);
+  gsr_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws.px_tab, ws.py_tab, h, w, ws.hf, ws.row0);
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
 }
@@ -117,6 +117,8 @@ static GsrFwdArgs gsr_fwd_args(const GsrWorkspace& ws, float* img, int h, int w,
   a.rec_in = ws.rec_in;
   a.box_in = ws.box_in;
   a.ntx = ws.ntx;
+  a.hf = ws.hf;
+  a.row0 = ws.row0;
   return a;
 }
 
@@ -200,13 +202,20 @@ static int gsr_launch_backward(const GsrWorkspace& ws, const float* sigmas, cons
   return GSR_OK;
 }
 
-extern "C" int gsr_forward(const float* sigmas, const float* coords, const float* colors,
-                           float* img, int s, int h, int w, int c, float dmax, float ksigma,
-                           uint32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
+// Rows [row0, row0 + h) of an hf-row image (hf = 0: the whole h-row image).
+static bool gsr_band_ok(int h, int hf, int row0) {
+  return hf == 0 || (hf >= 2 && hf <= GSR_MAX_DIM && row0 >= 0 && row0 + h <= hf);
+}
+
+static int gsr_forward_impl(const float* sigmas, const float* coords, const float* colors, float* img,
+                            int s, int h, int w, int c, int hf, int row0, float dmax, float ksigma,
+                            uint32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
   if (c != 3) return GSR_ERR_BAD_CHANNELS;
-  if (!gsr_dims_ok(s, h, w)) return GSR_ERR_BAD_SHAPE;
+  if (!gsr_dims_ok(s, h, w) || !gsr_band_ok(h, hf, row0)) return GSR_ERR_BAD_SHAPE;
   if (!img || (s > 0 && (!sigmas || !coords || !colors))) return GSR_ERR_NULL_POINTER;
-  const GsrWorkspace ws = gsr_carve(workspace, s, h, w);
+  GsrWorkspace ws = gsr_carve(workspace, s, h, w);
+  ws.hf = hf;
+  ws.row0 = row0;
   int rc = gsr_check_ws(workspace, workspace_bytes, ws.bytes);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -218,17 +227,19 @@ extern "C" int gsr_forward(const float* sigmas, const float* coords, const float
   return gsr_raster_forward(ws, img, h, w, keff, flags, st);
 }
 
-extern "C" int gsr_backward(const float* sigmas, const float* coords, const float* colors,
-                            const float* grads, float* grads_sigmas, float* grads_coords,
-                            float* grads_colors, int s, int h, int w, int c, float dmax,
-                            float ksigma, uint32_t flags, void* workspace, size_t workspace_bytes,
-                            void* stream) {
+static int gsr_backward_impl(const float* sigmas, const float* coords, const float* colors,
+                             const float* grads, float* grads_sigmas, float* grads_coords,
+                             float* grads_colors, int s, int h, int w, int c, int hf, int row0,
+                             float dmax, float ksigma, uint32_t flags, void* workspace,
+                             size_t workspace_bytes, void* stream) {
   if (c != 3) return GSR_ERR_BAD_CHANNELS;
-  if (!gsr_dims_ok(s, h, w)) return GSR_ERR_BAD_SHAPE;
+  if (!gsr_dims_ok(s, h, w) || !gsr_band_ok(h, hf, row0)) return GSR_ERR_BAD_SHAPE;
   if (!grads || (s > 0 && (!sigmas || !coords || !colors || !grads_sigmas || !grads_coords ||
                            !grads_colors)))
     return GSR_ERR_NULL_POINTER;
-  const GsrWorkspace ws = gsr_carve(workspace, s, h, w);
+  GsrWorkspace ws = gsr_carve(workspace, s, h, w);
+  ws.hf = hf;
+  ws.row0 = row0;
   int rc = gsr_check_ws(workspace, workspace_bytes, ws.bytes);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -239,6 +250,42 @@ extern "C" int gsr_backward(const float* sigmas, const float* coords, const floa
   if (rc) return rc;
   return gsr_launch_backward(ws, sigmas, grads, grads_sigmas, grads_coords, grads_colors, s, h, w,
                              flags, st);
+}
+
+extern "C" int gsr_forward(const float* sigmas, const float* coords, const float* colors,
+                           float* img, int s, int h, int w, int c, float dmax, float ksigma,
+                           uint32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
+  return gsr_forward_impl(sigmas, coords, colors, img, s, h, w, c, 0, 0, dmax, ksigma, flags, workspace,
+                          workspace_bytes, stream);
+}
+
+extern "C" int gsr_backward(const float* sigmas, const float* coords, const float* colors,
+                            const float* grads, float* grads_sigmas, float* grads_coords,
+                            float* grads_colors, int s, int h, int w, int c, float dmax,
+                            float ksigma, uint32_t flags, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  return gsr_backward_impl(sigmas, coords, colors, grads, grads_sigmas, grads_coords, grads_colors, s, h, w,
+                           c, 0, 0, dmax, ksigma, flags, workspace, workspace_bytes, stream);
+}
+
+// ---- row bands of one image (multi-GPU split of a single large image) ---------------------------
+extern "C" int gsr_forward_band(const float* sigmas, const float* coords, const float* colors,
+                                float* img_band, int s, int h, int w, int c, int row0, int rows,
+                                float dmax, float ksigma, uint32_t flags, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  if (h < 2 || h > GSR_MAX_DIM) return GSR_ERR_BAD_SHAPE;
+  return gsr_forward_impl(sigmas, coords, colors, img_band, s, rows, w, c, h, row0, dmax, ksigma, flags,
+                          workspace, workspace_bytes, stream);
+}
+
+extern "C" int gsr_backward_band(const float* sigmas, const float* coords, const float* colors,
+                                 const float* grads_band, float* grads_sigmas, float* grads_coords,
+                                 float* grads_colors, int s, int h, int w, int c, int row0, int rows,
+                                 float dmax, float ksigma, uint32_t flags, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  if (h < 2 || h > GSR_MAX_DIM) return GSR_ERR_BAD_SHAPE;
+  return gsr_backward_impl(sigmas, coords, colors, grads_band, grads_sigmas, grads_coords, grads_colors, s,
+                           rows, w, c, h, row0, dmax, ksigma, flags, workspace, workspace_bytes, stream);
 }
 
 // ---- split-phase form ---------------------------------------------------------------------------
@@ -400,6 +447,25 @@ extern "C" void gsr_host_setup(const float* sigmas, const float* coords, const f
     o[6] = st.large;
     o[7] = st.bin_y * ((w + GSR_BIN - 1) / GSR_BIN) + st.bin_x;
     o[8] = st.ext_x > st.ext_y ? st.ext_x : st.ext_y;
+  }
+}
+
+// Same for a row band: rows [row0, row0 + rows) of the h-row image; boxes are band-local.
+extern "C" void gsr_host_setup_band(const float* sigmas, const float* coords, const float* colors,
+                                    int s, int h, int w, int row0, int rows, float dmax, float ksigma,
+                                    int* out /* s x 6: live, x0, x1, y0, y1, binds */) {
+  const float keff = gsr_effective_ksigma(ksigma);
+  for (int i = 0; i < s; ++i) {
+    GsrSetup st = gsr_setup(sigmas[3 * i], sigmas[3 * i + 1], sigmas[3 * i + 2], coords[2 * i],
+                            coords[2 * i + 1], colors[3 * i], colors[3 * i + 1], colors[3 * i + 2],
+                            rows, w, dmax, keff, nullptr, nullptr, h, row0);
+    int* o = out + 6 * (size_t)i;
+    o[0] = st.live;
+    o[1] = st.x0;
+    o[2] = st.x1;
+    o[3] = st.y0;
+    o[4] = st.y1;
+    o[5] = st.binds;
   }
 }
 

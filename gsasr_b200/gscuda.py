@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["gs_render", "gs_render_backward", "set_ksigma", "get_ksigma"]
+__all__ = ["gs_render", "gs_render_backward", "gs_render_band", "gs_render_backward_band", "set_ksigma", "get_ksigma"]
 
 _ksigma = float(os.environ.get("GSR_KSIGMA", "0"))  # 0 -> library default (GSR_DEFAULT_KSIGMA)
 
@@ -111,4 +111,55 @@ def gs_render_backward(sigmas, coords, colors, grads, grads_sigmas, grads_coords
                             _ptr(grads_sigmas), _ptr(grads_coords), _ptr(grads_colors), s, h, w, c,
                             float(dmax), float(_ksigma if ksigma is None else ksigma), int(flags),
                             ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)
+
+
+# ---- row bands of one image (no counterpart in the reference, whose kernels always walk the whole
+# image, gs.cu:38-62): rows [row0, row0 + rows) of the h x w image, same conventions as gs_render.
+def gs_render_band(sigmas, coords, colors, band_img, s, h, w, c, row0, rows, dmax=float("inf"), *,
+                   ksigma=None, flags=0, workspace_buf=None):
+    L = _lib.load()
+    for t, n in ((sigmas, "sigmas"), (coords, "coords"), (colors, "colors"), (band_img, "band_img")):
+        _check_input(t, n)
+    s, h, w, c, row0, rows = int(s), int(h), int(w), int(c), int(row0), int(rows)
+    if c != 3:
+        raise RuntimeError("libgsraster: c must be 3 (the reference forward hard-codes 3 channels)")
+    _check_shape(sigmas, (s, 3), "sigmas")
+    _check_shape(coords, (s, 2), "coords")
+    _check_shape(colors, (s, 3), "colors")
+    if band_img.numel() != rows * w * c:
+        raise RuntimeError("band_img must have rows*w*c elements")
+    with torch.cuda.device(sigmas.device):
+        ws = workspace_buf if workspace_buf is not None else workspace(s, rows, w, sigmas.device)
+        rc = L.gsr_forward_band(_ptr(sigmas), _ptr(coords), _ptr(colors), band_img.data_ptr(), s, h, w, c,
+                                row0, rows, float(dmax), float(_ksigma if ksigma is None else ksigma),
+                                int(flags), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)
+
+
+def gs_render_backward_band(sigmas, coords, colors, band_grads, grads_sigmas, grads_coords, grads_colors,
+                            s, h, w, c, row0, rows, dmax=float("inf"), *, ksigma=None, flags=0,
+                            workspace_buf=None):
+    L = _lib.load()
+    for t, n in ((sigmas, "sigmas"), (coords, "coords"), (colors, "colors"), (band_grads, "band_grads"),
+                 (grads_sigmas, "grads_sigmas"), (grads_coords, "grads_coords"),
+                 (grads_colors, "grads_colors")):
+        _check_input(t, n)
+    s, h, w, c, row0, rows = int(s), int(h), int(w), int(c), int(row0), int(rows)
+    if c != 3:
+        raise RuntimeError("libgsraster: c must be 3")
+    _check_shape(sigmas, (s, 3), "sigmas")
+    _check_shape(coords, (s, 2), "coords")
+    _check_shape(colors, (s, 3), "colors")
+    _check_shape(grads_sigmas, (s, 3), "grads_sigmas")
+    _check_shape(grads_coords, (s, 2), "grads_coords")
+    _check_shape(grads_colors, (s, 3), "grads_colors")
+    if band_grads.numel() != rows * w * c:
+        raise RuntimeError("band_grads must have rows*w*c elements")
+    with torch.cuda.device(sigmas.device):
+        ws = workspace_buf if workspace_buf is not None else workspace(s, rows, w, sigmas.device)
+        rc = L.gsr_backward_band(_ptr(sigmas), _ptr(coords), _ptr(colors), band_grads.data_ptr(),
+                                 _ptr(grads_sigmas), _ptr(grads_coords), _ptr(grads_colors), s, h, w, c,
+                                 row0, rows, float(dmax), float(_ksigma if ksigma is None else ksigma),
+                                 int(flags), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)

@@ -57,6 +57,13 @@ def render_units_sharded(n_units: int, render_unit: Callable[[int], torch.Tensor
         src = owner_of(i, n_units, world)
         nd = int(shapes[i, 0])
         shape = [int(v) for v in shapes[i, 1:1 + nd]]
+        numel = 1
+        for v in shape:
+            numel *= v
+        if numel == 0:  # an empty unit (e.g. a rank without rows): nothing to exchange
+            if gather_to is None or rank == gather_to:
+                out.append(mine[i] if src == rank else torch.empty(shape, dtype=torch.float32, device=device))
+            continue
         if gather_to is None:
             buf = mine[i].contiguous() if src == rank else torch.empty(shape, dtype=torch.float32, device=device)
             dist.broadcast(buf, src=dist.get_global_rank(group, src) if group else src, group=group)
@@ -89,3 +96,82 @@ def render_batch_sharded(gs_parameters: Sequence[torch.Tensor], sr_sizes, scales
                          scale_modify=torch.tensor([sc, sc]), dmax=dmax)
 
     return render_units_sharded(len(gs_parameters), unit, gather_to=gather_to, group=group)
+
+
+# ---- one large image over several GPUs: row bands -------------------------------
+# Every rank holds all Gaussians (32 B each: 67 MB for the 2M-Gaussian headline field) and renders
+# the rows of its band with gsr_forward_band; the bands are then gathered.  Bands start on multiples
+# of 8 rows -- the rasteriser's region height -- so no region is split between two ranks.  Backward:
+# every rank turns its band of dL/dimg into partial parameter gradients (the gradients are linear in
+# the pixels), summed with one all-reduce of the (N,3)+(N,2)+(N,3) block.
+BAND_ALIGN = 8
+
+
+def band_rows(h: int, rank: int, world: int):
+    """(row0, rows) of `rank`'s band of an h-row image; rows == 0 if there are more ranks than
+    8-row strips.  Every non-empty band has at least 2 rows (the C ABI's minimum)."""
+    strips = (h + BAND_ALIGN - 1) // BAND_ALIGN
+    starts = [min(BAND_ALIGN * shard_range(strips, r, world)[0], h) for r in range(world)] + [h]
+    # a 1-row tail (h % 8 == 1 and the last strip alone in its band) takes a strip from the band above
+    last = max(r for r in range(world) if starts[r] < h)
+    if h - starts[last] < 2 and last > 0:
+        starts[last] -= BAND_ALIGN
+        for r in range(last):
+            starts[r] = min(starts[r], starts[last])
+    return starts[rank], starts[rank + 1] - starts[rank]
+
+
+def _band_forward_cuda(sigmas, coords, colors, h, w, row0, rows, dmax):
+    from . import gscuda
+
+    band = torch.zeros(rows, w, 3, dtype=torch.float32, device=sigmas.device)
+    gscuda.gs_render_band(sigmas, coords, colors, band, sigmas.shape[0], h, w, 3, row0, rows, dmax,
+                          flags=1)  # GSR_FLAG_OVERWRITE
+    return band
+
+
+def render_image_bands(sigmas, coords, colors, h: int, w: int, dmax: float, *, render_band=None,
+                       gather_to: int | None = None, group=None):
+    """gaussiansplatting_render of ONE (h,w) image split into row bands over the ranks of `group`.
+    Every rank passes the same (sigmas, coords, colors).  Returns the (h,w,3) image on `gather_to`
+    (on every rank if None), None elsewhere.  render_band(sigmas, coords, colors, h, w, row0, rows,
+    dmax) -> (rows,w,3) defaults to the CUDA band kernel."""
+    render_band = render_band or _band_forward_cuda
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def unit(r):
+        row0, rows = band_rows(h, r, world)
+        if rows == 0:
+            return torch.zeros(0, w, 3, dtype=torch.float32, device=sigmas.device)
+        return render_band(sigmas, coords, colors, h, w, row0, rows, dmax)
+
+    bands = render_units_sharded(world, unit, gather_to=gather_to, group=group)
+    return None if bands is None else torch.cat(bands, dim=0)
+
+
+def _band_backward_cuda(sigmas, coords, colors, grads_band, h, w, row0, rows, dmax):
+    from . import gscuda
+
+    gs, gc, gk = torch.zeros_like(sigmas), torch.zeros_like(coords), torch.zeros_like(colors)
+    gscuda.gs_render_backward_band(sigmas, coords, colors, grads_band.contiguous(), gs, gc, gk,
+                                   sigmas.shape[0], h, w, 3, row0, rows, dmax)
+    return gs, gc, gk
+
+
+def backward_image_bands(sigmas, coords, colors, grads, h: int, w: int, dmax: float, *,
+                         backward_band=None, group=None):
+    """Gradients of render_image_bands: `grads` is the full (h,w,3) dL/dimg (every rank reads only
+    its band of it).  Returns (grads_sigmas, grads_coords, grads_colors), identical on every rank
+    after one all-reduce(sum) of 32 bytes per Gaussian."""
+    backward_band = backward_band or _band_backward_cuda
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
+    row0, rows = band_rows(h, rank, world)
+    if rows > 0:
+        gs, gc, gk = backward_band(sigmas, coords, colors, grads[row0:row0 + rows], h, w, row0, rows, dmax)
+    else:
+        gs, gc, gk = torch.zeros_like(sigmas), torch.zeros_like(coords), torch.zeros_like(colors)
+    if world > 1:
+        packed = torch.cat([gs, gc, gk], dim=1).contiguous()  # (N,8): one collective instead of three
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        gs, gc, gk = packed[:, 0:3].contiguous(), packed[:, 3:5].contiguous(), packed[:, 5:8].contiguous()
+    return gs, gc, gk

@@ -92,6 +92,22 @@ int gsr_backward(const float* sigmas, const float* coords, const float* colors,
                  float* grads_colors, int s, int h, int w, int c, float dmax, float ksigma,
                  uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Row band of one image: rows [row0, row0 + rows) of the h x w image, for splitting a single large
+ * image over several GPUs (the reference has no counterpart: its kernels always walk
+ * the whole image, gs.cu:38-62).  img_band / grads_band hold `rows` rows ((rows,w,3), or (3,rows,w)
+ * with GSR_FLAG_CHW); pixel coordinates, dmax windows and inclusion sets are those of the FULL image,
+ * so the bands of a partition of [0,h) stacked together equal gsr_forward on the whole image (up to
+ * summation order), and the gradients of the bands SUM to gsr_backward's (the gradients are linear
+ * in the pixels).  rows >= 2.  Workspace: gsr_workspace_bytes(s, rows, w). */
+int gsr_forward_band(const float* sigmas, const float* coords, const float* colors, float* img_band,
+                     int s, int h, int w, int c, int row0, int rows, float dmax, float ksigma,
+                     uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
+int gsr_backward_band(const float* sigmas, const float* coords, const float* colors,
+                      const float* grads_band, float* grads_sigmas, float* grads_coords,
+                      float* grads_colors, int s, int h, int w, int c, int row0, int rows, float dmax,
+                      float ksigma, uint32_t flags, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
 /* Split-phase form.  gsr_forward == gsr_prepare + gsr_forward_prepared, gsr_backward ==
  * gsr_prepare + gsr_backward_prepared.  gsr_prepare runs the O(N) set-up (cull boxes, counting
  * sort by home bin) and leaves it in `workspace`; as long as the workspace is untouched and

@@ -12,6 +12,9 @@ extern "C" {
 /* out is (s,9) int32: live, x0, x1, y0, y1 (inclusive cull box), binds, large, home bin, extent */
 void gsr_host_setup(const float* sigmas, const float* coords, const float* colors, int s, int h,
                     int w, float dmax, float ksigma, int* out);
+/* Row-band view (gsr_forward_band): out is s x 6 = live, x0, x1, y0, y1 (band-local rows), binds. */
+void gsr_host_setup_band(const float* sigmas, const float* coords, const float* colors, int s, int h, int w,
+                         int row0, int rows, float dmax, float ksigma, int* out);
 /* inclusive pixel range of the reference's dmax window on an n-pixel axis (gs.cu:39-50) */
 void gsr_host_window_range(int n, float ctr, float dmax, int* lo, int* hi);
 /* 16-bit mask of the 8x8 regions of the 32x32 tile at (tx0,ty0) that Gaussian i may touch */

@@ -113,3 +113,24 @@ def test_large_class_and_bins():
     assert st[1, 6] == 0
     nbx = (w + bin_ - 1) // bin_
     assert st[1, 7] == ((h - 1) // bin_) * nbx + 0  # bottom-left corner bin
+
+
+@pytest.mark.parametrize("h,w,dmax,ksigma", [(97, 40, 0.07, 0.0), (64, 64, np.inf, 0.0), (50, 50, 0.5, float("inf")),
+                                             (33, 20, 0.02, float("inf"))])
+def test_band_setup_is_the_whole_image_box_cut_to_the_band(h, w, dmax, ksigma):
+    """gsr_forward_band's set-up: the cull box of a Gaussian in rows [row0, row0+rows) is its whole-image
+    box intersected with the band (band-local rows); x is untouched; a box that misses the band is dead."""
+    L = _lib.load()
+    rng = np.random.default_rng(h + w)
+    sig, xy, col = _random_field(rng, 200, 0.01, 0.3)
+    full = emulate.host_setup(sig, xy, col, h, w, dmax, ksigma)
+    for row0, rows in ((0, h), (0, 8), (8, 16), (h - 9, 9), (24, 2), (h - 2, 2)):
+        out = np.zeros((200, 6), np.int32)
+        L.gsr_host_setup_band(sig.ctypes.data, xy.ctypes.data, col.ctypes.data, 200, h, w, row0, rows,
+                              float(dmax), float(ksigma), out.ctypes.data)
+        for f, b in zip(full, out):
+            y0, y1 = max(int(f[3]), row0), min(int(f[4]), row0 + rows - 1)
+            if not f[0] or y0 > y1:
+                assert b[0] == 0
+            else:
+                assert b.tolist()[:5] == [1, int(f[1]), int(f[2]), y0 - row0, y1 - row0]

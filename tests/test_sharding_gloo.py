@@ -73,3 +73,68 @@ def test_units_sharded_over_two_ranks(n_units, gather_to):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), n_units, gather_to, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+# ---- one image split into row bands over the ranks (sharding.render_image_bands) ----------------
+def test_band_rows_partition_the_image():
+    for h in (2, 3, 8, 9, 16, 17, 25, 100, 2048):
+        for world in (1, 2, 3, 4, 8):
+            tot = 0
+            for r in range(world):
+                row0, rows = sharding.band_rows(h, r, world)
+                assert rows == 0 or (row0 == tot and rows >= 2 and row0 % sharding.BAND_ALIGN == 0)
+                tot += rows
+            assert tot == h
+
+
+def _band_field(h, w):
+    p = fields.raw_field(10, 10, seed=3)
+    s, c, k = fields.map_field(p, h, w, 2.0)
+    return s, c, k
+
+
+def _oracle_band(sigmas, coords, colors, h, w, row0, rows, dmax):
+    """Stand-in for the CUDA band kernel in the CPU test: the oracle's whole image, cut."""
+    from oracle import oracle
+
+    img = oracle.forward(sigmas.numpy(), coords.numpy(), colors.numpy(), h, w, dmax)
+    return torch.from_numpy(img[row0:row0 + rows].astype(np.float32))
+
+
+def _oracle_band_backward(sigmas, coords, colors, grads_band, h, w, row0, rows, dmax):
+    from oracle import oracle
+
+    g = np.zeros((h, w, 3), np.float32)
+    g[row0:row0 + rows] = grads_band.numpy()
+    return tuple(torch.from_numpy(a.astype(np.float32)) for a in
+                 oracle.backward(sigmas.numpy(), coords.numpy(), colors.numpy(), g, dmax))
+
+
+def _band_worker(rank, world, port, h, w, gather_to, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle
+
+        s, c, k = _band_field(h, w)
+        img = sharding.render_image_bands(s, c, k, h, w, 0.3, render_band=_oracle_band, gather_to=gather_to)
+        want = oracle.forward(s.numpy(), c.numpy(), k.numpy(), h, w, 0.3).astype(np.float32)
+        ok = (img is None and rank != gather_to) if (gather_to is not None and rank != gather_to) else \
+            (img is not None and tuple(img.shape) == (h, w, 3) and np.array_equal(img.numpy(), want))
+        g = torch.rand(h, w, 3, generator=torch.Generator().manual_seed(7))
+        got = sharding.backward_image_bands(s, c, k, g, h, w, 0.3, backward_band=_oracle_band_backward)
+        ref = oracle.backward(s.numpy(), c.numpy(), k.numpy(), g.numpy(), 0.3)
+        for a, b in zip(got, ref):
+            ok = ok and np.abs(a.numpy() - b).max() <= 1e-5 * max(np.abs(b).max(), 1e-12)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("h,w,gather_to", [(40, 24, None), (17, 12, 0), (9, 10, 1)])
+def test_image_bands_over_two_ranks(h, w, gather_to):
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_band_worker, args=(world, _free_port(), h, w, gather_to, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
