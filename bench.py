@@ -187,6 +187,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="HL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--split", default="images", choices=["images", "bands"],
+                    help="N > 1: 'images' = every rank its own image (weak scaling, the default); "
+                         "'bands' = one image split into row bands + gather (strong scaling)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -199,7 +202,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from gsasr_b200 import _lib, fields, gscuda
+    from gsasr_b200 import _lib, fields, gscuda, sharding
     from gsasr_b200 import build as gbuild
 
     gbuild.build()
@@ -213,7 +216,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = fields.CONFIGS[args.workload]
-    _, s, c, k, h, w = fields.make(cfg, seed=rank)  # every rank its own image (weak scaling)
+    # every rank its own image (weak scaling); the same image on every rank when it is split into bands
+    _, s, c, k, h, w = fields.make(cfg, seed=0 if args.split == "bands" else rank)
     n = s.shape[0]
     mp_img = h * w / 1e6
     s_h, c_h, k_h = (t.pin_memory() for t in (s, c, k))
@@ -223,7 +227,14 @@ def main():
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
 
+    def step_bands():
+        # --split bands (N > 1): ONE image, every rank renders its row band (gsr_forward_band), then the
+        # bands are gathered on every rank -- strong scaling, the gather is inside the timed region
+        sharding.render_image_bands(sd, cd, kd, h, w, DMAX, gather_to=None)
+
     def step():
+        if args.split == "bands" and world > 1:
+            return step_bands()
         _lib.check(L.gsr_forward(sd.data_ptr(), cd.data_ptr(), kd.data_ptr(), img.data_ptr(), n, h, w, 3,
                                  DMAX, 0.0, _lib.GSR_FLAG_OVERWRITE, ws.data_ptr(), ws.numel(), sptr))
 
@@ -254,7 +265,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    value = world * mp_img / (ms_step * 1e-3)
+    strong = args.split == "bands" and world > 1
+    value = (1 if strong else world) * mp_img / (ms_step * 1e-3)
 
     # ---- dominant kernel, timed alone with events through the split-phase ABI ----
     kern_ms = []
@@ -308,8 +320,8 @@ def main():
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload),
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args.workload), split=args.split),
             "clocks": clocks, "gpu_launches": KERNELS_PER_STEP * args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 12 * h * w,

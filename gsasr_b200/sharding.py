@@ -135,18 +135,43 @@ def render_image_bands(sigmas, coords, colors, h: int, w: int, dmax: float, *, r
     """gaussiansplatting_render of ONE (h,w) image split into row bands over the ranks of `group`.
     Every rank passes the same (sigmas, coords, colors).  Returns the (h,w,3) image on `gather_to`
     (on every rank if None), None elsewhere.  render_band(sigmas, coords, colors, h, w, row0, rows,
-    dmax) -> (rows,w,3) defaults to the CUDA band kernel."""
+    dmax) -> (rows,w,3) defaults to the CUDA band kernel.
+
+    The band shapes follow from (h, world) alone, so nothing but pixels is exchanged: every rank
+    renders its band and the bands -- contiguous row blocks of the (h,w,3) result -- are gathered
+    with ONE in-place all-gather when they are equal-sized, else one broadcast / send per band."""
     render_band = render_band or _band_forward_cuda
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-
-    def unit(r):
-        row0, rows = band_rows(h, r, world)
-        if rows == 0:
-            return torch.zeros(0, w, 3, dtype=torch.float32, device=sigmas.device)
-        return render_band(sigmas, coords, colors, h, w, row0, rows, dmax)
-
-    bands = render_units_sharded(world, unit, gather_to=gather_to, group=group)
-    return None if bands is None else torch.cat(bands, dim=0)
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return render_band(sigmas, coords, colors, h, w, 0, h, dmax)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    bands = [band_rows(h, r, world) for r in range(world)]
+    row0, rows = bands[rank]
+    mine = render_band(sigmas, coords, colors, h, w, row0, rows, dmax) if rows > 0 else None
+    glob = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    if gather_to is not None:  # point-to-point: only the stitching rank holds the image
+        if rank != gather_to:
+            if rows > 0:
+                dist.send(mine.contiguous(), dst=glob(gather_to), group=group)
+            return None
+        full = torch.empty(h, w, 3, dtype=torch.float32, device=sigmas.device)
+        for r, (r0, n) in enumerate(bands):
+            if n == 0:
+                continue
+            if r == rank:
+                full[r0:r0 + n].copy_(mine)
+            else:
+                dist.recv(full[r0:r0 + n], src=glob(r), group=group)
+        return full
+    full = torch.empty(h, w, 3, dtype=torch.float32, device=sigmas.device)
+    if rows > 0:
+        full[row0:row0 + rows].copy_(mine)
+    if all(n == bands[0][1] for _, n in bands):
+        dist.all_gather_into_tensor(full, full[row0:row0 + rows], group=group)  # in place: band r at offset r
+    else:
+        for r, (r0, n) in enumerate(bands):
+            if n > 0:
+                dist.broadcast(full[r0:r0 + n], src=glob(r), group=group)
+    return full
 
 
 def _band_backward_cuda(sigmas, coords, colors, grads_band, h, w, row0, rows, dmax):

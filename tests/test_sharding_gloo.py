@@ -131,7 +131,7 @@ def _band_worker(rank, world, port, h, w, gather_to, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("h,w,gather_to", [(40, 24, None), (17, 12, 0), (9, 10, 1)])
+@pytest.mark.parametrize("h,w,gather_to", [(40, 24, None), (32, 16, None), (17, 12, 0), (9, 10, 1)])
 def test_image_bands_over_two_ranks(h, w, gather_to):
     world = 2
     mgr = mp.Manager()
