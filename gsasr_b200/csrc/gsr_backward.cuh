@@ -27,20 +27,30 @@
 constexpr int GSR_BWD_THREADS = 512;
 constexpr int GSR_BWD_WARPS = GSR_BWD_THREADS / 32;
 constexpr int GSR_BWD_TILE = 32;                       // super tile side (multiple of GSR_BIN)
-constexpr int GSR_BWD_HALO = 24;                       // staged halo cap, pixels
-constexpr int GSR_BWD_RW = GSR_BWD_TILE + 2 * GSR_BWD_HALO;   // staged window side (80)
-constexpr int GSR_BWD_RS = 104;                        // plane row stride in words: >= RW, == 8 mod 32
-constexpr int GSR_BWD_PLANE = GSR_BWD_RW * GSR_BWD_RS; // words per plane
+#ifndef GSR_CFG_BWD_BATCH
+#define GSR_CFG_BWD_BATCH 16
+#endif
+#ifndef GSR_CFG_BWD_HALO
+#define GSR_CFG_BWD_HALO 16
+#endif
+constexpr int GSR_BWD_HALO = GSR_CFG_BWD_HALO;         // staged halo cap, pixels (5 sigma at x4 is <= 16.7)
+constexpr int GSR_BWD_RW = GSR_BWD_TILE + 2 * GSR_BWD_HALO;   // staged window side (64)
+// plane row stride in words: >= RW + padding, == 8 mod 32 (72 for a 64-pixel window, 104 for 80)
+constexpr int GSR_BWD_RS = ((GSR_BWD_RW + 8 - 8 + 31) / 32) * 32 + 8;
+constexpr int GSR_BWD_PAD_X = 8, GSR_BWD_PAD_Y = 3;    // a sweep may run up to 7 columns / 3 rows past a box
+constexpr int GSR_BWD_PLANE = (GSR_BWD_RW + GSR_BWD_PAD_Y) * GSR_BWD_RS; // words per plane
+constexpr int GSR_BWD_GCAP = 512;                      // Gaussians of a tile indexed per pass
 constexpr int GSR_BWD_LARGE_CHUNK = 64;                // large-list Gaussians per extra CTA
-static_assert(GSR_BWD_RS % 32 == 8 && GSR_BWD_RS >= GSR_BWD_RW, "conflict-free patch reads");
+static_assert(GSR_BWD_RS % 32 == 8 && GSR_BWD_RS >= GSR_BWD_RW + GSR_BWD_PAD_X, "conflict-free, padded patch reads");
 static_assert(GSR_BWD_TILE % GSR_BIN == 0, "super tile is made of whole bins");
 
-constexpr int GSR_BWD_BATCH = 16;  // Gaussians a warp reduces before one lane-parallel chain rule
+constexpr int GSR_BWD_BATCH = GSR_CFG_BWD_BATCH;  // Gaussians a warp reduces before one lane-parallel chain rule
 
 struct GsrBwdSmem {
   float plane[3 * GSR_BWD_PLANE];
-  float px[GSR_BWD_RW];
-  float py[GSR_BWD_RW];
+  float px[GSR_BWD_RW + GSR_BWD_PAD_X];
+  float py[GSR_BWD_RW + GSR_BWD_PAD_Y + 1];
+  int gidx[GSR_BWD_GCAP];                      // sorted index of the tile's Gaussians (current pass)
   float tot[GSR_BWD_WARPS][GSR_BWD_BATCH][8];  // reduced sums of the current batch
   int tot_gi[GSR_BWD_WARPS][GSR_BWD_BATCH];    // sorted index of the Gaussians of the batch
 };
@@ -111,24 +121,26 @@ __device__ __forceinline__ void gsr_bwd_sweep_smem(GsrBwdAcc& acc, uint32_t plan
                                                    uint32_t py_s, const float4& a0, const float4& a1,
                                                    int bx0, int bx1, int by0, int by1, int sx0,
                                                    int sy0, int lx, int ly) {
-  const int xlim = bx1 - sx0;
-  for (int yb = by0; yb <= by1; yb += 4) {
-    const int y = yb + ly;
-    const int yc = min(y, by1) - sy0;  // lanes past the box re-read its last row (v = 0 there)
+  // Lanes past the box read padding (finite values, see the staging code) and contribute v = 0.
+  const int nx = (bx1 - bx0 + 8) >> 3;            // 8-pixel steps per row
+  const int x0 = bx0 - sx0 + lx, xlast = bx1 - sx0;
+  const uint32_t xoff = (uint32_t)x0 * 4u;
+  for (int y = by0 + ly; y - ly <= by1; y += 4) {
+    const int yc = y - sy0;
     const bool yok = y <= by1;
     const float dy = gsr_lds32<0>(py_s + yc * 4) - a0.y;
     const float t1 = a0.w * dy;
     const float t0 = a1.x * dy * dy;
-    const uint32_t row = plane_s + yc * (GSR_BWD_RS * 4);
-    for (int xi = bx0 - sx0 + lx; xi - lx <= xlim; xi += 8) {
-      const uint32_t off = (uint32_t)min(xi, xlim) * 4u;
-      const bool ok = yok && xi <= xlim;
-      const float dx = gsr_lds32<0>(px_s + off) - a0.x;
+    uint32_t ad = plane_s + yc * (GSR_BWD_RS * 4) + xoff;
+    uint32_t pa = px_s + xoff;
+    int xi = x0;
+    for (int k = 0; k < nx; ++k, ad += 32, pa += 32, xi += 8) {
+      const float dx = gsr_lds32<0>(pa) - a0.x;
       const float e = fmaf(dx, fmaf(a0.z, dx, t1), t0);
-      const float g0 = gsr_lds32<0>(row + off);
-      const float g1 = gsr_lds32<GSR_BWD_PLANE * 4>(row + off);
-      const float g2 = gsr_lds32<2 * GSR_BWD_PLANE * 4>(row + off);
-      const float v = ok ? gsr_ex2(e) : 0.f;
+      const float g0 = gsr_lds32<0>(ad);
+      const float g1 = gsr_lds32<GSR_BWD_PLANE * 4>(ad);
+      const float g2 = gsr_lds32<2 * GSR_BWD_PLANE * 4>(ad);
+      const float v = (yok && xi <= xlast) ? gsr_ex2(e) : 0.f;
       gsr_bwd_accum(acc, v, g0, g1, g2, dx, dy, a1);
     }
   }
@@ -297,8 +309,19 @@ __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwd
   const int sx0 = max(tx0 - hx, 0), sx1 = min(tx0 + GSR_BWD_TILE - 1 + hx, p.w - 1);
   const int sy0 = max(ty0 - hy, 0), sy1 = min(ty0 + GSR_BWD_TILE - 1 + hy, p.h - 1);
   const int rw = sx1 - sx0 + 1, rh = sy1 - sy0 + 1;
-  if (tid < rw) sm.px[tid] = __ldg(p.px_tab + sx0 + tid);
-  if (tid >= 128 && tid - 128 < rh) sm.py[tid - 128] = __ldg(p.py_tab + sy0 + tid - 128);
+  // Coordinate tables and the zero padding a sweep may read past a box (7 columns / 3 rows): finite
+  // values there, multiplied by v = 0.
+  if (tid < rw + GSR_BWD_PAD_X) sm.px[tid] = tid < rw ? __ldg(p.px_tab + sx0 + tid) : 0.f;
+  if (tid >= 128 && tid - 128 < rh + GSR_BWD_PAD_Y)
+    sm.py[tid - 128] = tid - 128 < rh ? __ldg(p.py_tab + sy0 + tid - 128) : 0.f;
+  for (int e = tid; e < 3 * (rh + GSR_BWD_PAD_Y) * GSR_BWD_PAD_X; e += GSR_BWD_THREADS) {  // right margin
+    const int c = e / ((rh + GSR_BWD_PAD_Y) * GSR_BWD_PAD_X), q = e - c * (rh + GSR_BWD_PAD_Y) * GSR_BWD_PAD_X;
+    sm.plane[c * GSR_BWD_PLANE + (q / GSR_BWD_PAD_X) * GSR_BWD_RS + rw + (q % GSR_BWD_PAD_X)] = 0.f;
+  }
+  for (int e = tid; e < 3 * GSR_BWD_PAD_Y * rw; e += GSR_BWD_THREADS) {  // bottom margin
+    const int c = e / (GSR_BWD_PAD_Y * rw), q = e - c * GSR_BWD_PAD_Y * rw;
+    sm.plane[c * GSR_BWD_PLANE + (rh + q / rw) * GSR_BWD_RS + (q % rw)] = 0.f;
+  }
   if (p.flags & 2u) {  // CHW source: plane by plane
     const size_t gplane = (size_t)p.h * p.w;
     for (int r = warp; r < 3 * rh; r += GSR_BWD_WARPS) {
@@ -317,37 +340,48 @@ __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwd
       }
     }
   }
-  __syncthreads();
 
   const uint32_t plane_s = gsr_smem_addr(sm.plane), px_s = gsr_smem_addr(sm.px), py_s = gsr_smem_addr(sm.py);
-  // ---- one Gaussian per warp at a time, chain rule once per batch ----
-  for (int k0 = warp; k0 < ntot; k0 += GSR_BWD_WARPS * GSR_BWD_BATCH) {
-    int nb = 0;
-    for (int j = 0; j < GSR_BWD_BATCH; ++j) {
-      const int k = k0 + j * GSR_BWD_WARPS;
-      if (k >= ntot) break;
-      int gi = 0, kk = k;
+  for (int pass0 = 0; pass0 < ntot; pass0 += GSR_BWD_GCAP) {
+    // ---- index the Gaussians of this pass: position in the tile -> sorted index (one lookup each,
+    // instead of one per warp per Gaussian)
+    const int npass = min(ntot - pass0, GSR_BWD_GCAP);
+    __syncthreads();  // the previous pass is done with gidx
+    for (int t = tid; t < npass; t += GSR_BWD_THREADS) {
+      int gi = 0, kk = pass0 + t;
 #pragma unroll
       for (int r = 0; r < BPT; ++r) {
         if (kk >= 0 && kk < run_n[r]) gi = run_s[r] + kk;
         kk = kk < run_n[r] ? -1 : kk - run_n[r];
       }
-      const float4* rp = reinterpret_cast<const float4*>(p.rec + gi);
-      const float4 a0 = __ldg(rp), a1 = __ldg(rp + 1);
-      int bx0, bx1, by0, by1;
-      bool binds;
-      gsr_box_unpack(__ldg(p.box + gi), bx0, bx1, by0, by1, binds);
-      GsrBwdAcc acc = gsr_bwd_acc_zero();
-      if (bx0 >= sx0 && bx1 <= sx1 && by0 >= sy0 && by1 <= sy1)
-        gsr_bwd_sweep_smem(acc, plane_s, px_s, py_s, a0, a1, bx0, bx1, by0, by1, sx0, sy0, lx, ly);
-      else
-        gsr_bwd_sweep_gmem(acc, p, a0, a1, bx0, bx1, by0, by1, lx, ly);
-      gsr_bwd_reduce_store(acc, lane, sm.tot[warp][j]);
-      if (lane == 0) sm.tot_gi[warp][j] = gi;
-      ++nb;
+      sm.gidx[t] = gi;
     }
-    __syncwarp();
-    if (lane < nb) gsr_bwd_chain(sm.tot[warp][lane], p, sm.tot_gi[warp][lane]);
-    __syncwarp();
+    __syncthreads();  // also orders the staging above before the sweeps
+
+    // ---- one Gaussian per warp at a time, chain rule once per batch ----
+    for (int k0 = warp; k0 < npass; k0 += GSR_BWD_WARPS * GSR_BWD_BATCH) {
+      int nb = 0;
+      for (int j = 0; j < GSR_BWD_BATCH; ++j) {
+        const int k = k0 + j * GSR_BWD_WARPS;
+        if (k >= npass) break;
+        const int gi = sm.gidx[k];
+        const float4* rp = reinterpret_cast<const float4*>(p.rec + gi);
+        const float4 a0 = __ldg(rp), a1 = __ldg(rp + 1);
+        int bx0, bx1, by0, by1;
+        bool binds;
+        gsr_box_unpack(__ldg(p.box + gi), bx0, bx1, by0, by1, binds);
+        GsrBwdAcc acc = gsr_bwd_acc_zero();
+        if (bx0 >= sx0 && bx1 <= sx1 && by0 >= sy0 && by1 <= sy1)
+          gsr_bwd_sweep_smem(acc, plane_s, px_s, py_s, a0, a1, bx0, bx1, by0, by1, sx0, sy0, lx, ly);
+        else
+          gsr_bwd_sweep_gmem(acc, p, a0, a1, bx0, bx1, by0, by1, lx, ly);
+        gsr_bwd_reduce_store(acc, lane, sm.tot[warp][j]);
+        if (lane == 0) sm.tot_gi[warp][j] = gi;
+        ++nb;
+      }
+      __syncwarp();
+      if (lane < nb) gsr_bwd_chain(sm.tot[warp][lane], p, sm.tot_gi[warp][lane]);
+      __syncwarp();
+    }
   }
 }

@@ -7,10 +7,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "variants")
 VARIANTS = {
-    "t64": [],
-    "t32": ["GSR_CFG_RB_THREADS=32"],
-    "t64c12": ["GSR_CFG_RB_MIN_CTAS=12"],
-    "t96": ["GSR_CFG_RB_THREADS=96", "GSR_CFG_RB_MIN_CTAS=10"],
+    "h16": [],
+    "h24b8": ["GSR_CFG_BWD_HALO=24", "GSR_CFG_BWD_BATCH=8"],
+    "h16b8": ["GSR_CFG_BWD_BATCH=8"],
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
