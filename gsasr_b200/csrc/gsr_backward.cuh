@@ -35,19 +35,18 @@ constexpr int GSR_BWD_TILE = 32;                       // super tile side (multi
 #endif
 constexpr int GSR_BWD_HALO = GSR_CFG_BWD_HALO;         // staged halo cap, pixels (5 sigma at x4 is <= 16.7)
 constexpr int GSR_BWD_RW = GSR_BWD_TILE + 2 * GSR_BWD_HALO;   // staged window side (64)
-// plane row stride in words: >= RW + padding, == 8 mod 32 (72 for a 64-pixel window, 104 for 80)
-constexpr int GSR_BWD_RS = ((GSR_BWD_RW + 8 - 8 + 31) / 32) * 32 + 8;
+constexpr int GSR_BWD_RS = GSR_BWD_RW + 8;            // window row stride in pixels (one float4 each)
 constexpr int GSR_BWD_PAD_X = 8, GSR_BWD_PAD_Y = 3;    // a sweep may run up to 7 columns / 3 rows past a box
-constexpr int GSR_BWD_PLANE = (GSR_BWD_RW + GSR_BWD_PAD_Y) * GSR_BWD_RS; // words per plane
+constexpr int GSR_BWD_WIN = (GSR_BWD_RW + GSR_BWD_PAD_Y) * GSR_BWD_RS;   // float4 pixels of the staged window
 constexpr int GSR_BWD_GCAP = 512;                      // Gaussians of a tile indexed per pass
 constexpr int GSR_BWD_LARGE_CHUNK = 64;                // large-list Gaussians per extra CTA
-static_assert(GSR_BWD_RS % 32 == 8 && GSR_BWD_RS >= GSR_BWD_RW + GSR_BWD_PAD_X, "conflict-free, padded patch reads");
+static_assert(GSR_BWD_RS >= GSR_BWD_RW + GSR_BWD_PAD_X, "padded patch reads");
 static_assert(GSR_BWD_TILE % GSR_BIN == 0, "super tile is made of whole bins");
 
 constexpr int GSR_BWD_BATCH = GSR_CFG_BWD_BATCH;  // Gaussians a warp reduces before one lane-parallel chain rule
 
 struct GsrBwdSmem {
-  float plane[3 * GSR_BWD_PLANE];
+  float4 win[GSR_BWD_WIN];                     // {g_r, g_g, g_b, -}: one LDS.128 per pixel, a quarter-warp reads 128 contiguous bytes
   float px[GSR_BWD_RW + GSR_BWD_PAD_X];
   float py[GSR_BWD_RW + GSR_BWD_PAD_Y + 1];
   int gidx[GSR_BWD_GCAP];                      // sorted index of the tile's Gaussians (current pass)
@@ -117,31 +116,31 @@ __device__ __forceinline__ float gsr_lds32(uint32_t addr) {
   return v;
 }
 
-__device__ __forceinline__ void gsr_bwd_sweep_smem(GsrBwdAcc& acc, uint32_t plane_s, uint32_t px_s,
+__device__ __forceinline__ void gsr_bwd_sweep_smem(GsrBwdAcc& acc, uint32_t win_s, uint32_t px_s,
                                                    uint32_t py_s, const float4& a0, const float4& a1,
                                                    int bx0, int bx1, int by0, int by1, int sx0,
-                                                   int sy0, int lx, int ly) {
-  // Lanes past the box read padding (finite values, see the staging code) and contribute v = 0.
+                                                   int sy0, int lx, int ly, float xstep8) {
+  // Lanes past the box read zero padding (see the staging code) and contribute v = 0.
   const int nx = (bx1 - bx0 + 8) >> 3;            // 8-pixel steps per row
   const int x0 = bx0 - sx0 + lx, xlast = bx1 - sx0;
-  const uint32_t xoff = (uint32_t)x0 * 4u;
+  // dx of this lane's first column; the following columns are 8 pixels further each.  (The forward's
+  // bit-exact pixel table is not needed here: the inclusion set comes from the integer box, and the
+  // gradient tolerance is 1e-3 relative.)
+  const float dx_first = gsr_lds32<0>(px_s + x0 * 4) - a0.x;
   for (int y = by0 + ly; y - ly <= by1; y += 4) {
     const int yc = y - sy0;
     const bool yok = y <= by1;
     const float dy = gsr_lds32<0>(py_s + yc * 4) - a0.y;
     const float t1 = a0.w * dy;
     const float t0 = a1.x * dy * dy;
-    uint32_t ad = plane_s + yc * (GSR_BWD_RS * 4) + xoff;
-    uint32_t pa = px_s + xoff;
+    uint32_t ad = win_s + (uint32_t)(yc * GSR_BWD_RS + x0) * 16u;
+    float dx = dx_first;
     int xi = x0;
-    for (int k = 0; k < nx; ++k, ad += 32, pa += 32, xi += 8) {
-      const float dx = gsr_lds32<0>(pa) - a0.x;
+    for (int k = 0; k < nx; ++k, ad += 128, xi += 8, dx += xstep8) {
       const float e = fmaf(dx, fmaf(a0.z, dx, t1), t0);
-      const float g0 = gsr_lds32<0>(ad);
-      const float g1 = gsr_lds32<GSR_BWD_PLANE * 4>(ad);
-      const float g2 = gsr_lds32<2 * GSR_BWD_PLANE * 4>(ad);
+      const float4 g = gsr_lds128(ad);
       const float v = (yok && xi <= xlast) ? gsr_ex2(e) : 0.f;
-      gsr_bwd_accum(acc, v, g0, g1, g2, dx, dy, a1);
+      gsr_bwd_accum(acc, v, g.x, g.y, g.z, dx, dy, a1);
     }
   }
 }
@@ -314,34 +313,33 @@ __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwd
   if (tid < rw + GSR_BWD_PAD_X) sm.px[tid] = tid < rw ? __ldg(p.px_tab + sx0 + tid) : 0.f;
   if (tid >= 128 && tid - 128 < rh + GSR_BWD_PAD_Y)
     sm.py[tid - 128] = tid - 128 < rh ? __ldg(p.py_tab + sy0 + tid - 128) : 0.f;
-  for (int e = tid; e < 3 * (rh + GSR_BWD_PAD_Y) * GSR_BWD_PAD_X; e += GSR_BWD_THREADS) {  // right margin
-    const int c = e / ((rh + GSR_BWD_PAD_Y) * GSR_BWD_PAD_X), q = e - c * (rh + GSR_BWD_PAD_Y) * GSR_BWD_PAD_X;
-    sm.plane[c * GSR_BWD_PLANE + (q / GSR_BWD_PAD_X) * GSR_BWD_RS + rw + (q % GSR_BWD_PAD_X)] = 0.f;
-  }
-  for (int e = tid; e < 3 * GSR_BWD_PAD_Y * rw; e += GSR_BWD_THREADS) {  // bottom margin
-    const int c = e / (GSR_BWD_PAD_Y * rw), q = e - c * GSR_BWD_PAD_Y * rw;
-    sm.plane[c * GSR_BWD_PLANE + (rh + q / rw) * GSR_BWD_RS + (q % rw)] = 0.f;
-  }
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int e = tid; e < (rh + GSR_BWD_PAD_Y) * GSR_BWD_PAD_X; e += GSR_BWD_THREADS)  // right margin
+    sm.win[(e / GSR_BWD_PAD_X) * GSR_BWD_RS + rw + (e % GSR_BWD_PAD_X)] = zero4;
+  for (int e = tid; e < GSR_BWD_PAD_Y * rw; e += GSR_BWD_THREADS)  // bottom margin
+    sm.win[(rh + e / rw) * GSR_BWD_RS + (e % rw)] = zero4;
+  float* const winf = reinterpret_cast<float*>(sm.win);
   if (p.flags & 2u) {  // CHW source: plane by plane
     const size_t gplane = (size_t)p.h * p.w;
     for (int r = warp; r < 3 * rh; r += GSR_BWD_WARPS) {
       const int c = r / rh, yi = r - c * rh;
       const float* src = p.grads + c * gplane + (size_t)(sy0 + yi) * p.w + sx0;
-      float* dst = sm.plane + c * GSR_BWD_PLANE + yi * GSR_BWD_RS;
-      for (int e = lane; e < rw; e += 32) dst[e] = __ldg(src + e);
+      float* dst = winf + (size_t)yi * GSR_BWD_RS * 4 + c;
+      for (int e = lane; e < rw; e += 32) dst[e * 4] = __ldg(src + e);
     }
   } else {  // HWC source: a row of the window is 3*rw contiguous floats
     for (int yi = warp; yi < rh; yi += GSR_BWD_WARPS) {
       const float* src = p.grads + ((size_t)(sy0 + yi) * p.w + sx0) * 3;
-      float* dst = sm.plane + yi * GSR_BWD_RS;
+      float* dst = winf + (size_t)yi * GSR_BWD_RS * 4;
       for (int e = lane; e < 3 * rw; e += 32) {
         const int x = e / 3, c = e - 3 * x;
-        dst[c * GSR_BWD_PLANE + x] = __ldg(src + e);
+        dst[x * 4 + c] = __ldg(src + e);
       }
     }
   }
 
-  const uint32_t plane_s = gsr_smem_addr(sm.plane), px_s = gsr_smem_addr(sm.px), py_s = gsr_smem_addr(sm.py);
+  const uint32_t win_s = gsr_smem_addr(sm.win), px_s = gsr_smem_addr(sm.px), py_s = gsr_smem_addr(sm.py);
+  const float xstep8 = 16.0f / (float)(p.w - 1);  // eight pixels in normalised units
   for (int pass0 = 0; pass0 < ntot; pass0 += GSR_BWD_GCAP) {
     // ---- index the Gaussians of this pass: position in the tile -> sorted index (one lookup each,
     // instead of one per warp per Gaussian)
@@ -372,7 +370,7 @@ __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwd
         gsr_box_unpack(__ldg(p.box + gi), bx0, bx1, by0, by1, binds);
         GsrBwdAcc acc = gsr_bwd_acc_zero();
         if (bx0 >= sx0 && bx1 <= sx1 && by0 >= sy0 && by1 <= sy1)
-          gsr_bwd_sweep_smem(acc, plane_s, px_s, py_s, a0, a1, bx0, bx1, by0, by1, sx0, sy0, lx, ly);
+          gsr_bwd_sweep_smem(acc, win_s, px_s, py_s, a0, a1, bx0, bx1, by0, by1, sx0, sy0, lx, ly, xstep8);
         else
           gsr_bwd_sweep_gmem(acc, p, a0, a1, bx0, bx1, by0, by1, lx, ly);
         gsr_bwd_reduce_store(acc, lane, sm.tot[warp][j]);

@@ -7,9 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "variants")
 VARIANTS = {
-    "h16": [],
-    "h24b8": ["GSR_CFG_BWD_HALO=24", "GSR_CFG_BWD_BATCH=8"],
-    "h16b8": ["GSR_CFG_BWD_BATCH=8"],
+    "base": [],
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
