@@ -25,7 +25,9 @@
 #include "gsr_common.cuh"
 
 constexpr int GSR_STAT_EXT_X = 0, GSR_STAT_EXT_Y = 1, GSR_STAT_OVERFLOW = 2, GSR_STAT_ENTRIES = 3;
-constexpr int GSR_ENTRIES_PER_GAUSSIAN = 16;  // bucket capacity per region = 16 * N / regions + 32
+// bucket capacity per region = 40 * N / regions + 32: a Gaussian of the x4 head touches 6.8 regions on
+// average, one of the x8 head 23 (5 sigma = 33 px); 4 bytes per slot
+constexpr int GSR_ENTRIES_PER_GAUSSIAN = 40;
 
 struct GsrWorkspace {
   // ---- one block, cleared per call ----

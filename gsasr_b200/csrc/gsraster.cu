@@ -48,6 +48,27 @@ static int gsr_check_ws(void* workspace, size_t bytes, size_t need) {
   return GSR_OK;
 }
 
+
+// Resident grid of a persistent kernel on the current device: SM count x CTAs per SM.  Queried once
+// per (device, kernel) and cached -- immutable facts of the device, written once with the same
+// value by whichever thread gets there first.
+template <typename K>
+static int gsr_resident_grid(K kernel, int threads, int slot, int* out) {
+  static int cache[2][64];  // [kernel slot][device], 0 = not yet queried
+  int dev = 0;
+  GSR_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && cache[slot][dev] > 0) {
+    *out = cache[slot][dev];
+    return GSR_OK;
+  }
+  int nsm = 0, per_sm = 0;
+  GSR_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  GSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+  *out = nsm * (per_sm > 0 ? per_sm : 1);
+  if (dev >= 0 && dev < 64) cache[slot][dev] = *out;
+  return GSR_OK;
+}
+
 static int gsr_clear_and_tables(int h, int w, const GsrWorkspace& ws, cudaStream_t st) {
   GSR_CUDA(cudaMemsetAsync(ws.bin_count, 0, ws.zero_bytes, st));
   const int n = w > h ? w : h;
@@ -78,11 +99,10 @@ static int gsr_run_tiles(const float* sigmas, const float* coords, const float* 
                          cudaStream_t st) {
   if (s > 0) {
     // persistent CTAs: one resident wave, every CTA strides over the chunks of the input
-    int dev = 0, nsm = 0, per_sm = 0;
-    GSR_CUDA(cudaGetDevice(&dev));
-    GSR_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-    GSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gsr_region_build_kernel, GSR_RB_THREADS, 0));
-    const int want = (s + GSR_RB_THREADS - 1) / GSR_RB_THREADS, cap = nsm * (per_sm > 0 ? per_sm : 1);
+    int cap = 0;
+    const int rc = gsr_resident_grid(gsr_region_build_kernel, GSR_RB_THREADS, 0, &cap);
+    if (rc) return rc;
+    const int want = (s + GSR_RB_THREADS - 1) / GSR_RB_THREADS;
     gsr_region_build_kernel<<<want < cap ? want : cap, GSR_RB_THREADS, 0, st>>>(sigmas, coords, colors, s, h, w, dmax,
                                                                                keff, gsr_ecut(keff), ws);
   }
@@ -128,12 +148,11 @@ static int gsr_launch_forward_region(const GsrWorkspace& ws, float* img, int h, 
   GsrFwdArgs a = gsr_fwd_args(ws, img, h, w, keff, flags);
   a.want = 0;
   // persistent warps: one resident wave, every warp strides over the region pairs
-  int dev = 0, nsm = 0, per_sm = 0;
-  GSR_CUDA(cudaGetDevice(&dev));
-  GSR_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
-  GSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gsr_forward_region_kernel, GSR_FR_THREADS, 0));
+  int cap = 0;
+  const int rc = gsr_resident_grid(gsr_forward_region_kernel, GSR_FR_THREADS, 1, &cap);
+  if (rc) return rc;
   const int nunits = (ws.nrx / 2) * ws.nry;
-  const int want = (nunits + GSR_FR_WARPS - 1) / GSR_FR_WARPS, cap = nsm * (per_sm > 0 ? per_sm : 1);
+  const int want = (nunits + GSR_FR_WARPS - 1) / GSR_FR_WARPS;
   gsr_forward_region_kernel<<<want < cap ? want : cap, GSR_FR_THREADS, 0, st>>>(a);
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
