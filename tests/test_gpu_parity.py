@@ -299,3 +299,39 @@ def test_shuffled_input_takes_the_incoherent_path():
     a = _render(s, c, k, h, w, 0.1)
     b = _render(s[perm].contiguous(), c[perm].contiguous(), k[perm].contiguous(), h, w, 0.1)
     assert float((a - b).abs().max()) <= 2e-5
+
+
+@pytest.mark.parametrize("h,w", [(8, 32767), (32767, 6)])
+def test_maximum_dimension(h, w):
+    """The largest extent the C ABI accepts (32767: cull boxes are stored as 15-bit) against the oracle,
+    and one more is refused."""
+    rng = np.random.default_rng(h)
+    n = 600
+    sig = np.stack([rng.uniform(2e-4, 2e-3, n), rng.uniform(2e-4, 2e-3, n), np.tanh(rng.normal(0, 1, n)) * 0.99], 1)
+    if h > w:
+        sig = sig[:, [1, 0, 2]]
+    sig[:, 0 if h > w else 1] *= 200.0  # a few pixels wide along the short axis too
+    xy = rng.uniform(-1.0, 1.0, (n, 2))
+    col = rng.uniform(0, 1, (n, 3))
+    ref = oracle.forward(sig, xy, col, h, w, 0.01)
+    out = _render(sig, xy, col, h, w, 0.01).cpu().double().numpy()
+    assert np.abs(out - ref).max() <= FWD_TOL
+    g = rng.uniform(-1, 1, (h, w, 3)).astype(np.float32)
+    _assert_grads(_backward(sig, xy, col, g, 0.01), oracle.backward(sig, xy, col, g, 0.01))
+    L = _lib.load()
+    assert L.gsr_workspace_bytes(n, 32768, 8) == 0 and L.gsr_workspace_bytes(n, 8, 32768) == 0
+
+
+@pytest.mark.parametrize("ksigma", [None, float("inf")])
+def test_x8_head_field_takes_the_region_path(ksigma):
+    """A fea2gs-shaped field at x8 (sigma up to 6.7 px, 5 sigma = 33 px, ~23 regions per Gaussian): the CTA's
+    region rectangle exceeds the shared-memory budget of the set-up kernel (warp-ballot path) and the
+    buckets must still hold everything (no fallback), with oracle parity."""
+    p = fields.raw_field(48, 64, seed=4)
+    h, w = 48 * 4, 64 * 4   # 24x32 LR at x8 with 2x2 Gaussians per LR pixel
+    s, c, k = fields.map_field(p, h, w, 8.0)
+    ref = oracle.forward(s.numpy(), c.numpy(), k.numpy(), h, w, 0.3)
+    out = _render(s, c, k, h, w, 0.3, ksigma).cpu().double().numpy()
+    assert np.abs(out - ref).max() <= FWD_TOL
+    g = np.random.default_rng(0).uniform(-1, 1, (h, w, 3)).astype(np.float32)
+    _assert_grads(_backward(s, c, k, g, 0.3, ksigma), oracle.backward(s.numpy(), c.numpy(), k.numpy(), g, 0.3))
