@@ -284,8 +284,10 @@ GSR_HD bool gsr_band_xrange(const GsrEllipse& e, float ecut, int ya, int yb, int
 }
 
 GSR_HD uint32_t gsr_region_mask(const GsrRec& g, int bx0, int bx1, int by0, int by1, int tx0,
-                                int ty0, int h, int w, float ecut, int hf = 0, int row0 = 0) {
-  const GsrEllipse e = gsr_ellipse(g, h, w, hf, row0);
+                                int ty0, int h, int w, float ecut, int hf = 0, int row0 = 0, int bhs = 0) {
+  // uniform batch (bhs > 0): the Gaussian lives in the sample whose block of bhs rows holds its box
+  GsrEllipse e = gsr_ellipse(g, bhs > 0 ? bhs : h, w, hf, row0);
+  if (bhs > 0) e.cy += (float)((by0 / bhs) * bhs);
   uint32_t mask = 0;
   const int cx0 = bx0 > tx0 ? bx0 : tx0;
   const int cx1 = bx1 < tx0 + GSR_TILE_W - 1 ? bx1 : tx0 + GSR_TILE_W - 1;

@@ -142,6 +142,7 @@ struct GsrFwdArgs {
   const uint2* box_in;
   int ntx;
   int hf, row0;  // row-band view (see gsr_setup)
+  int bhs;       // uniform batch: rows per sample of the stacked image (0: single image)
 };
 
 // Builds the table of candidate runs for a pixel rectangle [x0,x1]x[y0,y1] (inclusive):
@@ -332,7 +333,7 @@ __global__ void __launch_bounds__(GSR_FWD_THREADS, GSR_CFG_MIN_CTAS) gsr_forward
         g.c = q1.x; g.r = q1.y; g.g = q1.z; g.bl = q1.w;
         int bx0, bx1, by0, by1;
         gsr_box_unpack(sm.box[slot], bx0, bx1, by0, by1, binds);
-        m = gsr_region_mask(g, bx0, bx1, by0, by1, tx0, ty0, p.h, p.w, p.ecut, p.hf, p.row0);
+        m = gsr_region_mask(g, bx0, bx1, by0, by1, tx0, ty0, p.h, p.w, p.ecut, p.hf, p.row0, p.bhs);
       }
       // Append to this warp's private list of every region touched (no atomics: the ranks come
       // from ballots).  Window-binding Gaussians and entries that do not fit go to the CTA-wide

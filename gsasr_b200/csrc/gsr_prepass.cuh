@@ -54,6 +54,7 @@ struct GsrWorkspace {
   float* py_tab;     // h
   size_t bytes;
   int hf, row0;      // row-band view: the image is rows [row0, row0 + h) of an hf-row image (hf = 0: whole)
+  int bn, bhs;       // uniform batch: the image is a stack of samples, bhs rows each, bn Gaussians each (0: single)
 };
 
 constexpr int GSR_SCAN_CHUNK = 4096;  // counters per scan CTA (1024 threads x 4)
@@ -101,6 +102,8 @@ static inline GsrWorkspace gsr_carve(void* base, int s, int h, int w) {
   ws.bytes = off;
   ws.hf = 0;
   ws.row0 = 0;
+  ws.bn = 0;
+  ws.bhs = 0;
   return ws;
 }
 
@@ -121,10 +124,16 @@ __device__ __forceinline__ void gsr_bin_one(const float* __restrict__ sigmas,
   const float cr = __ldg(colors + 3 * (size_t)i + 0);
   const float cg = __ldg(colors + 3 * (size_t)i + 1);
   const float cb = __ldg(colors + 3 * (size_t)i + 2);
-  GsrSetup st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, h, w, dmax, ksigma, ws.px_tab, ws.py_tab, ws.hf, ws.row0);
+  // uniform batch: set up in the sample's own image, then move to its block of rows of the stack
+  const int yoff = ws.bn > 0 ? (i / ws.bn) * ws.bhs : 0;
+  GsrSetup st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, ws.bn > 0 ? ws.bhs : h, w, dmax, ksigma, ws.px_tab,
+                          ws.py_tab, ws.hf, ws.row0);
   if (st.live) {
     const GsrRec r = gsr_make_rec(sx, sy, rho, x, y, cr, cg, cb);
     if (!(gsr_finite(r.a) && gsr_finite(r.b) && gsr_finite(r.c))) st.live = false;
+    st.y0 += yoff;
+    st.y1 += yoff;
+    st.bin_y += yoff / GSR_BIN;
   }
   int key = -1, rank = 0;
   if (st.live) {
@@ -157,10 +166,10 @@ gsr_bin_kernel(const float* __restrict__ sigmas, const float* __restrict__ coord
 // Pixel coordinate tables: the reference's rule (gs.cu:39,46), evaluated once per axis entry.
 __global__ void __launch_bounds__(256) gsr_table_kernel(float* __restrict__ px_tab,
                                                         float* __restrict__ py_tab, int h, int w,
-                                                        int hf, int row0) {
+                                                        int hf, int row0, int bhs) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < w) px_tab[i] = gsr_pix_coord(i, w);
-  if (i < h) py_tab[i] = hf > 0 ? gsr_pix_coord(i + row0, hf) : gsr_pix_coord(i, h);
+  if (i < h) py_tab[i] = bhs > 0 ? gsr_pix_coord(i % bhs, bhs) : hf > 0 ? gsr_pix_coord(i + row0, hf) : gsr_pix_coord(i, h);
 }
 
 // Exclusive scan of n = nb + 1 counters into n + 1 offsets.  One CTA of 1024 threads per
@@ -321,7 +330,7 @@ __device__ __forceinline__ void gsr_warp_append(bool live, const GsrRec& r, uint
                                                 int x1, int y0, int y1, int h, int w, int nrx,
                                                 float ecut, int* __restrict__ cnt,
                                                 uint32_t* __restrict__ ent, int cap, int* overflow,
-                                                int hf = 0, int row0 = 0) {
+                                                int hf = 0, int row0 = 0, int yoff = 0) {
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int b0 = live ? y0 / GSR_REGION : 0x3fffffff, b1 = live ? y1 / GSR_REGION : -1;
@@ -330,7 +339,10 @@ __device__ __forceinline__ void gsr_warp_append(bool live, const GsrRec& r, uint
   const int uc0 = __reduce_min_sync(full, c0), uc1 = __reduce_max_sync(full, c1);
   if (ub1 < ub0 || uc1 < uc0) return;  // no live lane
   GsrEllipse e;
-  if (live) e = gsr_ellipse(r, h, w, hf, row0);
+  if (live) {
+    e = gsr_ellipse(r, h, w, hf, row0);
+    e.cy += (float)yoff;  // uniform batch: the sample's block of rows
+  }
   if ((long long)(ub1 - ub0 + 1) * (uc1 - uc0 + 1) > GSR_COOP_MAX_PAIRS) {
     if (live)
       for (int b = b0; b <= b1; ++b) {
@@ -440,6 +452,8 @@ gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restric
     const int i = chunk * GSR_RB_THREADS + tid;
     const float sx = pf[0], sy = pf[1], rho = pf[2], x = pf[3], y = pf[4], cr = pf[5], cg = pf[6], cb = pf[7];
     request(chunk + gridDim.x);
+    // uniform batch: set up in the sample's own hl-row image, then move to its block of rows of the stack
+    const int yoff = ws.bn > 0 ? (i / ws.bn) * ws.bhs : 0, hl = ws.bn > 0 ? ws.bhs : h;
     GsrSetup st;
     st.live = false;
     st.binds = false;
@@ -448,10 +462,12 @@ gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restric
     GsrRec r;
     r.x = r.y = r.a = r.b = r.c = r.r = r.g = r.bl = 0.f;
     if (i < s) {
-      st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, h, w, dmax, ksigma, ws.px_tab, ws.py_tab, ws.hf, ws.row0);
+      st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, hl, w, dmax, ksigma, ws.px_tab, ws.py_tab, ws.hf, ws.row0);
       if (st.live) {
         r = gsr_make_rec(sx, sy, rho, x, y, cr, cg, cb);
         if (!(gsr_finite(r.a) && gsr_finite(r.b) && gsr_finite(r.c))) st.live = false;
+        st.y0 += yoff;
+        st.y1 += yoff;
       }
       if (st.live) {
         float4* dr = reinterpret_cast<float4*>(ws.rec_in + i);
@@ -488,12 +504,13 @@ gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restric
     const bool any_live = B1 >= B0 && C1 >= C0;  // CTA-uniform
     const int NC = C1 - C0 + 1, NR = any_live ? NC * (B1 - B0 + 1) : 0;
     if (any_live && (long long)NC * (B1 - B0 + 1) > GSR_RB_MAXR) {
-      gsr_warp_append(st.live, r, entry, st.x0, st.x1, st.y0, st.y1, h, w, ws.nrx, ecut, ws.reg_count, ws.entries,
-                      ws.reg_cap, overflow, ws.hf, ws.row0);
+      gsr_warp_append(st.live, r, entry, st.x0, st.x1, st.y0, st.y1, hl, w, ws.nrx, ecut, ws.reg_count, ws.entries,
+                      ws.reg_cap, overflow, ws.hf, ws.row0, yoff);
     } else if (any_live) {
       // ---- collect: one shared-memory atomic per (Gaussian, region)
       if (st.live) {
-        const GsrEllipse e = gsr_ellipse(r, h, w, ws.hf, ws.row0);
+        GsrEllipse e = gsr_ellipse(r, hl, w, ws.hf, ws.row0);
+        e.cy += (float)yoff;
         for (int b = b0; b <= b1; ++b) {
           int ya = b * GSR_REGION, yb = ya + GSR_REGION - 1, xl, xh;
           ya = ya > st.y0 ? ya : st.y0;

@@ -72,7 +72,7 @@ static int gsr_resident_grid(K kernel, int threads, int slot, int* out) {
 static int gsr_clear_and_tables(int h, int w, const GsrWorkspace& ws, cudaStream_t st) {
   GSR_CUDA(cudaMemsetAsync(ws.bin_count, 0, ws.zero_bytes, st));
   const int n = w > h ? w : h;
-  gsr_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws.px_tab, ws.py_tab, h, w, ws.hf, ws.row0);
+  gsr_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws.px_tab, ws.py_tab, h, w, ws.hf, ws.row0, ws.bhs);
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
 }
@@ -139,6 +139,7 @@ static GsrFwdArgs gsr_fwd_args(const GsrWorkspace& ws, float* img, int h, int w,
   a.ntx = ws.ntx;
   a.hf = ws.hf;
   a.row0 = ws.row0;
+  a.bhs = ws.bn > 0 ? ws.bhs : 0;
   return a;
 }
 
@@ -228,13 +229,16 @@ static bool gsr_band_ok(int h, int hf, int row0) {
 
 static int gsr_forward_impl(const float* sigmas, const float* coords, const float* colors, float* img,
                             int s, int h, int w, int c, int hf, int row0, float dmax, float ksigma,
-                            uint32_t flags, void* workspace, size_t workspace_bytes, void* stream) {
+                            uint32_t flags, void* workspace, size_t workspace_bytes, void* stream,
+                            int bn = 0, int bhs = 0) {
   if (c != 3) return GSR_ERR_BAD_CHANNELS;
   if (!gsr_dims_ok(s, h, w) || !gsr_band_ok(h, hf, row0)) return GSR_ERR_BAD_SHAPE;
   if (!img || (s > 0 && (!sigmas || !coords || !colors))) return GSR_ERR_NULL_POINTER;
   GsrWorkspace ws = gsr_carve(workspace, s, h, w);
   ws.hf = hf;
   ws.row0 = row0;
+  ws.bn = bn;
+  ws.bhs = bhs;
   int rc = gsr_check_ws(workspace, workspace_bytes, ws.bytes);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -250,7 +254,7 @@ static int gsr_backward_impl(const float* sigmas, const float* coords, const flo
                              const float* grads, float* grads_sigmas, float* grads_coords,
                              float* grads_colors, int s, int h, int w, int c, int hf, int row0,
                              float dmax, float ksigma, uint32_t flags, void* workspace,
-                             size_t workspace_bytes, void* stream) {
+                             size_t workspace_bytes, void* stream, int bn = 0, int bhs = 0) {
   if (c != 3) return GSR_ERR_BAD_CHANNELS;
   if (!gsr_dims_ok(s, h, w) || !gsr_band_ok(h, hf, row0)) return GSR_ERR_BAD_SHAPE;
   if (!grads || (s > 0 && (!sigmas || !coords || !colors || !grads_sigmas || !grads_coords ||
@@ -259,6 +263,8 @@ static int gsr_backward_impl(const float* sigmas, const float* coords, const flo
   GsrWorkspace ws = gsr_carve(workspace, s, h, w);
   ws.hf = hf;
   ws.row0 = row0;
+  ws.bn = bn;
+  ws.bhs = bhs;
   int rc = gsr_check_ws(workspace, workspace_bytes, ws.bytes);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -305,6 +311,72 @@ extern "C" int gsr_backward_band(const float* sigmas, const float* coords, const
   if (h < 2 || h > GSR_MAX_DIM) return GSR_ERR_BAD_SHAPE;
   return gsr_backward_impl(sigmas, coords, colors, grads_band, grads_sigmas, grads_coords, grads_colors, s,
                            rows, w, c, h, row0, dmax, ksigma, flags, workspace, workspace_bytes, stream);
+}
+
+// ---- uniform batches: B samples of the same shape rendered as ONE stacked image ------------------
+// Samples whose height is a multiple of the region height (8) are stacked into one (B*h, w) image --
+// every Gaussian is set up in its own sample's coordinates and moved to the sample's block of rows --
+// so a whole training batch takes one set-up and one raster launch (and one backward launch) instead
+// of B of each.  Stacks are cut to GSR_MAX_DIM rows; other shapes (and the CHW layout, whose batch
+// stride differs) take one call per sample.
+static int gsr_batch_group(int batch, int h, uint32_t flags) {
+  if (h % GSR_REGION != 0 || (flags & GSR_FLAG_CHW)) return 1;
+  int g = GSR_MAX_DIM / h;  // samples that fit one stack ...
+  if (g < 1 || batch < 1) return 1;
+  const int launches = (batch + g - 1) / g;
+  g = (batch + launches - 1) / launches;  // ... dealt evenly over the launches (32 x 1024 rows: 16 + 16)
+  return g;
+}
+
+extern "C" size_t gsr_workspace_bytes_batch_uniform(int batch, int s_per, int h, int w) {
+  if (batch < 0 || !gsr_dims_ok(s_per, h, w)) return 0;
+  if (batch == 0) return 256;
+  const int g = gsr_batch_group(batch, h, 0);
+  if ((long long)g * s_per > 0x7fffffffLL) return 0;
+  const size_t a = gsr_workspace_bytes(g * s_per, g * h, w), b = gsr_workspace_bytes(s_per, h, w);
+  return a > b ? a : b;
+}
+
+extern "C" int gsr_forward_batch_uniform(const float* sigmas, const float* coords, const float* colors,
+                                         float* imgs, int batch, int s_per, int h, int w, int c,
+                                         float dmax, float ksigma, uint32_t flags, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  if (batch < 0) return GSR_ERR_BAD_ARGUMENT;
+  if (!gsr_dims_ok(s_per, h, w)) return GSR_ERR_BAD_SHAPE;
+  const int g = gsr_batch_group(batch, h, flags);
+  for (int b0 = 0; b0 < batch; b0 += g) {
+    const int nb = batch - b0 < g ? batch - b0 : g;
+    const size_t go = (size_t)b0 * s_per;
+    const int rc = gsr_forward_impl(sigmas ? sigmas + 3 * go : nullptr, coords ? coords + 2 * go : nullptr,
+                                    colors ? colors + 3 * go : nullptr, imgs + (size_t)b0 * h * w * 3, nb * s_per,
+                                    nb * h, w, c, 0, 0, dmax, ksigma, flags, workspace, workspace_bytes, stream,
+                                    nb > 1 ? s_per : 0, nb > 1 ? h : 0);
+    if (rc) return rc;
+  }
+  return GSR_OK;
+}
+
+extern "C" int gsr_backward_batch_uniform(const float* sigmas, const float* coords, const float* colors,
+                                          const float* grads, float* grads_sigmas, float* grads_coords,
+                                          float* grads_colors, int batch, int s_per, int h, int w, int c,
+                                          float dmax, float ksigma, uint32_t flags, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+  if (batch < 0) return GSR_ERR_BAD_ARGUMENT;
+  if (!gsr_dims_ok(s_per, h, w)) return GSR_ERR_BAD_SHAPE;
+  const int g = gsr_batch_group(batch, h, flags);
+  for (int b0 = 0; b0 < batch; b0 += g) {
+    const int nb = batch - b0 < g ? batch - b0 : g;
+    const size_t go = (size_t)b0 * s_per;
+    const int rc = gsr_backward_impl(sigmas ? sigmas + 3 * go : nullptr, coords ? coords + 2 * go : nullptr,
+                                     colors ? colors + 3 * go : nullptr, grads + (size_t)b0 * h * w * 3,
+                                     grads_sigmas ? grads_sigmas + 3 * go : nullptr,
+                                     grads_coords ? grads_coords + 2 * go : nullptr,
+                                     grads_colors ? grads_colors + 3 * go : nullptr, nb * s_per, nb * h, w, c, 0, 0,
+                                     dmax, ksigma, flags, workspace, workspace_bytes, stream, nb > 1 ? s_per : 0,
+                                     nb > 1 ? h : 0);
+    if (rc) return rc;
+  }
+  return GSR_OK;
 }
 
 // ---- split-phase form ---------------------------------------------------------------------------
@@ -444,6 +516,54 @@ extern "C" int gsr_frontend_backward(const float* raw, const float* mapped, cons
   if (rc) return rc;
   gsr_unmap_kernel<<<(s + 255) / 256, 256, 0, st>>>(raw, gm, gm + 3 * (size_t)s, gm + 5 * (size_t)s,
                                                     grad_raw, s, h, w, step_size);
+  GSR_CUDA(cudaGetLastError());
+  return GSR_OK;
+}
+
+// Fused front end for a uniform batch: raw (batch*s_per,9) -> imgs (batch,h,w,3) (HWC per sample).
+extern "C" int gsr_frontend_forward_batch_uniform(const float* raw, float* mapped, float* imgs, int batch,
+                                                  int s_per, int h, int w, float step_size, float dmax,
+                                                  float ksigma, void* workspace, size_t workspace_bytes,
+                                                  void* stream) {
+  if (batch < 0) return GSR_ERR_BAD_ARGUMENT;
+  if (!gsr_dims_ok(s_per, h, w) || (long long)batch * s_per > 0x7fffffffLL) return GSR_ERR_BAD_SHAPE;
+  const int s = batch * s_per;
+  if (!imgs || (s > 0 && (!raw || !mapped))) return GSR_ERR_NULL_POINTER;
+  if (!(step_size > 0.0f)) return GSR_ERR_BAD_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s > 0) {
+    gsr_map_kernel<<<(s + 255) / 256, 256, 0, st>>>(raw, mapped, mapped + 3 * (size_t)s,
+                                                    mapped + 5 * (size_t)s, s, h, w, step_size);
+    GSR_CUDA(cudaGetLastError());
+  }
+  return gsr_forward_batch_uniform(mapped, mapped + 3 * (size_t)s, mapped + 5 * (size_t)s, imgs, batch, s_per, h,
+                                   w, 3, dmax, ksigma, GSR_FLAG_OVERWRITE, workspace, workspace_bytes, stream);
+}
+
+// grads (batch,h,w,3) -> grad_raw (batch*s_per,9), written.  Workspace: gsr_workspace_bytes_batch_uniform
+// + 32 bytes per Gaussian (rounded up to 256) for the mapped-parameter gradients.
+extern "C" int gsr_frontend_backward_batch_uniform(const float* raw, const float* mapped, const float* grads,
+                                                   float* grad_raw, int batch, int s_per, int h, int w,
+                                                   float step_size, float dmax, float ksigma,
+                                                   void* workspace, size_t workspace_bytes, void* stream) {
+  if (batch < 0) return GSR_ERR_BAD_ARGUMENT;
+  if (!gsr_dims_ok(s_per, h, w) || (long long)batch * s_per > 0x7fffffffLL) return GSR_ERR_BAD_SHAPE;
+  const int s = batch * s_per;
+  if (!grads || (s > 0 && (!raw || !mapped || !grad_raw))) return GSR_ERR_NULL_POINTER;
+  if (!(step_size > 0.0f)) return GSR_ERR_BAD_ARGUMENT;
+  if (s == 0) return GSR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t need = gsr_workspace_bytes_batch_uniform(batch, s_per, h, w);
+  const size_t stage = gsr_align_up((size_t)s * 8 * sizeof(float), 256);
+  if (!workspace || ((uintptr_t)workspace & 255u) || workspace_bytes < need + stage) return GSR_ERR_WORKSPACE;
+  float* gm = (float*)((char*)workspace + need);
+  GSR_CUDA(cudaMemsetAsync(gm, 0, (size_t)s * 8 * sizeof(float), st));
+  int rc = gsr_backward_batch_uniform(mapped, mapped + 3 * (size_t)s, mapped + 5 * (size_t)s, grads, gm,
+                                      gm + 3 * (size_t)s, gm + 5 * (size_t)s, batch, s_per, h, w, 3, dmax, ksigma,
+                                      0, workspace, need, stream);
+  if (rc) return rc;
+  gsr_unmap_kernel<<<(s + 255) / 256, 256, 0, st>>>(raw, gm, gm + 3 * (size_t)s, gm + 5 * (size_t)s, grad_raw, s,
+                                                    h, w, step_size);
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
 }

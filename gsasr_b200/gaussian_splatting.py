@@ -27,6 +27,7 @@ from . import gscuda as _gs
 
 __all__ = [
     "generate_2D_gaussian_splatting_step", "generate_2D_gaussian_splatting_step_buffer",
+    "generate_2D_gaussian_splatting_step_batch",
     "rendering_cuda", "rendering_cuda_buffer", "rendering_cuda_dmax", "rendering_cuda_dmax_buffer",
     "map_gaussians", "render_chw",
 ]
@@ -240,3 +241,74 @@ def generate_2D_gaussian_splatting_step_buffer(sr_size, gs_parameters, scale, sc
         final_image = rendering_cuda_buffer(sigma_x, sigma_y, rho, coords, colours_with_alpha, sr_size,
                                             step_size, device=sigma_x.device, buffer_size=buffer_size)
     return _sample(final_image, sample_coords)
+
+
+class _FusedFrontendBatch(Function):
+    """raw (B,N,9) -> (B,H,W,3) through gsr_frontend_forward_batch_uniform / _backward_batch_uniform."""
+
+    @staticmethod
+    def forward(ctx, raw, h, w, step_size, dmax):
+        L = _lib.load()
+        raw = raw.contiguous().float()
+        b, n = raw.shape[:2]
+        mapped = torch.empty(max(b * n, 1) * 8, device=raw.device, dtype=torch.float32)
+        out = torch.empty(b, h, w, 3, device=raw.device, dtype=torch.float32)
+        with torch.cuda.device(raw.device):
+            ws = _gs.workspace_batch(b, n, h, w, raw.device)
+            rc = L.gsr_frontend_forward_batch_uniform(raw.data_ptr(), mapped.data_ptr(), out.data_ptr(), b, n, h, w,
+                                                      float(step_size), float(dmax), float(_gs.get_ksigma()),
+                                                      ws.data_ptr(), ws.numel(),
+                                                      torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc)
+        ctx.save_for_backward(raw, mapped)
+        ctx.meta = (h, w, float(step_size), float(dmax))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad):
+        L = _lib.load()
+        raw, mapped = ctx.saved_tensors
+        h, w, step_size, dmax = ctx.meta
+        b, n = raw.shape[:2]
+        grad = grad.contiguous()
+        g_raw = torch.zeros_like(raw)
+        if b * n:
+            with torch.cuda.device(raw.device):
+                need = L.gsr_workspace_bytes_batch_uniform(b, n, h, w) + (b * n * 32 + 255) // 256 * 256
+                ws = torch.empty(need, dtype=torch.uint8, device=raw.device)
+                rc = L.gsr_frontend_backward_batch_uniform(raw.data_ptr(), mapped.data_ptr(), grad.data_ptr(),
+                                                           g_raw.data_ptr(), b, n, h, w, step_size, dmax,
+                                                           float(_gs.get_ksigma()), ws.data_ptr(), ws.numel(),
+                                                           torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc)
+        return g_raw, None, None, None, None
+
+
+def generate_2D_gaussian_splatting_step_batch(sr_size, gs_parameters, scale, scale_modify,
+                                              default_step_size=1.2, mode='scale_modify', if_dmax=True,
+                                              dmax_mode='fix', dmax=25, fused=False):
+    """generate_2D_gaussian_splatting_step for a whole batch of one shape: gs_parameters (B,N,9) ->
+    (B,3,H,W), the training loop's per-sample calls (gsasr_model.py:191-233) in one set-up and one
+    raster launch each way (gsr_forward_batch_uniform).  Same activations and mapping expressions as the
+    per-sample function, applied to the flattened batch, so the tensors handed to the rasteriser are
+    bit-identical (``fused=True``: the library's fused front end instead, parity 1e-4).  The result is a
+    view of the (B,H,W,3) render: a (B,3,H,W) tensor in torch.channels_last memory format (no transpose
+    pass)."""
+    from .gswrapper import gaussiansplatting_render_batch
+
+    if gs_parameters.dim() != 3 or gs_parameters.shape[-1] != 9:
+        raise RuntimeError("gs_parameters must be (B,N,9)")
+    b, n = gs_parameters.shape[:2]
+    dm = _resolve_dmax(if_dmax, dmax_mode, dmax, sr_size)
+    if fused:
+        step_size = float(default_step_size / (scale if mode == 'scale' else scale_modify[0]))
+        out = _FusedFrontendBatch.apply(gs_parameters, int(sr_size[0]), int(sr_size[1]), step_size, dm)
+        return out.permute(0, 3, 1, 2)
+    step_size, sigma_x, sigma_y, rho, coords, colours_with_alpha = _prepare(
+        gs_parameters.reshape(b * n, 9), scale, scale_modify, default_step_size, mode)
+    sigmas, coords = map_gaussians(sigma_x, sigma_y, rho, coords, sr_size, step_size)
+    out = gaussiansplatting_render_batch(sigmas.view(b, n, 3), coords.view(b, n, 2),
+                                         colours_with_alpha.contiguous().view(b, n, 3),
+                                         (int(sr_size[0]), int(sr_size[1])), dm)
+    return out.permute(0, 3, 1, 2)

@@ -21,7 +21,8 @@ import torch
 
 from . import _lib
 
-__all__ = ["gs_render", "gs_render_backward", "gs_render_band", "gs_render_backward_band", "set_ksigma", "get_ksigma"]
+__all__ = ["gs_render", "gs_render_backward", "gs_render_band", "gs_render_backward_band", "gs_render_batch",
+           "gs_render_backward_batch", "set_ksigma", "get_ksigma"]
 
 _ksigma = float(os.environ.get("GSR_KSIGMA", "0"))  # 0 -> library default (GSR_DEFAULT_KSIGMA)
 
@@ -162,4 +163,62 @@ def gs_render_backward_band(sigmas, coords, colors, band_grads, grads_sigmas, gr
                                  _ptr(grads_sigmas), _ptr(grads_coords), _ptr(grads_colors), s, h, w, c,
                                  row0, rows, float(dmax), float(_ksigma if ksigma is None else ksigma),
                                  int(flags), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)
+
+
+# ---- uniform batches (no counterpart in the reference, which renders sample by sample,
+# gsasr_model.py:191-233): `batch` samples of the same shape in one set-up and one raster launch.
+# sigmas (B,N,3), coords (B,N,2), colors (B,N,3), imgs / grads (B,h,w,3), all contiguous.
+def workspace_batch(batch: int, s_per: int, h: int, w: int, device) -> torch.Tensor:
+    n = _lib.load().gsr_workspace_bytes_batch_uniform(int(batch), int(s_per), int(h), int(w))
+    if n == 0:
+        raise RuntimeError(f"libgsraster: bad sizes batch={batch}, s={s_per}, h={h}, w={w}")
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def gs_render_batch(sigmas, coords, colors, rendered_imgs, dmax=float("inf"), *, ksigma=None, flags=0,
+                    workspace_buf=None):
+    L = _lib.load()
+    for t, n in ((sigmas, "sigmas"), (coords, "coords"), (colors, "colors"), (rendered_imgs, "rendered_imgs")):
+        _check_input(t, n)
+    if sigmas.dim() != 3 or rendered_imgs.dim() != 4:
+        raise RuntimeError("gs_render_batch: sigmas must be (B,N,3) and rendered_imgs (B,h,w,3)")
+    b, s = int(sigmas.shape[0]), int(sigmas.shape[1])
+    h, w = int(rendered_imgs.shape[1]), int(rendered_imgs.shape[2])
+    _check_shape(sigmas, (b, s, 3), "sigmas")
+    _check_shape(coords, (b, s, 2), "coords")
+    _check_shape(colors, (b, s, 3), "colors")
+    _check_shape(rendered_imgs, (b, h, w, 3), "rendered_imgs")
+    with torch.cuda.device(sigmas.device):
+        ws = workspace_buf if workspace_buf is not None else workspace_batch(b, s, h, w, sigmas.device)
+        rc = L.gsr_forward_batch_uniform(_ptr(sigmas), _ptr(coords), _ptr(colors), rendered_imgs.data_ptr(), b, s,
+                                         h, w, 3, float(dmax), float(_ksigma if ksigma is None else ksigma),
+                                         int(flags), ws.data_ptr(), ws.numel(),
+                                         torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)
+
+
+def gs_render_backward_batch(sigmas, coords, colors, grads, grads_sigmas, grads_coords, grads_colors,
+                             dmax=float("inf"), *, ksigma=None, flags=0, workspace_buf=None):
+    L = _lib.load()
+    for t, n in ((sigmas, "sigmas"), (coords, "coords"), (colors, "colors"), (grads, "grads"),
+                 (grads_sigmas, "grads_sigmas"), (grads_coords, "grads_coords"),
+                 (grads_colors, "grads_colors")):
+        _check_input(t, n)
+    if sigmas.dim() != 3 or grads.dim() != 4:
+        raise RuntimeError("gs_render_backward_batch: sigmas must be (B,N,3) and grads (B,h,w,3)")
+    b, s = int(sigmas.shape[0]), int(sigmas.shape[1])
+    h, w = int(grads.shape[1]), int(grads.shape[2])
+    _check_shape(coords, (b, s, 2), "coords")
+    _check_shape(colors, (b, s, 3), "colors")
+    _check_shape(grads, (b, h, w, 3), "grads")
+    _check_shape(grads_sigmas, (b, s, 3), "grads_sigmas")
+    _check_shape(grads_coords, (b, s, 2), "grads_coords")
+    _check_shape(grads_colors, (b, s, 3), "grads_colors")
+    with torch.cuda.device(sigmas.device):
+        ws = workspace_buf if workspace_buf is not None else workspace_batch(b, s, h, w, sigmas.device)
+        rc = L.gsr_backward_batch_uniform(_ptr(sigmas), _ptr(coords), _ptr(colors), grads.data_ptr(),
+                                          _ptr(grads_sigmas), _ptr(grads_coords), _ptr(grads_colors), b, s, h, w,
+                                          3, float(dmax), float(_ksigma if ksigma is None else ksigma), int(flags),
+                                          ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)

@@ -48,3 +48,33 @@ def gaussiansplatting_render(sigmas, coords, colors, image_size, dmax=100):
     c = colors.shape[-1]
     rendered_img = torch.zeros(h, w, c, device=colors.device, dtype=torch.float32)
     return GSCUDA.apply(sigmas, coords, colors, rendered_img, dmax)
+
+
+# ---- uniform batches (no counterpart in the reference, whose training loop renders sample by sample,
+# gsasr_model.py:191-233): the same autograd boundary for B samples of one shape, one launch each way.
+class GSCUDABatch(Function):
+    @staticmethod
+    def forward(ctx, sigmas, coords, colors, rendered_imgs, dmax=float("inf")):
+        ctx.save_for_backward(sigmas, coords, colors)
+        ctx.dmax = dmax
+        GSWrapper.gs_render_batch(sigmas, coords, colors, rendered_imgs, dmax)
+        return rendered_imgs
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        sigmas, coords, colors = ctx.saved_tensors
+        grads_sigmas = torch.zeros_like(sigmas)
+        grads_coords = torch.zeros_like(coords)
+        grads_colors = torch.zeros_like(colors)
+        GSWrapper.gs_render_backward_batch(sigmas, coords, colors, grad_output.contiguous(), grads_sigmas,
+                                           grads_coords, grads_colors, ctx.dmax)
+        return (grads_sigmas, grads_coords, grads_colors, None, None)
+
+
+def gaussiansplatting_render_batch(sigmas, coords, colors, image_size, dmax=100):
+    """(B,N,3), (B,N,2), (B,N,3) -> (B,h,w,3): gaussiansplatting_render for every sample of a batch."""
+    sigmas, coords, colors = sigmas.contiguous(), coords.contiguous(), colors.contiguous()
+    h, w = image_size[:2]
+    rendered = torch.zeros(sigmas.shape[0], h, w, 3, device=colors.device, dtype=torch.float32)
+    return GSCUDABatch.apply(sigmas, coords, colors, rendered, dmax)

@@ -143,6 +143,23 @@ int gsr_forward_batch(const gsr_sample* samples_host, int n, float ksigma, uint3
 int gsr_backward_batch(const gsr_sample* samples_host, int n, float ksigma, uint32_t flags,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Uniform batch: `batch` samples of the same shape, s_per Gaussians each, contiguous:
+ * sigmas (batch*s_per,3), coords (batch*s_per,2), colors (batch*s_per,3), imgs / grads (batch,h,w,3).
+ * The training loop's per-sample render (gsasr_model.py:191-233) for a batch whose samples share
+ * (h, w, dmax) in ONE set-up and ONE raster launch: when h is a multiple of 8 the samples are stacked
+ * into a (batch*h, w) image (cut to 32767 rows per launch); otherwise, and with GSR_FLAG_CHW, one
+ * call per sample.  Results equal `batch` calls of gsr_forward / gsr_backward (up to summation order).
+ * Workspace: gsr_workspace_bytes_batch_uniform(batch, s_per, h, w). */
+size_t gsr_workspace_bytes_batch_uniform(int batch, int s_per, int h, int w);
+int gsr_forward_batch_uniform(const float* sigmas, const float* coords, const float* colors, float* imgs,
+                              int batch, int s_per, int h, int w, int c, float dmax, float ksigma,
+                              uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
+int gsr_backward_batch_uniform(const float* sigmas, const float* coords, const float* colors,
+                               const float* grads, float* grads_sigmas, float* grads_coords,
+                               float* grads_colors, int batch, int s_per, int h, int w, int c, float dmax,
+                               float ksigma, uint32_t flags, void* workspace, size_t workspace_bytes,
+                               void* stream);
+
 /* Fused front end: raw head output (s,9) = (sx, sy, rho, alpha, r, g, b, mu_x, mu_y) ->
  * activations (gaussian_splatting.py:174-180) -> unit/coordinate mapping (:121-123) ->
  * render -> (3,h,w) image, written (not accumulated).  step_size = default_step_size / scale.
@@ -155,6 +172,18 @@ int gsr_frontend_forward(const float* raw_params, float* mapped, float* img_chw,
 int gsr_frontend_backward(const float* raw_params, const float* mapped, const float* grads_chw,
                           float* grad_raw, int s, int h, int w, float step_size, float dmax,
                           float ksigma, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The fused front end for a uniform batch: raw (batch*s_per,9) -> imgs (batch,h,w,3) (HWC per sample,
+ * i.e. a (batch,3,h,w) tensor in channels-last layout), and its backward from grads (batch,h,w,3).
+ * mapped: batch*s_per*8 floats.  Backward workspace: gsr_workspace_bytes_batch_uniform + 32 bytes per
+ * Gaussian rounded up to 256. */
+int gsr_frontend_forward_batch_uniform(const float* raw_params, float* mapped, float* imgs, int batch,
+                                       int s_per, int h, int w, float step_size, float dmax, float ksigma,
+                                       void* workspace, size_t workspace_bytes, void* stream);
+int gsr_frontend_backward_batch_uniform(const float* raw_params, const float* mapped, const float* grads,
+                                        float* grad_raw, int batch, int s_per, int h, int w,
+                                        float step_size, float dmax, float ksigma, void* workspace,
+                                        size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,101 @@
+"""Uniform batches (gsr_forward_batch_uniform / gsr_backward_batch_uniform): B samples of one shape rendered
+as one stacked image must equal B single-sample calls.  Needs a GPU: `-m gpu`."""
+import numpy as np
+import pytest
+import torch
+
+from gsasr_b200 import _lib, fields, gscuda
+from gsasr_b200.gswrapper import gaussiansplatting_render, gaussiansplatting_render_batch
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _batch(b, gh, gw, h, w, scale):
+    ss, cc, kk = [], [], []
+    for i in range(b):
+        s, c, k = fields.map_field(fields.raw_field(gh, gw, seed=10 + i), h, w, scale)
+        ss.append(s); cc.append(c); kk.append(k)
+    return tuple(torch.stack(t).to(DEV).contiguous() for t in (ss, cc, kk))
+
+
+@pytest.mark.parametrize("b,h,w,scale,dmax", [
+    (4, 64, 48, 2.0, 0.1),     # stacked: 4 x 64 rows
+    (3, 40, 72, 4.0, 0.05),    # stacked, windows bind, samples differ
+    (5, 36, 40, 2.0, 0.3),     # h % 8 != 0: one call per sample
+    (1, 32, 32, 2.0, 0.1),
+])
+def test_batch_equals_single_sample_calls(b, h, w, scale, dmax):
+    s, c, k = _batch(b, 24, 28, h, w, scale)
+    n = s.shape[1]
+    imgs = torch.zeros(b, h, w, 3, device=DEV)
+    gscuda.gs_render_batch(s, c, k, imgs, dmax)
+    g = torch.rand(b, h, w, 3, device=DEV, generator=torch.Generator(DEV).manual_seed(1))
+    gs, gc, gk = torch.zeros_like(s), torch.zeros_like(c), torch.zeros_like(k)
+    gscuda.gs_render_backward_batch(s, c, k, g, gs, gc, gk, dmax)
+    for i in range(b):
+        one = torch.zeros(h, w, 3, device=DEV)
+        gscuda.gs_render(s[i], c[i], k[i], one, n, h, w, 3, dmax)
+        assert float((imgs[i] - one).abs().max()) <= 2e-6
+        ref = oracle.forward(s[i].cpu().numpy(), c[i].cpu().numpy(), k[i].cpu().numpy(), h, w, dmax)
+        assert np.abs(imgs[i].cpu().double().numpy() - ref).max() <= 1e-4
+        ws = [torch.zeros_like(t[i]) for t in (s, c, k)]
+        gscuda.gs_render_backward(s[i], c[i], k[i], g[i].contiguous(), *ws, n, h, w, 3, dmax)
+        for a, w_ in zip((gs[i], gc[i], gk[i]), ws):
+            assert float((a - w_).abs().max()) <= 1e-5 * float(w_.abs().max())
+
+
+def test_batch_stack_is_cut_at_the_maximum_image_height():
+    """h = 4096: at most 7 samples fit a 32767-row stack, so 9 samples take two launches (5 + 4)."""
+    L = _lib.load()
+    b, h, w, n = 9, 4096, 16, 50
+    rng = np.random.default_rng(0)
+    s = torch.tensor(np.stack([rng.uniform(0.05, 0.2, (b, n)), rng.uniform(2e-4, 2e-3, (b, n)),
+                               np.zeros((b, n))], 2), dtype=torch.float32, device=DEV)
+    c = torch.tensor(rng.uniform(-1, 1, (b, n, 2)), dtype=torch.float32, device=DEV)
+    k = torch.tensor(rng.uniform(0, 1, (b, n, 3)), dtype=torch.float32, device=DEV)
+    imgs = torch.zeros(b, h, w, 3, device=DEV)
+    gscuda.gs_render_batch(s, c, k, imgs, 0.5)
+    for i in (0, 6, 7, 8):
+        one = torch.zeros(h, w, 3, device=DEV)
+        gscuda.gs_render(s[i], c[i], k[i], one, n, h, w, 3, 0.5)
+        assert float((imgs[i] - one).abs().max()) <= 2e-6
+    assert L.gsr_workspace_bytes_batch_uniform(9, n, 4096, 16) >= L.gsr_workspace_bytes(5 * n, 5 * 4096, 16)
+
+
+def test_batch_autograd_matches_per_sample_autograd():
+    b, h, w = 3, 48, 56
+    s, c, k = _batch(b, 20, 24, h, w, 2.0)
+    leaves = [t.clone().requires_grad_(True) for t in (s, c, k)]
+    out = gaussiansplatting_render_batch(*leaves, (h, w), 0.2)
+    wgt = torch.rand(b, h, w, 3, device=DEV, generator=torch.Generator(DEV).manual_seed(3))
+    (out * wgt).sum().backward()
+    for i in range(b):
+        li = [t[i].clone().requires_grad_(True) for t in (s, c, k)]
+        oi = gaussiansplatting_render(*li, (h, w), 0.2)
+        (oi * wgt[i]).sum().backward()
+        assert float((out[i] - oi).abs().max()) <= 2e-6
+        for a, bb in zip(leaves, li):
+            assert float((a.grad[i] - bb.grad).abs().max()) <= 1e-5 * float(bb.grad.abs().max())
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_batched_front_end_matches_per_sample_front_end(fused):
+    from gsasr_b200 import gaussian_splatting as gsp
+
+    b, h, w, scale = 3, 64, 64, 4.0
+    raw = torch.stack([fields.raw_field(16, 16, seed=20 + i) for i in range(b)]).to(DEV)
+    wgt = torch.rand(b, 3, h, w, device=DEV, generator=torch.Generator(DEV).manual_seed(5))
+    pb = raw.clone().requires_grad_(True)
+    out = gsp.generate_2D_gaussian_splatting_step_batch(torch.tensor([h, w]), pb, scale, torch.tensor([scale] * 2),
+                                                        dmax=0.1, fused=fused)
+    assert tuple(out.shape) == (b, 3, h, w)
+    (out * wgt).sum().backward()
+    for i in range(b):
+        pi = raw[i].clone().requires_grad_(True)
+        oi = gsp.generate_2D_gaussian_splatting_step(torch.tensor([h, w]), pi, scale, torch.tensor([scale] * 2),
+                                                     dmax=0.1, fused=fused)
+        (oi * wgt[i]).sum().backward()
+        assert float((out[i].detach() - oi.detach()).abs().max()) <= 2e-6
+        assert float((pb.grad[i] - pi.grad).abs().max()) <= 1e-5 * float(pi.grad.abs().max())

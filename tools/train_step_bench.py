@@ -53,6 +53,25 @@ for dmax in (0.5, 0.1):
         if world > 1:
             t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t)
         out[f"dmax{dmax}_{'fused' if fused else 'torchops'}_ms_per_step"] = round(ms, 3)
+    # the whole share as ONE uniform batch: one set-up + one raster launch each way (ground truth kept
+    # channels-last like the render, so the loss needs no transpose)
+    rawb, gtb = torch.stack(raws), torch.stack(gts).contiguous(memory_format=torch.channels_last)
+    for fused in (False, True):
+        def step_batch():
+            p = rawb.clone().requires_grad_(True)
+            img = gsp.generate_2D_gaussian_splatting_step_batch(torch.tensor([h, w]), p, cfg.scale, torch.tensor([cfg.scale] * 2), dmax=dmax, fused=fused)
+            ((img - gtb).abs().mean(dim=(1, 2, 3))).sum().backward()
+        for _ in range(3): step_batch()
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps): step_batch()
+        b.record(); torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / args.steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t)
+        out[f"dmax{dmax}_batch_{'fused' if fused else 'torchops'}_ms_per_step"] = round(ms, 3)
 if rank == 0:
     print(json.dumps({"config": "C5-shaped: batch %d x (256x256 LR -> x4, 262144 Gaussians), fwd+bwd render + L1" % args.batch,
                       "samples_per_gpu": hi - lo, "world": eff_world, **out}))
