@@ -24,7 +24,7 @@ else:
     from gsasr_b200 import fields, gscuda, _lib
     L = _lib.load(); dev = torch.device("cuda:0")
     res = {}
-    for cfg in ("HL", "C2d"):
+    for cfg in ("HL", "C2d", "C3", "C2"):
         _, s, c, k, h, w = fields.make(cfg)
         sd, cd, kd = s.to(dev), c.to(dev), k.to(dev); n = s.shape[0]
         img = torch.zeros(h, w, 3, device=dev); ws = gscuda.workspace(n, h, w, dev)
