@@ -30,6 +30,16 @@ class GsrSample(ctypes.Structure):
     ]
 
 
+GSR_MAX_CLIP = 8
+
+
+class GsrWindow(ctypes.Structure):
+    """struct gsr_window (include/gsraster.h)."""
+
+    _fields_ = [("row_stride", ctypes.c_longlong), ("pix_stride", ctypes.c_longlong),
+                ("chan_stride", ctypes.c_longlong), ("nclip", _i), ("clip", (_i * 4) * GSR_MAX_CLIP)]
+
+
 # name -> (restype, argtypes): every symbol include/gsraster.h declares
 SIGNATURES = {
     "gsr_version": (_i, []),
@@ -40,6 +50,8 @@ SIGNATURES = {
     "gsr_backward": (_i, [_vp] * 7 + [_i, _i, _i, _i, _f, _f, _u32, _vp, _sz, _vp]),
     "gsr_forward_band": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, _u32, _vp, _sz, _vp]),
     "gsr_backward_band": (_i, [_vp] * 7 + [_i, _i, _i, _i, _i, _i, _f, _f, _u32, _vp, _sz, _vp]),
+    "gsr_forward_window": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(GsrWindow), _i, _i, _i, _i, _f, _f, _u32, _vp,
+                                _sz, _vp]),
     "gsr_prepare": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _sz, _vp]),
     "gsr_forward_prepared": (_i, [_vp, _i, _i, _i, _f, _u32, _vp, _sz, _vp]),
     "gsr_backward_prepared": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _u32, _vp, _sz, _vp]),

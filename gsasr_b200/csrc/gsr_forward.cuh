@@ -121,6 +121,10 @@ __device__ __forceinline__ void gsr_eval_pair(uint32_t addr, gsr_f2 px2, float p
   accb = gsr_fma2(v2, gsr_pk(a1.w, a1.w), accb);
 }
 
+#ifndef GSR_MAX_CLIP
+#define GSR_MAX_CLIP 8  // as in include/gsraster.h
+#endif
+
 struct GsrFwdArgs {
   const GsrRec* rec;
   const uint2* box;
@@ -143,7 +147,27 @@ struct GsrFwdArgs {
   int ntx;
   int hf, row0;  // row-band view (see gsr_setup)
   int bhs;       // uniform batch: rows per sample of the stacked image (0: single image)
+  // destination addressing, in floats: pixel (hi, wi), channel ch lives at
+  //   img + hi * row_stride + wi * pix_stride + ch * chan_stride
+  // (HWC: 3w, 3, 1; CHW: w, 1, h*w; a window of a larger canvas: the canvas' strides, img = the address of
+  // the render's pixel (0,0)).  nclip > 0: only pixels inside one of the clip rectangles are written.
+  long long row_stride, pix_stride, chan_stride;
+  int nclip;
+  int clip[GSR_MAX_CLIP][4];  // x0, y0, x1, y1 (inclusive), render coordinates
 };
+
+__device__ __forceinline__ bool gsr_fwd_writable(const GsrFwdArgs& p, int hi, int wi) {
+  if (hi >= p.h || wi >= p.w) return false;
+  if (p.nclip == 0) return true;
+  bool in = false;
+#pragma unroll
+  for (int k = 0; k < GSR_MAX_CLIP; ++k)
+    in = in || (k < p.nclip && wi >= p.clip[k][0] && hi >= p.clip[k][1] && wi <= p.clip[k][2] && hi <= p.clip[k][3]);
+  return in;
+}
+__device__ __forceinline__ float* gsr_fwd_pixel(const GsrFwdArgs& p, int hi, int wi) {
+  return p.img + (long long)hi * p.row_stride + (long long)wi * p.pix_stride;
+}
 
 // Builds the table of candidate runs for a pixel rectangle [x0,x1]x[y0,y1] (inclusive):
 // one run per bin row within reach + the large list.  Executed by warp 0.
@@ -191,53 +215,14 @@ __device__ __forceinline__ void gsr_build_runs(const int* __restrict__ bin_off,
 __device__ __forceinline__ void gsr_fwd_writeout(const GsrFwdArgs& p, int hi, int wi0, float r0,
                                                  float g0, float b0, float r1, float g1, float b1,
                                                  bool force_over = false) {
-  if (hi < p.h) {
-    const bool over = force_over || (p.flags & 1u) != 0;
-    if (p.flags & 2u) {  // CHW
-      const size_t plane = (size_t)p.h * p.w;
-      float* o = p.img + (size_t)hi * p.w + wi0;
-      if (wi0 < p.w) {
-        o[0] = over ? r0 : o[0] + r0;
-        o[plane] = over ? g0 : o[plane] + g0;
-        o[2 * plane] = over ? b0 : o[2 * plane] + b0;
-      }
-      if (wi0 + 1 < p.w) {
-        o[1] = over ? r1 : o[1] + r1;
-        o[plane + 1] = over ? g1 : o[plane + 1] + g1;
-        o[2 * plane + 1] = over ? b1 : o[2 * plane + 1] + b1;
-      }
-    } else {  // HWC: 6 contiguous floats per lane
-      float* o = p.img + ((size_t)hi * p.w + wi0) * 3;
-      if (wi0 < p.w) {
-        o[0] = over ? r0 : o[0] + r0;
-        o[1] = over ? g0 : o[1] + g0;
-        o[2] = over ? b0 : o[2] + b0;
-      }
-      if (wi0 + 1 < p.w) {
-        o[3] = over ? r1 : o[3] + r1;
-        o[4] = over ? g1 : o[4] + g1;
-        o[5] = over ? b1 : o[5] + b1;
-      }
-    }
-  }
-}
-
-// Accumulate mode (the reference's contract): the old pixel values are fetched at the START of the
-// kernel and seed the accumulators, so their latency hides behind the raster work and the final
-// write is a plain store.
-__device__ __forceinline__ void gsr_fwd_readold(const GsrFwdArgs& p, int hi, int wi0, float& r0,
-                                                float& g0, float& b0, float& r1, float& g1, float& b1) {
-  r0 = g0 = b0 = r1 = g1 = b1 = 0.f;
-  if ((p.flags & 1u) != 0 || hi >= p.h) return;
-  if (p.flags & 2u) {
-    const size_t plane = (size_t)p.h * p.w;
-    const float* o = p.img + (size_t)hi * p.w + wi0;
-    if (wi0 < p.w) { r0 = o[0]; g0 = o[plane]; b0 = o[2 * plane]; }
-    if (wi0 + 1 < p.w) { r1 = o[1]; g1 = o[plane + 1]; b1 = o[2 * plane + 1]; }
-  } else {
-    const float* o = p.img + ((size_t)hi * p.w + wi0) * 3;
-    if (wi0 < p.w) { r0 = o[0]; g0 = o[1]; b0 = o[2]; }
-    if (wi0 + 1 < p.w) { r1 = o[3]; g1 = o[4]; b1 = o[5]; }
+  const bool over = force_over || (p.flags & 1u) != 0;
+  const float v[2][3] = {{r0, g0, b0}, {r1, g1, b1}};
+#pragma unroll
+  for (int xx = 0; xx < 2; ++xx) {
+    if (!gsr_fwd_writable(p, hi, wi0 + xx)) continue;
+    float* o = gsr_fwd_pixel(p, hi, wi0 + xx);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) o[ch * p.chan_stride] = over ? v[xx][ch] : o[ch * p.chan_stride] + v[xx][ch];
   }
 }
 
@@ -513,7 +498,7 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
   const uint32_t rec_h = gsr_smem_addr(&sm.rec[warp][0][0]) + half * GSR_FR_HALF_BYTES;  // this half's slice, stage 0
   const uint32_t box_s = gsr_smem_addr(&sm.box[warp][0][0]);
   const uint2* box_w = &sm.box[warp][0][0];
-  const bool over = (p.flags & 1u) != 0, chw = (p.flags & 2u) != 0;
+  const bool over = (p.flags & 1u) != 0;
 
   // Region of this half in unit v (-1: past the end) and the (raw) length of its bucket.
   auto region_of = [&](int v) { const int y = v / npx; return v < nunits ? y * p.nrx + (v - y * npx) * 2 + half : -1; };
@@ -641,19 +626,17 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
       gsr_upk(r1, v[1][0][0], v[1][1][0]);
       gsr_upk(g1, v[1][0][1], v[1][1][1]);
       gsr_upk(b1, v[1][0][2], v[1][1][2]);
-      const size_t plane = (size_t)p.h * p.w;
 #pragma unroll
       for (int yy = 0; yy < 2; ++yy) {
 #pragma unroll
         for (int xx = 0; xx < 2; ++xx) {
           const int hi = hi0 + yy, wi = wi0 + xx;
-          if (hi < p.h && wi < p.w) {
-            const size_t pix = (size_t)hi * p.w + wi;
+          if (gsr_fwd_writable(p, hi, wi)) {
+            float* o = gsr_fwd_pixel(p, hi, wi);
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-              float* o = chw ? p.img + ch * plane + pix : p.img + pix * 3 + ch;
-              if (over) *o = v[yy][xx][ch];
-              else atomicAdd(o, v[yy][xx][ch]);
+              if (over) o[ch * p.chan_stride] = v[yy][xx][ch];
+              else atomicAdd(o + ch * p.chan_stride, v[yy][xx][ch]);
             }
           }
         }

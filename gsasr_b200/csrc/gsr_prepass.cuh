@@ -23,6 +23,7 @@
 // not taken return at once (`guard`).
 #pragma once
 #include "gsr_common.cuh"
+struct gsr_window;
 
 constexpr int GSR_STAT_EXT_X = 0, GSR_STAT_EXT_Y = 1, GSR_STAT_OVERFLOW = 2, GSR_STAT_ENTRIES = 3;
 // bucket capacity per region = 40 * N / regions + 32: a Gaussian of the x4 head touches 6.8 regions on
@@ -54,6 +55,7 @@ struct GsrWorkspace {
   float* py_tab;     // h
   size_t bytes;
   int hf, row0;      // row-band view: the image is rows [row0, row0 + h) of an hf-row image (hf = 0: whole)
+  const struct gsr_window* win;  // host-side only: destination window of gsr_forward_window (NULL: plain image)
   int bn, bhs;       // uniform batch: the image is a stack of samples, bhs rows each, bn Gaussians each (0: single)
 };
 
@@ -104,6 +106,7 @@ static inline GsrWorkspace gsr_carve(void* base, int s, int h, int w) {
   ws.row0 = 0;
   ws.bn = 0;
   ws.bhs = 0;
+  ws.win = nullptr;
   return ws;
 }
 

@@ -140,6 +140,24 @@ static GsrFwdArgs gsr_fwd_args(const GsrWorkspace& ws, float* img, int h, int w,
   a.hf = ws.hf;
   a.row0 = ws.row0;
   a.bhs = ws.bn > 0 ? ws.bhs : 0;
+  if (flags & GSR_FLAG_CHW) {
+    a.row_stride = w;
+    a.pix_stride = 1;
+    a.chan_stride = (long long)h * w;
+  } else {
+    a.row_stride = 3LL * w;
+    a.pix_stride = 3;
+    a.chan_stride = 1;
+  }
+  a.nclip = 0;
+  if (ws.win) {  // a window of a larger destination (gsr_forward_window)
+    a.row_stride = ws.win->row_stride;
+    a.pix_stride = ws.win->pix_stride;
+    a.chan_stride = ws.win->chan_stride;
+    a.nclip = ws.win->nclip;
+    for (int k = 0; k < a.nclip; ++k)
+      for (int j = 0; j < 4; ++j) a.clip[k][j] = ws.win->clip[k][j];
+  }
   return a;
 }
 
@@ -230,7 +248,7 @@ static bool gsr_band_ok(int h, int hf, int row0) {
 static int gsr_forward_impl(const float* sigmas, const float* coords, const float* colors, float* img,
                             int s, int h, int w, int c, int hf, int row0, float dmax, float ksigma,
                             uint32_t flags, void* workspace, size_t workspace_bytes, void* stream,
-                            int bn = 0, int bhs = 0) {
+                            int bn = 0, int bhs = 0, const gsr_window* win = nullptr) {
   if (c != 3) return GSR_ERR_BAD_CHANNELS;
   if (!gsr_dims_ok(s, h, w) || !gsr_band_ok(h, hf, row0)) return GSR_ERR_BAD_SHAPE;
   if (!img || (s > 0 && (!sigmas || !coords || !colors))) return GSR_ERR_NULL_POINTER;
@@ -245,6 +263,7 @@ static int gsr_forward_impl(const float* sigmas, const float* coords, const floa
   const float keff = gsr_effective_ksigma(ksigma);
   rc = gsr_clear_and_tables(h, w, ws, st);
   if (rc) return rc;
+  ws.win = win;
   rc = gsr_prepare_forward(sigmas, coords, colors, s, h, w, dmax, keff, ws, st);
   if (rc) return rc;
   return gsr_raster_forward(ws, img, h, w, keff, flags, st);
@@ -291,6 +310,17 @@ extern "C" int gsr_backward(const float* sigmas, const float* coords, const floa
                             void* stream) {
   return gsr_backward_impl(sigmas, coords, colors, grads, grads_sigmas, grads_coords, grads_colors, s, h, w,
                            c, 0, 0, dmax, ksigma, flags, workspace, workspace_bytes, stream);
+}
+
+// ---- render into a window of a larger destination ---------------------------------------------
+extern "C" int gsr_forward_window(const float* sigmas, const float* coords, const float* colors,
+                                  float* origin, const gsr_window* win, int s, int h, int w, int c,
+                                  float dmax, float ksigma, uint32_t flags, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  if (!win) return GSR_ERR_NULL_POINTER;
+  if (win->nclip < 0 || win->nclip > GSR_MAX_CLIP || (flags & GSR_FLAG_CHW)) return GSR_ERR_BAD_ARGUMENT;
+  return gsr_forward_impl(sigmas, coords, colors, origin, s, h, w, c, 0, 0, dmax, ksigma, flags, workspace,
+                          workspace_bytes, stream, 0, 0, win);
 }
 
 // ---- row bands of one image (multi-GPU split of a single large image) ---------------------------

@@ -27,7 +27,7 @@ from . import gscuda as _gs
 
 __all__ = [
     "generate_2D_gaussian_splatting_step", "generate_2D_gaussian_splatting_step_buffer",
-    "generate_2D_gaussian_splatting_step_batch",
+    "generate_2D_gaussian_splatting_step_batch", "render_into_canvas",
     "rendering_cuda", "rendering_cuda_buffer", "rendering_cuda_dmax", "rendering_cuda_dmax_buffer",
     "map_gaussians", "render_chw",
 ]
@@ -312,3 +312,28 @@ def generate_2D_gaussian_splatting_step_batch(sr_size, gs_parameters, scale, sca
                                          colours_with_alpha.contiguous().view(b, n, 3),
                                          (int(sr_size[0]), int(sr_size[1])), dm)
     return out.permute(0, 3, 1, 2)
+
+
+def render_into_canvas(canvas, y0, x0, regions, sr_size, gs_parameters, scale, scale_modify,
+                       default_step_size=1.2, mode='scale_modify', if_dmax=True, dmax_mode='fix', dmax=25):
+    """Inference-only: generate_2D_gaussian_splatting_step whose (3,h,w) result is written straight into
+    `canvas` -- a contiguous (..., 3, H, W) float32 CUDA tensor (its last three dimensions are addressed),
+    possibly the memory of another GPU -- with its pixel (0,0) at canvas (y0, x0); only the pixels inside
+    `regions` = [(ya, yb, xa, xb), ...] (half-open, CANVAS coordinates) are written, the others are left
+    as they are.  Same activations / mapping expressions as the per-tile function; no tile buffer, no
+    paste pass."""
+    h, w = int(sr_size[0]), int(sr_size[1])
+    H, W = int(canvas.shape[-2]), int(canvas.shape[-1])
+    step_size, sigma_x, sigma_y, rho, coords, colours_with_alpha = _prepare(
+        gs_parameters, scale, scale_modify, default_step_size, mode)
+    sigmas, coords = map_gaussians(sigma_x, sigma_y, rho, coords, sr_size, step_size)
+    clips = []
+    for ya, yb, xa, xb in regions:
+        ya, yb, xa, xb = max(ya - y0, 0), min(yb - y0, h), max(xa - x0, 0), min(xb - x0, w)
+        if ya < yb and xa < xb:
+            clips.append((xa, ya, xb - 1, yb - 1))
+    if not clips:
+        return
+    _gs.gs_render_window(sigmas, coords.contiguous(), colours_with_alpha.contiguous(), canvas,
+                         y0 * W + x0, W, 1, H * W, clips, sigmas.shape[0], h, w,
+                         _resolve_dmax(if_dmax, dmax_mode, dmax, sr_size), flags=_OVER)

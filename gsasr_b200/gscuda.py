@@ -22,7 +22,7 @@ import torch
 from . import _lib
 
 __all__ = ["gs_render", "gs_render_backward", "gs_render_band", "gs_render_backward_band", "gs_render_batch",
-           "gs_render_backward_batch", "set_ksigma", "get_ksigma"]
+           "gs_render_backward_batch", "gs_render_window", "set_ksigma", "get_ksigma"]
 
 _ksigma = float(os.environ.get("GSR_KSIGMA", "0"))  # 0 -> library default (GSR_DEFAULT_KSIGMA)
 
@@ -221,4 +221,48 @@ def gs_render_backward_batch(sigmas, coords, colors, grads, grads_sigmas, grads_
                                           _ptr(grads_sigmas), _ptr(grads_coords), _ptr(grads_colors), b, s, h, w,
                                           3, float(dmax), float(_ksigma if ksigma is None else ksigma), int(flags),
                                           ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)
+
+
+# ---- render into a window of a larger destination (gsr_forward_window): the raster kernel writes the
+# tile's pixels straight into `dst` -- any float32 CUDA tensor, possibly the memory of ANOTHER GPU
+# (peer stores) -- at element offset `origin` for pixel (0,0) with the given strides (in elements);
+# only pixels inside one of `clips` = [(x0, y0, x1, y1), ...] (inclusive, render coordinates) are written.
+def gs_render_window(sigmas, coords, colors, dst, origin, row_stride, pix_stride, chan_stride, clips,
+                     s, h, w, dmax=float("inf"), *, ksigma=None, flags=0, workspace_buf=None):
+    L = _lib.load()
+    for t, n in ((sigmas, "sigmas"), (coords, "coords"), (colors, "colors")):
+        _check_input(t, n)
+    if not (isinstance(dst, torch.Tensor) and dst.is_cuda and dst.dtype == torch.float32):
+        raise RuntimeError("dst must be a float32 CUDA tensor")
+    s, h, w = int(s), int(h), int(w)
+    _check_shape(sigmas, (s, 3), "sigmas")
+    _check_shape(coords, (s, 2), "coords")
+    _check_shape(colors, (s, 3), "colors")
+    clips = [tuple(int(v) for v in c) for c in (clips or [])]
+    if len(clips) > _lib.GSR_MAX_CLIP:
+        raise RuntimeError(f"at most {_lib.GSR_MAX_CLIP} clip rectangles")
+    win = _lib.GsrWindow()
+    win.row_stride, win.pix_stride, win.chan_stride, win.nclip = int(row_stride), int(pix_stride), int(chan_stride), len(clips)
+    rects = clips if clips else [(0, 0, w - 1, h - 1)]
+    lo = hi = None
+    for k, (x0, y0, x1, y1) in enumerate(rects):
+        if not (0 <= x0 <= x1 < w and 0 <= y0 <= y1 < h):
+            raise RuntimeError(f"clip rectangle {(x0, y0, x1, y1)} is not inside the {h}x{w} render")
+        if clips:
+            for j, v in enumerate((x0, y0, x1, y1)):
+                win.clip[k][j] = v
+        for yy, xx in ((y0, x0), (y1, x1)):  # bounds of the touched elements (strides are non-negative)
+            a = int(origin) + yy * win.row_stride + xx * win.pix_stride
+            lo = a if lo is None else min(lo, a)
+            hi = a + 2 * win.chan_stride if hi is None else max(hi, a + 2 * win.chan_stride)
+    if min(win.row_stride, win.pix_stride, win.chan_stride) < 0 or lo < 0 or hi >= dst.numel():
+        raise RuntimeError("window leaves the destination tensor")
+    if not dst.is_contiguous():
+        raise RuntimeError("dst must be contiguous (the strides address its flat storage)")
+    with torch.cuda.device(sigmas.device):
+        ws = workspace_buf if workspace_buf is not None else workspace(s, h, w, sigmas.device)
+        rc = L.gsr_forward_window(_ptr(sigmas), _ptr(coords), _ptr(colors), dst.data_ptr() + 4 * int(origin),
+                                  win, s, h, w, 3, float(dmax), float(_ksigma if ksigma is None else ksigma),
+                                  int(flags), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)

@@ -108,6 +108,25 @@ int gsr_backward_band(const float* sigmas, const float* coords, const float* col
                       float ksigma, uint32_t flags, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* Render into a WINDOW of a larger destination (tiled inference: utils/split_and_joint_image.py:160-227
+ * renders every tile into its own buffer and pastes it into the canvas afterwards; here the raster
+ * kernel writes the tile's pixels straight into the canvas -- which may live on another GPU: peer
+ * stores over NVLink).  Pixel (y, x), channel ch of the h x w render is written to
+ *     origin + y * row_stride + x * pix_stride + ch * chan_stride            (strides in floats)
+ * if nclip == 0 or (x, y) lies inside one of the clip rectangles {x0, y0, x1, y1} (inclusive, render
+ * coordinates); other pixels are neither read nor written, so `origin` may point outside the
+ * destination as long as every clipped-in pixel is inside.  GSR_FLAG_OVERWRITE or accumulate;
+ * GSR_FLAG_CHW is expressed through the strides instead.  `win` is HOST memory. */
+#define GSR_MAX_CLIP 8
+typedef struct gsr_window {
+  long long row_stride, pix_stride, chan_stride;
+  int nclip;
+  int clip[GSR_MAX_CLIP][4];
+} gsr_window;
+int gsr_forward_window(const float* sigmas, const float* coords, const float* colors, float* origin,
+                       const gsr_window* win, int s, int h, int w, int c, float dmax, float ksigma,
+                       uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Split-phase form.  gsr_forward == gsr_prepare + gsr_forward_prepared, gsr_backward ==
  * gsr_prepare + gsr_backward_prepared.  gsr_prepare runs the O(N) set-up (cull boxes, counting
  * sort by home bin) and leaves it in `workspace`; as long as the workspace is untouched and

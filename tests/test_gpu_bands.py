@@ -111,3 +111,43 @@ def test_single_process_band_api_equals_whole_image():
     gscuda.gs_render_backward(s, c, k, g, *ws, s.shape[0], h, w, 3, 0.1)
     for a, b in zip((gs, gc, gk), ws):
         assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
+
+
+def test_direct_stitching_equals_tile_buffers_and_paste():
+    """split_and_joint_image(direct=True): tiles rendered straight into the canvas (gsr_forward_window with
+    the ownership regions) against the reference's route (tile buffers + stitch_tiles)."""
+    from gsasr_b200.split_and_joint_image import plan_tiles, split_and_joint_image
+
+    for scale, split, overlap, crop, hw in ((4.0, 40, 8, 4, (72, 100)), (2.5, 32, 6, 2, (60, 60))):
+        lq = torch.rand(1, 3, *hw, device=DEV)
+        plan = plan_tiles(hw[0], hw[1], scale, split, overlap)
+        raws = [fields.raw_field(2 * split, 2 * split, seed=i).to(DEV) for i in range(plan.n)]
+        calls = [0]
+
+        def fea2gs(feat, sv):
+            calls[0] += 1
+            return raws[(calls[0] - 1) % plan.n].unsqueeze(0)
+
+        sm = torch.tensor([scale, scale])
+        want = split_and_joint_image(lq, scale, split, overlap, lambda t: t, fea2gs, sm, crop_size=crop,
+                                     if_dmax=True, dmax=0.1)
+        calls[0] = 0
+        got = split_and_joint_image(lq, scale, split, overlap, lambda t: t, fea2gs, sm, crop_size=crop,
+                                    if_dmax=True, dmax=0.1, direct=True)
+        assert got.shape == want.shape
+        assert float((got - want).abs().max()) <= 2e-6
+
+
+def test_window_render_touches_only_its_clip_rectangles():
+    s, c, k = _field(48, 40, 300, seed=9)
+    full = _full(s, c, k, 48, 40, 0.2).permute(2, 0, 1).contiguous()          # (3,48,40)
+    canvas = torch.full((3, 80, 64), -5.0, device=DEV)
+    clips = [(4, 2, 30, 20), (0, 30, 39, 47)]
+    gscuda.gs_render_window(s, c, k, canvas, 10 * 64 + 7, 64, 1, 80 * 64, clips, s.shape[0], 48, 40, 0.2, flags=1)
+    torch.cuda.synchronize()
+    want = torch.full((3, 80, 64), -5.0, device=DEV)
+    for x0, y0, x1, y1 in clips:
+        want[:, 10 + y0:10 + y1 + 1, 7 + x0:7 + x1 + 1] = full[:, y0:y1 + 1, x0:x1 + 1]
+    assert float((canvas - want).abs().max()) <= 2e-6
+    with pytest.raises(RuntimeError):
+        gscuda.gs_render_window(s, c, k, canvas, 70 * 64, 64, 1, 80 * 64, [], s.shape[0], 48, 40, 0.2)  # leaves dst

@@ -94,3 +94,26 @@ def test_sharded_over_two_ranks(name):
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, _free_port(), name, ret), nprocs=2, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+# ---- ownership regions (direct / peer-write stitching): the paste order resolved in advance ------
+@pytest.mark.parametrize("h_lq,w_lq,scale,split,overlap,crop", [
+    (100, 130, 4.0, 48, 8, 4), (100, 130, 2.5, 48, 8, 2), (64, 64, 3.3, 40, 6, 3), (90, 50, 2.0, 40, 4, 2),
+    (48, 48, 4.0, 48, 8, 4),
+])
+def test_tile_regions_reproduce_the_paste_order(h_lq, w_lq, scale, split, overlap, crop):
+    """Pasting constant tiles (tile i filled with i+1) with the fixture-pinned stitch_tiles gives the
+    owner of every canvas pixel; tile_regions must describe exactly those pixels, disjointly."""
+    from gsasr_b200.split_and_joint_image import plan_tiles, stitch_tiles, tile_regions
+
+    plan = plan_tiles(h_lq, w_lq, scale, split, overlap)
+    tiles = [torch.full((1, 1, plan.split_sr, plan.split_sr), float(i + 1)) for i in range(plan.n)]
+    owner = stitch_tiles(tiles, plan, 1, 1, scale, crop)[0, 0].numpy()
+    got = np.zeros_like(owner)
+    regs = tile_regions(plan, crop, scale == int(scale))
+    for i, reg in enumerate(regs):
+        assert len(reg) <= 8
+        for y0, y1, x0, x1 in reg:
+            assert np.all(got[y0:y1, x0:x1] == 0), "regions overlap"
+            got[y0:y1, x0:x1] = i + 1
+    assert np.array_equal(got, owner)
