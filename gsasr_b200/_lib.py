@@ -52,6 +52,8 @@ SIGNATURES = {
     "gsr_backward_band": (_i, [_vp] * 7 + [_i, _i, _i, _i, _i, _i, _f, _f, _u32, _vp, _sz, _vp]),
     "gsr_forward_window": (_i, [_vp, _vp, _vp, _vp, ctypes.POINTER(GsrWindow), _i, _i, _i, _i, _f, _f, _u32, _vp,
                                 _sz, _vp]),
+    "gsr_frontend_forward_window": (_i, [_vp, _vp, _vp, ctypes.POINTER(GsrWindow), _i, _i, _i, _f, _f, _f, _u32, _vp,
+                                         _sz, _vp]),
     "gsr_prepare": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _sz, _vp]),
     "gsr_forward_prepared": (_i, [_vp, _i, _i, _i, _f, _u32, _vp, _sz, _vp]),
     "gsr_backward_prepared": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _u32, _vp, _sz, _vp]),

@@ -598,6 +598,24 @@ extern "C" int gsr_frontend_backward_batch_uniform(const float* raw, const float
   return GSR_OK;
 }
 
+// Fused front end into a window: raw (s,9) -> activations + mapping -> render into the destination.
+extern "C" int gsr_frontend_forward_window(const float* raw, float* mapped, float* origin,
+                                           const gsr_window* win, int s, int h, int w, float step_size,
+                                           float dmax, float ksigma, uint32_t flags, void* workspace,
+                                           size_t workspace_bytes, void* stream) {
+  if (!gsr_dims_ok(s, h, w)) return GSR_ERR_BAD_SHAPE;
+  if (!origin || !win || (s > 0 && (!raw || !mapped))) return GSR_ERR_NULL_POINTER;
+  if (!(step_size > 0.0f)) return GSR_ERR_BAD_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s > 0) {
+    gsr_map_kernel<<<(s + 255) / 256, 256, 0, st>>>(raw, mapped, mapped + 3 * (size_t)s,
+                                                    mapped + 5 * (size_t)s, s, h, w, step_size);
+    GSR_CUDA(cudaGetLastError());
+  }
+  return gsr_forward_window(mapped, mapped + 3 * (size_t)s, mapped + 5 * (size_t)s, origin, win, s, h, w, 3,
+                            dmax, ksigma, flags, workspace, workspace_bytes, stream);
+}
+
 // ---- CPU test hooks (no GPU needed): run the shared host/device culling code on the host ----
 extern "C" void gsr_host_setup(const float* sigmas, const float* coords, const float* colors,
                                int s, int h, int w, float dmax, float ksigma, int* out /* s x 9 */) {

@@ -315,7 +315,8 @@ def generate_2D_gaussian_splatting_step_batch(sr_size, gs_parameters, scale, sca
 
 
 def render_into_canvas(canvas, y0, x0, regions, sr_size, gs_parameters, scale, scale_modify,
-                       default_step_size=1.2, mode='scale_modify', if_dmax=True, dmax_mode='fix', dmax=25):
+                       default_step_size=1.2, mode='scale_modify', if_dmax=True, dmax_mode='fix', dmax=25,
+                       fused=False):
     """Inference-only: generate_2D_gaussian_splatting_step whose (3,h,w) result is written straight into
     `canvas` -- a contiguous (..., 3, H, W) float32 CUDA tensor (its last three dimensions are addressed),
     possibly the memory of another GPU -- with its pixel (0,0) at canvas (y0, x0); only the pixels inside
@@ -324,9 +325,6 @@ def render_into_canvas(canvas, y0, x0, regions, sr_size, gs_parameters, scale, s
     paste pass."""
     h, w = int(sr_size[0]), int(sr_size[1])
     H, W = int(canvas.shape[-2]), int(canvas.shape[-1])
-    step_size, sigma_x, sigma_y, rho, coords, colours_with_alpha = _prepare(
-        gs_parameters, scale, scale_modify, default_step_size, mode)
-    sigmas, coords = map_gaussians(sigma_x, sigma_y, rho, coords, sr_size, step_size)
     clips = []
     for ya, yb, xa, xb in regions:
         ya, yb, xa, xb = max(ya - y0, 0), min(yb - y0, h), max(xa - x0, 0), min(xb - x0, w)
@@ -334,6 +332,14 @@ def render_into_canvas(canvas, y0, x0, regions, sr_size, gs_parameters, scale, s
             clips.append((xa, ya, xb - 1, yb - 1))
     if not clips:
         return
+    dm = _resolve_dmax(if_dmax, dmax_mode, dmax, sr_size)
+    if fused:  # the library's fused front end (parity 1e-4) instead of ~15 elementwise torch kernels
+        step_size = float(default_step_size / (scale if mode == 'scale' else scale_modify[0]))
+        _gs.frontend_render_window(gs_parameters.contiguous().float(), canvas, y0 * W + x0, W, 1, H * W, clips,
+                                   h, w, step_size, dm, flags=_OVER)
+        return
+    step_size, sigma_x, sigma_y, rho, coords, colours_with_alpha = _prepare(
+        gs_parameters, scale, scale_modify, default_step_size, mode)
+    sigmas, coords = map_gaussians(sigma_x, sigma_y, rho, coords, sr_size, step_size)
     _gs.gs_render_window(sigmas, coords.contiguous(), colours_with_alpha.contiguous(), canvas,
-                         y0 * W + x0, W, 1, H * W, clips, sigmas.shape[0], h, w,
-                         _resolve_dmax(if_dmax, dmax_mode, dmax, sr_size), flags=_OVER)
+                         y0 * W + x0, W, 1, H * W, clips, sigmas.shape[0], h, w, dm, flags=_OVER)

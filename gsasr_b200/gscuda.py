@@ -22,7 +22,7 @@ import torch
 from . import _lib
 
 __all__ = ["gs_render", "gs_render_backward", "gs_render_band", "gs_render_backward_band", "gs_render_batch",
-           "gs_render_backward_batch", "gs_render_window", "set_ksigma", "get_ksigma"]
+           "gs_render_backward_batch", "gs_render_window", "frontend_render_window", "set_ksigma", "get_ksigma"]
 
 _ksigma = float(os.environ.get("GSR_KSIGMA", "0"))  # 0 -> library default (GSR_DEFAULT_KSIGMA)
 
@@ -228,25 +228,18 @@ def gs_render_backward_batch(sigmas, coords, colors, grads, grads_sigmas, grads_
 # tile's pixels straight into `dst` -- any float32 CUDA tensor, possibly the memory of ANOTHER GPU
 # (peer stores) -- at element offset `origin` for pixel (0,0) with the given strides (in elements);
 # only pixels inside one of `clips` = [(x0, y0, x1, y1), ...] (inclusive, render coordinates) are written.
-def gs_render_window(sigmas, coords, colors, dst, origin, row_stride, pix_stride, chan_stride, clips,
-                     s, h, w, dmax=float("inf"), *, ksigma=None, flags=0, workspace_buf=None):
-    L = _lib.load()
-    for t, n in ((sigmas, "sigmas"), (coords, "coords"), (colors, "colors")):
-        _check_input(t, n)
+def _window(dst, origin, row_stride, pix_stride, chan_stride, clips, h, w):
     if not (isinstance(dst, torch.Tensor) and dst.is_cuda and dst.dtype == torch.float32):
         raise RuntimeError("dst must be a float32 CUDA tensor")
-    s, h, w = int(s), int(h), int(w)
-    _check_shape(sigmas, (s, 3), "sigmas")
-    _check_shape(coords, (s, 2), "coords")
-    _check_shape(colors, (s, 3), "colors")
+    if not dst.is_contiguous():
+        raise RuntimeError("dst must be contiguous (the strides address its flat storage)")
     clips = [tuple(int(v) for v in c) for c in (clips or [])]
     if len(clips) > _lib.GSR_MAX_CLIP:
         raise RuntimeError(f"at most {_lib.GSR_MAX_CLIP} clip rectangles")
     win = _lib.GsrWindow()
     win.row_stride, win.pix_stride, win.chan_stride, win.nclip = int(row_stride), int(pix_stride), int(chan_stride), len(clips)
-    rects = clips if clips else [(0, 0, w - 1, h - 1)]
     lo = hi = None
-    for k, (x0, y0, x1, y1) in enumerate(rects):
+    for k, (x0, y0, x1, y1) in enumerate(clips if clips else [(0, 0, w - 1, h - 1)]):
         if not (0 <= x0 <= x1 < w and 0 <= y0 <= y1 < h):
             raise RuntimeError(f"clip rectangle {(x0, y0, x1, y1)} is not inside the {h}x{w} render")
         if clips:
@@ -258,11 +251,40 @@ def gs_render_window(sigmas, coords, colors, dst, origin, row_stride, pix_stride
             hi = a + 2 * win.chan_stride if hi is None else max(hi, a + 2 * win.chan_stride)
     if min(win.row_stride, win.pix_stride, win.chan_stride) < 0 or lo < 0 or hi >= dst.numel():
         raise RuntimeError("window leaves the destination tensor")
-    if not dst.is_contiguous():
-        raise RuntimeError("dst must be contiguous (the strides address its flat storage)")
+    return win
+
+
+def gs_render_window(sigmas, coords, colors, dst, origin, row_stride, pix_stride, chan_stride, clips,
+                     s, h, w, dmax=float("inf"), *, ksigma=None, flags=0, workspace_buf=None):
+    L = _lib.load()
+    for t, n in ((sigmas, "sigmas"), (coords, "coords"), (colors, "colors")):
+        _check_input(t, n)
+    s, h, w = int(s), int(h), int(w)
+    _check_shape(sigmas, (s, 3), "sigmas")
+    _check_shape(coords, (s, 2), "coords")
+    _check_shape(colors, (s, 3), "colors")
+    win = _window(dst, origin, row_stride, pix_stride, chan_stride, clips, h, w)
     with torch.cuda.device(sigmas.device):
         ws = workspace_buf if workspace_buf is not None else workspace(s, h, w, sigmas.device)
         rc = L.gsr_forward_window(_ptr(sigmas), _ptr(coords), _ptr(colors), dst.data_ptr() + 4 * int(origin),
                                   win, s, h, w, 3, float(dmax), float(_ksigma if ksigma is None else ksigma),
                                   int(flags), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)
+
+
+def frontend_render_window(raw, dst, origin, row_stride, pix_stride, chan_stride, clips, h, w, step_size,
+                           dmax=float("inf"), *, ksigma=None, flags=0):
+    """raw head output (s,9) -> fused activations / mapping -> render into the window (inference)."""
+    L = _lib.load()
+    _check_input(raw, "raw")
+    s, h, w = int(raw.shape[0]), int(h), int(w)
+    _check_shape(raw, (s, 9), "raw")
+    win = _window(dst, origin, row_stride, pix_stride, chan_stride, clips, h, w)
+    with torch.cuda.device(raw.device):
+        mapped = torch.empty(max(s, 1) * 8, dtype=torch.float32, device=raw.device)
+        ws = workspace(s, h, w, raw.device)
+        rc = L.gsr_frontend_forward_window(_ptr(raw), mapped.data_ptr(), dst.data_ptr() + 4 * int(origin), win, s, h,
+                                           w, float(step_size), float(dmax),
+                                           float(_ksigma if ksigma is None else ksigma), int(flags),
+                                           ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)

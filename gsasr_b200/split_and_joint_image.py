@@ -172,7 +172,7 @@ def _peer_canvas(numel: int, device, gather_to: int, group):
 def split_and_joint_image(lq, scale_factor, split_size, overlap_size, model_g, model_fea2gs, scale_modify,
                           crop_size=2, default_step_size=1.2, mode='scale_modify', cuda_rendering=True,
                           if_dmax=False, dmax_mode='fix', dmax=25, *, render_fn=None, gather_to=0, group=None,
-                          direct=False):
+                          direct=False, fused=False):
     """Returns the stitched (B,C,H_pad,W_pad) SR image on rank `gather_to` (every rank when it is
     None or when torch.distributed is not initialised); None on the other ranks.
 
@@ -180,7 +180,8 @@ def split_and_joint_image(lq, scale_factor, split_size, overlap_size, model_g, m
     the reference's paste order are known in advance (tile_regions), so the raster kernel writes each tile
     straight into the canvas (gsr_forward_window); with a process group the canvas lives in symmetric
     memory on `gather_to` and the other ranks' kernels store into it over NVLink (peer writes), the
-    transfer overlapping the raster pixel by pixel instead of following it as a gather."""
+    transfer overlapping the raster pixel by pixel instead of following it as a gather.  fused=True (with
+    direct) also replaces the elementwise torch kernels of the front end by the library's fused one."""
     h_lq, w_lq = lq.shape[-2:]
     plan = plan_tiles(h_lq, w_lq, scale_factor, split_size, overlap_size)
     lq_pad = F.pad(input=lq, pad=(0, plan.pad_w, 0, plan.pad_h), mode='reflect')
@@ -196,7 +197,7 @@ def split_and_joint_image(lq, scale_factor, split_size, overlap_size, model_g, m
     if direct:
         return _split_and_joint_direct(lq, plan, tile_parameters, scale_factor, scale_modify, crop_size,
                                        default_step_size, mode, cuda_rendering, if_dmax, dmax_mode, dmax,
-                                       gather_to, group)
+                                       gather_to, group, fused)
     if render_fn is None:
         from .gaussian_splatting import generate_2D_gaussian_splatting_step as render_fn
 
@@ -214,7 +215,8 @@ def split_and_joint_image(lq, scale_factor, split_size, overlap_size, model_g, m
 
 
 def _split_and_joint_direct(lq, plan, tile_parameters, scale_factor, scale_modify, crop_size,
-                            default_step_size, mode, cuda_rendering, if_dmax, dmax_mode, dmax, gather_to, group):
+                            default_step_size, mode, cuda_rendering, if_dmax, dmax_mode, dmax, gather_to, group,
+                            fused=False):
     import torch.distributed as dist
 
     from .gaussian_splatting import _no_python_renderer, render_into_canvas
@@ -246,7 +248,7 @@ def _split_and_joint_direct(lq, plan, tile_parameters, scale_factor, scale_modif
         hn, wn = divmod(i, plan.tiles_w)
         render_into_canvas(canvas, hn * step, wn * step, regions[i],
                            torch.tensor([plan.split_sr, plan.split_sr]), tile_parameters(i), scale_factor,
-                           scale_modify, default_step_size, mode, if_dmax, dmax_mode, dmax)
+                           scale_modify, default_step_size, mode, if_dmax, dmax_mode, dmax, fused)
     if not multi:
         return canvas
     torch.cuda.current_stream().synchronize()

@@ -204,6 +204,11 @@ int gsr_frontend_backward_batch_uniform(const float* raw_params, const float* ma
                                         float step_size, float dmax, float ksigma, void* workspace,
                                         size_t workspace_bytes, void* stream);
 
+/* gsr_frontend_forward into a window (see gsr_forward_window): raw head output -> destination pixels. */
+int gsr_frontend_forward_window(const float* raw_params, float* mapped, float* origin, const gsr_window* win,
+                                int s, int h, int w, float step_size, float dmax, float ksigma,
+                                uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

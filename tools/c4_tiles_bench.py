@@ -16,6 +16,9 @@ from gsasr_b200.sharding import shard_range
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=10)
+ap.add_argument("--direct", action="store_true", help="tiles written straight into the (peer) canvas")
+ap.add_argument("--fused", action="store_true", help="with --direct: fused front end")
+ap.add_argument("--check", action="store_true", help="compare with the tile-buffer route")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -36,7 +39,16 @@ def model_fea2gs(feat, scale_vector):
 sm = torch.tensor([scale, scale])
 def step():
     return split_and_joint_image(lq, scale, split, overlap, lambda t: t, model_fea2gs, sm, crop_size=crop,
-                                 if_dmax=True, dmax=0.1, gather_to=0)
+                                 if_dmax=True, dmax=0.1, gather_to=0, direct=args.direct, fused=args.fused)
+if args.check:
+    calls[0] = 0
+    ref = split_and_joint_image(lq, scale, split, overlap, lambda t: t, model_fea2gs, sm, crop_size=crop,
+                                if_dmax=True, dmax=0.1, gather_to=0, direct=False)
+    calls[0] = 0
+    got = step()
+    if rank == 0:
+        print("direct=%s vs tile buffers: max-abs %.2e" % (args.direct, float((got - ref).abs().max())), flush=True)
+    calls[0] = 0
 for _ in range(3): out = step()
 if world > 1: dist.barrier()
 torch.cuda.synchronize()
@@ -52,6 +64,6 @@ if world > 1:
 if rank == 0:
     h, w = out.shape[-2:]
     print(json.dumps({"config": "C4-shaped: 1024x1024 LR -> x4 via split_and_joint_image, %dx%d tiles of %d^2 LR, %d Gaussians each"
-                      % (plan.tiles_h, plan.tiles_w, split, raws[lo].shape[0]), "world": world, "sr": [h, w],
+                      % (plan.tiles_h, plan.tiles_w, split, raws[lo].shape[0]), "world": world, "direct": args.direct, "fused": args.fused, "sr": [h, w],
                       "ms_per_image": round(ms, 3), "mp_per_s": round(h * w / 1e6 / (ms * 1e-3), 1)}))
 if world > 1: dist.destroy_process_group()
