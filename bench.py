@@ -187,9 +187,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="HL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--split", default="images", choices=["images", "bands"],
+    ap.add_argument("--split", default="images", choices=["images", "bands", "bands-peer"],
                     help="N > 1: 'images' = every rank its own image (weak scaling, the default); "
-                         "'bands' = one image split into row bands + gather (strong scaling)")
+                         "'bands' = one image split into row bands + all-gather (strong scaling); 'bands-peer' = the "
+                         "bands stored straight into rank 0's image over NVLink by the raster kernel")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -217,7 +218,7 @@ def main():
 
     cfg = fields.CONFIGS[args.workload]
     # every rank its own image (weak scaling); the same image on every rank when it is split into bands
-    _, s, c, k, h, w = fields.make(cfg, seed=0 if args.split == "bands" else rank)
+    _, s, c, k, h, w = fields.make(cfg, seed=0 if args.split != "images" else rank)
     n = s.shape[0]
     mp_img = h * w / 1e6
     s_h, c_h, k_h = (t.pin_memory() for t in (s, c, k))
@@ -233,6 +234,8 @@ def main():
         sharding.render_image_bands(sd, cd, kd, h, w, DMAX, gather_to=None)
 
     def step():
+        if args.split == "bands-peer" and world > 1:
+            return sharding.render_image_bands_peer(sd, cd, kd, h, w, DMAX, gather_to=0)
         if args.split == "bands" and world > 1:
             return step_bands()
         _lib.check(L.gsr_forward(sd.data_ptr(), cd.data_ptr(), kd.data_ptr(), img.data_ptr(), n, h, w, 3,
@@ -265,7 +268,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    strong = args.split == "bands" and world > 1
+    strong = args.split in ("bands", "bands-peer") and world > 1
     value = (1 if strong else world) * mp_img / (ms_step * 1e-3)
 
     # ---- dominant kernel, timed alone with events through the split-phase ABI ----

@@ -130,6 +130,42 @@ def _band_forward_cuda(sigmas, coords, colors, h, w, row0, rows, dmax):
     return band
 
 
+_SYMM_IMAGES = {}
+
+
+def _peer_image(numel: int, device, root: int, group):
+    """Symmetric-memory image buffer: (this rank's buffer, view of `root`'s buffer, handle); cached."""
+    import torch.distributed._symmetric_memory as symm_mem
+
+    key = (numel, str(device), id(group))
+    if key not in _SYMM_IMAGES:
+        buf = symm_mem.empty(numel, dtype=torch.float32, device=device)
+        _SYMM_IMAGES[key] = (buf, symm_mem.rendezvous(buf, group=group if group is not None else dist.group.WORLD))
+    buf, hdl = _SYMM_IMAGES[key]
+    return buf, hdl.get_buffer(root, (numel,), torch.float32), hdl
+
+
+def render_image_bands_peer(sigmas, coords, colors, h: int, w: int, dmax: float, *, gather_to: int = 0,
+                            group=None):
+    """render_image_bands with the gather folded into the raster kernel: the (h,w,3) image lives in
+    symmetric memory on `gather_to` and every rank's band kernel stores its rows straight into it over
+    NVLink (peer writes) -- no collective, the transfer overlaps the raster.  Returns a view of the
+    symmetric buffer on `gather_to` (valid until the next call), None elsewhere.  CUDA + NCCL only."""
+    from . import gscuda
+
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return _band_forward_cuda(sigmas, coords, colors, h, w, 0, h, dmax)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mine, target, hdl = _peer_image(h * w * 3, sigmas.device, gather_to, group)
+    row0, rows = band_rows(h, rank, world)
+    if rows > 0:
+        band = target.view(h, w, 3)[row0:row0 + rows]  # contiguous rows of the stitching rank's image
+        gscuda.gs_render_band(sigmas, coords, colors, band, sigmas.shape[0], h, w, 3, row0, rows, dmax, flags=1)
+    torch.cuda.current_stream().synchronize()
+    hdl.barrier()  # every rank's stores have landed
+    return mine.view(h, w, 3) if rank == gather_to else None
+
+
 def render_image_bands(sigmas, coords, colors, h: int, w: int, dmax: float, *, render_band=None,
                        gather_to: int | None = None, group=None):
     """gaussiansplatting_render of ONE (h,w) image split into row bands over the ranks of `group`.

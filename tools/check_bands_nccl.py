@@ -20,6 +20,9 @@ for name in ("C1", "C2"):
     got = sharding.backward_image_bands(s, c, k, g, h, w, 0.1)
     want = [torch.zeros_like(t) for t in (s, c, k)]
     gscuda.gs_render_backward(s, c, k, g, *want, s.shape[0], h, w, 3, 0.1)
+    peer = sharding.render_image_bands_peer(s, c, k, h, w, 0.1, gather_to=0)
+    if rank == 0:
+        assert float((peer - full).abs().max()) <= 2e-6, "peer-written bands differ"
     err = float((img - full).abs().max())
     rel = max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(got, want))
     print(f"[rank {rank}/{dist.get_world_size()}] {name} {h}x{w}: bands vs whole image max-abs {err:.2e}, "
