@@ -484,6 +484,9 @@ __device__ __forceinline__ void gsr_eval_quad(uint32_t addr0, uint32_t addr1, gs
 // spreads the lane-per-record staging writes over all banks; the readers' offsets stay immediates.
 __device__ __forceinline__ uint32_t gsr_fr_swz(int j) { return (uint32_t)((j >> 2) & 1) * 16u; }
 
+// WINDOW = false: the plain (h,w,3) / (3,h,w) image, addressed with compile-time-simple arithmetic;
+// WINDOW = true: the general strided destination with clip rectangles (gsr_forward_window).
+template <bool WINDOW>
 __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forward_region_kernel(GsrFwdArgs p) {
   if (gsr_guard_skip(p.guard, p.want)) return;
   __shared__ GsrFwdRegionSmem sm;
@@ -498,7 +501,7 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
   const uint32_t rec_h = gsr_smem_addr(&sm.rec[warp][0][0]) + half * GSR_FR_HALF_BYTES;  // this half's slice, stage 0
   const uint32_t box_s = gsr_smem_addr(&sm.box[warp][0][0]);
   const uint2* box_w = &sm.box[warp][0][0];
-  const bool over = (p.flags & 1u) != 0;
+  const bool over = (p.flags & 1u) != 0, chw = (p.flags & 2u) != 0;
 
   // Region of this half in unit v (-1: past the end) and the (raw) length of its bucket.
   auto region_of = [&](int v) { const int y = v / npx; return v < nunits ? y * p.nrx + (v - y * npx) * 2 + half : -1; };
@@ -626,17 +629,28 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
       gsr_upk(r1, v[1][0][0], v[1][1][0]);
       gsr_upk(g1, v[1][0][1], v[1][1][1]);
       gsr_upk(b1, v[1][0][2], v[1][1][2]);
+      const size_t plane = (size_t)p.h * p.w;
 #pragma unroll
       for (int yy = 0; yy < 2; ++yy) {
 #pragma unroll
         for (int xx = 0; xx < 2; ++xx) {
           const int hi = hi0 + yy, wi = wi0 + xx;
-          if (gsr_fwd_writable(p, hi, wi)) {
-            float* o = gsr_fwd_pixel(p, hi, wi);
+          if (WINDOW) {
+            if (gsr_fwd_writable(p, hi, wi)) {
+              float* o = gsr_fwd_pixel(p, hi, wi);
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch) {
+                if (over) o[ch * p.chan_stride] = v[yy][xx][ch];
+                else atomicAdd(o + ch * p.chan_stride, v[yy][xx][ch]);
+              }
+            }
+          } else if (hi < p.h && wi < p.w) {
+            const size_t pix = (size_t)hi * p.w + wi;
 #pragma unroll
             for (int ch = 0; ch < 3; ++ch) {
-              if (over) o[ch * p.chan_stride] = v[yy][xx][ch];
-              else atomicAdd(o + ch * p.chan_stride, v[yy][xx][ch]);
+              float* o = chw ? p.img + ch * plane + pix : p.img + pix * 3 + ch;
+              if (over) *o = v[yy][xx][ch];
+              else atomicAdd(o, v[yy][xx][ch]);
             }
           }
         }

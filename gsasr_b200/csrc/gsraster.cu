@@ -168,11 +168,12 @@ static int gsr_launch_forward_region(const GsrWorkspace& ws, float* img, int h, 
   a.want = 0;
   // persistent warps: one resident wave, every warp strides over the region pairs
   int cap = 0;
-  const int rc = gsr_resident_grid(gsr_forward_region_kernel, GSR_FR_THREADS, 1, &cap);
+  const int rc = gsr_resident_grid(gsr_forward_region_kernel<false>, GSR_FR_THREADS, 1, &cap);
   if (rc) return rc;
   const int nunits = (ws.nrx / 2) * ws.nry;
   const int want = (nunits + GSR_FR_WARPS - 1) / GSR_FR_WARPS;
-  gsr_forward_region_kernel<<<want < cap ? want : cap, GSR_FR_THREADS, 0, st>>>(a);
+  if (ws.win) gsr_forward_region_kernel<true><<<want < cap ? want : cap, GSR_FR_THREADS, 0, st>>>(a);
+  else gsr_forward_region_kernel<false><<<want < cap ? want : cap, GSR_FR_THREADS, 0, st>>>(a);
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
 }
