@@ -320,6 +320,32 @@ def main():
         e2e_ms = float(t.item())
     e2e_value = world * mp_img / (e2e_ms * 1e-3)
 
+    # ---- the same end-to-end loop with the post-processing of inference_paper.py:136-138 fused into the
+    # raster kernel (gs_render_u8: clamp, x255, round, uint8 HWC): 3 bytes per pixel come back, not 12.
+    # An extra figure for the inference pipeline; `e2e` above stays the reference-shaped fp32 call.
+    outs_u8 = [torch.empty(h, w, 3, dtype=torch.uint8).pin_memory() for _ in range(NSTREAM)]
+
+    def e2e_u8_step(i):
+        st = streams[i % NSTREAM]
+        with torch.cuda.stream(st):
+            a, b, cc = s_h.to(dev, non_blocking=True), c_h.to(dev, non_blocking=True), k_h.to(dev, non_blocking=True)
+            o = torch.empty(h, w, 3, dtype=torch.uint8, device=dev)
+            gscuda.gs_render_u8(a, b, cc, o, n, h, w, DMAX, bgr=True)
+            outs_u8[i % NSTREAM].copy_(o, non_blocking=True)
+
+    for i in range(4):
+        e2e_u8_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(ksteps):
+        e2e_u8_step(i)
+    barrier()
+    e2e_u8_ms = (time.perf_counter() - t0) * 1e3 / ksteps
+    if world > 1:
+        t = torch.tensor([e2e_u8_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_u8_ms = float(t.item())
+
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -329,6 +355,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 12 * h * w,
                     "note": f"gscuda.gs_render from pinned host tensors, steps rotate over {NSTREAM} CUDA streams"},
+            "e2e_u8": {"value": world * mp_img / (e2e_u8_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_u8_ms,
+                       "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 3 * h * w,
+                       "note": "extra: gscuda.gs_render_u8 (fused clamp/x255/round/uint8 post-processing of "
+                               "inference_paper.py:136-138), uint8 HWC image copied back"},
             "roofline": {"bound": "hbm", "kernel": "gsr_forward_region_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes": alg_bytes, "kernel_ms": kern_ms,

@@ -10,6 +10,8 @@ LIB_PATH = os.environ.get("GSR_LIB_PATH") or os.path.join(HERE, "libgsraster.so"
 
 GSR_FLAG_OVERWRITE = 0x1
 GSR_FLAG_CHW = 0x2
+GSR_FLAG_U8 = 0x4
+GSR_FLAG_BGR = 0x8
 DEFAULT_KSIGMA = 5.0
 EXACT_KSIGMA = float("inf")
 

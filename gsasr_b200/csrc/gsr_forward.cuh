@@ -165,6 +165,10 @@ __device__ __forceinline__ bool gsr_fwd_writable(const GsrFwdArgs& p, int hi, in
     in = in || (k < p.nclip && wi >= p.clip[k][0] && hi >= p.clip[k][1] && wi <= p.clip[k][2] && hi <= p.clip[k][3]);
   return in;
 }
+// inference_paper.py:136-138: clamp_(0, 1), * 255.0, round() (half to even), astype(uint8); NaN -> 0
+__device__ __forceinline__ unsigned char gsr_to_u8(float v) {
+  return (unsigned char)__float2uint_rn(__saturatef(v) * 255.0f);
+}
 __device__ __forceinline__ float* gsr_fwd_pixel(const GsrFwdArgs& p, int hi, int wi) {
   return p.img + (long long)hi * p.row_stride + (long long)wi * p.pix_stride;
 }
@@ -220,6 +224,12 @@ __device__ __forceinline__ void gsr_fwd_writeout(const GsrFwdArgs& p, int hi, in
 #pragma unroll
   for (int xx = 0; xx < 2; ++xx) {
     if (!gsr_fwd_writable(p, hi, wi0 + xx)) continue;
+    if (p.flags & 4u) {  // uint8 (h,w,3) output
+      unsigned char* o8 = reinterpret_cast<unsigned char*>(p.img) + ((size_t)hi * p.w + wi0 + xx) * 3;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) o8[(p.flags & 8u) ? 2 - ch : ch] = gsr_to_u8(v[xx][ch]);
+      continue;
+    }
     float* o = gsr_fwd_pixel(p, hi, wi0 + xx);
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) o[ch * p.chan_stride] = over ? v[xx][ch] : o[ch * p.chan_stride] + v[xx][ch];
@@ -501,7 +511,7 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
   const uint32_t rec_h = gsr_smem_addr(&sm.rec[warp][0][0]) + half * GSR_FR_HALF_BYTES;  // this half's slice, stage 0
   const uint32_t box_s = gsr_smem_addr(&sm.box[warp][0][0]);
   const uint2* box_w = &sm.box[warp][0][0];
-  const bool over = (p.flags & 1u) != 0, chw = (p.flags & 2u) != 0;
+  const bool over = (p.flags & 1u) != 0, chw = (p.flags & 2u) != 0, u8 = (p.flags & 4u) != 0, bgr = (p.flags & 8u) != 0;
 
   // Region of this half in unit v (-1: past the end) and the (raw) length of its bucket.
   auto region_of = [&](int v) { const int y = v / npx; return v < nunits ? y * p.nrx + (v - y * npx) * 2 + half : -1; };
@@ -646,11 +656,18 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
             }
           } else if (hi < p.h && wi < p.w) {
             const size_t pix = (size_t)hi * p.w + wi;
+            if (u8) {  // fused post-processing: clamp, x255, round-half-even, uint8 (h,w,3)
+              unsigned char* o8 = reinterpret_cast<unsigned char*>(p.img) + pix * 3;
 #pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-              float* o = chw ? p.img + ch * plane + pix : p.img + pix * 3 + ch;
-              if (over) *o = v[yy][xx][ch];
-              else atomicAdd(o, v[yy][xx][ch]);
+              for (int ch = 0; ch < 3; ++ch)
+                o8[bgr ? 2 - ch : ch] = gsr_to_u8(v[yy][xx][ch]);
+            } else {
+#pragma unroll
+              for (int ch = 0; ch < 3; ++ch) {
+                float* o = chw ? p.img + ch * plane + pix : p.img + pix * 3 + ch;
+                if (over) *o = v[yy][xx][ch];
+                else atomicAdd(o, v[yy][xx][ch]);
+              }
             }
           }
         }

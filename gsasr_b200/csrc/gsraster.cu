@@ -253,6 +253,9 @@ static int gsr_forward_impl(const float* sigmas, const float* coords, const floa
   if (c != 3) return GSR_ERR_BAD_CHANNELS;
   if (!gsr_dims_ok(s, h, w) || !gsr_band_ok(h, hf, row0)) return GSR_ERR_BAD_SHAPE;
   if (!img || (s > 0 && (!sigmas || !coords || !colors))) return GSR_ERR_NULL_POINTER;
+  if ((flags & GSR_FLAG_U8) && (!(flags & GSR_FLAG_OVERWRITE) || (flags & GSR_FLAG_CHW) || win))
+    return GSR_ERR_BAD_ARGUMENT;  // uint8 output: written once, (h,w,3), whole image
+  if ((flags & GSR_FLAG_BGR) && !(flags & GSR_FLAG_U8)) return GSR_ERR_BAD_ARGUMENT;
   GsrWorkspace ws = gsr_carve(workspace, s, h, w);
   ws.hf = hf;
   ws.row0 = row0;
@@ -379,7 +382,10 @@ extern "C" int gsr_forward_batch_uniform(const float* sigmas, const float* coord
     const int nb = batch - b0 < g ? batch - b0 : g;
     const size_t go = (size_t)b0 * s_per;
     const int rc = gsr_forward_impl(sigmas ? sigmas + 3 * go : nullptr, coords ? coords + 2 * go : nullptr,
-                                    colors ? colors + 3 * go : nullptr, imgs + (size_t)b0 * h * w * 3, nb * s_per,
+                                    colors ? colors + 3 * go : nullptr,
+                                    (flags & GSR_FLAG_U8) ? (float*)((unsigned char*)imgs + (size_t)b0 * h * w * 3)
+                                                          : imgs + (size_t)b0 * h * w * 3,
+                                    nb * s_per,
                                     nb * h, w, c, 0, 0, dmax, ksigma, flags, workspace, workspace_bytes, stream,
                                     nb > 1 ? s_per : 0, nb > 1 ? h : 0);
     if (rc) return rc;

@@ -27,7 +27,7 @@ from . import gscuda as _gs
 
 __all__ = [
     "generate_2D_gaussian_splatting_step", "generate_2D_gaussian_splatting_step_buffer",
-    "generate_2D_gaussian_splatting_step_batch", "render_into_canvas",
+    "generate_2D_gaussian_splatting_step_batch", "generate_2D_gaussian_splatting_step_u8", "render_into_canvas",
     "rendering_cuda", "rendering_cuda_buffer", "rendering_cuda_dmax", "rendering_cuda_dmax_buffer",
     "map_gaussians", "render_chw",
 ]
@@ -343,3 +343,20 @@ def render_into_canvas(canvas, y0, x0, regions, sr_size, gs_parameters, scale, s
     sigmas, coords = map_gaussians(sigma_x, sigma_y, rho, coords, sr_size, step_size)
     _gs.gs_render_window(sigmas, coords.contiguous(), colours_with_alpha.contiguous(), canvas,
                          y0 * W + x0, W, 1, H * W, clips, sigmas.shape[0], h, w, dm, flags=_OVER)
+
+
+def generate_2D_gaussian_splatting_step_u8(sr_size, gs_parameters, scale, scale_modify, default_step_size=1.2,
+                                           mode='scale_modify', if_dmax=True, dmax_mode='fix', dmax=25, bgr=True):
+    """Inference-only: generate_2D_gaussian_splatting_step followed by the post-processing of
+    inference_paper.py:136-138 (clamp_(0,1), [2,1,0] channel swap, HWC, *255, round, uint8) in one
+    pass: the raster kernel writes the (H,W,3) uint8 image (b,g,r order by default, as cv2.imwrite
+    wants it) directly.  Equals the reference's chain except where a value falls within fp32 round-off
+    of a rounding boundary (differences of one level on isolated pixels)."""
+    step_size, sigma_x, sigma_y, rho, coords, colours_with_alpha = _prepare(
+        gs_parameters, scale, scale_modify, default_step_size, mode)
+    sigmas, coords = map_gaussians(sigma_x, sigma_y, rho, coords, sr_size, step_size)
+    h, w = int(sr_size[0]), int(sr_size[1])
+    out = torch.empty(h, w, 3, dtype=torch.uint8, device=sigmas.device)
+    _gs.gs_render_u8(sigmas, coords.contiguous(), colours_with_alpha.contiguous(), out, sigmas.shape[0], h, w,
+                     _resolve_dmax(if_dmax, dmax_mode, dmax, sr_size), bgr=bgr)
+    return out

@@ -22,7 +22,7 @@ import torch
 from . import _lib
 
 __all__ = ["gs_render", "gs_render_backward", "gs_render_band", "gs_render_backward_band", "gs_render_batch",
-           "gs_render_backward_batch", "gs_render_window", "frontend_render_window", "set_ksigma", "get_ksigma"]
+           "gs_render_backward_batch", "gs_render_window", "frontend_render_window", "gs_render_u8", "set_ksigma", "get_ksigma"]
 
 _ksigma = float(os.environ.get("GSR_KSIGMA", "0"))  # 0 -> library default (GSR_DEFAULT_KSIGMA)
 
@@ -287,4 +287,28 @@ def frontend_render_window(raw, dst, origin, row_stride, pix_stride, chan_stride
                                            w, float(step_size), float(dmax),
                                            float(_ksigma if ksigma is None else ksigma), int(flags),
                                            ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)
+
+
+# ---- fused post-processing: the (h,w,3) UINT8 image of inference_paper.py:136-138 straight from the
+# raster kernel -- round(clamp(value, 0, 1) * 255), optionally in cv2's b, g, r channel order -- without
+# an fp32 image in between (a quarter of the bytes to store and to copy to the host).
+def gs_render_u8(sigmas, coords, colors, out_u8, s, h, w, dmax=float("inf"), *, bgr=False, ksigma=None,
+                 workspace_buf=None):
+    L = _lib.load()
+    for t, n in ((sigmas, "sigmas"), (coords, "coords"), (colors, "colors")):
+        _check_input(t, n)
+    if not (isinstance(out_u8, torch.Tensor) and out_u8.is_cuda and out_u8.dtype == torch.uint8 and out_u8.is_contiguous()):
+        raise RuntimeError("out_u8 must be a contiguous uint8 CUDA tensor")
+    s, h, w = int(s), int(h), int(w)
+    _check_shape(sigmas, (s, 3), "sigmas")
+    _check_shape(coords, (s, 2), "coords")
+    _check_shape(colors, (s, 3), "colors")
+    _check_shape(out_u8, (h, w, 3), "out_u8")
+    flags = _lib.GSR_FLAG_OVERWRITE | _lib.GSR_FLAG_U8 | (_lib.GSR_FLAG_BGR if bgr else 0)
+    with torch.cuda.device(sigmas.device):
+        ws = workspace_buf if workspace_buf is not None else workspace(s, h, w, sigmas.device)
+        rc = L.gsr_forward(_ptr(sigmas), _ptr(coords), _ptr(colors), out_u8.data_ptr(), s, h, w, 3, float(dmax),
+                           float(_ksigma if ksigma is None else ksigma), flags, ws.data_ptr(), ws.numel(),
+                           torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)

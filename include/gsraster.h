@@ -73,6 +73,11 @@ typedef enum gsr_status {
 /* flags */
 #define GSR_FLAG_OVERWRITE 0x1u /* forward: img = sum instead of img += sum (skips the read) */
 #define GSR_FLAG_CHW 0x2u       /* forward: img is (3,h,w); backward: grads is (3,h,w)       */
+/* forward only, with GSR_FLAG_OVERWRITE, (h,w,3) layout: `img` is UINT8 -- the kernel writes
+ * round(clamp(value, 0, 1) * 255) (round-half-even, as numpy), i.e. the post-processing of
+ * inference_paper.py:136-138 fused into the write-out: no fp32 image, a quarter of the bytes. */
+#define GSR_FLAG_U8 0x4u
+#define GSR_FLAG_BGR 0x8u       /* with GSR_FLAG_U8: channel order b, g, r (cv2.imwrite's; :137) */
 
 int gsr_version(void);
 const char* gsr_status_string(int status);

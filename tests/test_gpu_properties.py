@@ -174,3 +174,38 @@ def test_reference_wrapper_source_runs_unmodified_on_our_module():
     GSWrapper.gs_render_backward(s, c, k, torch.tensor(g["weight"], device=DEV), gs, gc, gk, 4, h, w, 3, 0.5)
     torch.cuda.synchronize()
     assert np.abs(gk.cpu().numpy() - g["g_colors"]).max() <= 1e-3 * np.abs(g["g_colors"]).max()
+
+
+@pytest.mark.parametrize("bgr", [False, True])
+def test_fused_uint8_output_equals_the_reference_post_processing(bgr):
+    """GSR_FLAG_U8: clamp_(0,1) -> [2,1,0] -> HWC -> *255 -> round -> uint8 (inference_paper.py:136-138) inside
+    the raster kernel, against the same chain applied with numpy to our fp32 render."""
+    from gsasr_b200 import gaussian_splatting as gsp
+
+    _, s, c, k, h, w = fields.make("C1", 3)
+    k = k * 3.0 - 0.2                                   # values on both sides of the clamp
+    sd, cd, kd = s.to(DEV), c.to(DEV), k.to(DEV)
+    img = torch.zeros(h, w, 3, device=DEV)
+    gscuda.gs_render(sd, cd, kd, img, s.shape[0], h, w, 3, 0.1)
+    ref = img.cpu().clamp_(0, 1).numpy()
+    if bgr:
+        ref = ref[:, :, [2, 1, 0]]
+    ref = (ref * 255.0).round().astype(np.uint8)
+    out = torch.full((h, w, 3), 77, dtype=torch.uint8, device=DEV)
+    gscuda.gs_render_u8(sd, cd, kd, out, s.shape[0], h, w, 0.1, bgr=bgr)
+    got = out.cpu().numpy()
+    diff = np.abs(got.astype(np.int16) - ref.astype(np.int16))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3   # only fp32 round-off at a rounding boundary
+    assert got.min() == 0 and got.max() == 255
+    raw = fields.raw_field(32, 32, seed=1).to(DEV)
+    u8 = gsp.generate_2D_gaussian_splatting_step_u8(torch.tensor([64, 64]), raw, 2.0, torch.tensor([2.0, 2.0]), dmax=0.1, bgr=bgr)
+    f32 = gsp.generate_2D_gaussian_splatting_step(torch.tensor([64, 64]), raw, 2.0, torch.tensor([2.0, 2.0]), dmax=0.1)
+    want = f32.cpu().clamp_(0, 1).numpy()
+    want = np.transpose(want[[2, 1, 0]] if bgr else want, (1, 2, 0))
+    want = (want * 255.0).round().astype(np.uint8)
+    assert np.abs(u8.cpu().numpy().astype(np.int16) - want.astype(np.int16)).max() <= 1
+    with pytest.raises(RuntimeError):                    # uint8 output cannot be accumulated into
+        L = _lib.load()
+        ws = gscuda.workspace(s.shape[0], h, w, DEV)
+        _lib.check(L.gsr_forward(sd.data_ptr(), cd.data_ptr(), kd.data_ptr(), out.data_ptr(), s.shape[0], h, w, 3,
+                                 0.1, 0.0, _lib.GSR_FLAG_U8, ws.data_ptr(), ws.numel(), 0))
