@@ -1,0 +1,42 @@
+"""Small end-to-end exercise of every kernel path for compute-sanitizer (memcheck / racecheck / initcheck):
+forward (region path, window-binding path, bucket-overflow fallback), backward, bands, batch, window, uint8."""
+import os, sys
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from gsasr_b200 import fields, gscuda, sharding
+dev = torch.device("cuda:0")
+rng = np.random.default_rng(0)
+def field(n, sig):
+    s = np.stack([rng.uniform(*sig, n), rng.uniform(*sig, n), np.tanh(rng.normal(0, 1, n)) * 0.99], 1)
+    return tuple(torch.tensor(a, dtype=torch.float32, device=dev) for a in (s, rng.uniform(-1.1, 1.1, (n, 2)), rng.uniform(0, 1, (n, 3))))
+for (h, w, n, sig, dmax) in ((97, 70, 500, (0.01, 0.1), 0.07), (64, 64, 300, (0.2, 2.0), 10.0), (33, 129, 200, (0.005, 0.05), 0.02)):
+    s, c, k = field(n, sig)
+    img = torch.zeros(h, w, 3, device=dev)
+    gscuda.gs_render(s, c, k, img, n, h, w, 3, dmax)
+    g = torch.rand(h, w, 3, device=dev)
+    gs, gc, gk = torch.zeros_like(s), torch.zeros_like(c), torch.zeros_like(k)
+    gscuda.gs_render_backward(s, c, k, g, gs, gc, gk, n, h, w, 3, dmax)
+    band = torch.zeros(16, w, 3, device=dev)
+    gscuda.gs_render_band(s, c, k, band, n, h, w, 3, 8, 16, dmax, flags=1)
+    gscuda.gs_render_backward_band(s, c, k, g[8:24].contiguous(), gs, gc, gk, n, h, w, 3, 8, 16, dmax)
+    u8 = torch.empty(h, w, 3, dtype=torch.uint8, device=dev)
+    gscuda.gs_render_u8(s, c, k, u8, n, h, w, dmax, bgr=True)
+    canvas = torch.zeros(3, h + 20, w + 12, device=dev)
+    gscuda.gs_render_window(s, c, k, canvas, 5 * (w + 12) + 3, w + 12, 1, (h + 20) * (w + 12), [(0, 0, w - 1, h // 2), (2, h // 2 + 1, w - 3, h - 1)], n, h, w, dmax, flags=1)
+# clustered field: buckets overflow -> home-bin fallback
+n, h, w = 4000, 128, 128
+s = torch.tensor(np.stack([np.full(n, 0.02), np.full(n, 0.02), np.zeros(n)], 1), dtype=torch.float32, device=dev)
+c = torch.tensor(rng.normal(0, 0.01, (n, 2)), dtype=torch.float32, device=dev)
+k = torch.rand(n, 3, device=dev)
+img = torch.zeros(h, w, 3, device=dev)
+gscuda.gs_render(s, c, k, img, n, h, w, 3, 0.5)
+# uniform batch
+sb = torch.stack([field(256, (0.01, 0.1))[0] for _ in range(3)]); cb = torch.rand(3, 256, 2, device=dev) * 2 - 1; kb = torch.rand(3, 256, 3, device=dev)
+imgs = torch.zeros(3, 40, 48, 3, device=dev)
+gscuda.gs_render_batch(sb, cb, kb, imgs, 0.2)
+gscuda.gs_render_backward_batch(sb, cb, kb, torch.rand_like(imgs), torch.zeros_like(sb), torch.zeros_like(cb), torch.zeros_like(kb), 0.2)
+_, s, c, k, h, w = fields.make("C1", 0)
+sharding.render_image_bands(s.to(dev), c.to(dev), k.to(dev), h, w, 0.1)
+torch.cuda.synchronize()
+print("sanitize_smoke done")
