@@ -377,6 +377,7 @@ extern "C" int gsr_forward_batch_uniform(const float* sigmas, const float* coord
                                          size_t workspace_bytes, void* stream) {
   if (batch < 0) return GSR_ERR_BAD_ARGUMENT;
   if (!gsr_dims_ok(s_per, h, w)) return GSR_ERR_BAD_SHAPE;
+  if (batch > 0 && !imgs) return GSR_ERR_NULL_POINTER;
   const int g = gsr_batch_group(batch, h, flags);
   for (int b0 = 0; b0 < batch; b0 += g) {
     const int nb = batch - b0 < g ? batch - b0 : g;
@@ -400,6 +401,7 @@ extern "C" int gsr_backward_batch_uniform(const float* sigmas, const float* coor
                                           size_t workspace_bytes, void* stream) {
   if (batch < 0) return GSR_ERR_BAD_ARGUMENT;
   if (!gsr_dims_ok(s_per, h, w)) return GSR_ERR_BAD_SHAPE;
+  if (batch > 0 && !grads) return GSR_ERR_NULL_POINTER;
   const int g = gsr_batch_group(batch, h, flags);
   for (int b0 = 0; b0 < batch; b0 += g) {
     const int nb = batch - b0 < g ? batch - b0 : g;

@@ -113,3 +113,54 @@ def test_frontend_rejects_python_renderer():
     with pytest.raises(NotImplementedError):
         generate_2D_gaussian_splatting_step(torch.tensor([8, 8]), torch.zeros(4, 9), 2.0,
                                             torch.tensor([2.0, 2.0]), cuda_rendering=False)
+
+
+def test_argument_validation_of_the_band_batch_window_entry_points():
+    """No GPU work: every call fails validation before anything is launched."""
+    L = _lib.load()
+    fake, ws = ctypes.c_void_p(256), ctypes.c_void_p(4096)
+    fb = L.gsr_forward_band
+    assert fb(fake, fake, fake, fake, 10, 64, 64, 3, 60, 8, 0.1, 0.0, 0, ws, 1 << 30, None) == 2   # band leaves the image
+    assert fb(fake, fake, fake, fake, 10, 64, 64, 3, 0, 1, 0.1, 0.0, 0, ws, 1 << 30, None) == 2    # rows < 2
+    assert fb(fake, fake, fake, fake, 10, 40000, 64, 3, 0, 8, 0.1, 0.0, 0, ws, 1 << 30, None) == 2  # h too large
+    assert fb(fake, fake, fake, None, 10, 64, 64, 3, 8, 8, 0.1, 0.0, 0, ws, 1 << 30, None) == 1
+    assert L.gsr_backward_band(fake, fake, fake, fake, fake, fake, fake, 10, 64, 64, 3, -8, 8, 0.1, 0.0, 0, ws,
+                               1 << 30, None) == 2
+    # uniform batch
+    assert L.gsr_workspace_bytes_batch_uniform(0, 10, 64, 64) > 0
+    assert L.gsr_workspace_bytes_batch_uniform(-1, 10, 64, 64) == 0
+    assert L.gsr_workspace_bytes_batch_uniform(4, 10, 1, 64) == 0
+    one, four = L.gsr_workspace_bytes(10, 64, 64), L.gsr_workspace_bytes_batch_uniform(4, 10, 64, 64)
+    assert four == L.gsr_workspace_bytes(40, 256, 64) and four >= one      # four samples: one 256-row stack
+    assert L.gsr_workspace_bytes_batch_uniform(4, 10, 60, 64) == L.gsr_workspace_bytes(10, 60, 64)  # h % 8: per sample
+    fu = L.gsr_forward_batch_uniform
+    assert fu(fake, fake, fake, fake, -1, 10, 64, 64, 3, 0.1, 0.0, 0, ws, 1 << 30, None) == 5
+    assert fu(fake, fake, fake, None, 2, 10, 64, 64, 3, 0.1, 0.0, 0, ws, 1 << 30, None) == 1
+    assert fu(fake, fake, fake, fake, 2, 10, 64, 64, 4, 0.1, 0.0, 0, ws, 1 << 30, None) == 3
+    assert fu(fake, fake, fake, fake, 0, 10, 64, 64, 3, 0.1, 0.0, 0, None, 0, None) == 0          # empty batch
+    # window destination
+    win = _lib.GsrWindow()
+    win.row_stride, win.pix_stride, win.chan_stride, win.nclip = 64, 1, 4096, 0
+    fw = L.gsr_forward_window
+    assert fw(fake, fake, fake, fake, None, 10, 64, 64, 3, 0.1, 0.0, 1, ws, 1 << 30, None) == 1     # no window
+    win.nclip = _lib.GSR_MAX_CLIP + 1
+    assert fw(fake, fake, fake, fake, ctypes.byref(win), 10, 64, 64, 3, 0.1, 0.0, 1, ws, 1 << 30, None) == 5
+    win.nclip = 0
+    assert fw(fake, fake, fake, fake, ctypes.byref(win), 10, 64, 64, 3, 0.1, 0.0, _lib.GSR_FLAG_CHW, ws, 1 << 30, None) == 5
+    # uint8 output needs OVERWRITE and the (h,w,3) layout; BGR needs U8
+    f = L.gsr_forward
+    assert f(fake, fake, fake, fake, 10, 64, 64, 3, 0.1, 0.0, _lib.GSR_FLAG_U8, ws, 1 << 30, None) == 5
+    assert f(fake, fake, fake, fake, 10, 64, 64, 3, 0.1, 0.0, _lib.GSR_FLAG_U8 | 1 | _lib.GSR_FLAG_CHW, ws, 1 << 30, None) == 5
+    assert f(fake, fake, fake, fake, 10, 64, 64, 3, 0.1, 0.0, _lib.GSR_FLAG_BGR | 1, ws, 1 << 30, None) == 5
+
+
+def test_band_rows_and_tile_regions_need_no_gpu():
+    from gsasr_b200 import sharding
+    from gsasr_b200.split_and_joint_image import plan_tiles, tile_regions
+
+    assert sharding.band_rows(2048, 1, 2) == (1024, 1024)
+    plan = plan_tiles(1024, 1024, 4.0, 480, 8)
+    regs = tile_regions(plan, 4, True)
+    assert len(regs) == 9 and all(1 <= len(r) <= 8 for r in regs)
+    area = sum((y1 - y0) * (x1 - x0) for r in regs for y0, y1, x0, x1 in r)
+    assert area == plan.sr_h * plan.sr_w       # integer scale: the regions tile the whole canvas
