@@ -187,6 +187,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="HL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--compact", action="store_true",
+                    help="compact-sigma field (sigma_px ~ 0.6 instead of the model-like 1.67): few pixels per "
+                         "Gaussian, the regime where the raster approaches its HBM roofline (SURVEY 8d)")
     ap.add_argument("--split", default="images", choices=["images", "bands", "bands-peer"],
                     help="N > 1: 'images' = every rank its own image (weak scaling, the default); "
                          "'bands' = one image split into row bands + all-gather (strong scaling); 'bands-peer' = the "
@@ -218,7 +221,7 @@ def main():
 
     cfg = fields.CONFIGS[args.workload]
     # every rank its own image (weak scaling); the same image on every rank when it is split into bands
-    _, s, c, k, h, w = fields.make(cfg, seed=0 if args.split != "images" else rank)
+    _, s, c, k, h, w = fields.make(cfg, seed=0 if args.split != "images" else rank, compact=args.compact)
     n = s.shape[0]
     mp_img = h * w / 1e6
     s_h, c_h, k_h = (t.pin_memory() for t in (s, c, k))
@@ -350,7 +353,8 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args.workload), split=args.split),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args.workload), split=args.split,
+                           **({"sigma": "compact: 0.99999*sigmoid(N(-1.5,0.5^2))+1e-6"} if args.compact else {})),
             "clocks": clocks, "gpu_launches": KERNELS_PER_STEP * args.steps,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 12 * h * w,
@@ -362,7 +366,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "gsr_forward_region_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes": alg_bytes, "kernel_ms": kern_ms,
-                         "kernel_share_of_step": kern_ms / ms_step, "traffic": TRAFFIC.get(args.workload),
+                         "kernel_share_of_step": kern_ms / ms_step, "traffic": None if args.compact else TRAFFIC.get(args.workload),
                          "note": "the kernel is bound by the MUFU.EX2 / FP32 issue pipes, not by HBM: see DESIGN.md"},
         }
         if not args.no_cpu_baseline and world == 1:
