@@ -10,14 +10,16 @@
 constexpr int ITERS = 2048, UNROLL = 8;
 
 enum Kind { FFMA, FFMA2, MUFU, LDS128_SAME, LDS128_HALF, LDS128_QUARTER, LDS128_EIGHTH, LDS128_LANE, LDS64_SAME,
-            LDS32_SAME, SHFL, MIX2x2, MIX1x2, MIX2x2_NOCOL, MIX_MMA, FFMA2_BCAST, NKIND };
+            LDS32_SAME, SHFL, MIX2x2, MIX1x2, MIX2x2_NOCOL, MIX_MMA, FFMA2_BCAST, MIX2x2_SCOL, MIX2x2_SCOLEXP, MIX2x2_SCALAR, NKIND };
 static const char* kNames[NKIND] = {"ffma", "ffma2", "mufu.ex2", "lds128 one address/warp", "lds128 one address/half-warp",
                                     "lds128 one address/quarter-warp", "lds128 one address/4 lanes",
                                     "lds128 lane-distinct (conflict-free)", "lds64 one address/warp",
                                     "lds32 one address/warp", "shfl.idx",
                                     "eval 2x2 px/lane (per record-iteration)", "eval 1x2 px/lane (per record-iteration)",
                                     "eval 2x2 px/lane, colour FMAs removed", "eval column/lane + tf32 MMA colours (per 128 evals)",
-                                    "ffma2 scalar-broadcast operands, distinct regs"};
+                                    "ffma2 scalar-broadcast operands, distinct regs",
+                                    "eval 2x2 px/lane, scalar colour FMAs", "eval 2x2 px/lane, scalar colour + exponent FMAs",
+                                    "eval 2x2 px/lane, all scalar"};
 
 __device__ __forceinline__ float ex2(float x) { float y; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 typedef unsigned long long f2;
@@ -89,6 +91,52 @@ __global__ void __launch_bounds__(1024) bench(long long* cycles, float* sink, fl
     float x, y;
     upk(add2(add2(add2(r0, g0), add2(b0, r1)), add2(g1, b1)), x, y);
     a0 = x + y;
+  } else if (KIND == MIX2x2_SCOL || KIND == MIX2x2_SCOLEXP || KIND == MIX2x2_SCALAR) {
+    const float py0 = seed * lane, py1 = py0 + seed, px0 = seed * (lane & 3), px1 = px0 + seed;
+    const f2 px2 = pk(px0, px1), py2 = pk(py0, py1);
+    float c[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) c[i] = 0.f;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const uint32_t ad = base + (lane >> 4) * 2048 + ((it * UNROLL + u) & 63) * 32;
+        const float4 q0 = lds128(ad), q1 = lds128(ad + 16);
+        float e00, e01, e10, e11;
+        if (KIND == MIX2x2_SCALAR) {
+          const float dx0 = px0 + q0.x, dx1 = px1 + q0.x, dy0 = py0 + q0.y, dy1 = py1 + q0.y;
+          const float t1a = q0.w * dy0, t1b = q0.w * dy1, t0a = q1.x * dy0 * dy0, t0b = q1.x * dy1 * dy1;
+          e00 = fmaf(dx0, fmaf(q0.z, dx0, t1a), t0a); e01 = fmaf(dx1, fmaf(q0.z, dx1, t1a), t0a);
+          e10 = fmaf(dx0, fmaf(q0.z, dx0, t1b), t0b); e11 = fmaf(dx1, fmaf(q0.z, dx1, t1b), t0b);
+        } else {
+          const f2 dx2 = add2(px2, pk(q0.x, q0.x));
+          const f2 dy2 = add2(py2, pk(q0.y, q0.y));
+          const f2 t1 = mul2(pk(q0.w, q0.w), dy2);
+          const f2 t0 = mul2(mul2(pk(q1.x, q1.x), dy2), dy2);
+          float t1l, t1h, t0l, t0h;
+          upk(t1, t1l, t1h);
+          upk(t0, t0l, t0h);
+          if (KIND == MIX2x2_SCOLEXP) {
+            float dx0, dx1;
+            upk(dx2, dx0, dx1);
+            e00 = fmaf(dx0, fmaf(q0.z, dx0, t1l), t0l); e01 = fmaf(dx1, fmaf(q0.z, dx1, t1l), t0l);
+            e10 = fmaf(dx0, fmaf(q0.z, dx0, t1h), t0h); e11 = fmaf(dx1, fmaf(q0.z, dx1, t1h), t0h);
+          } else {
+            const f2 e0 = fma2(dx2, fma2(pk(q0.z, q0.z), dx2, pk(t1l, t1l)), pk(t0l, t0l));
+            const f2 e1 = fma2(dx2, fma2(pk(q0.z, q0.z), dx2, pk(t1h, t1h)), pk(t0h, t0h));
+            upk(e0, e00, e01);
+            upk(e1, e10, e11);
+          }
+        }
+        const float v00 = ex2(e00), v01 = ex2(e01), v10 = ex2(e10), v11 = ex2(e11);
+        c[0] = fmaf(v00, q1.y, c[0]); c[1] = fmaf(v00, q1.z, c[1]); c[2] = fmaf(v00, q1.w, c[2]);
+        c[3] = fmaf(v01, q1.y, c[3]); c[4] = fmaf(v01, q1.z, c[4]); c[5] = fmaf(v01, q1.w, c[5]);
+        c[6] = fmaf(v10, q1.y, c[6]); c[7] = fmaf(v10, q1.z, c[7]); c[8] = fmaf(v10, q1.w, c[8]);
+        c[9] = fmaf(v11, q1.y, c[9]); c[10] = fmaf(v11, q1.z, c[10]); c[11] = fmaf(v11, q1.w, c[11]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) a0 += c[i];
   } else if (KIND == MIX2x2_NOCOL) {
     const float py0 = seed * lane, py1 = py0 + seed;
     const f2 px2 = pk(seed * (lane & 3), seed * (lane & 3) + seed), py2 = pk(py0, py1);
@@ -251,7 +299,7 @@ int main() {
     run<FFMA>(warps); run<FFMA2>(warps); run<MUFU>(warps); run<SHFL>(warps);
     run<LDS128_SAME>(warps); run<LDS128_HALF>(warps); run<LDS128_QUARTER>(warps); run<LDS128_EIGHTH>(warps);
     run<LDS128_LANE>(warps); run<LDS64_SAME>(warps); run<LDS32_SAME>(warps);
-    run<MIX1x2>(warps); run<MIX2x2>(warps); run<MIX2x2_NOCOL>(warps); run<MIX_MMA>(warps); run<FFMA2_BCAST>(warps);
+    run<MIX1x2>(warps); run<MIX2x2>(warps); run<MIX2x2_NOCOL>(warps); run<MIX_MMA>(warps); run<FFMA2_BCAST>(warps); run<MIX2x2_SCOL>(warps); run<MIX2x2_SCOLEXP>(warps); run<MIX2x2_SCALAR>(warps);
   }
   return 0;
 }
