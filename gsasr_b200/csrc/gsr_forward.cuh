@@ -1,23 +1,27 @@
-// gsr_forward.cuh -- forward raster kernel (sm_100a).
+// gsr_forward.cuh -- forward raster kernels (sm_100a).
 //
-// Replaces _gs_render_cuda (utils/gs_cuda_dmax/gs.cu:7-64; utils/gs_cuda/gs.cu:9-61).
+// Replace _gs_render_cuda (utils/gs_cuda_dmax/gs.cu:7-64; utils/gs_cuda/gs.cu:9-61).
 // The reference scatters: one thread per Gaussian, three global atomics per (Gaussian,pixel).
-// Here the image is cut into 32x32 tiles, one CTA per tile, 16 warps each owning an 8x8 region
-// (two horizontally adjacent pixels per lane, accumulated in registers, written once).
+// Here pixels are gathered: accumulators live in registers and every pixel is written once.
 //
-// Per CTA, in rounds of at most GSR_FWD_CAP candidates:
-//   stage A  (warp-private, no CTA barrier inside)
-//     pass 1  every warp takes a contiguous slice of the round's candidates -- Gaussians of the
-//             home bins within reach of the tile (contiguous runs of the sorted arrays, one run
-//             per bin row) plus the "large" list -- four per lane, tests cull box vs tile and
-//             streams the 32 B records of the hits into its private shared-memory segment with
-//             cp.async (LDGSTS; no register staging);
-//     pass 2  one lane per hit: ellipse-vs-region mask (gsr_region_mask); hits that touch at
-//             least one region are appended to the CTA-wide scan list (one atomic per warp).
-//   stage C  (one warp per region)  ballot-scan the list 32 entries at a time; per Gaussian that
-//            touches the region: 2 LDS.128 (broadcast), then per pixel 1 FADD + 2 FFMA +
-//            MUFU.EX2 + 3 FFMA.  Gaussians whose dmax window binds take a second, predicated loop.
-// The bound is the MUFU pipe (16 ex2/clk/SM) and FP32 issue: see DESIGN.md.
+//   gsr_forward_region_kernel  (the fast path, second half of this file)  streams the per-region
+//       buckets built by gsr_region_build_kernel: half a warp per 8x8-pixel region, a 2x2 pixel block
+//       per lane, persistent independent warps, two-deep cp.async prefetch.  See its own comment.
+//   gsr_forward_bins_kernel    (the fallback, runs when a bucket overflowed)  finds a tile's candidates
+//       at run time.  The image is cut into 32x16 tiles, one CTA per tile (persistent over tiles), 8 warps
+//       each owning an 8x8 region (two horizontally adjacent pixels per lane).  Per tile, in rounds of
+//       at most GSR_FWD_CAP candidates:
+//         stage A  (warp-private, no CTA barrier inside)
+//           pass 1  every warp takes a slice of the round's candidates -- Gaussians of the home bins
+//                   within reach of the tile (contiguous runs of the sorted arrays, one run per bin
+//                   row) plus the "large" list -- tests cull box vs tile and streams the 32 B records
+//                   of the hits into its private shared-memory segment with cp.async;
+//           pass 2  one lane per hit: ellipse-vs-region mask (gsr_region_mask); hits are appended to
+//                   the per-(producer warp, region) lists (ranks from ballots, no atomics);
+//         stage C  (one warp per region)  walks the lists left for its region: per Gaussian 2 LDS.128
+//                  (broadcast), FADD + 3 FMUL, FADD2, 2 FFMA2, 2 MUFU.EX2, 3 FFMA2.  Gaussians whose
+//                  dmax window binds take the predicated evaluation.
+// Both are bound by the MUFU pipe (16 ex2/clk/SM): see DESIGN.md.
 #pragma once
 #include "gsr_prepass.cuh"
 

@@ -4,12 +4,13 @@
 //   T1 gsr_region_build_kernel  per Gaussian: exact dmax window /\ k-sigma box -> cull box, raster
 //                               record (written in input order); then for every 8x8-pixel region
 //                               the ellipse touches a 4-byte entry {index | binds << 31} is appended
-//                               to the region's bucket (warp-cooperative: one atomic per
-//                               (warp, region), 32 reservations in flight together).
-//   Every region owns a fixed-capacity bucket (16 N / regions + 32 entries: GSASR emits its Gaussians
+//                               to the region's bucket (small persistent CTAs collect their entries
+//                               per region in shared memory and reserve bucket slots with one global
+//                               atomic per (CTA, region); a warp-ballot path serves incoherent input).
+//   Every region owns a fixed-capacity bucket (40 N / regions + 32 entries: GSASR emits its Gaussians
 //   on a regular grid, utils/fea2gs.py:553-563, so the load per region is uniform); an entry that
 //   does not fit raises the overflow flag and the forward falls back to the home-bin pipeline.
-//   The forward kernel then needs no culling at all: one warp per region streams its bucket.
+//   The forward kernel then needs no culling at all: half a warp per region streams its bucket.
 //
 // Home-bin pipeline (backward; forward fallback when the tile lists overflow their capacity):
 //   K1 gsr_bin_kernel     per Gaussian: cull box, home bin, rank inside the bin (atomic), reach.
