@@ -15,6 +15,12 @@
  *   gsr_frontend_forward  <-  activations + unit mapping + render + HWC->CHW transpose
  *                             utils/gaussian_splatting.py:119-131,158-217
  *   gsr_frontend_backward <-  autograd of the same chain down to the raw (N,9) head output
+ *   gsr_*_batch_uniform   <-  the same per-sample loop for a batch of ONE shape, in one launch each way
+ *   gsr_forward_band /    <-  (new) rows [row0, row0+rows) of one image: a single large render split
+ *   gsr_backward_band         over several GPUs
+ *   gsr_forward_window    <-  (new) the tile buffer + paste pass of utils/split_and_joint_image.py:160-227:
+ *                             the kernel writes a tile's pixels straight into the (possibly remote) canvas
+ *   GSR_FLAG_U8           <-  the clamp / x255 / round / uint8 post-processing of inference_paper.py:136-138
  *
  * Conventions (all entry points):
  *   - plain pointers and sizes only; all pointers are DEVICE pointers unless named *_host;

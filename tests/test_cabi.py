@@ -164,3 +164,20 @@ def test_band_rows_and_tile_regions_need_no_gpu():
     assert len(regs) == 9 and all(1 <= len(r) <= 8 for r in regs)
     area = sum((y1 - y0) * (x1 - x0) for r in regs for y0, y1, x0, x1 in r)
     assert area == plan.sr_h * plan.sr_w       # integer scale: the regions tile the whole canvas
+
+
+@pytest.mark.parametrize("lang,compiler", [("c", "gcc"), ("c++", "g++")])
+def test_public_headers_compile_as_c_and_cpp(lang, compiler, tmp_path):
+    """include/*.h are plain C declarations (no torch / CUDA types): they must compile on their own."""
+    import shutil
+    import subprocess
+
+    if shutil.which(compiler) is None:
+        pytest.skip(f"{compiler} not available")
+    src = tmp_path / ("t.c" if lang == "c" else "t.cpp")
+    src.write_text('#include "gsraster.h"\n#include "gsraster_test.h"\n'
+                   'int main(void) { gsr_window w; gsr_sample s; (void)w; (void)s; '
+                   'return gsr_version() < 0; }\n')
+    r = subprocess.run([compiler, "-x", lang, "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
