@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(GSR_FWD_THREADS, GSR_CFG_MIN_CTAS) gsr_forward
 // the warp's units -- the bucket lengths of the next two units are requested a unit ahead -- so the
 // count -> entry -> record dependency chain is never waited for after the prologue.  Trip counts are
 // rounded up to a multiple of 4 with null records, so the evaluation loop is made of fully unrolled
-// blocks with immediate shared-memory offsets.  Window-binding Gaussians (entry bit 31) also bring their
+// blocks (16, 8, 4 records) with immediate shared-memory offsets.  Window-binding Gaussians (entry bit 31) also bring their
 // cull box and are evaluated with the exact per-pixel inclusion test.
 constexpr int GSR_FR_WARPS = 8;
 constexpr int GSR_FR_THREADS = 32 * GSR_FR_WARPS;
@@ -593,6 +593,14 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
     const int trip = min(CH, ntripA - c0);  // <= 0 for an empty pair
     if ((slow_a | slow_b) == 0) {
       int j = 0;
+      for (; j + 16 <= trip; j += 16) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const uint32_t a = buf + j * 32 + k * 32;
+          gsr_eval_quad<false>(a + gsr_fr_swz(k), a + (gsr_fr_swz(k) ^ 16u), nx2, ny2, true, true, true, true,
+                               r0, g0, b0, r1, g1, b1);
+        }
+      }
       for (; j + 8 <= trip; j += 8) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
