@@ -67,6 +67,11 @@ SIGNATURES = {
     "gsr_backward_batch_uniform": (_i, [_vp] * 7 + [_i, _i, _i, _i, _i, _f, _f, _u32, _vp, _sz, _vp]),
     "gsr_frontend_forward_batch_uniform": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _sz, _vp]),
     "gsr_frontend_backward_batch_uniform": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _sz, _vp]),
+    "gsr_workspace_bytes_batch_padded": (_sz, [_i, _i, _i, _i]),
+    "gsr_forward_batch_padded": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_f), _f, _f,
+                                      _u32, _vp, _sz, _vp]),
+    "gsr_backward_batch_padded": (_i, [_vp] * 7 + [_i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_f), _f, _f, _u32,
+                                                  _vp, _sz, _vp]),
     "gsr_frontend_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _vp, _sz, _vp]),
     "gsr_frontend_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _vp, _sz, _vp]),
 }

@@ -70,6 +70,8 @@ struct GsrBwdArgs {
   int h, w, nbx, nby, nb;
   int tiles_x, tiles_y;
   uint32_t flags;
+  const GsrBDesc* bdesc;  // padded batch (ragged != 0): records and moments are in canvas coordinates
+  int bn, ragged;
 };
 
 __device__ __forceinline__ float gsr_warp_sum(float v) {
@@ -226,15 +228,25 @@ __device__ __forceinline__ void gsr_bwd_chain(const float* t, const GsrBwdArgs& 
   const float sgx = __ldg(p.sigmas + 3 * (size_t)id + 0);
   const float sgy = __ldg(p.sigmas + 3 * (size_t)id + 1);
   const float rho = __ldg(p.sigmas + 3 * (size_t)id + 2);
-  const float Sx = t[3], Sy = t[4], Sxx = t[5], Sxy = t[6], Syy = t[7];
+  const float Sx = t[3], Sy = t[4], Sxx = t[5], Syy = t[7];
+  float Sxy = t[6];
   const float a = a0.z, b = a0.w, c = a1.x;
   const float iL = 0.6931471805599453f;  // 1 / log2(e)
-  const float gx = -(2.0f * a * Sx + b * Sy) * iL;
-  const float gy = -(2.0f * c * Sy + b * Sx) * iL;
+  float gx = -(2.0f * a * Sx + b * Sy) * iL;
+  float gy = -(2.0f * c * Sy + b * Sx) * iL;
+  float sxy_own = Sxy;  // sum u dx dy in the sample's OWN units (the explicit Sxy term of d/drho)
+  if (p.ragged) {
+    // padded batch: d_own = (ax, ay) * d_canvas.  The products conic x moment are invariant (so are the
+    // sigma gradients and Q); the centre gradients and the bare moment are not.
+    const GsrBDesc d = p.bdesc[id / p.bn];
+    gx = (float)((double)gx / d.ax);
+    gy = (float)((double)gy / d.ay);
+    sxy_own = (float)((double)Sxy * d.ax * d.ay);
+  }
   const float gsx = -(b * Sxy + 2.0f * a * Sxx) * iL / sgx;
   const float gsy = -(b * Sxy + 2.0f * c * Syy) * iL / sgy;
   const double Q = (double)a * Sxx + (double)b * Sxy + (double)c * Syy;
-  const float grho = (float)((2.0 * (double)rho * Q * (double)iL + (double)Sxy / ((double)sgx * sgy)) /
+  const float grho = (float)((2.0 * (double)rho * Q * (double)iL + (double)sxy_own / ((double)sgx * sgy)) /
                              (1.0 - (double)rho * rho));
   float* os = p.g_sigmas + 3 * (size_t)id;
   float* oc = p.g_coords + 2 * (size_t)id;

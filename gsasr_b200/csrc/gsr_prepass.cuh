@@ -26,6 +26,17 @@
 #include "gsr_common.cuh"
 struct gsr_window;
 
+// One sample of a padded (ragged) batch: its own image size and window inside the common (hmax, wmax)
+// block of the stacked canvas, and the ratios between the canvas' and its own coordinate normalisation
+// (pixel i sits at 2i/(n-1)-1 for an n-pixel axis, so px_own = ax * px_canvas + (ax - 1), ax = (W-1)/(w-1)).
+struct GsrBDesc {
+  int h, w;
+  float dmax;
+  int pad;
+  double ax, ay;  // double: a float ratio would move the centres by 1e-4 pixel
+};
+constexpr int GSR_BDESC_MAX = 1024;  // samples per stacked launch
+
 constexpr int GSR_STAT_EXT_X = 0, GSR_STAT_EXT_Y = 1, GSR_STAT_OVERFLOW = 2, GSR_STAT_ENTRIES = 3;
 // bucket capacity per region = 40 * N / regions + 32: a Gaussian of the x4 head touches 6.8 regions on
 // average, one of the x8 head 23 (5 sigma = 33 px); 4 bytes per slot
@@ -58,6 +69,8 @@ struct GsrWorkspace {
   int hf, row0;      // row-band view: the image is rows [row0, row0 + h) of an hf-row image (hf = 0: whole)
   const struct gsr_window* win;  // host-side only: destination window of gsr_forward_window (NULL: plain image)
   int bn, bhs;       // uniform batch: the image is a stack of samples, bhs rows each, bn Gaussians each (0: single)
+  GsrBDesc* bdesc;   // GSR_BDESC_MAX descriptors; read by the kernels only when `ragged`
+  int ragged;        // padded batch: per-sample (h, w, dmax) from bdesc, records rescaled to canvas coordinates
 };
 
 constexpr int GSR_SCAN_CHUNK = 4096;  // counters per scan CTA (1024 threads x 4)
@@ -97,6 +110,7 @@ static inline GsrWorkspace gsr_carve(void* base, int s, int h, int w) {
   ws.bin_off = (int*)take(((size_t)ws.nb + 2) * sizeof(int));
   ws.px_tab = (float*)take((size_t)w * sizeof(float));
   ws.py_tab = (float*)take((size_t)h * sizeof(float));
+  ws.bdesc = (GsrBDesc*)take((size_t)GSR_BDESC_MAX * sizeof(GsrBDesc));
   ws.box_tmp = (uint2*)take(sn * sizeof(uint2));
   ws.keyrank = (int2*)take(sn * sizeof(int2));
   ws.rec = (GsrRec*)take(sn * sizeof(GsrRec));
@@ -107,6 +121,7 @@ static inline GsrWorkspace gsr_carve(void* base, int s, int h, int w) {
   ws.row0 = 0;
   ws.bn = 0;
   ws.bhs = 0;
+  ws.ragged = 0;
   ws.win = nullptr;
   return ws;
 }
@@ -114,6 +129,54 @@ static inline GsrWorkspace gsr_carve(void* base, int s, int h, int w) {
 // A kernel of the path not taken returns at once: guard == nullptr means "always run".
 __device__ __forceinline__ bool gsr_guard_skip(const int* guard, int want) {
   return guard != nullptr && *(const volatile int*)guard != want;
+}
+
+
+// What a Gaussian's sample looks like: the image it is set up in (hl x wl, dmax), the row offset of its
+// block in the stacked canvas, and the coordinate ratios of a padded batch (1 otherwise).
+struct GsrSampleView {
+  int hl, wl, yoff;
+  float dmax;
+  double ax, ay;
+  const float* px_tab;
+  const float* py_tab;
+};
+__device__ __forceinline__ GsrSampleView gsr_sample_view(const GsrWorkspace& ws, int i, int h, int w, float dmax) {
+  GsrSampleView v;
+  v.hl = ws.bn > 0 ? ws.bhs : h;
+  v.wl = w;
+  v.yoff = ws.bn > 0 ? (i / ws.bn) * ws.bhs : 0;
+  v.dmax = dmax;
+  v.ax = v.ay = 1.0;
+  v.px_tab = ws.px_tab;
+  v.py_tab = ws.py_tab;
+  if (ws.ragged) {
+    const int b = i / ws.bn;
+    const GsrBDesc d = ws.bdesc[b < GSR_BDESC_MAX ? b : GSR_BDESC_MAX - 1];  // (threads past s: unused)
+    v.hl = d.h;
+    v.wl = d.w;
+    v.dmax = d.dmax;
+    v.ax = d.ax;
+    v.ay = d.ay;
+    v.px_tab = v.py_tab = nullptr;  // the canvas' tables are not the sample's: evaluate the rule directly
+  }
+  return v;
+}
+// Padded batch: a sample whose width / height is not a multiple of the region size shares its last regions
+// with padding pixels, which must stay 0: Gaussians whose box reaches those regions take the exact per-pixel
+// box test.
+__device__ __forceinline__ bool gsr_edge_binds(const GsrWorkspace& ws, const GsrSampleView& v, const GsrSetup& st) {
+  return ws.ragged && (((v.wl % GSR_REGION) != 0 && st.x1 / GSR_REGION == (v.wl - 1) / GSR_REGION) ||
+                       ((v.hl % GSR_REGION) != 0 && (st.y1 - v.yoff) / GSR_REGION == (v.hl - 1) / GSR_REGION));
+}
+// Record in CANVAS coordinates: d_own = a_ * d_canvas, so x_c = (x + 1) / ax - 1 and the conic scales.
+__device__ __forceinline__ void gsr_rescale_rec(GsrRec& r, const GsrSampleView& v) {
+  if (v.ax == 1.0 && v.ay == 1.0) return;
+  r.x = (float)(((double)r.x + 1.0) / v.ax - 1.0);
+  r.y = (float)(((double)r.y + 1.0) / v.ay - 1.0);
+  r.a = (float)((double)r.a * v.ax * v.ax);
+  r.b = (float)((double)r.b * v.ax * v.ay);
+  r.c = (float)((double)r.c * v.ay * v.ay);
 }
 
 __device__ __forceinline__ void gsr_bin_one(const float* __restrict__ sigmas,
@@ -128,16 +191,18 @@ __device__ __forceinline__ void gsr_bin_one(const float* __restrict__ sigmas,
   const float cr = __ldg(colors + 3 * (size_t)i + 0);
   const float cg = __ldg(colors + 3 * (size_t)i + 1);
   const float cb = __ldg(colors + 3 * (size_t)i + 2);
-  // uniform batch: set up in the sample's own image, then move to its block of rows of the stack
-  const int yoff = ws.bn > 0 ? (i / ws.bn) * ws.bhs : 0;
-  GsrSetup st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, ws.bn > 0 ? ws.bhs : h, w, dmax, ksigma, ws.px_tab,
-                          ws.py_tab, ws.hf, ws.row0);
+  // batches: set up in the sample's own image, then move to its block of rows of the stack
+  const GsrSampleView sv = gsr_sample_view(ws, i, h, w, dmax);
+  const int yoff = sv.yoff;
+  GsrSetup st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, sv.hl, sv.wl, sv.dmax, ksigma, sv.px_tab, sv.py_tab, ws.hf,
+                          ws.row0);
   if (st.live) {
     const GsrRec r = gsr_make_rec(sx, sy, rho, x, y, cr, cg, cb);
     if (!(gsr_finite(r.a) && gsr_finite(r.b) && gsr_finite(r.c))) st.live = false;
     st.y0 += yoff;
     st.y1 += yoff;
     st.bin_y += yoff / GSR_BIN;
+    if (gsr_edge_binds(ws, sv, st)) st.binds = true;
   }
   int key = -1, rank = 0;
   if (st.live) {
@@ -277,7 +342,8 @@ __device__ __forceinline__ void gsr_scatter_one(const float* __restrict__ sigmas
   const float cr = __ldg(colors + 3 * (size_t)i + 0);
   const float cg = __ldg(colors + 3 * (size_t)i + 1);
   const float cb = __ldg(colors + 3 * (size_t)i + 2);
-  const GsrRec r = gsr_make_rec(sx, sy, rho, x, y, cr, cg, cb);
+  GsrRec r = gsr_make_rec(sx, sy, rho, x, y, cr, cg, cb);
+  if (ws.ragged) gsr_rescale_rec(r, gsr_sample_view(ws, i, 0, 0, 0.f));  // padded batch: canvas coordinates
   float4* dr = reinterpret_cast<float4*>(ws.rec + dst);
   dr[0] = make_float4(r.x, r.y, r.a, r.b);
   dr[1] = make_float4(r.c, r.r, r.g, r.bl);
@@ -456,8 +522,11 @@ gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restric
     const int i = chunk * GSR_RB_THREADS + tid;
     const float sx = pf[0], sy = pf[1], rho = pf[2], x = pf[3], y = pf[4], cr = pf[5], cg = pf[6], cb = pf[7];
     request(chunk + gridDim.x);
-    // uniform batch: set up in the sample's own hl-row image, then move to its block of rows of the stack
-    const int yoff = ws.bn > 0 ? (i / ws.bn) * ws.bhs : 0, hl = ws.bn > 0 ? ws.bhs : h;
+    // batches: set up in the sample's own image (hl x wl, its dmax), then move to its block of rows of the
+    // stack; a padded batch stores the record rescaled to the canvas' coordinate normalisation, the raw
+    // one (r) keeps describing the ellipse in the sample's own pixels for the region masks
+    const GsrSampleView sv = gsr_sample_view(ws, i, h, w, dmax);
+    const int yoff = sv.yoff, hl = sv.hl, wl = sv.wl;
     GsrSetup st;
     st.live = false;
     st.binds = false;
@@ -466,17 +535,20 @@ gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restric
     GsrRec r;
     r.x = r.y = r.a = r.b = r.c = r.r = r.g = r.bl = 0.f;
     if (i < s) {
-      st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, hl, w, dmax, ksigma, ws.px_tab, ws.py_tab, ws.hf, ws.row0);
+      st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, hl, wl, sv.dmax, ksigma, sv.px_tab, sv.py_tab, ws.hf, ws.row0);
       if (st.live) {
         r = gsr_make_rec(sx, sy, rho, x, y, cr, cg, cb);
         if (!(gsr_finite(r.a) && gsr_finite(r.b) && gsr_finite(r.c))) st.live = false;
         st.y0 += yoff;
         st.y1 += yoff;
+        if (gsr_edge_binds(ws, sv, st)) st.binds = true;
       }
       if (st.live) {
+        GsrRec rs = r;
+        gsr_rescale_rec(rs, sv);
         float4* dr = reinterpret_cast<float4*>(ws.rec_in + i);
-        dr[0] = make_float4(r.x, r.y, r.a, r.b);
-        dr[1] = make_float4(r.c, r.r, r.g, r.bl);
+        dr[0] = make_float4(rs.x, rs.y, rs.a, rs.b);
+        dr[1] = make_float4(rs.c, rs.r, rs.g, rs.bl);
         if (st.binds) ws.box_in[i] = gsr_box_pack(st.x0, st.x1, st.y0, st.y1, true);
       }
     }
@@ -508,12 +580,12 @@ gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restric
     const bool any_live = B1 >= B0 && C1 >= C0;  // CTA-uniform
     const int NC = C1 - C0 + 1, NR = any_live ? NC * (B1 - B0 + 1) : 0;
     if (any_live && (long long)NC * (B1 - B0 + 1) > GSR_RB_MAXR) {
-      gsr_warp_append(st.live, r, entry, st.x0, st.x1, st.y0, st.y1, hl, w, ws.nrx, ecut, ws.reg_count, ws.entries,
+      gsr_warp_append(st.live, r, entry, st.x0, st.x1, st.y0, st.y1, hl, wl, ws.nrx, ecut, ws.reg_count, ws.entries,
                       ws.reg_cap, overflow, ws.hf, ws.row0, yoff);
     } else if (any_live) {
       // ---- collect: one shared-memory atomic per (Gaussian, region)
       if (st.live) {
-        GsrEllipse e = gsr_ellipse(r, hl, w, ws.hf, ws.row0);
+        GsrEllipse e = gsr_ellipse(r, hl, wl, ws.hf, ws.row0);
         e.cy += (float)yoff;
         for (int b = b0; b <= b1; ++b) {
           int ya = b * GSR_REGION, yb = ya + GSR_REGION - 1, xl, xh;

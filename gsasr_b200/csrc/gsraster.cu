@@ -233,6 +233,9 @@ static int gsr_launch_backward(const GsrWorkspace& ws, const float* sigmas, cons
   a.tiles_x = (w + GSR_BWD_TILE - 1) / GSR_BWD_TILE;
   a.tiles_y = (h + GSR_BWD_TILE - 1) / GSR_BWD_TILE;
   a.flags = flags;
+  a.bdesc = ws.bdesc;
+  a.bn = ws.bn;
+  a.ragged = ws.ragged;
   GSR_CUDA(cudaFuncSetAttribute(gsr_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(GsrBwdSmem)));
   const int grid = a.tiles_x * a.tiles_y + (s + GSR_BWD_LARGE_CHUNK - 1) / GSR_BWD_LARGE_CHUNK;
@@ -249,7 +252,8 @@ static bool gsr_band_ok(int h, int hf, int row0) {
 static int gsr_forward_impl(const float* sigmas, const float* coords, const float* colors, float* img,
                             int s, int h, int w, int c, int hf, int row0, float dmax, float ksigma,
                             uint32_t flags, void* workspace, size_t workspace_bytes, void* stream,
-                            int bn = 0, int bhs = 0, const gsr_window* win = nullptr) {
+                            int bn = 0, int bhs = 0, const gsr_window* win = nullptr,
+                            const GsrBDesc* bdesc_host = nullptr) {
   if (c != 3) return GSR_ERR_BAD_CHANNELS;
   if (!gsr_dims_ok(s, h, w) || !gsr_band_ok(h, hf, row0)) return GSR_ERR_BAD_SHAPE;
   if (!img || (s > 0 && (!sigmas || !coords || !colors))) return GSR_ERR_NULL_POINTER;
@@ -265,6 +269,10 @@ static int gsr_forward_impl(const float* sigmas, const float* coords, const floa
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const float keff = gsr_effective_ksigma(ksigma);
+  if (bdesc_host) {  // padded batch: per-sample descriptors (pageable host memory: staged before the call returns)
+    ws.ragged = 1;
+    GSR_CUDA(cudaMemcpyAsync(ws.bdesc, bdesc_host, (size_t)(s / bn) * sizeof(GsrBDesc), cudaMemcpyHostToDevice, st));
+  }
   rc = gsr_clear_and_tables(h, w, ws, st);
   if (rc) return rc;
   ws.win = win;
@@ -277,7 +285,8 @@ static int gsr_backward_impl(const float* sigmas, const float* coords, const flo
                              const float* grads, float* grads_sigmas, float* grads_coords,
                              float* grads_colors, int s, int h, int w, int c, int hf, int row0,
                              float dmax, float ksigma, uint32_t flags, void* workspace,
-                             size_t workspace_bytes, void* stream, int bn = 0, int bhs = 0) {
+                             size_t workspace_bytes, void* stream, int bn = 0, int bhs = 0,
+                             const GsrBDesc* bdesc_host = nullptr) {
   if (c != 3) return GSR_ERR_BAD_CHANNELS;
   if (!gsr_dims_ok(s, h, w) || !gsr_band_ok(h, hf, row0)) return GSR_ERR_BAD_SHAPE;
   if (!grads || (s > 0 && (!sigmas || !coords || !colors || !grads_sigmas || !grads_coords ||
@@ -292,6 +301,10 @@ static int gsr_backward_impl(const float* sigmas, const float* coords, const flo
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const float keff = gsr_effective_ksigma(ksigma);
+  if (bdesc_host) {
+    ws.ragged = 1;
+    GSR_CUDA(cudaMemcpyAsync(ws.bdesc, bdesc_host, (size_t)(s / bn) * sizeof(GsrBDesc), cudaMemcpyHostToDevice, st));
+  }
   rc = gsr_clear_and_tables(h, w, ws, st);
   if (rc) return rc;
   rc = gsr_run_bins(sigmas, coords, colors, s, h, w, dmax, keff, ws, nullptr, 0, st);
@@ -556,6 +569,101 @@ extern "C" int gsr_frontend_backward(const float* raw, const float* mapped, cons
   gsr_unmap_kernel<<<(s + 255) / 256, 256, 0, st>>>(raw, gm, gm + 3 * (size_t)s, gm + 5 * (size_t)s,
                                                     grad_raw, s, h, w, step_size);
   GSR_CUDA(cudaGetLastError());
+  return GSR_OK;
+}
+
+// ---- padded (ragged) batches: samples of DIFFERENT sizes in one launch ---------------------------
+// The training loop renders every sample at its own scale (gsasr_model.py:191-233: sr_size=gt_size[i])
+// and pads the results to the largest size.  Here the samples -- s_per Gaussians each -- are rendered into
+// the (batch, hmax, wmax, 3) padded buffer directly, stacked like a uniform batch: every Gaussian is set
+// up in its own sample's (h_b, w_b, dmax_b) image, and its record is rescaled to the canvas' coordinate
+// normalisation (d_own = (W-1)/(w_b-1) * d_canvas), so the raster kernels need nothing per sample.
+static int gsr_padded_group(int batch, int hmax) {
+  int g = GSR_MAX_DIM / hmax;
+  if (g > GSR_BDESC_MAX) g = GSR_BDESC_MAX;
+  if (g < 1 || batch < 1) return 1;
+  const int launches = (batch + g - 1) / g;
+  return (batch + launches - 1) / launches;
+}
+
+static int gsr_padded_check(int batch, int s_per, int hmax, int wmax, const int* hw_host) {
+  if (batch < 0) return GSR_ERR_BAD_ARGUMENT;
+  if (!gsr_dims_ok(s_per, hmax, wmax) || hmax % GSR_REGION != 0 || (long long)batch * s_per > 0x7fffffffLL)
+    return GSR_ERR_BAD_SHAPE;
+  if (batch > 0 && !hw_host) return GSR_ERR_NULL_POINTER;
+  for (int b = 0; b < batch; ++b)
+    if (hw_host[2 * b] < 2 || hw_host[2 * b] > hmax || hw_host[2 * b + 1] < 2 || hw_host[2 * b + 1] > wmax)
+      return GSR_ERR_BAD_SHAPE;
+  return GSR_OK;
+}
+
+static void gsr_padded_fill(GsrBDesc* d, int nb, int hmax, int wmax, const int* hw, const float* dmax_host, float dmax) {
+  for (int b = 0; b < nb; ++b) {
+    d[b].h = hw[2 * b];
+    d[b].w = hw[2 * b + 1];
+    d[b].dmax = dmax_host ? dmax_host[b] : dmax;
+    d[b].pad = 0;
+    d[b].ax = (double)(wmax - 1) / (double)(hw[2 * b + 1] - 1);
+    d[b].ay = (double)(hmax - 1) / (double)(hw[2 * b] - 1);
+  }
+}
+
+extern "C" size_t gsr_workspace_bytes_batch_padded(int batch, int s_per, int hmax, int wmax) {
+  if (batch < 0 || !gsr_dims_ok(s_per, hmax, wmax) || hmax % GSR_REGION != 0) return 0;
+  if (batch == 0) return 256;
+  const int g = gsr_padded_group(batch, hmax);
+  if ((long long)g * s_per > 0x7fffffffLL) return 0;
+  return gsr_workspace_bytes(g * s_per, g * hmax, wmax);
+}
+
+extern "C" int gsr_forward_batch_padded(const float* sigmas, const float* coords, const float* colors,
+                                        float* imgs, int batch, int s_per, int hmax, int wmax,
+                                        const int* hw_host, const float* dmax_host, float dmax,
+                                        float ksigma, uint32_t flags, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  int rc = gsr_padded_check(batch, s_per, hmax, wmax, hw_host);
+  if (rc) return rc;
+  if (flags & (GSR_FLAG_CHW | GSR_FLAG_U8)) return GSR_ERR_BAD_ARGUMENT;
+  if (batch > 0 && !imgs) return GSR_ERR_NULL_POINTER;
+  const int g = gsr_padded_group(batch, hmax);
+  GsrBDesc desc[GSR_BDESC_MAX];
+  for (int b0 = 0; b0 < batch; b0 += g) {
+    const int nb = batch - b0 < g ? batch - b0 : g;
+    const size_t go = (size_t)b0 * s_per;
+    gsr_padded_fill(desc, nb, hmax, wmax, hw_host + 2 * b0, dmax_host ? dmax_host + b0 : nullptr, dmax);
+    rc = gsr_forward_impl(sigmas ? sigmas + 3 * go : nullptr, coords ? coords + 2 * go : nullptr,
+                          colors ? colors + 3 * go : nullptr, imgs + (size_t)b0 * hmax * wmax * 3, nb * s_per,
+                          nb * hmax, wmax, 3, 0, 0, dmax, ksigma, flags, workspace, workspace_bytes, stream, s_per,
+                          hmax, nullptr, desc);
+    if (rc) return rc;
+  }
+  return GSR_OK;
+}
+
+extern "C" int gsr_backward_batch_padded(const float* sigmas, const float* coords, const float* colors,
+                                         const float* grads, float* grads_sigmas, float* grads_coords,
+                                         float* grads_colors, int batch, int s_per, int hmax, int wmax,
+                                         const int* hw_host, const float* dmax_host, float dmax,
+                                         float ksigma, uint32_t flags, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  int rc = gsr_padded_check(batch, s_per, hmax, wmax, hw_host);
+  if (rc) return rc;
+  if (flags & GSR_FLAG_CHW) return GSR_ERR_BAD_ARGUMENT;
+  if (batch > 0 && !grads) return GSR_ERR_NULL_POINTER;
+  const int g = gsr_padded_group(batch, hmax);
+  GsrBDesc desc[GSR_BDESC_MAX];
+  for (int b0 = 0; b0 < batch; b0 += g) {
+    const int nb = batch - b0 < g ? batch - b0 : g;
+    const size_t go = (size_t)b0 * s_per;
+    gsr_padded_fill(desc, nb, hmax, wmax, hw_host + 2 * b0, dmax_host ? dmax_host + b0 : nullptr, dmax);
+    rc = gsr_backward_impl(sigmas ? sigmas + 3 * go : nullptr, coords ? coords + 2 * go : nullptr,
+                           colors ? colors + 3 * go : nullptr, grads + (size_t)b0 * hmax * wmax * 3,
+                           grads_sigmas ? grads_sigmas + 3 * go : nullptr,
+                           grads_coords ? grads_coords + 2 * go : nullptr,
+                           grads_colors ? grads_colors + 3 * go : nullptr, nb * s_per, nb * hmax, wmax, 3, 0, 0,
+                           dmax, ksigma, flags, workspace, workspace_bytes, stream, s_per, hmax, desc);
+    if (rc) return rc;
+  }
   return GSR_OK;
 }
 

@@ -22,7 +22,7 @@ import torch
 from . import _lib
 
 __all__ = ["gs_render", "gs_render_backward", "gs_render_band", "gs_render_backward_band", "gs_render_batch",
-           "gs_render_backward_batch", "gs_render_window", "frontend_render_window", "gs_render_u8", "set_ksigma", "get_ksigma"]
+           "gs_render_backward_batch", "gs_render_batch_padded", "gs_render_backward_batch_padded", "gs_render_window", "frontend_render_window", "gs_render_u8", "set_ksigma", "get_ksigma"]
 
 _ksigma = float(os.environ.get("GSR_KSIGMA", "0"))  # 0 -> library default (GSR_DEFAULT_KSIGMA)
 
@@ -311,4 +311,80 @@ def gs_render_u8(sigmas, coords, colors, out_u8, s, h, w, dmax=float("inf"), *, 
         rc = L.gsr_forward(_ptr(sigmas), _ptr(coords), _ptr(colors), out_u8.data_ptr(), s, h, w, 3, float(dmax),
                            float(_ksigma if ksigma is None else ksigma), flags, ws.data_ptr(), ws.numel(),
                            torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)
+
+
+# ---- padded (ragged) batches: B samples of N Gaussians each, rendered at their OWN sizes into the
+# top-left corner of their slot of a (B, hmax, wmax, 3) buffer (the training loop's per-sample render +
+# F.pad, gsasr_model.py:191-233) in one set-up and one raster launch each way.  hmax % 8 == 0.
+def _sizes(sizes, b, hmax, wmax):
+    import ctypes
+
+    hw = (ctypes.c_int * (2 * b))()
+    if len(sizes) != b:
+        raise RuntimeError(f"sizes must list (h, w) for each of the {b} samples")
+    for i, (h, w) in enumerate(sizes):
+        hw[2 * i], hw[2 * i + 1] = int(h), int(w)
+    return hw
+
+
+def _dmaxes(dmax, b):
+    import ctypes
+
+    if isinstance(dmax, (int, float)):
+        return None, float(dmax)
+    arr = (ctypes.c_float * b)(*[float(v) for v in dmax])
+    return arr, 0.0
+
+
+def workspace_batch_padded(batch: int, s_per: int, hmax: int, wmax: int, device) -> torch.Tensor:
+    n = _lib.load().gsr_workspace_bytes_batch_padded(int(batch), int(s_per), int(hmax), int(wmax))
+    if n == 0:
+        raise RuntimeError(f"libgsraster: bad sizes batch={batch}, s={s_per}, hmax={hmax} (multiple of 8), wmax={wmax}")
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def gs_render_batch_padded(sigmas, coords, colors, rendered_imgs, sizes, dmax=float("inf"), *, ksigma=None,
+                           flags=0, workspace_buf=None):
+    L = _lib.load()
+    for t, n in ((sigmas, "sigmas"), (coords, "coords"), (colors, "colors"), (rendered_imgs, "rendered_imgs")):
+        _check_input(t, n)
+    b, s = int(sigmas.shape[0]), int(sigmas.shape[1])
+    hmax, wmax = int(rendered_imgs.shape[1]), int(rendered_imgs.shape[2])
+    _check_shape(sigmas, (b, s, 3), "sigmas")
+    _check_shape(coords, (b, s, 2), "coords")
+    _check_shape(colors, (b, s, 3), "colors")
+    _check_shape(rendered_imgs, (b, hmax, wmax, 3), "rendered_imgs")
+    hw = _sizes(sizes, b, hmax, wmax)
+    dm_arr, dm = _dmaxes(dmax, b)
+    with torch.cuda.device(sigmas.device):
+        ws = workspace_buf if workspace_buf is not None else workspace_batch_padded(b, s, hmax, wmax, sigmas.device)
+        rc = L.gsr_forward_batch_padded(_ptr(sigmas), _ptr(coords), _ptr(colors), rendered_imgs.data_ptr(), b, s, hmax,
+                                        wmax, hw, dm_arr, dm, float(_ksigma if ksigma is None else ksigma), int(flags),
+                                        ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc)
+
+
+def gs_render_backward_batch_padded(sigmas, coords, colors, grads, grads_sigmas, grads_coords, grads_colors, sizes,
+                                    dmax=float("inf"), *, ksigma=None, flags=0, workspace_buf=None):
+    L = _lib.load()
+    for t, n in ((sigmas, "sigmas"), (coords, "coords"), (colors, "colors"), (grads, "grads"),
+                 (grads_sigmas, "grads_sigmas"), (grads_coords, "grads_coords"), (grads_colors, "grads_colors")):
+        _check_input(t, n)
+    b, s = int(sigmas.shape[0]), int(sigmas.shape[1])
+    hmax, wmax = int(grads.shape[1]), int(grads.shape[2])
+    _check_shape(coords, (b, s, 2), "coords")
+    _check_shape(colors, (b, s, 3), "colors")
+    _check_shape(grads, (b, hmax, wmax, 3), "grads")
+    _check_shape(grads_sigmas, (b, s, 3), "grads_sigmas")
+    _check_shape(grads_coords, (b, s, 2), "grads_coords")
+    _check_shape(grads_colors, (b, s, 3), "grads_colors")
+    hw = _sizes(sizes, b, hmax, wmax)
+    dm_arr, dm = _dmaxes(dmax, b)
+    with torch.cuda.device(sigmas.device):
+        ws = workspace_buf if workspace_buf is not None else workspace_batch_padded(b, s, hmax, wmax, sigmas.device)
+        rc = L.gsr_backward_batch_padded(_ptr(sigmas), _ptr(coords), _ptr(colors), grads.data_ptr(), _ptr(grads_sigmas),
+                                         _ptr(grads_coords), _ptr(grads_colors), b, s, hmax, wmax, hw, dm_arr, dm,
+                                         float(_ksigma if ksigma is None else ksigma), int(flags), ws.data_ptr(),
+                                         ws.numel(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)

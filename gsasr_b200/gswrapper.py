@@ -78,3 +78,37 @@ def gaussiansplatting_render_batch(sigmas, coords, colors, image_size, dmax=100)
     h, w = image_size[:2]
     rendered = torch.zeros(sigmas.shape[0], h, w, 3, device=colors.device, dtype=torch.float32)
     return GSCUDABatch.apply(sigmas, coords, colors, rendered, dmax)
+
+
+class GSCUDABatchPadded(Function):
+    """Samples of different sizes in one launch: (B,N,·) parameters -> (B,hmax,wmax,3), sample b rendered at
+    sizes[b] = (h_b, w_b) into the top-left corner of its slot, zeros elsewhere (render + F.pad)."""
+
+    @staticmethod
+    def forward(ctx, sigmas, coords, colors, rendered_imgs, sizes, dmax=float("inf")):
+        ctx.save_for_backward(sigmas, coords, colors)
+        ctx.meta = (tuple((int(h), int(w)) for h, w in sizes), dmax)
+        GSWrapper.gs_render_batch_padded(sigmas, coords, colors, rendered_imgs, ctx.meta[0], dmax)
+        return rendered_imgs
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        sigmas, coords, colors = ctx.saved_tensors
+        sizes, dmax = ctx.meta
+        grads_sigmas = torch.zeros_like(sigmas)
+        grads_coords = torch.zeros_like(coords)
+        grads_colors = torch.zeros_like(colors)
+        GSWrapper.gs_render_backward_batch_padded(sigmas, coords, colors, grad_output.contiguous(), grads_sigmas,
+                                                  grads_coords, grads_colors, sizes, dmax)
+        return (grads_sigmas, grads_coords, grads_colors, None, None, None)
+
+
+def gaussiansplatting_render_batch_padded(sigmas, coords, colors, sizes, dmax=100, hmax=None, wmax=None):
+    """(B,N,3), (B,N,2), (B,N,3), sizes [(h_b, w_b)] -> (B,hmax,wmax,3); hmax defaults to the largest h_b
+    rounded up to a multiple of 8, wmax to the largest w_b."""
+    sigmas, coords, colors = sigmas.contiguous(), coords.contiguous(), colors.contiguous()
+    hmax = (max(int(h) for h, _ in sizes) + 7) // 8 * 8 if hmax is None else int(hmax)
+    wmax = max(int(w) for _, w in sizes) if wmax is None else int(wmax)
+    rendered = torch.zeros(sigmas.shape[0], hmax, wmax, 3, device=colors.device, dtype=torch.float32)
+    return GSCUDABatchPadded.apply(sigmas, coords, colors, rendered, sizes, dmax)

@@ -190,6 +190,25 @@ int gsr_backward_batch_uniform(const float* sigmas, const float* coords, const f
                                float ksigma, uint32_t flags, void* workspace, size_t workspace_bytes,
                                void* stream);
 
+/* Padded (ragged) batch: `batch` samples of s_per Gaussians each, rendered at their OWN sizes
+ * hw_host[2b] x hw_host[2b+1] (HOST array; 2 <= h_b <= hmax, 2 <= w_b <= wmax) and windows dmax_host[b]
+ * (HOST array, or NULL: `dmax` for all) into the top-left corner of their slot of the padded buffer
+ * imgs / grads (batch, hmax, wmax, 3) -- the training loop's per-sample render + F.pad to the largest
+ * size (gsasr_model.py:191-233) in one set-up and one raster launch each way.  hmax % 8 == 0.  Pixels of a
+ * slot outside its sample's image are written 0 (forward) / ignored (backward).  The dmax inclusion set of
+ * every sample is exact; values differ from `batch` separate calls by fp32 round-off only (~1e-6: the
+ * records are rescaled to the padded image's coordinate normalisation). */
+size_t gsr_workspace_bytes_batch_padded(int batch, int s_per, int hmax, int wmax);
+int gsr_forward_batch_padded(const float* sigmas, const float* coords, const float* colors, float* imgs,
+                             int batch, int s_per, int hmax, int wmax, const int* hw_host,
+                             const float* dmax_host, float dmax, float ksigma, uint32_t flags,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int gsr_backward_batch_padded(const float* sigmas, const float* coords, const float* colors,
+                              const float* grads, float* grads_sigmas, float* grads_coords,
+                              float* grads_colors, int batch, int s_per, int hmax, int wmax,
+                              const int* hw_host, const float* dmax_host, float dmax, float ksigma,
+                              uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Fused front end: raw head output (s,9) = (sx, sy, rho, alpha, r, g, b, mu_x, mu_y) ->
  * activations (gaussian_splatting.py:174-180) -> unit/coordinate mapping (:121-123) ->
  * render -> (3,h,w) image, written (not accumulated).  step_size = default_step_size / scale.

@@ -99,3 +99,79 @@ def test_batched_front_end_matches_per_sample_front_end(fused):
         (oi * wgt[i]).sum().backward()
         assert float((out[i].detach() - oi.detach()).abs().max()) <= 2e-6
         assert float((pb.grad[i] - pi.grad).abs().max()) <= 1e-5 * float(pi.grad.abs().max())
+
+
+# ---- padded (ragged) batches: every sample at its own size, one launch ------------------------------
+def _ragged(sizes, gh, gw, scales):
+    ss, cc, kk = [], [], []
+    for i, ((h, w), sc) in enumerate(zip(sizes, scales)):
+        s, c, k = fields.map_field(fields.raw_field(gh, gw, seed=40 + i), h, w, sc)
+        ss.append(s); cc.append(c); kk.append(k)
+    return tuple(torch.stack(t).to(DEV).contiguous() for t in (ss, cc, kk))
+
+
+@pytest.mark.parametrize("sizes,scales,dmax", [
+    ([(64, 48), (40, 72), (61, 33), (16, 80)], [2.0, 2.5, 2.0, 3.0], 0.1),
+    ([(50, 50), (48, 64), (33, 37)], [2.0, 2.0, 1.5], [0.05, 0.3, 0.02]),   # per-sample dmax, windows bind
+    ([(24, 24)], [1.0], 0.2),
+])
+def test_padded_batch_equals_per_sample_render_plus_padding(sizes, scales, dmax):
+    s, c, k = _ragged(sizes, 24, 28, scales)
+    b, n = s.shape[:2]
+    hmax = (max(h for h, _ in sizes) + 7) // 8 * 8
+    wmax = max(w for _, w in sizes) + 3
+    imgs = torch.full((b, hmax, wmax, 3), 9.0, device=DEV)
+    gscuda.gs_render_batch_padded(s, c, k, imgs, sizes, dmax, flags=1)
+    g = torch.rand(b, hmax, wmax, 3, device=DEV, generator=torch.Generator(DEV).manual_seed(2))
+    gs, gc, gk = torch.zeros_like(s), torch.zeros_like(c), torch.zeros_like(k)
+    gscuda.gs_render_backward_batch_padded(s, c, k, g, gs, gc, gk, sizes, dmax)
+    for i, (h, w) in enumerate(sizes):
+        dm = dmax if isinstance(dmax, float) else dmax[i]
+        one = torch.zeros(h, w, 3, device=DEV)
+        gscuda.gs_render(s[i], c[i], k[i], one, n, h, w, 3, dm)
+        assert float((imgs[i, :h, :w] - one).abs().max()) <= 2e-5      # fp32 round-off of the rescaled records
+        ref = oracle.forward(s[i].cpu().numpy(), c[i].cpu().numpy(), k[i].cpu().numpy(), h, w, dm)
+        assert np.abs(imgs[i, :h, :w].cpu().double().numpy() - ref).max() <= 1e-4
+        pad = imgs[i].clone()
+        pad[:h, :w] = 0
+        assert float(pad.abs().max()) == 0.0                             # the padding is written 0, exactly
+        ws = [torch.zeros_like(t[i]) for t in (s, c, k)]
+        gscuda.gs_render_backward(s[i], c[i], k[i], g[i, :h, :w].contiguous(), *ws, n, h, w, 3, dm)
+        for a, w_ in zip((gs[i], gc[i], gk[i]), ws):
+            assert float((a - w_).abs().max()) <= 2e-4 * float(w_.abs().max())
+
+
+def test_padded_batch_inclusion_counts_are_exact():
+    """Colours 1, huge sigma: the rounded images are per-pixel inclusion counts of each sample's OWN dmax
+    window on its OWN pixel grid -- compared exactly with the oracle."""
+    sizes, n, dmax = [(45, 61), (64, 40), (23, 77)], 200, 0.13
+    rng = np.random.default_rng(8)
+    s = torch.tensor(np.broadcast_to(np.array([1e3, 1e3, 0.0]), (3, n, 3)).copy(), dtype=torch.float32, device=DEV)
+    c = torch.tensor(rng.uniform(-1.05, 1.05, (3, n, 2)), dtype=torch.float32, device=DEV)
+    k = torch.ones(3, n, 3, device=DEV)
+    imgs = torch.zeros(3, 64, 80, 3, device=DEV)
+    gscuda.gs_render_batch_padded(s, c, k, imgs, sizes, dmax, ksigma=float("inf"))
+    for i, (h, w) in enumerate(sizes):
+        cnt = np.zeros((h, w))
+        for x0, x1, y0, y1 in oracle.ranges(c[i].cpu().numpy(), h, w, dmax):
+            if x1 >= x0 and y1 >= y0:
+                cnt[y0:y1 + 1, x0:x1 + 1] += 1
+        assert np.array_equal(np.rint(imgs[i, :h, :w, 0].cpu().numpy()), cnt)
+
+
+def test_padded_batch_autograd():
+    from gsasr_b200.gswrapper import gaussiansplatting_render_batch_padded
+
+    sizes, scales = [(40, 56), (48, 32)], [2.0, 2.0]
+    s, c, k = _ragged(sizes, 20, 24, scales)
+    leaves = [t.clone().requires_grad_(True) for t in (s, c, k)]
+    out = gaussiansplatting_render_batch_padded(*leaves, sizes, 0.2)
+    assert tuple(out.shape) == (2, 48, 56, 3)
+    wgt = torch.rand_like(out)
+    (out * wgt).sum().backward()
+    for i, (h, w) in enumerate(sizes):
+        li = [t[i].clone().requires_grad_(True) for t in (s, c, k)]
+        oi = gaussiansplatting_render(*li, (h, w), 0.2)
+        (oi * wgt[i, :h, :w]).sum().backward()
+        for a, bb in zip(leaves, li):
+            assert float((a.grad[i] - bb.grad).abs().max()) <= 2e-4 * float(bb.grad.abs().max())
