@@ -141,6 +141,9 @@ struct GsrSampleView {
   const float* px_tab;
   const float* py_tab;
 };
+// RAGGED is a compile-time switch: the common (single image / uniform batch) instantiations of the set-up
+// kernels carry none of the padded-batch code (it cost 9 us at HL when it was a run-time branch).
+template <bool RAGGED>
 __device__ __forceinline__ GsrSampleView gsr_sample_view(const GsrWorkspace& ws, int i, int h, int w, float dmax) {
   GsrSampleView v;
   v.hl = ws.bn > 0 ? ws.bhs : h;
@@ -150,7 +153,7 @@ __device__ __forceinline__ GsrSampleView gsr_sample_view(const GsrWorkspace& ws,
   v.ax = v.ay = 1.0;
   v.px_tab = ws.px_tab;
   v.py_tab = ws.py_tab;
-  if (ws.ragged) {
+  if (RAGGED) {
     const int b = i / ws.bn;
     const GsrBDesc d = ws.bdesc[b < GSR_BDESC_MAX ? b : GSR_BDESC_MAX - 1];  // (threads past s: unused)
     v.hl = d.h;
@@ -165,8 +168,9 @@ __device__ __forceinline__ GsrSampleView gsr_sample_view(const GsrWorkspace& ws,
 // Padded batch: a sample whose width / height is not a multiple of the region size shares its last regions
 // with padding pixels, which must stay 0: Gaussians whose box reaches those regions take the exact per-pixel
 // box test.
-__device__ __forceinline__ bool gsr_edge_binds(const GsrWorkspace& ws, const GsrSampleView& v, const GsrSetup& st) {
-  return ws.ragged && (((v.wl % GSR_REGION) != 0 && st.x1 / GSR_REGION == (v.wl - 1) / GSR_REGION) ||
+template <bool RAGGED>
+__device__ __forceinline__ bool gsr_edge_binds(const GsrSampleView& v, const GsrSetup& st) {
+  return RAGGED && (((v.wl % GSR_REGION) != 0 && st.x1 / GSR_REGION == (v.wl - 1) / GSR_REGION) ||
                        ((v.hl % GSR_REGION) != 0 && (st.y1 - v.yoff) / GSR_REGION == (v.hl - 1) / GSR_REGION));
 }
 // Record in CANVAS coordinates: d_own = a_ * d_canvas, so x_c = (x + 1) / ax - 1 and the conic scales.
@@ -179,6 +183,7 @@ __device__ __forceinline__ void gsr_rescale_rec(GsrRec& r, const GsrSampleView& 
   r.c = (float)((double)r.c * v.ay * v.ay);
 }
 
+template <bool RAGGED>
 __device__ __forceinline__ void gsr_bin_one(const float* __restrict__ sigmas,
                                             const float* __restrict__ coords,
                                             const float* __restrict__ colors, int i, int h, int w,
@@ -192,7 +197,7 @@ __device__ __forceinline__ void gsr_bin_one(const float* __restrict__ sigmas,
   const float cg = __ldg(colors + 3 * (size_t)i + 1);
   const float cb = __ldg(colors + 3 * (size_t)i + 2);
   // batches: set up in the sample's own image, then move to its block of rows of the stack
-  const GsrSampleView sv = gsr_sample_view(ws, i, h, w, dmax);
+  const GsrSampleView sv = gsr_sample_view<RAGGED>(ws, i, h, w, dmax);
   const int yoff = sv.yoff;
   GsrSetup st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, sv.hl, sv.wl, sv.dmax, ksigma, sv.px_tab, sv.py_tab, ws.hf,
                           ws.row0);
@@ -202,7 +207,7 @@ __device__ __forceinline__ void gsr_bin_one(const float* __restrict__ sigmas,
     st.y0 += yoff;
     st.y1 += yoff;
     st.bin_y += yoff / GSR_BIN;
-    if (gsr_edge_binds(ws, sv, st)) st.binds = true;
+    if (gsr_edge_binds<RAGGED>(sv, st)) st.binds = true;
   }
   int key = -1, rank = 0;
   if (st.live) {
@@ -223,13 +228,14 @@ __device__ __forceinline__ void gsr_bin_one(const float* __restrict__ sigmas,
 }
 
 // Grid-stride: a guarded launch of the path not taken uses a small grid and costs ~2 us.
+template <bool RAGGED>
 __global__ void __launch_bounds__(256)
 gsr_bin_kernel(const float* __restrict__ sigmas, const float* __restrict__ coords,
                const float* __restrict__ colors, int s, int h, int w, float dmax, float ksigma,
                GsrWorkspace ws, const int* guard, int want) {
   if (gsr_guard_skip(guard, want)) return;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s; i += gridDim.x * blockDim.x)
-    gsr_bin_one(sigmas, coords, colors, i, h, w, dmax, ksigma, ws);
+    gsr_bin_one<RAGGED>(sigmas, coords, colors, i, h, w, dmax, ksigma, ws);
 }
 
 // Pixel coordinate tables: the reference's rule (gs.cu:39,46), evaluated once per axis entry.
@@ -343,7 +349,7 @@ __device__ __forceinline__ void gsr_scatter_one(const float* __restrict__ sigmas
   const float cg = __ldg(colors + 3 * (size_t)i + 1);
   const float cb = __ldg(colors + 3 * (size_t)i + 2);
   GsrRec r = gsr_make_rec(sx, sy, rho, x, y, cr, cg, cb);
-  if (ws.ragged) gsr_rescale_rec(r, gsr_sample_view(ws, i, 0, 0, 0.f));  // padded batch: canvas coordinates
+  if (ws.ragged) gsr_rescale_rec(r, gsr_sample_view<true>(ws, i, 0, 0, 0.f));  // padded batch: canvas coordinates
   float4* dr = reinterpret_cast<float4*>(ws.rec + dst);
   dr[0] = make_float4(r.x, r.y, r.a, r.b);
   dr[1] = make_float4(r.c, r.r, r.g, r.bl);
@@ -490,6 +496,7 @@ struct GsrRegionBuildSmem {
 #ifndef GSR_CFG_RB_MIN_CTAS
 #define GSR_CFG_RB_MIN_CTAS (1024 / GSR_CFG_RB_THREADS)
 #endif
+template <bool RAGGED>
 __global__ void __launch_bounds__(GSR_RB_THREADS, GSR_CFG_RB_MIN_CTAS)
 gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restrict__ coords,
                       const float* __restrict__ colors, int s, int h, int w, float dmax,
@@ -525,7 +532,7 @@ gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restric
     // batches: set up in the sample's own image (hl x wl, its dmax), then move to its block of rows of the
     // stack; a padded batch stores the record rescaled to the canvas' coordinate normalisation, the raw
     // one (r) keeps describing the ellipse in the sample's own pixels for the region masks
-    const GsrSampleView sv = gsr_sample_view(ws, i, h, w, dmax);
+    const GsrSampleView sv = gsr_sample_view<RAGGED>(ws, i, h, w, dmax);
     const int yoff = sv.yoff, hl = sv.hl, wl = sv.wl;
     GsrSetup st;
     st.live = false;
@@ -541,11 +548,11 @@ gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restric
         if (!(gsr_finite(r.a) && gsr_finite(r.b) && gsr_finite(r.c))) st.live = false;
         st.y0 += yoff;
         st.y1 += yoff;
-        if (gsr_edge_binds(ws, sv, st)) st.binds = true;
+        if (gsr_edge_binds<RAGGED>(sv, st)) st.binds = true;
       }
       if (st.live) {
         GsrRec rs = r;
-        gsr_rescale_rec(rs, sv);
+        if (RAGGED) gsr_rescale_rec(rs, sv);
         float4* dr = reinterpret_cast<float4*>(ws.rec_in + i);
         dr[0] = make_float4(rs.x, rs.y, rs.a, rs.b);
         dr[1] = make_float4(rs.c, rs.r, rs.g, rs.bl);

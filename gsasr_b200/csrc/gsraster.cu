@@ -83,8 +83,10 @@ static int gsr_run_bins(const float* sigmas, const float* coords, const float* c
                         const int* guard, int want, cudaStream_t st) {
   // guarded (fallback) launches use a small grid-stride grid: the no-op case must stay cheap
   const int gs_grid = guard ? (s + 255) / 256 < 592 ? (s + 255) / 256 : 592 : (s + 255) / 256;
-  if (s > 0)
-    gsr_bin_kernel<<<gs_grid, 256, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff, ws, guard, want);
+  if (s > 0) {
+    if (ws.ragged) gsr_bin_kernel<true><<<gs_grid, 256, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff, ws, guard, want);
+    else gsr_bin_kernel<false><<<gs_grid, 256, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff, ws, guard, want);
+  }
   gsr_scan_kernel<<<ws.nscan, 1024, 0, st>>>(ws.bin_count, ws.bin_off, nullptr, ws.nb + 1,
                                              ws.scan_state, -1, ws.stats, guard, want);
   if (s > 0)
@@ -100,11 +102,15 @@ static int gsr_run_tiles(const float* sigmas, const float* coords, const float* 
   if (s > 0) {
     // persistent CTAs: one resident wave, every CTA strides over the chunks of the input
     int cap = 0;
-    const int rc = gsr_resident_grid(gsr_region_build_kernel, GSR_RB_THREADS, 0, &cap);
+    const int rc = gsr_resident_grid(gsr_region_build_kernel<false>, GSR_RB_THREADS, 0, &cap);
     if (rc) return rc;
-    const int want = (s + GSR_RB_THREADS - 1) / GSR_RB_THREADS;
-    gsr_region_build_kernel<<<want < cap ? want : cap, GSR_RB_THREADS, 0, st>>>(sigmas, coords, colors, s, h, w, dmax,
-                                                                               keff, gsr_ecut(keff), ws);
+    const int want = (s + GSR_RB_THREADS - 1) / GSR_RB_THREADS, grid = want < cap ? want : cap;
+    if (ws.ragged)
+      gsr_region_build_kernel<true><<<grid, GSR_RB_THREADS, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff,
+                                                                     gsr_ecut(keff), ws);
+    else
+      gsr_region_build_kernel<false><<<grid, GSR_RB_THREADS, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff,
+                                                                      gsr_ecut(keff), ws);
   }
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;

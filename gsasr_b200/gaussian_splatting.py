@@ -27,7 +27,8 @@ from . import gscuda as _gs
 
 __all__ = [
     "generate_2D_gaussian_splatting_step", "generate_2D_gaussian_splatting_step_buffer",
-    "generate_2D_gaussian_splatting_step_batch", "generate_2D_gaussian_splatting_step_u8", "render_into_canvas",
+    "generate_2D_gaussian_splatting_step_batch", "generate_2D_gaussian_splatting_step_batch_padded",
+    "generate_2D_gaussian_splatting_step_u8", "render_into_canvas",
     "rendering_cuda", "rendering_cuda_buffer", "rendering_cuda_dmax", "rendering_cuda_dmax_buffer",
     "map_gaussians", "render_chw",
 ]
@@ -360,3 +361,45 @@ def generate_2D_gaussian_splatting_step_u8(sr_size, gs_parameters, scale, scale_
     _gs.gs_render_u8(sigmas, coords.contiguous(), colours_with_alpha.contiguous(), out, sigmas.shape[0], h, w,
                      _resolve_dmax(if_dmax, dmax_mode, dmax, sr_size), bgr=bgr)
     return out
+
+
+def generate_2D_gaussian_splatting_step_batch_padded(sr_sizes, gs_parameters, scales, default_step_size=1.2,
+                                                     if_dmax=True, dmax_mode='fix', dmax=25, hmax=None, wmax=None):
+    """The training loop of gsasr_model.py:191-233 in one call: gs_parameters (B,N,9), sample b rendered at
+    sr_sizes[b] = (H_b, W_b) with step size default_step_size / scales[b] and padded with zeros to the
+    largest size (the loop's F.pad) -> (B,3,hmax,wmax) in channels-last layout.  Same activations and mapping
+    expressions as the per-sample function with the per-sample constants broadcast over the batch; one
+    set-up and one raster launch each way (gsr_forward_batch_padded)."""
+    from .gswrapper import gaussiansplatting_render_batch_padded
+
+    if gs_parameters.dim() != 3 or gs_parameters.shape[-1] != 9:
+        raise RuntimeError("gs_parameters must be (B,N,9)")
+    b = gs_parameters.shape[0]
+    dev = gs_parameters.device
+    sizes = [(int(s[0]), int(s[1])) for s in sr_sizes]
+    hs = torch.tensor([h for h, _ in sizes], device=dev).view(b, 1, 1)
+    ws_ = torch.tensor([w for _, w in sizes], device=dev).view(b, 1, 1)
+    step = torch.tensor([default_step_size / float(sc) for sc in scales], dtype=torch.float32, device=dev).view(b, 1, 1)
+    # prepare gaussian properties (:174-180)
+    sigma_x = 0.99999 * torch.sigmoid(gs_parameters[..., 0:1]) + 1e-6
+    sigma_y = 0.99999 * torch.sigmoid(gs_parameters[..., 1:2]) + 1e-6
+    rho = 0.999999 * torch.tanh(gs_parameters[..., 2:3])
+    alpha = torch.sigmoid(gs_parameters[..., 3:4])
+    colours = torch.sigmoid(gs_parameters[..., 4:7])
+    coords = (gs_parameters[..., 7:9] * 2 - 1)
+    colours_with_alpha = colours * alpha
+    # unit / coordinate mapping (:121-123) with every sample's own size and step
+    sigmas = torch.cat([sigma_y / step * 2 / (ws_ - 1), sigma_x / step * 2 / (hs - 1), rho], dim=-1).contiguous()
+    cx = (coords[..., 0:1] + 1 - 1 / ws_) * ws_ / (ws_ - 1) - 1.0
+    cy = (coords[..., 1:2] + 1 - 1 / hs) * hs / (hs - 1) - 1.0
+    coords = torch.cat([cx, cy], dim=-1).contiguous()
+    if not if_dmax:
+        dm = float("inf")
+    elif dmax_mode == 'dynamic':
+        dm = [float((dmax + 2) / min(h, w)) for h, w in sizes]
+    elif dmax_mode == 'fix':
+        dm = float(dmax)
+    else:
+        raise ValueError(f"dmax_mode-{dmax_mode} must be fix or dynamic")
+    out = gaussiansplatting_render_batch_padded(sigmas, coords, colours_with_alpha.contiguous(), sizes, dm, hmax, wmax)
+    return out.permute(0, 3, 1, 2)

@@ -72,6 +72,28 @@ for dmax in (0.5, 0.1):
         if world > 1:
             t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t)
         out[f"dmax{dmax}_batch_{'fused' if fused else 'torchops'}_ms_per_step"] = round(ms, 3)
+# ragged: every sample at its own scale in [3.5, 4] (HR 896..1024), the reference loop's shape, vs ONE padded launch
+import torch.nn.functional as F
+scs = [3.5 + 0.5 * ((i * 7) % 8) / 7.0 for i in range(len(raws))]
+szs = [(int(256 * sc) // 8 * 8, int(256 * sc) // 8 * 8) for sc in scs]
+gtp = torch.rand(len(raws), 3, 1024, 1024, device=dev).contiguous(memory_format=torch.channels_last)
+def step_loop_ragged():
+    for raw, gt, sc, (hh, ww) in zip(raws, gtp, scs, szs):
+        p = raw.clone().requires_grad_(True)
+        img = gsp.generate_2D_gaussian_splatting_step(torch.tensor([hh, ww]), p, sc, torch.tensor([sc] * 2), dmax=0.1, fused=True)
+        (img - gt[:, :hh, :ww]).abs().mean().backward()
+def step_padded():
+    p = rawb.clone().requires_grad_(True)
+    img = gsp.generate_2D_gaussian_splatting_step_batch_padded([torch.tensor(z) for z in szs], p, scs, dmax=0.1, hmax=1024, wmax=1024)
+    ((img - gtp).abs().mean(dim=(1, 2, 3))).sum().backward()
+for name, fn in (("ragged_loop_fused", step_loop_ragged), ("ragged_padded_batch", step_padded)):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps): fn()
+    b.record(); torch.cuda.synchronize()
+    out[f"{name}_ms_per_step"] = round(a.elapsed_time(b) / args.steps, 3)
 if rank == 0:
     print(json.dumps({"config": "C5-shaped: batch %d x (256x256 LR -> x4, 262144 Gaussians), fwd+bwd render + L1" % args.batch,
                       "samples_per_gpu": hi - lo, "world": eff_world, **out}))
