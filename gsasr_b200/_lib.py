@@ -72,6 +72,10 @@ SIGNATURES = {
                                       _u32, _vp, _sz, _vp]),
     "gsr_backward_batch_padded": (_i, [_vp] * 7 + [_i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_f), _f, _f, _u32,
                                                   _vp, _sz, _vp]),
+    "gsr_frontend_forward_batch_padded": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_f),
+                                               ctypes.POINTER(_f), _f, _f, _vp, _sz, _vp]),
+    "gsr_frontend_backward_batch_padded": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, ctypes.POINTER(_i),
+                                                ctypes.POINTER(_f), ctypes.POINTER(_f), _f, _f, _vp, _sz, _vp]),
     "gsr_frontend_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _vp, _sz, _vp]),
     "gsr_frontend_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _vp, _sz, _vp]),
 }

@@ -7,7 +7,7 @@
 // multiplication by the fp32 reciprocal); every operation is individually rounded (no FMA
 // contraction) so the mapped parameters agree with the unfused path to the last bit or one ulp.
 #pragma once
-#include "gsr_common.cuh"
+#include "gsr_prepass.cuh"
 
 __device__ __forceinline__ float gsr_sigmoid(float x) {
   return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
@@ -20,9 +20,15 @@ __device__ __forceinline__ float gsr_sigmoid(float x) {
 __global__ void __launch_bounds__(256)
 gsr_map_kernel(const float* __restrict__ raw, float* __restrict__ sigmas,
                float* __restrict__ coords, float* __restrict__ colors, int s, int h, int w,
-               float step) {
+               float step, const GsrBDesc* __restrict__ bdesc = nullptr, int bn = 0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= s) return;
+  if (bdesc) {  // padded batch: every sample its own size and step
+    const GsrBDesc d = bdesc[i / bn];
+    h = d.h;
+    w = d.w;
+    step = d.step;
+  }
   const float* p = raw + 9 * (size_t)i;
   const float inv_step = __fdiv_rn(1.0f, step);
   const float inv_w1 = __fdiv_rn(1.0f, (float)(w - 1)), inv_h1 = __fdiv_rn(1.0f, (float)(h - 1));
@@ -49,9 +55,16 @@ gsr_map_kernel(const float* __restrict__ raw, float* __restrict__ sigmas,
 __global__ void __launch_bounds__(256)
 gsr_unmap_kernel(const float* __restrict__ raw, const float* __restrict__ g_sigmas,
                  const float* __restrict__ g_coords, const float* __restrict__ g_colors,
-                 float* __restrict__ g_raw, int s, int h, int w, float step) {
+                 float* __restrict__ g_raw, int s, int h, int w, float step,
+                 const GsrBDesc* __restrict__ bdesc = nullptr, int bn = 0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= s) return;
+  if (bdesc) {
+    const GsrBDesc d = bdesc[i / bn];
+    h = d.h;
+    w = d.w;
+    step = d.step;
+  }
   const float* p = raw + 9 * (size_t)i;
   float* o = g_raw + 9 * (size_t)i;
   const float kx = 2.0f / (step * (float)(w - 1)), ky = 2.0f / (step * (float)(h - 1));

@@ -32,7 +32,7 @@ struct gsr_window;
 struct GsrBDesc {
   int h, w;
   float dmax;
-  int pad;
+  float step;     // step size of the sample (fused front end only)
   double ax, ay;  // double: a float ratio would move the centres by 1e-4 pixel
 };
 constexpr int GSR_BDESC_MAX = 1024;  // samples per stacked launch

@@ -603,12 +603,13 @@ static int gsr_padded_check(int batch, int s_per, int hmax, int wmax, const int*
   return GSR_OK;
 }
 
-static void gsr_padded_fill(GsrBDesc* d, int nb, int hmax, int wmax, const int* hw, const float* dmax_host, float dmax) {
+static void gsr_padded_fill(GsrBDesc* d, int nb, int hmax, int wmax, const int* hw, const float* dmax_host, float dmax,
+                            const float* step_host = nullptr) {
   for (int b = 0; b < nb; ++b) {
     d[b].h = hw[2 * b];
     d[b].w = hw[2 * b + 1];
     d[b].dmax = dmax_host ? dmax_host[b] : dmax;
-    d[b].pad = 0;
+    d[b].step = step_host ? step_host[b] : 0.0f;
     d[b].ax = (double)(wmax - 1) / (double)(hw[2 * b + 1] - 1);
     d[b].ay = (double)(hmax - 1) / (double)(hw[2 * b] - 1);
   }
@@ -737,6 +738,83 @@ extern "C" int gsr_frontend_forward_window(const float* raw, float* mapped, floa
   }
   return gsr_forward_window(mapped, mapped + 3 * (size_t)s, mapped + 5 * (size_t)s, origin, win, s, h, w, 3,
                             dmax, ksigma, flags, workspace, workspace_bytes, stream);
+}
+
+// Fused front end for a padded batch: raw (batch*s_per,9) -> imgs (batch,hmax,wmax,3); every sample its own
+// size hw_host[b] and step size step_host[b] (HOST arrays).
+extern "C" int gsr_frontend_forward_batch_padded(const float* raw, float* mapped, float* imgs, int batch,
+                                                 int s_per, int hmax, int wmax, const int* hw_host,
+                                                 const float* step_host, const float* dmax_host, float dmax,
+                                                 float ksigma, void* workspace, size_t workspace_bytes,
+                                                 void* stream) {
+  int rc = gsr_padded_check(batch, s_per, hmax, wmax, hw_host);
+  if (rc) return rc;
+  if (batch > 0 && (!raw || !mapped || !imgs || !step_host)) return GSR_ERR_NULL_POINTER;
+  for (int b = 0; b < batch; ++b)
+    if (!(step_host[b] > 0.0f)) return GSR_ERR_BAD_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t S = (size_t)batch * s_per;
+  float *sig = mapped, *crd = mapped + 3 * S, *col = mapped + 5 * S;
+  const int g = gsr_padded_group(batch, hmax);
+  GsrBDesc desc[GSR_BDESC_MAX];
+  for (int b0 = 0; b0 < batch; b0 += g) {
+    const int nb = batch - b0 < g ? batch - b0 : g, sg = nb * s_per;
+    const size_t go = (size_t)b0 * s_per;
+    const GsrWorkspace ws = gsr_carve(workspace, sg, nb * hmax, wmax);
+    rc = gsr_check_ws(workspace, workspace_bytes, ws.bytes);
+    if (rc) return rc;
+    gsr_padded_fill(desc, nb, hmax, wmax, hw_host + 2 * b0, dmax_host ? dmax_host + b0 : nullptr, dmax, step_host + b0);
+    GSR_CUDA(cudaMemcpyAsync(ws.bdesc, desc, (size_t)nb * sizeof(GsrBDesc), cudaMemcpyHostToDevice, st));
+    if (sg > 0) {
+      gsr_map_kernel<<<(sg + 255) / 256, 256, 0, st>>>(raw + 9 * go, sig + 3 * go, crd + 2 * go, col + 3 * go, sg, 0, 0,
+                                                       0.f, ws.bdesc, s_per);
+      GSR_CUDA(cudaGetLastError());
+    }
+    rc = gsr_forward_impl(sig + 3 * go, crd + 2 * go, col + 3 * go, imgs + (size_t)b0 * hmax * wmax * 3, sg, nb * hmax,
+                          wmax, 3, 0, 0, dmax, ksigma, GSR_FLAG_OVERWRITE, workspace, workspace_bytes, stream, s_per, hmax,
+                          nullptr, desc);
+    if (rc) return rc;
+  }
+  return GSR_OK;
+}
+
+// grads (batch,hmax,wmax,3) -> grad_raw (batch*s_per,9), written.  Workspace: gsr_workspace_bytes_batch_padded
+// + 32 bytes per Gaussian of the largest launch group (at most the whole batch), rounded up to 256.
+extern "C" int gsr_frontend_backward_batch_padded(const float* raw, const float* mapped, const float* grads,
+                                                  float* grad_raw, int batch, int s_per, int hmax, int wmax,
+                                                  const int* hw_host, const float* step_host,
+                                                  const float* dmax_host, float dmax, float ksigma,
+                                                  void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = gsr_padded_check(batch, s_per, hmax, wmax, hw_host);
+  if (rc) return rc;
+  if (batch > 0 && (!raw || !mapped || !grads || !grad_raw || !step_host)) return GSR_ERR_NULL_POINTER;
+  for (int b = 0; b < batch; ++b)
+    if (!(step_host[b] > 0.0f)) return GSR_ERR_BAD_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t S = (size_t)batch * s_per;
+  const float *sig = mapped, *crd = mapped + 3 * S, *col = mapped + 5 * S;
+  const int g = gsr_padded_group(batch, hmax);
+  const size_t need = gsr_workspace_bytes_batch_padded(batch, s_per, hmax, wmax);
+  const size_t stage = gsr_align_up((size_t)g * s_per * 8 * sizeof(float), 256);
+  if (!workspace || ((uintptr_t)workspace & 255u) || workspace_bytes < need + stage) return GSR_ERR_WORKSPACE;
+  float* gm = (float*)((char*)workspace + need);
+  GsrBDesc desc[GSR_BDESC_MAX];
+  for (int b0 = 0; b0 < batch; b0 += g) {
+    const int nb = batch - b0 < g ? batch - b0 : g, sg = nb * s_per;
+    if (sg == 0) continue;
+    const size_t go = (size_t)b0 * s_per;
+    const GsrWorkspace ws = gsr_carve(workspace, sg, nb * hmax, wmax);
+    gsr_padded_fill(desc, nb, hmax, wmax, hw_host + 2 * b0, dmax_host ? dmax_host + b0 : nullptr, dmax, step_host + b0);
+    GSR_CUDA(cudaMemsetAsync(gm, 0, (size_t)sg * 8 * sizeof(float), st));
+    rc = gsr_backward_impl(sig + 3 * go, crd + 2 * go, col + 3 * go, grads + (size_t)b0 * hmax * wmax * 3, gm,
+                           gm + 3 * (size_t)sg, gm + 5 * (size_t)sg, sg, nb * hmax, wmax, 3, 0, 0, dmax, ksigma, 0,
+                           workspace, need, stream, s_per, hmax, desc);
+    if (rc) return rc;
+    gsr_unmap_kernel<<<(sg + 255) / 256, 256, 0, st>>>(raw + 9 * go, gm, gm + 3 * (size_t)sg, gm + 5 * (size_t)sg,
+                                                       grad_raw + 9 * go, sg, 0, 0, 0.f, ws.bdesc, s_per);
+    GSR_CUDA(cudaGetLastError());
+  }
+  return GSR_OK;
 }
 
 // ---- CPU test hooks (no GPU needed): run the shared host/device culling code on the host ----

@@ -363,13 +363,61 @@ def generate_2D_gaussian_splatting_step_u8(sr_size, gs_parameters, scale, scale_
     return out
 
 
+class _FusedFrontendBatchPadded(Function):
+    """raw (B,N,9) -> (B,hmax,wmax,3) through gsr_frontend_forward_batch_padded / _backward_batch_padded."""
+
+    @staticmethod
+    def forward(ctx, raw, sizes, steps, dmaxes, hmax, wmax):
+        import ctypes
+
+        L = _lib.load()
+        raw = raw.contiguous().float()
+        b, n = raw.shape[:2]
+        hw = (ctypes.c_int * (2 * b))(*[int(v) for s_ in sizes for v in s_])
+        st = (ctypes.c_float * b)(*[float(v) for v in steps])
+        dm = (ctypes.c_float * b)(*[float(v) for v in dmaxes])
+        mapped = torch.empty(max(b * n, 1) * 8, device=raw.device, dtype=torch.float32)
+        out = torch.empty(b, hmax, wmax, 3, device=raw.device, dtype=torch.float32)
+        with torch.cuda.device(raw.device):
+            ws = _gs.workspace_batch_padded(b, n, hmax, wmax, raw.device)
+            rc = L.gsr_frontend_forward_batch_padded(raw.data_ptr(), mapped.data_ptr(), out.data_ptr(), b, n, hmax, wmax,
+                                                     hw, st, dm, 0.0, float(_gs.get_ksigma()), ws.data_ptr(), ws.numel(),
+                                                     torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc)
+        ctx.save_for_backward(raw, mapped)
+        ctx.meta = (hw, st, dm, hmax, wmax)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad):
+        L = _lib.load()
+        raw, mapped = ctx.saved_tensors
+        hw, st, dm, hmax, wmax = ctx.meta
+        b, n = raw.shape[:2]
+        grad = grad.contiguous()
+        g_raw = torch.zeros_like(raw)
+        if b * n:
+            with torch.cuda.device(raw.device):
+                need = L.gsr_workspace_bytes_batch_padded(b, n, hmax, wmax) + (b * n * 32 + 255) // 256 * 256
+                ws = torch.empty(need, dtype=torch.uint8, device=raw.device)
+                rc = L.gsr_frontend_backward_batch_padded(raw.data_ptr(), mapped.data_ptr(), grad.data_ptr(),
+                                                          g_raw.data_ptr(), b, n, hmax, wmax, hw, st, dm, 0.0,
+                                                          float(_gs.get_ksigma()), ws.data_ptr(), ws.numel(),
+                                                          torch.cuda.current_stream().cuda_stream)
+            _lib.check(rc)
+        return g_raw, None, None, None, None, None
+
+
 def generate_2D_gaussian_splatting_step_batch_padded(sr_sizes, gs_parameters, scales, default_step_size=1.2,
-                                                     if_dmax=True, dmax_mode='fix', dmax=25, hmax=None, wmax=None):
+                                                     if_dmax=True, dmax_mode='fix', dmax=25, hmax=None, wmax=None,
+                                                     fused=False):
     """The training loop of gsasr_model.py:191-233 in one call: gs_parameters (B,N,9), sample b rendered at
     sr_sizes[b] = (H_b, W_b) with step size default_step_size / scales[b] and padded with zeros to the
     largest size (the loop's F.pad) -> (B,3,hmax,wmax) in channels-last layout.  Same activations and mapping
-    expressions as the per-sample function with the per-sample constants broadcast over the batch; one
-    set-up and one raster launch each way (gsr_forward_batch_padded)."""
+    expressions as the per-sample function with the per-sample constants broadcast over the batch
+    (``fused=True``: the library's fused front end instead); one set-up and one raster launch each way
+    (gsr_forward_batch_padded)."""
     from .gswrapper import gaussiansplatting_render_batch_padded
 
     if gs_parameters.dim() != 3 or gs_parameters.shape[-1] != 9:
@@ -377,6 +425,20 @@ def generate_2D_gaussian_splatting_step_batch_padded(sr_sizes, gs_parameters, sc
     b = gs_parameters.shape[0]
     dev = gs_parameters.device
     sizes = [(int(s[0]), int(s[1])) for s in sr_sizes]
+    if not if_dmax:
+        dm = float("inf")
+    elif dmax_mode == 'dynamic':
+        dm = [float((dmax + 2) / min(h, w)) for h, w in sizes]
+    elif dmax_mode == 'fix':
+        dm = float(dmax)
+    else:
+        raise ValueError(f"dmax_mode-{dmax_mode} must be fix or dynamic")
+    if fused:
+        hm = (max(h for h, _ in sizes) + 7) // 8 * 8 if hmax is None else int(hmax)
+        wm = max(w for _, w in sizes) if wmax is None else int(wmax)
+        out = _FusedFrontendBatchPadded.apply(gs_parameters, sizes, [default_step_size / float(sc) for sc in scales],
+                                              dm if isinstance(dm, list) else [dm] * b, hm, wm)
+        return out.permute(0, 3, 1, 2)
     hs = torch.tensor([h for h, _ in sizes], device=dev).view(b, 1, 1)
     ws_ = torch.tensor([w for _, w in sizes], device=dev).view(b, 1, 1)
     step = torch.tensor([default_step_size / float(sc) for sc in scales], dtype=torch.float32, device=dev).view(b, 1, 1)
@@ -393,13 +455,5 @@ def generate_2D_gaussian_splatting_step_batch_padded(sr_sizes, gs_parameters, sc
     cx = (coords[..., 0:1] + 1 - 1 / ws_) * ws_ / (ws_ - 1) - 1.0
     cy = (coords[..., 1:2] + 1 - 1 / hs) * hs / (hs - 1) - 1.0
     coords = torch.cat([cx, cy], dim=-1).contiguous()
-    if not if_dmax:
-        dm = float("inf")
-    elif dmax_mode == 'dynamic':
-        dm = [float((dmax + 2) / min(h, w)) for h, w in sizes]
-    elif dmax_mode == 'fix':
-        dm = float(dmax)
-    else:
-        raise ValueError(f"dmax_mode-{dmax_mode} must be fix or dynamic")
     out = gaussiansplatting_render_batch_padded(sigmas, coords, colours_with_alpha.contiguous(), sizes, dm, hmax, wmax)
     return out.permute(0, 3, 1, 2)

@@ -234,6 +234,20 @@ int gsr_frontend_backward_batch_uniform(const float* raw_params, const float* ma
                                         float step_size, float dmax, float ksigma, void* workspace,
                                         size_t workspace_bytes, void* stream);
 
+/* The fused front end for a padded batch (see gsr_forward_batch_padded): every sample its own size
+ * hw_host[b] and step size step_host[b] = default_step_size / scale_b (HOST arrays).  mapped:
+ * batch*s_per*8 floats.  Backward workspace: gsr_workspace_bytes_batch_padded + 32 bytes per Gaussian of
+ * the batch, rounded up to 256. */
+int gsr_frontend_forward_batch_padded(const float* raw_params, float* mapped, float* imgs, int batch,
+                                      int s_per, int hmax, int wmax, const int* hw_host,
+                                      const float* step_host, const float* dmax_host, float dmax,
+                                      float ksigma, void* workspace, size_t workspace_bytes, void* stream);
+int gsr_frontend_backward_batch_padded(const float* raw_params, const float* mapped, const float* grads,
+                                       float* grad_raw, int batch, int s_per, int hmax, int wmax,
+                                       const int* hw_host, const float* step_host, const float* dmax_host,
+                                       float dmax, float ksigma, void* workspace, size_t workspace_bytes,
+                                       void* stream);
+
 /* gsr_frontend_forward into a window (see gsr_forward_window): raw head output -> destination pixels. */
 int gsr_frontend_forward_window(const float* raw_params, float* mapped, float* origin, const gsr_window* win,
                                 int s, int h, int w, float step_size, float dmax, float ksigma,

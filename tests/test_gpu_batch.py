@@ -177,7 +177,8 @@ def test_padded_batch_autograd():
             assert float((a.grad[i] - bb.grad).abs().max()) <= 2e-4 * float(bb.grad.abs().max())
 
 
-def test_padded_front_end_matches_the_per_sample_training_loop():
+@pytest.mark.parametrize("fused", [False, True])
+def test_padded_front_end_matches_the_per_sample_training_loop(fused):
     """generate_2D_gaussian_splatting_step_batch_padded against the loop of gsasr_model.py:191-233:
     per-sample render at its own scale / size, F.pad to the largest, values and gradients."""
     import torch.nn.functional as F
@@ -188,13 +189,15 @@ def test_padded_front_end_matches_the_per_sample_training_loop():
     sizes = [(32, 32), (48, 48), (40, 40)]                 # 16x16 LR at each scale
     raw = torch.stack([fields.raw_field(32, 32, seed=60 + i) for i in range(3)]).to(DEV)
     pb = raw.clone().requires_grad_(True)
-    out = gsp.generate_2D_gaussian_splatting_step_batch_padded([torch.tensor(s) for s in sizes], pb, scales, dmax=0.1)
+    out = gsp.generate_2D_gaussian_splatting_step_batch_padded([torch.tensor(s) for s in sizes], pb, scales, dmax=0.1,
+                                                               fused=fused)
     assert tuple(out.shape) == (3, 3, 48, 48)
     wgt = torch.rand(3, 3, 48, 48, device=DEV, generator=torch.Generator(DEV).manual_seed(4))
     (out * wgt).sum().backward()
     for i, ((h, w), sc) in enumerate(zip(sizes, scales)):
         pi = raw[i].clone().requires_grad_(True)
-        oi = gsp.generate_2D_gaussian_splatting_step(torch.tensor([h, w]), pi, sc, torch.tensor([sc, sc]), dmax=0.1)
+        oi = gsp.generate_2D_gaussian_splatting_step(torch.tensor([h, w]), pi, sc, torch.tensor([sc, sc]), dmax=0.1,
+                                                     fused=fused)
         oi = F.pad(oi, (0, 48 - w, 0, 48 - h), 'constant', 0)
         (oi * wgt[i]).sum().backward()
         assert float((out[i].detach() - oi.detach()).abs().max()) <= 2e-5

@@ -82,11 +82,12 @@ def step_loop_ragged():
         p = raw.clone().requires_grad_(True)
         img = gsp.generate_2D_gaussian_splatting_step(torch.tensor([hh, ww]), p, sc, torch.tensor([sc] * 2), dmax=0.1, fused=True)
         (img - gt[:, :hh, :ww]).abs().mean().backward()
-def step_padded():
+def step_padded(fused):
     p = rawb.clone().requires_grad_(True)
-    img = gsp.generate_2D_gaussian_splatting_step_batch_padded([torch.tensor(z) for z in szs], p, scs, dmax=0.1, hmax=1024, wmax=1024)
+    img = gsp.generate_2D_gaussian_splatting_step_batch_padded([torch.tensor(z) for z in szs], p, scs, dmax=0.1, hmax=1024, wmax=1024, fused=fused)
     ((img - gtp).abs().mean(dim=(1, 2, 3))).sum().backward()
-for name, fn in (("ragged_loop_fused", step_loop_ragged), ("ragged_padded_batch", step_padded)):
+for name, fn in (("ragged_loop_fused", step_loop_ragged), ("ragged_padded_batch_torchops", lambda: step_padded(False)),
+                 ("ragged_padded_batch_fused", lambda: step_padded(True))):
     for _ in range(3): fn()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
