@@ -36,6 +36,16 @@ sb = torch.stack([field(256, (0.01, 0.1))[0] for _ in range(3)]); cb = torch.ran
 imgs = torch.zeros(3, 40, 48, 3, device=dev)
 gscuda.gs_render_batch(sb, cb, kb, imgs, 0.2)
 gscuda.gs_render_backward_batch(sb, cb, kb, torch.rand_like(imgs), torch.zeros_like(sb), torch.zeros_like(cb), torch.zeros_like(kb), 0.2)
+# padded (ragged) batch, forward + backward, and its fused front end
+from gsasr_b200 import gaussian_splatting as gsp
+sizes = [(40, 48), (29, 37), (16, 50)]
+imgs = torch.zeros(3, 40, 52, 3, device=dev)
+gscuda.gs_render_batch_padded(sb, cb, kb, imgs, sizes, [0.2, 0.05, 0.4], flags=1)
+gscuda.gs_render_backward_batch_padded(sb, cb, kb, torch.rand_like(imgs), torch.zeros_like(sb), torch.zeros_like(cb), torch.zeros_like(kb), sizes, [0.2, 0.05, 0.4])
+raw = torch.randn(3, 256, 9, device=dev); raw[..., 7:9] = torch.rand(3, 256, 2, device=dev)
+raw.requires_grad_(True)
+out = gsp.generate_2D_gaussian_splatting_step_batch_padded([torch.tensor(z) for z in sizes], raw, [2.0, 1.5, 2.5], dmax=0.3, fused=True)
+out.sum().backward()
 _, s, c, k, h, w = fields.make("C1", 0)
 sharding.render_image_bands(s.to(dev), c.to(dev), k.to(dev), h, w, 0.1)
 torch.cuda.synchronize()
