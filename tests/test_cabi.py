@@ -181,3 +181,25 @@ def test_public_headers_compile_as_c_and_cpp(lang, compiler, tmp_path):
     r = subprocess.run([compiler, "-x", lang, "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_argument_validation_of_the_padded_batch_entry_points():
+    L = _lib.load()
+    fake, ws = ctypes.c_void_p(256), ctypes.c_void_p(4096)
+    hw = (ctypes.c_int * 4)(40, 48, 64, 64)
+    assert L.gsr_workspace_bytes_batch_padded(2, 10, 64, 64) == L.gsr_workspace_bytes(20, 128, 64)
+    assert L.gsr_workspace_bytes_batch_padded(2, 10, 60, 64) == 0                      # hmax % 8 != 0
+    fp = L.gsr_forward_batch_padded
+    ok_args = (2, 10, 64, 64, hw, None, 0.1, 0.0, 1, ws, 1 << 30, None)
+    assert fp(fake, fake, fake, None, *ok_args) == 1                                     # imgs NULL
+    assert fp(fake, fake, fake, fake, 2, 10, 60, 64, hw, None, 0.1, 0.0, 1, ws, 1 << 30, None) == 2   # hmax % 8
+    assert fp(fake, fake, fake, fake, 2, 10, 64, 64, None, None, 0.1, 0.0, 1, ws, 1 << 30, None) == 1  # no sizes
+    big = (ctypes.c_int * 4)(40, 48, 65, 64)
+    assert fp(fake, fake, fake, fake, 2, 10, 64, 64, big, None, 0.1, 0.0, 1, ws, 1 << 30, None) == 2   # h_b > hmax
+    tiny = (ctypes.c_int * 4)(40, 48, 64, 1)
+    assert fp(fake, fake, fake, fake, 2, 10, 64, 64, tiny, None, 0.1, 0.0, 1, ws, 1 << 30, None) == 2  # w_b < 2
+    assert fp(fake, fake, fake, fake, 2, 10, 64, 64, hw, None, 0.1, 0.0, _lib.GSR_FLAG_CHW, ws, 1 << 30, None) == 5
+    assert fp(fake, fake, fake, fake, 0, 10, 64, 64, hw, None, 0.1, 0.0, 1, None, 0, None) == 0         # empty batch
+    st = (ctypes.c_float * 2)(0.3, 0.0)
+    assert L.gsr_frontend_forward_batch_padded(fake, fake, fake, 2, 10, 64, 64, hw, st, None, 0.1, 0.0, ws, 1 << 30,
+                                               None) == 5                                 # step <= 0
