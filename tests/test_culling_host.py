@@ -134,3 +134,41 @@ def test_band_setup_is_the_whole_image_box_cut_to_the_band(h, w, dmax, ksigma):
                 assert b[0] == 0
             else:
                 assert b.tolist()[:5] == [1, int(f[1]), int(f[2]), y0 - row0, y1 - row0]
+
+
+def test_padded_batch_rescaling_algebra():
+    """gsr_forward_batch_padded renders a sample of size (h, w) inside a larger (H, W) image by rescaling its
+    records to the larger image's coordinate normalisation: x_c = (x+1)/ax - 1, (a, b, c) -> (a ax^2, b ax ay,
+    c ay^2) with ax = (W-1)/(w-1), ay = (H-1)/(h-1).  Checked here in float64 on the pixel grids: the exponent
+    of every pixel is unchanged, and so is the backward's chain rule after its corrections (centre gradients
+    / (ax, ay), bare Sxy * ax ay)."""
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        h, w = int(rng.integers(5, 60)), int(rng.integers(5, 60))
+        H, W = h + int(rng.integers(0, 30)), w + int(rng.integers(0, 30))
+        ax, ay = (W - 1) / (w - 1), (H - 1) / (h - 1)
+        x, y = rng.uniform(-1.2, 1.2, 2)
+        a, b, c = -rng.uniform(1, 500), rng.uniform(-50, 50), -rng.uniform(1, 500)
+        ii, jj = np.arange(w), np.arange(h)
+        dx_own = (2.0 * ii / (w - 1) - 1.0) - x
+        dy_own = (2.0 * jj / (h - 1) - 1.0) - y
+        xc, yc = (x + 1.0) / ax - 1.0, (y + 1.0) / ay - 1.0
+        dx_c = (2.0 * ii / (W - 1) - 1.0) - xc
+        dy_c = (2.0 * jj / (H - 1) - 1.0) - yc
+        assert np.allclose(dx_own, ax * dx_c, rtol=0, atol=1e-12) and np.allclose(dy_own, ay * dy_c, rtol=0, atol=1e-12)
+        e_own = a * dx_own[None, :] ** 2 + b * dx_own[None, :] * dy_own[:, None] + c * dy_own[:, None] ** 2
+        ac, bc, cc = a * ax * ax, b * ax * ay, c * ay * ay
+        e_c = ac * dx_c[None, :] ** 2 + bc * dx_c[None, :] * dy_c[:, None] + cc * dy_c[:, None] ** 2
+        assert np.allclose(e_own, e_c, rtol=1e-11, atol=1e-9)
+        # moments with arbitrary weights u: what the backward kernel accumulates, in either unit
+        u = rng.uniform(-1, 1, (h, w))
+        S = lambda dx, dy: (np.sum(u * dx[None, :]), np.sum(u * dy[:, None]), np.sum(u * dx[None, :] ** 2),
+                            np.sum(u * dx[None, :] * dy[:, None]), np.sum(u * dy[:, None] ** 2))
+        sx, sy, sxx, sxy, syy = S(dx_own, dy_own)
+        tx, ty, txx, txy, tyy = S(dx_c, dy_c)
+        gx_own, gx_c = -(2 * a * sx + b * sy), -(2 * ac * tx + bc * ty)
+        gy_own, gy_c = -(2 * c * sy + b * sx), -(2 * cc * ty + bc * tx)
+        assert np.isclose(gx_own, gx_c / ax, rtol=1e-9, atol=1e-9) and np.isclose(gy_own, gy_c / ay, rtol=1e-9, atol=1e-9)
+        assert np.isclose(b * sxy + 2 * a * sxx, bc * txy + 2 * ac * txx, rtol=1e-9, atol=1e-9)      # sigma_x term
+        assert np.isclose(a * sxx + b * sxy + c * syy, ac * txx + bc * txy + cc * tyy, rtol=1e-9, atol=1e-9)  # Q
+        assert np.isclose(sxy, txy * ax * ay, rtol=1e-9, atol=1e-9)
