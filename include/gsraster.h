@@ -31,7 +31,8 @@
  *     never throws: scratch comes from the caller (`workspace`, sized by gsr_workspace_bytes),
  *     work is enqueued on `stream` (a cudaStream_t / CUstream; NULL = legacy default stream,
  *     which is what the reference launches on), and the return value is a gsr_status;
- *   - re-entrant: no global mutable state; concurrent calls need distinct workspaces.
+ *   - re-entrant: no global mutable state (bar a write-once per-device cache of launch geometry);
+ *     concurrent calls need distinct workspaces.
  *
  * Semantics that are identical to the reference:
  *   - pixel (wi,hi) of Gaussian g is evaluated iff  |px(wi)-x| <= dmax  and  |py(hi)-y| <= dmax
