@@ -162,6 +162,58 @@ GSO_API void gso_forward(const float* sigmas, const float* coords, const float* 
   free(py);
 }
 
+/* Same sum restricted to the pixel rectangle rows [cy0, cy0+ch) x columns [cx0, cx0+cw) of the h x w image:
+ * crop (ch,cw,3) double, ACCUMULATED into.  Every Gaussian whose window reaches the rectangle contributes
+ * exactly the pairs gso_forward would have summed there (used by the full-size parity tests, where the
+ * whole image is out of the CPU's reach). */
+GSO_API void gso_forward_crop(const float* sigmas, const float* coords, const float* colors, double* crop,
+                              int s, int h, int w, float dmax, int mode, int cy0, int cx0, int ch, int cw) {
+  int* ranges = (int*)malloc(sizeof(int) * 4 * (size_t)(s > 0 ? s : 1));
+  gso_ranges(coords, s, h, w, dmax, ranges);
+  float* px = (float*)malloc(sizeof(float) * (size_t)w);
+  float* py = (float*)malloc(sizeof(float) * (size_t)h);
+  for (int i = 0; i < w; ++i) px[i] = pix_coord(i, w);
+  for (int i = 0; i < h; ++i) py[i] = pix_coord(i, h);
+#pragma omp parallel
+  {
+#ifdef _OPENMP
+    const int nt = omp_get_num_threads(), t = omp_get_thread_num();
+#else
+    const int nt = 1, t = 0;
+#endif
+    const int r0 = cy0 + (int)((long long)ch * t / nt), r1 = cy0 + (int)((long long)ch * (t + 1) / nt) - 1;
+    for (int g = 0; g < s; ++g) {
+      int x0 = ranges[4 * g], x1 = ranges[4 * g + 1];
+      int y0 = ranges[4 * g + 2], y1 = ranges[4 * g + 3];
+      if (x1 < x0 || y1 < y0) continue;
+      if (y0 < r0) y0 = r0;
+      if (y1 > r1) y1 = r1;
+      if (x0 < cx0) x0 = cx0;
+      if (x1 > cx0 + cw - 1) x1 = cx0 + cw - 1;
+      if (x1 < x0 || y1 < y0) continue;
+      const float sx = sigmas[3 * g], sy = sigmas[3 * g + 1], rho = sigmas[3 * g + 2];
+      const float cx = coords[2 * g], cy = coords[2 * g + 1];
+      const double cr = colors[3 * g], cg = colors[3 * g + 1], cb = colors[3 * g + 2];
+      for (int hi = y0; hi <= y1; ++hi) {
+        volatile float dyv = py[hi] - cy;
+        const float dy = dyv;
+        for (int wi = x0; wi <= x1; ++wi) {
+          volatile float dxv = px[wi] - cx;
+          const float dx = dxv;
+          const double v = pair_value(sx, sy, rho, dx, dy, mode);
+          double* o = crop + ((size_t)(hi - cy0) * cw + (wi - cx0)) * 3;
+          o[0] += v * cr;
+          o[1] += v * cg;
+          o[2] += v * cb;
+        }
+      }
+    }
+  }
+  free(ranges);
+  free(px);
+  free(py);
+}
+
 /* grads (h,w,3) float; outputs double, ACCUMULATED into: g_sigmas (s,3), g_coords (s,2),
  * g_colors (s,3).  Formulas: gs.cu:134-159. */
 GSO_API void gso_backward(const float* sigmas, const float* coords, const float* colors,

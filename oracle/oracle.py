@@ -5,8 +5,8 @@ bench.py's cpu_baseline / --impl reference legs -- never from gsasr_b200/.
 Oracle status: PINNED against (a) the reference's own brute-force formula, check.py's
 ``torch_version`` (utils/gs_cuda_dmax/check.py:4-31, run on CPU by tests/golden/make_golden.py,
 fixtures committed), and (b) the reference's CUDA kernels themselves, compiled unmodified from
-/root/reference into oracle/_ref/ and run on the B200 (tests/test_gpu_parity.py, and fixtures
-captured from them in tests/golden/ref_gpu_*.npz).
+/root/reference into oracle/_ref/ and run on the B200 (tests/test_gpu_parity.py,
+tests/test_gpu_fullsize.py).
 """
 from __future__ import annotations
 
@@ -63,6 +63,9 @@ def lib():
         L.gso_backward.argtypes = [_f32p, _f32p, _f32p, _f32p, _f64p, _f64p, _f64p, ctypes.c_int,
                                    ctypes.c_int, ctypes.c_int, ctypes.c_float]
         L.gso_backward.restype = None
+        L.gso_forward_crop.argtypes = [_f32p, _f32p, _f32p, _f64p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_float, ctypes.c_int] + [ctypes.c_int] * 4
+        L.gso_forward_crop.restype = None
         _lib = L
     return _lib
 
@@ -103,6 +106,23 @@ def forward(sigmas, coords, colors, h: int, w: int, dmax: float = float("inf"), 
     lib().gso_forward(_p(sigmas, _f32p), _p(coords, _f32p), _p(colors, _f32p), _p(img, _f64p),
                       _p(cnt, _i32p) if with_count else None, s, h, w, float(dmax), int(mode))
     return (img, cnt) if with_count else img
+
+
+def forward_crop(sigmas, coords, colors, h: int, w: int, dmax: float, y0: int, x0: int, ch: int, cw: int,
+                 mode: int = 0, rr=None) -> np.ndarray:
+    """Rows [y0, y0+ch) x columns [x0, x0+cw) of forward(...): float64 (ch,cw,3).  Exact -- every Gaussian
+    whose dmax window reaches the rectangle is summed -- but only the rectangle's pixels are evaluated, so
+    the full-size configs (4096^2) are within the CPU's reach."""
+    sigmas, coords, colors = _f32(sigmas), _f32(coords), _f32(colors)
+    assert 0 <= y0 and y0 + ch <= h and 0 <= x0 and x0 + cw <= w
+    if rr is None:  # (s,4) inclusion ranges; pass them in when several crops share the field
+        rr = ranges(coords, h, w, dmax)
+    sel = np.nonzero((rr[:, 0] < x0 + cw) & (rr[:, 1] >= x0) & (rr[:, 2] < y0 + ch) & (rr[:, 3] >= y0))[0]
+    sg, xy, col = (np.ascontiguousarray(a[sel]) for a in (sigmas, coords, colors))
+    crop = np.zeros((ch, cw, 3), dtype=np.float64)
+    lib().gso_forward_crop(_p(sg, _f32p), _p(xy, _f32p), _p(col, _f32p), _p(crop, _f64p), sg.shape[0], h, w,
+                           float(dmax), int(mode), int(y0), int(x0), int(ch), int(cw))
+    return crop
 
 
 def backward(sigmas, coords, colors, grads, dmax: float = float("inf")):

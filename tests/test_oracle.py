@@ -87,3 +87,17 @@ def test_frontend_fixture_matches_field_mapping():
         assert np.array_equal(sig.numpy(), g["sigmas"])
         assert np.array_equal(xy.numpy(), g["coords"])
         assert np.array_equal(col.numpy(), g["colors"])
+
+
+def test_crop_render_equals_the_same_rectangle_of_the_whole_render():
+    """oracle.forward_crop is the checker of the full-size GPU tests: pin it to oracle.forward."""
+    rng = np.random.default_rng(9)
+    s, h, w = 500, 70, 90
+    sig = np.stack([rng.uniform(0.01, 0.2, s), rng.uniform(0.01, 0.2, s), rng.uniform(-0.95, 0.95, s)], 1)
+    xy = rng.uniform(-1.1, 1.1, (s, 2))
+    col = rng.uniform(0, 1, (s, 3))
+    for dmax in (0.12, float("inf")):
+        whole = oracle.forward(sig, xy, col, h, w, dmax)
+        for y0, x0, ch, cw in ((0, 0, 16, 24), (54, 66, 16, 24), (20, 31, 33, 7), (0, 0, h, w)):
+            crop = oracle.forward_crop(sig, xy, col, h, w, dmax, y0, x0, ch, cw)
+            assert np.array_equal(crop, whole[y0:y0 + ch, x0:x0 + cw])
