@@ -86,6 +86,7 @@ TEST_SIGNATURES = {
     "gsr_host_setup_band": (None, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _f, _vp]),
     "gsr_host_window_range": (None, [_i, _f, _f, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "gsr_host_region_mask": (ctypes.c_uint, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _i]),
+    "gsr_host_entries": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _i]),
     "gsr_host_geometry": (None, [ctypes.POINTER(_i)] * 5),
 }
 

@@ -36,6 +36,18 @@ constexpr int GSR_NRX = GSR_TILE_W / GSR_REGION, GSR_NRY = GSR_TILE_H / GSR_REGI
 constexpr int GSR_LARGE_PX = GSR_CFG_LARGE_PX;  // half-extent above which a Gaussian goes to the "large" list
 static_assert(GSR_NRX * GSR_NRY <= 16, "region mask is 16 bits");
 constexpr int GSR_MAX_DIM = 32767;    // bbox corners are stored as int16
+// Region buckets of the forward fast path: one warp of gsr_forward_region_kernel rasterises a
+// GSR_RGW x GSR_RGH pixel region (a 2x2 pixel block per lane); four lanes -- a 4x4-pixel CELL -- share one
+// bit of the 8-bit cell mask every bucket entry carries (bit = cell row * 4 + cell column).
+#ifndef GSR_CFG_MASK_PER_BAND
+#define GSR_CFG_MASK_PER_BAND 0
+#endif
+constexpr int GSR_RGW = 16, GSR_RGH = 8, GSR_CELL = 4;
+constexpr int GSR_CELLS_X = GSR_RGW / GSR_CELL, GSR_CELLS_Y = GSR_RGH / GSR_CELL;
+static_assert(GSR_CELLS_X * GSR_CELLS_Y == 8 && GSR_CELLS_Y == 2, "entry = index | cell mask (8 bit) << 23 | binds << 31");
+constexpr int GSR_ENT_MASK_SHIFT = 23;
+constexpr uint32_t GSR_ENT_INDEX = (1u << GSR_ENT_MASK_SHIFT) - 1u;
+constexpr int GSR_BUCKET_MAX_S = 1 << GSR_ENT_MASK_SHIFT;  // more Gaussians per call than this take the home-bin path
 constexpr float GSR_LOG2E = 1.4426950408889634f;
 constexpr float GSR_CULL_PAD_PX = 0.02f;  // slack on every culling bound (pixels)
 
@@ -153,6 +165,40 @@ GSR_HD GsrSetup gsr_setup(float sx, float sy, float rho, float x, float y, float
     return o;
   if (sx == 0.0f || sy == 0.0f || !(fabsf(rho) < 1.0f)) return o;
 
+  // Fast path (single precision): the k-sigma box lies at least three pixels inside the dmax window on every
+  // side, so the window cannot bind and the box is a pure truncation bound -- pixels it drops carry less than
+  // exp(-k^2/2) whichever way a boundary pixel falls (fp32 rounding of the centre, <= 1e-3 px at 32767, is
+  // covered by the pad).  Everything else (window binds or nearly does, huge values) takes the double path.
+  {
+    const float hxf = 0.5f * (float)(w - 1), hyf = 0.5f * (float)(hf - 1);
+    const float cxf = (x + 1.0f) * hxf, cyf = (y + 1.0f) * hyf;
+    const float exf = ksigma * fabsf(sx) * hxf + (GSR_CULL_PAD_PX + 2.0e-6f * fabsf(cxf));
+    const float eyf = ksigma * fabsf(sy) * hyf + (GSR_CULL_PAD_PX + 2.0e-6f * fabsf(cyf));
+    const bool nowin = dmax != dmax || dmax >= 3.0e38f;
+    const bool inside = nowin || (dmax >= 0.0f && exf + 3.0f < dmax * hxf && eyf + 3.0f < dmax * hyf);
+    if (inside && fabsf(cxf) < 1.0e8f && fabsf(cyf) < 1.0e8f && exf < 1.0e8f && eyf < 1.0e8f) {
+      const int kx0 = (int)ceilf(cxf - exf), kx1 = (int)floorf(cxf + exf);
+      const int ky0 = (int)ceilf(cyf - eyf), ky1 = (int)floorf(cyf + eyf);
+      o.x0 = kx0 > 0 ? kx0 : 0;
+      o.x1 = kx1 < w - 1 ? kx1 : w - 1;
+      o.y0 = (ky0 > row0 ? ky0 : row0) - row0;  // band-local
+      o.y1 = (ky1 < rend ? ky1 : rend) - row0;
+      if (o.x0 > o.x1 || o.y0 > o.y1) return o;
+      o.live = true;
+      const float cyl = cyf - (float)row0;
+      const int nbx = (w + GSR_BIN - 1) / GSR_BIN, nby = (h + GSR_BIN - 1) / GSR_BIN;
+      const float bx = floorf(cxf * (1.0f / GSR_BIN)), by = floorf(cyl * (1.0f / GSR_BIN));
+      o.bin_x = (int)fminf(fmaxf(bx, 0.0f), (float)(nbx - 1));
+      o.bin_y = (int)fminf(fmaxf(by, 0.0f), (float)(nby - 1));
+      const float ccx = fminf(fmaxf(cxf, 0.0f), (float)(w - 1)), ccy = fminf(fmaxf(cyl, 0.0f), (float)(h - 1));
+      const float dxm = fmaxf(ccx - (float)o.x0, (float)o.x1 - ccx);
+      const float dym = fmaxf(ccy - (float)o.y0, (float)o.y1 - ccy);
+      o.ext_x = (int)ceilf(fmaxf(dxm, 0.0f));
+      o.ext_y = (int)ceilf(fmaxf(dym, 0.0f));
+      o.large = (o.ext_x > GSR_LARGE_PX) || (o.ext_y > GSR_LARGE_PX);
+      return o;
+    }
+  }
   const double hx = 0.5 * (double)(w - 1), hy = 0.5 * (double)(hf - 1);
   const double cx = ((double)x + 1.0) * hx, cy = ((double)y + 1.0) * hy;
   const double ex = (double)ksigma * fabs((double)sx) * hx + (double)GSR_CULL_PAD_PX;
@@ -211,15 +257,17 @@ GSR_HD GsrSetup gsr_setup(float sx, float sy, float rho, float x, float y, float
 //   E = log2(e) * w1 * (w2 dx^2 - 2 rho w3 dx dy + w4 dy^2),  w1 = -0.5/(1-rho^2), w2 = 1/sx^2 ...
 GSR_HD GsrRec gsr_make_rec(float sx, float sy, float rho, float x, float y, float cr, float cg,
                            float cb) {
-  const double r = (double)rho;
-  const double w1 = -0.5 / (1.0 - r * r) * 1.4426950408889634;
-  const double isx = 1.0 / (double)sx, isy = 1.0 / (double)sy;
+  // 1 - rho^2 cancels for |rho| -> 1 (the head emits up to 0.999999): formed in double, rounded once; the
+  // rest is single precision (relative error of a, b, c <= 4e-7, i.e. <= 2e-7 absolute on a value).
+  const float omr = (float)(1.0 - (double)rho * (double)rho);
+  const float w1 = -0.5f * GSR_LOG2E / omr;
+  const float isx = 1.0f / sx, isy = 1.0f / sy;
   GsrRec o;
   o.x = x;
   o.y = y;
-  o.a = (float)(w1 * isx * isx);
-  o.b = (float)(-2.0 * r * w1 * isx * isy);
-  o.c = (float)(w1 * isy * isy);
+  o.a = w1 * isx * isx;
+  o.b = -2.0f * rho * w1 * isx * isy;
+  o.c = w1 * isy * isy;
   o.r = cr;
   o.g = cg;
   o.bl = cb;
@@ -252,7 +300,27 @@ GSR_HD GsrEllipse gsr_ellipse(const GsrRec& g, int h, int w, int hf = 0, int row
   e.inv_a = 1.0f / a;
   e.kappa = -0.5f * b * e.inv_a;
   e.cp = c + 0.5f * e.kappa * b;
+  // a degenerate conic (overflow, a = 0) must not cull: an ellipse as wide as the box, checked ONCE here so
+  // that gsr_band_xrange needs no NaN handling
+  if (!(gsr_finite(e.inv_a) && gsr_finite(e.kappa) && gsr_finite(e.cp) && gsr_finite(e.cx) && gsr_finite(e.cy)) ||
+      !(e.inv_a < 0.0f) || e.cp > 0.0f) {
+    e.inv_a = -3.0e37f;
+    e.kappa = 0.0f;
+    e.cp = 0.0f;
+    e.cx = gsr_finite(e.cx) ? e.cx : 0.0f;
+    e.cy = gsr_finite(e.cy) ? e.cy : 0.0f;
+  }
   return e;
+}
+
+GSR_HD float gsr_sqrt_fast(float v) {
+#ifdef __CUDA_ARCH__
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));   // 1 MUFU; its 2^-22 relative error is inside the pad
+  return r;
+#else
+  return sqrtf(v);
+#endif
 }
 
 // Conservative pixel x-range [xl, xh] of {E >= ecut} over the rows ya..yb (inclusive, already
@@ -264,20 +332,13 @@ GSR_HD bool gsr_band_xrange(const GsrEllipse& e, float ecut, int ya, int yb, int
   // can only widen the band
   float t = da > 0.0f ? da : (db < 0.0f ? db : 0.0f);
   t = t > 0.0f ? fmaxf(t - GSR_CULL_PAD_PX, 0.0f) : fminf(t + GSR_CULL_PAD_PX, 0.0f);
-  float w2 = (ecut - e.cp * t * t) * e.inv_a;
-  if (!(w2 >= 0.0f)) {
-    if (w2 < 0.0f) return false;  // band entirely outside the ellipse
-    w2 = 3.0e38f;                 // NaN/inf from a degenerate conic: do not cull
-  }
-  const float hw = sqrtf(w2) + GSR_CULL_PAD_PX + 1.0e-6f * fabsf(e.cx);  // fp32 slack on cx
+  const float w2 = (ecut - e.cp * t * t) * e.inv_a;
+  if (w2 < 0.0f) return false;  // band entirely outside the ellipse
+  // fp32 slack on cx and on the approximate square root
+  const float hw = gsr_sqrt_fast(w2) * 1.000001f + (GSR_CULL_PAD_PX + 1.0e-6f * fabsf(e.cx));
   const float ma = e.cx + e.kappa * da, mb = e.cx + e.kappa * db;
-  float lo = fminf(ma, mb) - hw, hi = fmaxf(ma, mb) + hw;
-  if (!(lo == lo) || !(hi == hi)) {
-    lo = -3.0e38f;
-    hi = 3.0e38f;
-  }
-  lo = fmaxf(lo, (float)cx0);
-  hi = fminf(hi, (float)cx1);
+  const float lo = fmaxf(fminf(ma, mb) - hw, (float)cx0);
+  const float hi = fminf(fmaxf(ma, mb) + hw, (float)cx1);
   xl = (int)ceilf(lo);
   xh = (int)floorf(hi);
   return xl <= xh;
@@ -305,6 +366,87 @@ GSR_HD uint32_t gsr_region_mask(const GsrRec& g, int bx0, int bx1, int by0, int 
     mask |= bits << (ry * GSR_NRX);
   }
   return mask;
+}
+
+// ---- cell masks of the region buckets -----------------------------------------------------------
+// Cell-column ranges (4-pixel cells, inclusive; empty: cl > ch) of the two cell rows of region band `band`
+// (rows band*8 .. band*8+7) that the ellipse {E >= ecut} touches inside the cull box [x0,x1] x [y0,y1].
+// Returns false if the band is empty.  Conservative like gsr_band_xrange.
+GSR_HD bool gsr_band_cells(const GsrEllipse& e, float ecut, int band, int x0, int x1, int y0, int y1,
+                           int cl[2], int ch[2]) {
+#if GSR_CFG_MASK_PER_BAND
+  // one x-range for the whole band (the hull over its rows), given to every cell row the box reaches: the
+  // vertical culling stays exact (the box's y-range is the ellipse's), the horizontal one is that of 8 rows
+  int ya = band * GSR_RGH, yb = ya + GSR_RGH - 1, xl, xh;
+  ya = ya > y0 ? ya : y0;
+  yb = yb < y1 ? yb : y1;
+  cl[0] = cl[1] = 1;
+  ch[0] = ch[1] = 0;
+  if (ya > yb || !gsr_band_xrange(e, ecut, ya, yb, x0, x1, xl, xh)) return false;
+#pragma unroll
+  for (int r = 0; r < GSR_CELLS_Y; ++r) {
+    const int ra = band * GSR_RGH + r * GSR_CELL, rb_ = ra + GSR_CELL - 1;
+    if (ra <= yb && rb_ >= ya) {
+      cl[r] = xl / GSR_CELL;
+      ch[r] = xh / GSR_CELL;
+    }
+  }
+  return true;
+#else
+  bool any = false;
+#pragma unroll
+  for (int r = 0; r < GSR_CELLS_Y; ++r) {
+    int ya = band * GSR_RGH + r * GSR_CELL, yb = ya + GSR_CELL - 1, xl, xh;
+    ya = ya > y0 ? ya : y0;
+    yb = yb < y1 ? yb : y1;
+    cl[r] = 1;
+    ch[r] = 0;
+    if (ya <= yb && gsr_band_xrange(e, ecut, ya, yb, x0, x1, xl, xh)) {
+      cl[r] = (int)((unsigned)xl / GSR_CELL);  // 0 <= xl <= xh: unsigned division is a shift
+      ch[r] = (int)((unsigned)xh / GSR_CELL);
+      any = true;
+    }
+  }
+  return any;
+#endif
+}
+// Region-column range [c0, c1] of a band whose cell ranges are (cl, ch) (at least one non-empty).
+GSR_HD void gsr_band_columns(const int cl[2], const int ch[2], int& c0, int& c1) {
+  const bool e0 = cl[0] <= ch[0], e1 = cl[1] <= ch[1];
+  const int lo = e0 ? (e1 ? (cl[0] < cl[1] ? cl[0] : cl[1]) : cl[0]) : cl[1];
+  const int hi = e0 ? (e1 ? (ch[0] > ch[1] ? ch[0] : ch[1]) : ch[0]) : ch[1];
+  c0 = lo / GSR_CELLS_X;
+  c1 = hi / GSR_CELLS_X;
+}
+// 8-bit cell mask of region column c.
+GSR_HD uint32_t gsr_cell_mask(const int cl[2], const int ch[2], int c) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int r = 0; r < GSR_CELLS_Y; ++r) {
+    int lo = cl[r] - c * GSR_CELLS_X, hi = ch[r] - c * GSR_CELLS_X;
+    lo = lo > 0 ? lo : 0;
+    hi = hi < GSR_CELLS_X - 1 ? hi : GSR_CELLS_X - 1;
+    if (lo <= hi) m |= (((2u << hi) - 1u) & ~((1u << lo) - 1u)) << (r * GSR_CELLS_X);
+  }
+  return m;
+}
+
+// Row bitmaps: the same cell ranges as bit sets relative to cell column `cbase` (bit j = cell cbase + j), valid
+// when the cull box spans at most 32 cells from cbase.  The cell mask of region column c is then two shifts away.
+GSR_HD bool gsr_band_rowbits(const GsrEllipse& e, float ecut, int band, int x0, int x1, int y0, int y1, int cbase,
+                             uint32_t rb[2]) {
+  int cl[2], ch[2];
+  if (!gsr_band_cells(e, ecut, band, x0, x1, y0, y1, cl, ch)) return false;
+#pragma unroll
+  for (int r = 0; r < GSR_CELLS_Y; ++r) {
+    const int lo = cl[r] - cbase, hi = ch[r] - cbase;
+    rb[r] = lo <= hi ? (((2u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+  }
+  return true;
+}
+GSR_HD uint32_t gsr_rowbits_mask(const uint32_t rb[2], int c, int cbase) {
+  const unsigned sh = (unsigned)(c * GSR_CELLS_X - cbase);
+  return ((rb[0] >> sh) & 0xfu) | (((rb[1] >> sh) & 0xfu) << GSR_CELLS_X);
 }
 
 // Default and exact k-sigma handling shared by host API and kernels.

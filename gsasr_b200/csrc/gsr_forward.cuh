@@ -5,8 +5,9 @@
 // Here pixels are gathered: accumulators live in registers and every pixel is written once.
 //
 //   gsr_forward_region_kernel  (the fast path, second half of this file)  streams the per-region
-//       buckets built by gsr_region_build_kernel: half a warp per 8x8-pixel region, a 2x2 pixel block
-//       per lane, persistent independent warps, two-deep cp.async prefetch.  See its own comment.
+//       buckets built by gsr_region_build_kernel: a warp per 16x8-pixel region, a 2x2 pixel block per lane,
+//       every 4x4-pixel cell (four lanes) evaluating only the entries whose cell mask names it, persistent
+//       independent warps, two-deep cp.async prefetch.  See its own comment.
 //   gsr_forward_bins_kernel    (the fallback, runs when a bucket overflowed)  finds a tile's candidates
 //       at run time.  The image is cut into 32x16 tiles, one CTA per tile (persistent over tiles), 8 warps
 //       each owning an 8x8 region (two horizontally adjacent pixels per lane).  Per tile, in rounds of
@@ -148,7 +149,7 @@ struct GsrFwdArgs {
   const uint32_t* entries;
   const GsrRec* rec_in;
   const uint2* box_in;
-  int ntx;
+  int* sched;    // {next unit, finished warps}: dynamic work distribution, left at zero by the kernel
   int hf, row0;  // row-band view (see gsr_setup)
   int bhs;       // uniform batch: rows per sample of the stacked image (0: single image)
   // destination addressing, in floats: pixel (hi, wi), channel ch lives at
@@ -405,53 +406,77 @@ __global__ void __launch_bounds__(GSR_FWD_THREADS, GSR_CFG_MIN_CTAS) gsr_forward
 }
 
 // ---- region-bucket forward kernel (the fast path) ------------------------------------------------
-// One HALF-warp per 8x8-pixel region, a 2x2 pixel block per lane (accumulators in registers: six FP32x2
-// pairs), so a warp rasterises two horizontally adjacent regions at once, each half streaming its OWN
-// bucket (4-byte Gaussian indices written by gsr_region_build_kernel): the two halves read different
-// records with the same LDS.128 (one address per quarter-warp phase: conflict-free).  Per iteration --
-// one record per half, 128 pixel evaluations -- the warp issues 2 LDS.128, 2 FADD2 (dx, dy pairs),
-// 3 FMUL2 (row terms), 4 FFMA2 (exponents), 4 MUFU.EX2 and 6 FFMA2 (colour pairs): 21 instructions,
-// against 2 x 15 for the same work with one 1x2 block per lane.  FFMA2/FADD2/FMUL2 issue at full rate on
-// sm_100 (tools/ubench.cu), so the MUFU pipe (8 cycles per warp instruction per sub-partition) is the one
-// bound left: 32 cycles per iteration.
+// One warp per 16x8-pixel region, a 2x2 pixel block per lane (accumulators in registers: six FP32x2 pairs);
+// the four lanes of a 4x4-pixel CELL move together.  A bucket entry (written by gsr_region_build_kernel)
+// carries the Gaussian's index and an 8-bit mask of the cells its k-sigma ellipse reaches, and every cell
+// evaluates ONLY the entries that name it: of the 128 pixels of a region a Gaussian of the x4 head reaches
+// ~65 (half the cells), so half of the exponentials a whole-region evaluation would issue never are.
 //
-// Warps are persistent and independent (no CTA barrier, nothing shared between warps): warp g takes the
-// region pairs g, g + W, g + 2W, ...  Buckets are streamed in chunks of 32 entries per half through a
-// private, double-buffered shared-memory slice, two-deep: while chunk k is evaluated the records of chunk
-// k+1 are in flight as cp.async copies (global -> shared, no register staging; past the end of a bucket
-// the copy zero-fills, which makes a null record that adds exactly 0) and the entries of chunk k+2 are in
-// flight as loads whose values are not touched before the next iteration.  The chunk stream is flat over
-// the warp's units -- the bucket lengths of the next two units are requested a unit ahead -- so the
-// count -> entry -> record dependency chain is never waited for after the prologue.  Trip counts are
-// rounded up to a multiple of 4 with null records, so the evaluation loop is made of fully unrolled
-// blocks (16, 8, 4 records) with immediate shared-memory offsets.  Window-binding Gaussians (entry bit 31) also bring their
-// cull box and are evaluated with the exact per-pixel inclusion test.
-constexpr int GSR_FR_WARPS = 8;
+// Per chunk of up to 64 entries the warp (i) stages the 32-byte records with cp.async (global -> shared, no
+// register staging), (ii) turns the masks into eight per-cell slot lists in shared memory -- 16 ballots, the
+// ranks are popcounts, no atomics -- padded with the slot of a null record to a multiple of four, and
+// (iii) runs ONE loop of T = max over the cells of the list length: each lane reads its own cell's next
+// four slots (one LDS.32) and evaluates those records, so lanes of different cells work on different
+// records in the same instruction (LDS.128 with one address per cell: conflict-free or two-way).
+// Per record and lane: 2 LDS.128, 2 FADD2 (dx, dy pairs; the pixel coordinates are held negated), 3 FMUL2
+// (row terms), 4 FFMA2 (exponents), 4 MUFU.EX2, 6 FFMA2 (colours) + 2 integer instructions for the address.
+// A chunk takes every nch-th entry of the bucket (nch = chunks of the bucket), so that each is a stratified
+// sample of the bucket's Gaussians -- which arrive sorted by position for a fea2gs field -- and the eight
+// lists of a chunk come out nearly equally long (the loop runs as long as the longest).
+//
+// Warps are persistent and independent (no CTA barrier, nothing shared between warps) and take regions
+// from a global counter (fetched three regions ahead, so the atomic's latency is never waited for).  The
+// chunk stream is flat over a warp's regions, two-deep: while chunk k is evaluated the records of chunk k+1
+// are in flight as cp.async copies and the entries of chunk k+2 as loads whose values are not touched
+// before the next iteration.  Window-binding Gaussians (entry bit 31) also bring their cull box and are
+// evaluated with the exact per-pixel inclusion test.
+constexpr int GSR_FR_WARPS = 4;
 constexpr int GSR_FR_THREADS = 32 * GSR_FR_WARPS;
-constexpr int GSR_FR_CHUNK = 32;                       // records per half-warp per stage (two per lane)
-constexpr int GSR_FR_HALF_BYTES = GSR_FR_CHUNK * 32;   // one half's records of one stage
-constexpr int GSR_FR_STAGE_BYTES = 2 * GSR_FR_HALF_BYTES;
+constexpr int GSR_FR_CHUNK = 64;                          // entries per stage (two per lane)
+constexpr int GSR_FR_SLOTS = GSR_FR_CHUNK + 1;            // + the null record (slot GSR_FR_CHUNK)
+constexpr int GSR_FR_HI = GSR_FR_SLOTS * 16;              // byte offset of the second float4 of a record
+constexpr int GSR_FR_STAGE_BYTES = 2 * GSR_FR_HI;
+constexpr int GSR_FR_LIST = 2 * (GSR_FR_CHUNK + 4);       // bytes per cell list (16-bit shared addresses): 34 words, so
+                                                          // the eight cells' LDS.64 fall into different banks
+constexpr int GSR_FR_LIST_STAGE = 8 * GSR_FR_LIST;        // 1088 = 68 x 16
 #ifndef GSR_CFG_FR_MIN_CTAS
-#define GSR_CFG_FR_MIN_CTAS 3
+#define GSR_CFG_FR_MIN_CTAS 6
 #endif
-static_assert(GSR_REGION == 8, "a half-warp of 2x2 blocks covers an 8x8 region");
+static_assert(GSR_RGW == 16 && GSR_RGH == 8 && GSR_CELL == 4, "a warp of 2x2 blocks covers a 16x8 region, four lanes a cell");
 
 struct GsrFwdRegionSmem {
-  float4 rec[GSR_FR_WARPS][2][2 * GSR_FR_CHUNK * 2];  // per warp, 2 stages x 2 halves x 32 records x 2 float4
-  uint2 box[GSR_FR_WARPS][2][2 * GSR_FR_CHUNK];
+  float4 rec[GSR_FR_WARPS][2][2 * GSR_FR_SLOTS];   // per warp, 2 stages x { first float4 x 65, second float4 x 65 }
+  uint2 box[GSR_FR_WARPS][2][GSR_FR_CHUNK];
+  uint32_t list[GSR_FR_WARPS][2][GSR_FR_LIST_STAGE / 4];
 };
+static_assert(sizeof(GsrFwdRegionSmem) + 1024 < 65536, "cell lists hold 16-bit shared-memory addresses");
 
 __device__ __forceinline__ gsr_f2 gsr_mul2(gsr_f2 a, gsr_f2 b) {
   gsr_f2 d;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-// cp.async with a source size: 0 zero-fills the destination without reading.
-__device__ __forceinline__ void gsr_cp_async16z(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+__device__ __forceinline__ void gsr_cp_async16ca(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void gsr_cp_async8(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ uint32_t gsr_lds32u(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void gsr_sts16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%1], %0;" ::"h"((unsigned short)v), "r"(addr) : "memory");
+}
+__device__ __forceinline__ uint2 gsr_lds64u(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void gsr_sts128u(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(v) : "memory");
 }
 
 // One Gaussian against this lane's 2x2 pixel block.  nx2/ny2 hold the NEGATED pixel coordinates, so
@@ -494,10 +519,6 @@ __device__ __forceinline__ void gsr_eval_quad(uint32_t addr0, uint32_t addr1, gs
   b1 = gsr_fma2(vb, cb, b1);
 }
 
-// Shared-memory slot of record j of a half: the two float4 of records 4..7, 12..15, ... are swapped, which
-// spreads the lane-per-record staging writes over all banks; the readers' offsets stay immediates.
-__device__ __forceinline__ uint32_t gsr_fr_swz(int j) { return (uint32_t)((j >> 2) & 1) * 16u; }
-
 // WINDOW = false: the plain (h,w,3) / (3,h,w) image, addressed with compile-time-simple arithmetic;
 // WINDOW = true: the general strided destination with clip rectangles (gsr_forward_window).
 template <bool WINDOW>
@@ -505,145 +526,209 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
   if (gsr_guard_skip(p.guard, p.want)) return;
   __shared__ GsrFwdRegionSmem sm;
   constexpr int CH = GSR_FR_CHUNK;
+  const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int half = lane >> 4, l16 = lane & 15;
-  const int npx = p.nrx >> 1;  // region pairs per region row (nrx is a multiple of 4)
-  const int nunits = npx * p.nry;
-  const int nw = gridDim.x * GSR_FR_WARPS;
-  int u = blockIdx.x * GSR_FR_WARPS + warp;  // unit = pair of horizontally adjacent regions
-  if (u >= nunits) return;
-  const uint32_t rec_h = gsr_smem_addr(&sm.rec[warp][0][0]) + half * GSR_FR_HALF_BYTES;  // this half's slice, stage 0
+  const int cell = lane >> 2;
+  const unsigned lt = (1u << lane) - 1u;
+  const int nunits = p.nrx * p.nry;
+  const uint32_t rec_s = gsr_smem_addr(&sm.rec[warp][0][0]);
+  const uint32_t list_w = gsr_smem_addr(&sm.list[warp][0][0]);   // the warp's lists, stage 0
+  const uint32_t list_c = list_w + cell * GSR_FR_LIST;           // this lane's cell
   const uint32_t box_s = gsr_smem_addr(&sm.box[warp][0][0]);
   const uint2* box_w = &sm.box[warp][0][0];
   const bool over = (p.flags & 1u) != 0, chw = (p.flags & 2u) != 0, u8 = (p.flags & 4u) != 0, bgr = (p.flags & 8u) != 0;
+  const int total_warps = gridDim.x * GSR_FR_WARPS;
 
-  // Region of this half in unit v (-1: past the end) and the (raw) length of its bucket.
-  auto region_of = [&](int v) { const int y = v / npx; return v < nunits ? y * p.nrx + (v - y * npx) * 2 + half : -1; };
-  auto count_of = [&](int rid) { return rid >= 0 ? __ldg(p.reg_count + rid) : 0; };  // clamp with reg_cap on use
+  // the null record of both stages (slot CH): zero conic and colour, adds exactly 0
+  if (lane < 4) sm.rec[warp][lane >> 1][(lane & 1) * GSR_FR_SLOTS + CH] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  // Entries l16 and l16 + 16 of chunk (rid, c) -- loaded values are not touched before they are consumed
-  // one chunk later; validity is decided from the indices alone, so nothing is waited for here.
+  // ---- work distribution: units are taken from a global counter, four at a time at first, then one per
+  // finished unit -- requested three units before it is needed.
+  int uA, uB, uC, pend;  // pend: lane 0's counter value, in flight until the next advance
+  {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(p.sched, 4);
+    base = __shfl_sync(full, base, 0);
+    uA = base, uB = base + 1, uC = base + 2, pend = base + 3;
+  }
+  auto finish = [&]() {  // the last warp to leave resets the counters for the next launch
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (lane == 0) {
+      __threadfence();
+      if (atomicAdd(p.sched + 1, 1) == total_warps - 1) {
+        p.sched[0] = 0;
+        p.sched[1] = 0;
+      }
+    }
+  };
+  if (uA >= nunits) {
+    finish();
+    return;
+  }
+
+  auto count_of = [&](int u) { return u < nunits ? __ldg(p.reg_count + u) : 0; };  // clamp with reg_cap on use
+  auto chunks_of = [&](int n) { return n > CH ? (n + CH - 1) / CH : 1; };
+
+  // Entries lane and lane + 32 of chunk ci of unit u: positions ci + k * nch.  Loaded values are not touched
+  // before they are consumed one chunk later; validity is decided from the indices alone.
   uint32_t e1a = 0, e1b = 0;
   bool v1a = false, v1b = false;
-  auto request_entries = [&](int rid, int c, int n) {
-    const int i = c + l16;
-    v1a = i < n;
-    v1b = i + 16 < n;
-    const uint32_t* src = p.entries + (size_t)(rid < 0 ? 0 : rid) * p.reg_cap + i;
-    e1a = v1a ? __ldg(src) : 0u;
-    e1b = v1b ? __ldg(src + 16) : 0u;
+  auto request_entries = [&](int u, int ci, int n, int nch) {
+    const int i0 = ci + lane * nch, i1 = i0 + 32 * nch;
+    v1a = i0 < n;
+    v1b = i1 < n;
+    const uint32_t* src = p.entries + (size_t)(u < nunits ? u : 0) * p.reg_cap;
+    e1a = v1a ? __ldg(src + i0) : 0u;
+    e1b = v1b ? __ldg(src + i1) : 0u;
   };
-  // Records of the requested entries -> stage `st` (cp.async; null records past the end of a bucket).
-  // Returns this lane's two "window binds" flags in bits 0 and 1.
-  auto stage_records = [&](int st) {
-    unsigned fl = 0;
+  // Records of the requested entries -> stage `st` (cp.async), their cell lists -> list stage `st`.
+  // Returns the trip count of the chunk (longest list, rounded up to 4) and the binds ballots.
+  unsigned slow_a = 0, slow_b = 0;
+  auto stage_chunk = [&](int st) -> int {
+    const uint32_t rb = rec_s + st * GSR_FR_STAGE_BYTES;
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       const uint32_t en = t ? e1b : e1a;
       const bool v = t ? v1b : v1a;
-      const uint32_t gi = v ? (en & 0x7fffffffu) : 0u;
-      const int j = l16 + 16 * t;
-      const char* src = reinterpret_cast<const char*>(p.rec_in + gi);
-      const uint32_t dst = rec_h + st * GSR_FR_STAGE_BYTES + j * 32, sw = gsr_fr_swz(j);
-      gsr_cp_async16z(dst + sw, src, v ? 16u : 0u);
-      gsr_cp_async16z(dst + (sw ^ 16u), src + 16, v ? 16u : 0u);
-      if (v && (en >> 31)) {
-        gsr_cp_async8(box_s + (st * 2 * CH + half * CH + j) * 8, p.box_in + gi);
-        fl |= 1u << t;
+      if (v) {
+        const uint32_t gi = en & GSR_ENT_INDEX;
+        const int k = lane + 32 * t;
+        const char* src = reinterpret_cast<const char*>(p.rec_in + gi);
+        gsr_cp_async16ca(rb + k * 16, src);
+        gsr_cp_async16ca(rb + GSR_FR_HI + k * 16, src + 16);
+        if (en >> 31) gsr_cp_async8(box_s + (st * CH + k) * 8, p.box_in + gi);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    return fl;
+    slow_a = __ballot_sync(full, v1a && (e1a >> 31));
+    slow_b = __ballot_sync(full, v1b && (e1b >> 31));
+    // per-cell lists of 16-bit shared-memory addresses (the CTA's shared window is < 64 KB): every slot starts as
+    // the null record's; the rank of an entry in the list of cell q = number of earlier entries that name q, in
+    // the order (lane 0: first, second entry), (lane 1: ...).  The eight ranks of an entry come from ONE warp
+    // scan: the masks are spread to a byte per cell (two registers), the bytes are prefix-summed across the lanes
+    // with shuffles (counts stay below 256: at most 64 entries) -- no popcounts (they share the MUFU pipe).
+    const uint32_t lw = list_w + st * GSR_FR_LIST_STAGE;
+    const uint32_t null2 = (rb + CH * 16u) * 0x00010001u;
+    gsr_sts128u(lw + lane * 16, null2);
+    gsr_sts128u(lw + 512 + lane * 16, null2);
+    if (lane < 4) gsr_sts128u(lw + 1024 + lane * 16, null2);
+    const uint32_t ma = v1a ? (e1a >> GSR_ENT_MASK_SHIFT) & 0xffu : 0u, mb = v1b ? (e1b >> GSR_ENT_MASK_SHIFT) & 0xffu : 0u;
+    const uint32_t a_lo = ((ma & 15u) * 0x00204081u) & 0x01010101u, a_hi = ((ma >> 4) * 0x00204081u) & 0x01010101u;
+    const uint32_t b_lo = ((mb & 15u) * 0x00204081u) & 0x01010101u, b_hi = ((mb >> 4) * 0x00204081u) & 0x01010101u;
+    uint32_t s_lo = a_lo + b_lo, s_hi = a_hi + b_hi;  // inclusive prefix sums, a byte per cell
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t0 = __shfl_up_sync(full, s_lo, d), t1 = __shfl_up_sync(full, s_hi, d);
+      if (lane >= d) {
+        s_lo += t0;
+        s_hi += t1;
+      }
+    }
+    const uint32_t t_lo = __shfl_sync(full, s_lo, 31), t_hi = __shfl_sync(full, s_hi, 31);
+    const uint32_t ra_lo = s_lo - a_lo - b_lo, ra_hi = s_hi - a_hi - b_hi;  // exclusive: rank of the first entry
+    const uint32_t rb_lo = ra_lo + a_lo, rb_hi = ra_hi + a_hi;              // the second entry follows the first
+    __syncwarp();  // the null fill is complete before the slots are written
+    const uint32_t adr_a = rb + lane * 16u, adr_b = adr_a + 32 * 16u;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t ra = ((q < 4 ? ra_lo : ra_hi) >> (8 * (q & 3))) & 0xffu;
+      const uint32_t rbq = ((q < 4 ? rb_lo : rb_hi) >> (8 * (q & 3))) & 0xffu;
+      if ((ma >> q) & 1u) gsr_sts16(lw + q * GSR_FR_LIST + 2 * ra, adr_a);
+      if ((mb >> q) & 1u) gsr_sts16(lw + q * GSR_FR_LIST + 2 * rbq, adr_b);
+    }
+    const uint32_t tot = cell < 4 ? t_lo : t_hi;
+    const int mine = (int)((tot >> (8 * (cell & 3))) & 0xffu);
+    return (__reduce_max_sync(full, mine) + 3) & ~3;
   };
 
-  // Three units in flight: A is evaluated, B and C are known far enough ahead for the two-deep
-  // prefetch to run across unit boundaries.
-  int ridA = region_of(u), ridB = region_of(u + nw), ridC = region_of(u + 2 * nw);
-  int nA = min(count_of(ridA), p.reg_cap), nB = min(count_of(ridB), p.reg_cap), nC = count_of(ridC);
-  int ntripA = max(nA, __shfl_xor_sync(0xffffffffu, nA, 16));  // the longer bucket of the pair
-  int ntripB = max(nB, __shfl_xor_sync(0xffffffffu, nB, 16));
+  // Units in flight: A is evaluated, B and C are known far enough ahead for the two-deep prefetch to run
+  // across unit boundaries, `pend` is the counter value still in flight.
+  int nA = min(count_of(uA), p.reg_cap), nB = min(count_of(uB), p.reg_cap), nC = count_of(uC);
+  int nchA = chunks_of(nA), nchB = chunks_of(nB);
 
-  request_entries(ridA, 0, nA);
-  unsigned fl = stage_records(0);
-  unsigned slow_a = __ballot_sync(0xffffffffu, fl & 1u), slow_b = __ballot_sync(0xffffffffu, fl & 2u);
-  if (CH < ntripA) request_entries(ridA, CH, nA); else request_entries(ridB, 0, nB);
+  request_entries(uA, 0, nA, nchA);
+  int trip = stage_chunk(0);
+  unsigned slow_ac = slow_a, slow_bc = slow_b;
+  if (1 < nchA) request_entries(uA, 1, nA, nchA); else request_entries(uB, 0, nB, nchB);
 
-  int cur = 0, c0 = 0;
-  int ry = ridA / p.nrx, rx = ridA - ry * p.nrx;
-  int wi0 = rx * GSR_REGION + (l16 & 3) * 2, hi0 = ry * GSR_REGION + (l16 >> 2) * 2;
-  gsr_f2 nx2 = gsr_pk(-__ldg(p.px_tab + min(wi0, p.w - 1)), -__ldg(p.px_tab + min(wi0 + 1, p.w - 1)));
-  gsr_f2 ny2 = gsr_pk(-__ldg(p.py_tab + min(hi0, p.h - 1)), -__ldg(p.py_tab + min(hi0 + 1, p.h - 1)));
+  int cur = 0, ci = 0;
+  // pixel block of this lane in unit u: cell (cell & 3, cell >> 2), block (lane & 1, (lane >> 1) & 1) of the cell
+  const int bx = (cell & 3) * GSR_CELL + (lane & 1) * 2, by = (cell >> 2) * GSR_CELL + ((lane >> 1) & 1) * 2;
+  auto coords_of = [&](int u, gsr_f2& nx, gsr_f2& ny) {
+    const int uy = (u < nunits ? u : 0) / p.nrx, ux = (u < nunits ? u : 0) - uy * p.nrx;
+    const int wi = ux * GSR_RGW + bx, hi = uy * GSR_RGH + by;
+    nx = gsr_pk(-__ldg(p.px_tab + min(wi, p.w - 1)), -__ldg(p.px_tab + min(wi + 1, p.w - 1)));
+    ny = gsr_pk(-__ldg(p.py_tab + min(hi, p.h - 1)), -__ldg(p.py_tab + min(hi + 1, p.h - 1)));
+  };
+  gsr_f2 nx2, ny2, nx2B, ny2B;
+  coords_of(uA, nx2, ny2);
+  coords_of(uB, nx2B, ny2B);
   gsr_f2 r0 = gsr_pk(0.f, 0.f), g0 = r0, b0 = r0, r1 = r0, g1 = r0, b1 = r0;
 
-  for (;;) {  // one chunk (32 records per half) per iteration, flat over the warp's units
-    const uint32_t buf = rec_h + cur * GSR_FR_STAGE_BYTES;
+  for (;;) {  // one chunk per iteration, flat over the warp's units
+    const uint32_t rb = rec_s + cur * GSR_FR_STAGE_BYTES;
+    const uint32_t lb = list_c + cur * GSR_FR_LIST_STAGE;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();  // this chunk's records are visible; the other stage is free
-    // records of the next chunk (their entries were requested one chunk ago) ...
-    fl = stage_records(cur ^ 1);
-    const unsigned slow_an = __ballot_sync(0xffffffffu, fl & 1u), slow_bn = __ballot_sync(0xffffffffu, fl & 2u);
-    // ... and the entries of the chunk after it: (A, c0 + 2 CH), (B, 0), (B, CH) or (C, 0)
-    const bool last = c0 + CH >= ntripA;
+    __syncwarp();  // this chunk's records and lists are visible; the other stage is free
+    // records and lists of the next chunk (its entries were requested one chunk ago) ...
+    const int trip_n = stage_chunk(cur ^ 1);
+    const unsigned slow_an = slow_a, slow_bn = slow_b;
+    // ... and the entries of the chunk after it: (A, ci + 2), (B, 0), (B, 1) or (C, 0)
+    const bool last = ci + 1 >= nchA;
     if (!last) {
-      if (c0 + 2 * CH < ntripA) request_entries(ridA, c0 + 2 * CH, nA); else request_entries(ridB, 0, nB);
+      if (ci + 2 < nchA) request_entries(uA, ci + 2, nA, nchA); else request_entries(uB, 0, nB, nchB);
     } else {
-      if (CH < ntripB) request_entries(ridB, CH, nB); else request_entries(ridC, 0, min(nC, p.reg_cap));
+      if (1 < nchB) request_entries(uB, 1, nB, nchB);
+      else { const int n = min(nC, p.reg_cap); request_entries(uC, 0, n, chunks_of(n)); }
     }
 
-    const int trip = min(CH, ntripA - c0);  // <= 0 for an empty pair
-    if ((slow_a | slow_b) == 0) {
-      int j = 0;
-      for (; j + 16 <= trip; j += 16) {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const uint32_t a = buf + j * 32 + k * 32;
-          gsr_eval_quad<false>(a + gsr_fr_swz(k), a + (gsr_fr_swz(k) ^ 16u), nx2, ny2, true, true, true, true,
-                               r0, g0, b0, r1, g1, b1);
-        }
-      }
-      for (; j + 8 <= trip; j += 8) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t a = buf + j * 32 + k * 32;
-          gsr_eval_quad<false>(a + gsr_fr_swz(k), a + (gsr_fr_swz(k) ^ 16u), nx2, ny2, true, true, true, true,
-                               r0, g0, b0, r1, g1, b1);
-        }
-      }
-      for (; j < trip; j += 4) {  // records past the end of a bucket are null
+    if ((slow_ac | slow_bc) == 0) {
+      for (int t = 0; t < trip; t += 4) {
+        const uint2 s4 = gsr_lds64u(lb + 2 * t);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint32_t a = buf + j * 32 + k * 32;
-          const uint32_t sw = gsr_fr_swz(j);  // j is a multiple of 4: one swizzle for the block
-          gsr_eval_quad<false>(a + sw, a + (sw ^ 16u), nx2, ny2, true, true, true, true, r0, g0, b0, r1, g1, b1);
+          const uint32_t w2 = k < 2 ? s4.x : s4.y;
+          const uint32_t a = (k & 1) ? (w2 >> 16) : (w2 & 0xffffu);
+          gsr_eval_quad<false>(a, a + GSR_FR_HI, nx2, ny2, true, true, true, true, r0, g0, b0, r1, g1, b1);
         }
       }
     } else {
-      for (int j = 0; j < trip; ++j) {
-        const uint32_t a = buf + j * 32, sw = gsr_fr_swz(j);
-        // record j of this half was staged by lane (half, j & 15) as its entry number j >> 4
-        if ((((j & 16) ? slow_b : slow_a) >> (half * 16 + (j & 15))) & 1u) {  // exact inclusion
-          int bx0, bx1, by0, by1;
-          bool binds;
-          gsr_box_unpack(box_w[cur * 2 * CH + half * CH + j], bx0, bx1, by0, by1, binds);
-          const bool y0in = hi0 >= by0 && hi0 <= by1, y1in = hi0 + 1 >= by0 && hi0 + 1 <= by1;
-          const bool x0in = wi0 >= bx0 && wi0 <= bx1, x1in = wi0 + 1 >= bx0 && wi0 + 1 <= bx1;
-          gsr_eval_quad<true>(a + sw, a + (sw ^ 16u), nx2, ny2, y0in && x0in, y0in && x1in, y1in && x0in,
-                              y1in && x1in, r0, g0, b0, r1, g1, b1);
-        } else {
-          gsr_eval_quad<false>(a + sw, a + (sw ^ 16u), nx2, ny2, true, true, true, true, r0, g0, b0, r1, g1, b1);
+      const int uy = uA / p.nrx, ux = uA - uy * p.nrx;
+      const int wi0 = ux * GSR_RGW + bx, hi0 = uy * GSR_RGH + by;
+      for (int t = 0; t < trip; t += 4) {
+        const uint2 s4 = gsr_lds64u(lb + 2 * t);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t w2 = k < 2 ? s4.x : s4.y;
+          const uint32_t a = (k & 1) ? (w2 >> 16) : (w2 & 0xffffu);
+          const uint32_t slot = (a - rb) >> 4;
+          const bool binds = slot < 32 ? ((slow_ac >> slot) & 1u) : (slot < 64 ? ((slow_bc >> (slot - 32)) & 1u) : false);
+          bool m00 = true, m01 = true, m10 = true, m11 = true;
+          if (binds) {  // exact inclusion
+            int bx0, bx1, by0, by1;
+            bool bd;
+            gsr_box_unpack(box_w[cur * CH + slot], bx0, bx1, by0, by1, bd);
+            const bool y0in = hi0 >= by0 && hi0 <= by1, y1in = hi0 + 1 >= by0 && hi0 + 1 <= by1;
+            const bool x0in = wi0 >= bx0 && wi0 <= bx1, x1in = wi0 + 1 >= bx0 && wi0 + 1 <= bx1;
+            m00 = y0in && x0in, m01 = y0in && x1in, m10 = y1in && x0in, m11 = y1in && x1in;
+          }
+          gsr_eval_quad<true>(a, a + GSR_FR_HI, nx2, ny2, m00, m01, m10, m11, r0, g0, b0, r1, g1, b1);
         }
       }
     }
     cur ^= 1;
-    c0 += CH;
-    slow_a = slow_an;
-    slow_b = slow_bn;
+    ++ci;
+    trip = trip_n;
+    slow_ac = slow_an;
+    slow_bc = slow_bn;
     if (!last) continue;
 
     // ---- unit finished: write out.  Plain stores when the image is overwritten; fire-and-forget
     // reductions (RED) when the call accumulates into the caller's image (the reference's
     // contract): no read, no latency.
     {
+      const int uy = uA / p.nrx, ux = uA - uy * p.nrx;
+      const int wi0 = ux * GSR_RGW + bx, hi0 = uy * GSR_RGH + by;
       float v[2][2][3];
       gsr_upk(r0, v[0][0][0], v[0][1][0]);
       gsr_upk(g0, v[0][0][1], v[0][1][1]);
@@ -685,25 +770,25 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
         }
       }
     }
-    // ---- advance: B becomes A, C becomes B, a new C is requested (consumed one unit from now)
-    u += nw;
-    if (u >= nunits) break;
-    ridA = ridB;
+    // ---- advance: B becomes A, C becomes B, the pending counter value becomes C, a new one is requested
+    uA = uB;
+    if (uA >= nunits) break;
     nA = nB;
-    ntripA = ntripB;
-    ridB = ridC;
+    nchA = nchB;
+    uB = uC;
     nB = min(nC, p.reg_cap);  // requested one unit ago
-    ntripB = max(nB, __shfl_xor_sync(0xffffffffu, nB, 16));
-    ridC = region_of(u + 2 * nw);
-    nC = count_of(ridC);
-    c0 = 0;
-    ry = ridA / p.nrx;
-    rx = ridA - ry * p.nrx;
-    wi0 = rx * GSR_REGION + (l16 & 3) * 2;
-    hi0 = ry * GSR_REGION + (l16 >> 2) * 2;
-    nx2 = gsr_pk(-__ldg(p.px_tab + min(wi0, p.w - 1)), -__ldg(p.px_tab + min(wi0 + 1, p.w - 1)));
-    ny2 = gsr_pk(-__ldg(p.py_tab + min(hi0, p.h - 1)), -__ldg(p.py_tab + min(hi0 + 1, p.h - 1)));
+    nchB = chunks_of(nB);
+    uC = __shfl_sync(full, pend, 0);  // requested one unit ago
+    nC = count_of(uC);
+    // lane 0 only, predicated inside the asm (no divergent region): the result is not waited for before the
+    // next advance reads it
+    asm volatile("{\n\t.reg .pred pl0;\n\tsetp.eq.s32 pl0, %2, 0;\n\t@pl0 atom.global.add.u32 %0, [%1], 1;\n\t}"
+                 : "+r"(pend) : "l"(p.sched), "r"(lane) : "memory");
+    ci = 0;
+    nx2 = nx2B;
+    ny2 = ny2B;
+    coords_of(uB, nx2B, ny2B);
     r0 = g0 = b0 = r1 = g1 = b1 = gsr_pk(0.f, 0.f);
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");  // nothing may be in flight when the CTA's memory is released
+  finish();
 }

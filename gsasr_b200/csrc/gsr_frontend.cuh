@@ -9,14 +9,9 @@
 #pragma once
 #include "gsr_prepass.cuh"
 
-__device__ __forceinline__ float gsr_sigmoid(float x) {
-  return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
-}
-
-// raw (s,9) = (sx, sy, rho, alpha, r, g, b, mu_x, mu_y)
-//   sigmas (s,3) = (sy/step*2/(w-1), sx/step*2/(h-1), rho)      NOTE the x/y swap (:121)
-//   coords (s,2) = ((mu*2-1) + 1 - 1/n) * n / (n-1) - 1          (:122-123)
-//   colors (s,3) = sigmoid(rgb) * sigmoid(alpha)                 (:177-180)
+// raw (s,9) -> sigmas (s,3), coords (s,2), colors (s,3): gsr_map_one (gsr_prepass.cuh) as a kernel of its own.
+// The forward applies the same function inside its set-up kernel; this stand-alone form serves calls with more
+// Gaussians than the region buckets index.
 __global__ void __launch_bounds__(256)
 gsr_map_kernel(const float* __restrict__ raw, float* __restrict__ sigmas,
                float* __restrict__ coords, float* __restrict__ colors, int s, int h, int w,
@@ -29,26 +24,15 @@ gsr_map_kernel(const float* __restrict__ raw, float* __restrict__ sigmas,
     w = d.w;
     step = d.step;
   }
-  const float* p = raw + 9 * (size_t)i;
-  const float inv_step = __fdiv_rn(1.0f, step);
-  const float inv_w1 = __fdiv_rn(1.0f, (float)(w - 1)), inv_h1 = __fdiv_rn(1.0f, (float)(h - 1));
-  const float inv_w = __fdiv_rn(1.0f, (float)w), inv_h = __fdiv_rn(1.0f, (float)h);
-  const float sgx = __fadd_rn(__fmul_rn(0.99999f, gsr_sigmoid(__ldg(p + 0))), 1e-6f);
-  const float sgy = __fadd_rn(__fmul_rn(0.99999f, gsr_sigmoid(__ldg(p + 1))), 1e-6f);
-  const float rho = __fmul_rn(0.999999f, tanhf(__ldg(p + 2)));
-  const float alpha = gsr_sigmoid(__ldg(p + 3));
-  sigmas[3 * (size_t)i + 0] = __fmul_rn(__fmul_rn(__fmul_rn(sgy, inv_step), 2.0f), inv_w1);
-  sigmas[3 * (size_t)i + 1] = __fmul_rn(__fmul_rn(__fmul_rn(sgx, inv_step), 2.0f), inv_h1);
-  sigmas[3 * (size_t)i + 2] = rho;
-  const float mx = __fsub_rn(__fmul_rn(__ldg(p + 7), 2.0f), 1.0f);
-  const float my = __fsub_rn(__fmul_rn(__ldg(p + 8), 2.0f), 1.0f);
-  coords[2 * (size_t)i + 0] = __fsub_rn(
-      __fmul_rn(__fmul_rn(__fsub_rn(__fadd_rn(mx, 1.0f), inv_w), (float)w), inv_w1), 1.0f);
-  coords[2 * (size_t)i + 1] = __fsub_rn(
-      __fmul_rn(__fmul_rn(__fsub_rn(__fadd_rn(my, 1.0f), inv_h), (float)h), inv_h1), 1.0f);
-#pragma unroll
-  for (int c = 0; c < 3; ++c)
-    colors[3 * (size_t)i + c] = __fmul_rn(gsr_sigmoid(__ldg(p + 4 + c)), alpha);
+  const GsrMapped m = gsr_map_one(raw + 9 * (size_t)i, h, w, step);
+  sigmas[3 * (size_t)i + 0] = m.sx;
+  sigmas[3 * (size_t)i + 1] = m.sy;
+  sigmas[3 * (size_t)i + 2] = m.rho;
+  coords[2 * (size_t)i + 0] = m.x;
+  coords[2 * (size_t)i + 1] = m.y;
+  colors[3 * (size_t)i + 0] = m.cr;
+  colors[3 * (size_t)i + 1] = m.cg;
+  colors[3 * (size_t)i + 2] = m.cb;
 }
 
 // Chain rule of gsr_map_kernel: (d/dsigmas, d/dcoords, d/dcolors) -> d/draw (s,9), written.

@@ -2,15 +2,18 @@
 //
 // Region-bucket pipeline (forward fast path), ONE pass over the Gaussians:
 //   T1 gsr_region_build_kernel  per Gaussian: exact dmax window /\ k-sigma box -> cull box, raster
-//                               record (written in input order); then for every 8x8-pixel region
-//                               the ellipse touches a 4-byte entry {index | binds << 31} is appended
-//                               to the region's bucket (small persistent CTAs collect their entries
-//                               per region in shared memory and reserve bucket slots with one global
-//                               atomic per (CTA, region); a warp-ballot path serves incoherent input).
-//   Every region owns a fixed-capacity bucket (40 N / regions + 32 entries: GSASR emits its Gaussians
-//   on a regular grid, utils/fea2gs.py:553-563, so the load per region is uniform); an entry that
-//   does not fit raises the overflow flag and the forward falls back to the home-bin pipeline.
-//   The forward kernel then needs no culling at all: half a warp per region streams its bucket.
+//                               record (written in input order); then for every 16x8-pixel region
+//                               the ellipse touches a 4-byte entry {index | cell mask << 23 | binds << 31}
+//                               is appended to the region's bucket -- the mask says which of the region's
+//                               eight 4x4-pixel cells the ellipse reaches (small persistent CTAs collect
+//                               their entries per region in shared memory and reserve bucket slots with
+//                               one global atomic per (CTA, region); a warp-ballot path serves incoherent
+//                               input).  Optionally fed with the RAW head output: the activations and the
+//                               unit mapping of the front end are then applied here (gsr_map_one).
+//   Every region owns a fixed-capacity bucket (GSR_ENTRIES_PER_GAUSSIAN N / regions + 32 entries: GSASR
+//   emits its Gaussians on a regular grid, utils/fea2gs.py:553-563, so the load per region is uniform); an
+//   entry that does not fit raises the overflow flag and the forward falls back to the home-bin pipeline.
+//   The forward kernel then needs no culling at all: a warp per region streams its bucket.
 //
 // Home-bin pipeline (backward; forward fallback when the tile lists overflow their capacity):
 //   K1 gsr_bin_kernel     per Gaussian: cull box, home bin, rank inside the bin (atomic), reach.
@@ -38,9 +41,10 @@ struct GsrBDesc {
 constexpr int GSR_BDESC_MAX = 1024;  // samples per stacked launch
 
 constexpr int GSR_STAT_EXT_X = 0, GSR_STAT_EXT_Y = 1, GSR_STAT_OVERFLOW = 2, GSR_STAT_ENTRIES = 3;
-// bucket capacity per region = 40 * N / regions + 32: a Gaussian of the x4 head touches 6.8 regions on
-// average, one of the x8 head 23 (5 sigma = 33 px); 4 bytes per slot
-constexpr int GSR_ENTRIES_PER_GAUSSIAN = 40;
+// bucket capacity per region = 28 * N / regions + 32: a Gaussian of the x4 head touches 4.4 of the 16x8
+// regions on average, one of the x8 head 12.3 (5 sigma = 16.7 px on average, 33 px at most); 4 bytes per slot
+constexpr int GSR_ENTRIES_PER_GAUSSIAN = 28;
+constexpr int GSR_STAT_UNIT = 4, GSR_STAT_DONE = 5;  // work counter / finished-warp counter of the raster kernel
 
 struct GsrWorkspace {
   // ---- one block, cleared per call ----
@@ -52,8 +56,8 @@ struct GsrWorkspace {
   // ---- tile-list pipeline ----
   GsrRec* rec_in;    // s        records, input order
   uint2* box_in;     // s        packed cull boxes, input order (only read for window-binding ones)
-  uint32_t* entries; // nreg * reg_cap   Gaussian index | binds << 31
-  int ntx, nty, nrx, nry, nreg, reg_cap;
+  uint32_t* entries; // nreg * reg_cap   Gaussian index | cell mask << 23 | binds << 31
+  int nrx, nry, nreg, reg_cap;  // GSR_RGW x GSR_RGH pixel regions
   // ---- home-bin pipeline ----
   int* bin_off;      // nb + 2   exclusive offsets; [nb] = start of large, [nb+1] = n_live
   uint2* box_tmp;    // s   (unsorted)
@@ -83,10 +87,8 @@ static inline GsrWorkspace gsr_carve(void* base, int s, int h, int w) {
   ws.nbx = (w + GSR_BIN - 1) / GSR_BIN;
   ws.nby = (h + GSR_BIN - 1) / GSR_BIN;
   ws.nb = ws.nbx * ws.nby;
-  ws.ntx = (w + GSR_TILE_W - 1) / GSR_TILE_W;
-  ws.nty = (h + GSR_TILE_H - 1) / GSR_TILE_H;
-  ws.nrx = ws.ntx * GSR_NRX;  // region grid padded to whole tiles
-  ws.nry = ws.nty * GSR_NRY;
+  ws.nrx = (w + GSR_RGW - 1) / GSR_RGW;
+  ws.nry = (h + GSR_RGH - 1) / GSR_RGH;
   ws.nreg = ws.nrx * ws.nry;
   size_t off = 0;
   char* p = (char*)base;
@@ -170,8 +172,8 @@ __device__ __forceinline__ GsrSampleView gsr_sample_view(const GsrWorkspace& ws,
 // box test.
 template <bool RAGGED>
 __device__ __forceinline__ bool gsr_edge_binds(const GsrSampleView& v, const GsrSetup& st) {
-  return RAGGED && (((v.wl % GSR_REGION) != 0 && st.x1 / GSR_REGION == (v.wl - 1) / GSR_REGION) ||
-                       ((v.hl % GSR_REGION) != 0 && (st.y1 - v.yoff) / GSR_REGION == (v.hl - 1) / GSR_REGION));
+  return RAGGED && (((v.wl % GSR_RGW) != 0 && st.x1 / GSR_RGW == (v.wl - 1) / GSR_RGW) ||
+                       ((v.hl % GSR_RGH) != 0 && (st.y1 - v.yoff) / GSR_RGH == (v.hl - 1) / GSR_RGH));
 }
 // Record in CANVAS coordinates: d_own = a_ * d_canvas, so x_c = (x + 1) / ax - 1 and the conic scales.
 __device__ __forceinline__ void gsr_rescale_rec(GsrRec& r, const GsrSampleView& v) {
@@ -366,269 +368,227 @@ gsr_scatter_kernel(const float* __restrict__ sigmas, const float* __restrict__ c
     gsr_scatter_one(sigmas, coords, colors, i, ws);
 }
 
-// ---- tile-list pipeline -------------------------------------------------------------------------
-// Warp-cooperative bucket append.  The 32 Gaussians of a warp are consecutive in the input, which
-// for a fea2gs field means spatially adjacent (utils/fea2gs.py:553-563), so their region sets
-// overlap heavily.  Regions are addressed as (band, column): band = 8-row strip of the image.
-//   1. per band of the warp's union every lane computes the column range its ellipse covers
-//      (gsr_band_xrange); per (band, column) of the union one ballot tells which lanes touch the
-//      region, and non-empty pairs are dealt to the lanes, 32 at a time;
-//   2. lane = pair: ONE atomicAdd reserves the pair's slots (32 reservations in flight per
-//      instruction, so the atomic round trip is paid once per batch, not once per pair), then the
-//      lane streams the entries of its pair -- fetched from the owning lanes with shuffles -- into
-//      the region's bucket.
-// If the union is large (incoherent input order) every lane walks its own regions with one atomic
-// per entry.  All 32 lanes must call this function (dead lanes pass live = false).
-constexpr int GSR_COOP_MAX_PAIRS = 256;
-
-__device__ __forceinline__ void gsr_warp_flush_pairs(unsigned bal, int rid, uint32_t entry,
-                                                     int* __restrict__ cnt, uint32_t* __restrict__ ent,
-                                                     int cap, int* overflow) {
-  const unsigned full = 0xffffffffu;
-  uint32_t* dst = ent;
-  int room = 0;
-  if (bal) {
-    const int base = atomicAdd(cnt + rid, __popc(bal));
-    dst = ent + (size_t)rid * cap + base;
-    room = cap - base;  // entries that still fit
-    if (room < __popc(bal)) *overflow = 1;
-  }
-  const int iters = __reduce_max_sync(full, __popc(bal));
-  for (int k = 0; k < iters; ++k) {
-    const int src = bal ? __ffs(bal) - 1 : 0;
-    const uint32_t en = __shfl_sync(full, entry, src);
-    if (bal && k < room) dst[k] = en;
-    bal &= bal - 1;
-  }
+// ---- region-bucket pipeline ---------------------------------------------------------------------
+// Front end, folded in (utils/gaussian_splatting.py:174-180 activations, :121-123 unit / coordinate mapping of
+// rendering_cuda_dmax): raw (s,9) = (sx, sy, rho, alpha, r, g, b, mu_x, mu_y) ->
+//   sigmas = (sy/step*2/(w-1), sx/step*2/(h-1), rho)     NOTE the x/y swap (:121)
+//   coords = ((mu*2-1) + 1 - 1/n) * n / (n-1) - 1         (:122-123)
+//   colors = sigmoid(rgb) * sigmoid(alpha)                (:177-180)
+// The arithmetic follows what PyTorch executes on the INFERENCE path (inference_paper.py:113-131: sr_size and
+// scale_modify are CPU tensors, so CUDA tensor / CPU-scalar divisions run as a multiplication by the fp32
+// reciprocal); every operation is individually rounded (no FMA contraction) so the mapped parameters agree
+// with the unfused path to the last bit or one ulp.
+__device__ __forceinline__ float gsr_sigmoid(float x) {
+  return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+}
+struct GsrMapped {
+  float sx, sy, rho, x, y, cr, cg, cb;
+};
+__device__ __forceinline__ GsrMapped gsr_map_one(const float* __restrict__ p, int h, int w, float step) {
+  const float inv_step = __fdiv_rn(1.0f, step);
+  const float inv_w1 = __fdiv_rn(1.0f, (float)(w - 1)), inv_h1 = __fdiv_rn(1.0f, (float)(h - 1));
+  const float inv_w = __fdiv_rn(1.0f, (float)w), inv_h = __fdiv_rn(1.0f, (float)h);
+  const float sgx = __fadd_rn(__fmul_rn(0.99999f, gsr_sigmoid(__ldg(p + 0))), 1e-6f);
+  const float sgy = __fadd_rn(__fmul_rn(0.99999f, gsr_sigmoid(__ldg(p + 1))), 1e-6f);
+  const float alpha = gsr_sigmoid(__ldg(p + 3));
+  GsrMapped m;
+  m.sx = __fmul_rn(__fmul_rn(__fmul_rn(sgy, inv_step), 2.0f), inv_w1);
+  m.sy = __fmul_rn(__fmul_rn(__fmul_rn(sgx, inv_step), 2.0f), inv_h1);
+  m.rho = __fmul_rn(0.999999f, tanhf(__ldg(p + 2)));
+  const float mx = __fsub_rn(__fmul_rn(__ldg(p + 7), 2.0f), 1.0f);
+  const float my = __fsub_rn(__fmul_rn(__ldg(p + 8), 2.0f), 1.0f);
+  m.x = __fsub_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fadd_rn(mx, 1.0f), inv_w), (float)w), inv_w1), 1.0f);
+  m.y = __fsub_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fadd_rn(my, 1.0f), inv_h), (float)h), inv_h1), 1.0f);
+  m.cr = __fmul_rn(gsr_sigmoid(__ldg(p + 4)), alpha);
+  m.cg = __fmul_rn(gsr_sigmoid(__ldg(p + 5)), alpha);
+  m.cb = __fmul_rn(gsr_sigmoid(__ldg(p + 6)), alpha);
+  return m;
 }
 
-__device__ __forceinline__ void gsr_warp_append(bool live, const GsrRec& r, uint32_t entry, int x0,
-                                                int x1, int y0, int y1, int h, int w, int nrx,
-                                                float ecut, int* __restrict__ cnt,
-                                                uint32_t* __restrict__ ent, int cap, int* overflow,
-                                                int hf = 0, int row0 = 0, int yoff = 0) {
-  const unsigned full = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int b0 = live ? y0 / GSR_REGION : 0x3fffffff, b1 = live ? y1 / GSR_REGION : -1;
-  const int c0 = live ? x0 / GSR_REGION : 0x3fffffff, c1 = live ? x1 / GSR_REGION : -1;
-  const int ub0 = __reduce_min_sync(full, b0), ub1 = __reduce_max_sync(full, b1);
-  const int uc0 = __reduce_min_sync(full, c0), uc1 = __reduce_max_sync(full, c1);
-  if (ub1 < ub0 || uc1 < uc0) return;  // no live lane
-  GsrEllipse e;
-  if (live) {
-    e = gsr_ellipse(r, h, w, hf, row0);
-    e.cy += (float)yoff;  // uniform batch: the sample's block of rows
-  }
-  if ((long long)(ub1 - ub0 + 1) * (uc1 - uc0 + 1) > GSR_COOP_MAX_PAIRS) {
-    if (live)
-      for (int b = b0; b <= b1; ++b) {
-        int ya = b * GSR_REGION, yb = ya + GSR_REGION - 1, xl, xh;
-        ya = ya > y0 ? ya : y0;
-        yb = yb < y1 ? yb : y1;
-        if (!gsr_band_xrange(e, ecut, ya, yb, x0, x1, xl, xh)) continue;
-        for (int c = xl / GSR_REGION; c <= xh / GSR_REGION; ++c) {
-          const int rid = b * nrx + c;
-          const int pos = atomicAdd(cnt + rid, 1);
-          if (pos < cap) ent[(size_t)rid * cap + pos] = entry;
-          else *overflow = 1;
-        }
-      }
-    return;
-  }
-  int slot = 0;  // pairs dealt in the current batch (warp-uniform)
-  unsigned mybal = 0;
-  int myrid = 0;
-  for (int b = ub0; b <= ub1; ++b) {
-    int rc0 = 1, rc1 = 0;  // this lane's column range in band b (empty by default)
-    if (live && b >= b0 && b <= b1) {
-      int ya = b * GSR_REGION, yb = ya + GSR_REGION - 1, xl, xh;
-      ya = ya > y0 ? ya : y0;
-      yb = yb < y1 ? yb : y1;
-      if (gsr_band_xrange(e, ecut, ya, yb, x0, x1, xl, xh)) {
-        rc0 = xl / GSR_REGION;
-        rc1 = xh / GSR_REGION;
-      }
-    }
-    // columns that any lane touches in this band
-    const int bc0 = __reduce_min_sync(full, rc0 <= rc1 ? rc0 : 0x3fffffff);
-    const int bc1 = __reduce_max_sync(full, rc0 <= rc1 ? rc1 : -1);
-    for (int c = bc0; c <= bc1; ++c) {
-      const unsigned bal = __ballot_sync(full, rc0 <= c && c <= rc1);
-      if (bal) {
-        if (lane == slot) {
-          mybal = bal;
-          myrid = b * nrx + c;
-        }
-        if (++slot == 32) {
-          gsr_warp_flush_pairs(mybal, myrid, entry, cnt, ent, cap, overflow);
-          slot = 0;
-          mybal = 0;
-        }
-      }
-    }
-  }
-  if (slot) gsr_warp_flush_pairs(mybal, myrid, entry, cnt, ent, cap, overflow);
-}
-
-// CTA-cooperative bucket append (the common case).  The Gaussians of a CTA are consecutive in the input
-// -- for a fea2gs field a piece of one grid row -- so the regions they touch form a small rectangle
-// (18 x 4 regions for 64 Gaussians at x4).  When it has at most GSR_RB_MAXR regions the CTA collects its
-// entries per region in shared memory (one shared-memory atomic per entry for the slot), reserves each
-// non-empty region's slots in the global bucket with ONE atomicAdd (a thread per region) and copies the
-// short lists out.  A list longer than GSR_RB_LCAP spills its tail straight to the bucket (one global
-// atomic per entry); a CTA whose rectangle is larger (incoherent input order) takes the ballot-based
-// path above.  CTAs are small (two warps: the barriers cost little and many CTAs are in different
-// phases at any time) and persistent: each strides over the chunks of the input and requests the
-// parameters of its next chunk before it processes the current one.
+// Bucket append.  One thread per Gaussian walks the region bands of its box and collects its entries
+// {index | cell mask << 23 | binds << 31} with their region ids in a PRIVATE shared-memory list (no atomics, no
+// barrier: a thread only ever touches its own column).  The lists are then appended to the regions' buckets four
+// positions at a time: the 32 Gaussians of a warp are consecutive in the input, which for a fea2gs field means
+// spatially adjacent (utils/fea2gs.py:553-563), so at the same list position neighbouring lanes name the same
+// region; runs of lanes that do form a group, the group's first lane reserves the group's slots with ONE global
+// atomicAdd and every lane stores its entry at its rank.  The four atomics of a batch are issued back to back
+// before the first result is used, so a warp exposes one atomic round trip per four list positions instead of
+// one per position.  All loops are warp-uniform (trip counts are warp maxima, lanes past their own range are
+// predicated off): no divergent nesting, and no special path for wide (x8) or incoherent input, which merely
+// forms smaller groups.
 #ifndef GSR_CFG_RB_THREADS
 #define GSR_CFG_RB_THREADS 64
 #endif
 constexpr int GSR_RB_THREADS = GSR_CFG_RB_THREADS;
-constexpr int GSR_RB_MAXR = 2 * GSR_RB_THREADS;
-constexpr int GSR_RB_LCAP = 16;
-
-struct GsrRegionBuildSmem {
-  int cnt[GSR_RB_MAXR];
-  uint32_t list[GSR_RB_MAXR][GSR_RB_LCAP + 1];  // odd row stride: a thread per region reads conflict-free
-  int red[4][(GSR_RB_THREADS + 31) / 32];
-};
-
 #ifndef GSR_CFG_RB_MIN_CTAS
 #define GSR_CFG_RB_MIN_CTAS (1024 / GSR_CFG_RB_THREADS)
 #endif
-template <bool RAGGED>
+constexpr int GSR_RB_ECAP = 16;  // list positions per Gaussian between two flushes
+
+struct GsrRegionBuildSmem {
+  uint2 list[GSR_RB_ECAP][GSR_RB_THREADS];  // {entry, region id}
+};
+
+// Appends list positions [0, n) of every lane (n <= GSR_RB_ECAP, lane-dependent).  Warp-collective.
+__device__ __forceinline__ void gsr_bucket_flush(const GsrRegionBuildSmem& sm, int tid, int lane, int n,
+                                                 int* __restrict__ cnt, uint32_t* __restrict__ ent, int cap,
+                                                 int* overflow) {
+  const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+  const int nmax = __reduce_max_sync(full, n);
+  for (int e0 = 0; e0 < nmax; e0 += 4) {
+    unsigned grp[4];
+    int base[4];
+    uint2 it[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const bool v = e0 + t < n;
+      it[t] = sm.list[(e0 + t) & (GSR_RB_ECAP - 1)][tid];
+      // runs of consecutive lanes naming the same region form a group (lanes without an entry at this
+      // position get an id no region has): heads from one shuffle + ballot, no match instruction
+      const int key = v ? (int)it[t].y : -1 - lane;
+      const int prev = __shfl_up_sync(full, key, 1);
+      const unsigned heads = __ballot_sync(full, lane == 0 || prev != key);
+      const unsigned upto = lt | (1u << lane);
+      const int lead = 31 - __clz(heads & upto);          // my run's first lane
+      const unsigned above = heads & ~upto;
+      const int end = above ? __ffs(above) - 1 : 32;      // one past my run's last lane
+      grp[t] = v ? (unsigned)((lead << 8) | (lane - lead)) | 0x10000u : 0u;  // {valid, leader, rank}
+      base[t] = 0;
+      // the run's first lane reserves the run's slots (predicated atomic: no divergent region, and the result
+      // is not waited for before the second loop)
+      asm volatile("{\n\t.reg .pred pa;\n\tsetp.ne.s32 pa, %3, 0;\n\t@pa atom.global.add.s32 %0, [%1], %2;\n\t}"
+                   : "+r"(base[t]) : "l"(cnt + (v ? (int)it[t].y : 0)), "r"(end - lead), "r"((int)(v && lane == lead))
+                   : "memory");
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const unsigned g = grp[t];
+      const int b = __shfl_sync(full, base[t], (g >> 8) & 31);
+      if (g) {
+        const int pos = b + (int)(g & 0xffu);
+        if (pos < cap) ent[(size_t)it[t].y * cap + pos] = it[t].x;
+        else *overflow = 1;
+      }
+    }
+  }
+}
+
+// RAW: `sigmas` points to the raw head output (s,9); the mapped parameters are written to msig (s,3), mcrd (s,2),
+// mcol (s,3) -- what the backward and the autograd boundary need -- and used from registers: no second pass
+// over them.  step: the front end's step size (padded batches: per sample).
+template <bool RAGGED, bool RAW>
 __global__ void __launch_bounds__(GSR_RB_THREADS, GSR_CFG_RB_MIN_CTAS)
 gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restrict__ coords,
-                      const float* __restrict__ colors, int s, int h, int w, float dmax,
-                      float ksigma, float ecut, GsrWorkspace ws) {
+                        const float* __restrict__ colors, float* __restrict__ msig, float* __restrict__ mcrd,
+                        float* __restrict__ mcol, int s, int h, int w, float dmax, float ksigma, float ecut,
+                        float step, GsrWorkspace ws) {
   __shared__ GsrRegionBuildSmem sm;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const unsigned full = 0xffffffffu;
   int* const overflow = ws.stats + GSR_STAT_OVERFLOW;
   const int nchunks = (s + GSR_RB_THREADS - 1) / GSR_RB_THREADS;
 
-  float pf[8];
-  auto request = [&](int chunk) {
-    const int i = chunk * GSR_RB_THREADS + tid;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) pf[k] = 0.f;
-    if (chunk < nchunks && i < s) {
-      pf[0] = __ldg(sigmas + 3 * (size_t)i + 0);
-      pf[1] = __ldg(sigmas + 3 * (size_t)i + 1);
-      pf[2] = __ldg(sigmas + 3 * (size_t)i + 2);
-      pf[3] = __ldg(coords + 2 * (size_t)i + 0);
-      pf[4] = __ldg(coords + 2 * (size_t)i + 1);
-      pf[5] = __ldg(colors + 3 * (size_t)i + 0);
-      pf[6] = __ldg(colors + 3 * (size_t)i + 1);
-      pf[7] = __ldg(colors + 3 * (size_t)i + 2);
-    }
-  };
-  request(blockIdx.x);
-
   for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     const int i = chunk * GSR_RB_THREADS + tid;
-    const float sx = pf[0], sy = pf[1], rho = pf[2], x = pf[3], y = pf[4], cr = pf[5], cg = pf[6], cb = pf[7];
-    request(chunk + gridDim.x);
     // batches: set up in the sample's own image (hl x wl, its dmax), then move to its block of rows of the
     // stack; a padded batch stores the record rescaled to the canvas' coordinate normalisation, the raw
-    // one (r) keeps describing the ellipse in the sample's own pixels for the region masks
-    const GsrSampleView sv = gsr_sample_view<RAGGED>(ws, i, h, w, dmax);
+    // one (r) keeps describing the ellipse in the sample's own pixels for the cell masks
+    const GsrSampleView sv = gsr_sample_view<RAGGED>(ws, i < s ? i : 0, h, w, dmax);
     const int yoff = sv.yoff, hl = sv.hl, wl = sv.wl;
     GsrSetup st;
     st.live = false;
     st.binds = false;
     st.x0 = st.y0 = 1;
     st.x1 = st.y1 = 0;
-    GsrRec r;
-    r.x = r.y = r.a = r.b = r.c = r.r = r.g = r.bl = 0.f;
+    GsrEllipse e;
+    e.cx = e.cy = e.inv_a = e.kappa = e.cp = 0.f;
     if (i < s) {
+      float sx, sy, rho, x, y, cr, cg, cb;
+      if (RAW) {
+        float stp = step;
+        if (RAGGED) stp = ws.bdesc[i / ws.bn].step;
+        const GsrMapped m = gsr_map_one(sigmas + 9 * (size_t)i, ws.hf > 0 ? ws.hf : hl, wl, stp);
+        sx = m.sx, sy = m.sy, rho = m.rho, x = m.x, y = m.y, cr = m.cr, cg = m.cg, cb = m.cb;
+        float* ms = msig + 3 * (size_t)i;
+        float* mc = mcrd + 2 * (size_t)i;
+        float* mk = mcol + 3 * (size_t)i;
+        ms[0] = sx, ms[1] = sy, ms[2] = rho;
+        mc[0] = x, mc[1] = y;
+        mk[0] = cr, mk[1] = cg, mk[2] = cb;
+      } else {
+        sx = __ldg(sigmas + 3 * (size_t)i + 0);
+        sy = __ldg(sigmas + 3 * (size_t)i + 1);
+        rho = __ldg(sigmas + 3 * (size_t)i + 2);
+        x = __ldg(coords + 2 * (size_t)i + 0);
+        y = __ldg(coords + 2 * (size_t)i + 1);
+        cr = __ldg(colors + 3 * (size_t)i + 0);
+        cg = __ldg(colors + 3 * (size_t)i + 1);
+        cb = __ldg(colors + 3 * (size_t)i + 2);
+      }
       st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, hl, wl, sv.dmax, ksigma, sv.px_tab, sv.py_tab, ws.hf, ws.row0);
       if (st.live) {
-        r = gsr_make_rec(sx, sy, rho, x, y, cr, cg, cb);
+        const GsrRec r = gsr_make_rec(sx, sy, rho, x, y, cr, cg, cb);
         if (!(gsr_finite(r.a) && gsr_finite(r.b) && gsr_finite(r.c))) st.live = false;
         st.y0 += yoff;
         st.y1 += yoff;
         if (gsr_edge_binds<RAGGED>(sv, st)) st.binds = true;
-      }
-      if (st.live) {
-        GsrRec rs = r;
-        if (RAGGED) gsr_rescale_rec(rs, sv);
-        float4* dr = reinterpret_cast<float4*>(ws.rec_in + i);
-        dr[0] = make_float4(rs.x, rs.y, rs.a, rs.b);
-        dr[1] = make_float4(rs.c, rs.r, rs.g, rs.bl);
-        if (st.binds) ws.box_in[i] = gsr_box_pack(st.x0, st.x1, st.y0, st.y1, true);
+        if (st.live) {
+          GsrRec rs = r;
+          if (RAGGED) gsr_rescale_rec(rs, sv);
+          float4* dr = reinterpret_cast<float4*>(ws.rec_in + i);
+          dr[0] = make_float4(rs.x, rs.y, rs.a, rs.b);
+          dr[1] = make_float4(rs.c, rs.r, rs.g, rs.bl);
+          if (st.binds) ws.box_in[i] = gsr_box_pack(st.x0, st.x1, st.y0, st.y1, true);
+          e = gsr_ellipse(r, hl, wl, ws.hf, ws.row0);
+          e.cy += (float)yoff;
+        }
       }
     }
     const uint32_t entry = (uint32_t)i | (st.binds ? 0x80000000u : 0u);
 
-    // ---- the CTA's region rectangle
-    const int b0 = st.live ? st.y0 / GSR_REGION : 0x3fffffff, b1 = st.live ? st.y1 / GSR_REGION : -1;
-    const int c0 = st.live ? st.x0 / GSR_REGION : 0x3fffffff, c1 = st.live ? st.x1 / GSR_REGION : -1;
-    {
-      const int wb0 = __reduce_min_sync(full, b0), wb1 = __reduce_max_sync(full, b1);
-      const int wc0 = __reduce_min_sync(full, c0), wc1 = __reduce_max_sync(full, c1);
-      if (lane == 0) {
-        sm.red[0][warp] = wb0;
-        sm.red[1][warp] = wb1;
-        sm.red[2][warp] = wc0;
-        sm.red[3][warp] = wc1;
+    // ---- walk the region bands of the box (warp-uniform trip counts)
+    // (box corners of a live Gaussian are non-negative: unsigned divisions are shifts)
+    const int b0 = (int)((unsigned)st.y0 / GSR_RGH), nb = st.live ? (int)((unsigned)st.y1 / GSR_RGH) - b0 + 1 : 0;
+    const int cbase = (int)((unsigned)st.x0 / GSR_RGW) * GSR_CELLS_X;
+    // every box of the warp spans at most 32 cells: row bitmaps (else the general mask function, for all lanes)
+    const bool narrow = __all_sync(full, !st.live || (int)((unsigned)st.x1 / GSR_CELL) - cbase < 32);
+    const int KB = __reduce_max_sync(full, nb);
+    int n = 0;  // entries in this lane's list
+    for (int k = 0; k < KB; ++k) {
+      const int b = b0 + k;
+      uint32_t rb[2] = {0u, 0u};
+      int cl[2] = {1, 1}, ch[2] = {0, 0}, ca = 0, ncol = 0;
+      if (k < nb) {
+        if (narrow) {
+          if (gsr_band_rowbits(e, ecut, b, st.x0, st.x1, st.y0, st.y1, cbase, rb)) {
+            const uint32_t any = rb[0] | rb[1];
+            ca = (int)((unsigned)(cbase + __ffs(any) - 1) / GSR_CELLS_X);
+            ncol = (int)((unsigned)(cbase + 31 - __clz(any)) / GSR_CELLS_X) - ca + 1;
+          }
+        } else if (gsr_band_cells(e, ecut, b, st.x0, st.x1, st.y0, st.y1, cl, ch)) {
+          int cb_;
+          gsr_band_columns(cl, ch, ca, cb_);
+          ncol = cb_ - ca + 1;
+        }
       }
-    }
-    for (int k = tid; k < GSR_RB_MAXR; k += GSR_RB_THREADS) sm.cnt[k] = 0;
-    __syncthreads();
-    int B0 = 0x3fffffff, B1 = -1, C0 = 0x3fffffff, C1 = -1;
+      const int KC = __reduce_max_sync(full, ncol);
+      for (int j0 = 0; j0 < KC; j0 += 4) {
 #pragma unroll
-    for (int k = 0; k < (GSR_RB_THREADS + 31) / 32; ++k) {
-      B0 = min(B0, sm.red[0][k]);
-      B1 = max(B1, sm.red[1][k]);
-      C0 = min(C0, sm.red[2][k]);
-      C1 = max(C1, sm.red[3][k]);
-    }
-    const bool any_live = B1 >= B0 && C1 >= C0;  // CTA-uniform
-    const int NC = C1 - C0 + 1, NR = any_live ? NC * (B1 - B0 + 1) : 0;
-    if (any_live && (long long)NC * (B1 - B0 + 1) > GSR_RB_MAXR) {
-      gsr_warp_append(st.live, r, entry, st.x0, st.x1, st.y0, st.y1, hl, wl, ws.nrx, ecut, ws.reg_count, ws.entries,
-                      ws.reg_cap, overflow, ws.hf, ws.row0, yoff);
-    } else if (any_live) {
-      // ---- collect: one shared-memory atomic per (Gaussian, region)
-      if (st.live) {
-        GsrEllipse e = gsr_ellipse(r, hl, wl, ws.hf, ws.row0);
-        e.cy += (float)yoff;
-        for (int b = b0; b <= b1; ++b) {
-          int ya = b * GSR_REGION, yb = ya + GSR_REGION - 1, xl, xh;
-          ya = ya > st.y0 ? ya : st.y0;
-          yb = yb < st.y1 ? yb : st.y1;
-          if (!gsr_band_xrange(e, ecut, ya, yb, st.x0, st.x1, xl, xh)) continue;
-          const int row = (b - B0) * NC - C0;
-          for (int c = xl / GSR_REGION; c <= xh / GSR_REGION; ++c) {
-            const int slot = atomicAdd(&sm.cnt[row + c], 1);
-            if (slot < GSR_RB_LCAP) {
-              sm.list[row + c][slot] = entry;
-            } else {  // list full: straight to the bucket
-              const int rid = b * ws.nrx + c;
-              const int pos = atomicAdd(ws.reg_count + rid, 1);
-              if (pos < ws.reg_cap) ws.entries[(size_t)rid * ws.reg_cap + pos] = entry;
-              else *overflow = 1;
-            }
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = j0 + jj, c = ca + j;
+          uint32_t m = 0u;
+          if (j < ncol) m = narrow ? gsr_rowbits_mask(rb, c, cbase) : gsr_cell_mask(cl, ch, c);
+          if (m != 0u) {
+            sm.list[n][tid] = make_uint2(entry | (m << GSR_ENT_MASK_SHIFT), (uint32_t)(b * ws.nrx + c));
+            ++n;
           }
         }
-      }
-      __syncthreads();
-      // ---- reserve and copy out: a thread per region of the rectangle -- ONE global atomic for the
-      // region's slots, then its short list goes to the bucket
-      for (int k = tid; k < NR; k += GSR_RB_THREADS) {
-        const int n = min(sm.cnt[k], GSR_RB_LCAP);
-        if (n > 0) {
-          const int rb = k / NC;
-          const int rid = (B0 + rb) * ws.nrx + C0 + (k - rb * NC);
-          const int pos = atomicAdd(ws.reg_count + rid, n);
-          uint32_t* dst = ws.entries + (size_t)rid * ws.reg_cap + pos;
-          const int room = ws.reg_cap - pos;
-          if (room < n) *overflow = 1;
-          for (int j = 0; j < n && j < room; ++j) dst[j] = sm.list[k][j];
+        if (__any_sync(full, n > GSR_RB_ECAP - 4)) {  // the next four might not fit
+          gsr_bucket_flush(sm, tid, lane, n, ws.reg_count, ws.entries, ws.reg_cap, overflow);
+          n = 0;
         }
       }
     }
-    __syncthreads();  // shared memory is reused by the next chunk
+    gsr_bucket_flush(sm, tid, lane, n, ws.reg_count, ws.entries, ws.reg_cap, overflow);
   }
 }

@@ -4,6 +4,7 @@
 #include "../../include/gsraster.h"
 #include "gsr_backward.cuh"
 #include "gsr_frontend.cuh"
+#include <atomic>
 
 static thread_local int g_last_cuda_error = 0;
 
@@ -50,22 +51,51 @@ static int gsr_check_ws(void* workspace, size_t bytes, size_t need) {
 
 
 // Resident grid of a persistent kernel on the current device: SM count x CTAs per SM.  Queried once
-// per (device, kernel) and cached -- immutable facts of the device, written once with the same
-// value by whichever thread gets there first.
-template <typename K>
-static int gsr_resident_grid(K kernel, int threads, int slot, int* out) {
-  static int cache[2][64];  // [kernel slot][device], 0 = not yet queried
+// per (device, kernel) and cached -- immutable facts of the device; the cache is a table of relaxed atomics
+// (every thread that races to fill an entry writes the same value).
+static int gsr_sm_count(int* out) {
+  static std::atomic<int> cache[64];
   int dev = 0;
   GSR_CUDA(cudaGetDevice(&dev));
-  if (dev >= 0 && dev < 64 && cache[slot][dev] > 0) {
-    *out = cache[slot][dev];
-    return GSR_OK;
+  int v = (dev >= 0 && dev < 64) ? cache[dev].load(std::memory_order_relaxed) : 0;
+  if (v <= 0) {
+    GSR_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+    if (dev >= 0 && dev < 64) cache[dev].store(v, std::memory_order_relaxed);
+  }
+  *out = v;
+  return GSR_OK;
+}
+
+template <typename K>
+static int gsr_resident_grid(K kernel, int threads, int slot, int* out) {
+  static std::atomic<int> cache[2][64];  // [kernel slot][device], 0 = not yet queried
+  int dev = 0;
+  GSR_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64) {
+    const int v = cache[slot][dev].load(std::memory_order_relaxed);
+    if (v > 0) {
+      *out = v;
+      return GSR_OK;
+    }
   }
   int nsm = 0, per_sm = 0;
-  GSR_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  const int rc = gsr_sm_count(&nsm);
+  if (rc) return rc;
   GSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
   *out = nsm * (per_sm > 0 ? per_sm : 1);
-  if (dev >= 0 && dev < 64) cache[slot][dev] = *out;
+  if (dev >= 0 && dev < 64) cache[slot][dev].store(*out, std::memory_order_relaxed);
+  return GSR_OK;
+}
+
+// Kernels that need more than 48 KB of dynamic shared memory opt in once per (device, kernel).
+template <typename K>
+static int gsr_optin_smem(K kernel, int bytes, int slot) {
+  static std::atomic<int> done[2][64];
+  int dev = 0;
+  GSR_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && done[slot][dev].load(std::memory_order_relaxed)) return GSR_OK;
+  GSR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (dev >= 0 && dev < 64) done[slot][dev].store(1, std::memory_order_relaxed);
   return GSR_OK;
 }
 
@@ -96,21 +126,43 @@ static int gsr_run_bins(const float* sigmas, const float* coords, const float* c
 }
 
 // Region-bucket pipeline (one kernel).  Raises stats[GSR_STAT_OVERFLOW] when a bucket overflows.
+// raw != NULL: the kernel is fed with the raw head output (s,9) and applies the front end itself, leaving the
+// mapped parameters in `mapped` (= sigmas / coords / colors, which then need not be initialised).
 static int gsr_run_tiles(const float* sigmas, const float* coords, const float* colors, int s,
                          int h, int w, float dmax, float keff, const GsrWorkspace& ws,
-                         cudaStream_t st) {
+                         cudaStream_t st, const float* raw = nullptr, float step = 0.f) {
+  if (s > GSR_BUCKET_MAX_S) {
+    // the bucket entries hold 23-bit indices: larger calls take the home-bin path (flag = 1, little endian)
+    if (raw) {
+      gsr_map_kernel<<<(s + 255) / 256, 256, 0, st>>>(raw, (float*)sigmas, (float*)coords, (float*)colors, s, h, w, step,
+                                                      ws.ragged ? ws.bdesc : nullptr, ws.bn);
+      GSR_CUDA(cudaGetLastError());
+    }
+    GSR_CUDA(cudaMemsetAsync(ws.stats + GSR_STAT_OVERFLOW, 1, 1, st));
+    return GSR_OK;
+  }
   if (s > 0) {
     // persistent CTAs: one resident wave, every CTA strides over the chunks of the input
     int cap = 0;
-    const int rc = gsr_resident_grid(gsr_region_build_kernel<false>, GSR_RB_THREADS, 0, &cap);
+    const int rc = gsr_resident_grid(gsr_region_build_kernel<false, false>, GSR_RB_THREADS, 0, &cap);
     if (rc) return rc;
     const int want = (s + GSR_RB_THREADS - 1) / GSR_RB_THREADS, grid = want < cap ? want : cap;
-    if (ws.ragged)
-      gsr_region_build_kernel<true><<<grid, GSR_RB_THREADS, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff,
-                                                                     gsr_ecut(keff), ws);
-    else
-      gsr_region_build_kernel<false><<<grid, GSR_RB_THREADS, 0, st>>>(sigmas, coords, colors, s, h, w, dmax, keff,
-                                                                      gsr_ecut(keff), ws);
+    const float ec = gsr_ecut(keff);
+    float *ms = (float*)sigmas, *mc = (float*)coords, *mk = (float*)colors;  // RAW: outputs
+    if (raw) {
+      if (ws.ragged)
+        gsr_region_build_kernel<true, true><<<grid, GSR_RB_THREADS, 0, st>>>(raw, nullptr, nullptr, ms, mc, mk, s, h, w,
+                                                                             dmax, keff, ec, step, ws);
+      else
+        gsr_region_build_kernel<false, true><<<grid, GSR_RB_THREADS, 0, st>>>(raw, nullptr, nullptr, ms, mc, mk, s, h, w,
+                                                                              dmax, keff, ec, step, ws);
+    } else if (ws.ragged) {
+      gsr_region_build_kernel<true, false><<<grid, GSR_RB_THREADS, 0, st>>>(sigmas, coords, colors, nullptr, nullptr,
+                                                                            nullptr, s, h, w, dmax, keff, ec, 0.f, ws);
+    } else {
+      gsr_region_build_kernel<false, false><<<grid, GSR_RB_THREADS, 0, st>>>(sigmas, coords, colors, nullptr, nullptr,
+                                                                             nullptr, s, h, w, dmax, keff, ec, 0.f, ws);
+    }
   }
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
@@ -142,7 +194,7 @@ static GsrFwdArgs gsr_fwd_args(const GsrWorkspace& ws, float* img, int h, int w,
   a.entries = ws.entries;
   a.rec_in = ws.rec_in;
   a.box_in = ws.box_in;
-  a.ntx = ws.ntx;
+  a.sched = ws.stats + GSR_STAT_UNIT;
   a.hf = ws.hf;
   a.row0 = ws.row0;
   a.bhs = ws.bn > 0 ? ws.bhs : 0;
@@ -172,11 +224,11 @@ static int gsr_launch_forward_region(const GsrWorkspace& ws, float* img, int h, 
                                    uint32_t flags, cudaStream_t st) {
   GsrFwdArgs a = gsr_fwd_args(ws, img, h, w, keff, flags);
   a.want = 0;
-  // persistent warps: one resident wave, every warp strides over the region pairs
+  // persistent warps: one resident wave, every warp takes regions from the work counter
   int cap = 0;
   const int rc = gsr_resident_grid(gsr_forward_region_kernel<false>, GSR_FR_THREADS, 1, &cap);
   if (rc) return rc;
-  const int nunits = (ws.nrx / 2) * ws.nry;
+  const int nunits = ws.nrx * ws.nry;
   const int want = (nunits + GSR_FR_WARPS - 1) / GSR_FR_WARPS;
   if (ws.win) gsr_forward_region_kernel<true><<<want < cap ? want : cap, GSR_FR_THREADS, 0, st>>>(a);
   else gsr_forward_region_kernel<false><<<want < cap ? want : cap, GSR_FR_THREADS, 0, st>>>(a);
@@ -189,10 +241,13 @@ static int gsr_launch_forward_bins(const GsrWorkspace& ws, float* img, int h, in
                                    uint32_t flags, cudaStream_t st) {
   GsrFwdArgs a = gsr_fwd_args(ws, img, h, w, keff, flags);
   a.want = 1;
-  GSR_CUDA(cudaFuncSetAttribute(gsr_forward_bins_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(GsrFwdSmem)));
+  int rc = gsr_optin_smem(gsr_forward_bins_kernel, (int)sizeof(GsrFwdSmem), 0);
+  if (rc) return rc;
+  int nsm = 0;
+  rc = gsr_sm_count(&nsm);
+  if (rc) return rc;
   const int ntiles = ((w + GSR_TILE_W - 1) / GSR_TILE_W) * ((h + GSR_TILE_H - 1) / GSR_TILE_H);
-  const int grid = ntiles < 148 * GSR_CFG_MIN_CTAS ? ntiles : 148 * GSR_CFG_MIN_CTAS;
+  const int grid = ntiles < nsm * GSR_CFG_MIN_CTAS ? ntiles : nsm * GSR_CFG_MIN_CTAS;
   gsr_forward_bins_kernel<<<grid, GSR_FWD_THREADS, sizeof(GsrFwdSmem), st>>>(a);
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
@@ -201,8 +256,8 @@ static int gsr_launch_forward_bins(const GsrWorkspace& ws, float* img, int h, in
 // Whole forward set-up: tile lists, plus the guarded home-bin fallback.
 static int gsr_prepare_forward(const float* sigmas, const float* coords, const float* colors, int s,
                                int h, int w, float dmax, float keff, const GsrWorkspace& ws,
-                               cudaStream_t st) {
-  int rc = gsr_run_tiles(sigmas, coords, colors, s, h, w, dmax, keff, ws, st);
+                               cudaStream_t st, const float* raw = nullptr, float step = 0.f) {
+  int rc = gsr_run_tiles(sigmas, coords, colors, s, h, w, dmax, keff, ws, st, raw, step);
   if (rc) return rc;
   return gsr_run_bins(sigmas, coords, colors, s, h, w, dmax, keff, ws, ws.stats + GSR_STAT_OVERFLOW, 1, st);
 }
@@ -242,10 +297,32 @@ static int gsr_launch_backward(const GsrWorkspace& ws, const float* sigmas, cons
   a.bdesc = ws.bdesc;
   a.bn = ws.bn;
   a.ragged = ws.ragged;
-  GSR_CUDA(cudaFuncSetAttribute(gsr_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(GsrBwdSmem)));
+  const int rcs = gsr_optin_smem(gsr_backward_kernel, (int)sizeof(GsrBwdSmem), 1);
+  if (rcs) return rcs;
   const int grid = a.tiles_x * a.tiles_y + (s + GSR_BWD_LARGE_CHUNK - 1) / GSR_BWD_LARGE_CHUNK;
   gsr_backward_kernel<<<grid, GSR_BWD_THREADS, sizeof(GsrBwdSmem), st>>>(a);
+  GSR_CUDA(cudaGetLastError());
+  return GSR_OK;
+}
+
+// Padded batches: the per-sample descriptors travel as KERNEL PARAMETERS (by value, 96 per launch), not through a
+// copy from pageable host memory: nothing of the caller's host memory is referenced after the call returns and
+// the call can be captured into a CUDA graph.
+constexpr int GSR_BDESC_PER_LAUNCH = 96;
+struct GsrBDescBlock {
+  GsrBDesc d[GSR_BDESC_PER_LAUNCH];
+};
+static_assert(sizeof(GsrBDescBlock) <= 3500, "kernel parameter space");
+__global__ void gsr_bdesc_store_kernel(GsrBDescBlock blk, GsrBDesc* __restrict__ dst, int n) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = blk.d[threadIdx.x];
+}
+static int gsr_stage_bdesc(const GsrWorkspace& ws, const GsrBDesc* host, int n, cudaStream_t st) {
+  for (int o = 0; o < n; o += GSR_BDESC_PER_LAUNCH) {
+    GsrBDescBlock blk;
+    const int m = n - o < GSR_BDESC_PER_LAUNCH ? n - o : GSR_BDESC_PER_LAUNCH;
+    for (int k = 0; k < m; ++k) blk.d[k] = host[o + k];
+    gsr_bdesc_store_kernel<<<1, GSR_BDESC_PER_LAUNCH, 0, st>>>(blk, ws.bdesc + o, m);
+  }
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
 }
@@ -259,7 +336,8 @@ static int gsr_forward_impl(const float* sigmas, const float* coords, const floa
                             int s, int h, int w, int c, int hf, int row0, float dmax, float ksigma,
                             uint32_t flags, void* workspace, size_t workspace_bytes, void* stream,
                             int bn = 0, int bhs = 0, const gsr_window* win = nullptr,
-                            const GsrBDesc* bdesc_host = nullptr) {
+                            const GsrBDesc* bdesc_host = nullptr, int nsamples = 0, const float* raw = nullptr,
+                            float step = 0.f) {
   if (c != 3) return GSR_ERR_BAD_CHANNELS;
   if (!gsr_dims_ok(s, h, w) || !gsr_band_ok(h, hf, row0)) return GSR_ERR_BAD_SHAPE;
   if (!img || (s > 0 && (!sigmas || !coords || !colors))) return GSR_ERR_NULL_POINTER;
@@ -275,14 +353,15 @@ static int gsr_forward_impl(const float* sigmas, const float* coords, const floa
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const float keff = gsr_effective_ksigma(ksigma);
-  if (bdesc_host) {  // padded batch: per-sample descriptors (pageable host memory: staged before the call returns)
+  if (bdesc_host) {  // padded batch: per-sample descriptors
     ws.ragged = 1;
-    GSR_CUDA(cudaMemcpyAsync(ws.bdesc, bdesc_host, (size_t)(s / bn) * sizeof(GsrBDesc), cudaMemcpyHostToDevice, st));
+    rc = gsr_stage_bdesc(ws, bdesc_host, nsamples, st);
+    if (rc) return rc;
   }
   rc = gsr_clear_and_tables(h, w, ws, st);
   if (rc) return rc;
   ws.win = win;
-  rc = gsr_prepare_forward(sigmas, coords, colors, s, h, w, dmax, keff, ws, st);
+  rc = gsr_prepare_forward(sigmas, coords, colors, s, h, w, dmax, keff, ws, st, raw, step);
   if (rc) return rc;
   return gsr_raster_forward(ws, img, h, w, keff, flags, st);
 }
@@ -292,7 +371,7 @@ static int gsr_backward_impl(const float* sigmas, const float* coords, const flo
                              float* grads_colors, int s, int h, int w, int c, int hf, int row0,
                              float dmax, float ksigma, uint32_t flags, void* workspace,
                              size_t workspace_bytes, void* stream, int bn = 0, int bhs = 0,
-                             const GsrBDesc* bdesc_host = nullptr) {
+                             const GsrBDesc* bdesc_host = nullptr, int nsamples = 0) {
   if (c != 3) return GSR_ERR_BAD_CHANNELS;
   if (!gsr_dims_ok(s, h, w) || !gsr_band_ok(h, hf, row0)) return GSR_ERR_BAD_SHAPE;
   if (!grads || (s > 0 && (!sigmas || !coords || !colors || !grads_sigmas || !grads_coords ||
@@ -309,7 +388,8 @@ static int gsr_backward_impl(const float* sigmas, const float* coords, const flo
   const float keff = gsr_effective_ksigma(ksigma);
   if (bdesc_host) {
     ws.ragged = 1;
-    GSR_CUDA(cudaMemcpyAsync(ws.bdesc, bdesc_host, (size_t)(s / bn) * sizeof(GsrBDesc), cudaMemcpyHostToDevice, st));
+    rc = gsr_stage_bdesc(ws, bdesc_host, nsamples, st);
+    if (rc) return rc;
   }
   rc = gsr_clear_and_tables(h, w, ws, st);
   if (rc) return rc;
@@ -390,10 +470,11 @@ extern "C" size_t gsr_workspace_bytes_batch_uniform(int batch, int s_per, int h,
   return a > b ? a : b;
 }
 
-extern "C" int gsr_forward_batch_uniform(const float* sigmas, const float* coords, const float* colors,
-                                         float* imgs, int batch, int s_per, int h, int w, int c,
-                                         float dmax, float ksigma, uint32_t flags, void* workspace,
-                                         size_t workspace_bytes, void* stream) {
+static int gsr_forward_batch_uniform_impl(const float* sigmas, const float* coords, const float* colors,
+                                          float* imgs, int batch, int s_per, int h, int w, int c,
+                                          float dmax, float ksigma, uint32_t flags, void* workspace,
+                                          size_t workspace_bytes, void* stream, const float* raw = nullptr,
+                                          float step = 0.f) {
   if (batch < 0) return GSR_ERR_BAD_ARGUMENT;
   if (!gsr_dims_ok(s_per, h, w)) return GSR_ERR_BAD_SHAPE;
   if (batch > 0 && !imgs) return GSR_ERR_NULL_POINTER;
@@ -407,10 +488,19 @@ extern "C" int gsr_forward_batch_uniform(const float* sigmas, const float* coord
                                                           : imgs + (size_t)b0 * h * w * 3,
                                     nb * s_per,
                                     nb * h, w, c, 0, 0, dmax, ksigma, flags, workspace, workspace_bytes, stream,
-                                    nb > 1 ? s_per : 0, nb > 1 ? h : 0);
+                                    nb > 1 ? s_per : 0, nb > 1 ? h : 0, nullptr, nullptr, 0,
+                                    raw ? raw + 9 * go : nullptr, step);
     if (rc) return rc;
   }
   return GSR_OK;
+}
+
+extern "C" int gsr_forward_batch_uniform(const float* sigmas, const float* coords, const float* colors,
+                                         float* imgs, int batch, int s_per, int h, int w, int c,
+                                         float dmax, float ksigma, uint32_t flags, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  return gsr_forward_batch_uniform_impl(sigmas, coords, colors, imgs, batch, s_per, h, w, c, dmax, ksigma, flags,
+                                        workspace, workspace_bytes, stream);
 }
 
 extern "C" int gsr_backward_batch_uniform(const float* sigmas, const float* coords, const float* colors,
@@ -538,15 +628,11 @@ extern "C" int gsr_frontend_forward(const float* raw, float* mapped, float* img_
   if (!gsr_dims_ok(s, h, w)) return GSR_ERR_BAD_SHAPE;
   if (!img_chw || (s > 0 && (!raw || !mapped))) return GSR_ERR_NULL_POINTER;
   if (!(step_size > 0.0f)) return GSR_ERR_BAD_ARGUMENT;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (s > 0) {
-    gsr_map_kernel<<<(s + 255) / 256, 256, 0, st>>>(raw, mapped, mapped + 3 * (size_t)s,
-                                                    mapped + 5 * (size_t)s, s, h, w, step_size);
-    GSR_CUDA(cudaGetLastError());
-  }
-  return gsr_forward(mapped, mapped + 3 * (size_t)s, mapped + 5 * (size_t)s, img_chw, s, h, w, 3,
-                     dmax, ksigma, GSR_FLAG_OVERWRITE | GSR_FLAG_CHW, workspace, workspace_bytes,
-                     stream);
+  // the set-up kernel applies the activations and the unit mapping itself and leaves the mapped parameters
+  // in `mapped` for the backward: no separate elementwise pass, no second read of them
+  return gsr_forward_impl(mapped, mapped + 3 * (size_t)s, mapped + 5 * (size_t)s, img_chw, s, h, w, 3, 0, 0, dmax,
+                          ksigma, GSR_FLAG_OVERWRITE | GSR_FLAG_CHW, workspace, workspace_bytes, stream, 0, 0, nullptr,
+                          nullptr, 0, raw, step_size);
 }
 
 extern "C" int gsr_frontend_backward(const float* raw, const float* mapped, const float* grads_chw,
@@ -641,7 +727,7 @@ extern "C" int gsr_forward_batch_padded(const float* sigmas, const float* coords
     rc = gsr_forward_impl(sigmas ? sigmas + 3 * go : nullptr, coords ? coords + 2 * go : nullptr,
                           colors ? colors + 3 * go : nullptr, imgs + (size_t)b0 * hmax * wmax * 3, nb * s_per,
                           nb * hmax, wmax, 3, 0, 0, dmax, ksigma, flags, workspace, workspace_bytes, stream, s_per,
-                          hmax, nullptr, desc);
+                          hmax, nullptr, desc, nb);
     if (rc) return rc;
   }
   return GSR_OK;
@@ -668,7 +754,7 @@ extern "C" int gsr_backward_batch_padded(const float* sigmas, const float* coord
                            grads_sigmas ? grads_sigmas + 3 * go : nullptr,
                            grads_coords ? grads_coords + 2 * go : nullptr,
                            grads_colors ? grads_colors + 3 * go : nullptr, nb * s_per, nb * hmax, wmax, 3, 0, 0,
-                           dmax, ksigma, flags, workspace, workspace_bytes, stream, s_per, hmax, desc);
+                           dmax, ksigma, flags, workspace, workspace_bytes, stream, s_per, hmax, desc, nb);
     if (rc) return rc;
   }
   return GSR_OK;
@@ -684,14 +770,9 @@ extern "C" int gsr_frontend_forward_batch_uniform(const float* raw, float* mappe
   const int s = batch * s_per;
   if (!imgs || (s > 0 && (!raw || !mapped))) return GSR_ERR_NULL_POINTER;
   if (!(step_size > 0.0f)) return GSR_ERR_BAD_ARGUMENT;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (s > 0) {
-    gsr_map_kernel<<<(s + 255) / 256, 256, 0, st>>>(raw, mapped, mapped + 3 * (size_t)s,
-                                                    mapped + 5 * (size_t)s, s, h, w, step_size);
-    GSR_CUDA(cudaGetLastError());
-  }
-  return gsr_forward_batch_uniform(mapped, mapped + 3 * (size_t)s, mapped + 5 * (size_t)s, imgs, batch, s_per, h,
-                                   w, 3, dmax, ksigma, GSR_FLAG_OVERWRITE, workspace, workspace_bytes, stream);
+  return gsr_forward_batch_uniform_impl(mapped, mapped + 3 * (size_t)s, mapped + 5 * (size_t)s, imgs, batch, s_per, h,
+                                        w, 3, dmax, ksigma, GSR_FLAG_OVERWRITE, workspace, workspace_bytes, stream, raw,
+                                        step_size);
 }
 
 // grads (batch,h,w,3) -> grad_raw (batch*s_per,9), written.  Workspace: gsr_workspace_bytes_batch_uniform
@@ -730,14 +811,9 @@ extern "C" int gsr_frontend_forward_window(const float* raw, float* mapped, floa
   if (!gsr_dims_ok(s, h, w)) return GSR_ERR_BAD_SHAPE;
   if (!origin || !win || (s > 0 && (!raw || !mapped))) return GSR_ERR_NULL_POINTER;
   if (!(step_size > 0.0f)) return GSR_ERR_BAD_ARGUMENT;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (s > 0) {
-    gsr_map_kernel<<<(s + 255) / 256, 256, 0, st>>>(raw, mapped, mapped + 3 * (size_t)s,
-                                                    mapped + 5 * (size_t)s, s, h, w, step_size);
-    GSR_CUDA(cudaGetLastError());
-  }
-  return gsr_forward_window(mapped, mapped + 3 * (size_t)s, mapped + 5 * (size_t)s, origin, win, s, h, w, 3,
-                            dmax, ksigma, flags, workspace, workspace_bytes, stream);
+  if (win->nclip < 0 || win->nclip > GSR_MAX_CLIP || (flags & GSR_FLAG_CHW)) return GSR_ERR_BAD_ARGUMENT;
+  return gsr_forward_impl(mapped, mapped + 3 * (size_t)s, mapped + 5 * (size_t)s, origin, s, h, w, 3, 0, 0, dmax,
+                          ksigma, flags, workspace, workspace_bytes, stream, 0, 0, win, nullptr, 0, raw, step_size);
 }
 
 // Fused front end for a padded batch: raw (batch*s_per,9) -> imgs (batch,hmax,wmax,3); every sample its own
@@ -764,15 +840,9 @@ extern "C" int gsr_frontend_forward_batch_padded(const float* raw, float* mapped
     rc = gsr_check_ws(workspace, workspace_bytes, ws.bytes);
     if (rc) return rc;
     gsr_padded_fill(desc, nb, hmax, wmax, hw_host + 2 * b0, dmax_host ? dmax_host + b0 : nullptr, dmax, step_host + b0);
-    GSR_CUDA(cudaMemcpyAsync(ws.bdesc, desc, (size_t)nb * sizeof(GsrBDesc), cudaMemcpyHostToDevice, st));
-    if (sg > 0) {
-      gsr_map_kernel<<<(sg + 255) / 256, 256, 0, st>>>(raw + 9 * go, sig + 3 * go, crd + 2 * go, col + 3 * go, sg, 0, 0,
-                                                       0.f, ws.bdesc, s_per);
-      GSR_CUDA(cudaGetLastError());
-    }
     rc = gsr_forward_impl(sig + 3 * go, crd + 2 * go, col + 3 * go, imgs + (size_t)b0 * hmax * wmax * 3, sg, nb * hmax,
                           wmax, 3, 0, 0, dmax, ksigma, GSR_FLAG_OVERWRITE, workspace, workspace_bytes, stream, s_per, hmax,
-                          nullptr, desc);
+                          nullptr, desc, nb, raw + 9 * go, 1.0f);
     if (rc) return rc;
   }
   return GSR_OK;
@@ -808,7 +878,7 @@ extern "C" int gsr_frontend_backward_batch_padded(const float* raw, const float*
     GSR_CUDA(cudaMemsetAsync(gm, 0, (size_t)sg * 8 * sizeof(float), st));
     rc = gsr_backward_impl(sig + 3 * go, crd + 2 * go, col + 3 * go, grads + (size_t)b0 * hmax * wmax * 3, gm,
                            gm + 3 * (size_t)sg, gm + 5 * (size_t)sg, sg, nb * hmax, wmax, 3, 0, 0, dmax, ksigma, 0,
-                           workspace, need, stream, s_per, hmax, desc);
+                           workspace, need, stream, s_per, hmax, desc, nb);
     if (rc) return rc;
     gsr_unmap_kernel<<<(sg + 255) / 256, 256, 0, st>>>(raw + 9 * go, gm, gm + 3 * (size_t)sg, gm + 5 * (size_t)sg,
                                                        grad_raw + 9 * go, sg, 0, 0, 0.f, ws.bdesc, s_per);
@@ -874,6 +944,49 @@ extern "C" unsigned gsr_host_region_mask(const float* sigmas, const float* coord
   GsrRec r = gsr_make_rec(sigmas[3 * i], sigmas[3 * i + 1], sigmas[3 * i + 2], coords[2 * i],
                           coords[2 * i + 1], colors[3 * i], colors[3 * i + 1], colors[3 * i + 2]);
   return gsr_region_mask(r, st.x0, st.x1, st.y0, st.y1, tx0, ty0, h, w, gsr_ecut(keff));
+}
+
+// Bucket entries of Gaussian i as the set-up kernel's shared-memory path writes them: triples
+// (region column, region row, 8-bit cell mask), at most cap of them; returns their number (0: not live).
+extern "C" int gsr_host_entries(const float* sigmas, const float* coords, const float* colors, int i, int h,
+                                int w, float dmax, float ksigma, int* out, int cap) {
+  const float keff = gsr_effective_ksigma(ksigma);
+  GsrSetup st = gsr_setup(sigmas[3 * i], sigmas[3 * i + 1], sigmas[3 * i + 2], coords[2 * i],
+                          coords[2 * i + 1], colors[3 * i], colors[3 * i + 1], colors[3 * i + 2], h,
+                          w, dmax, keff);
+  if (!st.live) return 0;
+  const GsrRec r = gsr_make_rec(sigmas[3 * i], sigmas[3 * i + 1], sigmas[3 * i + 2], coords[2 * i],
+                                coords[2 * i + 1], colors[3 * i], colors[3 * i + 1], colors[3 * i + 2]);
+  if (!(gsr_finite(r.a) && gsr_finite(r.b) && gsr_finite(r.c))) return 0;
+  const GsrEllipse e = gsr_ellipse(r, h, w);
+  int n = 0;
+  const int cbase = (st.x0 / GSR_RGW) * GSR_CELLS_X;
+  const bool narrow = st.x1 / GSR_CELL - cbase < 32;
+  for (int b = st.y0 / GSR_RGH; b <= st.y1 / GSR_RGH; ++b) {
+    uint32_t rb[2] = {0u, 0u};
+    int cl[2], ch[2], ca, cb;
+    if (narrow) {
+      if (!gsr_band_rowbits(e, gsr_ecut(keff), b, st.x0, st.x1, st.y0, st.y1, cbase, rb)) continue;
+      const uint32_t any = rb[0] | rb[1];
+      int lo = 0, hi = 31;
+      while (!((any >> lo) & 1u)) ++lo;
+      while (!((any >> hi) & 1u)) --hi;
+      ca = (cbase + lo) / GSR_CELLS_X;
+      cb = (cbase + hi) / GSR_CELLS_X;
+    } else {
+      if (!gsr_band_cells(e, gsr_ecut(keff), b, st.x0, st.x1, st.y0, st.y1, cl, ch)) continue;
+      gsr_band_columns(cl, ch, ca, cb);
+    }
+    for (int c = ca; c <= cb; ++c) {
+      if (n < cap) {
+        out[3 * n + 0] = c;
+        out[3 * n + 1] = b;
+        out[3 * n + 2] = (int)(narrow ? gsr_rowbits_mask(rb, c, cbase) : gsr_cell_mask(cl, ch, c));
+      }
+      ++n;
+    }
+  }
+  return n;
 }
 
 extern "C" void gsr_host_geometry(int* tile_w, int* tile_h, int* bin, int* region, int* large_px) {

@@ -13,8 +13,12 @@ variants differentiate correctly (the reference drops the gradient of all but th
 gswrapper.py:44).  ``fused=True`` additionally replaces the ~15 elementwise torch kernels by the
 library's fused front end (gsr_frontend_forward / _backward; parity 1e-4, not bitwise).
 
-``cuda_rendering=False`` selected the reference's PyTorch resampling renderer (rendering_python,
-:11-84), a different algorithm that is not part of this library: it raises here.
+``cuda_rendering=False`` selects rendering_python (:11-84), the reference's PyTorch resampling renderer: every
+Gaussian is tabulated on a num_step x num_step grid, normalised by its largest sample, and resampled bilinearly
+onto the image.  It is a DIFFERENT function of the parameters than the CUDA kernels (max-abs 0.65 apart on a
+random field) and the path BASELINE config 1 times; mirrored here in plain torch ops (any device)
+so that callers that pass cuda_rendering=False keep working.  It is not a fallback of the CUDA path: nothing
+routes to it unless the caller asks for it by name.
 """
 from __future__ import annotations
 
@@ -26,7 +30,7 @@ from . import _lib
 from . import gscuda as _gs
 
 __all__ = [
-    "generate_2D_gaussian_splatting_step", "generate_2D_gaussian_splatting_step_buffer",
+    "generate_2D_gaussian_splatting_step", "generate_2D_gaussian_splatting_step_buffer", "rendering_python",
     "generate_2D_gaussian_splatting_step_batch", "generate_2D_gaussian_splatting_step_batch_padded",
     "generate_2D_gaussian_splatting_step_u8", "render_into_canvas",
     "rendering_cuda", "rendering_cuda_buffer", "rendering_cuda_dmax", "rendering_cuda_dmax_buffer",
@@ -156,8 +160,8 @@ class _FusedFrontend(Function):
         return g_raw, None, None, None, None
 
 
-def _prepare(gs_parameters, scale, scale_modify, default_step_size, mode):
-    # set step_size according to scale factor (:164-171)
+def _step_size(scale, scale_modify, default_step_size, mode):
+    """Step size from the scale factor (:164-171): the same checks for the unfused and the fused paths."""
     if mode == 'scale':
         final_scale = scale
     elif mode == 'scale_modify':
@@ -165,7 +169,11 @@ def _prepare(gs_parameters, scale, scale_modify, default_step_size, mode):
         final_scale = scale_modify[0]
     else:
         raise ValueError(f"mode-{mode} must be scale or scale_modify")
-    step_size = default_step_size / final_scale
+    return default_step_size / final_scale
+
+
+def _prepare(gs_parameters, scale, scale_modify, default_step_size, mode):
+    step_size = _step_size(scale, scale_modify, default_step_size, mode)
     # prepare gaussian properties (:174-180)
     sigma_x = 0.99999 * torch.sigmoid(gs_parameters[:, 0:1]) + 1e-6
     sigma_y = 0.99999 * torch.sigmoid(gs_parameters[:, 1:2]) + 1e-6
@@ -187,11 +195,56 @@ def _resolve_dmax(if_dmax, dmax_mode, dmax, sr_size):
     raise ValueError(f"dmax_mode-{dmax_mode} must be fix or dynamic")
 
 
-def _no_python_renderer():
-    raise NotImplementedError(
-        "cuda_rendering=False selects the reference's PyTorch resampling renderer "
-        "(utils/gaussian_splatting.py:11-84), which this library does not provide; "
-        "the B200 rasteriser has no CPU path")
+def rendering_python(sigma_x, sigma_y, rho, coords, colours_with_alpha, sr_size, step_size, device,
+                     max_buffer=2000):
+    """The reference's PyTorch renderer (utils/gaussian_splatting.py:11-84), restated.
+
+    Per Gaussian: K[i,j] = N(d_ij; 0, Sigma) on the num_step x num_step grid d_ij = ((i, j) - (n-1)/2) * step_size
+    (num_step = int(20 / step_size); sigma_x pairs with the ROW offset, :37-45), divided by (max_ij K + 1e-4)
+    (:61-65); the table is resampled bilinearly with zero padding onto the (H, W) image through an affine grid
+    that maps output coordinate o (align_corners=False) to table coordinate (o - centre) * size / num_step
+    (:69-80); colour-weighted tables are summed.  Differences to the reference's code: the 2x2 covariance is
+    inverted in closed form, and one channel is resampled instead of three identical ones (a third of the
+    (2000,3,H,W) temporaries); results agree to fp32 round-off."""
+    import torch.nn.functional as F
+
+    sr_h, sr_w = int(sr_size[0]), int(sr_size[1])
+    step_size = float(step_size)
+    sx, sy, r = sigma_x.reshape(-1).float(), sigma_y.reshape(-1).float(), rho.reshape(-1).float()
+    det = sx * sx * sy * sy - (r * sx * sy) ** 2
+    if bool((det < 0).any()):
+        raise ValueError("Covariance matrix must be positive semi-definite")
+    # inverse covariance: [[sy^2, -r sx sy], [-r sx sy, sx^2]] / det
+    ixx, ixy, iyy = sy * sy / det, -r * sx * sy / det, sx * sx / det
+    num_step = int(10 * 2 / step_size)
+    ax = torch.arange(num_step, dtype=torch.float32, device=device) * step_size
+    ax = ax - ax.mean()
+    u, v = ax[:, None], ax[None, :]  # u: row offset (pairs with sigma_x), v: column offset
+    norm = 1.0 / (2.0 * torch.pi * torch.sqrt(det))
+    final_image = torch.zeros((3, sr_h, sr_w), device=device)
+    n = sx.shape[0]
+    for a in range(0, n, max_buffer):
+        b = min(a + max_buffer, n)
+        z = -0.5 * (ixx[a:b, None, None] * u * u + 2.0 * ixy[a:b, None, None] * u * v + iyy[a:b, None, None] * v * v)
+        kernel = torch.exp(z) * norm[a:b, None, None]
+        kmax = kernel.amax(dim=(-2, -1), keepdim=True)
+        kernel = (kernel / (kmax + 1e-4)).unsqueeze(1)  # (b,1,n,n)
+        theta = torch.zeros(b - a, 2, 3, dtype=torch.float32, device=device)
+        theta[:, 0, 0] = sr_w / num_step
+        theta[:, 1, 1] = sr_h / num_step
+        theta[:, 0, 2] = -coords[a:b, 0] * sr_w / num_step
+        theta[:, 1, 2] = -coords[a:b, 1] * sr_h / num_step
+        grid = F.affine_grid(theta, size=(b - a, 1, sr_h, sr_w), align_corners=False)
+        moved = F.grid_sample(kernel, grid, align_corners=False)  # (b,1,H,W)
+        final_image += torch.einsum('bhw,bc->chw', moved[:, 0], colours_with_alpha[a:b].float())
+    return final_image
+
+
+def _python_renderer(gs_parameters, sr_size, scale, scale_modify, default_step_size, mode):
+    step_size, sigma_x, sigma_y, rho, coords, colours_with_alpha = _prepare(
+        gs_parameters, scale, scale_modify, default_step_size, mode)
+    return rendering_python(sigma_x, sigma_y, rho, coords, colours_with_alpha, sr_size, step_size,
+                            device=sigma_x.device)
 
 
 def _sample(final_image, sample_coords):
@@ -205,10 +258,11 @@ def generate_2D_gaussian_splatting_step(sr_size, gs_parameters, scale, scale_mod
                                         sample_coords=None, default_step_size=1.2,
                                         cuda_rendering=True, mode='scale_modify',
                                         if_dmax=True, dmax_mode='fix', dmax=25, fused=False):
-    if not cuda_rendering:
-        _no_python_renderer()
+    if not cuda_rendering:  # the reference's PyTorch renderer, on request (:210-212)
+        return _sample(_python_renderer(gs_parameters, sr_size, scale, scale_modify, default_step_size, mode),
+                       sample_coords)
     if fused:
-        step_size = float(default_step_size / (scale if mode == 'scale' else scale_modify[0]))
+        step_size = float(_step_size(scale, scale_modify, default_step_size, mode))
         final_image = _FusedFrontend.apply(gs_parameters, int(sr_size[0]), int(sr_size[1]), step_size,
                                            _resolve_dmax(if_dmax, dmax_mode, dmax, sr_size))
         return _sample(final_image, sample_coords)
@@ -229,8 +283,9 @@ def generate_2D_gaussian_splatting_step_buffer(sr_size, gs_parameters, scale, sc
                                                cuda_rendering=True, mode='scale_modify',
                                                if_dmax=True, dmax_mode='fix', dmax=25,
                                                buffer_size=4000000):
-    if not cuda_rendering:
-        _no_python_renderer()
+    if not cuda_rendering:  # (:258-260) the reference ignores buffer_size on this path too
+        return _sample(_python_renderer(gs_parameters, sr_size, scale, scale_modify, default_step_size, mode),
+                       sample_coords)
     step_size, sigma_x, sigma_y, rho, coords, colours_with_alpha = _prepare(
         gs_parameters, scale, scale_modify, default_step_size, mode)
     if if_dmax:
@@ -303,7 +358,7 @@ def generate_2D_gaussian_splatting_step_batch(sr_size, gs_parameters, scale, sca
     b, n = gs_parameters.shape[:2]
     dm = _resolve_dmax(if_dmax, dmax_mode, dmax, sr_size)
     if fused:
-        step_size = float(default_step_size / (scale if mode == 'scale' else scale_modify[0]))
+        step_size = float(_step_size(scale, scale_modify, default_step_size, mode))
         out = _FusedFrontendBatch.apply(gs_parameters, int(sr_size[0]), int(sr_size[1]), step_size, dm)
         return out.permute(0, 3, 1, 2)
     step_size, sigma_x, sigma_y, rho, coords, colours_with_alpha = _prepare(
@@ -335,7 +390,7 @@ def render_into_canvas(canvas, y0, x0, regions, sr_size, gs_parameters, scale, s
         return
     dm = _resolve_dmax(if_dmax, dmax_mode, dmax, sr_size)
     if fused:  # the library's fused front end (parity 1e-4) instead of ~15 elementwise torch kernels
-        step_size = float(default_step_size / (scale if mode == 'scale' else scale_modify[0]))
+        step_size = float(_step_size(scale, scale_modify, default_step_size, mode))
         _gs.frontend_render_window(gs_parameters.contiguous().float(), canvas, y0 * W + x0, W, 1, H * W, clips,
                                    h, w, step_size, dm, flags=_OVER)
         return

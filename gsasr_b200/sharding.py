@@ -47,6 +47,8 @@ def render_units_sharded(n_units: int, render_unit: Callable[[int], torch.Tensor
     backend = dist.get_backend(group)
     if backend == "nccl":
         device = torch.device("cuda", torch.cuda.current_device())
+    # torch.distributed takes GLOBAL ranks for src / dst whatever the group: translate group-local ones
+    glob = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
     shapes = torch.zeros(n_units, 9, dtype=torch.int64, device=device)  # [ndim, up to 8 extents]
     for i, t in mine.items():
         shapes[i, 0] = t.dim()
@@ -66,17 +68,17 @@ def render_units_sharded(n_units: int, render_unit: Callable[[int], torch.Tensor
             continue
         if gather_to is None:
             buf = mine[i].contiguous() if src == rank else torch.empty(shape, dtype=torch.float32, device=device)
-            dist.broadcast(buf, src=dist.get_global_rank(group, src) if group else src, group=group)
+            dist.broadcast(buf, src=glob(src), group=group)
             out.append(buf)
         else:
             if src == gather_to:
                 if rank == gather_to:
                     out.append(mine[i])
             elif rank == src:
-                dist.send(mine[i].contiguous(), dst=gather_to, group=group)
+                dist.send(mine[i].contiguous(), dst=glob(gather_to), group=group)
             elif rank == gather_to:
                 buf = torch.empty(shape, dtype=torch.float32, device=device)
-                dist.recv(buf, src=src, group=group)
+                dist.recv(buf, src=glob(src), group=group)
                 out.append(buf)
     if gather_to is None or rank == gather_to:
         return out
@@ -150,7 +152,9 @@ def render_image_bands_peer(sigmas, coords, colors, h: int, w: int, dmax: float,
     """render_image_bands with the gather folded into the raster kernel: the (h,w,3) image lives in
     symmetric memory on `gather_to` and every rank's band kernel stores its rows straight into it over
     NVLink (peer writes) -- no collective, the transfer overlaps the raster.  Returns a view of the
-    symmetric buffer on `gather_to` (valid until the next call), None elsewhere.  CUDA + NCCL only."""
+    symmetric buffer on `gather_to` (valid until the next call: a call first drains every rank's current stream
+    and meets at a barrier, so work already queued on the returned view completes before it is overwritten),
+    None elsewhere.  CUDA + NCCL only."""
     from . import gscuda
 
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
@@ -158,6 +162,10 @@ def render_image_bands_peer(sigmas, coords, colors, h: int, w: int, dmax: float,
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     mine, target, hdl = _peer_image(h * w * 3, sigmas.device, gather_to, group)
     row0, rows = band_rows(h, rank, world)
+    # The buffer is reused from call to call: no rank may store into it while the stitching rank's stream
+    # still reads the image the previous call returned.  Everybody waits for everybody's queued work first.
+    torch.cuda.current_stream().synchronize()
+    hdl.barrier()
     if rows > 0:
         band = target.view(h, w, 3)[row0:row0 + rows]  # contiguous rows of the stitching rank's image
         gscuda.gs_render_band(sigmas, coords, colors, band, sigmas.shape[0], h, w, 3, row0, rows, dmax, flags=1)

@@ -214,16 +214,34 @@ def split_and_joint_image(lq, scale_factor, split_size, overlap_size, model_g, m
     return stitch_tiles(tiles, plan, lq.shape[0], lq.shape[1], scale_factor, crop_size)
 
 
+def split_and_joint_image_buffer(lq, scale_factor, split_size, overlap_size, model_g, model_fea2gs, scale_modify,
+                                 crop_size=2, default_step_size=1.2, mode='scale_modify', cuda_rendering=True,
+                                 if_dmax=False, dmax_mode='fix', dmax=25, buffer_size=4000000, *, gather_to=0,
+                                 group=None):
+    """TrainTestGSASR/basicsr/utils/split_and_joint_image.py:142-285: split_and_joint_image whose tiles are
+    rendered by generate_2D_gaussian_splatting_step_buffer -- the Gaussians of a tile are handed to the
+    rasteriser in slices of `buffer_size`, accumulated into the same image.  Same tiling, paste rules and
+    multi-GPU tile sharding as split_and_joint_image."""
+    from .gaussian_splatting import generate_2D_gaussian_splatting_step_buffer
+
+    def render_fn(**kw):
+        return generate_2D_gaussian_splatting_step_buffer(buffer_size=buffer_size, **kw)
+
+    return split_and_joint_image(lq, scale_factor, split_size, overlap_size, model_g, model_fea2gs, scale_modify,
+                                 crop_size, default_step_size, mode, cuda_rendering, if_dmax, dmax_mode, dmax,
+                                 render_fn=render_fn, gather_to=gather_to, group=group)
+
+
 def _split_and_joint_direct(lq, plan, tile_parameters, scale_factor, scale_modify, crop_size,
                             default_step_size, mode, cuda_rendering, if_dmax, dmax_mode, dmax, gather_to, group,
                             fused=False):
     import torch.distributed as dist
 
-    from .gaussian_splatting import _no_python_renderer, render_into_canvas
+    from .gaussian_splatting import render_into_canvas
     from .sharding import shard_range
 
     if not cuda_rendering:
-        _no_python_renderer()
+        raise RuntimeError("direct=True writes tiles from the CUDA raster kernel; use direct=False with cuda_rendering=False")
     if lq.shape[0] != 1 or lq.shape[1] != 3:
         raise RuntimeError("direct=True renders one RGB image (B = 1, C = 3), like the reference's tile loop")
     regions = tile_regions(plan, crop_size, scale_factor == int(scale_factor))

@@ -20,6 +20,10 @@ void gsr_host_window_range(int n, float ctr, float dmax, int* lo, int* hi);
 /* 16-bit mask of the 8x8 regions of the 32x32 tile at (tx0,ty0) that Gaussian i may touch */
 unsigned gsr_host_region_mask(const float* sigmas, const float* coords, const float* colors, int i,
                               int h, int w, float dmax, float ksigma, int tx0, int ty0);
+/* bucket entries of Gaussian i (forward fast path): out is n x 3 = region column (16 px), region row (8 px),
+ * 8-bit mask of the region's 4x4-pixel cells (bit = cell row * 4 + cell column); returns n (may exceed cap) */
+int gsr_host_entries(const float* sigmas, const float* coords, const float* colors, int i, int h, int w,
+                     float dmax, float ksigma, int* out, int cap);
 void gsr_host_geometry(int* tile_w, int* tile_h, int* bin, int* region, int* large_px);
 
 #ifdef __cplusplus

@@ -68,3 +68,42 @@ def emulate_forward(sigmas, coords, colors, h, w, dmax, ksigma):
                     img[ya:yb, xa:xb, :] += v[:, :, None] * colors[g].astype(np.float64)[None, None, :]
                     npairs += v.size
     return img, npairs
+
+
+def emulate_forward_cells(sigmas, coords, colors, h, w, dmax, ksigma):
+    """Same for the region-bucket fast path: exactly the (Gaussian, 4x4-pixel cell) pairs the bucket entries
+    name (gsr_host_entries: 16x8-pixel regions, 8-bit cell masks).  Returns (img float64, pairs evaluated)."""
+    L = _lib.load()
+    sigmas = np.ascontiguousarray(sigmas, np.float32)
+    coords = np.ascontiguousarray(coords, np.float32)
+    colors = np.ascontiguousarray(colors, np.float32)
+    st = host_setup(sigmas, coords, colors, h, w, dmax, ksigma)
+    px, py = pix_coords(w), pix_coords(h)
+    img = np.zeros((h, w, 3))
+    npairs = 0
+    cap = 4096
+    out = np.zeros((cap, 3), dtype=np.int32)
+    for g in np.nonzero(st[:, 0])[0]:
+        _, x0, x1, y0, y1, binds, _, _, _ = st[g]
+        n = L.gsr_host_entries(sigmas.ctypes.data, coords.ctypes.data, colors.ctypes.data, int(g), h, w,
+                               float(dmax), float(ksigma), out.ctypes.data, cap)
+        assert n <= cap
+        sx, sy, rho = (float(v) for v in sigmas[g])
+        w1 = -0.5 / (1.0 - rho * rho)
+        for c, b, m in out[:n]:
+            for cell in range(8):
+                if not (m >> cell) & 1:
+                    continue
+                xa, ya = c * 16 + (cell & 3) * 4, b * 8 + (cell >> 2) * 4
+                xb, yb = min(xa + 4, w), min(ya + 4, h)
+                if binds:
+                    xa, xb, ya, yb = max(xa, x0), min(xb, x1 + 1), max(ya, y0), min(yb, y1 + 1)
+                if xa >= xb or ya >= yb:
+                    continue
+                dx = (px[xa:xb] - coords[g, 0]).astype(np.float64)[None, :]
+                dy = (py[ya:yb] - coords[g, 1]).astype(np.float64)[:, None]
+                q = dx * dx / (sx * sx) - 2 * rho * dx * dy / (sx * sy) + dy * dy / (sy * sy)
+                v = np.exp(w1 * q)
+                img[ya:yb, xa:xb, :] += v[:, :, None] * colors[g].astype(np.float64)[None, None, :]
+                npairs += v.size
+    return img, npairs

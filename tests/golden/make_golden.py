@@ -14,6 +14,9 @@
       and call generate_2D_gaussian_splatting_step on a seeded raw (N,9) tensor: the recorded
       (sigmas, coords, colors, dmax) pin activations + unit/coordinate mapping (:174-180,121-123).
 
+  python_renderer_*.npz
+      The image of the reference's PyTorch renderer (rendering_python, cuda_rendering=False) on a seeded field.
+
 Nothing here runs at test time; tests only read the .npz files.
 """
 import importlib.util
@@ -94,6 +97,30 @@ def frontend_fixture(n_side, scale, seed, dmax, dmax_mode):
     return rec
 
 
+def python_renderer_fixture(n_side, scale, seed):
+    """The reference's PyTorch renderer (utils/gaussian_splatting.py:11-84, cuda_rendering=False) run unmodified on
+    the CPU on a seeded raw (N,9) tensor: pins the mirror gsasr_b200.gaussian_splatting.rendering_python."""
+    sys.path.insert(0, REF)
+    for name in ("utils.gs_cuda_dmax.gswrapper", "utils.gs_cuda.gswrapper"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    import utils.gaussian_splatting as gsp
+
+    g = torch.Generator().manual_seed(seed)
+    raw = torch.randn(n_side * n_side, 9, generator=g)
+    jj, ii = torch.meshgrid(torch.arange(n_side, dtype=torch.float32), torch.arange(n_side, dtype=torch.float32),
+                            indexing="xy")
+    raw[:, 7] = (jj.reshape(-1) + 0.5) / n_side + raw[:, 7] * (0.5 / n_side)
+    raw[:, 8] = (ii.reshape(-1) + 0.5) / n_side + raw[:, 8] * (0.5 / n_side)
+    lr = n_side // 2
+    h, w = int(np.floor(lr * scale)) + 2, int(np.floor(lr * scale))
+    out = gsp.generate_2D_gaussian_splatting_step(
+        sr_size=torch.tensor([h, w]), gs_parameters=raw.clone(), scale=scale,
+        scale_modify=torch.tensor([scale, scale]), default_step_size=1.2, cuda_rendering=False,
+        mode='scale_modify')
+    assert tuple(out.shape) == (3, h, w)
+    return dict(raw=raw.numpy(), img=out.numpy(), h=h, w=w, scale=np.float32(scale))
+
+
 def stitch_fixture(h_lq, w_lq, scale, split, overlap, crop, seed):
     """The reference's split_and_joint_image (utils/split_and_joint_image.py:98-232) run unmodified
     on CPU with stub networks and a stub renderer that returns seeded random tiles: pins the tile
@@ -126,6 +153,8 @@ def main():
     np.savez(os.path.join(OUT, "check_dmax_narrow.npz"), **run_check(cd, 24, (37, 45), 0.2, 7, 0.15))
     np.savez(os.path.join(OUT, "frontend_x4_fix.npz"), **frontend_fixture(16, 4.0, 0, 0.1, 'fix'))
     np.savez(os.path.join(OUT, "frontend_x2p5_dynamic.npz"), **frontend_fixture(12, 2.5, 1, 25, 'dynamic'))
+    np.savez(os.path.join(OUT, "python_renderer_x2.npz"), **python_renderer_fixture(24, 2.0, 3))
+    np.savez(os.path.join(OUT, "python_renderer_x3p5.npz"), **python_renderer_fixture(16, 3.5, 4))
     np.savez(os.path.join(OUT, "stitch_x4.npz"), **stitch_fixture(40, 52, 4.0, 16, 4, 2, 0))
     np.savez(os.path.join(OUT, "stitch_x2p5.npz"), **stitch_fixture(37, 45, 2.5, 14, 3, 2, 1))
     np.savez(os.path.join(OUT, "stitch_x3p3.npz"), **stitch_fixture(50, 31, 3.3, 12, 2, 3, 2))

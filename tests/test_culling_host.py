@@ -76,6 +76,33 @@ def test_default_ksigma_error_budget(cfg, dmax):
     assert np.abs(img - ref).max() < 1e-5
 
 
+@pytest.mark.parametrize("h,w,dmax,ksigma", [(40, 72, 0.2, float("inf")), (97, 33, 0.08, float("inf")),
+                                             (64, 64, np.inf, float("inf")), (50, 50, 0.5, float("inf"))])
+def test_cell_masks_exact_mode_reproduces_the_inclusion_set(h, w, dmax, ksigma):
+    """Region-bucket path, ksigma=inf: the cell masks drop nothing the reference sums (values below 2^-126 aside)."""
+    rng = np.random.default_rng(h * w + 1)
+    sig, xy, col = _random_field(rng, 150, 0.01, 0.4)
+    ref = oracle.forward(sig, xy, col, h, w, dmax)
+    img, _ = emulate.emulate_forward_cells(sig, xy, col, h, w, dmax, ksigma)
+    assert np.abs(img - ref).max() < 1e-12
+
+
+@pytest.mark.parametrize("cfg,dmax", [("C1", 0.1), ("C1", 0.05)])
+def test_cell_masks_default_ksigma_error_budget_and_work(cfg, dmax):
+    """Default k-sigma through the cell masks: truncation a decade below the 1e-4 tolerance, and the number of
+    (Gaussian, pixel) pairs the masks leave is well below what whole 16x8 regions would evaluate."""
+    _, s, c, k, h, w = fields.make(cfg)
+    s, c, k = s.numpy(), c.numpy(), k.numpy()
+    ref = oracle.forward(s, c, k, h, w, dmax)
+    img, pairs = emulate.emulate_forward_cells(s, c, k, h, w, dmax, 0.0)
+    assert np.abs(img - ref).max() < 1e-5
+    L = _lib.load()
+    out = np.zeros((4096, 3), dtype=np.int32)
+    entries = sum(L.gsr_host_entries(s.ctypes.data, c.ctypes.data, k.ctypes.data, g, h, w, float(dmax), 0.0,
+                                     out.ctypes.data, 4096) for g in range(0, s.shape[0], 8))
+    assert pairs < 0.75 * 128 * entries * 8
+
+
 def test_degenerate_gaussians_are_skipped_or_kept_consistently():
     h, w = 48, 80
     sig = np.array([[0.1, 0.1, 0.0], [0.0, 0.1, 0.0], [0.1, 0.1, 1.0], [np.nan, 0.1, 0.0],

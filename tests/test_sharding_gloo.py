@@ -75,6 +75,36 @@ def test_units_sharded_over_two_ranks(n_units, gather_to):
     assert dict(ret) == {0: True, 1: True}
 
 
+def _subgroup_worker(rank, world, port, n_units, gather_to, ret):
+    """World of 3, the render runs in the subgroup {1, 2}: group-local rank r is global rank r + 1, so a send /
+    recv / broadcast that forgets the translation goes to the wrong peer (or hangs)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sub = dist.new_group([1, 2])  # every rank must take part in the creation
+        ok = True
+        if rank in (1, 2):
+            out = sharding.render_units_sharded(n_units, _unit_image, gather_to=gather_to, group=sub)
+            local = rank - 1
+            if gather_to is None or local == gather_to:
+                ok = out is not None and len(out) == n_units and all(
+                    torch.equal(o, _unit_image(i)) for i, o in enumerate(out))
+            else:
+                ok = out is None
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_units,gather_to", [(5, 0), (4, 1), (3, None)])
+def test_units_sharded_in_a_subgroup_uses_global_ranks(n_units, gather_to):
+    world = 3
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_subgroup_worker, args=(world, _free_port(), n_units, gather_to, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True, 2: True}
+
+
 # ---- one image split into row bands over the ranks (sharding.render_image_bands) ----------------
 def test_band_rows_partition_the_image():
     for h in (2, 3, 8, 9, 16, 17, 25, 100, 2048):
