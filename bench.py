@@ -13,11 +13,19 @@ exchange step, so at N GPUs every rank rasterises its own image of the same shap
 no collective in the timed region); `value` is the whole-job MP/s: N * MP / max-over-ranks time.
 
 A step is one forward pass of the hot path (set-up + raster kernels) with the Gaussian tensors
-and the image resident in HBM.  `e2e` is the same metric through the plugin call a GSASR user
-makes (gscuda.gs_render) from pinned HOST buffers, host<->device copies inside the timed region.
-`roofline` is for the dominant kernel (gsr_forward_region_kernel), timed with CUDA events on the launch
-stream via the split-phase C ABI.  `cpu_baseline` / `--impl reference` time the CPU restatement
-of the reference algorithm (oracle/, OpenMP over all host cores) on a bounded sample.
+and the image resident in HBM.  What the JSON line carries besides the contract's keys:
+
+  e2e            the same metric through the plugin call a GSASR user makes (gscuda.gs_render) from pinned HOST
+                 buffers, host<->device copies inside the timed region; every rank bound to its GPU's NUMA node.
+  roofline       the dominant kernel (gsr_forward_region_kernel), timed with CUDA events on the launch stream via
+                 the split-phase C ABI; `step_breakdown` gives set-up / raster / backward beside it.
+  sustained      the same step looped for >= 1 s: ms per step and the clocks sampled under that load.
+  strong         (N > 1) ONE image over the N GPUs in row bands: all-gather and peer-store forward, backward with
+                 its all-reduce, each against the single-GPU time measured in the same run.
+  cpu_baseline   the CPU restatement of the reference algorithm (oracle/, OpenMP over all host cores) on a bounded
+                 sample; `cpu_reference_python` = the reference's OWN PyTorch-CPU renderer (rendering_python,
+                 unmodified, BASELINE config 1) timed on the same host cores.
+  gpu_reference  the reference's own CUDA kernels (oracle/_ref, rebuilt for sm_100a) on BASELINE config 2, same box.
 """
 from __future__ import annotations
 
@@ -45,6 +53,42 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def host_cores() -> int:
+    """Cores this process may use: the affinity mask if there is one, else the machine's count.  torchrun
+    exports OMP_NUM_THREADS=1, which must not decide how many cores the CPU arms are given."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def bind_to_gpu_numa(local: int):
+    """Pin this rank's threads to the NUMA node its GPU hangs off, BEFORE the pinned host buffers are allocated
+    (first touch places them on that node).  Best effort: returns what was done for the JSON line."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return {"numa_node": None, "note": "no NUMA information for this GPU"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus": len(allowed)}
+    except Exception as exc:
+        return {"numa_node": None, "note": f"not bound: {exc}"}
 
 
 class ClockSampler:
@@ -94,15 +138,14 @@ class CpuPort:
     """The CPU restatement of the reference algorithm (oracle/gs_oracle.c, fp32 mode, dmax window
     semantics, OpenMP over all host cores) on an evenly strided sample of the workload's Gaussians."""
 
-    def __init__(self, cfg_name: str, threads: int | None = None):
+    def __init__(self, cfg_name: str):
         import numpy as np
 
         from gsasr_b200 import fields
         from oracle import oracle
 
         oracle.build()
-        if threads:
-            oracle.set_num_threads(threads)
+        oracle.set_num_threads(host_cores())  # explicitly: torchrun's OMP_NUM_THREADS=1 does not apply to this arm
         self.oracle, self.np, self.name = oracle, np, cfg_name
         self.cores = oracle.num_threads()
         _, s, c, k, self.h, self.w = fields.make(cfg_name, 0)
@@ -139,6 +182,81 @@ def cpu_sample(cfg_name: str, seconds: float = 12.0):
     return port.mps(m, t), port.cores, port.describe(m, t), t
 
 
+def cpu_reference_python():
+    """The reference's OWN CPU path: utils/gaussian_splatting.py rendering_python (cuda_rendering=False), unmodified
+    (staged by oracle/ref_py.py), on BASELINE config 1 (64x64 LR -> x2, 16,384 Gaussians, 128x128), all host cores.
+    A different function of the parameters than the CUDA path: a timing comparator, not a parity one."""
+    try:
+        import torch
+
+        from gsasr_b200 import fields
+        from oracle import ref_py
+
+        if not ref_py.have():
+            return {"unavailable": "oracle/_ref/ref_py not staged (built where /root/reference exists)"}
+        gsp = ref_py.load("utils.gaussian_splatting")
+        cores = host_cores()
+        torch.set_num_threads(cores)
+        cfg = fields.CONFIGS["C1"]
+        raw = fields.raw_field(*cfg.grid, seed=0)
+        h, w = cfg.hr
+        args = dict(sr_size=torch.tensor([h, w]), scale=cfg.scale, scale_modify=torch.tensor([cfg.scale, cfg.scale]),
+                    cuda_rendering=False)
+        ts = []
+        for i in range(4):  # 1 warm-up + 3
+            t0 = time.perf_counter()
+            gsp.generate_2D_gaussian_splatting_step(gs_parameters=raw.clone(), **args)
+            ts.append(time.perf_counter() - t0)
+        t = sorted(ts[1:])[1]
+        return {"value": h * w / 1e6 / t, "unit": UNIT, "seconds_per_call": t, "cores": cores, "kind": "reference",
+                "config": "C1: 64x64 LR -> x2, 16,384 Gaussians, 128x128 (BASELINE configs[0])",
+                "sample": "whole image, median of 3 calls after 1 warm-up, torch CPU threads = cores"}
+    except Exception as exc:
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+
+
+def gpu_reference(dev):
+    """The reference's own CUDA kernels (oracle/_ref/libgsref_dmax.so: gs_cuda_dmax rebuilt for sm_100a, unmodified) on
+    BASELINE config 2 (256x256 LR -> x4, 262,144 Gaussians, 1024x1024), beside this library on the same tensors."""
+    try:
+        import torch
+
+        from gsasr_b200 import fields, gscuda
+        from oracle import oracle
+
+        if not oracle.have_ref():
+            return {"unavailable": "oracle/_ref not built"}
+        _, s, c, k, h, w = fields.make("C2", 0)
+        sd, cd, kd = s.to(dev), c.to(dev), k.to(dev)
+        n = sd.shape[0]
+        R = oracle.RefKernels(True)
+        g = torch.rand(h, w, 3, device=dev)
+
+        def wall(fn, reps):
+            fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / reps * 1e3
+
+        ref_f = wall(lambda: R.forward(sd, cd, kd, torch.zeros(h, w, 3, device=dev), DMAX), 2)
+        ref_b = wall(lambda: R.backward(sd, cd, kd, g, torch.zeros_like(sd), torch.zeros_like(cd), torch.zeros_like(kd), DMAX), 1)
+        img = torch.zeros(h, w, 3, device=dev)
+        ws = gscuda.workspace(n, h, w, dev)
+        gs, gc, gk = torch.zeros_like(sd), torch.zeros_like(cd), torch.zeros_like(kd)
+        our_f = wall(lambda: gscuda.gs_render(sd, cd, kd, img, n, h, w, 3, DMAX, workspace_buf=ws), 50)
+        our_b = wall(lambda: gscuda.gs_render_backward(sd, cd, kd, g, gs, gc, gk, n, h, w, 3, DMAX, workspace_buf=ws), 50)
+        return {"config": "C2: 256x256 LR -> x4, 262,144 Gaussians, 1024x1024, dmax 0.1 (BASELINE configs[1])",
+                "reference_fwd_ms": ref_f, "reference_bwd_ms": ref_b, "ours_fwd_ms": our_f, "ours_bwd_ms": our_b,
+                "reference_fwd_mps": h * w / 1e6 / (ref_f * 1e-3), "ours_fwd_mps": h * w / 1e6 / (our_f * 1e-3),
+                "note": "gscuda-level calls (accumulate contract), wall clock around synchronised calls; the reference "
+                        "walks the exact dmax window, this library also culls at k = 5 sigma"}
+    except Exception as exc:
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+
+
 def run_reference(args, rank):
     """--impl reference: every step renders the same bounded sample; the whole run is sized to ~90 s."""
     if rank != 0:
@@ -161,22 +279,32 @@ def run_reference(args, rank):
         "config": dict(workload_config(args.workload), split=args.split),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": port.cores, "kind": "port",
                          "sample": port.describe(m, t)},
+        "cpu_reference_python": cpu_reference_python(),
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "the reference's own implementation of this path is CUDA-only (gs_cuda_dmax); its CPU arm is the "
-                "oracle port of that algorithm on the host cores; a step renders the bounded sample described in "
-                "cpu_baseline.sample and value extrapolates it to the whole image",
+        "note": "the reference's own implementation of this path at this shape is CUDA-only (gs_cuda_dmax); its CPU arm "
+                "is the oracle port of that algorithm on the host cores (all of them, whatever OMP_NUM_THREADS says); a "
+                "step renders the bounded sample described in cpu_baseline.sample and value extrapolates it to the "
+                "whole image.  cpu_reference_python times the reference's PyTorch-CPU renderer on the one config it "
+                "can hold in memory (BASELINE configs[0])",
     }
     print(json.dumps(out), flush=True)
 
 
 def workload_config(name):
-    from gsasr_b200 import fields
+    from gsasr_b200 import _lib, fields
     cfg = fields.CONFIGS[name]
     h, w = cfg.hr
+    try:
+        ws_mb = _lib.load().gsr_workspace_bytes(cfg.n, h, w) / 1e6
+    except Exception:
+        ws_mb = float("nan")
     return {"workload": name, "lr": [cfg.lr_h, cfg.lr_w], "scale": cfg.scale, "hr": [h, w],
             "gaussians": cfg.n, "dmax": DMAX, "sigma": "model-like: 0.99999*sigmoid(N(0,1))+1e-6",
             "ksigma": "library default (5)",
-            "l2": "per-step working set (params 67 MB + image 101 MB + workspace 564 MB) exceeds the 126 MB L2"}
+            "image_mode": "value: GSR_FLAG_OVERWRITE (one plain store per pixel, what the front-end mirror uses); "
+                          "`accumulate` and `e2e` use the reference's accumulate-into-rendered_img contract",
+            "l2": f"per-step working set (params {32 * cfg.n / 1e6:.0f} MB + image {12 * h * w / 1e6:.0f} MB + workspace "
+                  f"{ws_mb:.0f} MB) exceeds the 126 MB L2"}
 
 
 def main():
@@ -187,6 +315,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="HL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip gpu_reference / strong / sustained (quick runs)")
     ap.add_argument("--compact", action="store_true",
                     help="compact-sigma field (sigma_px ~ 0.6 instead of the model-like 1.67): few pixels per "
                          "Gaussian, the regime where the raster approaches its HBM roofline (SURVEY 8d)")
@@ -202,6 +331,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
+
+    numa = bind_to_gpu_numa(local) if world > 1 or os.environ.get("GSR_BIND_NUMA") else {"numa_node": None, "note": "single rank: not bound"}
 
     import torch
     import torch.distributed as dist
@@ -248,18 +379,41 @@ def main():
         # bands are gathered on every rank -- strong scaling, the gather is inside the timed region
         sharding.render_image_bands(sd, cd, kd, h, w, DMAX, gather_to=None)
 
+    def fwd(flags):
+        _lib.check(L.gsr_forward(sd.data_ptr(), cd.data_ptr(), kd.data_ptr(), img.data_ptr(), n, h, w, 3,
+                                 DMAX, 0.0, flags, ws.data_ptr(), ws.numel(), sptr))
+
     def step():
         if args.split == "bands-peer" and world > 1:
             return sharding.render_image_bands_peer(sd, cd, kd, h, w, DMAX, gather_to=0)
         if args.split == "bands" and world > 1:
             return step_bands()
-        _lib.check(L.gsr_forward(sd.data_ptr(), cd.data_ptr(), kd.data_ptr(), img.data_ptr(), n, h, w, 3,
-                                 DMAX, 0.0, _lib.GSR_FLAG_OVERWRITE, ws.data_ptr(), ws.numel(), sptr))
+        fwd(_lib.GSR_FLAG_OVERWRITE)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def maxr(v):
+        if world > 1:
+            t = torch.tensor([v], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return v
+
+    def timed(fn, reps, warm=3):
+        """Device time of `reps` back-to-back calls (CUDA events on the launch stream), ms per call."""
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -278,27 +432,53 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    ms_total = maxr(ms_total)
     ms_step = ms_total / args.steps
-    strong = args.split in ("bands", "bands-peer") and world > 1
-    value = (1 if strong else world) * mp_img / (ms_step * 1e-3)
+    strong_main = args.split in ("bands", "bands-peer") and world > 1
+    value = (1 if strong_main else world) * mp_img / (ms_step * 1e-3)
+
+    # ---- the same step for >= 1 s: the clocks under sustained load (the K-step region above lasts milliseconds)
+    sustained = None
+    if not args.no_extras:
+        reps = max(args.steps, int(1200.0 / max(ms_step, 1e-3)))
+        s2 = ClockSampler(local)
+        if rank == 0:
+            s2.start()
+        barrier()
+        e0.record()
+        for _ in range(reps):
+            step()
+        e1.record()
+        barrier()
+        sus_ms = maxr(e0.elapsed_time(e1)) / reps
+        sustained = {"steps": reps, "ms_per_step": sus_ms,
+                     "value": (1 if strong_main else world) * mp_img / (sus_ms * 1e-3), "unit": UNIT,
+                     "clocks": s2.stop() if rank == 0 else None}
+
+    # ---- the reference's contract: accumulate into the caller's image (RED instead of plain stores)
+    acc_ms = maxr(timed(lambda: fwd(0), min(args.steps, 50)))
 
     # ---- dominant kernel, timed alone with events through the split-phase ABI ----
-    kern_ms = []
-    for _ in range(min(args.steps, 30)):
+    def prepare():
         _lib.check(L.gsr_prepare(sd.data_ptr(), cd.data_ptr(), kd.data_ptr(), n, h, w, DMAX, 0.0, ws.data_ptr(),
                                  ws.numel(), sptr))
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+
+    def raster():
         _lib.check(L.gsr_forward_prepared(img.data_ptr(), n, h, w, 0.0, _lib.GSR_FLAG_OVERWRITE, ws.data_ptr(),
                                           ws.numel(), sptr))
-        b.record()
-        torch.cuda.synchronize()
-        kern_ms.append(a.elapsed_time(b))
-    kern_ms = sum(kern_ms) / len(kern_ms)
+
+    prepare()
+    kern_ms = timed(raster, min(args.steps, 30))
+    prep_ms = timed(prepare, min(args.steps, 30))  # region build + the home-bin sort the backward needs
+    grd = torch.rand(h, w, 3, device=dev)
+    gs_, gc_, gk_ = torch.zeros_like(sd), torch.zeros_like(cd), torch.zeros_like(kd)
+
+    def bwd():
+        _lib.check(L.gsr_backward(sd.data_ptr(), cd.data_ptr(), kd.data_ptr(), grd.data_ptr(), gs_.data_ptr(),
+                                  gc_.data_ptr(), gk_.data_ptr(), n, h, w, 3, DMAX, 0.0, 0, ws.data_ptr(), ws.numel(),
+                                  sptr))
+
+    bwd_ms = timed(bwd, min(args.steps, 20))
     alg_bytes = 32 * n + 12 * h * w
     peak, peak_src = peaks()
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
@@ -320,19 +500,18 @@ def main():
             gscuda.gs_render(a, b, cc, o, n, h, w, 3, DMAX)
             outs_h[i % NSTREAM].copy_(o, non_blocking=True)
 
-    for i in range(4):
-        e2e_step(i)
-    barrier()
-    ksteps = max(6, min(args.steps, 40))
-    t0 = time.perf_counter()
-    for i in range(ksteps):
-        e2e_step(i)
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / ksteps
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    def e2e_loop(fn):
+        for i in range(4):
+            fn(i)
+        barrier()
+        ksteps = max(6, min(args.steps, 40))
+        t0 = time.perf_counter()
+        for i in range(ksteps):
+            fn(i)
+        barrier()
+        return maxr((time.perf_counter() - t0) * 1e3 / ksteps)
+
+    e2e_ms = e2e_loop(e2e_step)
     e2e_value = world * mp_img / (e2e_ms * 1e-3)
 
     # ---- the same end-to-end loop with the post-processing of inference_paper.py:136-138 fused into the
@@ -348,50 +527,121 @@ def main():
             gscuda.gs_render_u8(a, b, cc, o, n, h, w, DMAX, bgr=True)
             outs_u8[i % NSTREAM].copy_(o, non_blocking=True)
 
-    for i in range(4):
-        e2e_u8_step(i)
+    e2e_u8_ms = e2e_loop(e2e_u8_step)
+
+    # ---- host<->device link of this rank, alone and with all ranks copying at once (what limits e2e scaling)
+    def copy_gbs():
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            s_h.to(dev, non_blocking=True), c_h.to(dev, non_blocking=True), k_h.to(dev, non_blocking=True)
+        torch.cuda.synchronize()
+        up = 5 * 32 * n / (time.perf_counter() - t0) / 1e9
+        t0 = time.perf_counter()
+        for _ in range(5):
+            outs_h[0].copy_(img, non_blocking=True)
+        torch.cuda.synchronize()
+        return up, 5 * 12 * h * w / (time.perf_counter() - t0) / 1e9
+
     barrier()
-    t0 = time.perf_counter()
-    for i in range(ksteps):
-        e2e_u8_step(i)
-    barrier()
-    e2e_u8_ms = (time.perf_counter() - t0) * 1e3 / ksteps
+    h2d_gbs, d2h_gbs = copy_gbs()
     if world > 1:
-        t = torch.tensor([e2e_u8_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_u8_ms = float(t.item())
+        t = torch.tensor([h2d_gbs, d2h_gbs], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        h2d_gbs, d2h_gbs = float(t[0]), float(t[1])
+
+    # ---- strong scaling: ONE image over the N GPUs in row bands ----
+    strong = None
+    if world > 1 and not args.no_extras:
+        _, s0, c0, k0, _, _ = fields.make(cfg, seed=0)  # the same field on every rank
+        s0, c0, k0 = s0.to(dev), c0.to(dev), k0.to(dev)
+        g0 = torch.rand(h, w, 3, device=dev, generator=torch.Generator(dev).manual_seed(7))
+
+        def coll(fn, reps=20):
+            for _ in range(3):
+                fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            barrier()
+            return maxr((time.perf_counter() - t0) * 1e3 / reps)
+
+        one_f = maxr(timed(lambda: gscuda.gs_render(s0, c0, k0, img, n, h, w, 3, DMAX, flags=1, workspace_buf=ws), 20))
+        gsz = [torch.zeros_like(s0), torch.zeros_like(c0), torch.zeros_like(k0)]
+        one_b = maxr(timed(lambda: gscuda.gs_render_backward(s0, c0, k0, g0, *gsz, n, h, w, 3, DMAX, workspace_buf=ws), 10))
+        ag = coll(lambda: sharding.render_image_bands(s0, c0, k0, h, w, DMAX, gather_to=None))
+        try:
+            pr = coll(lambda: sharding.render_image_bands_peer(s0, c0, k0, h, w, DMAX, gather_to=0))
+        except Exception as exc:  # symmetric memory unavailable: report, do not fail the bench
+            pr = None
+            peer_note = f"{type(exc).__name__}: {exc}"
+        bb = coll(lambda: sharding.backward_image_bands(s0, c0, k0, g0, h, w, DMAX), 10)
+        strong = {
+            "what": f"ONE {h}x{w} image ({n} Gaussians) split into {world} row bands; wall clock per call incl. the "
+                    "collective and the stream synchronisation, max over ranks",
+            "single_gpu_fwd_ms": one_f, "single_gpu_bwd_ms": one_b,
+            "bands_allgather_fwd_ms": ag, "bands_allgather_mps": mp_img / (ag * 1e-3),
+            "bands_allgather_efficiency": one_f / (world * ag),
+            "bands_peer_fwd_ms": pr, "bands_peer_mps": (mp_img / (pr * 1e-3)) if pr else None,
+            "bands_peer_efficiency": (one_f / (world * pr)) if pr else None,
+            "bands_bwd_allreduce_ms": bb, "bands_bwd_efficiency": one_b / (world * bb),
+            "collectives": {"forward_allgather_bytes_per_rank": 12 * h * w // world,
+                            "forward_peer_store_bytes_per_rank": 12 * h * w // world,
+                            "backward_allreduce_bytes": 32 * n},
+        }
+        if pr is None:
+            strong["bands_peer_note"] = peer_note
 
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(workload_config(args.workload), split=args.split,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong" if strong_main else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(args.workload), split=args.split,
                            **({"sigma": "compact: 0.99999*sigmoid(N(-1.5,0.5^2))+1e-6"} if args.compact else {})),
             "clocks": clocks, "gpu_launches": KERNELS_PER_STEP * args.steps,
+            "accumulate": {"ms_per_step": acc_ms, "value": world * mp_img / (acc_ms * 1e-3), "unit": UNIT,
+                           "note": "gsr_forward with flags = 0: the reference's accumulate-into-rendered_img contract "
+                                   "(vector RED per pixel pair instead of plain stores)"},
+            "sustained": sustained,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 12 * h * w,
+                    "h2d_gbs_per_rank_min": h2d_gbs, "d2h_gbs_per_rank_min": d2h_gbs, "numa": numa,
                     "note": f"gscuda.gs_render from pinned host tensors, steps rotate over {NSTREAM} CUDA streams"},
             "e2e_u8": {"value": world * mp_img / (e2e_u8_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_u8_ms,
                        "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 3 * h * w,
-                       "note": "extra: gscuda.gs_render_u8 (fused clamp/x255/round/uint8 post-processing of "
-                               "inference_paper.py:136-138), uint8 HWC image copied back"},
+                       "note": "the inference pipeline's e2e: gscuda.gs_render_u8 (fused clamp/x255/round/uint8 "
+                               "post-processing of inference_paper.py:136-138), uint8 HWC image copied back"},
             "roofline": {"bound": "hbm", "kernel": "gsr_forward_region_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes": alg_bytes, "kernel_ms": kern_ms,
                          "kernel_share_of_step": kern_ms / ms_step, "traffic": None if args.compact else TRAFFIC.get(args.workload),
+                         "step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak,
                          "note": "the kernel is bound by the MUFU.EX2 / FP32 issue pipes, not by HBM: see DESIGN.md"},
+            "step_breakdown": {"raster_ms": kern_ms, "prepare_ms": prep_ms, "forward_step_ms": ms_step,
+                               "backward_call_ms": bwd_ms,
+                               "note": "prepare = region build + home-bin sort (gsr_prepare); backward_call = set-up + "
+                                       "gsr_backward_kernel, B_bwd = 64 N + 12 H W bytes",
+                               "backward_frac": (64 * n + 12 * h * w) / (bwd_ms * 1e-3) / 1e9 / peak},
         }
+        if strong is not None:
+            out["strong"] = strong
+        if world == 1 and not args.no_extras:
+            out["gpu_reference"] = gpu_reference(dev)
         if not args.no_cpu_baseline and world == 1:
             mps, cores, sample, _ = cpu_sample(args.workload)
             out["cpu_baseline"] = {"value": mps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            out["cpu_reference_python"] = cpu_reference_python()
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of gsr_forward_kernel per launch, from the
+# dram__bytes_read.sum + dram__bytes_write.sum of gsr_forward_region_kernel per launch, from the
 # `ncu --set full` capture summarised under profiles/ (bytes); None where not captured.
-TRAFFIC = {"HL": 216.8e6}  # profiles/r01_fwd_halfwarp_HL_ncu_full.txt: 150.0 MB read + 66.8 MB written
+TRAFFIC = {"HL": 277.1e6}  # profiles/r02_fwd_cells_HL_ncu_full.txt: 214.0 MB read + 63.1 MB written
 
 if __name__ == "__main__":
     main()

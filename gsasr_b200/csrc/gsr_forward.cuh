@@ -739,6 +739,17 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
       const size_t plane = (size_t)p.h * p.w;
 #pragma unroll
       for (int yy = 0; yy < 2; ++yy) {
+        if (!WINDOW && !over && !chw && !u8 && (p.w & 1) == 0) {
+          // accumulate into an (h,w,3) image of even width: the lane's two pixels of this row are six contiguous
+          // floats at an 8-byte aligned address (wi0 is even) -- three vector reductions instead of six scalar ones
+          if (hi0 + yy < p.h && wi0 < p.w) {  // (w even, wi0 even: both pixels of the pair are inside)
+            float* o = p.img + ((size_t)(hi0 + yy) * p.w + wi0) * 3;
+            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(o), "f"(v[yy][0][0]), "f"(v[yy][0][1]) : "memory");
+            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(o + 2), "f"(v[yy][0][2]), "f"(v[yy][1][0]) : "memory");
+            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(o + 4), "f"(v[yy][1][1]), "f"(v[yy][1][2]) : "memory");
+          }
+          continue;
+        }
 #pragma unroll
         for (int xx = 0; xx < 2; ++xx) {
           const int hi = hi0 + yy, wi = wi0 + xx;

@@ -516,14 +516,27 @@ gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restric
         mc[0] = x, mc[1] = y;
         mk[0] = cr, mk[1] = cg, mk[2] = cb;
       } else {
-        sx = __ldg(sigmas + 3 * (size_t)i + 0);
         sy = __ldg(sigmas + 3 * (size_t)i + 1);
-        rho = __ldg(sigmas + 3 * (size_t)i + 2);
-        x = __ldg(coords + 2 * (size_t)i + 0);
         y = __ldg(coords + 2 * (size_t)i + 1);
-        cr = __ldg(colors + 3 * (size_t)i + 0);
-        cg = __ldg(colors + 3 * (size_t)i + 1);
-        cb = __ldg(colors + 3 * (size_t)i + 2);
+        sx = rho = x = cr = cg = cb = 0.f;
+        // row-band view (one image split over several GPUs): a Gaussian whose k-sigma rows miss the band by more
+        // than a pixel is dropped after these two loads -- the set-up cost of a band is its share of the image's
+        bool reach = true;
+        if (ws.hf > 0) {
+          const float hyf = 0.5f * (float)(ws.hf - 1);
+          const float cyf = (y + 1.0f) * hyf, eyf = ksigma * fabsf(sy) * hyf + 1.0f;
+          reach = !(cyf + eyf < (float)ws.row0 - 1.0f || cyf - eyf > (float)(ws.row0 + h));
+        }
+        if (reach) {
+          sx = __ldg(sigmas + 3 * (size_t)i + 0);
+          rho = __ldg(sigmas + 3 * (size_t)i + 2);
+          x = __ldg(coords + 2 * (size_t)i + 0);
+          cr = __ldg(colors + 3 * (size_t)i + 0);
+          cg = __ldg(colors + 3 * (size_t)i + 1);
+          cb = __ldg(colors + 3 * (size_t)i + 2);
+        } else {
+          sy = 0.f;  // sigma = 0: gsr_setup returns "not live" at its first test
+        }
       }
       st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, hl, wl, sv.dmax, ksigma, sv.px_tab, sv.py_tab, ws.hf, ws.row0);
       if (st.live) {

@@ -135,11 +135,11 @@ def _band_forward_cuda(sigmas, coords, colors, h, w, row0, rows, dmax):
 _SYMM_IMAGES = {}
 
 
-def _peer_image(numel: int, device, root: int, group):
+def _peer_image(numel: int, device, root: int, group, slot: int = 0):
     """Symmetric-memory image buffer: (this rank's buffer, view of `root`'s buffer, handle); cached."""
     import torch.distributed._symmetric_memory as symm_mem
 
-    key = (numel, str(device), id(group))
+    key = (numel, str(device), id(group), slot)
     if key not in _SYMM_IMAGES:
         buf = symm_mem.empty(numel, dtype=torch.float32, device=device)
         _SYMM_IMAGES[key] = (buf, symm_mem.rendezvous(buf, group=group if group is not None else dist.group.WORLD))
@@ -147,30 +147,36 @@ def _peer_image(numel: int, device, root: int, group):
     return buf, hdl.get_buffer(root, (numel,), torch.float32), hdl
 
 
+_PEER_CALLS = {}
+
+
 def render_image_bands_peer(sigmas, coords, colors, h: int, w: int, dmax: float, *, gather_to: int = 0,
                             group=None):
     """render_image_bands with the gather folded into the raster kernel: the (h,w,3) image lives in
     symmetric memory on `gather_to` and every rank's band kernel stores its rows straight into it over
     NVLink (peer writes) -- no collective, the transfer overlaps the raster.  Returns a view of the
-    symmetric buffer on `gather_to` (valid until the next call: a call first drains every rank's current stream
-    and meets at a barrier, so work already queued on the returned view completes before it is overwritten),
-    None elsewhere.  CUDA + NCCL only."""
+    symmetric buffer on `gather_to`, None elsewhere.  CUDA + NCCL only.
+
+    Lifetime of the returned view: calls alternate between TWO symmetric images, and every call ends with all
+    ranks draining their current stream and meeting at a barrier.  The image of call k is therefore overwritten
+    no earlier than call k+2, i.e. after the exit barrier of call k+1 -- by which time everything the stitching
+    rank queued on its current stream up to that barrier (the readers of image k) has completed.  Work queued on
+    OTHER streams must be ordered by the caller; a caller that keeps the image longer clones it."""
     from . import gscuda
 
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return _band_forward_cuda(sigmas, coords, colors, h, w, 0, h, dmax)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    mine, target, hdl = _peer_image(h * w * 3, sigmas.device, gather_to, group)
+    key = (h * w * 3, str(sigmas.device), id(group))
+    slot = _PEER_CALLS.get(key, 0)
+    _PEER_CALLS[key] = slot ^ 1
+    mine, target, hdl = _peer_image(h * w * 3, sigmas.device, gather_to, group, slot)
     row0, rows = band_rows(h, rank, world)
-    # The buffer is reused from call to call: no rank may store into it while the stitching rank's stream
-    # still reads the image the previous call returned.  Everybody waits for everybody's queued work first.
-    torch.cuda.current_stream().synchronize()
-    hdl.barrier()
     if rows > 0:
         band = target.view(h, w, 3)[row0:row0 + rows]  # contiguous rows of the stitching rank's image
         gscuda.gs_render_band(sigmas, coords, colors, band, sigmas.shape[0], h, w, 3, row0, rows, dmax, flags=1)
     torch.cuda.current_stream().synchronize()
-    hdl.barrier()  # every rank's stores have landed
+    hdl.barrier()  # every rank's stores have landed (and every rank's earlier work on this stream is done)
     return mine.view(h, w, 3) if rank == gather_to else None
 
 

@@ -49,8 +49,8 @@ def test_workspace_bytes():
     assert L.gsr_workspace_bytes(0, 64, 64) > 0
     for bad in ((-1, 64, 64), (10, 1, 64), (10, 64, 1), (10, 40000, 64), (10, 64, 40000)):
         assert L.gsr_workspace_bytes(*bad) == 0
-    # bounded by sizes alone: ~260 B per Gaussian (records, boxes, 40 bucket slots) + ~140 B per 8x8 region
-    assert L.gsr_workspace_bytes(2097152, 2048, 4096) < 600 * 2**20
+    # bounded by sizes alone: ~215 B per Gaussian (records, boxes, 28 bucket slots) + ~140 B per 16x8 region
+    assert L.gsr_workspace_bytes(2097152, 2048, 4096) < 450 * 2**20
 
 
 def test_argument_validation_without_gpu():
@@ -105,14 +105,19 @@ def test_top_level_gscuda_module_has_reference_surface():
     assert callable(gscuda.gs_render) and callable(gscuda.gs_render_backward)
 
 
-def test_frontend_rejects_python_renderer():
-    import torch
-
-    from gsasr_b200.gaussian_splatting import generate_2D_gaussian_splatting_step
-
-    with pytest.raises(NotImplementedError):
-        generate_2D_gaussian_splatting_step(torch.tensor([8, 8]), torch.zeros(4, 9), 2.0,
-                                            torch.tensor([2.0, 2.0]), cuda_rendering=False)
+def test_padded_batch_with_no_gaussians_is_validated_not_divided():
+    """s_per == 0 used to reach `s / s_per` (SIGFPE): the sample count now travels explicitly.  Without a
+    GPU the call must come back with an error CODE (the first CUDA call fails), not kill the process."""
+    L = _lib.load()
+    fake, ws = ctypes.c_void_p(256), ctypes.c_void_p(4096)
+    hw = (ctypes.c_int * 4)(64, 64, 40, 48)
+    need = L.gsr_workspace_bytes_batch_padded(2, 0, 64, 64)
+    assert need > 0
+    rc = L.gsr_forward_batch_padded(None, None, None, fake, 2, 0, 64, 64, hw, None, 0.1, 0.0, 0, ws, need, None)
+    assert rc in (0, 6)   # GSR_OK on a GPU box, GSR_ERR_CUDA here
+    rc = L.gsr_backward_batch_padded(None, None, None, fake, None, None, None, 2, 0, 64, 64, hw, None, 0.1, 0.0, 0,
+                                     ws, need, None)
+    assert rc in (0, 6)
 
 
 def test_argument_validation_of_the_band_batch_window_entry_points():

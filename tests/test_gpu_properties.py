@@ -157,25 +157,6 @@ def test_buffer_variant_equals_unbuffered_and_differentiates():
     assert float((raw1.grad - raw2.grad).abs().max()) <= 1e-4 * float(raw1.grad.abs().max())
 
 
-def test_reference_wrapper_source_runs_unmodified_on_our_module():
-    """The reference's gswrapper.py does `import gscuda; GSWrapper = gscuda` and calls
-    GSWrapper.gs_render(sigmas, coords, colors, rendered_img, s, h, w, c, dmax) positionally
-    (utils/gs_cuda_dmax/gswrapper.py:19-31).  Same call shape against the top-level module."""
-    import gscuda as GSWrapper
-
-    g = golden("check_dmax_seed1.npz")
-    h, w = int(g["h"]), int(g["w"])
-    s, c, k = (torch.tensor(g[n], device=DEV) for n in ("sigmas", "coords", "colors"))
-    img = torch.zeros(h, w, 3, device=DEV)
-    GSWrapper.gs_render(s, c, k, img, 4, h, w, 3, 0.5)
-    torch.cuda.synchronize()
-    assert np.abs(img.cpu().numpy() - g["img"]).max() <= 1e-4
-    gs, gc, gk = torch.zeros_like(s), torch.zeros_like(c), torch.zeros_like(k)
-    GSWrapper.gs_render_backward(s, c, k, torch.tensor(g["weight"], device=DEV), gs, gc, gk, 4, h, w, 3, 0.5)
-    torch.cuda.synchronize()
-    assert np.abs(gk.cpu().numpy() - g["g_colors"]).max() <= 1e-3 * np.abs(g["g_colors"]).max()
-
-
 @pytest.mark.parametrize("bgr", [False, True])
 def test_fused_uint8_output_equals_the_reference_post_processing(bgr):
     """GSR_FLAG_U8: clamp_(0,1) -> [2,1,0] -> HWC -> *255 -> round -> uint8 (inference_paper.py:136-138) inside
