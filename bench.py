@@ -567,6 +567,11 @@ def main():
             barrier()
             return maxr((time.perf_counter() - t0) * 1e3 / reps)
 
+        def dev_ms(fn, reps=20):
+            """device time per call: CUDA events on the launch stream around `reps` calls, max over ranks"""
+            barrier()
+            return maxr(timed(fn, reps))
+
         one_f = maxr(timed(lambda: gscuda.gs_render(s0, c0, k0, img, n, h, w, 3, DMAX, flags=1, workspace_buf=ws), 20))
         gsz = [torch.zeros_like(s0), torch.zeros_like(c0), torch.zeros_like(k0)]
         one_b = maxr(timed(lambda: gscuda.gs_render_backward(s0, c0, k0, g0, *gsz, n, h, w, 3, DMAX, workspace_buf=ws), 10))
@@ -577,6 +582,12 @@ def main():
             pr = None
             peer_note = f"{type(exc).__name__}: {exc}"
         bb = coll(lambda: sharding.backward_image_bands(s0, c0, k0, g0, h, w, DMAX), 10)
+        ag_dev = dev_ms(lambda: sharding.render_image_bands(s0, c0, k0, h, w, DMAX, gather_to=None))
+        pr_dev = dev_ms(lambda: sharding.render_image_bands_peer(s0, c0, k0, h, w, DMAX, gather_to=0)) if pr else None
+        bb_dev = dev_ms(lambda: sharding.backward_image_bands(s0, c0, k0, g0, h, w, DMAX), 10)
+        r0_, rows_ = sharding.band_rows(h, rank, world)
+        band_img = torch.zeros(rows_, w, 3, device=dev)
+        band_only = dev_ms(lambda: gscuda.gs_render_band(s0, c0, k0, band_img, n, h, w, 3, r0_, rows_, DMAX, flags=1))
         strong = {
             "what": f"ONE {h}x{w} image ({n} Gaussians) split into {world} row bands; wall clock per call incl. the "
                     "collective and the stream synchronisation, max over ranks",
@@ -586,6 +597,14 @@ def main():
             "bands_peer_fwd_ms": pr, "bands_peer_mps": (mp_img / (pr * 1e-3)) if pr else None,
             "bands_peer_efficiency": (one_f / (world * pr)) if pr else None,
             "bands_bwd_allreduce_ms": bb, "bands_bwd_efficiency": one_b / (world * bb),
+            "device_time_ms": {"band_kernels_only": band_only, "bands_allgather": ag_dev, "bands_peer": pr_dev,
+                               "bands_bwd_allreduce": bb_dev,
+                               "note": "CUDA-event time on the launch stream (max over ranks): what the GPUs need; the "
+                                       "wall-clock figures above add the host's launch path of a sub-millisecond call"},
+            "device_efficiency": {"band_kernels_only": one_f / (world * band_only),
+                                  "bands_allgather": one_f / (world * ag_dev),
+                                  "bands_peer": (one_f / (world * pr_dev)) if pr_dev else None,
+                                  "bands_bwd_allreduce": one_b / (world * bb_dev)},
             "collectives": {"forward_allgather_bytes_per_rank": 12 * h * w // world,
                             "forward_peer_store_bytes_per_rank": 12 * h * w // world,
                             "backward_allreduce_bytes": 32 * n},

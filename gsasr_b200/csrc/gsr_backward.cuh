@@ -43,12 +43,17 @@ constexpr int GSR_BWD_LARGE_CHUNK = 64;                // large-list Gaussians p
 static_assert(GSR_BWD_RS >= GSR_BWD_RW + GSR_BWD_PAD_X, "padded patch reads");
 static_assert(GSR_BWD_TILE % GSR_BIN == 0, "super tile is made of whole bins");
 
-constexpr int GSR_BWD_BATCH = GSR_CFG_BWD_BATCH;  // Gaussians a warp reduces before one lane-parallel chain rule
+constexpr int GSR_BWD_BATCH = GSR_CFG_BWD_BATCH;
+#ifndef GSR_CFG_BWD_ELLIPSE_MIN_W
+#define GSR_CFG_BWD_ELLIPSE_MIN_W 25
+#endif
+constexpr int GSR_BWD_ELLIPSE_MIN_W = GSR_CFG_BWD_ELLIPSE_MIN_W;  // Gaussians a warp reduces before one lane-parallel chain rule
 
 struct GsrBwdSmem {
   float4 win[GSR_BWD_WIN];                     // {g_r, g_g, g_b, -}: one LDS.128 per pixel, a quarter-warp reads 128 contiguous bytes
   float px[GSR_BWD_RW + GSR_BWD_PAD_X];
   float py[GSR_BWD_RW + GSR_BWD_PAD_Y + 1];
+  float4 zero4;                                // what lanes past a box read instead of a neighbour's gradients
   int gidx[GSR_BWD_GCAP];                      // sorted index of the tile's Gaussians (current pass)
   float tot[GSR_BWD_WARPS][GSR_BWD_BATCH][8];  // reduced sums of the current batch
   int tot_gi[GSR_BWD_WARPS][GSR_BWD_BATCH];    // sorted index of the Gaussians of the batch
@@ -72,7 +77,18 @@ struct GsrBwdArgs {
   uint32_t flags;
   const GsrBDesc* bdesc;  // padded batch (ragged != 0): records and moments are in canvas coordinates
   int bn, ragged;
+  int hf, row0, bhs;      // row-band view / rows per sample of a stacked batch (see gsr_setup, gsr_region_mask)
 };
+
+// The k-sigma ellipse of a sorted record in the pixel units of the image the kernel sweeps (band-local rows; the
+// sample's block of rows of a stacked batch), and the cut-off of the set-up that made the boxes.
+__device__ __forceinline__ GsrEllipse gsr_bwd_ellipse(const GsrBwdArgs& p, const float4& a0, const float4& a1, int by0) {
+  GsrRec r;
+  r.x = a0.x, r.y = a0.y, r.a = a0.z, r.b = a0.w, r.c = a1.x, r.r = r.g = r.bl = 0.f;
+  GsrEllipse e = gsr_ellipse(r, p.bhs > 0 ? p.bhs : p.h, p.w, p.hf, p.row0);
+  if (p.bhs > 0) e.cy += (float)((by0 / p.bhs) * p.bhs);
+  return e;
+}
 
 __device__ __forceinline__ float gsr_warp_sum(float v) {
 #pragma unroll
@@ -118,10 +134,10 @@ __device__ __forceinline__ float gsr_lds32(uint32_t addr) {
   return v;
 }
 
-__device__ __forceinline__ void gsr_bwd_sweep_smem(GsrBwdAcc& acc, uint32_t win_s, uint32_t px_s,
+__device__ __forceinline__ void gsr_bwd_sweep_smem_box(GsrBwdAcc& acc, uint32_t win_s, uint32_t px_s,
                                                    uint32_t py_s, const float4& a0, const float4& a1,
                                                    int bx0, int bx1, int by0, int by1, int sx0,
-                                                   int sy0, int lx, int ly, float xstep8) {
+                                                   int sy0, int lx, int ly, float xstep8, uint32_t zero_s) {
   // Lanes past the box read zero padding (see the staging code) and contribute v = 0.
   const int nx = (bx1 - bx0 + 8) >> 3;            // 8-pixel steps per row
   const int x0 = bx0 - sx0 + lx, xlast = bx1 - sx0;
@@ -140,8 +156,52 @@ __device__ __forceinline__ void gsr_bwd_sweep_smem(GsrBwdAcc& acc, uint32_t win_
     int xi = x0;
     for (int k = 0; k < nx; ++k, ad += 128, xi += 8, dx += xstep8) {
       const float e = fmaf(dx, fmaf(a0.z, dx, t1), t0);
-      const float4 g = gsr_lds128(ad);
-      const float v = (yok && xi <= xlast) ? gsr_ex2(e) : 0.f;
+      // lanes past the box read a zero pixel instead of a neighbour's real gradients: an inf / NaN in dL/dimg
+      // outside this Gaussian's box cannot reach its sums as 0 * inf
+      const bool ok = yok && xi <= xlast;
+      const float4 g = gsr_lds128(ok ? ad : zero_s);
+      const float v = ok ? gsr_ex2(e) : 0.f;
+      gsr_bwd_accum(acc, v, g.x, g.y, g.z, dx, dy, a1);
+    }
+  }
+}
+
+// Wide boxes (x8 fields: 5 sigma = 33 px): every 4-row strip of the box is swept only over the columns the
+// Gaussian's k-sigma ellipse reaches in it (gsr_band_xrange, warp-uniform) instead of the box's full width;
+// pixels it skips carry less than exp(-k^2/2), the same truncation the forward applies.  For the 17-pixel boxes
+// of a x4 field the per-strip range costs more than the patches it saves (measured: HL 1.84 ms vs 1.43 ms), so
+// boxes narrower than GSR_BWD_ELLIPSE_MIN_W take the rectangular sweep above.
+__device__ __forceinline__ void gsr_bwd_sweep_smem(GsrBwdAcc& acc, uint32_t win_s, uint32_t px_s,
+                                                   uint32_t py_s, const float4& a0, const float4& a1,
+                                                   int bx0, int bx1, int by0, int by1, int sx0,
+                                                   int sy0, int lx, int ly, float xstep8, const GsrEllipse* el,
+                                                   float ecut, uint32_t zero_s) {
+  // Lanes past the box read zero padding (see the staging code) and contribute v = 0.
+  for (int yb = by0; yb <= by1; yb += 4) {
+    int xa = bx0, xb = bx1;
+    if (el) {
+      const int ye = min(yb + 3, by1);
+      if (!gsr_band_xrange(*el, ecut, yb, ye, bx0, bx1, xa, xb)) continue;
+    }
+    const int y = yb + ly;
+    const int nx = (xb - xa + 8) >> 3;            // 8-pixel steps per row
+    const int x0 = xa - sx0 + lx, xlast = xb - sx0;
+    // dx of this lane's first column; the following columns are 8 pixels further each.  (The forward's
+    // bit-exact pixel table is not needed here: the inclusion set comes from the integer box, and the
+    // gradient tolerance is 1e-3 relative.)
+    const int yc = y - sy0;
+    const bool yok = y <= by1;
+    const float dy = gsr_lds32<0>(py_s + yc * 4) - a0.y;
+    const float t1 = a0.w * dy;
+    const float t0 = a1.x * dy * dy;
+    uint32_t ad = win_s + (uint32_t)(yc * GSR_BWD_RS + x0) * 16u;
+    float dx = gsr_lds32<0>(px_s + x0 * 4) - a0.x;
+    int xi = x0;
+    for (int k = 0; k < nx; ++k, ad += 128, xi += 8, dx += xstep8) {
+      const float e = fmaf(dx, fmaf(a0.z, dx, t1), t0);
+      const bool ok = yok && xi <= xlast;
+      const float4 g = gsr_lds128(ok ? ad : zero_s);  // (see gsr_bwd_sweep_smem_box)
+      const float v = ok ? gsr_ex2(e) : 0.f;
       gsr_bwd_accum(acc, v, g.x, g.y, g.z, dx, dy, a1);
     }
   }
@@ -150,20 +210,26 @@ __device__ __forceinline__ void gsr_bwd_sweep_smem(GsrBwdAcc& acc, uint32_t win_
 // Same sweep with gradients read from global memory (through L1/L2).
 __device__ __forceinline__ void gsr_bwd_sweep_gmem(GsrBwdAcc& acc, const GsrBwdArgs& p,
                                                    const float4& a0, const float4& a1, int bx0,
-                                                   int bx1, int by0, int by1, int lx, int ly) {
+                                                   int bx1, int by0, int by1, int lx, int ly, const GsrEllipse* el,
+                                                   float ecut) {
   const bool chw = (p.flags & 2u) != 0;
   const size_t plane = (size_t)p.h * p.w;
   for (int yb = by0; yb <= by1; yb += 4) {
+    int xa = bx0, xe = bx1;
+    if (el) {
+      const int ye = min(yb + 3, by1);
+      if (!gsr_band_xrange(*el, ecut, yb, ye, bx0, bx1, xa, xe)) continue;
+    }
     const int y = yb + ly;
     const int yc = min(y, by1);
     const bool yok = y <= by1;
     const float dy = __ldg(p.py_tab + yc) - a0.y;
     const float t1 = a0.w * dy;
     const float t0 = a1.x * dy * dy;
-    for (int xb = bx0; xb <= bx1; xb += 8) {
+    for (int xb = xa; xb <= xe; xb += 8) {
       const int x = xb + lx;
-      const int xc = min(x, bx1);
-      const bool ok = yok && x <= bx1;
+      const int xc = min(x, xe);
+      const bool ok = yok && x <= xe;
       const float dx = __ldg(p.px_tab + xc) - a0.x;
       const float e = fmaf(dx, fmaf(a0.z, dx, t1), t0);
       float g0, g1, g2;
@@ -267,6 +333,7 @@ __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwd
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lx = lane & 7, ly = lane >> 3;
   const int ntiles = p.tiles_x * p.tiles_y;
+  const float ecut = gsr_ecut(__int_as_float(__ldg(p.stats + GSR_STAT_KSIGMA)));  // the k of the set-up that made the boxes
 
   if ((int)blockIdx.x >= ntiles) {
     // ---- "large" list: no staging, one chunk per CTA ----
@@ -284,7 +351,8 @@ __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwd
         bool binds;
         gsr_box_unpack(__ldg(p.box + gi), bx0, bx1, by0, by1, binds);
         GsrBwdAcc acc = gsr_bwd_acc_zero();
-        gsr_bwd_sweep_gmem(acc, p, a0, a1, bx0, bx1, by0, by1, lx, ly);
+        const GsrEllipse el = gsr_bwd_ellipse(p, a0, a1, by0);
+        gsr_bwd_sweep_gmem(acc, p, a0, a1, bx0, bx1, by0, by1, lx, ly, &el, ecut);
         gsr_bwd_reduce_store(acc, lane, sm.tot[warp][j]);
         if (lane == 0) sm.tot_gi[warp][j] = gi;
         ++nb;
@@ -351,6 +419,8 @@ __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwd
   }
 
   const uint32_t win_s = gsr_smem_addr(sm.win), px_s = gsr_smem_addr(sm.px), py_s = gsr_smem_addr(sm.py);
+  const uint32_t zero_s = gsr_smem_addr(&sm.zero4);
+  if (tid == 0) sm.zero4 = zero4;
   const float xstep8 = 16.0f / (float)(p.w - 1);  // eight pixels in normalised units
   for (int pass0 = 0; pass0 < ntot; pass0 += GSR_BWD_GCAP) {
     // ---- index the Gaussians of this pass: position in the tile -> sorted index (one lookup each,
@@ -381,10 +451,17 @@ __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwd
         bool binds;
         gsr_box_unpack(__ldg(p.box + gi), bx0, bx1, by0, by1, binds);
         GsrBwdAcc acc = gsr_bwd_acc_zero();
-        if (bx0 >= sx0 && bx1 <= sx1 && by0 >= sy0 && by1 <= sy1)
-          gsr_bwd_sweep_smem(acc, win_s, px_s, py_s, a0, a1, bx0, bx1, by0, by1, sx0, sy0, lx, ly, xstep8);
-        else
-          gsr_bwd_sweep_gmem(acc, p, a0, a1, bx0, bx1, by0, by1, lx, ly);
+        const bool wide = bx1 - bx0 + 1 >= GSR_BWD_ELLIPSE_MIN_W;  // warp-uniform
+        const bool staged = bx0 >= sx0 && bx1 <= sx1 && by0 >= sy0 && by1 <= sy1;
+        if (staged && !wide) {
+          gsr_bwd_sweep_smem_box(acc, win_s, px_s, py_s, a0, a1, bx0, bx1, by0, by1, sx0, sy0, lx, ly, xstep8, zero_s);
+        } else {
+          const GsrEllipse el = gsr_bwd_ellipse(p, a0, a1, by0);
+          if (staged)
+            gsr_bwd_sweep_smem(acc, win_s, px_s, py_s, a0, a1, bx0, bx1, by0, by1, sx0, sy0, lx, ly, xstep8, &el, ecut, zero_s);
+          else
+            gsr_bwd_sweep_gmem(acc, p, a0, a1, bx0, bx1, by0, by1, lx, ly, wide ? &el : nullptr, ecut);
+        }
         gsr_bwd_reduce_store(acc, lane, sm.tot[warp][j]);
         if (lane == 0) sm.tot_gi[warp][j] = gi;
         ++nb;

@@ -44,6 +44,7 @@ constexpr int GSR_STAT_EXT_X = 0, GSR_STAT_EXT_Y = 1, GSR_STAT_OVERFLOW = 2, GSR
 // bucket capacity per region = 28 * N / regions + 32: a Gaussian of the x4 head touches 4.4 of the 16x8
 // regions on average, one of the x8 head 12.3 (5 sigma = 16.7 px on average, 33 px at most); 4 bytes per slot
 constexpr int GSR_ENTRIES_PER_GAUSSIAN = 28;
+constexpr int GSR_STAT_KSIGMA = 6;                   // effective k-sigma of the home-bin set-up (float bits), for the backward
 constexpr int GSR_STAT_UNIT = 4, GSR_STAT_DONE = 5;  // work counter / finished-warp counter of the raster kernel
 
 struct GsrWorkspace {
@@ -236,6 +237,7 @@ gsr_bin_kernel(const float* __restrict__ sigmas, const float* __restrict__ coord
                const float* __restrict__ colors, int s, int h, int w, float dmax, float ksigma,
                GsrWorkspace ws, const int* guard, int want) {
   if (gsr_guard_skip(guard, want)) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) ws.stats[GSR_STAT_KSIGMA] = __float_as_int(ksigma);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s; i += gridDim.x * blockDim.x)
     gsr_bin_one<RAGGED>(sigmas, coords, colors, i, h, w, dmax, ksigma, ws);
 }

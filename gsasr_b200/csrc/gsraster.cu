@@ -297,6 +297,9 @@ static int gsr_launch_backward(const GsrWorkspace& ws, const float* sigmas, cons
   a.bdesc = ws.bdesc;
   a.bn = ws.bn;
   a.ragged = ws.ragged;
+  a.hf = ws.hf;
+  a.row0 = ws.row0;
+  a.bhs = ws.bn > 0 ? ws.bhs : 0;
   const int rcs = gsr_optin_smem(gsr_backward_kernel, (int)sizeof(GsrBwdSmem), 1);
   if (rcs) return rcs;
   const int grid = a.tiles_x * a.tiles_y + (s + GSR_BWD_LARGE_CHUNK - 1) / GSR_BWD_LARGE_CHUNK;

@@ -148,6 +148,7 @@ def _peer_image(numel: int, device, root: int, group, slot: int = 0):
 
 
 _PEER_CALLS = {}
+_PEER_VIEWS = {}
 
 
 def render_image_bands_peer(sigmas, coords, colors, h: int, w: int, dmax: float, *, gather_to: int = 0,
@@ -157,27 +158,36 @@ def render_image_bands_peer(sigmas, coords, colors, h: int, w: int, dmax: float,
     NVLink (peer writes) -- no collective, the transfer overlaps the raster.  Returns a view of the
     symmetric buffer on `gather_to`, None elsewhere.  CUDA + NCCL only.
 
-    Lifetime of the returned view: calls alternate between TWO symmetric images, and every call ends with all
-    ranks draining their current stream and meeting at a barrier.  The image of call k is therefore overwritten
-    no earlier than call k+2, i.e. after the exit barrier of call k+1 -- by which time everything the stitching
-    rank queued on its current stream up to that barrier (the readers of image k) has completed.  Work queued on
+    Lifetime of the returned view: calls alternate between TWO symmetric images, and every call ends with a
+    stream-ordered barrier across the ranks.  The image of call k is therefore overwritten no earlier than call
+    k+2, whose kernels run behind the barrier of call k+1 on every rank -- and that barrier completes only after
+    everything the stitching rank queued on its current stream before it (the readers of image k).  Work queued on
     OTHER streams must be ordered by the caller; a caller that keeps the image longer clones it."""
     from . import gscuda
 
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return _band_forward_cuda(sigmas, coords, colors, h, w, 0, h, dmax)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    key = (h * w * 3, str(sigmas.device), id(group))
+    key = (h, w, str(sigmas.device), id(group), gather_to)
     slot = _PEER_CALLS.get(key, 0)
     _PEER_CALLS[key] = slot ^ 1
-    mine, target, hdl = _peer_image(h * w * 3, sigmas.device, gather_to, group, slot)
-    row0, rows = band_rows(h, rank, world)
+    if (key, slot) not in _PEER_VIEWS:  # peer views, the band slice and the workspace are set up once
+        mine, target, hdl = _peer_image(h * w * 3, sigmas.device, gather_to, group, slot)
+        row0, rows = band_rows(h, rank, world)
+        band = target.view(h, w, 3)[row0:row0 + rows] if rows > 0 else None  # rows of the stitching rank's image
+        ws = gscuda.workspace(sigmas.shape[0], max(rows, 2), w, sigmas.device)
+        _PEER_VIEWS[(key, slot)] = (mine.view(h, w, 3), band, hdl, row0, rows, ws, sigmas.shape[0])
+    mine, band, hdl, row0, rows, ws, n_ws = _PEER_VIEWS[(key, slot)]
+    if n_ws < sigmas.shape[0]:
+        ws = gscuda.workspace(sigmas.shape[0], max(rows, 2), w, sigmas.device)
+        _PEER_VIEWS[(key, slot)] = (mine, band, hdl, row0, rows, ws, sigmas.shape[0])
     if rows > 0:
-        band = target.view(h, w, 3)[row0:row0 + rows]  # contiguous rows of the stitching rank's image
-        gscuda.gs_render_band(sigmas, coords, colors, band, sigmas.shape[0], h, w, 3, row0, rows, dmax, flags=1)
-    torch.cuda.current_stream().synchronize()
-    hdl.barrier()  # every rank's stores have landed (and every rank's earlier work on this stream is done)
-    return mine.view(h, w, 3) if rank == gather_to else None
+        gscuda.gs_render_band(sigmas, coords, colors, band, sigmas.shape[0], h, w, 3, row0, rows, dmax, flags=1,
+                              workspace_buf=ws)
+    # Stream-ordered barrier (a kernel on the current stream that signals every peer and waits for all of them):
+    # behind it, every rank's stores of this call have landed; no host synchronisation, the call returns at once.
+    hdl.barrier()
+    return mine if rank == gather_to else None
 
 
 def render_image_bands(sigmas, coords, colors, h: int, w: int, dmax: float, *, render_band=None,

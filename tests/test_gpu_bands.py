@@ -85,7 +85,9 @@ def test_band_gradients_sum_to_the_whole_image_gradients():
     ref = oracle.backward(s.cpu().numpy(), c.cpu().numpy(), k.cpu().numpy(), g.cpu().numpy(), dmax)
     for a, b, r in zip(acc, want, ref):
         scale = float(b.abs().max())
-        assert float((a - b).abs().max()) <= 1e-5 * scale
+        # wide boxes are swept strip by strip inside the k-sigma ellipse, and the strips of a band start at the
+        # band's first row: the two sweeps drop slightly different sub-exp(-12.5) terms
+        assert float((a - b).abs().max()) <= 1e-4 * scale
         assert np.abs(a.cpu().double().numpy() - r).max() <= 1e-3 * np.abs(r).max()
 
 

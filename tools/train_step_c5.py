@@ -30,6 +30,9 @@ ap.add_argument("--scale", type=float, default=4.0)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--dmax", type=float, default=0.5, help="training YAMLs use 0.5")
 ap.add_argument("--ddp", action="store_true")
+ap.add_argument("--no-checkpoint", action="store_true",
+                help="the head's own activation checkpointing (use_checkpoint, fea2gsropeamp.py:520) is ON by default: "
+                     "4 samples of 16 x 256^2 Gaussians do not fit 180 GB without it")
 ap.add_argument("--depth", default="default", choices=["default", "yaml", "tiny"],
                 help="head depth: class defaults (1x2 cross, 6x6 self), the HATL YAML's (4x4, 8x6), or 1x1/1x1")
 args = ap.parse_args()
@@ -49,7 +52,7 @@ depth = {"default": dict(num_crossattn_blocks=1, num_crossattn_layers=2, num_sel
          "tiny": dict(num_crossattn_blocks=1, num_crossattn_layers=1, num_selfattn_blocks=1, num_selfattn_layers=1)}[args.depth]
 torch.manual_seed(0)
 head = head_mod.Fea2GS_ROPE_AMP(inchannel=64, channel=192, num_heads=6, num_gs_seed=256, window_size=16,
-                                shuffle_scale1=2, shuffle_scale2=2, **depth).to(dev)
+                                shuffle_scale1=2, shuffle_scale2=2, use_checkpoint=not args.no_checkpoint, **depth).to(dev)
 model = torch.nn.parallel.DistributedDataParallel(head, device_ids=[local]) if (args.ddp and world > 1) else head
 opt = torch.optim.Adam(model.parameters(), lr=1e-5)
 B, lr, sc = args.per_gpu, args.lr, args.scale
@@ -94,7 +97,8 @@ def ev(fn, steps):
 
 out = {"config": f"C5: {world} GPU(s) x {B} samples, {lr}x{lr} LR -> x{sc:g} ({H}x{W}), Fea2GS_ROPE_AMP head "
                  f"(window 16, 256 seeds, shuffle 2x2 = 16 Gaussians per LR pixel: {16 * lr * lr} per sample; depth "
-                 f"'{args.depth}' {depth}), bf16 autocast, dmax {args.dmax}, ddp={bool(args.ddp and world > 1)}",
+                 f"'{args.depth}' {depth}, use_checkpoint={not args.no_checkpoint}), bf16 autocast, dmax {args.dmax}, "
+                 f"ddp={bool(args.ddp and world > 1)}",
        "n_gpus": world, "global_batch": world * B}
 with torch.no_grad():
     n_per = int(head_forward().shape[1])
