@@ -424,8 +424,8 @@ __global__ void __launch_bounds__(GSR_FWD_THREADS, GSR_CFG_MIN_CTAS) gsr_forward
 // sample of the bucket's Gaussians -- which arrive sorted by position for a fea2gs field -- and the eight
 // lists of a chunk come out nearly equally long (the loop runs as long as the longest).
 //
-// Warps are persistent and independent (no CTA barrier, nothing shared between warps) and take regions
-// from a global counter (fetched three regions ahead, so the atomic's latency is never waited for).  The
+// Warps are persistent and independent (no CTA barrier, nothing shared between warps) and claim regions
+// from a global counter, two at a time and well ahead of need (one at a time near the end of the image).  The
 // chunk stream is flat over a warp's regions, two-deep: while chunk k is evaluated the records of chunk k+1
 // are in flight as cp.async copies and the entries of chunk k+2 as loads whose values are not touched
 // before the next iteration.  Window-binding Gaussians (entry bit 31) also bring their cull box and are
@@ -542,15 +542,35 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
   // the null record of both stages (slot CH): zero conic and colour, adds exactly 0
   if (lane < 4) sm.rec[warp][lane >> 1][(lane & 1) * GSR_FR_SLOTS + CH] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  // ---- work distribution: units are taken from a global counter, four at a time at first, then one per
-  // finished unit -- requested three units before it is needed.
-  int uA, uB, uC, pend;  // pend: lane 0's counter value, in flight until the next advance
+  // ---- work distribution: units are claimed from a global counter, two at a time while plenty are left (one hot
+  // address serves every warp of the GPU: one atomic per unit made it the kernel's largest single stall) and one
+  // at a time near the end; a claim is requested a whole claim's worth of units before it is needed.
+  // claims of two while at least eight units per warp remain ahead: the tail (and small images) balance unit by unit
+  auto claim_size = [&](int progress) { return progress + 8 * total_warps < nunits ? 2 : 1; };
+  int uA, uB, uC;
+  int qn, qe;              // [qn, qe): units claimed and not yet handed out
+  int pend, pend_n;        // lane 0's counter value of the claim in flight, and its size
   {
+    pend_n = claim_size(3 * total_warps);
     int base = 0;
-    if (lane == 0) base = atomicAdd(p.sched, 4);
+    if (lane == 0) base = atomicAdd(p.sched, 3 + pend_n);
     base = __shfl_sync(full, base, 0);
-    uA = base, uB = base + 1, uC = base + 2, pend = base + 3;
+    uA = base, uB = base + 1, uC = base + 2;
+    qn = qe = base + 3;    // nothing queued: the first refill takes the claim made here
+    pend = base + 3;
   }
+  auto take_unit = [&]() {  // next unit of this warp; refills from the claim in flight and requests another
+    if (qn == qe) {
+      qn = __shfl_sync(full, pend, 0);
+      qe = qn + pend_n;
+      pend_n = claim_size(qn);
+      // lane 0 only, predicated inside the asm (no divergent region): the result is not waited for before the
+      // claim is needed, several units from now
+      asm volatile("{\n\t.reg .pred pl0;\n\tsetp.eq.s32 pl0, %2, 0;\n\t@pl0 atom.global.add.u32 %0, [%1], %3;\n\t}"
+                   : "+r"(pend) : "l"(p.sched), "r"(lane), "r"(pend_n) : "memory");
+    }
+    return qn++;
+  };
   auto finish = [&]() {  // the last warp to leave resets the counters for the next launch
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (lane == 0) {
@@ -642,7 +662,7 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
   };
 
   // Units in flight: A is evaluated, B and C are known far enough ahead for the two-deep prefetch to run
-  // across unit boundaries, `pend` is the counter value still in flight.
+  // across unit boundaries; further units wait in the claimed range [qn, qe) and in the claim in flight.
   int nA = min(count_of(uA), p.reg_cap), nB = min(count_of(uB), p.reg_cap), nC = count_of(uC);
   int nchA = chunks_of(nA), nchB = chunks_of(nB);
 
@@ -781,7 +801,7 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
         }
       }
     }
-    // ---- advance: B becomes A, C becomes B, the pending counter value becomes C, a new one is requested
+    // ---- advance: B becomes A, C becomes B, the next claimed unit becomes C
     uA = uB;
     if (uA >= nunits) break;
     nA = nB;
@@ -789,12 +809,8 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
     uB = uC;
     nB = min(nC, p.reg_cap);  // requested one unit ago
     nchB = chunks_of(nB);
-    uC = __shfl_sync(full, pend, 0);  // requested one unit ago
+    uC = take_unit();
     nC = count_of(uC);
-    // lane 0 only, predicated inside the asm (no divergent region): the result is not waited for before the
-    // next advance reads it
-    asm volatile("{\n\t.reg .pred pl0;\n\tsetp.eq.s32 pl0, %2, 0;\n\t@pl0 atom.global.add.u32 %0, [%1], 1;\n\t}"
-                 : "+r"(pend) : "l"(p.sched), "r"(lane) : "memory");
     ci = 0;
     nx2 = nx2B;
     ny2 = ny2B;

@@ -8,6 +8,12 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "variants")
 VARIANTS = {
     "base": [],
+    "fr5": ["GSR_CFG_FR_MIN_CTAS=5"],
+    "fr7": ["GSR_CFG_FR_MIN_CTAS=7"],
+    "fr8": ["GSR_CFG_FR_MIN_CTAS=8"],
+    "rb12": ["GSR_CFG_RB_MIN_CTAS=12"],
+    "rb128": ["GSR_CFG_RB_THREADS=128", "GSR_CFG_RB_MIN_CTAS=8"],
+    "rb32": ["GSR_CFG_RB_THREADS=32", "GSR_CFG_RB_MIN_CTAS=32"],
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
@@ -24,7 +30,7 @@ else:
     from gsasr_b200 import fields, gscuda, _lib
     L = _lib.load(); dev = torch.device("cuda:0")
     res = {}
-    for cfg in ("HL", "C2d", "C3", "C2"):
+    for cfg in (("HL",) if os.environ.get("GSR_SWEEP_FAST") else ("HL", "C2d", "C3", "C2")):
         _, s, c, k, h, w = fields.make(cfg)
         sd, cd, kd = s.to(dev), c.to(dev), k.to(dev); n = s.shape[0]
         img = torch.zeros(h, w, 3, device=dev); ws = gscuda.workspace(n, h, w, dev)
