@@ -23,6 +23,7 @@ HEADERS = [
     "gsr_common.cuh",
     "gsr_prepass.cuh",
     "gsr_forward.cuh",
+    "gsr_forward_ws.cuh",
     "gsr_backward.cuh",
     "gsr_frontend.cuh",
     os.path.join("..", "..", "include", "gsraster.h"),

@@ -22,7 +22,7 @@
 //   d/drho = -2 w1 (2 w1 rho (w2 Sxx - 2 rho w3 Sxy + w4 Syy) + w3 Sxy)
 //   d/dcol_c = sum v g_c
 #pragma once
-#include "gsr_forward.cuh"
+#include "gsr_forward_ws.cuh"
 
 constexpr int GSR_BWD_THREADS = 512;
 constexpr int GSR_BWD_WARPS = GSR_BWD_THREADS / 32;

@@ -519,6 +519,50 @@ __device__ __forceinline__ void gsr_eval_quad(uint32_t addr0, uint32_t addr1, gs
   b1 = gsr_fma2(vb, cb, b1);
 }
 
+// Per-cell lists of 16-bit shared-memory addresses (the CTA's shared window is < 64 KB) for one staged chunk: every
+// slot starts as the null record's; the rank of an entry in the list of cell q = number of earlier entries that
+// name q, in the order (lane 0: first, second entry), (lane 1: ...).  The eight ranks of an entry come from ONE warp
+// scan: the masks are spread to a byte per cell (two registers), the bytes are prefix-summed across the lanes with
+// shuffles (counts stay below 256: at most 64 entries) -- no popcounts (they share the MUFU pipe).
+// lw: the stage's lists; rb: the stage's records; (v1a, e1a), (v1b, e1b): this lane's two entries.  Returns the
+// length of the list of this lane's cell.  Warp-collective.
+__device__ __forceinline__ int gsr_fr_build_lists(uint32_t lw, uint32_t rb, int lane, int cell, bool v1a, uint32_t e1a,
+                                                  bool v1b, uint32_t e1b) {
+  constexpr int CH = GSR_FR_CHUNK;
+  const unsigned full = 0xffffffffu;
+  const uint32_t null2 = (rb + CH * 16u) * 0x00010001u;
+  gsr_sts128u(lw + lane * 16, null2);
+  gsr_sts128u(lw + 512 + lane * 16, null2);
+  if (lane < 4) gsr_sts128u(lw + 1024 + lane * 16, null2);
+  const uint32_t ma = v1a ? (e1a >> GSR_ENT_MASK_SHIFT) & 0xffu : 0u, mb = v1b ? (e1b >> GSR_ENT_MASK_SHIFT) & 0xffu : 0u;
+  const uint32_t a_lo = ((ma & 15u) * 0x00204081u) & 0x01010101u, a_hi = ((ma >> 4) * 0x00204081u) & 0x01010101u;
+  const uint32_t b_lo = ((mb & 15u) * 0x00204081u) & 0x01010101u, b_hi = ((mb >> 4) * 0x00204081u) & 0x01010101u;
+  uint32_t s_lo = a_lo + b_lo, s_hi = a_hi + b_hi;  // inclusive prefix sums, a byte per cell
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t0 = __shfl_up_sync(full, s_lo, d), t1 = __shfl_up_sync(full, s_hi, d);
+    if (lane >= d) {
+      s_lo += t0;
+      s_hi += t1;
+    }
+  }
+  const uint32_t t_lo = __shfl_sync(full, s_lo, 31), t_hi = __shfl_sync(full, s_hi, 31);
+  const uint32_t ra_lo = s_lo - a_lo - b_lo, ra_hi = s_hi - a_hi - b_hi;  // exclusive: rank of the first entry
+  const uint32_t rb_lo = ra_lo + a_lo, rb_hi = ra_hi + a_hi;              // the second entry follows the first
+  __syncwarp();  // the null fill is complete before the slots are written
+  const uint32_t adr_a = rb + lane * 16u, adr_b = adr_a + 32 * 16u;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const uint32_t ra = ((q < 4 ? ra_lo : ra_hi) >> (8 * (q & 3))) & 0xffu;
+    const uint32_t rbq = ((q < 4 ? rb_lo : rb_hi) >> (8 * (q & 3))) & 0xffu;
+    if ((ma >> q) & 1u) gsr_sts16(lw + q * GSR_FR_LIST + 2 * ra, adr_a);
+    if ((mb >> q) & 1u) gsr_sts16(lw + q * GSR_FR_LIST + 2 * rbq, adr_b);
+  }
+  const uint32_t tot = cell < 4 ? t_lo : t_hi;
+  const int mine = (int)((tot >> (8 * (cell & 3))) & 0xffu);
+  return mine;
+}
+
 // WINDOW = false: the plain (h,w,3) / (3,h,w) image, addressed with compile-time-simple arithmetic;
 // WINDOW = true: the general strided destination with clip rectangles (gsr_forward_window).
 template <bool WINDOW>
@@ -622,42 +666,7 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
     asm volatile("cp.async.commit_group;" ::: "memory");
     slow_a = __ballot_sync(full, v1a && (e1a >> 31));
     slow_b = __ballot_sync(full, v1b && (e1b >> 31));
-    // per-cell lists of 16-bit shared-memory addresses (the CTA's shared window is < 64 KB): every slot starts as
-    // the null record's; the rank of an entry in the list of cell q = number of earlier entries that name q, in
-    // the order (lane 0: first, second entry), (lane 1: ...).  The eight ranks of an entry come from ONE warp
-    // scan: the masks are spread to a byte per cell (two registers), the bytes are prefix-summed across the lanes
-    // with shuffles (counts stay below 256: at most 64 entries) -- no popcounts (they share the MUFU pipe).
-    const uint32_t lw = list_w + st * GSR_FR_LIST_STAGE;
-    const uint32_t null2 = (rb + CH * 16u) * 0x00010001u;
-    gsr_sts128u(lw + lane * 16, null2);
-    gsr_sts128u(lw + 512 + lane * 16, null2);
-    if (lane < 4) gsr_sts128u(lw + 1024 + lane * 16, null2);
-    const uint32_t ma = v1a ? (e1a >> GSR_ENT_MASK_SHIFT) & 0xffu : 0u, mb = v1b ? (e1b >> GSR_ENT_MASK_SHIFT) & 0xffu : 0u;
-    const uint32_t a_lo = ((ma & 15u) * 0x00204081u) & 0x01010101u, a_hi = ((ma >> 4) * 0x00204081u) & 0x01010101u;
-    const uint32_t b_lo = ((mb & 15u) * 0x00204081u) & 0x01010101u, b_hi = ((mb >> 4) * 0x00204081u) & 0x01010101u;
-    uint32_t s_lo = a_lo + b_lo, s_hi = a_hi + b_hi;  // inclusive prefix sums, a byte per cell
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t0 = __shfl_up_sync(full, s_lo, d), t1 = __shfl_up_sync(full, s_hi, d);
-      if (lane >= d) {
-        s_lo += t0;
-        s_hi += t1;
-      }
-    }
-    const uint32_t t_lo = __shfl_sync(full, s_lo, 31), t_hi = __shfl_sync(full, s_hi, 31);
-    const uint32_t ra_lo = s_lo - a_lo - b_lo, ra_hi = s_hi - a_hi - b_hi;  // exclusive: rank of the first entry
-    const uint32_t rb_lo = ra_lo + a_lo, rb_hi = ra_hi + a_hi;              // the second entry follows the first
-    __syncwarp();  // the null fill is complete before the slots are written
-    const uint32_t adr_a = rb + lane * 16u, adr_b = adr_a + 32 * 16u;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const uint32_t ra = ((q < 4 ? ra_lo : ra_hi) >> (8 * (q & 3))) & 0xffu;
-      const uint32_t rbq = ((q < 4 ? rb_lo : rb_hi) >> (8 * (q & 3))) & 0xffu;
-      if ((ma >> q) & 1u) gsr_sts16(lw + q * GSR_FR_LIST + 2 * ra, adr_a);
-      if ((mb >> q) & 1u) gsr_sts16(lw + q * GSR_FR_LIST + 2 * rbq, adr_b);
-    }
-    const uint32_t tot = cell < 4 ? t_lo : t_hi;
-    const int mine = (int)((tot >> (8 * (cell & 3))) & 0xffu);
+    const int mine = gsr_fr_build_lists(list_w + st * GSR_FR_LIST_STAGE, rb, lane, cell, v1a, e1a, v1b, e1b);
     return (__reduce_max_sync(full, mine) + 3) & ~3;
   };
 

@@ -5,6 +5,7 @@
 #include "gsr_backward.cuh"
 #include "gsr_frontend.cuh"
 #include <atomic>
+#include <cstdlib>
 
 static thread_local int g_last_cuda_error = 0;
 
@@ -67,8 +68,8 @@ static int gsr_sm_count(int* out) {
 }
 
 template <typename K>
-static int gsr_resident_grid(K kernel, int threads, int slot, int* out) {
-  static std::atomic<int> cache[2][64];  // [kernel slot][device], 0 = not yet queried
+static int gsr_resident_grid(K kernel, int threads, int slot, int* out, size_t dyn_smem = 0) {
+  static std::atomic<int> cache[3][64];  // [kernel slot][device], 0 = not yet queried
   int dev = 0;
   GSR_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64) {
@@ -81,7 +82,7 @@ static int gsr_resident_grid(K kernel, int threads, int slot, int* out) {
   int nsm = 0, per_sm = 0;
   const int rc = gsr_sm_count(&nsm);
   if (rc) return rc;
-  GSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+  GSR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem));
   *out = nsm * (per_sm > 0 ? per_sm : 1);
   if (dev >= 0 && dev < 64) cache[slot][dev].store(*out, std::memory_order_relaxed);
   return GSR_OK;
@@ -90,7 +91,7 @@ static int gsr_resident_grid(K kernel, int threads, int slot, int* out) {
 // Kernels that need more than 48 KB of dynamic shared memory opt in once per (device, kernel).
 template <typename K>
 static int gsr_optin_smem(K kernel, int bytes, int slot) {
-  static std::atomic<int> done[2][64];
+  static std::atomic<int> done[4][64];
   int dev = 0;
   GSR_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && done[slot][dev].load(std::memory_order_relaxed)) return GSR_OK;
@@ -220,18 +221,48 @@ static GsrFwdArgs gsr_fwd_args(const GsrWorkspace& ws, float* img, int h, int w,
 }
 
 // Raster over the region buckets (runs when every bucket fitted) ...
+// Two kernels share the evaluation loop.  gsr_forward_region_kernel (every warp stages and evaluates) wins when a
+// warp has many regions to walk (HL: 18 per warp, 283 vs 303 us; C3: 405 vs 440 us); the warp-specialised
+// gsr_forward_region_ws_kernel (producer / consumer warp pairs, gsr_forward_ws.cuh) wins when there are only a few
+// regions per warp, where its deeper staging pipeline and coarser warp count balance better (C2: 84 -> 62 us,
+// C2d: 245 -> 162 us).  GSR_FR_WS=0/1 in the environment forces one of them (tuning aid, read once).
+#ifndef GSR_CFG_FR_WS_UNITS_PER_WARP
+#define GSR_CFG_FR_WS_UNITS_PER_WARP 12
+#endif
+static int gsr_ws_override() {
+  static const int v = [] {
+    const char* e = getenv("GSR_FR_WS");
+    return e && (e[0] == '0' || e[0] == '1') ? e[0] - '0' : -1;
+  }();
+  return v;
+}
 static int gsr_launch_forward_region(const GsrWorkspace& ws, float* img, int h, int w, float keff,
                                    uint32_t flags, cudaStream_t st) {
   GsrFwdArgs a = gsr_fwd_args(ws, img, h, w, keff, flags);
   a.want = 0;
-  // persistent warps: one resident wave, every warp takes regions from the work counter
-  int cap = 0;
-  const int rc = gsr_resident_grid(gsr_forward_region_kernel<false>, GSR_FR_THREADS, 1, &cap);
-  if (rc) return rc;
   const int nunits = ws.nrx * ws.nry;
-  const int want = (nunits + GSR_FR_WARPS - 1) / GSR_FR_WARPS;
-  if (ws.win) gsr_forward_region_kernel<true><<<want < cap ? want : cap, GSR_FR_THREADS, 0, st>>>(a);
-  else gsr_forward_region_kernel<false><<<want < cap ? want : cap, GSR_FR_THREADS, 0, st>>>(a);
+  int cap = 0;
+  int rc = gsr_resident_grid(gsr_forward_region_kernel<false>, GSR_FR_THREADS, 1, &cap);
+  if (rc) return rc;
+  const int ov = gsr_ws_override();
+  const bool use_ws = ov >= 0 ? ov != 0 : (long long)nunits < (long long)GSR_CFG_FR_WS_UNITS_PER_WARP * cap * GSR_FR_WARPS;
+  if (use_ws) {
+    // persistent warp pairs: one resident wave, every producer warp takes regions from the work counter
+    rc = gsr_optin_smem(gsr_forward_region_ws_kernel<false>, (int)sizeof(GsrWsSmem), 2);
+    if (rc) return rc;
+    rc = gsr_optin_smem(gsr_forward_region_ws_kernel<true>, (int)sizeof(GsrWsSmem), 3);
+    if (rc) return rc;
+    rc = gsr_resident_grid(gsr_forward_region_ws_kernel<false>, GSR_WS_THREADS, 2, &cap, sizeof(GsrWsSmem));
+    if (rc) return rc;
+    const int want = (nunits + GSR_WS_PAIRS - 1) / GSR_WS_PAIRS, grid = want < cap ? want : cap;
+    if (ws.win) gsr_forward_region_ws_kernel<true><<<grid, GSR_WS_THREADS, sizeof(GsrWsSmem), st>>>(a);
+    else gsr_forward_region_ws_kernel<false><<<grid, GSR_WS_THREADS, sizeof(GsrWsSmem), st>>>(a);
+  } else {
+    // persistent warps: one resident wave, every warp takes regions from the work counter
+    const int want = (nunits + GSR_FR_WARPS - 1) / GSR_FR_WARPS;
+    if (ws.win) gsr_forward_region_kernel<true><<<want < cap ? want : cap, GSR_FR_THREADS, 0, st>>>(a);
+    else gsr_forward_region_kernel<false><<<want < cap ? want : cap, GSR_FR_THREADS, 0, st>>>(a);
+  }
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
 }

@@ -8,12 +8,9 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "variants")
 VARIANTS = {
     "base": [],
-    "fr5": ["GSR_CFG_FR_MIN_CTAS=5"],
-    "fr7": ["GSR_CFG_FR_MIN_CTAS=7"],
-    "fr8": ["GSR_CFG_FR_MIN_CTAS=8"],
-    "rb12": ["GSR_CFG_RB_MIN_CTAS=12"],
-    "rb128": ["GSR_CFG_RB_THREADS=128", "GSR_CFG_RB_MIN_CTAS=8"],
-    "rb32": ["GSR_CFG_RB_THREADS=32", "GSR_CFG_RB_MIN_CTAS=32"],
+    "ws_p56_c72": ["GSR_CFG_WS_PROD_REGS=56", "GSR_CFG_WS_CONS_REGS=72"],
+    "ws_p40_c88": ["GSR_CFG_WS_PROD_REGS=40", "GSR_CFG_WS_CONS_REGS=88"],
+    "ws_3ctas": ["GSR_CFG_WS_MIN_CTAS=3"],
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
