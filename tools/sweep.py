@@ -8,9 +8,7 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "variants")
 VARIANTS = {
     "base": [],
-    "ws_p56_c72": ["GSR_CFG_WS_PROD_REGS=56", "GSR_CFG_WS_CONS_REGS=72"],
-    "ws_p40_c88": ["GSR_CFG_WS_PROD_REGS=40", "GSR_CFG_WS_CONS_REGS=88"],
-    "ws_3ctas": ["GSR_CFG_WS_MIN_CTAS=3"],
+    "mask_per_band": ["GSR_CFG_MASK_PER_BAND=1"],
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
