@@ -137,7 +137,7 @@ struct GsrSetup {
   int ext_x, ext_y;     // ceil of the distance from the centre to the far box edge (pixels)
 };
 
-GSR_HD bool gsr_finite(float v) { return v == v && fabsf(v) < 3.0e38f; }
+GSR_HD bool gsr_finite(float v) { return fabsf(v) < 3.0e38f; }  // false for NaN
 
 // Cull box = exact dmax window  INTERSECT  [c - (k*sigma_px + pad), c + (k*sigma_px + pad)].
 // The image may be a ROW BAND of a taller one: rows [row0, row0 + h) of an hf-row image (hf = 0: the
@@ -160,10 +160,10 @@ GSR_HD GsrSetup gsr_setup(float sx, float sy, float rho, float x, float y, float
   o.x1 = o.y1 = 0;
   o.bin_x = o.bin_y = 0;
   o.ext_x = o.ext_y = 0;
-  if (!(gsr_finite(sx) && gsr_finite(sy) && gsr_finite(rho) && gsr_finite(x) && gsr_finite(y) &&
-        gsr_finite(cr) && gsr_finite(cg) && gsr_finite(cb)))
+  // (bitwise &: one predicate chain instead of eight branches)
+  if (!(gsr_finite(sx) & gsr_finite(sy) & gsr_finite(rho) & gsr_finite(x) & gsr_finite(y) & gsr_finite(cr) &
+        gsr_finite(cg) & gsr_finite(cb) & (sx != 0.0f) & (sy != 0.0f) & (fabsf(rho) < 1.0f)))
     return o;
-  if (sx == 0.0f || sy == 0.0f || !(fabsf(rho) < 1.0f)) return o;
 
   // Fast path (single precision): the k-sigma box lies at least three pixels inside the dmax window on every
   // side, so the window cannot bind and the box is a pure truncation bound -- pixels it drops carry less than
@@ -302,8 +302,8 @@ GSR_HD GsrEllipse gsr_ellipse(const GsrRec& g, int h, int w, int hf = 0, int row
   e.cp = c + 0.5f * e.kappa * b;
   // a degenerate conic (overflow, a = 0) must not cull: an ellipse as wide as the box, checked ONCE here so
   // that gsr_band_xrange needs no NaN handling
-  if (!(gsr_finite(e.inv_a) && gsr_finite(e.kappa) && gsr_finite(e.cp) && gsr_finite(e.cx) && gsr_finite(e.cy)) ||
-      !(e.inv_a < 0.0f) || e.cp > 0.0f) {
+  if (!(gsr_finite(e.inv_a) & gsr_finite(e.kappa) & gsr_finite(e.cp) & gsr_finite(e.cx) & gsr_finite(e.cy) &
+        (e.inv_a < 0.0f) & !(e.cp > 0.0f))) {
     e.inv_a = -3.0e37f;
     e.kappa = 0.0f;
     e.cp = 0.0f;

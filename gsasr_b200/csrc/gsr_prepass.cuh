@@ -432,7 +432,9 @@ struct GsrRegionBuildSmem {
 };
 
 // Appends list positions [0, n) of every lane (n <= GSR_RB_ECAP, lane-dependent).  Warp-collective.
-__device__ __forceinline__ void gsr_bucket_flush(const GsrRegionBuildSmem& sm, int tid, int lane, int n,
+// list: [GSR_RB_ECAP][STRIDE] items, this lane's column is `col`.
+template <int STRIDE>
+__device__ __forceinline__ void gsr_bucket_flush(const uint2* list, int col, int lane, int n,
                                                  int* __restrict__ cnt, uint32_t* __restrict__ ent, int cap,
                                                  int* overflow) {
   const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
@@ -444,7 +446,7 @@ __device__ __forceinline__ void gsr_bucket_flush(const GsrRegionBuildSmem& sm, i
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const bool v = e0 + t < n;
-      it[t] = sm.list[(e0 + t) & (GSR_RB_ECAP - 1)][tid];
+      it[t] = list[((e0 + t) & (GSR_RB_ECAP - 1)) * STRIDE + col];
       // runs of consecutive lanes naming the same region form a group (lanes without an entry at this
       // position get an id no region has): heads from one shuffle + ballot, no match instruction
       const int key = v ? (int)it[t].y : -1 - lane;
@@ -599,11 +601,281 @@ gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restric
           }
         }
         if (__any_sync(full, n > GSR_RB_ECAP - 4)) {  // the next four might not fit
-          gsr_bucket_flush(sm, tid, lane, n, ws.reg_count, ws.entries, ws.reg_cap, overflow);
+          gsr_bucket_flush<GSR_RB_THREADS>(&sm.list[0][0], tid, lane, n, ws.reg_count, ws.entries, ws.reg_cap, overflow);
           n = 0;
         }
       }
     }
-    gsr_bucket_flush(sm, tid, lane, n, ws.reg_count, ws.entries, ws.reg_cap, overflow);
+    gsr_bucket_flush<GSR_RB_THREADS>(&sm.list[0][0], tid, lane, n, ws.reg_count, ws.entries, ws.reg_cap, overflow);
   }
+}
+
+// ---- region build, balanced form (the default) -------------------------------------------------------------
+// Same output as gsr_region_build_kernel, arranged so that no lane waits for the widest Gaussian of its warp.
+// A warp takes 32 consecutive Gaussians.
+//   phase A  one lane per Gaussian: set-up, record, ellipse -- ellipse and cull box go to the warp's shared memory;
+//   phase B  one lane per (Gaussian, region band) ITEM: the bitmaps of the band's two cell rows, the band's first
+//            region column and its column count, left in shared memory; the items' (band, column) ENTRIES are
+//            listed column-major per batch of 32 items, so that neighbouring list positions hold neighbouring
+//            Gaussians at the same relative position -- which mostly name the same region;
+//   phase C  one lane per entry: cell mask from the item's bitmaps; runs of lanes naming the same region are
+//            found with one shuffle + ballot and the run's first lane reserves the run's bucket slots with ONE
+//            atomic (two list positions per lane in flight before the first result is used).
+// The old kernel ran every lane for the warp's maximum number of bands and of columns: 1960 -> ~1300 warp
+// instructions per 32 Gaussians at HL.  A warp holding a Gaussian wider than 32 cells or taller than GSR_RB2_MAXB
+// bands walks the generic way.
+#ifndef GSR_CFG_RB2
+#define GSR_CFG_RB2 1
+#endif
+#ifndef GSR_CFG_RB2_MIN_CTAS
+#define GSR_CFG_RB2_MIN_CTAS 8
+#endif
+constexpr int GSR_RB2_WARPS = 4;
+constexpr int GSR_RB2_THREADS = 32 * GSR_RB2_WARPS;
+constexpr int GSR_RB2_MAXB = 12;    // region bands per Gaussian on the balanced path
+constexpr int GSR_RB2_PASS = 128;   // items per pass (four batches of 32)
+constexpr int GSR_RB2_MAXC = 8;     // region columns per item: 32 cells from the first column's first cell
+
+struct GsrRb2Warp {
+  union {
+    struct {
+      float4 p0[32];                                 // cx, cy, inv_a, kappa
+      float4 p1[32];                                 // cp, box.x, box.y (gsr_box_pack, binds in bit 15 of box.x), -
+      uint4 item[GSR_RB2_PASS];                      // row bits 0, row bits 1, first region id, shift | lane << 8 | binds << 13
+      uint16_t items[32 * GSR_RB2_MAXB];             // lane | band offset << 5, k-major
+      uint16_t ents[GSR_RB2_PASS * GSR_RB2_MAXC];    // item slot | column << 7
+    } b;
+    uint2 list[GSR_RB_ECAP][32];                     // generic walk: {entry, region id} per lane
+  };
+};
+
+// Generic walk of one lane's box (any width): the old kernel's loop, on a warp-private list.  Warp-collective.
+__device__ __noinline__ void gsr_rb_walk_generic(uint2 (*list)[32], int lane, const GsrSetup st, const GsrEllipse e,
+                                                 uint32_t entry, float ecut, int nrx, int* __restrict__ cnt,
+                                                 uint32_t* __restrict__ ent, int cap, int* overflow);
+
+template <bool RAGGED, bool RAW>
+__global__ void __launch_bounds__(GSR_RB2_THREADS, GSR_CFG_RB2_MIN_CTAS)
+gsr_region_build2_kernel(const float* __restrict__ sigmas, const float* __restrict__ coords,
+                         const float* __restrict__ colors, float* __restrict__ msig, float* __restrict__ mcrd,
+                         float* __restrict__ mcol, int s, int h, int w, float dmax, float ksigma, float ecut,
+                         float step, GsrWorkspace ws) {
+  __shared__ GsrRb2Warp smw[GSR_RB2_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  GsrRb2Warp& sm = smw[warp];
+  const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+  int* const overflow = ws.stats + GSR_STAT_OVERFLOW;
+  const int nchunks = (s + 31) / 32;
+
+  for (int chunk = blockIdx.x * GSR_RB2_WARPS + warp; chunk < nchunks; chunk += gridDim.x * GSR_RB2_WARPS) {
+    const int i = chunk * 32 + lane;
+    // ---- phase A: one lane per Gaussian (see gsr_region_build_kernel for the batch views)
+    const GsrSampleView sv = gsr_sample_view<RAGGED>(ws, i < s ? i : 0, h, w, dmax);
+    const int yoff = sv.yoff, hl = sv.hl, wl = sv.wl;
+    GsrSetup st;
+    st.live = false;
+    st.binds = false;
+    st.x0 = st.y0 = 1;
+    st.x1 = st.y1 = 0;
+    GsrEllipse e;
+    e.cx = e.cy = e.inv_a = e.kappa = e.cp = 0.f;
+    if (i < s) {
+      float sx, sy, rho, x, y, cr, cg, cb;
+      if (RAW) {
+        float stp = step;
+        if (RAGGED) stp = ws.bdesc[i / ws.bn].step;
+        const GsrMapped m = gsr_map_one(sigmas + 9 * (size_t)i, ws.hf > 0 ? ws.hf : hl, wl, stp);
+        sx = m.sx, sy = m.sy, rho = m.rho, x = m.x, y = m.y, cr = m.cr, cg = m.cg, cb = m.cb;
+        float* ms = msig + 3 * (size_t)i;
+        float* mc = mcrd + 2 * (size_t)i;
+        float* mk = mcol + 3 * (size_t)i;
+        ms[0] = sx, ms[1] = sy, ms[2] = rho;
+        mc[0] = x, mc[1] = y;
+        mk[0] = cr, mk[1] = cg, mk[2] = cb;
+      } else {
+        sy = __ldg(sigmas + 3 * (size_t)i + 1);
+        y = __ldg(coords + 2 * (size_t)i + 1);
+        sx = rho = x = cr = cg = cb = 0.f;
+        // row-band view: a Gaussian whose k-sigma rows miss the band by more than a pixel is dropped after two loads
+        bool reach = true;
+        if (ws.hf > 0) {
+          const float hyf = 0.5f * (float)(ws.hf - 1);
+          const float cyf = (y + 1.0f) * hyf, eyf = ksigma * fabsf(sy) * hyf + 1.0f;
+          reach = !(cyf + eyf < (float)ws.row0 - 1.0f || cyf - eyf > (float)(ws.row0 + h));
+        }
+        if (reach) {
+          sx = __ldg(sigmas + 3 * (size_t)i + 0);
+          rho = __ldg(sigmas + 3 * (size_t)i + 2);
+          x = __ldg(coords + 2 * (size_t)i + 0);
+          cr = __ldg(colors + 3 * (size_t)i + 0);
+          cg = __ldg(colors + 3 * (size_t)i + 1);
+          cb = __ldg(colors + 3 * (size_t)i + 2);
+        } else {
+          sy = 0.f;  // sigma = 0: gsr_setup returns "not live" at its first test
+        }
+      }
+      st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, hl, wl, sv.dmax, ksigma, sv.px_tab, sv.py_tab, ws.hf, ws.row0);
+      if (st.live) {
+        const GsrRec r = gsr_make_rec(sx, sy, rho, x, y, cr, cg, cb);
+        if (!(gsr_finite(r.a) & gsr_finite(r.b) & gsr_finite(r.c))) st.live = false;
+        st.y0 += yoff;
+        st.y1 += yoff;
+        if (gsr_edge_binds<RAGGED>(sv, st)) st.binds = true;
+        if (st.live) {
+          GsrRec rs = r;
+          if (RAGGED) gsr_rescale_rec(rs, sv);
+          float4* dr = reinterpret_cast<float4*>(ws.rec_in + i);
+          dr[0] = make_float4(rs.x, rs.y, rs.a, rs.b);
+          dr[1] = make_float4(rs.c, rs.r, rs.g, rs.bl);
+          if (st.binds) ws.box_in[i] = gsr_box_pack(st.x0, st.x1, st.y0, st.y1, true);
+          e = gsr_ellipse(r, hl, wl, ws.hf, ws.row0);
+          e.cy += (float)yoff;
+        }
+      }
+    }
+    if (!st.live) {
+      st.x0 = st.y0 = 1;
+      st.x1 = st.y1 = 0;
+    }
+    const uint32_t entry = (uint32_t)i | (st.binds ? 0x80000000u : 0u);
+    // (box corners of a live Gaussian are non-negative: unsigned divisions are shifts)
+    const int nb = st.live ? (int)((unsigned)st.y1 / GSR_RGH) - (int)((unsigned)st.y0 / GSR_RGH) + 1 : 0;
+    const int cbase0 = (int)((unsigned)st.x0 / GSR_RGW) * GSR_CELLS_X;
+    const bool fits = !st.live || ((int)((unsigned)st.x1 / GSR_CELL) - cbase0 < 32 && nb <= GSR_RB2_MAXB);
+    if (!__all_sync(full, fits)) {
+      gsr_rb_walk_generic(sm.list, lane, st, e, entry, ecut, ws.nrx, ws.reg_count, ws.entries, ws.reg_cap, overflow);
+      __syncwarp();
+      continue;
+    }
+    const uint2 pk = gsr_box_pack(st.x0, st.x1, st.y0, st.y1, st.binds);
+    sm.b.p0[lane] = make_float4(e.cx, e.cy, e.inv_a, e.kappa);
+    sm.b.p1[lane] = make_float4(e.cp, __uint_as_float(pk.x), __uint_as_float(pk.y), 0.f);
+    // item list, k-major: (every lane with a band k), k = 0, 1, ...
+    const int KB = __reduce_max_sync(full, nb);
+    int nitems = 0;
+    for (int k = 0; k < KB; ++k) {
+      const unsigned have = __ballot_sync(full, k < nb);
+      if (k < nb) sm.b.items[nitems + __popc(have & lt)] = (uint16_t)(lane | (k << 5));
+      nitems += __popc(have);
+    }
+    __syncwarp();
+    const uint32_t ibase = (uint32_t)(chunk * 32);
+
+    for (int pass0 = 0; pass0 < nitems; pass0 += GSR_RB2_PASS) {
+      const int pend = min(nitems, pass0 + GSR_RB2_PASS);
+      // ---- phase B: one lane per (Gaussian, band)
+      int nent = 0;
+      for (int t0 = pass0; t0 < pend; t0 += 32) {
+        const bool act = t0 + lane < pend;
+        const uint32_t item = act ? sm.b.items[t0 + lane] : 0u;
+        const int g = (int)(item & 31u), k = (int)(item >> 5);
+        const float4 q0 = sm.b.p0[g], q1 = sm.b.p1[g];
+        GsrEllipse eg;
+        eg.cx = q0.x;
+        eg.cy = q0.y;
+        eg.inv_a = q0.z;
+        eg.kappa = q0.w;
+        eg.cp = q1.x;
+        int x0, x1, y0, y1;
+        bool binds;
+        gsr_box_unpack(make_uint2(__float_as_uint(q1.y), __float_as_uint(q1.z)), x0, x1, y0, y1, binds);
+        const int b = (int)((unsigned)y0 / GSR_RGH) + k;
+        const int cbase = (int)((unsigned)x0 / GSR_RGW) * GSR_CELLS_X;
+        uint32_t rb[2] = {0u, 0u};
+        int ca = 0, ncol = 0;
+        if (act && gsr_band_rowbits(eg, ecut, b, x0, x1, y0, y1, cbase, rb)) {
+          const uint32_t any = rb[0] | rb[1];
+          ca = (int)((unsigned)(cbase + __ffs(any) - 1) / GSR_CELLS_X);
+          ncol = (int)((unsigned)(cbase + 31 - __clz(any)) / GSR_CELLS_X) - ca + 1;
+        }
+        const int slot = t0 - pass0 + lane;
+        sm.b.item[slot] = make_uint4(rb[0], rb[1], (uint32_t)(b * ws.nrx + ca),
+                                     (uint32_t)(ca * GSR_CELLS_X - cbase) | ((uint32_t)g << 8) | (binds ? 0x2000u : 0u));
+        // entries of this batch, column-major
+        const int KC = __reduce_max_sync(full, ncol);
+        for (int j = 0; j < KC; ++j) {
+          const unsigned have = __ballot_sync(full, j < ncol);
+          if (j < ncol) sm.b.ents[nent + __popc(have & lt)] = (uint16_t)(slot | (j << 7));
+          nent += __popc(have);
+        }
+      }
+      __syncwarp();
+      // ---- phase C: one lane per entry, two list positions per lane and round
+      for (int t0 = 0; t0 < nent; t0 += 64) {
+        uint32_t m[2], word[2];
+        int rid[2], base[2], lead[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int t = t0 + 32 * u + lane;
+          const uint32_t en = t < nent ? sm.b.ents[t] : 0u;
+          const uint4 it = sm.b.item[en & 127u];
+          const int j = (int)(en >> 7);
+          const unsigned sh = (it.w & 31u) + 4u * (unsigned)j;
+          m[u] = t < nent ? ((it.x >> sh) & 0xfu) | (((it.y >> sh) & 0xfu) << GSR_CELLS_X) : 0u;
+          rid[u] = (int)it.z + j;
+          word[u] = (ibase + ((it.w >> 8) & 31u)) | ((it.w & 0x2000u) << 18) | (m[u] << GSR_ENT_MASK_SHIFT);
+          // runs of consecutive lanes naming the same region form a group (lanes without an entry get an id no
+          // region has): heads from one shuffle + ballot
+          const int key = m[u] ? rid[u] : -1 - lane;
+          const int prev = __shfl_up_sync(full, key, 1);
+          const unsigned heads = __ballot_sync(full, lane == 0 || prev != key);
+          const unsigned upto = lt | (1u << lane);
+          lead[u] = 31 - __clz(heads & upto);                 // my run's first lane
+          const unsigned above = heads & ~upto;
+          const int end = above ? __ffs(above) - 1 : 32;      // one past my run's last lane
+          base[u] = 0;
+          // the run's first lane reserves the run's slots (predicated atomic: no divergent region; the result is
+          // not waited for before the second loop)
+          asm volatile("{\n\t.reg .pred pa;\n\tsetp.ne.s32 pa, %3, 0;\n\t@pa atom.global.add.s32 %0, [%1], %2;\n\t}"
+                       : "+r"(base[u]) : "l"(ws.reg_count + (m[u] ? rid[u] : 0)), "r"(end - lead[u]),
+                         "r"((int)(m[u] != 0u && lane == lead[u])) : "memory");
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int bs = __shfl_sync(full, base[u], lead[u]);
+          if (m[u]) {
+            const int pos = bs + lane - lead[u];
+            if (pos < ws.reg_cap) ws.entries[(size_t)rid[u] * ws.reg_cap + pos] = word[u];
+            else *overflow = 1;
+          }
+        }
+      }
+      __syncwarp();  // items and entries are rewritten by the next pass / chunk
+    }
+  }
+}
+
+__device__ __noinline__ void gsr_rb_walk_generic(uint2 (*list)[32], int lane, const GsrSetup st, const GsrEllipse e,
+                                                 uint32_t entry, float ecut, int nrx, int* __restrict__ cnt,
+                                                 uint32_t* __restrict__ ent, int cap, int* overflow) {
+  const unsigned full = 0xffffffffu;
+  const int b0 = (int)((unsigned)st.y0 / GSR_RGH), nb = st.live ? (int)((unsigned)st.y1 / GSR_RGH) - b0 + 1 : 0;
+  const int KB = __reduce_max_sync(full, nb);
+  int n = 0;
+  for (int k = 0; k < KB; ++k) {
+    const int b = b0 + k;
+    int cl[2] = {1, 1}, ch[2] = {0, 0}, ca = 0, ncol = 0;
+    if (k < nb && gsr_band_cells(e, ecut, b, st.x0, st.x1, st.y0, st.y1, cl, ch)) {
+      int cb_;
+      gsr_band_columns(cl, ch, ca, cb_);
+      ncol = cb_ - ca + 1;
+    }
+    const int KC = __reduce_max_sync(full, ncol);
+    for (int j0 = 0; j0 < KC; j0 += 4) {
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = j0 + jj, c = ca + j;
+        const uint32_t m = j < ncol ? gsr_cell_mask(cl, ch, c) : 0u;
+        if (m != 0u) {
+          list[n][lane] = make_uint2(entry | (m << GSR_ENT_MASK_SHIFT), (uint32_t)(b * nrx + c));
+          ++n;
+        }
+      }
+      if (__any_sync(full, n > GSR_RB_ECAP - 4)) {  // the next four might not fit
+        gsr_bucket_flush<32>(&list[0][0], lane, lane, n, cnt, ent, cap, overflow);
+        n = 0;
+      }
+    }
+  }
+  gsr_bucket_flush<32>(&list[0][0], lane, lane, n, cnt, ent, cap, overflow);
 }

@@ -8,7 +8,8 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "variants")
 VARIANTS = {
     "base": [],
-    "mask_per_band": ["GSR_CFG_MASK_PER_BAND=1"],
+    "rb_old": ["GSR_CFG_RB2=0"],
+    "rb2_ctas6": ["GSR_CFG_RB2_MIN_CTAS=6"],
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
