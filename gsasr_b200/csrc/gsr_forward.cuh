@@ -436,9 +436,14 @@ constexpr int GSR_FR_CHUNK = 64;                          // entries per stage (
 constexpr int GSR_FR_SLOTS = GSR_FR_CHUNK + 1;            // + the null record (slot GSR_FR_CHUNK)
 constexpr int GSR_FR_HI = GSR_FR_SLOTS * 16;              // byte offset of the second float4 of a record
 constexpr int GSR_FR_STAGE_BYTES = 2 * GSR_FR_HI;
-constexpr int GSR_FR_LIST = 2 * (GSR_FR_CHUNK + 4);       // bytes per cell list (16-bit shared addresses): 34 words, so
-                                                          // the eight cells' LDS.64 fall into different banks
-constexpr int GSR_FR_LIST_STAGE = 8 * GSR_FR_LIST;        // 1088 = 68 x 16
+#ifndef GSR_CFG_FR_LW
+#define GSR_CFG_FR_LW 2
+#endif
+constexpr int GSR_FR_LW = GSR_CFG_FR_LW;                  // bytes per list entry: a 16- or 32-bit shared-memory address
+constexpr int GSR_FR_LIST = GSR_FR_LW * (GSR_FR_CHUNK + 4);  // bytes per cell list: 34 (68) words, so the eight cells'
+                                                          // LDS.64 (LDS.128) fall into different banks
+constexpr int GSR_FR_LIST_STAGE = 8 * GSR_FR_LIST;        // 1088 = 68 x 16 (2176)
+static_assert(GSR_FR_LW == 2 || GSR_FR_LW == 4, "list entries are 16- or 32-bit addresses");
 #ifndef GSR_CFG_FR_MIN_CTAS
 #define GSR_CFG_FR_MIN_CTAS 6
 #endif
@@ -449,7 +454,7 @@ struct GsrFwdRegionSmem {
   uint2 box[GSR_FR_WARPS][2][GSR_FR_CHUNK];
   uint32_t list[GSR_FR_WARPS][2][GSR_FR_LIST_STAGE / 4];
 };
-static_assert(sizeof(GsrFwdRegionSmem) + 1024 < 65536, "cell lists hold 16-bit shared-memory addresses");
+static_assert(GSR_FR_LW == 4 || sizeof(GsrFwdRegionSmem) + 1024 < 65536, "cell lists hold 16-bit shared-memory addresses");
 
 __device__ __forceinline__ gsr_f2 gsr_mul2(gsr_f2 a, gsr_f2 b) {
   gsr_f2 d;
@@ -477,6 +482,18 @@ __device__ __forceinline__ uint2 gsr_lds64u(uint32_t addr) {
 }
 __device__ __forceinline__ void gsr_sts128u(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void gsr_sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// Four consecutive slots (positions t .. t+3, t a multiple of 4) of a cell list -> four record addresses.
+__device__ __forceinline__ void gsr_fr_load4(uint32_t lb, int t, uint32_t a[4]) {
+  if (GSR_FR_LW == 2) {
+    const uint2 s4 = gsr_lds64u(lb + 2 * t);
+    a[0] = s4.x & 0xffffu, a[1] = s4.x >> 16, a[2] = s4.y & 0xffffu, a[3] = s4.y >> 16;
+  } else {
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(lb + 4 * t));
+  }
 }
 
 // One Gaussian against this lane's 2x2 pixel block.  nx2/ny2 hold the NEGATED pixel coordinates, so
@@ -530,10 +547,10 @@ __device__ __forceinline__ int gsr_fr_build_lists(uint32_t lw, uint32_t rb, int 
                                                   bool v1b, uint32_t e1b) {
   constexpr int CH = GSR_FR_CHUNK;
   const unsigned full = 0xffffffffu;
-  const uint32_t null2 = (rb + CH * 16u) * 0x00010001u;
-  gsr_sts128u(lw + lane * 16, null2);
-  gsr_sts128u(lw + 512 + lane * 16, null2);
-  if (lane < 4) gsr_sts128u(lw + 1024 + lane * 16, null2);
+  const uint32_t null2 = (rb + CH * 16u) * (GSR_FR_LW == 2 ? 0x00010001u : 1u);
+#pragma unroll
+  for (int o = 0; o < GSR_FR_LIST_STAGE; o += 512)
+    if (o + 512 <= GSR_FR_LIST_STAGE || lane < (GSR_FR_LIST_STAGE - o) / 16) gsr_sts128u(lw + o + lane * 16, null2);
   const uint32_t ma = v1a ? (e1a >> GSR_ENT_MASK_SHIFT) & 0xffu : 0u, mb = v1b ? (e1b >> GSR_ENT_MASK_SHIFT) & 0xffu : 0u;
   const uint32_t a_lo = ((ma & 15u) * 0x00204081u) & 0x01010101u, a_hi = ((ma >> 4) * 0x00204081u) & 0x01010101u;
   const uint32_t b_lo = ((mb & 15u) * 0x00204081u) & 0x01010101u, b_hi = ((mb >> 4) * 0x00204081u) & 0x01010101u;
@@ -555,8 +572,13 @@ __device__ __forceinline__ int gsr_fr_build_lists(uint32_t lw, uint32_t rb, int 
   for (int q = 0; q < 8; ++q) {
     const uint32_t ra = ((q < 4 ? ra_lo : ra_hi) >> (8 * (q & 3))) & 0xffu;
     const uint32_t rbq = ((q < 4 ? rb_lo : rb_hi) >> (8 * (q & 3))) & 0xffu;
-    if ((ma >> q) & 1u) gsr_sts16(lw + q * GSR_FR_LIST + 2 * ra, adr_a);
-    if ((mb >> q) & 1u) gsr_sts16(lw + q * GSR_FR_LIST + 2 * rbq, adr_b);
+    if (GSR_FR_LW == 2) {
+      if ((ma >> q) & 1u) gsr_sts16(lw + q * GSR_FR_LIST + 2 * ra, adr_a);
+      if ((mb >> q) & 1u) gsr_sts16(lw + q * GSR_FR_LIST + 2 * rbq, adr_b);
+    } else {
+      if ((ma >> q) & 1u) gsr_sts32(lw + q * GSR_FR_LIST + 4 * ra, adr_a);
+      if ((mb >> q) & 1u) gsr_sts32(lw + q * GSR_FR_LIST + 4 * rbq, adr_b);
+    }
   }
   const uint32_t tot = cell < 4 ? t_lo : t_hi;
   const int mine = (int)((tot >> (8 * (cell & 3))) & 0xffu);
@@ -713,11 +735,11 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
 
     if ((slow_ac | slow_bc) == 0) {
       for (int t = 0; t < trip; t += 4) {
-        const uint2 s4 = gsr_lds64u(lb + 2 * t);
+        uint32_t a4[4];
+        gsr_fr_load4(lb, t, a4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint32_t w2 = k < 2 ? s4.x : s4.y;
-          const uint32_t a = (k & 1) ? (w2 >> 16) : (w2 & 0xffffu);
+          const uint32_t a = a4[k];
           gsr_eval_quad<false>(a, a + GSR_FR_HI, nx2, ny2, true, true, true, true, r0, g0, b0, r1, g1, b1);
         }
       }
@@ -725,11 +747,11 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
       const int uy = uA / p.nrx, ux = uA - uy * p.nrx;
       const int wi0 = ux * GSR_RGW + bx, hi0 = uy * GSR_RGH + by;
       for (int t = 0; t < trip; t += 4) {
-        const uint2 s4 = gsr_lds64u(lb + 2 * t);
+        uint32_t a4[4];
+        gsr_fr_load4(lb, t, a4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint32_t w2 = k < 2 ? s4.x : s4.y;
-          const uint32_t a = (k & 1) ? (w2 >> 16) : (w2 & 0xffffu);
+          const uint32_t a = a4[k];
           const uint32_t slot = (a - rb) >> 4;
           const bool binds = slot < 32 ? ((slow_ac >> slot) & 1u) : (slot < 64 ? ((slow_bc >> (slot - 32)) & 1u) : false);
           bool m00 = true, m01 = true, m10 = true, m11 = true;

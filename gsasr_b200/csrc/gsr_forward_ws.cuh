@@ -51,7 +51,7 @@ struct GsrWsSmem {
   unsigned long long full[GSR_WS_PAIRS][GSR_WS_STAGES];
   unsigned long long empty[GSR_WS_PAIRS][GSR_WS_STAGES];
 };
-static_assert(sizeof(GsrWsSmem) + 1024 < 65536, "cell lists hold 16-bit shared-memory addresses");
+static_assert(GSR_FR_LW == 4 || sizeof(GsrWsSmem) + 1024 < 65536, "cell lists hold 16-bit shared-memory addresses");
 
 __device__ __forceinline__ void gsr_mbar_init(uint32_t bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -260,21 +260,21 @@ __global__ void __launch_bounds__(GSR_WS_THREADS, GSR_CFG_WS_MIN_CTAS) gsr_forwa
     }
     if ((slow_a | slow_b) == 0) {
       for (int t = 0; t < trip; t += 4) {
-        const uint2 s4 = gsr_lds64u(lb + 2 * t);
+        uint32_t a4[4];
+        gsr_fr_load4(lb, t, a4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint32_t w2 = k < 2 ? s4.x : s4.y;
-          const uint32_t a = (k & 1) ? (w2 >> 16) : (w2 & 0xffffu);
+          const uint32_t a = a4[k];
           gsr_eval_quad<false>(a, a + GSR_FR_HI, nx2, ny2, true, true, true, true, r0, g0, b0, r1, g1, b1);
         }
       }
     } else {
       for (int t = 0; t < trip; t += 4) {
-        const uint2 s4 = gsr_lds64u(lb + 2 * t);
+        uint32_t a4[4];
+        gsr_fr_load4(lb, t, a4);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint32_t w2 = k < 2 ? s4.x : s4.y;
-          const uint32_t a = (k & 1) ? (w2 >> 16) : (w2 & 0xffffu);
+          const uint32_t a = a4[k];
           const uint32_t slot = (a - sb) >> 4;
           const bool binds = slot < 32 ? ((slow_a >> slot) & 1u) : (slot < 64 ? ((slow_b >> (slot - 32)) & 1u) : false);
           bool m00 = true, m01 = true, m10 = true, m11 = true;

@@ -750,12 +750,22 @@ gsr_region_build2_kernel(const float* __restrict__ sigmas, const float* __restri
     const uint2 pk = gsr_box_pack(st.x0, st.x1, st.y0, st.y1, st.binds);
     sm.b.p0[lane] = make_float4(e.cx, e.cy, e.inv_a, e.kappa);
     sm.b.p1[lane] = make_float4(e.cp, __uint_as_float(pk.x), __uint_as_float(pk.y), 0.f);
-    // item list, k-major: (every lane with a band k), k = 0, 1, ...
-    const int KB = __reduce_max_sync(full, nb);
+    // item list, band-major: (every lane whose box reaches band b), b = first band of the warp, ...  Lanes next to
+    // each other in the list are then neighbouring Gaussians in the SAME band (whatever their jitter across a band
+    // boundary).  Input whose bands lie far apart (incoherent order, a chunk across two samples of a batch) lists
+    // by band offset instead.
+    const int b0 = (int)((unsigned)st.y0 / GSR_RGH);
+    const int bmin = __reduce_min_sync(full, nb > 0 ? b0 : 0x7fffffff);
+    const int bmax = __reduce_max_sync(full, nb > 0 ? b0 + nb - 1 : -1);
+    const bool by_band = bmax - bmin < 2 * GSR_RB2_MAXB;
+    const int KB = by_band ? bmax - bmin + 1 : __reduce_max_sync(full, nb);
+    const int kfirst = by_band ? bmin - b0 : 0;  // this lane's band offset at list round 0
     int nitems = 0;
-    for (int k = 0; k < KB; ++k) {
-      const unsigned have = __ballot_sync(full, k < nb);
-      if (k < nb) sm.b.items[nitems + __popc(have & lt)] = (uint16_t)(lane | (k << 5));
+    for (int kk = 0; kk < KB; ++kk) {
+      const int k = kfirst + kk;
+      const bool has = k >= 0 && k < nb;
+      const unsigned have = __ballot_sync(full, has);
+      if (has) sm.b.items[nitems + __popc(have & lt)] = (uint16_t)(lane | (k << 5));
       nitems += __popc(have);
     }
     __syncwarp();
@@ -791,11 +801,17 @@ gsr_region_build2_kernel(const float* __restrict__ sigmas, const float* __restri
         const int slot = t0 - pass0 + lane;
         sm.b.item[slot] = make_uint4(rb[0], rb[1], (uint32_t)(b * ws.nrx + ca),
                                      (uint32_t)(ca * GSR_CELLS_X - cbase) | ((uint32_t)g << 8) | (binds ? 0x2000u : 0u));
-        // entries of this batch, column-major
-        const int KC = __reduce_max_sync(full, ncol);
-        for (int j = 0; j < KC; ++j) {
-          const unsigned have = __ballot_sync(full, j < ncol);
-          if (j < ncol) sm.b.ents[nent + __popc(have & lt)] = (uint16_t)(slot | (j << 7));
+        // entries of this batch, column-major (by absolute region column when the batch's columns lie close)
+        const int cmin = __reduce_min_sync(full, ncol > 0 ? ca : 0x7fffffff);
+        const int cmax = __reduce_max_sync(full, ncol > 0 ? ca + ncol - 1 : -1);
+        const bool by_col = cmax - cmin < 2 * GSR_RB2_MAXC;
+        const int KC = by_col ? cmax - cmin + 1 : __reduce_max_sync(full, ncol);
+        const int jfirst = by_col ? cmin - ca : 0;
+        for (int jj = 0; jj < KC; ++jj) {
+          const int j = jfirst + jj;
+          const bool has = j >= 0 && j < ncol;
+          const unsigned have = __ballot_sync(full, has);
+          if (has) sm.b.ents[nent + __popc(have & lt)] = (uint16_t)(slot | (j << 7));
           nent += __popc(have);
         }
       }

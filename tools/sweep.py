@@ -9,7 +9,6 @@ VDIR = os.path.join(ROOT, "variants")
 VARIANTS = {
     "base": [],
     "rb_old": ["GSR_CFG_RB2=0"],
-    "rb2_ctas6": ["GSR_CFG_RB2_MIN_CTAS=6"],
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
