@@ -444,8 +444,11 @@ constexpr int GSR_FR_LIST = GSR_FR_LW * (GSR_FR_CHUNK + 4);  // bytes per cell l
                                                           // LDS.64 (LDS.128) fall into different banks
 constexpr int GSR_FR_LIST_STAGE = 8 * GSR_FR_LIST;        // 1088 = 68 x 16 (2176)
 static_assert(GSR_FR_LW == 2 || GSR_FR_LW == 4, "list entries are 16- or 32-bit addresses");
+#ifndef GSR_CFG_FR_TAIL
+#define GSR_CFG_FR_TAIL 1   // trip counts are not rounded up to the unroll factor: a chunk's last 1-3 list positions run singly
+#endif
 #ifndef GSR_CFG_FR_MIN_CTAS
-#define GSR_CFG_FR_MIN_CTAS 6
+#define GSR_CFG_FR_MIN_CTAS 5
 #endif
 static_assert(GSR_RGW == 16 && GSR_RGH == 8 && GSR_CELL == 4, "a warp of 2x2 blocks covers a 16x8 region, four lanes a cell");
 
@@ -689,7 +692,11 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
     slow_a = __ballot_sync(full, v1a && (e1a >> 31));
     slow_b = __ballot_sync(full, v1b && (e1b >> 31));
     const int mine = gsr_fr_build_lists(list_w + st * GSR_FR_LIST_STAGE, rb, lane, cell, v1a, e1a, v1b, e1b);
+#if GSR_CFG_FR_TAIL
+    return __reduce_max_sync(full, mine);
+#else
     return (__reduce_max_sync(full, mine) + 3) & ~3;
+#endif
   };
 
   // Units in flight: A is evaluated, B and C are known far enough ahead for the two-deep prefetch to run
@@ -734,6 +741,25 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
     }
 
     if ((slow_ac | slow_bc) == 0) {
+#if GSR_CFG_FR_TAIL
+      int t = 0;
+      for (; t + 4 <= trip; t += 4) {
+        uint32_t a4[4];
+        gsr_fr_load4(lb, t, a4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t a = a4[k];
+          gsr_eval_quad<false>(a, a + GSR_FR_HI, nx2, ny2, true, true, true, true, r0, g0, b0, r1, g1, b1);
+        }
+      }
+      if (t < trip) {  // one to three left: two at once, then one
+        uint32_t a4[4];
+        gsr_fr_load4(lb, t, a4);
+        gsr_eval_quad<false>(a4[0], a4[0] + GSR_FR_HI, nx2, ny2, true, true, true, true, r0, g0, b0, r1, g1, b1);
+        if (t + 1 < trip) gsr_eval_quad<false>(a4[1], a4[1] + GSR_FR_HI, nx2, ny2, true, true, true, true, r0, g0, b0, r1, g1, b1);
+        if (t + 2 < trip) gsr_eval_quad<false>(a4[2], a4[2] + GSR_FR_HI, nx2, ny2, true, true, true, true, r0, g0, b0, r1, g1, b1);
+      }
+#else
       for (int t = 0; t < trip; t += 4) {
         uint32_t a4[4];
         gsr_fr_load4(lb, t, a4);
@@ -743,6 +769,7 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
           gsr_eval_quad<false>(a, a + GSR_FR_HI, nx2, ny2, true, true, true, true, r0, g0, b0, r1, g1, b1);
         }
       }
+#endif
     } else {
       const int uy = uA / p.nrx, ux = uA - uy * p.nrx;
       const int wi0 = ux * GSR_RGW + bx, hi0 = uy * GSR_RGH + by;

@@ -8,7 +8,9 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "variants")
 VARIANTS = {
     "base": [],
-    "rb_old": ["GSR_CFG_RB2=0"],
+    "c4": ["GSR_CFG_FR_MIN_CTAS=4"],
+    "c5_lw4": ["GSR_CFG_FR_LW=4"],
+    "c4_lw4": ["GSR_CFG_FR_LW=4", "GSR_CFG_FR_MIN_CTAS=4"],
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
