@@ -12,6 +12,7 @@ GSR_FLAG_OVERWRITE = 0x1
 GSR_FLAG_CHW = 0x2
 GSR_FLAG_U8 = 0x4
 GSR_FLAG_BGR = 0x8
+GSR_FLAG_ROW_STORES = 0x10
 DEFAULT_KSIGMA = 5.0
 EXACT_KSIGMA = float("inf")
 

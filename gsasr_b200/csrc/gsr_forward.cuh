@@ -456,6 +456,7 @@ struct GsrFwdRegionSmem {
   float4 rec[GSR_FR_WARPS][2][2 * GSR_FR_SLOTS];   // per warp, 2 stages x { first float4 x 65, second float4 x 65 }
   uint2 box[GSR_FR_WARPS][2][GSR_FR_CHUNK];
   uint32_t list[GSR_FR_WARPS][2][GSR_FR_LIST_STAGE / 4];
+  float4 tile[GSR_FR_WARPS][GSR_RGW * GSR_RGH * 3 / 4];  // write-out staging (gsr_fr_write_unit)
 };
 static_assert(GSR_FR_LW == 4 || sizeof(GsrFwdRegionSmem) + 1024 < 65536, "cell lists hold 16-bit shared-memory addresses");
 
@@ -588,6 +589,118 @@ __device__ __forceinline__ int gsr_fr_build_lists(uint32_t lw, uint32_t rb, int 
   return mine;
 }
 
+// ---- write-out of a finished 16x8 region (both raster kernels) ----------------------------------------------
+// v[yy][xx][ch]: this lane's 2x2 block at region offset (bx, by); (ux, uy): the region.  `tile` is 1536 bytes of
+// warp-private shared memory.  Plain stores when the image is overwritten, fire-and-forget reductions (RED) when
+// the call accumulates into the caller's image (the reference's contract): no read, no latency.
+// Writing the uint8 image (w % 16 == 0), or overwriting an (h,w,3) fp32 image (w % 4 == 0) under
+// GSR_FLAG_ROW_STORES, a region inside the image goes through the tile and leaves as 128-bit stores of whole
+// region rows (48 / 192 contiguous bytes): what matters when the image lives on ANOTHER GPU
+// (render_image_bands_peer) -- NVLink packets of 16 bytes per lane instead of 4; on a local fp32 image the
+// detour costs 1 % (HL 279.6 vs 276.7 us), hence the flag.
+#ifndef GSR_CFG_FR_STAGE_OUT
+#define GSR_CFG_FR_STAGE_OUT 1
+#endif
+constexpr int GSR_FR_TILE_BYTES = GSR_RGW * GSR_RGH * 3 * 4;
+template <bool WINDOW>
+__device__ __forceinline__ void gsr_fr_write_unit(const GsrFwdArgs& p, uint32_t tile, int lane, int ux, int uy, int bx,
+                                                  int by, const float (&v)[2][2][3]) {
+  const bool over = (p.flags & 1u) != 0, chw = (p.flags & 2u) != 0, u8 = (p.flags & 4u) != 0, bgr = (p.flags & 8u) != 0;
+  const int wi0 = ux * GSR_RGW + bx, hi0 = uy * GSR_RGH + by;
+  const size_t plane = (size_t)p.h * p.w;
+  if (GSR_CFG_FR_STAGE_OUT && !WINDOW && (ux + 1) * GSR_RGW <= p.w && (uy + 1) * GSR_RGH <= p.h &&
+      (reinterpret_cast<uintptr_t>(p.img) & 15u) == 0) {
+    if (u8 && (p.w & 15) == 0) {
+      // bytes of the tile: [row][pixel][channel], 48 per row; a lane's row piece is 6 bytes at an even offset
+#pragma unroll
+      for (int yy = 0; yy < 2; ++yy) {
+        uint32_t b[6];
+#pragma unroll
+        for (int xx = 0; xx < 2; ++xx)
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) b[xx * 3 + (bgr ? 2 - ch : ch)] = gsr_to_u8(v[yy][xx][ch]);
+        const uint32_t a = tile + ((by + yy) * GSR_RGW + bx) * 3;
+        gsr_sts16(a, b[0] | (b[1] << 8));
+        gsr_sts16(a + 2, b[2] | (b[3] << 8));
+        gsr_sts16(a + 4, b[4] | (b[5] << 8));
+      }
+      __syncwarp();
+      if (lane < GSR_RGH * 3) {  // 24 x 16 bytes
+        const int row = lane / 3, part = lane - row * 3;
+        uint4 q;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(tile + lane * 16) : "memory");
+        unsigned char* o8 = reinterpret_cast<unsigned char*>(p.img) + ((size_t)(uy * GSR_RGH + row) * p.w + ux * GSR_RGW) * 3;
+        *reinterpret_cast<uint4*>(o8 + part * 16) = q;
+      }
+      __syncwarp();
+      return;
+    }
+    if (over && !chw && !u8 && (p.flags & 16u) != 0 && (p.w & 3) == 0) {  // GSR_FLAG_ROW_STORES
+      // floats of the tile: [row][pixel][channel], 48 per row; a lane's row piece is 6 floats, 8-byte aligned
+#pragma unroll
+      for (int yy = 0; yy < 2; ++yy) {
+        const uint32_t a = tile + ((by + yy) * GSR_RGW + bx) * 12;
+        asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(v[yy][0][0]), "f"(v[yy][0][1]) : "memory");
+        asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a + 8), "f"(v[yy][0][2]), "f"(v[yy][1][0]) : "memory");
+        asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a + 16), "f"(v[yy][1][1]), "f"(v[yy][1][2]) : "memory");
+      }
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {  // 96 x 16 bytes, 12 per region row
+        const int i = lane + 32 * j, row = i / 12, part = i - row * 12;
+        float4 q;  // (volatile + memory clobber: ordered after the staging stores, unlike gsr_lds128)
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(tile + i * 16) : "memory");
+        float* o = p.img + ((size_t)(uy * GSR_RGH + row) * p.w + ux * GSR_RGW) * 3;
+        *reinterpret_cast<float4*>(o + part * 4) = q;
+      }
+      __syncwarp();
+      return;
+    }
+  }
+#pragma unroll
+  for (int yy = 0; yy < 2; ++yy) {
+    if (!WINDOW && !over && !chw && !u8 && (p.w & 1) == 0) {
+      // accumulate into an (h,w,3) image of even width: the lane's two pixels of this row are six contiguous
+      // floats at an 8-byte aligned address (wi0 is even) -- three vector reductions instead of six scalar ones
+      if (hi0 + yy < p.h && wi0 < p.w) {  // (w even, wi0 even: both pixels of the pair are inside)
+        float* o = p.img + ((size_t)(hi0 + yy) * p.w + wi0) * 3;
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(o), "f"(v[yy][0][0]), "f"(v[yy][0][1]) : "memory");
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(o + 2), "f"(v[yy][0][2]), "f"(v[yy][1][0]) : "memory");
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(o + 4), "f"(v[yy][1][1]), "f"(v[yy][1][2]) : "memory");
+      }
+      continue;
+    }
+#pragma unroll
+    for (int xx = 0; xx < 2; ++xx) {
+      const int hi = hi0 + yy, wi = wi0 + xx;
+      if (WINDOW) {
+        if (gsr_fwd_writable(p, hi, wi)) {
+          float* o = gsr_fwd_pixel(p, hi, wi);
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            if (over) o[ch * p.chan_stride] = v[yy][xx][ch];
+            else atomicAdd(o + ch * p.chan_stride, v[yy][xx][ch]);
+          }
+        }
+      } else if (hi < p.h && wi < p.w) {
+        const size_t pix = (size_t)hi * p.w + wi;
+        if (u8) {  // fused post-processing: clamp, x255, round-half-even, uint8 (h,w,3)
+          unsigned char* o8 = reinterpret_cast<unsigned char*>(p.img) + pix * 3;
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) o8[bgr ? 2 - ch : ch] = gsr_to_u8(v[yy][xx][ch]);
+        } else {
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            float* o = chw ? p.img + ch * plane + pix : p.img + pix * 3 + ch;
+            if (over) *o = v[yy][xx][ch];
+            else atomicAdd(o, v[yy][xx][ch]);
+          }
+        }
+      }
+    }
+  }
+}
+
 // WINDOW = false: the plain (h,w,3) / (3,h,w) image, addressed with compile-time-simple arithmetic;
 // WINDOW = true: the general strided destination with clip rectangles (gsr_forward_window).
 template <bool WINDOW>
@@ -605,7 +718,7 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
   const uint32_t list_c = list_w + cell * GSR_FR_LIST;           // this lane's cell
   const uint32_t box_s = gsr_smem_addr(&sm.box[warp][0][0]);
   const uint2* box_w = &sm.box[warp][0][0];
-  const bool over = (p.flags & 1u) != 0, chw = (p.flags & 2u) != 0, u8 = (p.flags & 4u) != 0, bgr = (p.flags & 8u) != 0;
+  const uint32_t tile_s = gsr_smem_addr(&sm.tile[warp][0]);
   const int total_warps = gridDim.x * GSR_FR_WARPS;
 
   // the null record of both stages (slot CH): zero conic and colour, adds exactly 0
@@ -801,12 +914,9 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
     slow_bc = slow_bn;
     if (!last) continue;
 
-    // ---- unit finished: write out.  Plain stores when the image is overwritten; fire-and-forget
-    // reductions (RED) when the call accumulates into the caller's image (the reference's
-    // contract): no read, no latency.
+    // ---- unit finished: write out
     {
       const int uy = uA / p.nrx, ux = uA - uy * p.nrx;
-      const int wi0 = ux * GSR_RGW + bx, hi0 = uy * GSR_RGH + by;
       float v[2][2][3];
       gsr_upk(r0, v[0][0][0], v[0][1][0]);
       gsr_upk(g0, v[0][0][1], v[0][1][1]);
@@ -814,50 +924,7 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
       gsr_upk(r1, v[1][0][0], v[1][1][0]);
       gsr_upk(g1, v[1][0][1], v[1][1][1]);
       gsr_upk(b1, v[1][0][2], v[1][1][2]);
-      const size_t plane = (size_t)p.h * p.w;
-#pragma unroll
-      for (int yy = 0; yy < 2; ++yy) {
-        if (!WINDOW && !over && !chw && !u8 && (p.w & 1) == 0) {
-          // accumulate into an (h,w,3) image of even width: the lane's two pixels of this row are six contiguous
-          // floats at an 8-byte aligned address (wi0 is even) -- three vector reductions instead of six scalar ones
-          if (hi0 + yy < p.h && wi0 < p.w) {  // (w even, wi0 even: both pixels of the pair are inside)
-            float* o = p.img + ((size_t)(hi0 + yy) * p.w + wi0) * 3;
-            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(o), "f"(v[yy][0][0]), "f"(v[yy][0][1]) : "memory");
-            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(o + 2), "f"(v[yy][0][2]), "f"(v[yy][1][0]) : "memory");
-            asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(o + 4), "f"(v[yy][1][1]), "f"(v[yy][1][2]) : "memory");
-          }
-          continue;
-        }
-#pragma unroll
-        for (int xx = 0; xx < 2; ++xx) {
-          const int hi = hi0 + yy, wi = wi0 + xx;
-          if (WINDOW) {
-            if (gsr_fwd_writable(p, hi, wi)) {
-              float* o = gsr_fwd_pixel(p, hi, wi);
-#pragma unroll
-              for (int ch = 0; ch < 3; ++ch) {
-                if (over) o[ch * p.chan_stride] = v[yy][xx][ch];
-                else atomicAdd(o + ch * p.chan_stride, v[yy][xx][ch]);
-              }
-            }
-          } else if (hi < p.h && wi < p.w) {
-            const size_t pix = (size_t)hi * p.w + wi;
-            if (u8) {  // fused post-processing: clamp, x255, round-half-even, uint8 (h,w,3)
-              unsigned char* o8 = reinterpret_cast<unsigned char*>(p.img) + pix * 3;
-#pragma unroll
-              for (int ch = 0; ch < 3; ++ch)
-                o8[bgr ? 2 - ch : ch] = gsr_to_u8(v[yy][xx][ch]);
-            } else {
-#pragma unroll
-              for (int ch = 0; ch < 3; ++ch) {
-                float* o = chw ? p.img + ch * plane + pix : p.img + pix * 3 + ch;
-                if (over) *o = v[yy][xx][ch];
-                else atomicAdd(o, v[yy][xx][ch]);
-              }
-            }
-          }
-        }
-      }
+      gsr_fr_write_unit<WINDOW>(p, tile_s, lane, ux, uy, bx, by, v);
     }
     // ---- advance: B becomes A, C becomes B, the next claimed unit becomes C
     uA = uB;

@@ -50,6 +50,7 @@ struct GsrWsSmem {
   GsrWsStage st[GSR_WS_PAIRS][GSR_WS_STAGES];
   unsigned long long full[GSR_WS_PAIRS][GSR_WS_STAGES];
   unsigned long long empty[GSR_WS_PAIRS][GSR_WS_STAGES];
+  float4 tile[GSR_WS_PAIRS][GSR_RGW * GSR_RGH * 3 / 4];  // write-out staging of the consumer warps
 };
 static_assert(GSR_FR_LW == 4 || sizeof(GsrWsSmem) + 1024 < 65536, "cell lists hold 16-bit shared-memory addresses");
 
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(GSR_WS_THREADS, GSR_CFG_WS_MIN_CTAS) gsr_forwa
 #if GSR_CFG_WS_MIN_CTAS == 4
   asm volatile("setmaxnreg.inc.sync.aligned.u32 " GSR_STR(GSR_CFG_WS_CONS_REGS) ";");
 #endif
-  const bool over = (p.flags & 1u) != 0, chw = (p.flags & 2u) != 0, u8 = (p.flags & 4u) != 0, bgr = (p.flags & 8u) != 0;
+  const uint32_t tile_s = gsr_smem_addr(&sm.tile[pair][0]);
   gsr_f2 nx2 = gsr_pk(0.f, 0.f), ny2 = nx2;
   gsr_f2 r0 = gsr_pk(0.f, 0.f), g0 = r0, b0 = r0, r1 = r0, g1 = r0, b1 = r0;
   for (int it = 0;; ++it) {
@@ -301,46 +302,6 @@ __global__ void __launch_bounds__(GSR_WS_THREADS, GSR_CFG_WS_MIN_CTAS) gsr_forwa
     gsr_upk(r1, v[1][0][0], v[1][1][0]);
     gsr_upk(g1, v[1][0][1], v[1][1][1]);
     gsr_upk(b1, v[1][0][2], v[1][1][2]);
-    const size_t plane = (size_t)p.h * p.w;
-#pragma unroll
-    for (int yy = 0; yy < 2; ++yy) {
-      if (!WINDOW && !over && !chw && !u8 && (p.w & 1) == 0) {
-        if (hi0 + yy < p.h && wi0 < p.w) {
-          float* o = p.img + ((size_t)(hi0 + yy) * p.w + wi0) * 3;
-          asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(o), "f"(v[yy][0][0]), "f"(v[yy][0][1]) : "memory");
-          asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(o + 2), "f"(v[yy][0][2]), "f"(v[yy][1][0]) : "memory");
-          asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(o + 4), "f"(v[yy][1][1]), "f"(v[yy][1][2]) : "memory");
-        }
-        continue;
-      }
-#pragma unroll
-      for (int xx = 0; xx < 2; ++xx) {
-        const int hi = hi0 + yy, wi = wi0 + xx;
-        if (WINDOW) {
-          if (gsr_fwd_writable(p, hi, wi)) {
-            float* o = gsr_fwd_pixel(p, hi, wi);
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-              if (over) o[ch * p.chan_stride] = v[yy][xx][ch];
-              else atomicAdd(o + ch * p.chan_stride, v[yy][xx][ch]);
-            }
-          }
-        } else if (hi < p.h && wi < p.w) {
-          const size_t pix = (size_t)hi * p.w + wi;
-          if (u8) {
-            unsigned char* o8 = reinterpret_cast<unsigned char*>(p.img) + pix * 3;
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) o8[bgr ? 2 - ch : ch] = gsr_to_u8(v[yy][xx][ch]);
-          } else {
-#pragma unroll
-            for (int ch = 0; ch < 3; ++ch) {
-              float* o = chw ? p.img + ch * plane + pix : p.img + pix * 3 + ch;
-              if (over) *o = v[yy][xx][ch];
-              else atomicAdd(o, v[yy][xx][ch]);
-            }
-          }
-        }
-      }
-    }
+    gsr_fr_write_unit<WINDOW>(p, tile_s, lane, ux, uy, bx, by, v);
   }
 }

@@ -123,10 +123,12 @@ def band_rows(h: int, rank: int, world: int):
     return starts[rank], starts[rank + 1] - starts[rank]
 
 
-def _band_forward_cuda(sigmas, coords, colors, h, w, row0, rows, dmax):
+def _band_forward_cuda(sigmas, coords, colors, h, w, row0, rows, dmax, out=None):
+    """Renders rows [row0, row0 + rows) into `out` (a contiguous (rows,w,3) view, e.g. the band's rows of the
+    full image: no band buffer, no copy) or into a fresh tensor; every pixel is written (GSR_FLAG_OVERWRITE)."""
     from . import gscuda
 
-    band = torch.zeros(rows, w, 3, dtype=torch.float32, device=sigmas.device)
+    band = out if out is not None else torch.empty(rows, w, 3, dtype=torch.float32, device=sigmas.device)
     gscuda.gs_render_band(sigmas, coords, colors, band, sigmas.shape[0], h, w, 3, row0, rows, dmax,
                           flags=1)  # GSR_FLAG_OVERWRITE
     return band
@@ -182,7 +184,8 @@ def render_image_bands_peer(sigmas, coords, colors, h: int, w: int, dmax: float,
         ws = gscuda.workspace(sigmas.shape[0], max(rows, 2), w, sigmas.device)
         _PEER_VIEWS[(key, slot)] = (mine, band, hdl, row0, rows, ws, sigmas.shape[0])
     if rows > 0:
-        gscuda.gs_render_band(sigmas, coords, colors, band, sigmas.shape[0], h, w, 3, row0, rows, dmax, flags=1,
+        gscuda.gs_render_band(sigmas, coords, colors, band, sigmas.shape[0], h, w, 3, row0, rows, dmax,
+                              flags=0x1 | 0x10,  # GSR_FLAG_OVERWRITE | GSR_FLAG_ROW_STORES: 16-byte packets over NVLink
                               workspace_buf=ws)
     # Stream-ordered barrier (a kernel on the current stream that signals every peer and waits for all of them):
     # behind it, every rank's stores of this call have landed; no host synchronisation, the call returns at once.
@@ -200,12 +203,18 @@ def render_image_bands(sigmas, coords, colors, h: int, w: int, dmax: float, *, r
     The band shapes follow from (h, world) alone, so nothing but pixels is exchanged: every rank
     renders its band and the bands -- contiguous row blocks of the (h,w,3) result -- are gathered
     with ONE in-place all-gather when they are equal-sized, else one broadcast / send per band."""
+    direct = render_band is None  # the CUDA band kernel writes its rows straight into the full image
     render_band = render_band or _band_forward_cuda
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return render_band(sigmas, coords, colors, h, w, 0, h, dmax)
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     bands = [band_rows(h, r, world) for r in range(world)]
     row0, rows = bands[rank]
+    if direct and gather_to is None:
+        full = torch.empty(h, w, 3, dtype=torch.float32, device=sigmas.device)
+        if rows > 0:
+            _band_forward_cuda(sigmas, coords, colors, h, w, row0, rows, dmax, out=full[row0:row0 + rows])
+        return _gather_bands(full, bands, rank, group)
     mine = render_band(sigmas, coords, colors, h, w, row0, rows, dmax) if rows > 0 else None
     glob = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
     if gather_to is not None:  # point-to-point: only the stitching rank holds the image
@@ -225,6 +234,14 @@ def render_image_bands(sigmas, coords, colors, h: int, w: int, dmax: float, *, r
     full = torch.empty(h, w, 3, dtype=torch.float32, device=sigmas.device)
     if rows > 0:
         full[row0:row0 + rows].copy_(mine)
+    return _gather_bands(full, bands, rank, group)
+
+
+def _gather_bands(full, bands, rank, group):
+    """All ranks end up with every band of `full` (each rank has filled its own): ONE in-place all-gather when the
+    bands are equal-sized, else one broadcast per band."""
+    glob = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    row0, rows = bands[rank]
     if all(n == bands[0][1] for _, n in bands):
         dist.all_gather_into_tensor(full, full[row0:row0 + rows], group=group)  # in place: band r at offset r
     else:

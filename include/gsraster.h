@@ -85,6 +85,12 @@ typedef enum gsr_status {
  * inference_paper.py:136-138 fused into the write-out: no fp32 image, a quarter of the bytes. */
 #define GSR_FLAG_U8 0x4u
 #define GSR_FLAG_BGR 0x8u       /* with GSR_FLAG_U8: channel order b, g, r (cv2.imwrite's; :137) */
+/* forward, with GSR_FLAG_OVERWRITE, (h,w,3) fp32 layout, w % 4 == 0, img 16-byte aligned: finished 16x8-pixel
+ * regions leave the SM as 128-bit stores of whole region rows (192 contiguous bytes) staged through shared
+ * memory, instead of 4-byte stores.  For an image in ANOTHER GPU's memory (peer mapping over NVLink): 16-byte
+ * write packets.  Same pixels either way; ~1 % slower on a local image, hence opt-in.  Ignored where it does not
+ * apply.  (The uint8 image of GSR_FLAG_U8 always leaves that way when w % 16 == 0.) */
+#define GSR_FLAG_ROW_STORES 0x10u
 
 int gsr_version(void);
 const char* gsr_status_string(int status);

@@ -153,3 +153,24 @@ def test_window_render_touches_only_its_clip_rectangles():
     assert float((canvas - want).abs().max()) <= 2e-6
     with pytest.raises(RuntimeError):
         gscuda.gs_render_window(s, c, k, canvas, 70 * 64, 64, 1, 80 * 64, [], s.shape[0], 48, 40, 0.2)  # leaves dst
+
+
+@pytest.mark.parametrize("h,w", [(64, 48), (72, 100), (40, 70), (33, 64)])
+def test_row_stores_write_the_same_pixels(h, w):
+    """GSR_FLAG_ROW_STORES (finished regions leave as 128-bit stores of whole region rows, staged through shared
+    memory: what render_image_bands_peer uses for an image in another GPU's memory) changes how pixels are stored,
+    not their values: bit-identical to the plain overwrite, incl. partial edge regions and widths that are not a
+    multiple of 4 (where the flag must fall back)."""
+    s, c, k = _field(h, w, 600, seed=h + w)
+    a = torch.full((h, w, 3), 7.0, device=DEV)
+    b = torch.full((h, w, 3), -3.0, device=DEV)
+    gscuda.gs_render(s, c, k, a, s.shape[0], h, w, 3, 0.3, flags=0x1)
+    gscuda.gs_render(s, c, k, b, s.shape[0], h, w, 3, 0.3, flags=0x1 | 0x10)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    # the uint8 write-out takes the staged path whenever w % 16 == 0 and the per-pixel path otherwise
+    u8 = torch.full((h, w, 3), 77, dtype=torch.uint8, device=DEV)
+    gscuda.gs_render_u8(s, c, k, u8, s.shape[0], h, w, 0.3)
+    want = (a.clamp(0, 1) * 255.0).round().to(torch.int16)
+    diff = (u8.to(torch.int16) - want).abs()
+    assert int(diff.max()) <= 1 and float((diff > 0).float().mean()) < 1e-3

@@ -8,9 +8,7 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "variants")
 VARIANTS = {
     "base": [],
-    "c4": ["GSR_CFG_FR_MIN_CTAS=4"],
-    "c5_lw4": ["GSR_CFG_FR_LW=4"],
-    "c4_lw4": ["GSR_CFG_FR_LW=4", "GSR_CFG_FR_MIN_CTAS=4"],
+    "nostage": ["GSR_CFG_FR_STAGE_OUT=0"],
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
