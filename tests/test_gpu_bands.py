@@ -159,15 +159,15 @@ def test_window_render_touches_only_its_clip_rectangles():
 def test_row_stores_write_the_same_pixels(h, w):
     """GSR_FLAG_ROW_STORES (finished regions leave as 128-bit stores of whole region rows, staged through shared
     memory: what render_image_bands_peer uses for an image in another GPU's memory) changes how pixels are stored,
-    not their values: bit-identical to the plain overwrite, incl. partial edge regions and widths that are not a
-    multiple of 4 (where the flag must fall back)."""
+    not their values: equal to the plain overwrite up to the summation order of two runs, incl. partial edge
+    regions and widths that are not a multiple of 4 (where the flag must fall back)."""
     s, c, k = _field(h, w, 600, seed=h + w)
     a = torch.full((h, w, 3), 7.0, device=DEV)
     b = torch.full((h, w, 3), -3.0, device=DEV)
     gscuda.gs_render(s, c, k, a, s.shape[0], h, w, 3, 0.3, flags=0x1)
     gscuda.gs_render(s, c, k, b, s.shape[0], h, w, 3, 0.3, flags=0x1 | 0x10)
     torch.cuda.synchronize()
-    assert torch.equal(a, b)
+    assert float((a - b).abs().max()) <= 2 * SELF_TOL
     # the uint8 write-out takes the staged path whenever w % 16 == 0 and the per-pixel path otherwise
     u8 = torch.full((h, w, 3), 77, dtype=torch.uint8, device=DEV)
     gscuda.gs_render_u8(s, c, k, u8, s.shape[0], h, w, 0.3)
