@@ -13,6 +13,7 @@ GSR_FLAG_CHW = 0x2
 GSR_FLAG_U8 = 0x4
 GSR_FLAG_BGR = 0x8
 GSR_FLAG_ROW_STORES = 0x10
+GSR_FLAG_DETERMINISTIC = 0x20
 DEFAULT_KSIGMA = 5.0
 EXACT_KSIGMA = float("inf")
 
@@ -79,6 +80,9 @@ SIGNATURES = {
                                                 ctypes.POINTER(_f), ctypes.POINTER(_f), _f, _f, _vp, _sz, _vp]),
     "gsr_frontend_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _vp, _sz, _vp]),
     "gsr_frontend_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _vp, _sz, _vp]),
+    "gsr_l1_crop_workspace_bytes": (_sz, []),
+    "gsr_l1_crop_loss": (_i, [_vp, ctypes.POINTER(ctypes.c_longlong), _vp, ctypes.POINTER(ctypes.c_longlong), _vp, _vp,
+                              _i, _i, _i, ctypes.POINTER(_i), _f, _i, _vp, _sz, _vp]),
 }
 
 # CPU test hooks (include/gsraster_test.h)

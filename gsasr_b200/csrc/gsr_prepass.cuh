@@ -45,6 +45,7 @@ constexpr int GSR_STAT_EXT_X = 0, GSR_STAT_EXT_Y = 1, GSR_STAT_OVERFLOW = 2, GSR
 // regions on average, one of the x8 head 12.3 (5 sigma = 16.7 px on average, 33 px at most); 4 bytes per slot
 constexpr int GSR_ENTRIES_PER_GAUSSIAN = 28;
 constexpr int GSR_STAT_KSIGMA = 6;                   // effective k-sigma of the home-bin set-up (float bits), for the backward
+constexpr int GSR_STAT_UNSORTED = 7;                 // deterministic mode: a bucket was too long to be sorted
 constexpr int GSR_STAT_UNIT = 4, GSR_STAT_DONE = 5;  // work counter / finished-warp counter of the raster kernel
 
 struct GsrWorkspace {
@@ -895,3 +896,87 @@ __device__ __noinline__ void gsr_rb_walk_generic(uint2 (*list)[32], int lane, co
   }
   gsr_bucket_flush<32>(&list[0][0], lane, lane, n, cnt, ent, cap, overflow);
 }
+
+// ---- deterministic mode (GSR_FLAG_DETERMINISTIC) -------------------------------------------------------------
+// Bucket ranks come from atomics, so the ORDER of a bucket's entries -- and with it the order in which a pixel's
+// terms are added in fp32 -- differs from run to run (as do the reference's atomicAdds).  Sorting every bucket by
+// Gaussian index makes buckets, chunks and cell lists functions of the input alone: the forward becomes
+// bit-reproducible (the backward already is: one warp owns a Gaussian, fixed sweep order, no atomics).  Indices
+// are unique within a bucket, so the rank of an entry is the number of smaller ones: counted against the whole
+// bucket in shared memory (four keys per LDS.128), no exchange network.  One warp per bucket; buckets longer than
+// GSR_SORT_MAX entries are sorted by a whole CTA through the bucket itself (rank pass, barrier, write pass).
+constexpr int GSR_SORT_WARPS = 4;
+constexpr int GSR_SORT_MAX = 1024;  // entries per warp-sorted bucket (4 KB of shared memory per warp)
+
+__global__ void __launch_bounds__(32 * GSR_SORT_WARPS)
+gsr_bucket_sort_kernel(uint32_t* __restrict__ entries, const int* __restrict__ reg_count, int cap, int nreg,
+                       const int* guard, int want) {
+  if (gsr_guard_skip(guard, want)) return;
+  __shared__ __align__(16) uint32_t buf[GSR_SORT_WARPS][GSR_SORT_MAX + 4];   // entries
+  __shared__ __align__(16) uint32_t kbuf[GSR_SORT_WARPS][GSR_SORT_MAX + 4];  // keys: index << 9 (flag bits shifted out)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* b = buf[warp];
+  uint32_t* kb = kbuf[warp];
+  constexpr int SH = 32 - GSR_ENT_MASK_SHIFT;
+  for (int r = blockIdx.x * GSR_SORT_WARPS + warp; r < nreg; r += gridDim.x * GSR_SORT_WARPS) {
+    const int n = min(__ldg(reg_count + r), cap);
+    if (n < 2 || n > GSR_SORT_MAX) continue;  // (longer buckets: gsr_bucket_sort_long_kernel)
+    uint32_t* e = entries + (size_t)r * cap;
+    const int n4 = (n + 3) & ~3;
+    for (int i = lane; i < n4; i += 32) {
+      const uint32_t v = i < n ? e[i] : 0xffffffffu;
+      b[i] = v;
+      kb[i] = i < n ? v << SH : 0xffffffffu;  // sentinel keys are never smaller
+    }
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      const uint32_t key = kb[i];
+      int rank = 0;
+      for (int j = 0; j < n4; j += 4) {
+        const uint4 q = *reinterpret_cast<const uint4*>(kb + j);
+        rank += (q.x < key) + (q.y < key) + (q.z < key) + (q.w < key);
+      }
+      e[rank] = b[i];
+    }
+    __syncwarp();
+  }
+}
+
+// Buckets longer than GSR_SORT_MAX (dense or clustered fields): one CTA per bucket, keys read from the bucket
+// itself (L1/L2), ranks kept in registers until every thread has finished reading.
+constexpr int GSR_SORT_LONG_PER_THREAD = 32;  // 256 threads x 32 = 8192 entries; longer buckets stay unsorted
+__global__ void __launch_bounds__(256)
+gsr_bucket_sort_long_kernel(uint32_t* __restrict__ entries, const int* __restrict__ reg_count, int cap, int nreg,
+                            const int* guard, int want, int* unsorted) {
+  if (gsr_guard_skip(guard, want)) return;
+  for (int r = blockIdx.x; r < nreg; r += gridDim.x) {
+    const int n = min(__ldg(reg_count + r), cap);
+    if (n <= GSR_SORT_MAX) continue;
+    if (n > 256 * GSR_SORT_LONG_PER_THREAD) {
+      if (threadIdx.x == 0) *unsorted = 1;
+      continue;
+    }
+    uint32_t* e = entries + (size_t)r * cap;
+    uint32_t v[GSR_SORT_LONG_PER_THREAD];
+    int rank[GSR_SORT_LONG_PER_THREAD];
+#pragma unroll 1
+    for (int t = 0; t < GSR_SORT_LONG_PER_THREAD; ++t) {
+      const int i = threadIdx.x + 256 * t;
+      v[t] = 0u;
+      rank[t] = 0;
+      if (i < n) {
+        v[t] = e[i];
+        const uint32_t key = v[t] & GSR_ENT_INDEX;
+        int rk = 0;
+        for (int j = 0; j < n; ++j) rk += ((*(const volatile uint32_t*)(e + j)) & GSR_ENT_INDEX) < key;
+        rank[t] = rk;
+      }
+    }
+    __syncthreads();  // every read of the bucket is done
+#pragma unroll 1
+    for (int t = 0; t < GSR_SORT_LONG_PER_THREAD; ++t)
+      if (threadIdx.x + 256 * t < n) e[rank[t]] = v[t];
+    __syncthreads();
+  }
+}
+

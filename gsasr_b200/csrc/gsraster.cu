@@ -4,6 +4,7 @@
 #include "../../include/gsraster.h"
 #include "gsr_backward.cuh"
 #include "gsr_frontend.cuh"
+#include "gsr_loss.cuh"
 #include <atomic>
 #include <cstdlib>
 
@@ -298,9 +299,28 @@ static int gsr_prepare_forward(const float* sigmas, const float* coords, const f
   return gsr_run_bins(sigmas, coords, colors, s, h, w, dmax, keff, ws, ws.stats + GSR_STAT_OVERFLOW, 1, st);
 }
 
+// GSR_FLAG_DETERMINISTIC: every bucket sorted by Gaussian index before it is rasterised (idempotent: a prepared
+// workspace may be rasterised any number of times).
+static int gsr_sort_buckets(const GsrWorkspace& ws, cudaStream_t st) {
+  int nsm = 0;
+  const int rc = gsr_sm_count(&nsm);
+  if (rc) return rc;
+  const int* guard = ws.stats + GSR_STAT_OVERFLOW;
+  const int want = (ws.nreg + GSR_SORT_WARPS - 1) / GSR_SORT_WARPS, cap = nsm * 16;
+  gsr_bucket_sort_kernel<<<want < cap ? want : cap, 32 * GSR_SORT_WARPS, 0, st>>>(ws.entries, ws.reg_count, ws.reg_cap,
+                                                                                  ws.nreg, guard, 0);
+  if (ws.reg_cap > GSR_SORT_MAX)  // only then can a bucket be longer than the warp sort takes
+    gsr_bucket_sort_long_kernel<<<ws.nreg < nsm * 8 ? ws.nreg : nsm * 8, 256, 0, st>>>(
+        ws.entries, ws.reg_count, ws.reg_cap, ws.nreg, guard, 0, ws.stats + GSR_STAT_UNSORTED);
+  GSR_CUDA(cudaGetLastError());
+  return GSR_OK;
+}
+
 static int gsr_raster_forward(const GsrWorkspace& ws, float* img, int h, int w, float keff,
                               uint32_t flags, cudaStream_t st) {
-  int rc = gsr_launch_forward_region(ws, img, h, w, keff, flags, st);
+  int rc = (flags & GSR_FLAG_DETERMINISTIC) ? gsr_sort_buckets(ws, st) : GSR_OK;
+  if (rc) return rc;
+  rc = gsr_launch_forward_region(ws, img, h, w, keff, flags, st);
   if (rc) return rc;
   return gsr_launch_forward_bins(ws, img, h, w, keff, flags, st);
 }
@@ -1034,4 +1054,51 @@ extern "C" void gsr_host_geometry(int* tile_w, int* tile_h, int* bin, int* regio
   *bin = GSR_BIN;
   *region = GSR_REGION;
   *large_px = GSR_LARGE_PX;
+}
+
+// ---- fused crop + L1 loss + gradient (gsasr_model.py:212-234) ---------------------------------------------------
+constexpr int GSR_LOSS_MAX_GRID = 148 * 8;
+extern "C" size_t gsr_l1_crop_workspace_bytes(void) { return 256 + (size_t)GSR_LOSS_MAX_GRID * sizeof(double); }
+
+extern "C" int gsr_l1_crop_loss(const float* sr, const long long* sr_strides, const float* gt,
+                                const long long* gt_strides, float* grad, float* loss, int batch, int hmax,
+                                int wmax, const int* hw_host, float weight, int accumulate, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  if (!sr || !gt || !grad || !loss || !sr_strides || !gt_strides || !hw_host) return GSR_ERR_NULL_POINTER;
+  if (batch < 0 || hmax < 1 || wmax < 1 || hmax > GSR_MAX_DIM || wmax > GSR_MAX_DIM) return GSR_ERR_BAD_SHAPE;
+  int rc = gsr_check_ws(workspace, workspace_bytes, gsr_l1_crop_workspace_bytes());
+  if (rc) return rc;
+  for (int b = 0; b < batch; ++b)
+    if (hw_host[2 * b] < 1 || hw_host[2 * b] > hmax || hw_host[2 * b + 1] < 1 || hw_host[2 * b + 1] > wmax)
+      return GSR_ERR_BAD_SHAPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  GSR_CUDA(cudaMemsetAsync(workspace, 0, 256, st));  // the finished-CTA counter
+  if (batch == 0 && !accumulate) GSR_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  for (int b0 = 0; b0 < batch; b0 += GSR_LOSS_MAX_BATCH) {
+    const int nb = batch - b0 < GSR_LOSS_MAX_BATCH ? batch - b0 : GSR_LOSS_MAX_BATCH;
+    GsrLossArgs a;
+    a.sr = sr + (long long)b0 * sr_strides[0];
+    a.gt = gt + (long long)b0 * gt_strides[0];
+    a.grad = grad + (long long)b0 * sr_strides[0];
+    a.sr_n = sr_strides[0], a.sr_c = sr_strides[1], a.sr_h = sr_strides[2], a.sr_w = sr_strides[3];
+    a.gt_n = gt_strides[0], a.gt_c = gt_strides[1], a.gt_h = gt_strides[2], a.gt_w = gt_strides[3];
+    a.batch = nb;
+    a.hmax = hmax;
+    a.wmax = wmax;
+    a.weight = weight;
+    a.counter = (unsigned int*)workspace;
+    a.partial = (double*)((char*)workspace + 256);
+    a.loss = loss;
+    a.accumulate = accumulate || b0 > 0;
+    for (int b = 0; b < nb; ++b) {
+      a.hw[b][0] = (short)hw_host[2 * (b0 + b)];
+      a.hw[b][1] = (short)hw_host[2 * (b0 + b) + 1];
+    }
+    const long long total = (long long)nb * hmax * wmax;
+    const long long want = (total + GSR_LOSS_THREADS - 1) / GSR_LOSS_THREADS;
+    const int grid = (int)(want < GSR_LOSS_MAX_GRID ? want : GSR_LOSS_MAX_GRID);
+    gsr_l1_crop_kernel<<<grid, GSR_LOSS_THREADS, 0, st>>>(a);
+  }
+  GSR_CUDA(cudaGetLastError());
+  return GSR_OK;
 }

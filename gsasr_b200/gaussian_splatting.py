@@ -261,7 +261,7 @@ def generate_2D_gaussian_splatting_step(sr_size, gs_parameters, scale, scale_mod
     if not cuda_rendering:  # the reference's PyTorch renderer, on request (:210-212)
         return _sample(_python_renderer(gs_parameters, sr_size, scale, scale_modify, default_step_size, mode),
                        sample_coords)
-    if fused:
+    if fused and not _gs.get_deterministic():  # (the fused entry points carry no flags: deterministic mode renders unfused)
         step_size = float(_step_size(scale, scale_modify, default_step_size, mode))
         final_image = _FusedFrontend.apply(gs_parameters, int(sr_size[0]), int(sr_size[1]), step_size,
                                            _resolve_dmax(if_dmax, dmax_mode, dmax, sr_size))
@@ -357,7 +357,7 @@ def generate_2D_gaussian_splatting_step_batch(sr_size, gs_parameters, scale, sca
         raise RuntimeError("gs_parameters must be (B,N,9)")
     b, n = gs_parameters.shape[:2]
     dm = _resolve_dmax(if_dmax, dmax_mode, dmax, sr_size)
-    if fused:
+    if fused and not _gs.get_deterministic():  # (the fused entry points carry no flags: deterministic mode renders unfused)
         step_size = float(_step_size(scale, scale_modify, default_step_size, mode))
         out = _FusedFrontendBatch.apply(gs_parameters, int(sr_size[0]), int(sr_size[1]), step_size, dm)
         return out.permute(0, 3, 1, 2)
@@ -389,7 +389,7 @@ def render_into_canvas(canvas, y0, x0, regions, sr_size, gs_parameters, scale, s
     if not clips:
         return
     dm = _resolve_dmax(if_dmax, dmax_mode, dmax, sr_size)
-    if fused:  # the library's fused front end (parity 1e-4) instead of ~15 elementwise torch kernels
+    if fused and not _gs.get_deterministic():  # (the fused entry points carry no flags: deterministic mode renders unfused)  # the library's fused front end (parity 1e-4) instead of ~15 elementwise torch kernels
         step_size = float(_step_size(scale, scale_modify, default_step_size, mode))
         _gs.frontend_render_window(gs_parameters.contiguous().float(), canvas, y0 * W + x0, W, 1, H * W, clips,
                                    h, w, step_size, dm, flags=_OVER)
@@ -488,7 +488,7 @@ def generate_2D_gaussian_splatting_step_batch_padded(sr_sizes, gs_parameters, sc
         dm = float(dmax)
     else:
         raise ValueError(f"dmax_mode-{dmax_mode} must be fix or dynamic")
-    if fused:
+    if fused and not _gs.get_deterministic():  # (the fused entry points carry no flags: deterministic mode renders unfused)
         hm = (max(h for h, _ in sizes) + 7) // 8 * 8 if hmax is None else int(hmax)
         wm = max(w for _, w in sizes) if wmax is None else int(wmax)
         out = _FusedFrontendBatchPadded.apply(gs_parameters, sizes, [default_step_size / float(sc) for sc in scales],

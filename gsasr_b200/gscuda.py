@@ -22,7 +22,7 @@ import torch
 from . import _lib
 
 __all__ = ["gs_render", "gs_render_backward", "gs_render_band", "gs_render_backward_band", "gs_render_batch",
-           "gs_render_backward_batch", "gs_render_batch_padded", "gs_render_backward_batch_padded", "gs_render_window", "frontend_render_window", "gs_render_u8", "set_ksigma", "get_ksigma"]
+           "gs_render_backward_batch", "gs_render_batch_padded", "gs_render_backward_batch_padded", "gs_render_window", "frontend_render_window", "gs_render_u8", "set_ksigma", "get_ksigma", "set_deterministic", "get_deterministic"]
 
 _ksigma = float(os.environ.get("GSR_KSIGMA", "0"))  # 0 -> library default (GSR_DEFAULT_KSIGMA)
 
@@ -36,6 +36,26 @@ def set_ksigma(k: float) -> None:
 
 def get_ksigma() -> float:
     return _ksigma
+
+
+_deterministic = os.environ.get("GSR_DETERMINISTIC", "0") not in ("", "0")
+
+
+def set_deterministic(on: bool) -> None:
+    """Bit-reproducible forward renders (GSR_FLAG_DETERMINISTIC: every region list is sorted by Gaussian index
+    before it is rasterised, ~10 % slower).  The reference's atomicAdd accumulation (gs.cu:58-60) is not
+    reproducible run to run; neither is this library's default forward (in the last bits).  The backward always
+    is.  Also settable with GSR_DETERMINISTIC=1 in the environment."""
+    global _deterministic
+    _deterministic = bool(on)
+
+
+def get_deterministic() -> bool:
+    return _deterministic
+
+
+def _fwd_flags(flags) -> int:
+    return int(flags) | (_lib.GSR_FLAG_DETERMINISTIC if _deterministic else 0)
 
 
 def _check_input(t, name: str) -> None:
@@ -83,7 +103,7 @@ def gs_render(sigmas, coords, colors, rendered_img, s, h, w, c, dmax=float("inf"
     with torch.cuda.device(sigmas.device):
         ws = workspace_buf if workspace_buf is not None else workspace(s, h, w, sigmas.device)
         rc = L.gsr_forward(_ptr(sigmas), _ptr(coords), _ptr(colors), rendered_img.data_ptr(), s, h, w, c,
-                           float(dmax), float(_ksigma if ksigma is None else ksigma), int(flags),
+                           float(dmax), float(_ksigma if ksigma is None else ksigma), _fwd_flags(flags),
                            ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)
 
@@ -134,7 +154,7 @@ def gs_render_band(sigmas, coords, colors, band_img, s, h, w, c, row0, rows, dma
         ws = workspace_buf if workspace_buf is not None else workspace(s, rows, w, sigmas.device)
         rc = L.gsr_forward_band(_ptr(sigmas), _ptr(coords), _ptr(colors), band_img.data_ptr(), s, h, w, c,
                                 row0, rows, float(dmax), float(_ksigma if ksigma is None else ksigma),
-                                int(flags), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+                                _fwd_flags(flags), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)
 
 
@@ -193,7 +213,7 @@ def gs_render_batch(sigmas, coords, colors, rendered_imgs, dmax=float("inf"), *,
         ws = workspace_buf if workspace_buf is not None else workspace_batch(b, s, h, w, sigmas.device)
         rc = L.gsr_forward_batch_uniform(_ptr(sigmas), _ptr(coords), _ptr(colors), rendered_imgs.data_ptr(), b, s,
                                          h, w, 3, float(dmax), float(_ksigma if ksigma is None else ksigma),
-                                         int(flags), ws.data_ptr(), ws.numel(),
+                                         _fwd_flags(flags), ws.data_ptr(), ws.numel(),
                                          torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)
 
@@ -268,7 +288,7 @@ def gs_render_window(sigmas, coords, colors, dst, origin, row_stride, pix_stride
         ws = workspace_buf if workspace_buf is not None else workspace(s, h, w, sigmas.device)
         rc = L.gsr_forward_window(_ptr(sigmas), _ptr(coords), _ptr(colors), dst.data_ptr() + 4 * int(origin),
                                   win, s, h, w, 3, float(dmax), float(_ksigma if ksigma is None else ksigma),
-                                  int(flags), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+                                  _fwd_flags(flags), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)
 
 
@@ -285,7 +305,7 @@ def frontend_render_window(raw, dst, origin, row_stride, pix_stride, chan_stride
         ws = workspace(s, h, w, raw.device)
         rc = L.gsr_frontend_forward_window(_ptr(raw), mapped.data_ptr(), dst.data_ptr() + 4 * int(origin), win, s, h,
                                            w, float(step_size), float(dmax),
-                                           float(_ksigma if ksigma is None else ksigma), int(flags),
+                                           float(_ksigma if ksigma is None else ksigma), _fwd_flags(flags),
                                            ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)
 
@@ -309,7 +329,7 @@ def gs_render_u8(sigmas, coords, colors, out_u8, s, h, w, dmax=float("inf"), *, 
     with torch.cuda.device(sigmas.device):
         ws = workspace_buf if workspace_buf is not None else workspace(s, h, w, sigmas.device)
         rc = L.gsr_forward(_ptr(sigmas), _ptr(coords), _ptr(colors), out_u8.data_ptr(), s, h, w, 3, float(dmax),
-                           float(_ksigma if ksigma is None else ksigma), flags, ws.data_ptr(), ws.numel(),
+                           float(_ksigma if ksigma is None else ksigma), _fwd_flags(flags), ws.data_ptr(), ws.numel(),
                            torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)
 
@@ -360,7 +380,7 @@ def gs_render_batch_padded(sigmas, coords, colors, rendered_imgs, sizes, dmax=fl
     with torch.cuda.device(sigmas.device):
         ws = workspace_buf if workspace_buf is not None else workspace_batch_padded(b, s, hmax, wmax, sigmas.device)
         rc = L.gsr_forward_batch_padded(_ptr(sigmas), _ptr(coords), _ptr(colors), rendered_imgs.data_ptr(), b, s, hmax,
-                                        wmax, hw, dm_arr, dm, float(_ksigma if ksigma is None else ksigma), int(flags),
+                                        wmax, hw, dm_arr, dm, float(_ksigma if ksigma is None else ksigma), _fwd_flags(flags),
                                         ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)
 

@@ -91,6 +91,12 @@ typedef enum gsr_status {
  * write packets.  Same pixels either way; ~1 % slower on a local image, hence opt-in.  Ignored where it does not
  * apply.  (The uint8 image of GSR_FLAG_U8 always leaves that way when w % 16 == 0.) */
 #define GSR_FLAG_ROW_STORES 0x10u
+/* forward: bit-reproducible output.  The lists a region's pixels are summed from are filled with atomics, so
+ * the fp32 summation order -- like that of the reference's atomicAdd (gs.cu:58-60) -- differs from run to run in
+ * the last bits.  With this flag every list is sorted by Gaussian index first (HL: +~10 % time): the image is
+ * then a function of the inputs alone.  Holds while the region lists fit their buckets (no fallback to the
+ * home-bin kernel) and no bucket exceeds 8192 entries; the backward is always deterministic. */
+#define GSR_FLAG_DETERMINISTIC 0x20u
 
 int gsr_version(void);
 const char* gsr_status_string(int status);
@@ -259,6 +265,23 @@ int gsr_frontend_backward_batch_padded(const float* raw_params, const float* map
 int gsr_frontend_forward_window(const float* raw_params, float* mapped, float* origin, const gsr_window* win,
                                 int s, int h, int w, float step_size, float dmax, float ksigma,
                                 uint32_t flags, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The training loop's pixel loss, fused with its crop and its gradient (gsasr_model.py:212-234: F.pad to the
+ * batch's largest size, crop output and ground truth back to (h_b, w_b), L1Loss(reduction='mean') per sample,
+ * divided by the batch size):
+ *     loss = weight * sum_b 1 / (3 h_b w_b) * sum_{c, y < h_b, x < w_b} |sr[b,c,y,x] - gt[b,c,y,x]|
+ * (the caller passes weight = loss_weight / batch size).  sr and gt are addressed as element (b,c,y,x) at
+ * b*n + c*c + y*h + x*w of their stride arrays {n, c, h, w} (in floats) -- any layout, e.g. the channels-last
+ * (batch,hmax,wmax,3) image of gsr_forward_batch_padded and a (batch,3,H,W) ground truth.  Writes *loss (device,
+ * one float; accumulate != 0: adds to it) and grad = dloss/dsr in sr's layout over the whole (batch,3,hmax,wmax)
+ * block, zero outside the crops -- the `grads` array of gsr_backward_batch_padded.  hw_host: batch x (h_b, w_b),
+ * HOST memory, 1 <= h_b <= hmax, 1 <= w_b <= wmax.  workspace: gsr_l1_crop_workspace_bytes() bytes, 256-byte
+ * aligned.  The sum is reduced in a fixed order: bit-reproducible.  No counterpart in the reference's extension
+ * (basicsr/losses L1Loss + slicing: four elementwise passes and a reduction per sample). */
+size_t gsr_l1_crop_workspace_bytes(void);
+int gsr_l1_crop_loss(const float* sr, const long long* sr_strides, const float* gt, const long long* gt_strides,
+                     float* grad, float* loss, int batch, int hmax, int wmax, const int* hw_host, float weight,
+                     int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -208,3 +208,20 @@ def test_argument_validation_of_the_padded_batch_entry_points():
     st = (ctypes.c_float * 2)(0.3, 0.0)
     assert L.gsr_frontend_forward_batch_padded(fake, fake, fake, 2, 10, 64, 64, hw, st, None, 0.1, 0.0, ws, 1 << 30,
                                                None) == 5                                 # step <= 0
+
+
+def test_argument_validation_of_the_fused_loss():
+    L = _lib.load()
+    fake = ctypes.c_void_p(256)
+    ws = ctypes.c_void_p(4096)
+    st = (ctypes.c_longlong * 4)(1, 1, 1, 1)
+    hw = (ctypes.c_int * 4)(8, 8, 4, 9)
+    need = L.gsr_l1_crop_workspace_bytes()
+    f = L.gsr_l1_crop_loss
+    assert need >= 256 + 8
+    assert f(None, st, fake, st, fake, fake, 2, 8, 8, hw, 1.0, 0, ws, need, None) == 1        # sr NULL
+    assert f(fake, st, fake, st, fake, None, 2, 8, 8, hw, 1.0, 0, ws, need, None) == 1        # loss NULL
+    assert f(fake, st, fake, st, fake, fake, 2, 0, 8, hw, 1.0, 0, ws, need, None) == 2        # hmax < 1
+    assert f(fake, st, fake, st, fake, fake, 2, 8, 8, hw, 1.0, 0, ws, need, None) == 2        # w_1 = 9 > wmax
+    assert f(fake, st, fake, st, fake, fake, 1, 8, 8, hw, 1.0, 0, ws, 16, None) == 4          # workspace too small
+    assert f(fake, st, fake, st, fake, fake, 1, 8, 8, hw, 1.0, 0, None, need, None) == 4

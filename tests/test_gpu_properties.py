@@ -190,3 +190,42 @@ def test_fused_uint8_output_equals_the_reference_post_processing(bgr):
         ws = gscuda.workspace(s.shape[0], h, w, DEV)
         _lib.check(L.gsr_forward(sd.data_ptr(), cd.data_ptr(), kd.data_ptr(), out.data_ptr(), s.shape[0], h, w, 3,
                                  0.1, 0.0, _lib.GSR_FLAG_U8, ws.data_ptr(), ws.numel(), 0))
+
+
+def test_deterministic_mode_is_bit_reproducible():
+    """GSR_FLAG_DETERMINISTIC: region lists sorted by Gaussian index -> the fp32 summation order, and with it every
+    bit of the image, is a function of the inputs alone (the reference's atomicAdd accumulation, gs.cu:58-60, is
+    not reproducible).  Checked on a dense field (C2d-like density: hundreds of entries per list), on an image with
+    partial edge regions, and against the default mode to summation-order tolerance."""
+    for name, seed in (("C2", 0), ("C1", 3)):
+        _, s, c, k, h, w = fields.make(name, seed)
+        sd, cd, kd = s.to(DEV), c.to(DEV), k.to(DEV)
+        imgs = []
+        for rep in range(3):
+            img = torch.zeros(h, w, 3, device=DEV)
+            gscuda.gs_render(sd, cd, kd, img, s.shape[0], h, w, 3, 0.1, flags=0x20)
+            imgs.append(img)
+        torch.cuda.synchronize()
+        assert torch.equal(imgs[0], imgs[1]) and torch.equal(imgs[0], imgs[2])
+        ref = torch.zeros(h, w, 3, device=DEV)
+        gscuda.gs_render(sd, cd, kd, ref, s.shape[0], h, w, 3, 0.1)
+        assert float((ref - imgs[0]).abs().max()) <= 1e-5
+    # odd sizes (partial regions), huge lists (every Gaussian covers the image: the long-bucket sort)
+    rng = np.random.default_rng(5)
+    n, h, w = 3000, 37, 53
+    sg = torch.tensor(np.stack([rng.uniform(0.5, 2, n), rng.uniform(0.5, 2, n), rng.uniform(-0.5, 0.5, n)], 1), dtype=torch.float32, device=DEV)
+    xy = torch.tensor(rng.uniform(-1, 1, (n, 2)), dtype=torch.float32, device=DEV)
+    col = torch.tensor(rng.uniform(0, 1e-3, (n, 3)), dtype=torch.float32, device=DEV)
+    outs = []
+    for rep in range(2):
+        img = torch.zeros(h, w, 3, device=DEV)
+        gscuda.gs_render(sg, xy, col, img, n, h, w, 3, flags=0x20)
+        outs.append(img)
+    assert torch.equal(outs[0], outs[1])
+    try:
+        gscuda.set_deterministic(True)
+        a = torch.zeros(h, w, 3, device=DEV)
+        gscuda.gs_render(sg, xy, col, a, n, h, w, 3)
+        assert torch.equal(a, outs[0])
+    finally:
+        gscuda.set_deterministic(False)

@@ -8,7 +8,6 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "variants")
 VARIANTS = {
     "base": [],
-    "nostage": ["GSR_CFG_FR_STAGE_OUT=0"],
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
@@ -43,6 +42,12 @@ else:
             a.record(); L.gsr_forward_prepared(img.data_ptr(), n, h, w, 0.0, 0, ws.data_ptr(), ws.numel(), sp); b.record()
             torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
         res[cfg + "_fwd_acc_us"] = round(1e3 * float(np.median(ts[3:])), 1)
+        ts = []
+        for i in range(13):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); L.gsr_forward_prepared(img.data_ptr(), n, h, w, 0.0, 1 | 0x20, ws.data_ptr(), ws.numel(), sp); b.record()
+            torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+        res[cfg + "_fwd_det_us"] = round(1e3 * float(np.median(ts[3:])), 1)
         ts = []
         for i in range(13):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
