@@ -42,7 +42,7 @@ sys.path.insert(0, ROOT)
 METRIC = "HR megapixels/sec rasterized (fwd) at x4, 2M Gaussians"
 UNIT = "MP/s"
 DMAX = 0.1
-KERNELS_PER_STEP = 7  # table, region_build, forward_region + the guarded fallback (bin, scan, scatter, forward_bins)
+KERNELS_PER_STEP = 4  # table, region_build2, forward_region + the device-guarded fallback (home-bin set-up + raster in one kernel)
 
 
 def peaks():

@@ -241,10 +241,7 @@ __device__ __forceinline__ void gsr_fwd_writeout(const GsrFwdArgs& p, int hi, in
   }
 }
 
-__global__ void __launch_bounds__(GSR_FWD_THREADS, GSR_CFG_MIN_CTAS) gsr_forward_bins_kernel(GsrFwdArgs p) {
-  if (gsr_guard_skip(p.guard, p.want)) return;
-  extern __shared__ __align__(16) unsigned char gsr_smem_raw[];
-  GsrFwdSmem& sm = *reinterpret_cast<GsrFwdSmem*>(gsr_smem_raw);
+__device__ __forceinline__ void gsr_forward_bins_body(const GsrFwdArgs& p, GsrFwdSmem& sm) {
   constexpr int NR = GSR_NRX;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -403,6 +400,36 @@ __global__ void __launch_bounds__(GSR_FWD_THREADS, GSR_CFG_MIN_CTAS) gsr_forward
     gsr_fwd_writeout(p, hi, wi0, r0, g0, b0, r1, g1, b1);
   }
   }  // tile loop
+}
+
+__global__ void __launch_bounds__(GSR_FWD_THREADS, GSR_CFG_MIN_CTAS) gsr_forward_bins_kernel(GsrFwdArgs p) {
+  if (gsr_guard_skip(p.guard, p.want)) return;
+  extern __shared__ __align__(16) unsigned char gsr_smem_raw[];
+  gsr_forward_bins_body(p, *reinterpret_cast<GsrFwdSmem*>(gsr_smem_raw));
+}
+
+// The forward's fallback as ONE launch: when a region bucket overflowed, the home-bin set-up (gsr_bin_one, scan,
+// gsr_scatter_one -- the kernels K1..K3 as phases separated by grid barriers) and then the raster over the home
+// bins; when none did -- the normal case -- every CTA returns at once, and the call has paid for one idle launch
+// instead of four (3.4 us instead of 13 at HL).  The grid is one resident wave (sized by occupancy).
+template <bool RAGGED>
+__global__ void __launch_bounds__(GSR_FWD_THREADS, GSR_CFG_MIN_CTAS)
+gsr_forward_fallback_kernel(GsrFwdArgs p, const float* __restrict__ sigmas, const float* __restrict__ coords,
+                            const float* __restrict__ colors, int s, float dmax, float ksigma, GsrWorkspace ws) {
+  if (gsr_guard_skip(p.guard, p.want)) return;
+  extern __shared__ __align__(16) unsigned char gsr_smem_raw[];
+  int* const barrier = ws.stats + GSR_STAT_BARRIER;
+  int phase = 0;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+  if (gtid == 0) ws.stats[GSR_STAT_KSIGMA] = __float_as_int(ksigma);
+  for (int i0 = blockIdx.x * blockDim.x; i0 < s; i0 += gsize)  // (whole warps enter gsr_bin_one: it votes)
+    if (i0 + (int)threadIdx.x < s) gsr_bin_one<RAGGED>(sigmas, coords, colors, i0 + threadIdx.x, p.h, p.w, dmax, ksigma, ws);
+  gsr_grid_barrier(barrier, (++phase) * gridDim.x);
+  gsr_grid_scan(ws.bin_count, ws.bin_off, ws.nb + 1, ws.scan_state, barrier, phase);
+  gsr_grid_barrier(barrier, (++phase) * gridDim.x);
+  for (int i = gtid; i < s; i += gsize) gsr_scatter_one(sigmas, coords, colors, i, ws);
+  gsr_grid_barrier(barrier, (++phase) * gridDim.x);
+  gsr_forward_bins_body(p, *reinterpret_cast<GsrFwdSmem*>(gsr_smem_raw));
 }
 
 // ---- region-bucket forward kernel (the fast path) ------------------------------------------------

@@ -46,12 +46,13 @@ constexpr int GSR_STAT_EXT_X = 0, GSR_STAT_EXT_Y = 1, GSR_STAT_OVERFLOW = 2, GSR
 constexpr int GSR_ENTRIES_PER_GAUSSIAN = 28;
 constexpr int GSR_STAT_KSIGMA = 6;                   // effective k-sigma of the home-bin set-up (float bits), for the backward
 constexpr int GSR_STAT_UNSORTED = 7;                 // deterministic mode: a bucket was too long to be sorted
+constexpr int GSR_STAT_BARRIER = 8;                  // arrival counter of the fallback kernel's grid barriers
 constexpr int GSR_STAT_UNIT = 4, GSR_STAT_DONE = 5;  // work counter / finished-warp counter of the raster kernel
 
 struct GsrWorkspace {
   // ---- one block, cleared per call ----
   int* bin_count;    // nb + 1
-  int* stats;        // 8 ints, see GSR_STAT_*
+  int* stats;        // 16 ints, see GSR_STAT_*
   int* scan_state;   // 2 * nscan     look-back state of the bin scan
   int* reg_count;    // nreg      entries appended to each region's bucket (may exceed reg_cap)
   size_t zero_bytes;
@@ -101,10 +102,10 @@ static inline GsrWorkspace gsr_carve(void* base, int s, int h, int w) {
   };
   const size_t sn = (size_t)(s > 0 ? s : 1);
   ws.nscan = (ws.nb + 1 + GSR_SCAN_CHUNK - 1) / GSR_SCAN_CHUNK;
-  ws.zero_bytes = ((size_t)ws.nb + 1 + 8 + 2 * (size_t)ws.nscan + (size_t)ws.nreg) * sizeof(int);
+  ws.zero_bytes = ((size_t)ws.nb + 1 + 16 + 2 * (size_t)ws.nscan + (size_t)ws.nreg) * sizeof(int);
   ws.bin_count = (int*)take(ws.zero_bytes);
   ws.stats = ws.bin_count ? ws.bin_count + ws.nb + 1 : nullptr;
-  ws.scan_state = ws.bin_count ? ws.stats + 8 : nullptr;
+  ws.scan_state = ws.bin_count ? ws.stats + 16 : nullptr;
   ws.reg_count = ws.bin_count ? ws.scan_state + 2 * ws.nscan : nullptr;
   ws.rec_in = (GsrRec*)take(sn * sizeof(GsrRec));
   ws.box_in = (uint2*)take(sn * sizeof(uint2));
@@ -369,6 +370,84 @@ gsr_scatter_kernel(const float* __restrict__ sigmas, const float* __restrict__ c
   if (gsr_guard_skip(guard, want)) return;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < s; i += gridDim.x * blockDim.x)
     gsr_scatter_one(sigmas, coords, colors, i, ws);
+}
+
+// ---- the home-bin pipeline as phases of ONE resident grid (the forward's fallback kernel) -------------------
+// Barrier across a grid whose CTAs are all resident (the caller sizes the grid by occupancy): arrival counter in
+// the cleared block of the workspace, `target` = arrivals expected so far (phase number x gridDim.x).
+__device__ __forceinline__ void gsr_grid_barrier(int* counter, int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1);
+    while (*(volatile int*)counter < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+// Exclusive scan of n counters into n + 1 offsets by the whole grid (256-thread CTAs), two phases around one
+// barrier: chunk totals, then offsets.  `part` holds one int per GSR_SCAN_CHUNK counters.
+__device__ __forceinline__ void gsr_grid_scan(const int* __restrict__ count, int* __restrict__ off, int n, int* part,
+                                              int* barrier, int& phase) {
+  __shared__ int red[256 / 32 + 1];
+  constexpr int PER = GSR_SCAN_CHUNK / 256;  // counters per thread
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nchunks = (n + GSR_SCAN_CHUNK - 1) / GSR_SCAN_CHUNK;
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    int v = 0;
+    for (int k = 0; k < PER; ++k) {
+      const int i = c * GSR_SCAN_CHUNK + tid * PER + k;
+      v += i < n ? count[i] : 0;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (tid == 0) {
+      int t = 0;
+      for (int k = 0; k < 256 / 32; ++k) t += red[k];
+      part[c] = t;
+    }
+    __syncthreads();
+  }
+  gsr_grid_barrier(barrier, (++phase) * gridDim.x);
+  for (int c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    int carry = 0;
+    for (int j = tid; j < c; j += 256) carry += *(volatile int*)(part + j);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) carry += __shfl_xor_sync(0xffffffffu, carry, d);
+    if (lane == 0) red[warp] = carry;
+    __syncthreads();
+    carry = 0;
+    for (int k = 0; k < 256 / 32; ++k) carry += red[k];
+    __syncthreads();
+    // this thread's PER counters, then an exclusive scan of the thread sums over the CTA
+    int loc[PER], sum = 0;
+    for (int k = 0; k < PER; ++k) {
+      const int i = c * GSR_SCAN_CHUNK + tid * PER + k;
+      loc[k] = i < n ? count[i] : 0;
+      sum += loc[k];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) red[warp] = incl;
+    __syncthreads();
+    int wpre = 0;
+    for (int k = 0; k < warp; ++k) wpre += red[k];
+    int run = carry + wpre + incl - sum;
+    for (int k = 0; k < PER; ++k) {
+      const int i = c * GSR_SCAN_CHUNK + tid * PER + k;
+      if (i < n) off[i] = run;
+      run += loc[k];
+      if (i == n - 1) off[n] = run;
+    }
+    __syncthreads();
+  }
 }
 
 // ---- region-bucket pipeline ---------------------------------------------------------------------

@@ -70,7 +70,7 @@ static int gsr_sm_count(int* out) {
 
 template <typename K>
 static int gsr_resident_grid(K kernel, int threads, int slot, int* out, size_t dyn_smem = 0) {
-  static std::atomic<int> cache[3][64];  // [kernel slot][device], 0 = not yet queried
+  static std::atomic<int> cache[4][64];  // [kernel slot][device], 0 = not yet queried
   int dev = 0;
   GSR_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64) {
@@ -92,7 +92,7 @@ static int gsr_resident_grid(K kernel, int threads, int slot, int* out, size_t d
 // Kernels that need more than 48 KB of dynamic shared memory opt in once per (device, kernel).
 template <typename K>
 static int gsr_optin_smem(K kernel, int bytes, int slot) {
-  static std::atomic<int> done[4][64];
+  static std::atomic<int> done[6][64];
   int dev = 0;
   GSR_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && done[slot][dev].load(std::memory_order_relaxed)) return GSR_OK;
@@ -290,13 +290,35 @@ static int gsr_launch_forward_bins(const GsrWorkspace& ws, float* img, int h, in
   return GSR_OK;
 }
 
-// Whole forward set-up: tile lists, plus the guarded home-bin fallback.
+// Whole forward set-up: the region buckets (the home-bin fallback is part of the fallback raster kernel).
 static int gsr_prepare_forward(const float* sigmas, const float* coords, const float* colors, int s,
                                int h, int w, float dmax, float keff, const GsrWorkspace& ws,
                                cudaStream_t st, const float* raw = nullptr, float step = 0.f) {
-  int rc = gsr_run_tiles(sigmas, coords, colors, s, h, w, dmax, keff, ws, st, raw, step);
+  return gsr_run_tiles(sigmas, coords, colors, s, h, w, dmax, keff, ws, st, raw, step);
+}
+
+// The fallback as one launch: home-bin set-up + raster over the home bins, all of it skipped on the device unless
+// a bucket overflowed (gsr_forward_fallback_kernel).
+static int gsr_launch_forward_fallback(const GsrWorkspace& ws, float* img, int h, int w, float keff, uint32_t flags,
+                                       cudaStream_t st, const float* sigmas, const float* coords,
+                                       const float* colors, int s, float dmax) {
+  GsrFwdArgs a = gsr_fwd_args(ws, img, h, w, keff, flags);
+  a.want = 1;
+  int rc = gsr_optin_smem(gsr_forward_fallback_kernel<false>, (int)sizeof(GsrFwdSmem), 4);
   if (rc) return rc;
-  return gsr_run_bins(sigmas, coords, colors, s, h, w, dmax, keff, ws, ws.stats + GSR_STAT_OVERFLOW, 1, st);
+  rc = gsr_optin_smem(gsr_forward_fallback_kernel<true>, (int)sizeof(GsrFwdSmem), 5);
+  if (rc) return rc;
+  int cap = 0;  // every CTA must be resident: the phases are separated by grid barriers
+  rc = gsr_resident_grid(gsr_forward_fallback_kernel<false>, GSR_FWD_THREADS, 3, &cap, sizeof(GsrFwdSmem));
+  if (rc) return rc;
+  if (ws.ragged)
+    gsr_forward_fallback_kernel<true><<<cap, GSR_FWD_THREADS, sizeof(GsrFwdSmem), st>>>(a, sigmas, coords, colors, s,
+                                                                                         dmax, keff, ws);
+  else
+    gsr_forward_fallback_kernel<false><<<cap, GSR_FWD_THREADS, sizeof(GsrFwdSmem), st>>>(a, sigmas, coords, colors, s,
+                                                                                          dmax, keff, ws);
+  GSR_CUDA(cudaGetLastError());
+  return GSR_OK;
 }
 
 // GSR_FLAG_DETERMINISTIC: every bucket sorted by Gaussian index before it is rasterised (idempotent: a prepared
@@ -316,13 +338,18 @@ static int gsr_sort_buckets(const GsrWorkspace& ws, cudaStream_t st) {
   return GSR_OK;
 }
 
+// bins_ready: gsr_prepare has set up the home bins (split-phase API); otherwise (one-call forward) the fallback
+// kernel does it when needed.
 static int gsr_raster_forward(const GsrWorkspace& ws, float* img, int h, int w, float keff,
-                              uint32_t flags, cudaStream_t st) {
+                              uint32_t flags, cudaStream_t st, bool bins_ready, const float* sigmas = nullptr,
+                              const float* coords = nullptr, const float* colors = nullptr, int s = 0,
+                              float dmax = 0.f) {
   int rc = (flags & GSR_FLAG_DETERMINISTIC) ? gsr_sort_buckets(ws, st) : GSR_OK;
   if (rc) return rc;
   rc = gsr_launch_forward_region(ws, img, h, w, keff, flags, st);
   if (rc) return rc;
-  return gsr_launch_forward_bins(ws, img, h, w, keff, flags, st);
+  if (bins_ready) return gsr_launch_forward_bins(ws, img, h, w, keff, flags, st);
+  return gsr_launch_forward_fallback(ws, img, h, w, keff, flags, st, sigmas, coords, colors, s, dmax);
 }
 
 static int gsr_launch_backward(const GsrWorkspace& ws, const float* sigmas, const float* grads,
@@ -422,7 +449,8 @@ static int gsr_forward_impl(const float* sigmas, const float* coords, const floa
   ws.win = win;
   rc = gsr_prepare_forward(sigmas, coords, colors, s, h, w, dmax, keff, ws, st, raw, step);
   if (rc) return rc;
-  return gsr_raster_forward(ws, img, h, w, keff, flags, st);
+  // (raw: the set-up kernel has left the mapped parameters in sigmas / coords / colors)
+  return gsr_raster_forward(ws, img, h, w, keff, flags, st, false, sigmas, coords, colors, s, dmax);
 }
 
 static int gsr_backward_impl(const float* sigmas, const float* coords, const float* colors,
@@ -611,7 +639,7 @@ extern "C" int gsr_forward_prepared(float* img, int s, int h, int w, float ksigm
   const GsrWorkspace ws = gsr_carve(workspace, s, h, w);
   int rc = gsr_check_ws(workspace, workspace_bytes, ws.bytes);
   if (rc) return rc;
-  return gsr_raster_forward(ws, img, h, w, gsr_effective_ksigma(ksigma), flags, (cudaStream_t)stream);
+  return gsr_raster_forward(ws, img, h, w, gsr_effective_ksigma(ksigma), flags, (cudaStream_t)stream, true);
 }
 
 extern "C" int gsr_backward_prepared(const float* sigmas, const float* grads, float* grads_sigmas,
