@@ -660,7 +660,7 @@ def main():
 
 # dram__bytes_read.sum + dram__bytes_write.sum of gsr_forward_region_kernel per launch, from the
 # `ncu --set full` capture summarised under profiles/ (bytes); None where not captured.
-TRAFFIC = {"HL": 277.1e6}  # profiles/r02_fwd_cells_HL_ncu_full.txt: 214.0 MB read + 63.1 MB written
+TRAFFIC = {"HL": 276.6e6}  # profiles/r02_fwd_final_HL_ncu_full.txt: 213.5 MB read + 63.1 MB written
 
 if __name__ == "__main__":
     main()

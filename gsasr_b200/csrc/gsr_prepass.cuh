@@ -244,13 +244,16 @@ gsr_bin_kernel(const float* __restrict__ sigmas, const float* __restrict__ coord
     gsr_bin_one<RAGGED>(sigmas, coords, colors, i, h, w, dmax, ksigma, ws);
 }
 
-// Pixel coordinate tables: the reference's rule (gs.cu:39,46), evaluated once per axis entry.
+// Pixel coordinate tables: the reference's rule (gs.cu:39,46), evaluated once per axis entry -- and the clearing
+// of the workspace's counter block (zero16 x 16 bytes from `zero`), which would otherwise be a launch of its own.
 __global__ void __launch_bounds__(256) gsr_table_kernel(float* __restrict__ px_tab,
                                                         float* __restrict__ py_tab, int h, int w,
-                                                        int hf, int row0, int bhs) {
+                                                        int hf, int row0, int bhs, uint4* __restrict__ zero,
+                                                        size_t zero16) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < w) px_tab[i] = gsr_pix_coord(i, w);
   if (i < h) py_tab[i] = bhs > 0 ? gsr_pix_coord(i % bhs, bhs) : hf > 0 ? gsr_pix_coord(i + row0, hf) : gsr_pix_coord(i, h);
+  for (size_t k = (size_t)i; k < zero16; k += (size_t)gridDim.x * blockDim.x) zero[k] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // Exclusive scan of n = nb + 1 counters into n + 1 offsets.  One CTA of 1024 threads per

@@ -102,9 +102,12 @@ static int gsr_optin_smem(K kernel, int bytes, int slot) {
 }
 
 static int gsr_clear_and_tables(int h, int w, const GsrWorkspace& ws, cudaStream_t st) {
-  GSR_CUDA(cudaMemsetAsync(ws.bin_count, 0, ws.zero_bytes, st));
+  // one launch: the tables and the zeroing of the counter block (carved in multiples of 256 bytes)
   const int n = w > h ? w : h;
-  gsr_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(ws.px_tab, ws.py_tab, h, w, ws.hf, ws.row0, ws.bhs);
+  const size_t zero16 = gsr_align_up(ws.zero_bytes, 256) / 16;
+  const size_t want = (zero16 + 255) / 256 > (size_t)((n + 255) / 256) ? (zero16 + 255) / 256 : (size_t)((n + 255) / 256);
+  gsr_table_kernel<<<(int)(want < 1184 ? want : 1184), 256, 0, st>>>(ws.px_tab, ws.py_tab, h, w, ws.hf, ws.row0, ws.bhs,
+                                                                    reinterpret_cast<uint4*>(ws.bin_count), zero16);
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
 }
