@@ -581,6 +581,14 @@ def main():
         except Exception as exc:  # symmetric memory unavailable: report, do not fail the bench
             pr = None
             peer_note = f"{type(exc).__name__}: {exc}"
+        try:
+            pr8 = coll(lambda: sharding.render_image_bands_peer(s0, c0, k0, h, w, DMAX, gather_to=0, u8=True))
+            pr8_dev = dev_ms(lambda: sharding.render_image_bands_peer(s0, c0, k0, h, w, DMAX, gather_to=0, u8=True))
+            u8img = torch.empty(h, w, 3, dtype=torch.uint8, device=dev)
+            one_u8 = maxr(timed(lambda: gscuda.gs_render_u8(s0, c0, k0, u8img, n, h, w, DMAX, workspace_buf=ws), 20))
+        except Exception as exc:
+            pr8 = pr8_dev = one_u8 = None
+            peer_note = f"{type(exc).__name__}: {exc}"
         bb = coll(lambda: sharding.backward_image_bands(s0, c0, k0, g0, h, w, DMAX), 10)
         ag_dev = dev_ms(lambda: sharding.render_image_bands(s0, c0, k0, h, w, DMAX, gather_to=None))
         pr_dev = dev_ms(lambda: sharding.render_image_bands_peer(s0, c0, k0, h, w, DMAX, gather_to=0)) if pr else None
@@ -596,6 +604,12 @@ def main():
             "bands_allgather_efficiency": one_f / (world * ag),
             "bands_peer_fwd_ms": pr, "bands_peer_mps": (mp_img / (pr * 1e-3)) if pr else None,
             "bands_peer_efficiency": (one_f / (world * pr)) if pr else None,
+            "bands_peer_u8": None if pr8 is None else {
+                "what": "the inference result: the (h,w,3) uint8 image of inference_paper.py:136-138 written by the band "
+                        "kernels into the stitching rank's memory (3 bytes per pixel over NVLink)",
+                "single_gpu_u8_fwd_ms": one_u8, "fwd_ms": pr8, "device_ms": pr8_dev,
+                "efficiency": one_u8 / (world * pr8), "device_efficiency": one_u8 / (world * pr8_dev),
+                "peer_store_bytes_per_rank": 3 * h * w // world},
             "bands_bwd_allreduce_ms": bb, "bands_bwd_efficiency": one_b / (world * bb),
             "device_time_ms": {"band_kernels_only": band_only, "bands_allgather": ag_dev, "bands_peer": pr_dev,
                                "bands_bwd_allreduce": bb_dev,

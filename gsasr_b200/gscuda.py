@@ -140,8 +140,14 @@ def gs_render_backward(sigmas, coords, colors, grads, grads_sigmas, grads_coords
 def gs_render_band(sigmas, coords, colors, band_img, s, h, w, c, row0, rows, dmax=float("inf"), *,
                    ksigma=None, flags=0, workspace_buf=None):
     L = _lib.load()
-    for t, n in ((sigmas, "sigmas"), (coords, "coords"), (colors, "colors"), (band_img, "band_img")):
+    for t, n in ((sigmas, "sigmas"), (coords, "coords"), (colors, "colors")):
         _check_input(t, n)
+    if int(flags) & _lib.GSR_FLAG_U8:  # the fused uint8 post-processing: band_img is the (rows,w,3) uint8 band
+        if not (isinstance(band_img, torch.Tensor) and band_img.is_cuda and band_img.is_contiguous()
+                and band_img.dtype == torch.uint8):
+            raise RuntimeError("band_img must be a contiguous uint8 CUDA tensor with GSR_FLAG_U8")
+    else:
+        _check_input(band_img, "band_img")
     s, h, w, c, row0, rows = int(s), int(h), int(w), int(c), int(row0), int(rows)
     if c != 3:
         raise RuntimeError("libgsraster: c must be 3 (the reference forward hard-codes 3 channels)")

@@ -137,16 +137,16 @@ def _band_forward_cuda(sigmas, coords, colors, h, w, row0, rows, dmax, out=None)
 _SYMM_IMAGES = {}
 
 
-def _peer_image(numel: int, device, root: int, group, slot: int = 0):
+def _peer_image(numel: int, device, root: int, group, slot: int = 0, dtype=torch.float32):
     """Symmetric-memory image buffer: (this rank's buffer, view of `root`'s buffer, handle); cached."""
     import torch.distributed._symmetric_memory as symm_mem
 
-    key = (numel, str(device), id(group), slot)
+    key = (numel, str(device), id(group), slot, dtype)
     if key not in _SYMM_IMAGES:
-        buf = symm_mem.empty(numel, dtype=torch.float32, device=device)
+        buf = symm_mem.empty(numel, dtype=dtype, device=device)
         _SYMM_IMAGES[key] = (buf, symm_mem.rendezvous(buf, group=group if group is not None else dist.group.WORLD))
     buf, hdl = _SYMM_IMAGES[key]
-    return buf, hdl.get_buffer(root, (numel,), torch.float32), hdl
+    return buf, hdl.get_buffer(root, (numel,), dtype), hdl
 
 
 _PEER_CALLS = {}
@@ -154,7 +154,7 @@ _PEER_VIEWS = {}
 
 
 def render_image_bands_peer(sigmas, coords, colors, h: int, w: int, dmax: float, *, gather_to: int = 0,
-                            group=None):
+                            group=None, u8: bool = False, bgr: bool = False):
     """render_image_bands with the gather folded into the raster kernel: the (h,w,3) image lives in
     symmetric memory on `gather_to` and every rank's band kernel stores its rows straight into it over
     NVLink (peer writes) -- no collective, the transfer overlaps the raster.  Returns a view of the
@@ -164,17 +164,27 @@ def render_image_bands_peer(sigmas, coords, colors, h: int, w: int, dmax: float,
     stream-ordered barrier across the ranks.  The image of call k is therefore overwritten no earlier than call
     k+2, whose kernels run behind the barrier of call k+1 on every rank -- and that barrier completes only after
     everything the stitching rank queued on its current stream before it (the readers of image k).  Work queued on
-    OTHER streams must be ordered by the caller; a caller that keeps the image longer clones it."""
+    OTHER streams must be ordered by the caller; a caller that keeps the image longer clones it.
+
+    u8=True: the inference pipeline's result instead -- the (h,w,3) uint8 image of inference_paper.py:136-138
+    (clamp, x255, round; bgr=True: cv2's channel order), produced by the raster kernel's write-out
+    (GSR_FLAG_U8): 3 bytes per pixel cross NVLink instead of 12."""
     from . import gscuda
 
+    dtype = torch.uint8 if u8 else torch.float32
+    flags = (0x1 | 0x4 | (0x8 if bgr else 0)) if u8 else (0x1 | 0x10)  # OVERWRITE | U8 [| BGR]  /  OVERWRITE | ROW_STORES
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return _band_forward_cuda(sigmas, coords, colors, h, w, 0, h, dmax)
+        if not u8:
+            return _band_forward_cuda(sigmas, coords, colors, h, w, 0, h, dmax)
+        out = torch.empty(h, w, 3, dtype=torch.uint8, device=sigmas.device)
+        gscuda.gs_render_band(sigmas, coords, colors, out, sigmas.shape[0], h, w, 3, 0, h, dmax, flags=flags)
+        return out
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    key = (h, w, str(sigmas.device), id(group), gather_to)
+    key = (h, w, str(sigmas.device), id(group), gather_to, u8)
     slot = _PEER_CALLS.get(key, 0)
     _PEER_CALLS[key] = slot ^ 1
     if (key, slot) not in _PEER_VIEWS:  # peer views, the band slice and the workspace are set up once
-        mine, target, hdl = _peer_image(h * w * 3, sigmas.device, gather_to, group, slot)
+        mine, target, hdl = _peer_image(h * w * 3, sigmas.device, gather_to, group, slot, dtype)
         row0, rows = band_rows(h, rank, world)
         band = target.view(h, w, 3)[row0:row0 + rows] if rows > 0 else None  # rows of the stitching rank's image
         ws = gscuda.workspace(sigmas.shape[0], max(rows, 2), w, sigmas.device)
@@ -185,7 +195,7 @@ def render_image_bands_peer(sigmas, coords, colors, h: int, w: int, dmax: float,
         _PEER_VIEWS[(key, slot)] = (mine, band, hdl, row0, rows, ws, sigmas.shape[0])
     if rows > 0:
         gscuda.gs_render_band(sigmas, coords, colors, band, sigmas.shape[0], h, w, 3, row0, rows, dmax,
-                              flags=0x1 | 0x10,  # GSR_FLAG_OVERWRITE | GSR_FLAG_ROW_STORES: 16-byte packets over NVLink
+                              flags=flags,  # fp32: GSR_FLAG_ROW_STORES -- 16-byte packets over NVLink (uint8: always)
                               workspace_buf=ws)
     # Stream-ordered barrier (a kernel on the current stream that signals every peer and waits for all of them):
     # behind it, every rank's stores of this call have landed; no host synchronisation, the call returns at once.

@@ -23,6 +23,12 @@ for name in ("C1", "C2"):
     peer = sharding.render_image_bands_peer(s, c, k, h, w, 0.1, gather_to=0)
     if rank == 0:
         assert float((peer - full).abs().max()) <= 2e-6, "peer-written bands differ"
+    torch.cuda.synchronize()
+    peer8 = sharding.render_image_bands_peer(s, c, k, h, w, 0.1, gather_to=0, u8=True)
+    if rank == 0:  # the uint8 image of inference_paper.py:136-138, from every rank's band kernel
+        want8 = (full.clamp(0, 1) * 255.0).round().to(torch.int16)
+        d8 = (peer8.to(torch.int16) - want8).abs()
+        assert int(d8.max()) <= 1 and float((d8 > 0).float().mean()) < 1e-3, "peer-written uint8 bands differ"
     err = float((img - full).abs().max())
     rel = max(float((a - b).abs().max() / b.abs().max()) for a, b in zip(got, want))
     print(f"[rank {rank}/{dist.get_world_size()}] {name} {h}x{w}: bands vs whole image max-abs {err:.2e}, "
