@@ -5,7 +5,7 @@
 // Here pixels are gathered: accumulators live in registers and every pixel is written once.
 //
 //   gsr_forward_region_kernel  (the fast path, second half of this file)  streams the per-region
-//       buckets built by gsr_region_build_kernel: a warp per 16x8-pixel region, a 2x2 pixel block per lane,
+//       buckets built by gsr_region_build2_kernel: a warp per 16x8-pixel region, a 2x2 pixel block per lane,
 //       every 4x4-pixel cell (four lanes) evaluating only the entries whose cell mask names it, persistent
 //       independent warps, two-deep cp.async prefetch.  See its own comment.
 //   gsr_forward_bins_kernel    (the fallback, runs when a bucket overflowed)  finds a tile's candidates
@@ -434,7 +434,7 @@ gsr_forward_fallback_kernel(GsrFwdArgs p, const float* __restrict__ sigmas, cons
 
 // ---- region-bucket forward kernel (the fast path) ------------------------------------------------
 // One warp per 16x8-pixel region, a 2x2 pixel block per lane (accumulators in registers: six FP32x2 pairs);
-// the four lanes of a 4x4-pixel CELL move together.  A bucket entry (written by gsr_region_build_kernel)
+// the four lanes of a 4x4-pixel CELL move together.  A bucket entry (written by gsr_region_build2_kernel)
 // carries the Gaussian's index and an 8-bit mask of the cells its k-sigma ellipse reaches, and every cell
 // evaluates ONLY the entries that name it: of the 128 pixels of a region a Gaussian of the x4 head reaches
 // ~65 (half the cells), so half of the exponentials a whole-region evaluation would issue never are.

@@ -1,15 +1,13 @@
 // gsr_prepass.cuh -- O(N) set-up pipelines shared by forward and backward.
 //
 // Region-bucket pipeline (forward fast path), ONE pass over the Gaussians:
-//   T1 gsr_region_build_kernel  per Gaussian: exact dmax window /\ k-sigma box -> cull box, raster
+//   T1 gsr_region_build2_kernel per Gaussian: exact dmax window /\ k-sigma box -> cull box, raster
 //                               record (written in input order); then for every 16x8-pixel region
 //                               the ellipse touches a 4-byte entry {index | cell mask << 23 | binds << 31}
 //                               is appended to the region's bucket -- the mask says which of the region's
-//                               eight 4x4-pixel cells the ellipse reaches (small persistent CTAs collect
-//                               their entries per region in shared memory and reserve bucket slots with
-//                               one global atomic per (CTA, region); a warp-ballot path serves incoherent
-//                               input).  Optionally fed with the RAW head output: the activations and the
-//                               unit mapping of the front end are then applied here (gsr_map_one).
+//                               eight 4x4-pixel cells the ellipse reaches.  Optionally fed with the RAW head
+//                               output: the activations and the unit mapping of the front end are then
+//                               applied here (gsr_map_one).
 //   Every region owns a fixed-capacity bucket (GSR_ENTRIES_PER_GAUSSIAN N / regions + 32 entries: GSASR
 //   emits its Gaussians on a regular grid, utils/fea2gs.py:553-563, so the load per region is uniform); an
 //   entry that does not fit raises the overflow flag and the forward falls back to the home-bin pipeline.
@@ -24,7 +22,8 @@
 //
 // Memory is bounded by sizes alone (no data-dependent allocation, no host sync): the choice between
 // the two forward paths is made ON THE DEVICE through stats[GSR_STAT_OVERFLOW]; kernels of the path
-// not taken return at once (`guard`).
+// not taken return at once (`guard`).  In a one-call forward K1..K3 run as phases of the fallback raster
+// kernel itself (gsr_forward_fallback_kernel, gsr_forward.cuh), so the normal path pays for ONE idle launch.
 #pragma once
 #include "gsr_common.cuh"
 struct gsr_window;
@@ -501,20 +500,8 @@ __device__ __forceinline__ GsrMapped gsr_map_one(const float* __restrict__ p, in
 // one per position.  All loops are warp-uniform (trip counts are warp maxima, lanes past their own range are
 // predicated off): no divergent nesting, and no special path for wide (x8) or incoherent input, which merely
 // forms smaller groups.
-#ifndef GSR_CFG_RB_THREADS
-#define GSR_CFG_RB_THREADS 64
-#endif
-constexpr int GSR_RB_THREADS = GSR_CFG_RB_THREADS;
-#ifndef GSR_CFG_RB_MIN_CTAS
-#define GSR_CFG_RB_MIN_CTAS (1024 / GSR_CFG_RB_THREADS)
-#endif
 constexpr int GSR_RB_ECAP = 16;  // list positions per Gaussian between two flushes
 
-struct GsrRegionBuildSmem {
-  uint2 list[GSR_RB_ECAP][GSR_RB_THREADS];  // {entry, region id}
-};
-
-// Appends list positions [0, n) of every lane (n <= GSR_RB_ECAP, lane-dependent).  Warp-collective.
 // list: [GSR_RB_ECAP][STRIDE] items, this lane's column is `col`.
 template <int STRIDE>
 __device__ __forceinline__ void gsr_bucket_flush(const uint2* list, int col, int lane, int n,
@@ -560,141 +547,10 @@ __device__ __forceinline__ void gsr_bucket_flush(const uint2* list, int col, int
   }
 }
 
-// RAW: `sigmas` points to the raw head output (s,9); the mapped parameters are written to msig (s,3), mcrd (s,2),
-// mcol (s,3) -- what the backward and the autograd boundary need -- and used from registers: no second pass
-// over them.  step: the front end's step size (padded batches: per sample).
-template <bool RAGGED, bool RAW>
-__global__ void __launch_bounds__(GSR_RB_THREADS, GSR_CFG_RB_MIN_CTAS)
-gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restrict__ coords,
-                        const float* __restrict__ colors, float* __restrict__ msig, float* __restrict__ mcrd,
-                        float* __restrict__ mcol, int s, int h, int w, float dmax, float ksigma, float ecut,
-                        float step, GsrWorkspace ws) {
-  __shared__ GsrRegionBuildSmem sm;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const unsigned full = 0xffffffffu;
-  int* const overflow = ws.stats + GSR_STAT_OVERFLOW;
-  const int nchunks = (s + GSR_RB_THREADS - 1) / GSR_RB_THREADS;
-
-  for (int chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
-    const int i = chunk * GSR_RB_THREADS + tid;
-    // batches: set up in the sample's own image (hl x wl, its dmax), then move to its block of rows of the
-    // stack; a padded batch stores the record rescaled to the canvas' coordinate normalisation, the raw
-    // one (r) keeps describing the ellipse in the sample's own pixels for the cell masks
-    const GsrSampleView sv = gsr_sample_view<RAGGED>(ws, i < s ? i : 0, h, w, dmax);
-    const int yoff = sv.yoff, hl = sv.hl, wl = sv.wl;
-    GsrSetup st;
-    st.live = false;
-    st.binds = false;
-    st.x0 = st.y0 = 1;
-    st.x1 = st.y1 = 0;
-    GsrEllipse e;
-    e.cx = e.cy = e.inv_a = e.kappa = e.cp = 0.f;
-    if (i < s) {
-      float sx, sy, rho, x, y, cr, cg, cb;
-      if (RAW) {
-        float stp = step;
-        if (RAGGED) stp = ws.bdesc[i / ws.bn].step;
-        const GsrMapped m = gsr_map_one(sigmas + 9 * (size_t)i, ws.hf > 0 ? ws.hf : hl, wl, stp);
-        sx = m.sx, sy = m.sy, rho = m.rho, x = m.x, y = m.y, cr = m.cr, cg = m.cg, cb = m.cb;
-        float* ms = msig + 3 * (size_t)i;
-        float* mc = mcrd + 2 * (size_t)i;
-        float* mk = mcol + 3 * (size_t)i;
-        ms[0] = sx, ms[1] = sy, ms[2] = rho;
-        mc[0] = x, mc[1] = y;
-        mk[0] = cr, mk[1] = cg, mk[2] = cb;
-      } else {
-        sy = __ldg(sigmas + 3 * (size_t)i + 1);
-        y = __ldg(coords + 2 * (size_t)i + 1);
-        sx = rho = x = cr = cg = cb = 0.f;
-        // row-band view (one image split over several GPUs): a Gaussian whose k-sigma rows miss the band by more
-        // than a pixel is dropped after these two loads -- the set-up cost of a band is its share of the image's
-        bool reach = true;
-        if (ws.hf > 0) {
-          const float hyf = 0.5f * (float)(ws.hf - 1);
-          const float cyf = (y + 1.0f) * hyf, eyf = ksigma * fabsf(sy) * hyf + 1.0f;
-          reach = !(cyf + eyf < (float)ws.row0 - 1.0f || cyf - eyf > (float)(ws.row0 + h));
-        }
-        if (reach) {
-          sx = __ldg(sigmas + 3 * (size_t)i + 0);
-          rho = __ldg(sigmas + 3 * (size_t)i + 2);
-          x = __ldg(coords + 2 * (size_t)i + 0);
-          cr = __ldg(colors + 3 * (size_t)i + 0);
-          cg = __ldg(colors + 3 * (size_t)i + 1);
-          cb = __ldg(colors + 3 * (size_t)i + 2);
-        } else {
-          sy = 0.f;  // sigma = 0: gsr_setup returns "not live" at its first test
-        }
-      }
-      st = gsr_setup(sx, sy, rho, x, y, cr, cg, cb, hl, wl, sv.dmax, ksigma, sv.px_tab, sv.py_tab, ws.hf, ws.row0);
-      if (st.live) {
-        const GsrRec r = gsr_make_rec(sx, sy, rho, x, y, cr, cg, cb);
-        if (!(gsr_finite(r.a) && gsr_finite(r.b) && gsr_finite(r.c))) st.live = false;
-        st.y0 += yoff;
-        st.y1 += yoff;
-        if (gsr_edge_binds<RAGGED>(sv, st)) st.binds = true;
-        if (st.live) {
-          GsrRec rs = r;
-          if (RAGGED) gsr_rescale_rec(rs, sv);
-          float4* dr = reinterpret_cast<float4*>(ws.rec_in + i);
-          dr[0] = make_float4(rs.x, rs.y, rs.a, rs.b);
-          dr[1] = make_float4(rs.c, rs.r, rs.g, rs.bl);
-          if (st.binds) ws.box_in[i] = gsr_box_pack(st.x0, st.x1, st.y0, st.y1, true);
-          e = gsr_ellipse(r, hl, wl, ws.hf, ws.row0);
-          e.cy += (float)yoff;
-        }
-      }
-    }
-    const uint32_t entry = (uint32_t)i | (st.binds ? 0x80000000u : 0u);
-
-    // ---- walk the region bands of the box (warp-uniform trip counts)
-    // (box corners of a live Gaussian are non-negative: unsigned divisions are shifts)
-    const int b0 = (int)((unsigned)st.y0 / GSR_RGH), nb = st.live ? (int)((unsigned)st.y1 / GSR_RGH) - b0 + 1 : 0;
-    const int cbase = (int)((unsigned)st.x0 / GSR_RGW) * GSR_CELLS_X;
-    // every box of the warp spans at most 32 cells: row bitmaps (else the general mask function, for all lanes)
-    const bool narrow = __all_sync(full, !st.live || (int)((unsigned)st.x1 / GSR_CELL) - cbase < 32);
-    const int KB = __reduce_max_sync(full, nb);
-    int n = 0;  // entries in this lane's list
-    for (int k = 0; k < KB; ++k) {
-      const int b = b0 + k;
-      uint32_t rb[2] = {0u, 0u};
-      int cl[2] = {1, 1}, ch[2] = {0, 0}, ca = 0, ncol = 0;
-      if (k < nb) {
-        if (narrow) {
-          if (gsr_band_rowbits(e, ecut, b, st.x0, st.x1, st.y0, st.y1, cbase, rb)) {
-            const uint32_t any = rb[0] | rb[1];
-            ca = (int)((unsigned)(cbase + __ffs(any) - 1) / GSR_CELLS_X);
-            ncol = (int)((unsigned)(cbase + 31 - __clz(any)) / GSR_CELLS_X) - ca + 1;
-          }
-        } else if (gsr_band_cells(e, ecut, b, st.x0, st.x1, st.y0, st.y1, cl, ch)) {
-          int cb_;
-          gsr_band_columns(cl, ch, ca, cb_);
-          ncol = cb_ - ca + 1;
-        }
-      }
-      const int KC = __reduce_max_sync(full, ncol);
-      for (int j0 = 0; j0 < KC; j0 += 4) {
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int j = j0 + jj, c = ca + j;
-          uint32_t m = 0u;
-          if (j < ncol) m = narrow ? gsr_rowbits_mask(rb, c, cbase) : gsr_cell_mask(cl, ch, c);
-          if (m != 0u) {
-            sm.list[n][tid] = make_uint2(entry | (m << GSR_ENT_MASK_SHIFT), (uint32_t)(b * ws.nrx + c));
-            ++n;
-          }
-        }
-        if (__any_sync(full, n > GSR_RB_ECAP - 4)) {  // the next four might not fit
-          gsr_bucket_flush<GSR_RB_THREADS>(&sm.list[0][0], tid, lane, n, ws.reg_count, ws.entries, ws.reg_cap, overflow);
-          n = 0;
-        }
-      }
-    }
-    gsr_bucket_flush<GSR_RB_THREADS>(&sm.list[0][0], tid, lane, n, ws.reg_count, ws.entries, ws.reg_cap, overflow);
-  }
-}
-
-// ---- region build, balanced form (the default) -------------------------------------------------------------
-// Same output as gsr_region_build_kernel, arranged so that no lane waits for the widest Gaussian of its warp.
+// ---- region build ------------------------------------------------------------------------------------------------
+// Arranged so that no lane waits for the widest Gaussian of its warp (round 1-2's kernel ran every lane for the
+// warp's maximum number of bands and columns: 1960 warp instructions per 32 Gaussians at HL, now ~1750 with a
+// third of the atomics).
 // A warp takes 32 consecutive Gaussians.
 //   phase A  one lane per Gaussian: set-up, record, ellipse -- ellipse and cull box go to the warp's shared memory;
 //   phase B  one lane per (Gaussian, region band) ITEM: the bitmaps of the band's two cell rows, the band's first
@@ -704,12 +560,11 @@ gsr_region_build_kernel(const float* __restrict__ sigmas, const float* __restric
 //   phase C  one lane per entry: cell mask from the item's bitmaps; runs of lanes naming the same region are
 //            found with one shuffle + ballot and the run's first lane reserves the run's bucket slots with ONE
 //            atomic (two list positions per lane in flight before the first result is used).
-// The old kernel ran every lane for the warp's maximum number of bands and of columns: 1960 -> ~1300 warp
-// instructions per 32 Gaussians at HL.  A warp holding a Gaussian wider than 32 cells or taller than GSR_RB2_MAXB
-// bands walks the generic way.
-#ifndef GSR_CFG_RB2
-#define GSR_CFG_RB2 1
-#endif
+// A warp holding a Gaussian wider than 32 cells or taller than GSR_RB2_MAXB bands walks the generic way
+// (gsr_rb_walk_generic: per-lane lists, appended four positions at a time).
+// RAW: `sigmas` points to the raw head output (s,9); the mapped parameters are written to msig (s,3), mcrd (s,2),
+// mcol (s,3) -- what the backward and the autograd boundary need -- and used from registers: no second pass
+// over them.  step: the front end's step size (padded batches: per sample).
 #ifndef GSR_CFG_RB2_MIN_CTAS
 #define GSR_CFG_RB2_MIN_CTAS 8
 #endif
@@ -752,7 +607,7 @@ gsr_region_build2_kernel(const float* __restrict__ sigmas, const float* __restri
 
   for (int chunk = blockIdx.x * GSR_RB2_WARPS + warp; chunk < nchunks; chunk += gridDim.x * GSR_RB2_WARPS) {
     const int i = chunk * 32 + lane;
-    // ---- phase A: one lane per Gaussian (see gsr_region_build_kernel for the batch views)
+    // ---- phase A: one lane per Gaussian (batches: set up in the sample's own image, then moved to its block of rows of the stack)
     const GsrSampleView sv = gsr_sample_view<RAGGED>(ws, i < s ? i : 0, h, w, dmax);
     const int yoff = sv.yoff, hl = sv.hl, wl = sv.wl;
     GsrSetup st;

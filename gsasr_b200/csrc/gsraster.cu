@@ -149,21 +149,11 @@ static int gsr_run_tiles(const float* sigmas, const float* coords, const float* 
   if (s > 0) {
     const float ec = gsr_ecut(keff);
     float *ms = (float*)sigmas, *mc = (float*)coords, *mk = (float*)colors;  // RAW: outputs
-#if GSR_CFG_RB2
     // one warp per 32 Gaussians (warps stride over the chunks only when the grid limit is hit)
     const long long want = ((long long)s + GSR_RB2_THREADS - 1) / GSR_RB2_THREADS;
     const int grid = (int)(want < (1 << 20) ? want : (1 << 20));
 #define GSR_RB_LAUNCH(RG, RW, a0, a1, a2, o0, o1, o2, stp) \
   gsr_region_build2_kernel<RG, RW><<<grid, GSR_RB2_THREADS, 0, st>>>(a0, a1, a2, o0, o1, o2, s, h, w, dmax, keff, ec, stp, ws)
-#else
-    // persistent CTAs: one resident wave, every CTA strides over the chunks of the input
-    int cap = 0;
-    const int rc = gsr_resident_grid(gsr_region_build_kernel<false, false>, GSR_RB_THREADS, 0, &cap);
-    if (rc) return rc;
-    const int want = (s + GSR_RB_THREADS - 1) / GSR_RB_THREADS, grid = want < cap ? want : cap;
-#define GSR_RB_LAUNCH(RG, RW, a0, a1, a2, o0, o1, o2, stp) \
-  gsr_region_build_kernel<RG, RW><<<grid, GSR_RB_THREADS, 0, st>>>(a0, a1, a2, o0, o1, o2, s, h, w, dmax, keff, ec, stp, ws)
-#endif
     if (raw) {
       if (ws.ragged) GSR_RB_LAUNCH(true, true, raw, nullptr, nullptr, ms, mc, mk, step);
       else GSR_RB_LAUNCH(false, true, raw, nullptr, nullptr, ms, mc, mk, step);
