@@ -30,6 +30,9 @@ constexpr int GSR_WS_STAGES = 3;
 // (-DGSR_CFG_WS_MIN_CTAS=4): the CTA is allocated 64 registers per thread, the warpgroup of producers gives
 // registers back and the warpgroup of consumers takes them (setmaxnreg 48 / 80, 56 / 72, 40 / 88: sixteen + sixteen
 // warps per SM) -- no faster at HL (302-306 us vs 302 us) and slower on small images (C2 75 vs 62 us).
+#ifndef GSR_CFG_WS_SYNC_ARRIVE
+#define GSR_CFG_WS_SYNC_ARRIVE 0
+#endif
 #ifndef GSR_CFG_WS_PROD_REGS
 #define GSR_CFG_WS_PROD_REGS 48
 #endif
@@ -199,7 +202,14 @@ __global__ void __launch_bounds__(GSR_WS_THREADS, GSR_CFG_WS_MIN_CTAS) gsr_forwa
         }
       }
       // the lane's share of "full": arrives by itself when the copies this lane issued so far have landed
+#if GSR_CFG_WS_SYNC_ARRIVE
+      // (checking aid: compute-sanitizer's racecheck does not follow cp.async.mbarrier.arrive -- it reports every
+      // staged record as a write/read hazard; waiting for the copies and arriving explicitly is equivalent and clean)
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      gsr_mbar_arrive(full_s + s * 8);
+#else
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_s + s * 8) : "memory");
+#endif
       int trip = 0;
       unsigned slow_a = 0, slow_b = 0;
       if (!stop) {

@@ -1,5 +1,6 @@
 """Small end-to-end exercise of every kernel path for compute-sanitizer (memcheck / racecheck / initcheck):
-forward (region path, window-binding path, bucket-overflow fallback), backward, bands, batch, window, uint8."""
+forward (region path, window-binding path, bucket-overflow fallback incl. its grid barriers), backward, bands, batch,
+window, uint8, deterministic mode, row stores, fused loss."""
 import os, sys
 import numpy as np
 import torch
@@ -46,6 +47,19 @@ raw = torch.randn(3, 256, 9, device=dev); raw[..., 7:9] = torch.rand(3, 256, 2, 
 raw.requires_grad_(True)
 out = gsp.generate_2D_gaussian_splatting_step_batch_padded([torch.tensor(z) for z in sizes], raw, [2.0, 1.5, 2.5], dmax=0.3, fused=True)
 out.sum().backward()
+# round 2: deterministic mode (bucket sort, short and long buckets), row stores, staged uint8, fused loss
+from gsasr_b200 import losses
+_, s, c, k, h, w = fields.make("C1", 1)
+sd, cd, kd = s.to(dev), c.to(dev), k.to(dev)
+img = torch.zeros(h, w, 3, device=dev)
+gscuda.gs_render(sd, cd, kd, img, s.shape[0], h, w, 3, 0.1, flags=0x1 | 0x10 | 0x20)
+big = field(2000, (0.5, 2.0))
+img2 = torch.zeros(37, 53, 3, device=dev)
+gscuda.gs_render(*big, img2, 2000, 37, 53, 3, flags=0x20)
+u8 = torch.empty(h, w, 3, dtype=torch.uint8, device=dev)
+gscuda.gs_render_u8(sd, cd, kd, u8, s.shape[0], h, w, 0.1)
+srb = torch.rand(3, 3, 40, 52, device=dev).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2).requires_grad_(True)
+losses.l1_crop_loss_padded(srb, torch.rand(3, 3, 44, 60, device=dev), sizes, 0.5).backward()
 _, s, c, k, h, w = fields.make("C1", 0)
 sharding.render_image_bands(s.to(dev), c.to(dev), k.to(dev), h, w, 0.1)
 torch.cuda.synchronize()

@@ -8,6 +8,7 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "variants")
 VARIANTS = {
     "base": [],
+    "ws_sync_arrive": ["GSR_CFG_WS_SYNC_ARRIVE=1"],
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
