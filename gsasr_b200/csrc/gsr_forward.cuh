@@ -477,6 +477,9 @@ static_assert(GSR_FR_LW == 2 || GSR_FR_LW == 4, "list entries are 16- or 32-bit 
 #ifndef GSR_CFG_FR_MIN_CTAS
 #define GSR_CFG_FR_MIN_CTAS 5
 #endif
+#ifndef GSR_CFG_FR_UNROLL8
+#define GSR_CFG_FR_UNROLL8 1   // eight list positions per iteration while they last, then four, then singly (-1.7 %)
+#endif
 static_assert(GSR_RGW == 16 && GSR_RGH == 8 && GSR_CELL == 4, "a warp of 2x2 blocks covers a 16x8 region, four lanes a cell");
 
 struct GsrFwdRegionSmem {
@@ -883,6 +886,17 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_FR_MIN_CTAS) gsr_forwa
     if ((slow_ac | slow_bc) == 0) {
 #if GSR_CFG_FR_TAIL
       int t = 0;
+#if GSR_CFG_FR_UNROLL8
+      for (; t + 8 <= trip; t += 8) {
+        uint32_t a4[4], b4[4];
+        gsr_fr_load4(lb, t, a4);
+        gsr_fr_load4(lb, t + 4, b4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gsr_eval_quad<false>(a4[k], a4[k] + GSR_FR_HI, nx2, ny2, true, true, true, true, r0, g0, b0, r1, g1, b1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) gsr_eval_quad<false>(b4[k], b4[k] + GSR_FR_HI, nx2, ny2, true, true, true, true, r0, g0, b0, r1, g1, b1);
+      }
+#endif
       for (; t + 4 <= trip; t += 4) {
         uint32_t a4[4];
         gsr_fr_load4(lb, t, a4);
