@@ -11,7 +11,8 @@
 Reported per variant: ms per step (max over ranks), the render's own forward+backward time on the same tensors and
 its share of the step.  Render variants: `reference-loop` = the reference's generate_2D_gaussian_splatting_step
 (its own file, running on this repo's gscuda) once per sample, as gsasr_model.py:191-233 does; `batch` = one
-uniform-batch call of this library (one set-up + one raster launch each way).
+uniform-batch call of this library (one set-up + one raster launch each way); `batch-fused` = the same with the front
+end folded into the set-up kernel and the L1 loss + its gradient as one kernel (losses.l1_crop_loss_padded).
 
     torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/train_step_c5.py [--ddp] [--steps 5]
     python tools/train_step_c5.py --per-gpu 1 --depth tiny          (single GPU smoke run)
@@ -21,6 +22,7 @@ import torch
 import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gsasr_b200 import gaussian_splatting as gsp
+from gsasr_b200 import losses
 from oracle import ref_py
 
 ap = argparse.ArgumentParser()
@@ -103,18 +105,31 @@ out = {"config": f"C5: {world} GPU(s) x {B} samples, {lr}x{lr} LR -> x{sc:g} ({H
 with torch.no_grad():
     n_per = int(head_forward().shape[1])
 out["gaussians_per_sample"] = n_per
-for name, render in (("reference-loop", render_reference_loop), ("batch", render_batch)):
+def render_batch_fused(params):  # + the front end folded into the set-up kernel
+    return gsp.generate_2D_gaussian_splatting_step_batch(sr_size, params, sc, scale_modify, dmax=args.dmax, fused=True)
+
+
+def loss_torch(sr):
+    return (sr - gt).abs().mean()
+
+
+def loss_fused(sr):  # crop + L1 + gradient in one kernel (equal sizes: the crop is the whole image)
+    return losses.l1_crop_loss_padded(sr, gt, [(H, W)] * B)
+
+
+for name, render, loss_fn in (("reference-loop", render_reference_loop, loss_torch), ("batch", render_batch, loss_torch),
+                              ("batch-fused", render_batch_fused, loss_fused)):
     def step():
         opt.zero_grad(set_to_none=True)
         params = head_forward()
-        loss = (render(params) - gt).abs().mean()
+        loss = loss_fn(render(params))
         loss.backward()
         opt.step()
     params0 = head_forward().detach()
 
     def render_only():
         p = params0.clone().requires_grad_(True)
-        (render(p) - gt).abs().mean().backward()
+        loss_fn(render(p)).backward()
 
     def head_only():
         opt.zero_grad(set_to_none=True)
