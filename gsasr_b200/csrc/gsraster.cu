@@ -290,6 +290,9 @@ static int gsr_prepare_forward(const float* sigmas, const float* coords, const f
   return gsr_run_tiles(sigmas, coords, colors, s, h, w, dmax, keff, ws, st, raw, step);
 }
 
+#ifndef GSR_CFG_FALLBACK_COOP
+#define GSR_CFG_FALLBACK_COOP 1
+#endif
 // The fallback as one launch: home-bin set-up + raster over the home bins, all of it skipped on the device unless
 // a bucket overflowed (gsr_forward_fallback_kernel).
 static int gsr_launch_forward_fallback(const GsrWorkspace& ws, float* img, int h, int w, float keff, uint32_t flags,
@@ -304,12 +307,17 @@ static int gsr_launch_forward_fallback(const GsrWorkspace& ws, float* img, int h
   int cap = 0;  // every CTA must be resident: the phases are separated by grid barriers
   rc = gsr_resident_grid(gsr_forward_fallback_kernel<false>, GSR_FWD_THREADS, 3, &cap, sizeof(GsrFwdSmem));
   if (rc) return rc;
-  if (ws.ragged)
-    gsr_forward_fallback_kernel<true><<<cap, GSR_FWD_THREADS, sizeof(GsrFwdSmem), st>>>(a, sigmas, coords, colors, s,
-                                                                                         dmax, keff, ws);
-  else
-    gsr_forward_fallback_kernel<false><<<cap, GSR_FWD_THREADS, sizeof(GsrFwdSmem), st>>>(a, sigmas, coords, colors, s,
-                                                                                          dmax, keff, ws);
+  // A COOPERATIVE launch: the driver starts the grid only when all of its CTAs can be resident at once, so the
+  // barriers cannot deadlock against other work on the device (e.g. a second forward call on another stream).
+  GsrWorkspace wsv = ws;
+  void* args[] = {(void*)&a, (void*)&sigmas, (void*)&coords, (void*)&colors, (void*)&s, (void*)&dmax, (void*)&keff,
+                  (void*)&wsv};
+  const void* fn = ws.ragged ? (const void*)gsr_forward_fallback_kernel<true> : (const void*)gsr_forward_fallback_kernel<false>;
+#if GSR_CFG_FALLBACK_COOP
+  GSR_CUDA(cudaLaunchCooperativeKernel(fn, dim3(cap), dim3(GSR_FWD_THREADS), args, sizeof(GsrFwdSmem), st));
+#else
+  GSR_CUDA(cudaLaunchKernel(fn, dim3(cap), dim3(GSR_FWD_THREADS), args, sizeof(GsrFwdSmem), st));
+#endif
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
 }

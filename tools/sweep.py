@@ -9,6 +9,7 @@ VDIR = os.path.join(ROOT, "variants")
 VARIANTS = {
     "base": [],
     "ws_sync_arrive": ["GSR_CFG_WS_SYNC_ARRIVE=1"],
+    "fallback_plain_launch": ["GSR_CFG_FALLBACK_COOP=0"],
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
