@@ -80,6 +80,7 @@ SIGNATURES = {
                                                 ctypes.POINTER(_f), ctypes.POINTER(_f), _f, _f, _vp, _sz, _vp]),
     "gsr_frontend_forward": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _vp, _sz, _vp]),
     "gsr_frontend_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _vp, _sz, _vp]),
+    "gsr_head_tail_forward": (_i, [_vp] * 8 + [_i, _i, _i, _vp]),
     "gsr_l1_crop_workspace_bytes": (_sz, []),
     "gsr_l1_crop_loss": (_i, [_vp, ctypes.POINTER(ctypes.c_longlong), _vp, ctypes.POINTER(ctypes.c_longlong), _vp, _vp,
                               _i, _i, _i, ctypes.POINTER(_i), _f, _i, _vp, _sz, _vp]),
@@ -93,6 +94,7 @@ TEST_SIGNATURES = {
     "gsr_host_region_mask": (ctypes.c_uint, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _i, _i]),
     "gsr_host_entries": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _i]),
     "gsr_host_geometry": (None, [ctypes.POINTER(_i)] * 5),
+    "gsr_test_umma_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
 }
 
 _lib = None

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgsraster.so")
 
-SOURCES = ["gsraster.cu"]
+SOURCES = ["gsraster.cu", "gsr_head.cu"]
 HEADERS = [
     "gsr_common.cuh",
     "gsr_prepass.cuh",
@@ -26,6 +26,8 @@ HEADERS = [
     "gsr_forward_ws.cuh",
     "gsr_backward.cuh",
     "gsr_frontend.cuh",
+    "gsr_loss.cuh",
+    "gsr_umma.cuh",
     os.path.join("..", "..", "include", "gsraster.h"),
 ]
 

@@ -283,6 +283,26 @@ int gsr_l1_crop_loss(const float* sr, const long long* sr_strides, const float* 
                      float* grad, float* loss, int batch, int hmax, int wmax, const int* hw_host, float weight,
                      int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Head-tail fusion (utils/fea2gs.py:496-541 and :611-633; the same code in utils/fea2gsropeamp.py:571-719): the five
+ * per-Gaussian MLPs  Linear(C,C) - ReLU - Linear(C,4C) - ReLU - Linear(4C,k),  k = 2 (sigma), 1 (rho), 1 (alpha),
+ * 3 (rgb), 2 (mean), on the (m, C) feature rows after UPNet, the normalisation of the means by the grid size, the
+ * reference points and the concatenation -- ONE kernel on the tcgen05 tensor cores (bf16 operands, fp32 accumulation
+ * in tensor memory; the hidden layers never reach HBM).  Forward only (inference).
+ *   x_bf16   (m, 192) bf16: the feature rows, channels zero-padded to 192 (C = 180 or 192); row = (sample, iy, ix)
+ *   w1_bf16  (5*192, 192) bf16: first Linear of the five MLPs, [out, in] as nn.Linear stores it, zero-padded
+ *   b1       (5, 192) fp32
+ *   w2_bf16  (5*768, 192) bf16: second Linear, [out, in], zero-padded (4C = 720 or 768)
+ *   b2       (5, 768) fp32
+ *   w3       (9, 768) fp32: last Linear, rows in output order sigma_x, sigma_y, rho, alpha, r, g, b, mean_x, mean_y
+ *   b3       (9) fp32
+ *   raw      (m, 9) fp32, written: what torch.cat([...], dim=-1) returns at fea2gs.py:632 -- the input of
+ *            generate_2D_gaussian_splatting_step / gsr_frontend_forward
+ *   grid_h, grid_w: the Gaussian grid of one sample (m = samples * grid_h * grid_w).
+ * Pointers 16-byte aligned.  Arithmetic: the reference under bf16 autocast with the last Linear kept in fp32. */
+int gsr_head_tail_forward(const void* x_bf16, const void* w1_bf16, const float* b1, const void* w2_bf16,
+                          const float* b2, const float* w3, const float* b3, float* raw, int m, int grid_h,
+                          int grid_w, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

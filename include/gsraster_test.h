@@ -25,6 +25,9 @@ unsigned gsr_host_region_mask(const float* sigmas, const float* coords, const fl
 int gsr_host_entries(const float* sigmas, const float* coords, const float* colors, int i, int h, int w,
                      float dmax, float ksigma, int* out, int cap);
 void gsr_host_geometry(int* tile_w, int* tile_h, int* bin, int* region, int* large_px);
+/* unit test of the tcgen05 / TMEM / TMA building block of the head-tail kernel (needs a GPU): c (m x n fp32) =
+ * a (m x 192 bf16) * b (n x 192 bf16)^T, m % 128 == 0, n = 128 or 192, one 128-row tile per CTA */
+int gsr_test_umma_gemm(const void* a_bf16, const void* b_bf16, float* c, int m, int n, int k, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,93 @@
+"""Head-tail fusion (gsr_head_tail_forward: the five MLPs of the fea2gs head on the tcgen05 tensor cores) against the
+reference's expression (utils/fea2gs.py:496-541, 611-633) evaluated with torch.  Needs a GPU: `-m gpu`."""
+import pytest
+import torch
+import torch.nn as nn
+
+from gsasr_b200 import _lib, head_tail
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _blocks(c, seed):
+    torch.manual_seed(seed)
+    return [nn.Sequential(nn.Linear(c, c), nn.ReLU(), nn.Linear(c, 4 * c), nn.ReLU(), nn.Linear(4 * c, k)).to(DEV)
+            for k in (2, 1, 1, 3, 2)]   # mlp_block_sigma / rho / alpha / rgb / mean, gs_up_factor = 1
+
+
+def _reference(query, blks, emulate):
+    """fea2gs.py:611-633 on the (b, H, W, C) map.  emulate=True: the kernel's arithmetic (bf16 operands, fp32
+    accumulation, first hidden layer rounded to bf16, last Linear in fp32)."""
+    b, gh, gw, _ = query.shape
+    outs = []
+    for blk in blks:
+        if emulate:
+            x = query.to(torch.bfloat16).float()
+            h1 = torch.relu(x @ blk[0].weight.to(torch.bfloat16).float().t() + blk[0].bias).to(torch.bfloat16).float()
+            h2 = torch.relu(h1 @ blk[2].weight.to(torch.bfloat16).float().t() + blk[2].bias)
+            outs.append(h2 @ blk[4].weight.t() + blk[4].bias)
+        else:
+            outs.append(blk(query))
+    sig, rho, al, rgb, mean = [o.reshape(b, -1, o.shape[-1]) for o in outs]
+    mean = mean / torch.tensor([gw, gh], device=query.device)[None, None]
+    sy, sx = 1 / gh, 1 / gw
+    ry, rx = torch.meshgrid(torch.linspace(sy / 2, 1 - sy / 2, gh, dtype=torch.float32, device=query.device),
+                            torch.linspace(sx / 2, 1 - sx / 2, gw, dtype=torch.float32, device=query.device), indexing="ij")
+    mean = mean + torch.stack((rx.reshape(-1), ry.reshape(-1)), -1)[None]
+    return torch.cat([sig, rho, al, rgb, mean], -1)
+
+
+def test_umma_building_block_matches_matmul():
+    """One 128 x n tile per CTA: TMA (128-byte swizzle) -> tcgen05.mma (kind::f16, bf16 -> fp32 in TMEM) -> tcgen05.ld."""
+    L = _lib.load()
+    torch.manual_seed(0)
+    for m, n in ((128, 192), (512, 192), (256, 128)):
+        a = torch.randn(m, 192, device=DEV).to(torch.bfloat16)
+        b = torch.randn(n, 192, device=DEV).to(torch.bfloat16)
+        c = torch.full((m, n), float("nan"), device=DEV)
+        _lib.check(L.gsr_test_umma_gemm(a.data_ptr(), b.data_ptr(), c.data_ptr(), m, n, 192, None))
+        torch.cuda.synchronize()
+        ref = a.float() @ b.float().t()
+        assert float((c - ref).abs().max()) <= 1e-3  # fp32 accumulation order only
+
+
+@pytest.mark.parametrize("c,b,gh,gw", [(192, 1, 16, 8), (192, 2, 48, 40), (180, 1, 24, 24), (192, 1, 64, 75),
+                                       (180, 3, 5, 7)])
+def test_fused_head_tail_matches_the_reference_expression(c, b, gh, gw):
+    """Against the same arithmetic in torch (tight) and against the reference's fp32 modules (bf16 operand rounding:
+    the tolerance of the reference's own bf16-autocast training path); partial last tile, C = 180 padding, the
+    reference-point columns exactly."""
+    blks = _blocks(c, seed=c + gh)
+    q = torch.randn(b, gh, gw, c, device=DEV)
+    pk = head_tail.PackedHeadTail(blks, DEV)
+    out = head_tail.fused_head_tail(q, pk)
+    assert out.shape == (b, gh * gw, 9)
+    with torch.no_grad():
+        emu, ref = _reference(q, blks, True), _reference(q, blks, False)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            amp = _reference(q, blks, False).float()
+    assert float((out - emu).abs().max()) <= 2e-3   # a hidden activation on a bf16 rounding boundary
+    assert float((out - ref).abs().max()) <= 1e-2   # bf16 operands vs fp32
+    assert float((out - ref).abs().max()) <= 1.5 * float((amp - ref).abs().max()) + 1e-3   # no worse than autocast
+    # means: zero weights -> exactly the reference points (torch.linspace's formula)
+    for blk in blks:
+        for lin in (blk[0], blk[2], blk[4]):
+            nn.init.zeros_(lin.weight), nn.init.zeros_(lin.bias)
+    z = head_tail.fused_head_tail(q, head_tail.PackedHeadTail(blks, DEV))
+    with torch.no_grad():
+        assert torch.equal(z, _reference(q, blks, False))
+
+
+def test_fused_head_tail_feeds_the_renderer():
+    """raw (b, N, 9) is what generate_2D_gaussian_splatting_step takes: head tail -> fused front end -> raster."""
+    from gsasr_b200 import gaussian_splatting as gsp
+
+    blks = _blocks(192, seed=1)
+    q = torch.randn(1, 32, 32, 192, device=DEV)
+    raw = head_tail.fused_head_tail(q, head_tail.PackedHeadTail(blks, DEV))
+    with torch.no_grad():
+        ref = _reference(q, blks, False)
+    a = gsp.generate_2D_gaussian_splatting_step(torch.tensor([64, 64]), raw[0], 2.0, torch.tensor([2.0, 2.0]), dmax=0.3, fused=True)
+    b = gsp.generate_2D_gaussian_splatting_step(torch.tensor([64, 64]), ref[0], 2.0, torch.tensor([2.0, 2.0]), dmax=0.3, fused=True)
+    assert a.shape == (3, 64, 64) and float((a - b).abs().max()) <= 5e-2
