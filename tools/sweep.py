@@ -10,6 +10,7 @@ VARIANTS = {
     "base": [],
     "ws_sync_arrive": ["GSR_CFG_WS_SYNC_ARRIVE=1"],
     "fallback_plain_launch": ["GSR_CFG_FALLBACK_COOP=0"],
+    "head_parts2": ["GSH_CFG_EPI_PARTS=2"],
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
