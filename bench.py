@@ -26,6 +26,9 @@ and the image resident in HBM.  What the JSON line carries besides the contract'
                  sample; `cpu_reference_python` = the reference's OWN PyTorch-CPU renderer (rendering_python,
                  unmodified, BASELINE config 1) timed on the same host cores.
   gpu_reference  the reference's own CUDA kernels (oracle/_ref, rebuilt for sm_100a) on BASELINE config 2, same box.
+  head_tail      (beside the headline) the five MLPs that produce the headline field's 2,097,152 raw
+                 Gaussians from (N, 192) features, as ONE tcgen05 kernel: ms, TFLOP/s, fraction of the measured bf16
+                 tensor peak, and torch's bf16-autocast time for the same modules.
 """
 from __future__ import annotations
 
@@ -211,6 +214,57 @@ def cpu_reference_python():
         return {"value": h * w / 1e6 / t, "unit": UNIT, "seconds_per_call": t, "cores": cores, "kind": "reference",
                 "config": "C1: 64x64 LR -> x2, 16,384 Gaussians, 128x128 (BASELINE configs[0])",
                 "sample": "whole image, median of 3 calls after 1 warm-up, torch CPU threads = cores"}
+    except Exception as exc:
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+
+
+def head_tail_bench(dev):
+    """gsr_head_tail_forward at the headline field's size (1024 x 2048 Gaussian grid, C = 192) beside torch running the
+    same five nn.Sequential MLPs under bf16 autocast (a quarter of the rows, extrapolated: the unfused path
+    materialises rows x 768 activations per head)."""
+    try:
+        import torch
+        import torch.nn as nn
+
+        from gsasr_b200 import head_tail
+
+        c, gh, gw = 192, 1024, 2048
+        torch.manual_seed(0)
+        blks = [nn.Sequential(nn.Linear(c, c), nn.ReLU(), nn.Linear(c, 4 * c), nn.ReLU(), nn.Linear(4 * c, k)).to(dev)
+                for k in (2, 1, 1, 3, 2)]
+        pk = head_tail.PackedHeadTail(blks, dev)
+        q = torch.randn(1, gh, gw, c, device=dev, dtype=torch.bfloat16)
+
+        def ev(fn, reps):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        ms = ev(lambda: head_tail.fused_head_tail(q, pk), 5)
+        flop = 2.0 * gh * gw * (5 * (c * c + c * 4 * c) + 4 * c * 9)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            qs = q[:, :gh // 4]
+            ref_ms = 4 * ev(lambda: [blk(qs) for blk in blks], 3)
+        peak = None
+        try:
+            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        except Exception:
+            pass
+        tf = flop / (ms * 1e-3) / 1e12
+        return {"rows": gh * gw, "channels": c, "ms": ms, "tflops": tf, "flop": flop,
+                "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
+                             "frac": (tf / peak) if peak else None,
+                             "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, cuBLAS burst)"},
+                "torch_bf16_autocast_ms": ref_ms,
+                "note": "gsr_head_tail_forward: TMA weight ring -> tcgen05.mma (bf16, fp32 in TMEM) -> epilogue "
+                        "(ReLU, next operand in shared memory, last Linear on the CUDA cores); includes the bf16 "
+                        "cast of the features"}
     except Exception as exc:
         return {"unavailable": f"{type(exc).__name__}: {exc}"}
 
@@ -663,6 +717,7 @@ def main():
             out["strong"] = strong
         if world == 1 and not args.no_extras:
             out["gpu_reference"] = gpu_reference(dev)
+            out["head_tail"] = head_tail_bench(dev)
         if not args.no_cpu_baseline and world == 1:
             mps, cores, sample, _ = cpu_sample(args.workload)
             out["cpu_baseline"] = {"value": mps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
