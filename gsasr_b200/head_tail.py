@@ -82,3 +82,41 @@ def fused_head_tail(query: torch.Tensor, packed: PackedHeadTail) -> torch.Tensor
                                      m, gh, gw, torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)
     return raw.view(b, gh * gw, 9)
+
+
+class _CaptureTail(torch.nn.Module):
+    """Stands in for one mlp_block_* while the reference head's own forward runs: remembers the feature map the tail is
+    applied to and returns zeros of the right shape (the reference's concatenation of them is discarded)."""
+
+    def __init__(self, k, store):
+        super().__init__()
+        self.k, self.store = k, store
+
+    def forward(self, query):
+        if not self.store:
+            self.store.append(query)
+        return query.new_zeros(*query.shape[:-1], self.k)
+
+
+def forward_fused_tail(head, srcs, scale, packed: PackedHeadTail | None = None) -> torch.Tensor:
+    """``head(srcs, scale)`` of a reference Fea2GS / Fea2GS_ROPE_AMP instance (utils/fea2gs.py:565-633,
+    utils/fea2gsropeamp.py:655-719) with its tail -- the five MLPs, the mean normalisation, the reference points, the
+    concatenation -- computed by the fused tensor-core kernel.  The body (embeddings, window cross-attention, Gaussian
+    self-attention, UPNet) is the module's OWN forward, unmodified: the five ``mlp_block_*`` are swapped for capture
+    stubs while it runs.  Inference only (no gradient flows through the fused tail)."""
+    if packed is None:
+        packed = getattr(head, "_gsr_packed_tail", None)
+        if packed is None:
+            packed = PackedHeadTail.from_module(head)
+            head._gsr_packed_tail = packed  # (weights are read once: rebuild after loading another checkpoint)
+    store, saved = [], {}
+    try:
+        for name, k in zip(_ORDER, _KOUT):
+            saved[name] = head._modules[name]
+            head._modules[name] = _CaptureTail(k, store)
+        with torch.no_grad():
+            head(srcs, scale)
+    finally:
+        for name, mod in saved.items():
+            head._modules[name] = mod
+    return fused_head_tail(store[0], packed)

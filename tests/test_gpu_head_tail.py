@@ -91,3 +91,32 @@ def test_fused_head_tail_feeds_the_renderer():
     a = gsp.generate_2D_gaussian_splatting_step(torch.tensor([64, 64]), raw[0], 2.0, torch.tensor([2.0, 2.0]), dmax=0.3, fused=True)
     b = gsp.generate_2D_gaussian_splatting_step(torch.tensor([64, 64]), ref[0], 2.0, torch.tensor([2.0, 2.0]), dmax=0.3, fused=True)
     assert a.shape == (3, 64, 64) and float((a - b).abs().max()) <= 5e-2
+
+
+def test_reference_head_with_fused_tail_is_a_drop_in():
+    """The reference's OWN Fea2GS module (utils/fea2gs.py, staged unmodified by oracle/ref_py.py) end to end:
+    head(srcs, scale) against forward_fused_tail(head, srcs, scale) -- same body, fused tail -- and the images both
+    parameter sets render to."""
+    from oracle import ref_py
+    if not ref_py.have():
+        pytest.skip("reference python files not staged (oracle/_ref/ref_py)")
+    from gsasr_b200 import gaussian_splatting as gsp
+
+    fea2gs = ref_py.load("utils.fea2gs")
+    torch.manual_seed(0)
+    head = fea2gs.Fea2GS(inchannel=64, channel=180, num_heads=6, num_gs_seed=64, window_size=8, num_crossattn_blocks=1,
+                         num_crossattn_layers=1, num_selfattn_blocks=1, num_selfattn_layers=1).to(DEV).eval()
+    srcs = torch.randn(2, 64, 16, 24, device=DEV)
+    scale = torch.tensor([2.0, 2.0], device=DEV)
+    with torch.no_grad():
+        want = head(srcs, scale)                      # (2, N, 9), fp32 modules
+    got = head_tail.forward_fused_tail(head, srcs, scale)
+    assert got.shape == want.shape
+    assert isinstance(head.mlp_block_sigma, torch.nn.Sequential)   # the module is left as it was
+    assert float((got - want).abs().max()) <= 2e-2                 # bf16 operands vs fp32 modules, |params| ~ 1
+    assert float((got[..., 7:9] - want[..., 7:9]).abs().max()) <= 1e-3   # means: divided by the grid size
+    h, w = 32, 48
+    for b in range(2):
+        a = gsp.generate_2D_gaussian_splatting_step(torch.tensor([h, w]), got[b], 2.0, torch.tensor([2.0, 2.0]), dmax=0.3, fused=True)
+        r = gsp.generate_2D_gaussian_splatting_step(torch.tensor([h, w]), want[b], 2.0, torch.tensor([2.0, 2.0]), dmax=0.3, fused=True)
+        assert float((a - r).abs().max()) <= 0.05 * max(1.0, float(r.abs().max()))
