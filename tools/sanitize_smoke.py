@@ -60,6 +60,11 @@ u8 = torch.empty(h, w, 3, dtype=torch.uint8, device=dev)
 gscuda.gs_render_u8(sd, cd, kd, u8, s.shape[0], h, w, 0.1)
 srb = torch.rand(3, 3, 40, 52, device=dev).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2).requires_grad_(True)
 losses.l1_crop_loss_padded(srb, torch.rand(3, 3, 44, 60, device=dev), sizes, 0.5).backward()
+# head tail (tcgen05 / TMEM / TMA): two tiles, the second partial; C = 180 padding
+import torch.nn as nn
+from gsasr_b200 import head_tail
+blks = [nn.Sequential(nn.Linear(180, 180), nn.ReLU(), nn.Linear(180, 720), nn.ReLU(), nn.Linear(720, kk)).to(dev) for kk in (2, 1, 1, 3, 2)]
+head_tail.fused_head_tail(torch.randn(1, 12, 15, 180, device=dev), head_tail.PackedHeadTail(blks, dev))
 _, s, c, k, h, w = fields.make("C1", 0)
 sharding.render_image_bands(s.to(dev), c.to(dev), k.to(dev), h, w, 0.1)
 torch.cuda.synchronize()
