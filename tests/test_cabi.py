@@ -225,3 +225,33 @@ def test_argument_validation_of_the_fused_loss():
     assert f(fake, st, fake, st, fake, fake, 2, 8, 8, hw, 1.0, 0, ws, need, None) == 2        # w_1 = 9 > wmax
     assert f(fake, st, fake, st, fake, fake, 1, 8, 8, hw, 1.0, 0, ws, 16, None) == 4          # workspace too small
     assert f(fake, st, fake, st, fake, fake, 1, 8, 8, hw, 1.0, 0, None, need, None) == 4
+
+
+def test_argument_validation_of_the_head_tail():
+    L = _lib.load()
+    fake = ctypes.c_void_p(256)
+    f = L.gsr_head_tail_forward
+    assert f(None, fake, fake, fake, fake, fake, fake, fake, 128, 8, 16, None) == 1     # x NULL
+    assert f(fake, fake, fake, fake, fake, fake, fake, None, 128, 8, 16, None) == 1     # raw NULL
+    assert f(fake, fake, fake, fake, fake, fake, fake, fake, -1, 8, 16, None) == 2      # m < 0
+    assert f(fake, fake, fake, fake, fake, fake, fake, fake, 128, 0, 16, None) == 2     # empty grid
+    assert f(fake, fake, fake, fake, fake, fake, fake, fake, 0, 8, 16, None) == 0       # nothing to do
+
+
+def test_head_tail_weight_packing_needs_no_gpu():
+    """PackedHeadTail: C = 180 / 4C = 720 zero-padded to 192 / 768, rows of the last Linear in output order."""
+    import torch
+    import torch.nn as nn
+    from gsasr_b200 import head_tail
+
+    torch.manual_seed(0)
+    blks = [nn.Sequential(nn.Linear(180, 180), nn.ReLU(), nn.Linear(180, 720), nn.ReLU(), nn.Linear(720, k)) for k in (2, 1, 1, 3, 2)]
+    pk = head_tail.PackedHeadTail(blks, "cpu")
+    assert pk.w1.shape == (5 * 192, 192) and pk.w2.shape == (5 * 768, 192) and pk.w3.shape == (9, 768)
+    assert pk.w1.dtype == torch.bfloat16 and pk.b2.dtype == torch.float32
+    assert float(pk.w1[180:192].abs().max()) == 0 and float(pk.w1[:, 180:].abs().max()) == 0     # padding
+    assert float(pk.w2[720:768].abs().max()) == 0 and float(pk.w3[:, 720:].abs().max()) == 0
+    assert torch.equal(pk.w3[4:7, :720], blks[3][4].weight.detach())                             # rgb rows 4..6
+    assert torch.equal(pk.b3, torch.cat([b[4].bias.detach() for b in blks]))
+    with pytest.raises(RuntimeError):
+        head_tail.PackedHeadTail([nn.Sequential(nn.Linear(256, 256), nn.ReLU(), nn.Linear(256, 1024), nn.ReLU(), nn.Linear(1024, k)) for k in (2, 1, 1, 3, 2)], "cpu")
