@@ -424,13 +424,13 @@ gsh_head_tail_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       if (et == 0) GSH_TRACE(h * 64 + 3);
       const float* b1 = sb1 + h * GSH_CP;
 #pragma unroll 1
-      for (int c0 = part * 32; c0 < GSH_CP; c0 += 32 * GSH_PARTS) {
-        uint32_t v[32];
-        gsu::tmem_ld_32x32(tmem + lane_base + c0, v);
+      for (int c0 = part * 16; c0 < GSH_CP; c0 += 16 * GSH_PARTS) {  // 16-column pieces: twelve over the parts, evenly
+        uint32_t v[16];
+        gsu::tmem_ld_32x16(tmem + lane_base + c0, v);
         gsu::tmem_ld_wait();
         const int kb = c0 >> 6, chunk0 = (c0 & 63) >> 3;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {  // eight bf16 = one 16-byte chunk of the row
+        for (int g = 0; g < 2; ++g) {  // eight bf16 = one 16-byte chunk of the row
           const float4 ba = *reinterpret_cast<const float4*>(b1 + c0 + g * 8), bb = *reinterpret_cast<const float4*>(b1 + c0 + g * 8 + 4);
           const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
           uint32_t w[4];
