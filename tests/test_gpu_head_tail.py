@@ -120,3 +120,34 @@ def test_reference_head_with_fused_tail_is_a_drop_in():
         a = gsp.generate_2D_gaussian_splatting_step(torch.tensor([h, w]), got[b], 2.0, torch.tensor([2.0, 2.0]), dmax=0.3, fused=True)
         r = gsp.generate_2D_gaussian_splatting_step(torch.tensor([h, w]), want[b], 2.0, torch.tensor([2.0, 2.0]), dmax=0.3, fused=True)
         assert float((a - r).abs().max()) <= 0.05 * max(1.0, float(r.abs().max()))
+
+
+def test_pipeline_from_encoder_features_to_uint8_image():
+    """inference_paper.py:117-138 after the encoder: the reference's own decoder + its own
+    generate_2D_gaussian_splatting_step (running on this repo's gscuda) + numpy post-processing, against
+    pipeline.render_from_features (fused tail, fused front end, fused uint8 write-out)."""
+    import numpy as np
+    from oracle import ref_py
+    if not ref_py.have():
+        pytest.skip("reference python files not staged (oracle/_ref/ref_py)")
+    from gsasr_b200 import pipeline
+
+    fea2gs = ref_py.load("utils.fea2gs")
+    ref_gsp = ref_py.load("utils.gaussian_splatting")
+    torch.manual_seed(1)
+    head = fea2gs.Fea2GS(inchannel=64, channel=180, num_heads=6, num_gs_seed=64, window_size=8, num_crossattn_blocks=1,
+                         num_crossattn_layers=1, num_selfattn_blocks=1, num_selfattn_layers=1).to(DEV).eval()
+    feats = torch.randn(1, 64, 16, 16, device=DEV)
+    scale, size = 2.0, torch.tensor([32, 32])
+    with torch.no_grad():
+        params = head(feats, torch.tensor([scale], device=DEV))[0]
+        out = ref_gsp.generate_2D_gaussian_splatting_step(gs_parameters=params, sr_size=size, scale=scale, sample_coords=None,
+                                                          scale_modify=torch.tensor([scale, scale]), default_step_size=1.2,
+                                                          cuda_rendering=True, mode='scale_modify', if_dmax=True,
+                                                          dmax_mode='fix', dmax=0.3)
+    want = out.float().cpu().clamp_(0, 1).numpy()
+    want = (np.transpose(want[[2, 1, 0], :, :], (1, 2, 0)) * 255.0).round().astype(np.uint8)
+    got = pipeline.render_from_features(head, feats, scale, size, dmax=0.3)[0].cpu().numpy()
+    assert got.shape == want.shape == (32, 32, 3)
+    diff = np.abs(got.astype(np.int16) - want.astype(np.int16))
+    assert diff.max() <= 6 and diff.mean() <= 1.0     # bf16 tail vs fp32 modules: a few grey levels at most
