@@ -839,9 +839,10 @@ __device__ __noinline__ void gsr_rb_walk_generic(uint2 (*list)[32], int lane, co
 // terms are added in fp32 -- differs from run to run (as do the reference's atomicAdds).  Sorting every bucket by
 // Gaussian index makes buckets, chunks and cell lists functions of the input alone: the forward becomes
 // bit-reproducible (the backward already is: one warp owns a Gaussian, fixed sweep order, no atomics).  Indices
-// are unique within a bucket, so the rank of an entry is the number of smaller ones: counted against the whole
-// bucket in shared memory (four keys per LDS.128), no exchange network.  One warp per bucket; buckets longer than
-// GSR_SORT_MAX entries are sorted by a whole CTA through the bucket itself (rank pass, barrier, write pass).
+// are unique within a bucket.  One warp per bucket: a stable LSD radix sort in shared memory on the index minus the
+// bucket's smallest one (two 8-bit passes cover a fea2gs bucket); buckets longer than GSR_SORT_MAX entries are ranked
+// by a whole CTA through the bucket itself (an entry's rank is the number of smaller keys: rank pass, barrier, write
+// pass).
 constexpr int GSR_SORT_WARPS = 4;
 constexpr int GSR_SORT_MAX = 1024;  // entries per warp-sorted bucket (4 KB of shared memory per warp)
 
@@ -849,32 +850,76 @@ __global__ void __launch_bounds__(32 * GSR_SORT_WARPS)
 gsr_bucket_sort_kernel(uint32_t* __restrict__ entries, const int* __restrict__ reg_count, int cap, int nreg,
                        const int* guard, int want) {
   if (gsr_guard_skip(guard, want)) return;
-  __shared__ __align__(16) uint32_t buf[GSR_SORT_WARPS][GSR_SORT_MAX + 4];   // entries
-  __shared__ __align__(16) uint32_t kbuf[GSR_SORT_WARPS][GSR_SORT_MAX + 4];  // keys: index << 9 (flag bits shifted out)
+  __shared__ __align__(16) uint32_t buf[GSR_SORT_WARPS][2][GSR_SORT_MAX + 4];  // entries, ping-pong
+  __shared__ int hist[GSR_SORT_WARPS][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t* b = buf[warp];
-  uint32_t* kb = kbuf[warp];
-  constexpr int SH = 32 - GSR_ENT_MASK_SHIFT;
+  const unsigned full = 0xffffffffu, lt = (1u << lane) - 1u;
+  int* hs = hist[warp];
   for (int r = blockIdx.x * GSR_SORT_WARPS + warp; r < nreg; r += gridDim.x * GSR_SORT_WARPS) {
     const int n = min(__ldg(reg_count + r), cap);
     if (n < 2 || n > GSR_SORT_MAX) continue;  // (longer buckets: gsr_bucket_sort_long_kernel)
     uint32_t* e = entries + (size_t)r * cap;
-    const int n4 = (n + 3) & ~3;
-    for (int i = lane; i < n4; i += 32) {
-      const uint32_t v = i < n ? e[i] : 0xffffffffu;
-      b[i] = v;
-      kb[i] = i < n ? v << SH : 0xffffffffu;  // sentinel keys are never smaller
-    }
-    __syncwarp();
+    uint32_t* src = buf[warp][0];
+    uint32_t* dst = buf[warp][1];
+    uint32_t kmin = 0xffffffffu, kmax = 0u;
     for (int i = lane; i < n; i += 32) {
-      const uint32_t key = kb[i];
-      int rank = 0;
-      for (int j = 0; j < n4; j += 4) {
-        const uint4 q = *reinterpret_cast<const uint4*>(kb + j);
-        rank += (q.x < key) + (q.y < key) + (q.z < key) + (q.w < key);
-      }
-      e[rank] = b[i];
+      const uint32_t v = e[i], k = v & GSR_ENT_INDEX;
+      src[i] = v;
+      kmin = min(kmin, k);
+      kmax = max(kmax, k);
     }
+    kmin = __reduce_min_sync(full, kmin);
+    kmax = __reduce_max_sync(full, kmax);
+    // Stable LSD radix sort on (index - smallest index of the bucket), 8 bits per pass: the Gaussians of a region come
+    // from a few rows of the field, so two passes cover the range of a fea2gs bucket (three always suffice: 23 bits).
+    const uint32_t range = kmax - kmin;
+    const int passes = range < 256u ? 1 : range < 65536u ? 2 : 3;
+    for (int ps = 0; ps < passes; ++ps) {
+      const int shift = 8 * ps;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) hs[lane * 8 + k] = 0;
+      __syncwarp();
+      for (int i = lane; i < n; i += 32) atomicAdd(hs + ((((src[i] & GSR_ENT_INDEX) - kmin) >> shift) & 255u), 1);
+      __syncwarp();
+      {  // exclusive scan of the 256 counters: eight per lane
+        int c[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          c[k] = hs[lane * 8 + k];
+          sum += c[k];
+        }
+        int incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int t = __shfl_up_sync(full, incl, d);
+          if (lane >= d) incl += t;
+        }
+        int run = incl - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          hs[lane * 8 + k] = run;
+          run += c[k];
+        }
+      }
+      __syncwarp();
+      for (int i0 = 0; i0 < n; i0 += 32) {  // in order: entries with equal digits keep their order (stable)
+        const int i = i0 + lane;
+        const bool valid = i < n;
+        const uint32_t v = valid ? src[i] : 0u;
+        const int d = valid ? (int)((((v & GSR_ENT_INDEX) - kmin) >> shift) & 255u) : 256 + lane;
+        const unsigned peers = __match_any_sync(full, d);
+        const int base = valid ? hs[d] : 0;
+        __syncwarp();
+        if (valid && lane == __ffs(peers) - 1) hs[d] = base + __popc(peers);
+        __syncwarp();
+        if (valid) dst[base + __popc(peers & lt)] = v;
+      }
+      __syncwarp();
+      uint32_t* t = src;
+      src = dst;
+      dst = t;
+    }
+    for (int i = lane; i < n; i += 32) e[i] = src[i];
     __syncwarp();
   }
 }

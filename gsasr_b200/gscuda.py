@@ -43,7 +43,7 @@ _deterministic = os.environ.get("GSR_DETERMINISTIC", "0") not in ("", "0")
 
 def set_deterministic(on: bool) -> None:
     """Bit-reproducible forward renders (GSR_FLAG_DETERMINISTIC: every region list is sorted by Gaussian index
-    before it is rasterised, ~10 % slower).  The reference's atomicAdd accumulation (gs.cu:58-60) is not
+    before it is rasterised, ~30 % slower).  The reference's atomicAdd accumulation (gs.cu:58-60) is not
     reproducible run to run; neither is this library's default forward (in the last bits).  The backward always
     is.  Also settable with GSR_DETERMINISTIC=1 in the environment."""
     global _deterministic

@@ -93,7 +93,7 @@ typedef enum gsr_status {
 #define GSR_FLAG_ROW_STORES 0x10u
 /* forward: bit-reproducible output.  The lists a region's pixels are summed from are filled with atomics, so
  * the fp32 summation order -- like that of the reference's atomicAdd (gs.cu:58-60) -- differs from run to run in
- * the last bits.  With this flag every list is sorted by Gaussian index first (HL: +~10 % time): the image is
+ * the last bits.  With this flag every list is sorted by Gaussian index first (HL: +30 % of the step): the image is
  * then a function of the inputs alone.  Holds while the region lists fit their buckets (no fallback to the
  * home-bin kernel) and no bucket exceeds 8192 entries; the backward is always deterministic. */
 #define GSR_FLAG_DETERMINISTIC 0x20u
