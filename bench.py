@@ -80,8 +80,30 @@ def bind_to_gpu_numa(local: int):
         dom, rest = bus.split(":", 1)
         path = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}/numa_node"
         node = int(open(path).read().strip())
+        how = "sysfs"
         if node < 0:
-            return {"numa_node": None, "note": "no NUMA information for this GPU"}
+            # virtualised boxes hide the PCI device's node: NVML's own CPU affinity for the GPU, else an even split of
+            # the GPUs over the host's memory nodes (GPUs 0..n/2-1 on node 0, ... -- the usual 8-GPU board)
+            nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+            try:
+                words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+                aff = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+            except Exception:
+                aff = set()
+            node = None
+            if aff and len(aff) < (os.cpu_count() or 1):
+                for nd in nodes:
+                    cl = set()
+                    for part in open(f"/sys/devices/system/node/node{nd}/cpulist").read().strip().split(","):
+                        a, _, b = part.partition("-")
+                        cl.update(range(int(a), int(b or a) + 1))
+                    if aff <= cl:
+                        node, how = nd, "nvml cpu affinity"
+            if node is None:
+                if len(nodes) < 2:
+                    return {"numa_node": None, "note": "no NUMA information for this GPU (one memory node visible)"}
+                ngpu = max(pynvml.nvmlDeviceGetCount(), 1)
+                node, how = nodes[min(local * len(nodes) // ngpu, len(nodes) - 1)], "assumed: GPUs split evenly over the memory nodes"
         cpus = set()
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
@@ -89,7 +111,7 @@ def bind_to_gpu_numa(local: int):
         allowed = cpus & set(os.sched_getaffinity(0))
         if allowed:
             os.sched_setaffinity(0, allowed)
-        return {"numa_node": node, "cpus": len(allowed)}
+        return {"numa_node": node, "cpus": len(allowed), "how": how}
     except Exception as exc:
         return {"numa_node": None, "note": f"not bound: {exc}"}
 
