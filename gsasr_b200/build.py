@@ -67,21 +67,40 @@ def build_variant(defines, out_path: str) -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile libgsraster.so for sm_100a; returns its path."""
+    """Compile libgsraster.so for sm_100a; returns its path.  Safe when several processes call it at once (one rank
+    per GPU under torchrun): the build runs under a file lock, into a per-process temporary, and whoever gets the lock
+    second finds the library fresh."""
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB + ".tmp"]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    log = proc.stdout + proc.stderr
-    with open(os.path.join(HERE, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if proc.returncode != 0:
-        sys.stderr.write(log)
-        raise RuntimeError("nvcc failed building libgsraster.so")
-    os.replace(LIB + ".tmp", LIB)
-    if verbose:
-        sys.stderr.write(log)
-    return LIB
+    import fcntl
+
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():
+                return LIB
+            try:
+                nvcc = nvcc_path()
+            except RuntimeError:
+                if os.path.exists(LIB):  # no compiler on this machine: the shipped library is what there is
+                    sys.stderr.write("[gsasr_b200.build] sources are newer than libgsraster.so but nvcc is not here: using the library as is\n")
+                    return LIB
+                raise
+            tmp = f"{LIB}.{os.getpid()}.tmp"
+            cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", tmp]
+            proc = subprocess.run(cmd, capture_output=True, text=True)
+            log = proc.stdout + proc.stderr
+            with open(os.path.join(HERE, "build.log"), "w") as f:
+                f.write(" ".join(cmd) + "\n" + log)
+            if proc.returncode != 0:
+                sys.stderr.write(log)
+                raise RuntimeError("nvcc failed building libgsraster.so")
+            os.replace(tmp, LIB)
+            if verbose:
+                sys.stderr.write(log)
+            return LIB
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 if __name__ == "__main__":

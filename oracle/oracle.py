@@ -28,8 +28,17 @@ _i32p = ctypes.POINTER(ctypes.c_int32)
 def build(force: bool = False) -> str:
     """gcc-build the C restatement (and, when /root/reference exists, the reference kernels)."""
     src = os.path.join(HERE, "gs_oracle.c")
-    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
-        subprocess.run(["make", "-C", HERE, "oracle"], check=True, capture_output=True)
+    stale = lambda: not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src)
+    if force or stale():
+        import fcntl
+
+        with open(LIB_PATH + ".lock", "w") as lock:  # several processes may get here at once
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if force or stale():
+                    subprocess.run(["make", "-C", HERE, "oracle"], check=True, capture_output=True)
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
