@@ -8,9 +8,9 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "variants")
 VARIANTS = {
     "base": [],
-    "ws_sync_arrive": ["GSR_CFG_WS_SYNC_ARRIVE=1"],
-    "fallback_plain_launch": ["GSR_CFG_FALLBACK_COOP=0"],
-    "head_parts2": ["GSH_CFG_EPI_PARTS=2"],
+    # examples of what has been swept: GSR_CFG_FR_MIN_CTAS, GSR_CFG_FR_LW=4, GSR_CFG_FR_TAIL=0,
+    # GSR_CFG_FR_UNROLL8=0, GSR_CFG_RB2_MIN_CTAS, GSR_CFG_MASK_PER_BAND=1, GSR_CFG_FALLBACK_COOP=0, GSH_CFG_EPI_PARTS=2
+    "ws_sync_arrive": ["GSR_CFG_WS_SYNC_ARRIVE=1"],  # racecheck aid (profiles/r02_sanitizer.md)
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
