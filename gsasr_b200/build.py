@@ -25,6 +25,7 @@ HEADERS = [
     "gsr_forward.cuh",
     "gsr_forward_ws.cuh",
     "gsr_backward.cuh",
+    "gsr_backward_region.cuh",
     "gsr_frontend.cuh",
     "gsr_loss.cuh",
     "gsr_umma.cuh",

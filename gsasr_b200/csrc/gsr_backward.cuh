@@ -78,6 +78,8 @@ struct GsrBwdArgs {
   const GsrBDesc* bdesc;  // padded batch (ragged != 0): records and moments are in canvas coordinates
   int bn, ragged;
   int hf, row0, bhs;      // row-band view / rows per sample of a stacked batch (see gsr_setup, gsr_region_mask)
+  const int* guard;       // run only if *guard == want (nullptr: always)
+  int want;
 };
 
 // The k-sigma ellipse of a sorted record in the pixel units of the image the kernel sweeps (band-local rows; the
@@ -328,6 +330,7 @@ __device__ __forceinline__ void gsr_bwd_chain(const float* t, const GsrBwdArgs& 
 }
 
 __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwdArgs p) {
+  if (gsr_guard_skip(p.guard, p.want)) return;
   extern __shared__ __align__(16) unsigned char gsr_smem_raw[];
   GsrBwdSmem& sm = *reinterpret_cast<GsrBwdSmem*>(gsr_smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

@@ -577,8 +577,10 @@ __device__ __forceinline__ void gsr_eval_quad(uint32_t addr0, uint32_t addr1, gs
 // shuffles (counts stay below 256: at most 64 entries) -- no popcounts (they share the MUFU pipe).
 // lw: the stage's lists; rb: the stage's records; (v1a, e1a), (v1b, e1b): this lane's two entries.  Returns the
 // length of the list of this lane's cell.  Warp-collective.
+// RANKS: also hand back {masks (first | second << 8), ranks of the first entry (cells 0-3, 4-7), of the second}.
+template <bool RANKS = false>
 __device__ __forceinline__ int gsr_fr_build_lists(uint32_t lw, uint32_t rb, int lane, int cell, bool v1a, uint32_t e1a,
-                                                  bool v1b, uint32_t e1b) {
+                                                  bool v1b, uint32_t e1b, uint32_t* rk = nullptr) {
   constexpr int CH = GSR_FR_CHUNK;
   const unsigned full = 0xffffffffu;
   const uint32_t null2 = (rb + CH * 16u) * (GSR_FR_LW == 2 ? 0x00010001u : 1u);
@@ -613,6 +615,13 @@ __device__ __forceinline__ int gsr_fr_build_lists(uint32_t lw, uint32_t rb, int 
       if ((ma >> q) & 1u) gsr_sts32(lw + q * GSR_FR_LIST + 4 * ra, adr_a);
       if ((mb >> q) & 1u) gsr_sts32(lw + q * GSR_FR_LIST + 4 * rbq, adr_b);
     }
+  }
+  if (RANKS) {
+    rk[0] = ma | (mb << 8);
+    rk[1] = ra_lo;
+    rk[2] = ra_hi;
+    rk[3] = rb_lo;
+    rk[4] = rb_hi;
   }
   const uint32_t tot = cell < 4 ? t_lo : t_hi;
   const int mine = (int)((tot >> (8 * (cell & 3))) & 0xffu);

@@ -66,7 +66,8 @@ struct GsrWorkspace {
   int2* keyrank;     // s   (unsorted)  key = bin id, -1 = skipped
   GsrRec* rec;       // s   (sorted)
   uint2* box;        // s   (sorted)
-  int* ids;          // s   (sorted -> original index)
+  int* ids;
+  float* mom;  // (s, 8) moment rows of the region backward          // s   (sorted -> original index)
   int nbx, nby, nb, nscan;
   // ---- both ----
   float* px_tab;     // w
@@ -120,6 +121,7 @@ static inline GsrWorkspace gsr_carve(void* base, int s, int h, int w) {
   ws.rec = (GsrRec*)take(sn * sizeof(GsrRec));
   ws.box = (uint2*)take(sn * sizeof(uint2));
   ws.ids = (int*)take(sn * sizeof(int));
+  ws.mom = (float*)take(sn * 8 * sizeof(float));
   ws.bytes = off;
   ws.hf = 0;
   ws.row0 = 0;

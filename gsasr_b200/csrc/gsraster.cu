@@ -3,6 +3,7 @@
 // forward and backward raster kernels, fused front end, and CPU test hooks.
 #include "../../include/gsraster.h"
 #include "gsr_backward.cuh"
+#include "gsr_backward_region.cuh"
 #include "gsr_frontend.cuh"
 #include "gsr_loss.cuh"
 #include <atomic>
@@ -92,7 +93,7 @@ static int gsr_resident_grid(K kernel, int threads, int slot, int* out, size_t d
 // Kernels that need more than 48 KB of dynamic shared memory opt in once per (device, kernel).
 template <typename K>
 static int gsr_optin_smem(K kernel, int bytes, int slot) {
-  static std::atomic<int> done[6][64];
+  static std::atomic<int> done[8][64];
   int dev = 0;
   GSR_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && done[slot][dev].load(std::memory_order_relaxed)) return GSR_OK;
@@ -355,9 +356,11 @@ static int gsr_raster_forward(const GsrWorkspace& ws, float* img, int h, int w, 
 
 static int gsr_launch_backward(const GsrWorkspace& ws, const float* sigmas, const float* grads,
                                float* gs, float* gc, float* gk, int s, int h, int w,
-                               uint32_t flags, cudaStream_t st) {
+                               uint32_t flags, cudaStream_t st, bool guarded = false) {
   if (s == 0) return GSR_OK;
   GsrBwdArgs a;
+  a.guard = guarded ? ws.stats + GSR_STAT_OVERFLOW : nullptr;
+  a.want = 1;
   a.rec = ws.rec;
   a.box = ws.box;
   a.ids = ws.ids;
@@ -388,6 +391,51 @@ static int gsr_launch_backward(const GsrWorkspace& ws, const float* sigmas, cons
   if (rcs) return rcs;
   const int grid = a.tiles_x * a.tiles_y + (s + GSR_BWD_LARGE_CHUNK - 1) / GSR_BWD_LARGE_CHUNK;
   gsr_backward_kernel<<<grid, GSR_BWD_THREADS, sizeof(GsrBwdSmem), st>>>(a);
+  GSR_CUDA(cudaGetLastError());
+  return GSR_OK;
+}
+
+// Backward over the region buckets (gsr_backward_region.cuh) + the chain rule per Gaussian; both skipped on the
+// device when a bucket overflowed (the Gaussian-centric kernel over the home bins then runs instead).
+#ifndef GSR_CFG_BWD_REGION
+#define GSR_CFG_BWD_REGION 1
+#endif
+static int gsr_bwd_region_override() {
+  static const int v = [] {
+    const char* e = getenv("GSR_BWD_REGION");
+    return e && (e[0] == '0' || e[0] == '1') ? e[0] - '0' : -1;
+  }();
+  return v;
+}
+static bool gsr_bwd_use_region(uint32_t flags) {
+  if (flags & GSR_FLAG_DETERMINISTIC) return false;  // the atomics' order is not reproducible
+  const int ov = gsr_bwd_region_override();
+  return ov >= 0 ? ov != 0 : GSR_CFG_BWD_REGION != 0;
+}
+static int gsr_clear_moments(const GsrWorkspace& ws, int s, cudaStream_t st) {
+  if (s > 0) GSR_CUDA(cudaMemsetAsync(ws.mom, 0, (size_t)s * 8 * sizeof(float), st));
+  return GSR_OK;
+}
+static int gsr_launch_backward_region(const GsrWorkspace& ws, const float* sigmas, const float* grads, float* gs,
+                                      float* gc, float* gk, int s, int h, int w, float keff, uint32_t flags,
+                                      cudaStream_t st) {
+  if (s == 0) return GSR_OK;
+  GsrFwdArgs a = gsr_fwd_args(ws, nullptr, h, w, keff, flags);
+  a.want = 0;
+  GsrBwdRegionArgs q;
+  q.grads = grads;
+  q.mom = ws.mom;
+  const int nunits = ws.nrx * ws.nry;
+  int cap = 0;
+  int rc = gsr_optin_smem(gsr_backward_region_kernel, (int)sizeof(GsrBwdRegionSmem), 6);
+  if (rc) return rc;
+  rc = gsr_resident_grid(gsr_backward_region_kernel, GSR_FR_THREADS, 0, &cap, sizeof(GsrBwdRegionSmem));
+  if (rc) return rc;
+  const int want = (nunits + GSR_FR_WARPS - 1) / GSR_FR_WARPS;
+  gsr_backward_region_kernel<<<want < cap ? want : cap, GSR_FR_THREADS, sizeof(GsrBwdRegionSmem), st>>>(a, q);
+  const int cg = (s + 255) / 256;
+  gsr_bwd_chain_kernel<<<cg < 1184 ? cg : 1184, 256, 0, st>>>(ws.mom, ws.rec_in, sigmas, gs, gc, gk, s, a.guard, 0,
+                                                             ws.ragged ? ws.bdesc : nullptr, ws.bn);
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
 }
@@ -481,10 +529,21 @@ static int gsr_backward_impl(const float* sigmas, const float* coords, const flo
   }
   rc = gsr_clear_and_tables(h, w, ws, st);
   if (rc) return rc;
-  rc = gsr_run_bins(sigmas, coords, colors, s, h, w, dmax, keff, ws, nullptr, 0, st);
+  if (!gsr_bwd_use_region(flags)) {
+    rc = gsr_run_bins(sigmas, coords, colors, s, h, w, dmax, keff, ws, nullptr, 0, st);
+    if (rc) return rc;
+    return gsr_launch_backward(ws, sigmas, grads, grads_sigmas, grads_coords, grads_colors, s, h, w, flags, st);
+  }
+  // region buckets; if one overflows, the home-bin sort and the Gaussian-centric kernel (guarded launches)
+  rc = gsr_clear_moments(ws, s, st);
   if (rc) return rc;
-  return gsr_launch_backward(ws, sigmas, grads, grads_sigmas, grads_coords, grads_colors, s, h, w,
-                             flags, st);
+  rc = gsr_run_tiles(sigmas, coords, colors, s, h, w, dmax, keff, ws, st);
+  if (rc) return rc;
+  rc = gsr_launch_backward_region(ws, sigmas, grads, grads_sigmas, grads_coords, grads_colors, s, h, w, keff, flags, st);
+  if (rc) return rc;
+  rc = gsr_run_bins(sigmas, coords, colors, s, h, w, dmax, keff, ws, ws.stats + GSR_STAT_OVERFLOW, 1, st);
+  if (rc) return rc;
+  return gsr_launch_backward(ws, sigmas, grads, grads_sigmas, grads_coords, grads_colors, s, h, w, flags, st, true);
 }
 
 extern "C" int gsr_forward(const float* sigmas, const float* coords, const float* colors,
@@ -653,8 +712,15 @@ extern "C" int gsr_backward_prepared(const float* sigmas, const float* grads, fl
   const GsrWorkspace ws = gsr_carve(workspace, s, h, w);
   int rc = gsr_check_ws(workspace, workspace_bytes, ws.bytes);
   if (rc) return rc;
-  return gsr_launch_backward(ws, sigmas, grads, grads_sigmas, grads_coords, grads_colors, s, h, w,
-                             flags, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!gsr_bwd_use_region(flags))
+    return gsr_launch_backward(ws, sigmas, grads, grads_sigmas, grads_coords, grads_colors, s, h, w, flags, st);
+  rc = gsr_clear_moments(ws, s, st);
+  if (rc) return rc;
+  const float keff = gsr_effective_ksigma(0.f);  // (not used by the region backward: the buckets are already built)
+  rc = gsr_launch_backward_region(ws, sigmas, grads, grads_sigmas, grads_coords, grads_colors, s, h, w, keff, flags, st);
+  if (rc) return rc;
+  return gsr_launch_backward(ws, sigmas, grads, grads_sigmas, grads_coords, grads_colors, s, h, w, flags, st, true);
 }
 
 // ---- ragged batches -------------------------------------------------------------------------
