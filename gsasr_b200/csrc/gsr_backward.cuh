@@ -329,19 +329,17 @@ __device__ __forceinline__ void gsr_bwd_chain(const float* t, const GsrBwdArgs& 
   ok[2] += t[2];
 }
 
-__global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwdArgs p) {
-  if (gsr_guard_skip(p.guard, p.want)) return;
-  extern __shared__ __align__(16) unsigned char gsr_smem_raw[];
-  GsrBwdSmem& sm = *reinterpret_cast<GsrBwdSmem*>(gsr_smem_raw);
+// One block of work: a 64x64 tile's Gaussians (bid < tiles) or a chunk of the "large" list.
+__device__ __forceinline__ void gsr_backward_block(const GsrBwdArgs& p, GsrBwdSmem& sm, const int bid) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int lx = lane & 7, ly = lane >> 3;
   const int ntiles = p.tiles_x * p.tiles_y;
   const float ecut = gsr_ecut(__int_as_float(__ldg(p.stats + GSR_STAT_KSIGMA)));  // the k of the set-up that made the boxes
 
-  if ((int)blockIdx.x >= ntiles) {
+  if (bid >= ntiles) {
     // ---- "large" list: no staging, one chunk per CTA ----
     const int l0 = __ldg(p.bin_off + p.nb), l1 = __ldg(p.bin_off + p.nb + 1);
-    const int c0 = l0 + ((int)blockIdx.x - ntiles) * GSR_BWD_LARGE_CHUNK;
+    const int c0 = l0 + (bid - ntiles) * GSR_BWD_LARGE_CHUNK;
     const int c1 = min(c0 + GSR_BWD_LARGE_CHUNK, l1);
     for (int g0 = c0 + warp; g0 < c1; g0 += GSR_BWD_WARPS * GSR_BWD_BATCH) {
       int nb = 0;
@@ -367,7 +365,7 @@ __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwd
     return;
   }
 
-  const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
+  const int tx = bid % p.tiles_x, ty = bid / p.tiles_x;
   const int tx0 = tx * GSR_BWD_TILE, ty0 = ty * GSR_BWD_TILE;
   // Gaussians homed in this tile: one contiguous run per bin row.
   constexpr int BPT = GSR_BWD_TILE / GSR_BIN;
@@ -473,5 +471,18 @@ __global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwd
       if (lane < nb) gsr_bwd_chain(sm.tot[warp][lane], p, sm.tot_gi[warp][lane]);
       __syncwarp();
     }
+  }
+}
+
+// The grid is the number of blocks of work when the launch is unconditional; a guarded launch (the fallback behind
+// the region backward) uses a small grid that strides over them: 40,960 CTAs that only read the guard and leave
+// took 169 us at the headline shape.
+__global__ void __launch_bounds__(GSR_BWD_THREADS, 2) gsr_backward_kernel(GsrBwdArgs p, int nblocks) {
+  if (gsr_guard_skip(p.guard, p.want)) return;
+  extern __shared__ __align__(16) unsigned char gsr_smem_raw[];
+  GsrBwdSmem& sm = *reinterpret_cast<GsrBwdSmem*>(gsr_smem_raw);
+  for (int bid = blockIdx.x; bid < nblocks; bid += gridDim.x) {
+    gsr_backward_block(p, sm, bid);
+    __syncthreads();  // shared memory is reused by the next block of work
   }
 }

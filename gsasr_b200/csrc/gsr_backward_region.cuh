@@ -19,11 +19,12 @@
 #include "gsr_forward_ws.cuh"
 
 #ifndef GSR_CFG_BR_T
-#define GSR_CFG_BR_T 32   // list positions parked before the entries gather their sums (16: one more CTA per SM)
+#define GSR_CFG_BR_T 28   // list positions parked before the entries gather their sums: as many as three CTAs per SM allow
 #endif
 #ifndef GSR_CFG_BR_MIN_CTAS
 #define GSR_CFG_BR_MIN_CTAS (GSR_CFG_BR_T <= 16 ? 4 : 3)
 #endif
+static_assert(GSR_FR_LW == 2, "the cell lists are read as 16-bit addresses");
 constexpr int GSR_BR_T = GSR_CFG_BR_T;
 constexpr int GSR_BR_ROW = 8 * 32 + 16;  // bytes per list position: 8 cells x 8 sums, padded (gather: conflict-free)
 
@@ -33,6 +34,7 @@ struct GsrBwdRegionSmem {
   uint32_t list[GSR_FR_WARPS][2][GSR_FR_LIST_STAGE / 4];
   uint4 meta[GSR_FR_WARPS][2][2][32];  // per stage and lane: {masks, ranks a (2), index a}, {ranks b (2), index b, -}
   float4 park[GSR_FR_WARPS][GSR_BR_T * GSR_BR_ROW / 16];  // (list position, cell) -> the cell's eight sums
+  float4 gtile[GSR_FR_WARPS][8][4 * 3];  // dL/dimg of the unit being evaluated: [cell][row][channel] x 4 columns
 };
 static_assert(offsetof(GsrBwdRegionSmem, box) < 65536, "16-bit list addresses: the records sit in the first 64 KB");
 struct GsrBwdRegionArgs {
@@ -40,74 +42,70 @@ struct GsrBwdRegionArgs {
   float* mom;          // (s, 8) moment rows, zero on entry
 };
 
-// One record against this lane's 2x2 block: the eight sums over its four pixels, reduced over the cell's four lanes
-// and parked at dst.  nx2 / ny2: negated pixel coordinates (d = x - px: the odd moments come out
-// with the opposite sign of the reference's dx = px - x; gsr_bwd_chain_kernel accounts for it).
+// One record against a whole 4x4 CELL, by one lane: the four lanes of a cell take four consecutive positions of the
+// cell's list, so the eight sums of a (cell, entry) pair are complete in one lane -- no cross-lane reduction (in the
+// first version, a 2x2 block per lane, the shuffles and selects of that reduction were 44 % of all instructions).
+// nxp / nyb: NEGATED pixel coordinates of the cell's four columns (two pairs) and four rows (each twice), so d = x - px: the odd
+// moments come out with the opposite sign of the reference's dx = px - x (gsr_bwd_chain_kernel accounts for it).
+// gt: the cell's dL/dimg in shared memory, [row][channel][column]; dst: the 32 bytes of the (list position, cell) row.
 template <bool MASKED>
-__device__ __forceinline__ void gsr_bwd_eval_quad(uint32_t addr0, uint32_t dst, gsr_f2 nx2, gsr_f2 ny2, bool m00,
-                                                  bool m01, bool m10, bool m11, const gsr_f2 (&g)[2][3], int lane) {
+__device__ __forceinline__ void gsr_bwd_eval_cell(uint32_t addr0, uint32_t dst, const gsr_f2 (&nxp)[2], const gsr_f2 (&nyb)[4],
+                                                  const float4* __restrict__ gt, unsigned xin, unsigned yin) {
   const float4 a0 = gsr_lds128(addr0);               // x, y, a, b
   const float4 a1 = gsr_lds128(addr0 + GSR_FR_HI);   // c, r, g, bl
-  const gsr_f2 dx2 = gsr_add2(nx2, gsr_pk(a0.x, a0.x));
-  const gsr_f2 dy2 = gsr_add2(ny2, gsr_pk(a0.y, a0.y));
-  const gsr_f2 t1 = gsr_mul2(gsr_pk(a0.w, a0.w), dy2);
-  const gsr_f2 t0 = gsr_mul2(gsr_mul2(gsr_pk(a1.x, a1.x), dy2), dy2);
-  float t1a, t1b, t0a, t0b, dya, dyb;
-  gsr_upk(t1, t1a, t1b);
-  gsr_upk(t0, t0a, t0b);
-  gsr_upk(dy2, dya, dyb);
-  const gsr_f2 a2 = gsr_pk(a0.z, a0.z);
-  const gsr_f2 ea = gsr_fma2(dx2, gsr_fma2(a2, dx2, gsr_pk(t1a, t1a)), gsr_pk(t0a, t0a));
-  const gsr_f2 eb = gsr_fma2(dx2, gsr_fma2(a2, dx2, gsr_pk(t1b, t1b)), gsr_pk(t0b, t0b));
-  float e00, e01, e10, e11;
-  gsr_upk(ea, e00, e01);
-  gsr_upk(eb, e10, e11);
-  float v00 = gsr_ex2(e00), v01 = gsr_ex2(e01), v10 = gsr_ex2(e10), v11 = gsr_ex2(e11);
-  if (MASKED) {
-    v00 = m00 ? v00 : 0.f;
-    v01 = m01 ? v01 : 0.f;
-    v10 = m10 ? v10 : 0.f;
-    v11 = m11 ? v11 : 0.f;
-  }
-  const gsr_f2 va = gsr_pk(v00, v01), vb = gsr_pk(v10, v11);
+  const gsr_f2 x2 = gsr_pk(a0.x, a0.x), a2 = gsr_pk(a0.z, a0.z);
+  const gsr_f2 dx0 = gsr_add2(nxp[0], x2), dx1 = gsr_add2(nxp[1], x2);
+  const gsr_f2 ad0 = gsr_mul2(a2, dx0), ad1 = gsr_mul2(a2, dx1);
   const gsr_f2 cr = gsr_pk(a1.y, a1.y), cg = gsr_pk(a1.z, a1.z), cb = gsr_pk(a1.w, a1.w);
-  const gsr_f2 ua = gsr_mul2(va, gsr_fma2(g[0][0], cr, gsr_fma2(g[0][1], cg, gsr_mul2(g[0][2], cb))));
-  const gsr_f2 ub = gsr_mul2(vb, gsr_fma2(g[1][0], cr, gsr_fma2(g[1][1], cg, gsr_mul2(g[1][2], cb))));
-  const gsr_f2 dya2 = gsr_pk(dya, dya), dyb2 = gsr_pk(dyb, dyb);
-  const gsr_f2 uxa = gsr_mul2(ua, dx2), uxb = gsr_mul2(ub, dx2), uya = gsr_mul2(ua, dya2), uyb = gsr_mul2(ub, dyb2);
-  gsr_f2 pk8[8];  // each: {column 0, column 1} halves of one sum
-  pk8[0] = gsr_fma2(va, g[0][0], gsr_mul2(vb, g[1][0]));
-  pk8[1] = gsr_fma2(va, g[0][1], gsr_mul2(vb, g[1][1]));
-  pk8[2] = gsr_fma2(va, g[0][2], gsr_mul2(vb, g[1][2]));
-  pk8[3] = gsr_add2(uxa, uxb);
-  pk8[4] = gsr_add2(uya, uyb);
-  pk8[5] = gsr_fma2(uxa, dx2, gsr_mul2(uxb, dx2));
-  pk8[6] = gsr_fma2(uxa, dya2, gsr_mul2(uxb, dyb2));
-  pk8[7] = gsr_fma2(uya, dya2, gsr_mul2(uyb, dyb2));
+  const gsr_f2 y2 = gsr_pk(a0.y, a0.y), b2 = gsr_pk(a0.w, a0.w), c2 = gsr_pk(a1.x, a1.x);
+  // every sum is kept as a pair over the two column halves until the end (rows enter as broadcast pairs)
+  gsr_f2 Cr = gsr_pk(0.f, 0.f), Cg = Cr, Cb = Cr, Sx2 = Cr, Sy2 = Cr, Sxx2 = Cr, Sxy2 = Cr, Syy2 = Cr;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const gsr_f2 dyb = gsr_add2(nyb[r], y2);
+    const gsr_f2 t12 = gsr_mul2(b2, dyb), t02 = gsr_mul2(gsr_mul2(c2, dyb), dyb);
+    const gsr_f2 e0 = gsr_fma2(dx0, gsr_add2(ad0, t12), t02), e1 = gsr_fma2(dx1, gsr_add2(ad1, t12), t02);
+    float ea, eb, ec, ed;
+    gsr_upk(e0, ea, eb);
+    gsr_upk(e1, ec, ed);
+    float va = gsr_ex2(ea), vb = gsr_ex2(eb), vc = gsr_ex2(ec), vd = gsr_ex2(ed);
+    if (MASKED) {
+      const bool yr = (yin >> r) & 1u;
+      va = (yr && (xin & 1u)) ? va : 0.f;
+      vb = (yr && (xin & 2u)) ? vb : 0.f;
+      vc = (yr && (xin & 4u)) ? vc : 0.f;
+      vd = (yr && (xin & 8u)) ? vd : 0.f;
+    }
+    const gsr_f2 v0 = gsr_pk(va, vb), v1 = gsr_pk(vc, vd);
+    const float4 gr = gt[r * 3 + 0], gg = gt[r * 3 + 1], gb = gt[r * 3 + 2];
+    const gsr_f2 gr0 = gsr_pk(gr.x, gr.y), gr1 = gsr_pk(gr.z, gr.w), gg0 = gsr_pk(gg.x, gg.y), gg1 = gsr_pk(gg.z, gg.w);
+    const gsr_f2 gb0 = gsr_pk(gb.x, gb.y), gb1 = gsr_pk(gb.z, gb.w);
+    const gsr_f2 u0 = gsr_mul2(v0, gsr_fma2(gr0, cr, gsr_fma2(gg0, cg, gsr_mul2(gb0, cb))));
+    const gsr_f2 u1 = gsr_mul2(v1, gsr_fma2(gr1, cr, gsr_fma2(gg1, cg, gsr_mul2(gb1, cb))));
+    Cr = gsr_fma2(v0, gr0, gsr_fma2(v1, gr1, Cr));
+    Cg = gsr_fma2(v0, gg0, gsr_fma2(v1, gg1, Cg));
+    Cb = gsr_fma2(v0, gb0, gsr_fma2(v1, gb1, Cb));
+    const gsr_f2 ux0 = gsr_mul2(u0, dx0), ux1 = gsr_mul2(u1, dx1);
+    Sxx2 = gsr_fma2(ux0, dx0, gsr_fma2(ux1, dx1, Sxx2));
+    const gsr_f2 rx = gsr_add2(ux0, ux1), ry = gsr_mul2(gsr_add2(u0, u1), dyb);  // the row's u dx and u dy, by column half
+    Sx2 = gsr_add2(Sx2, rx);
+    Sxy2 = gsr_fma2(rx, dyb, Sxy2);
+    Sy2 = gsr_add2(Sy2, ry);
+    Syy2 = gsr_fma2(ry, dyb, Syy2);
+  }
   float s[8];
+  {
+    const gsr_f2 all[8] = {Cr, Cg, Cb, Sx2, Sy2, Sxx2, Sxy2, Syy2};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float lo, hi;
-    gsr_upk(pk8[i], lo, hi);
-    s[i] = lo + hi;
+    for (int i = 0; i < 8; ++i) {
+      float lo, hi;
+      gsr_upk(all[i], lo, hi);
+      s[i] = lo + hi;
+    }
   }
-  // recursive halving over the cell's four lanes: lane (bit 1, bit 0) ends with sums 4 * bit0 + 2 * bit1 + {0, 1}
-  const bool b0 = lane & 1, b1 = lane & 2;
-  float w[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float send = b0 ? s[i] : s[i + 4], keep = b0 ? s[i + 4] : s[i];
-    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-  }
-  float z[2];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float send = b1 ? w[i] : w[i + 2], keep = b1 ? w[i + 2] : w[i];
-    z[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  // dst: this lane's 8 bytes of the (list position, cell) row.  (The null record that pads the lists parks sums
-  // nobody gathers.)
-  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(dst), "f"(z[0]), "f"(z[1]) : "memory");
+  // (the null record that pads the lists parks sums nobody gathers)
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(s[0]), "f"(s[1]), "f"(s[2]), "f"(s[3]) : "memory");
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16), "f"(s[4]), "f"(s[5]), "f"(s[6]), "f"(s[7]) : "memory");
 }
 
 __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backward_region_kernel(GsrFwdArgs p, GsrBwdRegionArgs q) {
@@ -126,7 +124,8 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backw
   const uint32_t box_s = gsr_smem_addr(&sm.box[warp][0][0]);
   const uint2* box_w = &sm.box[warp][0][0];
   const uint32_t park_w = gsr_smem_addr(&sm.park[warp][0]);
-  const uint32_t park_l = park_w + cell * 32 + ((lane & 1) ? 16 : 0) + ((lane & 2) ? 8 : 0);  // this lane's two sums of a row
+  const uint32_t park_l = park_w + cell * 32;  // this lane's cell in a row
+  const float4* gt = &sm.gtile[warp][cell][0];
   const int total_warps = gridDim.x * GSR_FR_WARPS;
 
   // the null record of both stages (slot CH): zero conic and colour, adds exactly 0
@@ -237,17 +236,25 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backw
   int cur = 0, ci = 0;
   // pixel block of this lane in unit u: cell (cell & 3, cell >> 2), block (lane & 1, (lane >> 1) & 1) of the cell
   const int bx = (cell & 3) * GSR_CELL + (lane & 1) * 2, by = (cell >> 2) * GSR_CELL + ((lane >> 1) & 1) * 2;
-  auto coords_of = [&](int u, gsr_f2& nx, gsr_f2& ny) {
+  // NEGATED coordinates of this lane's CELL in unit u: four columns (two pairs), four rows
+  const int cx = (cell & 3) * GSR_CELL, cy = (cell >> 2) * GSR_CELL;
+  auto coords_of = [&](int u, gsr_f2 (&nx)[2], gsr_f2 (&ny)[4]) {
     const int uy = (u < nunits ? u : 0) / p.nrx, ux = (u < nunits ? u : 0) - uy * p.nrx;
-    const int wi = ux * GSR_RGW + bx, hi = uy * GSR_RGH + by;
-    nx = gsr_pk(-__ldg(p.px_tab + min(wi, p.w - 1)), -__ldg(p.px_tab + min(wi + 1, p.w - 1)));
-    ny = gsr_pk(-__ldg(p.py_tab + min(hi, p.h - 1)), -__ldg(p.py_tab + min(hi + 1, p.h - 1)));
+    const int wi = ux * GSR_RGW + cx, hi = uy * GSR_RGH + cy;
+    nx[0] = gsr_pk(-__ldg(p.px_tab + min(wi, p.w - 1)), -__ldg(p.px_tab + min(wi + 1, p.w - 1)));
+    nx[1] = gsr_pk(-__ldg(p.px_tab + min(wi + 2, p.w - 1)), -__ldg(p.px_tab + min(wi + 3, p.w - 1)));
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float v = -__ldg(p.py_tab + min(hi + r, p.h - 1));
+      ny[r] = gsr_pk(v, v);
+    }
   };
-  gsr_f2 nx2, ny2, nx2B, ny2B;
-  coords_of(uA, nx2, ny2);
-  coords_of(uB, nx2B, ny2B);
-  // dL/dimg of this lane's 2x2 block in unit u: {row 0, row 1} x {r, g, b}, each a pair over the two columns
-  // (pixels outside the image: 0)
+  gsr_f2 nxA[2], nxB[2];
+  gsr_f2 nyA[4], nyB[4];
+  coords_of(uA, nxA, nyA);
+  coords_of(uB, nxB, nyB);
+  // dL/dimg of unit u: fetched a 2x2 block per lane ({row 0, row 1} x {r, g, b}, each a pair over the two columns;
+  // pixels outside the image: 0), then laid down in the warp's tile for the lanes that evaluate whole cells
   const bool chw = (p.flags & 2u) != 0;
   const size_t plane = (size_t)p.h * p.w;
   auto grads_of = [&](int u, gsr_f2 (&g)[2][3]) {
@@ -267,9 +274,22 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backw
         g[yy][ch] = gsr_pk(v[0], v[1]);
       }
   };
-  gsr_f2 gA[2][3], gB[2][3];
-  grads_of(uA, gA);
+  auto store_tile = [&](const gsr_f2 (&g)[2][3]) {  // [cell][row][channel][column]
+    float* base = reinterpret_cast<float*>(&sm.gtile[warp][cell][0]) + (((lane >> 1) & 1) * 2) * 12 + (lane & 1) * 2;
+#pragma unroll
+    for (int yy = 0; yy < 2; ++yy)
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        float lo, hi;
+        gsr_upk(g[yy][ch], lo, hi);
+        *reinterpret_cast<float2*>(base + yy * 12 + ch * 4) = make_float2(lo, hi);
+      }
+  };
+  gsr_f2 gB[2][3];
+  grads_of(uA, gB);
+  store_tile(gB);
   grads_of(uB, gB);
+  __syncwarp();
   for (;;) {  // one chunk per iteration, flat over the warp's units
     const uint32_t rb = rec_s + cur * GSR_FR_STAGE_BYTES;
     const uint32_t lb = list_c + cur * GSR_FR_LIST_STAGE;
@@ -294,50 +314,39 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backw
 #pragma unroll
     for (int i = 0; i < 8; ++i) sa[i] = sb[i] = 0.f;
     const int uy = uA / p.nrx, ux = uA - uy * p.nrx;
-    const int wi0 = ux * GSR_RGW + bx, hi0 = uy * GSR_RGH + by;
+    const int wi0 = ux * GSR_RGW + cx, hi0 = uy * GSR_RGH + cy;  // the lane's cell
     for (int t0 = 0; t0 < trip; t0 += GSR_BR_T) {
       const int te = min(trip, t0 + GSR_BR_T);
       const uint32_t pk = park_l - t0 * GSR_BR_ROW;  // row of list position t: pk + t * GSR_BR_ROW
+      // the four lanes of a cell take positions t .. t + 3 (positions past the list's end hold the null record)
       if ((slow_ac | slow_bc) == 0) {
-        int t = t0;
-        for (; t + 4 <= te; t += 4) {
-          uint32_t a4[4];
-          gsr_fr_load4(lb, t, a4);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            gsr_bwd_eval_quad<false>(a4[k], pk + (t + k) * GSR_BR_ROW, nx2, ny2, true, true, true, true, gA, lane);
-        }
-        if (t < te) {  // one to three left
-          uint32_t a4[4];
-          gsr_fr_load4(lb, t, a4);
-          gsr_bwd_eval_quad<false>(a4[0], pk + t * GSR_BR_ROW, nx2, ny2, true, true, true, true, gA, lane);
-          if (t + 1 < te) gsr_bwd_eval_quad<false>(a4[1], pk + (t + 1) * GSR_BR_ROW, nx2, ny2, true, true, true, true, gA, lane);
-          if (t + 2 < te) gsr_bwd_eval_quad<false>(a4[2], pk + (t + 2) * GSR_BR_ROW, nx2, ny2, true, true, true, true, gA, lane);
+        for (int t = t0 + (lane & 3); t < te; t += 4) {
+          const uint32_t a = gsr_lds16u(lb + 2 * t);
+          gsr_bwd_eval_cell<false>(a, pk + t * GSR_BR_ROW, nxA, nyA, gt, 15u, 15u);
         }
       } else {
-        for (int t = t0; t < te; t += 4) {
-          uint32_t a4[4];
-          gsr_fr_load4(lb, t, a4);
+        for (int t = t0 + (lane & 3); t < te; t += 4) {
+          const uint32_t a = gsr_lds16u(lb + 2 * t);
+          const uint32_t slot = (a - rb) >> 4;
+          const bool binds = slot < 32 ? ((slow_ac >> slot) & 1u) : (slot < 64 ? ((slow_bc >> (slot - 32)) & 1u) : false);
+          unsigned xin = 15u, yin = 15u;
+          if (binds) {  // exact inclusion
+            int bx0, bx1, by0, by1;
+            bool bd;
+            gsr_box_unpack(box_w[cur * CH + slot], bx0, bx1, by0, by1, bd);
+            xin = yin = 0u;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (t + k >= te) break;
-            const uint32_t a = a4[k];
-            const uint32_t slot = (a - rb) >> 4;
-            const bool binds = slot < 32 ? ((slow_ac >> slot) & 1u) : (slot < 64 ? ((slow_bc >> (slot - 32)) & 1u) : false);
-            bool m00 = true, m01 = true, m10 = true, m11 = true;
-            if (binds) {  // exact inclusion
-              int bx0, bx1, by0, by1;
-              bool bd;
-              gsr_box_unpack(box_w[cur * CH + slot], bx0, bx1, by0, by1, bd);
-              const bool y0in = hi0 >= by0 && hi0 <= by1, y1in = hi0 + 1 >= by0 && hi0 + 1 <= by1;
-              const bool x0in = wi0 >= bx0 && wi0 <= bx1, x1in = wi0 + 1 >= bx0 && wi0 + 1 <= bx1;
-              m00 = y0in && x0in, m01 = y0in && x1in, m10 = y1in && x0in, m11 = y1in && x1in;
+            for (int k = 0; k < 4; ++k) {
+              xin |= (wi0 + k >= bx0 && wi0 + k <= bx1) ? 1u << k : 0u;
+              yin |= (hi0 + k >= by0 && hi0 + k <= by1) ? 1u << k : 0u;
             }
-            gsr_bwd_eval_quad<true>(a, pk + (t + k) * GSR_BR_ROW, nx2, ny2, m00, m01, m10, m11, gA, lane);
           }
+          gsr_bwd_eval_cell<true>(a, pk + t * GSR_BR_ROW, nxA, nyA, gt, xin, yin);
         }
       }
       __syncwarp();  // the block's rows are parked
+      // (unrolled over the cells and predicated: sixteen independent bodies.  Loops over the set bits of the masks
+      // issue fewer instructions but run as a dependent chain: HL 866 -> 1034 us)
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const uint32_t ra = (((c < 4 ? mA.y : mA.z) >> (8 * (c & 3))) & 0xffu) - (uint32_t)t0;
@@ -382,14 +391,13 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backw
     uC = take_unit();
     nC = count_of(uC);
     ci = 0;
-    nx2 = nx2B;
-    ny2 = ny2B;
-    coords_of(uB, nx2B, ny2B);
+    nxA[0] = nxB[0], nxA[1] = nxB[1];
 #pragma unroll
-    for (int yy = 0; yy < 2; ++yy)
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) gA[yy][ch] = gB[yy][ch];
+    for (int r = 0; r < 4; ++r) nyA[r] = nyB[r];
+    coords_of(uB, nxB, nyB);
+    store_tile(gB);  // (every lane is past its last read of the tile: the gather's __syncwarp)
     grads_of(uB, gB);
+    __syncwarp();
   }
   finish();
 }

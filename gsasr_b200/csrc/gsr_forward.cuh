@@ -509,6 +509,11 @@ __device__ __forceinline__ uint32_t gsr_lds32u(uint32_t addr) {
 __device__ __forceinline__ void gsr_sts16(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u16 [%1], %0;" ::"h"((unsigned short)v), "r"(addr) : "memory");
 }
+__device__ __forceinline__ uint32_t gsr_lds16u(uint32_t addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ uint2 gsr_lds64u(uint32_t addr) {
   uint2 v;
   asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));

@@ -389,8 +389,15 @@ static int gsr_launch_backward(const GsrWorkspace& ws, const float* sigmas, cons
   a.bhs = ws.bn > 0 ? ws.bhs : 0;
   const int rcs = gsr_optin_smem(gsr_backward_kernel, (int)sizeof(GsrBwdSmem), 1);
   if (rcs) return rcs;
-  const int grid = a.tiles_x * a.tiles_y + (s + GSR_BWD_LARGE_CHUNK - 1) / GSR_BWD_LARGE_CHUNK;
-  gsr_backward_kernel<<<grid, GSR_BWD_THREADS, sizeof(GsrBwdSmem), st>>>(a);
+  const int nblocks = a.tiles_x * a.tiles_y + (s + GSR_BWD_LARGE_CHUNK - 1) / GSR_BWD_LARGE_CHUNK;
+  int grid = nblocks;
+  if (guarded) {  // normally a no-op: keep it cheap
+    int nsm = 0;
+    const int rc = gsr_sm_count(&nsm);
+    if (rc) return rc;
+    grid = nblocks < 2 * nsm ? nblocks : 2 * nsm;
+  }
+  gsr_backward_kernel<<<grid, GSR_BWD_THREADS, sizeof(GsrBwdSmem), st>>>(a, nblocks);
   GSR_CUDA(cudaGetLastError());
   return GSR_OK;
 }
