@@ -26,6 +26,8 @@
 #endif
 static_assert(GSR_FR_LW == 2, "the cell lists are read as 16-bit addresses");
 constexpr int GSR_BR_T = GSR_CFG_BR_T;
+__device__ __forceinline__ float gsr_lo(gsr_f2 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float gsr_hi(gsr_f2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
 constexpr int GSR_BR_ROW = 8 * 32 + 16;  // bytes per list position: 8 cells x 8 sums, padded (gather: conflict-free)
 
 struct GsrBwdRegionSmem {
@@ -48,11 +50,11 @@ struct GsrBwdRegionArgs {
 // nxp / nyb: NEGATED pixel coordinates of the cell's four columns (two pairs) and four rows (each twice), so d = x - px: the odd
 // moments come out with the opposite sign of the reference's dx = px - x (gsr_bwd_chain_kernel accounts for it).
 // gt: the cell's dL/dimg in shared memory, [row][channel][column]; dst: the 32 bytes of the (list position, cell) row.
+// a0 = {x, y, a, b}, a1 = {c, r, g, bl}: the staged record.
 template <bool MASKED>
-__device__ __forceinline__ void gsr_bwd_eval_cell(uint32_t addr0, uint32_t dst, const gsr_f2 (&nxp)[2], const gsr_f2 (&nyb)[4],
-                                                  const float4* __restrict__ gt, unsigned xin, unsigned yin) {
-  const float4 a0 = gsr_lds128(addr0);               // x, y, a, b
-  const float4 a1 = gsr_lds128(addr0 + GSR_FR_HI);   // c, r, g, bl
+__device__ __forceinline__ void gsr_bwd_eval_cell(const float4 a0, const float4 a1, uint32_t dst, const gsr_f2 (&nxp)[2],
+                                                  const gsr_f2 (&nyb)[4], const float4* __restrict__ gt, unsigned xin,
+                                                  unsigned yin) {
   const gsr_f2 x2 = gsr_pk(a0.x, a0.x), a2 = gsr_pk(a0.z, a0.z);
   const gsr_f2 dx0 = gsr_add2(nxp[0], x2), dx1 = gsr_add2(nxp[1], x2);
   const gsr_f2 ad0 = gsr_mul2(a2, dx0), ad1 = gsr_mul2(a2, dx1);
@@ -310,24 +312,33 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backw
     // ---- evaluate, a block of GSR_BR_T list positions at a time; after each block the lane gathers the sums of
     // its own two entries (entry k's row in cell q's list is its rank there)
     const uint4 mA = sm.meta[warp][cur][0][lane], mB = sm.meta[warp][cur][1][lane];
-    float sa[8], sb[8];
+    gsr_f2 sa[4], sb[4];  // the eight sums of the lane's two entries, as pairs
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sa[i] = sb[i] = 0.f;
+    for (int i = 0; i < 4; ++i) sa[i] = sb[i] = gsr_pk(0.f, 0.f);
     const int uy = uA / p.nrx, ux = uA - uy * p.nrx;
     const int wi0 = ux * GSR_RGW + cx, hi0 = uy * GSR_RGH + cy;  // the lane's cell
     for (int t0 = 0; t0 < trip; t0 += GSR_BR_T) {
       const int te = min(trip, t0 + GSR_BR_T);
       const uint32_t pk = park_l - t0 * GSR_BR_ROW;  // row of list position t: pk + t * GSR_BR_ROW
       // the four lanes of a cell take positions t .. t + 3 (positions past the list's end hold the null record)
+      // (the record of the lane's next position is fetched before the current one is evaluated; the lists are
+      // null-padded past any position read here)
+      int t = t0 + (lane & 3);
+      uint32_t an = gsr_lds16u(lb + 2 * t);
+      float4 n0 = gsr_lds128(an), n1 = gsr_lds128(an + GSR_FR_HI);
       if ((slow_ac | slow_bc) == 0) {
-        for (int t = t0 + (lane & 3); t < te; t += 4) {
-          const uint32_t a = gsr_lds16u(lb + 2 * t);
-          gsr_bwd_eval_cell<false>(a, pk + t * GSR_BR_ROW, nxA, nyA, gt, 15u, 15u);
+        for (; t < te; t += 4) {
+          const float4 c0 = n0, c1 = n1;
+          an = gsr_lds16u(lb + 2 * (t + 4));
+          n0 = gsr_lds128(an), n1 = gsr_lds128(an + GSR_FR_HI);
+          gsr_bwd_eval_cell<false>(c0, c1, pk + t * GSR_BR_ROW, nxA, nyA, gt, 15u, 15u);
         }
       } else {
-        for (int t = t0 + (lane & 3); t < te; t += 4) {
-          const uint32_t a = gsr_lds16u(lb + 2 * t);
-          const uint32_t slot = (a - rb) >> 4;
+        for (; t < te; t += 4) {
+          const float4 c0 = n0, c1 = n1;
+          const uint32_t slot = (an - rb) >> 4;
+          an = gsr_lds16u(lb + 2 * (t + 4));
+          n0 = gsr_lds128(an), n1 = gsr_lds128(an + GSR_FR_HI);
           const bool binds = slot < 32 ? ((slow_ac >> slot) & 1u) : (slot < 64 ? ((slow_bc >> (slot - 32)) & 1u) : false);
           unsigned xin = 15u, yin = 15u;
           if (binds) {  // exact inclusion
@@ -341,7 +352,7 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backw
               yin |= (hi0 + k >= by0 && hi0 + k <= by1) ? 1u << k : 0u;
             }
           }
-          gsr_bwd_eval_cell<true>(a, pk + t * GSR_BR_ROW, nxA, nyA, gt, xin, yin);
+          gsr_bwd_eval_cell<true>(c0, c1, pk + t * GSR_BR_ROW, nxA, nyA, gt, xin, yin);
         }
       }
       __syncwarp();  // the block's rows are parked
@@ -353,11 +364,13 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backw
         const uint32_t rq = (((c < 4 ? mB.x : mB.y) >> (8 * (c & 3))) & 0xffu) - (uint32_t)t0;
         if (((mA.x >> c) & 1u) && ra < (uint32_t)GSR_BR_T) {
           const float4 r0 = gsr_lds128(park_w + ra * GSR_BR_ROW + c * 32), r1 = gsr_lds128(park_w + ra * GSR_BR_ROW + c * 32 + 16);
-          sa[0] += r0.x, sa[1] += r0.y, sa[2] += r0.z, sa[3] += r0.w, sa[4] += r1.x, sa[5] += r1.y, sa[6] += r1.z, sa[7] += r1.w;
+          sa[0] = gsr_add2(sa[0], gsr_pk(r0.x, r0.y)), sa[1] = gsr_add2(sa[1], gsr_pk(r0.z, r0.w));
+          sa[2] = gsr_add2(sa[2], gsr_pk(r1.x, r1.y)), sa[3] = gsr_add2(sa[3], gsr_pk(r1.z, r1.w));
         }
         if (((mA.x >> (8 + c)) & 1u) && rq < (uint32_t)GSR_BR_T) {
           const float4 r0 = gsr_lds128(park_w + rq * GSR_BR_ROW + c * 32), r1 = gsr_lds128(park_w + rq * GSR_BR_ROW + c * 32 + 16);
-          sb[0] += r0.x, sb[1] += r0.y, sb[2] += r0.z, sb[3] += r0.w, sb[4] += r1.x, sb[5] += r1.y, sb[6] += r1.z, sb[7] += r1.w;
+          sb[0] = gsr_add2(sb[0], gsr_pk(r0.x, r0.y)), sb[1] = gsr_add2(sb[1], gsr_pk(r0.z, r0.w));
+          sb[2] = gsr_add2(sb[2], gsr_pk(r1.x, r1.y)), sb[3] = gsr_add2(sb[3], gsr_pk(r1.z, r1.w));
         }
       }
       __syncwarp();  // gathered: the rows may be overwritten
@@ -365,13 +378,13 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backw
     // ---- the chunk's sums -> the Gaussians' moment rows
     if (mA.w != 0xffffffffu) {
       float* mo = q.mom + (size_t)mA.w * 8;
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mo), "f"(sa[0]), "f"(sa[1]), "f"(sa[2]), "f"(sa[3]) : "memory");
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mo + 4), "f"(sa[4]), "f"(sa[5]), "f"(sa[6]), "f"(sa[7]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mo), "f"(gsr_lo(sa[0])), "f"(gsr_hi(sa[0])), "f"(gsr_lo(sa[1])), "f"(gsr_hi(sa[1])) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mo + 4), "f"(gsr_lo(sa[2])), "f"(gsr_hi(sa[2])), "f"(gsr_lo(sa[3])), "f"(gsr_hi(sa[3])) : "memory");
     }
     if (mB.z != 0xffffffffu) {
       float* mo = q.mom + (size_t)mB.z * 8;
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mo), "f"(sb[0]), "f"(sb[1]), "f"(sb[2]), "f"(sb[3]) : "memory");
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mo + 4), "f"(sb[4]), "f"(sb[5]), "f"(sb[6]), "f"(sb[7]) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mo), "f"(gsr_lo(sb[0])), "f"(gsr_hi(sb[0])), "f"(gsr_lo(sb[1])), "f"(gsr_hi(sb[1])) : "memory");
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mo + 4), "f"(gsr_lo(sb[2])), "f"(gsr_hi(sb[2])), "f"(gsr_lo(sb[3])), "f"(gsr_hi(sb[3])) : "memory");
     }
     cur ^= 1;
     ++ci;
