@@ -731,8 +731,9 @@ def main():
                          "note": "the kernel is bound by the MUFU.EX2 / FP32 issue pipes, not by HBM: see DESIGN.md"},
             "step_breakdown": {"raster_ms": kern_ms, "prepare_ms": prep_ms, "forward_step_ms": ms_step,
                                "backward_call_ms": bwd_ms,
-                               "note": "prepare = region build + home-bin sort (gsr_prepare); backward_call = set-up + "
-                                       "gsr_backward_kernel, B_bwd = 64 N + 12 H W bytes",
+                               "note": "prepare = region build + home-bin sort (gsr_prepare); backward_call = region "
+                                       "build + gsr_backward_region_kernel + chain-rule kernel (gsr_backward), "
+                                       "B_bwd = 64 N + 12 H W bytes",
                                "backward_frac": (64 * n + 12 * h * w) / (bwd_ms * 1e-3) / 1e9 / peak},
         }
         if strong is not None:

@@ -42,10 +42,12 @@ _deterministic = os.environ.get("GSR_DETERMINISTIC", "0") not in ("", "0")
 
 
 def set_deterministic(on: bool) -> None:
-    """Bit-reproducible forward renders (GSR_FLAG_DETERMINISTIC: every region list is sorted by Gaussian index
-    before it is rasterised, ~30 % slower).  The reference's atomicAdd accumulation (gs.cu:58-60) is not
-    reproducible run to run; neither is this library's default forward (in the last bits).  The backward always
-    is.  Also settable with GSR_DETERMINISTIC=1 in the environment."""
+    """Bit-reproducible renders and gradients (GSR_FLAG_DETERMINISTIC).  Forward: every region list is sorted by
+    Gaussian index before it is rasterised (~30 % slower).  Backward: the Gaussian-centric kernel (one warp owns a
+    Gaussian, fixed sweep order, one writer per output; ~1.9x slower at the headline shape) instead of the default
+    backward over the region buckets, whose partial sums meet in atomics.  The reference's atomicAdd accumulation
+    (gs.cu:58-60, :163-174) is not reproducible run to run; neither are this library's defaults (in the last bits).
+    Also settable with GSR_DETERMINISTIC=1 in the environment."""
     global _deterministic
     _deterministic = bool(on)
 
@@ -130,7 +132,7 @@ def gs_render_backward(sigmas, coords, colors, grads, grads_sigmas, grads_coords
         ws = workspace_buf if workspace_buf is not None else workspace(s, h, w, sigmas.device)
         rc = L.gsr_backward(_ptr(sigmas), _ptr(coords), _ptr(colors), grads.data_ptr(),
                             _ptr(grads_sigmas), _ptr(grads_coords), _ptr(grads_colors), s, h, w, c,
-                            float(dmax), float(_ksigma if ksigma is None else ksigma), int(flags),
+                            float(dmax), float(_ksigma if ksigma is None else ksigma), _fwd_flags(flags),
                             ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)
 
@@ -188,7 +190,7 @@ def gs_render_backward_band(sigmas, coords, colors, band_grads, grads_sigmas, gr
         rc = L.gsr_backward_band(_ptr(sigmas), _ptr(coords), _ptr(colors), band_grads.data_ptr(),
                                  _ptr(grads_sigmas), _ptr(grads_coords), _ptr(grads_colors), s, h, w, c,
                                  row0, rows, float(dmax), float(_ksigma if ksigma is None else ksigma),
-                                 int(flags), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+                                 _fwd_flags(flags), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)
 
 
@@ -245,7 +247,7 @@ def gs_render_backward_batch(sigmas, coords, colors, grads, grads_sigmas, grads_
         ws = workspace_buf if workspace_buf is not None else workspace_batch(b, s, h, w, sigmas.device)
         rc = L.gsr_backward_batch_uniform(_ptr(sigmas), _ptr(coords), _ptr(colors), grads.data_ptr(),
                                           _ptr(grads_sigmas), _ptr(grads_coords), _ptr(grads_colors), b, s, h, w,
-                                          3, float(dmax), float(_ksigma if ksigma is None else ksigma), int(flags),
+                                          3, float(dmax), float(_ksigma if ksigma is None else ksigma), _fwd_flags(flags),
                                           ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)
 
@@ -411,6 +413,6 @@ def gs_render_backward_batch_padded(sigmas, coords, colors, grads, grads_sigmas,
         ws = workspace_buf if workspace_buf is not None else workspace_batch_padded(b, s, hmax, wmax, sigmas.device)
         rc = L.gsr_backward_batch_padded(_ptr(sigmas), _ptr(coords), _ptr(colors), grads.data_ptr(), _ptr(grads_sigmas),
                                          _ptr(grads_coords), _ptr(grads_colors), b, s, hmax, wmax, hw, dm_arr, dm,
-                                         float(_ksigma if ksigma is None else ksigma), int(flags), ws.data_ptr(),
+                                         float(_ksigma if ksigma is None else ksigma), _fwd_flags(flags), ws.data_ptr(),
                                          ws.numel(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc)

@@ -91,11 +91,14 @@ typedef enum gsr_status {
  * write packets.  Same pixels either way; ~1 % slower on a local image, hence opt-in.  Ignored where it does not
  * apply.  (The uint8 image of GSR_FLAG_U8 always leaves that way when w % 16 == 0.) */
 #define GSR_FLAG_ROW_STORES 0x10u
-/* forward: bit-reproducible output.  The lists a region's pixels are summed from are filled with atomics, so
- * the fp32 summation order -- like that of the reference's atomicAdd (gs.cu:58-60) -- differs from run to run in
- * the last bits.  With this flag every list is sorted by Gaussian index first (HL: +30 % of the step): the image is
+/* bit-reproducible output.  Forward: the lists a region's pixels are summed from are filled with atomics, so the
+ * fp32 summation order -- like that of the reference's atomicAdd (gs.cu:58-60) -- differs from run to run in the
+ * last bits.  With this flag every list is sorted by Gaussian index first (HL: +30 % of the step): the image is
  * then a function of the inputs alone.  Holds while the region lists fit their buckets (no fallback to the
- * home-bin kernel) and no bucket exceeds 8192 entries; the backward is always deterministic. */
+ * home-bin kernel) and no bucket exceeds 8192 entries.  Backward: the default kernel walks the same region buckets
+ * and its partial sums meet in atomics (like the reference's, gs.cu:163-174); with this flag the Gaussian-centric
+ * kernel runs instead (one warp owns a Gaussian, fixed sweep order, one writer per output: always reproducible,
+ * 1.9x slower at the headline shape). */
 #define GSR_FLAG_DETERMINISTIC 0x20u
 
 int gsr_version(void);

@@ -227,8 +227,23 @@ def test_deterministic_mode_is_bit_reproducible():
         a = torch.zeros(h, w, 3, device=DEV)
         gscuda.gs_render(sg, xy, col, a, n, h, w, 3)
         assert torch.equal(a, outs[0])
+        # ... and gradients: the flag selects the Gaussian-centric backward (no atomics)
+        _, s, c, k, h, w = fields.make("C2", 1)
+        sd, cd, kd = s.to(DEV), c.to(DEV), k.to(DEV)
+        g = torch.rand(h, w, 3, device=DEV)
+        runs = []
+        for rep in range(3):
+            out = [torch.zeros_like(sd), torch.zeros_like(cd), torch.zeros_like(kd)]
+            gscuda.gs_render_backward(sd, cd, kd, g, *out, s.shape[0], h, w, 3, 0.1)
+            runs.append(out)
+        for x, y, z in zip(*runs):
+            assert torch.equal(x, y) and torch.equal(x, z)
     finally:
         gscuda.set_deterministic(False)
+    fast = [torch.zeros_like(sd), torch.zeros_like(cd), torch.zeros_like(kd)]
+    gscuda.gs_render_backward(sd, cd, kd, g, *fast, s.shape[0], h, w, 3, 0.1)  # default: over the region buckets
+    for x, f in zip(runs[0], fast):
+        assert float((f - x).abs().max()) <= 2e-4 * float(x.abs().max())  # fp32 summation order (sigma gradients cancel)
 
 
 def test_calls_are_cuda_graph_capturable():
@@ -246,22 +261,28 @@ def test_calls_are_cuda_graph_capturable():
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):  # warm-up outside the capture (lazy module loading, attribute opt-ins)
         gscuda.gs_render(sd, cd, kd, img, n, h, w, 3, 0.1, flags=0x1 | 0x20, workspace_buf=ws)
+        gscuda.gs_render_backward(sd, cd, kd, g, gs, gc, gk, n, h, w, 3, 0.1, flags=0x20, workspace_buf=ws)
         gscuda.gs_render_backward(sd, cd, kd, g, gs, gc, gk, n, h, w, 3, 0.1, workspace_buf=ws)
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
     gs.zero_(), gc.zero_(), gk.zero_()
+    fast = [torch.zeros_like(sd), torch.zeros_like(cd), torch.zeros_like(kd)]  # the default (region) backward
     with torch.cuda.graph(graph):
         gscuda.gs_render(sd, cd, kd, img, n, h, w, 3, 0.1, flags=0x1 | 0x20, workspace_buf=ws)
-        gscuda.gs_render_backward(sd, cd, kd, g, gs, gc, gk, n, h, w, 3, 0.1, workspace_buf=ws)
+        gscuda.gs_render_backward(sd, cd, kd, g, gs, gc, gk, n, h, w, 3, 0.1, flags=0x20, workspace_buf=ws)
+        gscuda.gs_render_backward(sd, cd, kd, g, *fast, n, h, w, 3, 0.1, workspace_buf=ws)
     kd.mul_(0.5)  # new values in the captured buffers
     gs.zero_(), gc.zero_(), gk.zero_()
+    for t_ in fast:
+        t_.zero_()
     graph.replay()
     torch.cuda.synchronize()
     want = torch.zeros(h, w, 3, device=DEV)
     gscuda.gs_render(sd, cd, kd, want, n, h, w, 3, 0.1, flags=0x1 | 0x20)
     ws2 = [torch.zeros_like(sd), torch.zeros_like(cd), torch.zeros_like(kd)]
-    gscuda.gs_render_backward(sd, cd, kd, g, *ws2, n, h, w, 3, 0.1)
+    gscuda.gs_render_backward(sd, cd, kd, g, *ws2, n, h, w, 3, 0.1, flags=0x20)
     assert torch.equal(img, want)              # deterministic mode: bit-identical, replayed or not
-    for a, b in zip((gs, gc, gk), ws2):
-        assert torch.equal(a, b)               # the backward is deterministic by construction
+    for a, b, f in zip((gs, gc, gk), ws2, fast):
+        assert torch.equal(a, b)               # (Gaussian-centric backward: one writer per output, fixed order)
+        assert float((f - b).abs().max()) <= 2e-4 * float(b.abs().max()) + 1e-12  # region backward: summation order
