@@ -2,69 +2,60 @@
 //
 // The Gaussian-centric backward (gsr_backward.cuh) sweeps every Gaussian's cull BOX one pixel per lane and step and
 // spends half of its instructions outside the sweeps (staging, indexing, reductions per Gaussian).  This kernel walks
-// the structure the forward walks instead: a warp per 16x8-pixel region, a 2x2 pixel block per lane, per-cell lists
-// of the bucket entries whose cell mask names the cell -- the same staging pipeline, list building and chunk loop as
-// gsr_forward_region_kernel -- and per (entry, cell) accumulates the EIGHT sums the gradients are linear in
+// the structure the forward walks instead: a warp per 16x8-pixel region, the bucket's entries staged in chunks of 64
+// records (the same claim / request / cp.async pipeline as gsr_forward_region_kernel), every entry carrying the 8-bit
+// mask of the region's 4x4-pixel cells its ellipse reaches.  A chunk's (cell, entry) pairs are laid out as ONE flat
+// list -- cell after cell, each cell's entries in staging order -- and dealt to the lanes round-robin: a lane
+// evaluates a pair's whole 4x4 cell by itself and gets the EIGHT sums the gradients are linear in
 //     sum v g_r, sum v g_g, sum v g_b, Sx, Sy, Sxx, Sxy, Syy      (u = v sum_c g_c col_c; S* = sum u {dx, dy, dx^2, dx dy, dy^2})
-// over the lane's four pixels, reduces them over the cell's four lanes (6 shuffles: recursive halving) and parks
-// them in shared memory at (list position, cell) -- a (cell, entry) pair is evaluated once per chunk, so this is a
-// plain 8-byte store per lane, no atomics (shared-memory float atomics are compare-and-swap loops: the first version
-// of this kernel spent a third of its time in them).  After a block of list positions, lane k gathers the rows of
-// ITS two staged entries (their cells and list ranks are what the list builder computed) into registers and, at the
-// end of the chunk, adds them to the Gaussian's row of a moment array in global memory (2 vector REDs per entry and
-// region); gsr_bwd_chain_kernel then applies the chain rule of gs.cu:139-159 once per Gaussian.  ~70 instructions per 128 (Gaussian, pixel) pairs
-// against 26 per 32 in the box sweeps, none of the per-Gaussian overhead, and no home-bin sort.
+// complete in its registers -- no cross-lane reduction, no idle lanes behind the longest cell list -- and adds them to
+// the Gaussian's row of a moment array in global memory (2 vector REDs per pair); gsr_bwd_chain_kernel then applies
+// the chain rule of gs.cu:139-159 once per Gaussian.  No home-bin sort.
+// History (HL, kernel + chain + clearing): 2x2 block per lane, sums reduced over a cell's four lanes and added to
+// per-slot accumulators with shared-memory float atomics (compare-and-swap loops) 1.58 ms; parked per (list position,
+// cell) and gathered per entry 1.10 ms; a whole cell per lane (the reduction was 44 % of the instructions) 0.87 ms;
+// three CTAs per SM, record prefetch 0.77 ms; this version see DESIGN.md.
 // Summation order follows the atomics: not bit-reproducible -- GSR_FLAG_DETERMINISTIC keeps the Gaussian-centric kernel.
 #pragma once
 #include "gsr_forward_ws.cuh"
 
-#ifndef GSR_CFG_BR_T
-#define GSR_CFG_BR_T 28   // list positions parked before the entries gather their sums: as many as three CTAs per SM allow
-#endif
 #ifndef GSR_CFG_BR_MIN_CTAS
-#define GSR_CFG_BR_MIN_CTAS (GSR_CFG_BR_T <= 16 ? 4 : 3)
+#define GSR_CFG_BR_MIN_CTAS 3
 #endif
-static_assert(GSR_FR_LW == 2, "the cell lists are read as 16-bit addresses");
-constexpr int GSR_BR_T = GSR_CFG_BR_T;
-__device__ __forceinline__ float gsr_lo(gsr_f2 v) { return __uint_as_float((uint32_t)v); }
-__device__ __forceinline__ float gsr_hi(gsr_f2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
-constexpr int GSR_BR_ROW = 8 * 32 + 16;  // bytes per list position: 8 cells x 8 sums, padded (gather: conflict-free)
+constexpr int GSR_BR_FLAT = 8 * GSR_FR_CHUNK + 32;  // items of a chunk's flat list: every cell of every entry, + padding
 
 struct GsrBwdRegionSmem {
-  float4 rec[GSR_FR_WARPS][2][2 * GSR_FR_SLOTS];
+  float4 rec[GSR_FR_WARPS][2][2 * GSR_FR_SLOTS];   // per warp, 2 stages x { first float4 x 65, second float4 x 65 }
   uint2 box[GSR_FR_WARPS][2][GSR_FR_CHUNK];
-  uint32_t list[GSR_FR_WARPS][2][GSR_FR_LIST_STAGE / 4];
-  uint4 meta[GSR_FR_WARPS][2][2][32];  // per stage and lane: {masks, ranks a (2), index a}, {ranks b (2), index b, -}
-  float4 park[GSR_FR_WARPS][GSR_BR_T * GSR_BR_ROW / 16];  // (list position, cell) -> the cell's eight sums
-  float4 gtile[GSR_FR_WARPS][8][4 * 3];  // dL/dimg of the unit being evaluated: [cell][row][channel] x 4 columns
+  uint32_t flat[GSR_FR_WARPS][2][GSR_BR_FLAT];     // record address (16 bits: first 64 KB of the window) | cell << 16
+  int gidx[GSR_FR_WARPS][2][GSR_FR_CHUNK];         // Gaussian index of every staged slot
+  float4 gtile[GSR_FR_WARPS][8][4 * 3];            // dL/dimg of the unit being evaluated: [cell][row][channel] x 4 columns
+  float4 cx[GSR_FR_WARPS][4], cy[GSR_FR_WARPS][2]; // its NEGATED pixel coordinates: 16 columns, 8 rows
 };
-static_assert(offsetof(GsrBwdRegionSmem, box) < 65536, "16-bit list addresses: the records sit in the first 64 KB");
 struct GsrBwdRegionArgs {
   const float* grads;  // dL/dimg, (h,w,3) or (3,h,w) (flag 2)
   float* mom;          // (s, 8) moment rows, zero on entry
 };
 
-// One record against a whole 4x4 CELL, by one lane: the four lanes of a cell take four consecutive positions of the
-// cell's list, so the eight sums of a (cell, entry) pair are complete in one lane -- no cross-lane reduction (in the
-// first version, a 2x2 block per lane, the shuffles and selects of that reduction were 44 % of all instructions).
-// nxp / nyb: NEGATED pixel coordinates of the cell's four columns (two pairs) and four rows (each twice), so d = x - px: the odd
-// moments come out with the opposite sign of the reference's dx = px - x (gsr_bwd_chain_kernel accounts for it).
-// gt: the cell's dL/dimg in shared memory, [row][channel][column]; dst: the 32 bytes of the (list position, cell) row.
-// a0 = {x, y, a, b}, a1 = {c, r, g, bl}: the staged record.
+// One record against a whole 4x4 CELL, by one lane.  a0 = {x, y, a, b}, a1 = {c, r, g, bl}: the staged record;
+// X / Y: NEGATED pixel coordinates of the cell's four columns / rows, so d = x - px: the odd moments come out with the
+// opposite sign of the reference's dx = px - x (gsr_bwd_chain_kernel accounts for it).  gt: the cell's dL/dimg in
+// shared memory, [row][channel][column]; mo: the Gaussian's moment row (nullptr: the null record that pads the list).
 template <bool MASKED>
-__device__ __forceinline__ void gsr_bwd_eval_cell(const float4 a0, const float4 a1, uint32_t dst, const gsr_f2 (&nxp)[2],
-                                                  const gsr_f2 (&nyb)[4], const float4* __restrict__ gt, unsigned xin,
-                                                  unsigned yin) {
+__device__ __forceinline__ void gsr_bwd_eval_cell(const float4 a0, const float4 a1, const float4 X, const float4 Y,
+                                                  const float4* __restrict__ gt, unsigned xin, unsigned yin, float* mo) {
   const gsr_f2 x2 = gsr_pk(a0.x, a0.x), a2 = gsr_pk(a0.z, a0.z);
-  const gsr_f2 dx0 = gsr_add2(nxp[0], x2), dx1 = gsr_add2(nxp[1], x2);
+  const gsr_f2 dx0 = gsr_add2(gsr_pk(X.x, X.y), x2), dx1 = gsr_add2(gsr_pk(X.z, X.w), x2);
   const gsr_f2 ad0 = gsr_mul2(a2, dx0), ad1 = gsr_mul2(a2, dx1);
   const gsr_f2 cr = gsr_pk(a1.y, a1.y), cg = gsr_pk(a1.z, a1.z), cb = gsr_pk(a1.w, a1.w);
-  const gsr_f2 y2 = gsr_pk(a0.y, a0.y), b2 = gsr_pk(a0.w, a0.w), c2 = gsr_pk(a1.x, a1.x);
+  const gsr_f2 b2 = gsr_pk(a0.w, a0.w), c2 = gsr_pk(a1.x, a1.x);
+  const float ny[4] = {Y.x, Y.y, Y.z, Y.w};
   // every sum is kept as a pair over the two column halves until the end (rows enter as broadcast pairs)
   gsr_f2 Cr = gsr_pk(0.f, 0.f), Cg = Cr, Cb = Cr, Sx2 = Cr, Sy2 = Cr, Sxx2 = Cr, Sxy2 = Cr, Syy2 = Cr;
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    const gsr_f2 dyb = gsr_add2(nyb[r], y2);
+    const float dy = ny[r] + a0.y;
+    const gsr_f2 dyb = gsr_pk(dy, dy);
     const gsr_f2 t12 = gsr_mul2(b2, dyb), t02 = gsr_mul2(gsr_mul2(c2, dyb), dyb);
     const gsr_f2 e0 = gsr_fma2(dx0, gsr_add2(ad0, t12), t02), e1 = gsr_fma2(dx1, gsr_add2(ad1, t12), t02);
     float ea, eb, ec, ed;
@@ -105,29 +96,62 @@ __device__ __forceinline__ void gsr_bwd_eval_cell(const float4 a0, const float4 
       s[i] = lo + hi;
     }
   }
-  // (the null record that pads the lists parks sums nobody gathers)
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(s[0]), "f"(s[1]), "f"(s[2]), "f"(s[3]) : "memory");
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16), "f"(s[4]), "f"(s[5]), "f"(s[6]), "f"(s[7]) : "memory");
+  if (mo) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mo), "f"(s[0]), "f"(s[1]), "f"(s[2]), "f"(s[3]) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mo + 4), "f"(s[4]), "f"(s[5]), "f"(s[6]), "f"(s[7]) : "memory");
+  }
+}
+
+// The flat list of one staged chunk: item = record address | cell << 16, the items of cell 0 first, then cell 1, ...,
+// within a cell in the order (lane 0: first, second entry), (lane 1: ...).  The eight ranks of an entry come from ONE
+// warp scan (the masks spread to a byte per cell, prefix-summed across the lanes; counts stay below 256), the cells'
+// offsets from the totals.  32 null items follow the last one (lanes read one item ahead).  Returns the item count.
+// lw: the stage's list; rb: the stage's records; (v1a, e1a), (v1b, e1b): this lane's two entries.  Warp-collective.
+__device__ __forceinline__ int gsr_br_build_flat(uint32_t lw, uint32_t rb, int lane, bool v1a, uint32_t e1a, bool v1b,
+                                                 uint32_t e1b) {
+  const unsigned full = 0xffffffffu;
+  const uint32_t ma = v1a ? (e1a >> GSR_ENT_MASK_SHIFT) & 0xffu : 0u, mb = v1b ? (e1b >> GSR_ENT_MASK_SHIFT) & 0xffu : 0u;
+  const uint32_t a_lo = ((ma & 15u) * 0x00204081u) & 0x01010101u, a_hi = ((ma >> 4) * 0x00204081u) & 0x01010101u;
+  const uint32_t b_lo = ((mb & 15u) * 0x00204081u) & 0x01010101u, b_hi = ((mb >> 4) * 0x00204081u) & 0x01010101u;
+  uint32_t s_lo = a_lo + b_lo, s_hi = a_hi + b_hi;  // inclusive prefix sums, a byte per cell
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t0 = __shfl_up_sync(full, s_lo, d), t1 = __shfl_up_sync(full, s_hi, d);
+    if (lane >= d) {
+      s_lo += t0;
+      s_hi += t1;
+    }
+  }
+  const uint32_t t_lo = __shfl_sync(full, s_lo, 31), t_hi = __shfl_sync(full, s_hi, 31);
+  const uint32_t ra_lo = s_lo - a_lo - b_lo, ra_hi = s_hi - a_hi - b_hi;  // exclusive: rank of the first entry
+  const uint32_t rb_lo = ra_lo + a_lo, rb_hi = ra_hi + a_hi;              // the second entry follows the first
+  const uint32_t adr_a = rb + lane * 16u, adr_b = adr_a + 32 * 16u;
+  uint32_t off = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const uint32_t ra = ((q < 4 ? ra_lo : ra_hi) >> (8 * (q & 3))) & 0xffu;
+    const uint32_t rbq = ((q < 4 ? rb_lo : rb_hi) >> (8 * (q & 3))) & 0xffu;
+    if ((ma >> q) & 1u) gsr_sts32(lw + 4 * (off + ra), adr_a | ((uint32_t)q << 16));
+    if ((mb >> q) & 1u) gsr_sts32(lw + 4 * (off + rbq), adr_b | ((uint32_t)q << 16));
+    off += ((q < 4 ? t_lo : t_hi) >> (8 * (q & 3))) & 0xffu;
+  }
+  gsr_sts32(lw + 4 * (off + lane), rb + GSR_FR_CHUNK * 16u);  // null items
+  return (int)off;
 }
 
 __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backward_region_kernel(GsrFwdArgs p, GsrBwdRegionArgs q) {
   if (gsr_guard_skip(p.guard, p.want)) return;
   extern __shared__ __align__(16) unsigned char gsr_br_smem_raw[];
   GsrBwdRegionSmem& sm = *reinterpret_cast<GsrBwdRegionSmem*>(gsr_br_smem_raw);
+  static_assert(offsetof(GsrBwdRegionSmem, box) < 65536, "16-bit record addresses: the records sit in the first 64 KB");
   constexpr int CH = GSR_FR_CHUNK;
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int cell = lane >> 2;
-  const unsigned lt = (1u << lane) - 1u;
   const int nunits = p.nrx * p.nry;
   const uint32_t rec_s = gsr_smem_addr(&sm.rec[warp][0][0]);
-  const uint32_t list_w = gsr_smem_addr(&sm.list[warp][0][0]);   // the warp's lists, stage 0
-  const uint32_t list_c = list_w + cell * GSR_FR_LIST;           // this lane's cell
+  const uint32_t flat_w = gsr_smem_addr(&sm.flat[warp][0][0]);   // the warp's flat list, stage 0
   const uint32_t box_s = gsr_smem_addr(&sm.box[warp][0][0]);
   const uint2* box_w = &sm.box[warp][0][0];
-  const uint32_t park_w = gsr_smem_addr(&sm.park[warp][0]);
-  const uint32_t park_l = park_w + cell * 32;  // this lane's cell in a row
-  const float4* gt = &sm.gtile[warp][cell][0];
   const int total_warps = gridDim.x * GSR_FR_WARPS;
 
   // the null record of both stages (slot CH): zero conic and colour, adds exactly 0
@@ -192,8 +216,8 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backw
     e1a = v1a ? __ldg(src + i0) : 0u;
     e1b = v1b ? __ldg(src + i1) : 0u;
   };
-  // Records of the requested entries -> stage `st` (cp.async), their cell lists -> list stage `st`.
-  // Returns the trip count of the chunk (longest list, rounded up to 4) and the binds ballots.
+  // Records of the requested entries -> stage `st` (cp.async), their (cell, entry) pairs -> flat list of stage `st`.
+  // Returns the number of pairs, and the binds ballots.
   unsigned slow_a = 0, slow_b = 0;
   auto stage_chunk = [&](int st) -> int {
     const uint32_t rb = rec_s + st * GSR_FR_STAGE_BYTES;
@@ -201,28 +225,20 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backw
     for (int t = 0; t < 2; ++t) {
       const uint32_t en = t ? e1b : e1a;
       const bool v = t ? v1b : v1a;
+      const int k = lane + 32 * t;
       if (v) {
         const uint32_t gi = en & GSR_ENT_INDEX;
-        const int k = lane + 32 * t;
         const char* src = reinterpret_cast<const char*>(p.rec_in + gi);
         gsr_cp_async16ca(rb + k * 16, src);
         gsr_cp_async16ca(rb + GSR_FR_HI + k * 16, src + 16);
         if (en >> 31) gsr_cp_async8(box_s + (st * CH + k) * 8, p.box_in + gi);
+        sm.gidx[warp][st][k] = (int)gi;  // whom the slot's sums belong to
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     slow_a = __ballot_sync(full, v1a && (e1a >> 31));
     slow_b = __ballot_sync(full, v1b && (e1b >> 31));
-    uint32_t rk[5];
-    const int mine = gsr_fr_build_lists<true>(list_w + st * GSR_FR_LIST_STAGE, rb, lane, cell, v1a, e1a, v1b, e1b, rk);
-    // whom the parked sums belong to, and where they are parked (read back by this lane only)
-    sm.meta[warp][st][0][lane] = make_uint4(rk[0], rk[1], rk[2], v1a ? (e1a & GSR_ENT_INDEX) : 0xffffffffu);
-    sm.meta[warp][st][1][lane] = make_uint4(rk[3], rk[4], v1b ? (e1b & GSR_ENT_INDEX) : 0xffffffffu, 0u);
-#if GSR_CFG_FR_TAIL
-    return __reduce_max_sync(full, mine);
-#else
-    return (__reduce_max_sync(full, mine) + 3) & ~3;
-#endif
+    return gsr_br_build_flat(flat_w + st * (GSR_BR_FLAT * 4), rb, lane, v1a, e1a, v1b, e1b);
   };
 
   // Units in flight: A is evaluated, B and C are known far enough ahead for the two-deep prefetch to run
@@ -231,35 +247,20 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backw
   int nchA = chunks_of(nA), nchB = chunks_of(nB);
 
   request_entries(uA, 0, nA, nchA);
-  int trip = stage_chunk(0);
+  int total = stage_chunk(0);
   unsigned slow_ac = slow_a, slow_bc = slow_b;
   if (1 < nchA) request_entries(uA, 1, nA, nchA); else request_entries(uB, 0, nB, nchB);
 
   int cur = 0, ci = 0;
-  // pixel block of this lane in unit u: cell (cell & 3, cell >> 2), block (lane & 1, (lane >> 1) & 1) of the cell
+  // What a unit needs besides its bucket: dL/dimg of its 16x8 pixels and their coordinates.  Fetched a unit ahead
+  // into registers -- a 2x2 block of dL/dimg per lane ({row 0, row 1} x {r, g, b}, each a pair over the two columns;
+  // pixels outside the image: 0) and one coordinate (lanes 0-15: columns, 16-23: rows) -- and laid down in the warp's
+  // shared memory when the unit's turn comes.
+  const int cell = lane >> 2;
   const int bx = (cell & 3) * GSR_CELL + (lane & 1) * 2, by = (cell >> 2) * GSR_CELL + ((lane >> 1) & 1) * 2;
-  // NEGATED coordinates of this lane's CELL in unit u: four columns (two pairs), four rows
-  const int cx = (cell & 3) * GSR_CELL, cy = (cell >> 2) * GSR_CELL;
-  auto coords_of = [&](int u, gsr_f2 (&nx)[2], gsr_f2 (&ny)[4]) {
-    const int uy = (u < nunits ? u : 0) / p.nrx, ux = (u < nunits ? u : 0) - uy * p.nrx;
-    const int wi = ux * GSR_RGW + cx, hi = uy * GSR_RGH + cy;
-    nx[0] = gsr_pk(-__ldg(p.px_tab + min(wi, p.w - 1)), -__ldg(p.px_tab + min(wi + 1, p.w - 1)));
-    nx[1] = gsr_pk(-__ldg(p.px_tab + min(wi + 2, p.w - 1)), -__ldg(p.px_tab + min(wi + 3, p.w - 1)));
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const float v = -__ldg(p.py_tab + min(hi + r, p.h - 1));
-      ny[r] = gsr_pk(v, v);
-    }
-  };
-  gsr_f2 nxA[2], nxB[2];
-  gsr_f2 nyA[4], nyB[4];
-  coords_of(uA, nxA, nyA);
-  coords_of(uB, nxB, nyB);
-  // dL/dimg of unit u: fetched a 2x2 block per lane ({row 0, row 1} x {r, g, b}, each a pair over the two columns;
-  // pixels outside the image: 0), then laid down in the warp's tile for the lanes that evaluate whole cells
   const bool chw = (p.flags & 2u) != 0;
   const size_t plane = (size_t)p.h * p.w;
-  auto grads_of = [&](int u, gsr_f2 (&g)[2][3]) {
+  auto fetch_unit = [&](int u, gsr_f2 (&g)[2][3], float& coord) {
     const int uy = (u < nunits ? u : 0) / p.nrx, ux = (u < nunits ? u : 0) - uy * p.nrx;
     const int wi = ux * GSR_RGW + bx, hi = uy * GSR_RGH + by;
 #pragma unroll
@@ -275,8 +276,10 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backw
         }
         g[yy][ch] = gsr_pk(v[0], v[1]);
       }
+    coord = lane < 16 ? -__ldg(p.px_tab + min(ux * GSR_RGW + lane, p.w - 1))
+                      : -__ldg(p.py_tab + min(uy * GSR_RGH + (lane & 7), p.h - 1));
   };
-  auto store_tile = [&](const gsr_f2 (&g)[2][3]) {  // [cell][row][channel][column]
+  auto store_unit = [&](const gsr_f2 (&g)[2][3], float coord) {  // tile: [cell][row][channel][column]
     float* base = reinterpret_cast<float*>(&sm.gtile[warp][cell][0]) + (((lane >> 1) & 1) * 2) * 12 + (lane & 1) * 2;
 #pragma unroll
     for (int yy = 0; yy < 2; ++yy)
@@ -286,19 +289,23 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backw
         gsr_upk(g[yy][ch], lo, hi);
         *reinterpret_cast<float2*>(base + yy * 12 + ch * 4) = make_float2(lo, hi);
       }
+    if (lane < 16) reinterpret_cast<float*>(&sm.cx[warp][0])[lane] = coord;
+    else if (lane < 24) reinterpret_cast<float*>(&sm.cy[warp][0])[lane - 16] = coord;
   };
   gsr_f2 gB[2][3];
-  grads_of(uA, gB);
-  store_tile(gB);
-  grads_of(uB, gB);
+  float coordB;
+  fetch_unit(uA, gB, coordB);
+  store_unit(gB, coordB);
+  fetch_unit(uB, gB, coordB);
   __syncwarp();
+
   for (;;) {  // one chunk per iteration, flat over the warp's units
     const uint32_t rb = rec_s + cur * GSR_FR_STAGE_BYTES;
-    const uint32_t lb = list_c + cur * GSR_FR_LIST_STAGE;
+    const uint32_t fb = flat_w + cur * (GSR_BR_FLAT * 4);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();  // this chunk's records and lists are visible; the other stage is free
-    // records and lists of the next chunk (its entries were requested one chunk ago) ...
-    const int trip_n = stage_chunk(cur ^ 1);
+    __syncwarp();  // this chunk's records and list are visible; the other stage is free
+    // records and list of the next chunk (its entries were requested one chunk ago) ...
+    const int total_n = stage_chunk(cur ^ 1);
     const unsigned slow_an = slow_a, slow_bn = slow_b;
     // ... and the entries of the chunk after it: (A, ci + 2), (B, 0), (B, 1) or (C, 0)
     const bool last = ci + 1 >= nchA;
@@ -309,42 +316,33 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backw
       else { const int n = min(nC, p.reg_cap); request_entries(uC, 0, n, chunks_of(n)); }
     }
 
-    // ---- evaluate, a block of GSR_BR_T list positions at a time; after each block the lane gathers the sums of
-    // its own two entries (entry k's row in cell q's list is its rank there)
-    const uint4 mA = sm.meta[warp][cur][0][lane], mB = sm.meta[warp][cur][1][lane];
-    gsr_f2 sa[4], sb[4];  // the eight sums of the lane's two entries, as pairs
-#pragma unroll
-    for (int i = 0; i < 4; ++i) sa[i] = sb[i] = gsr_pk(0.f, 0.f);
-    const int uy = uA / p.nrx, ux = uA - uy * p.nrx;
-    const int wi0 = ux * GSR_RGW + cx, hi0 = uy * GSR_RGH + cy;  // the lane's cell
-    for (int t0 = 0; t0 < trip; t0 += GSR_BR_T) {
-      const int te = min(trip, t0 + GSR_BR_T);
-      const uint32_t pk = park_l - t0 * GSR_BR_ROW;  // row of list position t: pk + t * GSR_BR_ROW
-      // the four lanes of a cell take positions t .. t + 3 (positions past the list's end hold the null record)
-      // (the record of the lane's next position is fetched before the current one is evaluated; the lists are
-      // null-padded past any position read here)
-      int t = t0 + (lane & 3);
-      uint32_t an = gsr_lds16u(lb + 2 * t);
-      float4 n0 = gsr_lds128(an), n1 = gsr_lds128(an + GSR_FR_HI);
-      if ((slow_ac | slow_bc) == 0) {
-        for (; t < te; t += 4) {
-          const float4 c0 = n0, c1 = n1;
-          an = gsr_lds16u(lb + 2 * (t + 4));
-          n0 = gsr_lds128(an), n1 = gsr_lds128(an + GSR_FR_HI);
-          gsr_bwd_eval_cell<false>(c0, c1, pk + t * GSR_BR_ROW, nxA, nyA, gt, 15u, 15u);
-        }
-      } else {
-        for (; t < te; t += 4) {
-          const float4 c0 = n0, c1 = n1;
-          const uint32_t slot = (an - rb) >> 4;
-          an = gsr_lds16u(lb + 2 * (t + 4));
-          n0 = gsr_lds128(an), n1 = gsr_lds128(an + GSR_FR_HI);
-          const bool binds = slot < 32 ? ((slow_ac >> slot) & 1u) : (slot < 64 ? ((slow_bc >> (slot - 32)) & 1u) : false);
+    // ---- evaluate: item lane, lane + 32, ... of the flat list; the item after next is fetched ahead (the list
+    // ends in 32 null items)
+    {
+      const int uy = uA / p.nrx, ux = uA - uy * p.nrx;
+      const bool slow = (slow_ac | slow_bc) != 0;
+      int i = lane;
+      uint32_t itn = gsr_lds32u(fb + 4 * i);
+      float4 n0 = gsr_lds128(itn & 0xffffu), n1 = gsr_lds128((itn & 0xffffu) + GSR_FR_HI);
+      for (; i < total; i += 32) {
+        const float4 c0 = n0, c1 = n1;
+        const uint32_t it = itn;
+        itn = gsr_lds32u(fb + 4 * (i + 32));
+        n0 = gsr_lds128(itn & 0xffffu), n1 = gsr_lds128((itn & 0xffffu) + GSR_FR_HI);
+        const uint32_t cq = it >> 16, slot = ((it & 0xffffu) - rb) >> 4;  // (slot < CH: i < total)
+        float* mo = q.mom + (size_t)sm.gidx[warp][cur][slot & (CH - 1)] * 8;
+        const float4 X = sm.cx[warp][cq & 3], Y = sm.cy[warp][cq >> 2];
+        const float4* gt = &sm.gtile[warp][cq][0];
+        if (!slow) {
+          gsr_bwd_eval_cell<false>(c0, c1, X, Y, gt, 15u, 15u, mo);
+        } else {
+          const bool binds = slot < 32 ? ((slow_ac >> slot) & 1u) : ((slow_bc >> (slot - 32)) & 1u);
           unsigned xin = 15u, yin = 15u;
           if (binds) {  // exact inclusion
             int bx0, bx1, by0, by1;
             bool bd;
             gsr_box_unpack(box_w[cur * CH + slot], bx0, bx1, by0, by1, bd);
+            const int wi0 = ux * GSR_RGW + (int)(cq & 3) * GSR_CELL, hi0 = uy * GSR_RGH + (int)(cq >> 2) * GSR_CELL;
             xin = yin = 0u;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -352,43 +350,13 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backw
               yin |= (hi0 + k >= by0 && hi0 + k <= by1) ? 1u << k : 0u;
             }
           }
-          gsr_bwd_eval_cell<true>(c0, c1, pk + t * GSR_BR_ROW, nxA, nyA, gt, xin, yin);
+          gsr_bwd_eval_cell<true>(c0, c1, X, Y, gt, xin, yin, mo);
         }
       }
-      __syncwarp();  // the block's rows are parked
-      // (unrolled over the cells and predicated: sixteen independent bodies.  Loops over the set bits of the masks
-      // issue fewer instructions but run as a dependent chain: HL 866 -> 1034 us)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const uint32_t ra = (((c < 4 ? mA.y : mA.z) >> (8 * (c & 3))) & 0xffu) - (uint32_t)t0;
-        const uint32_t rq = (((c < 4 ? mB.x : mB.y) >> (8 * (c & 3))) & 0xffu) - (uint32_t)t0;
-        if (((mA.x >> c) & 1u) && ra < (uint32_t)GSR_BR_T) {
-          const float4 r0 = gsr_lds128(park_w + ra * GSR_BR_ROW + c * 32), r1 = gsr_lds128(park_w + ra * GSR_BR_ROW + c * 32 + 16);
-          sa[0] = gsr_add2(sa[0], gsr_pk(r0.x, r0.y)), sa[1] = gsr_add2(sa[1], gsr_pk(r0.z, r0.w));
-          sa[2] = gsr_add2(sa[2], gsr_pk(r1.x, r1.y)), sa[3] = gsr_add2(sa[3], gsr_pk(r1.z, r1.w));
-        }
-        if (((mA.x >> (8 + c)) & 1u) && rq < (uint32_t)GSR_BR_T) {
-          const float4 r0 = gsr_lds128(park_w + rq * GSR_BR_ROW + c * 32), r1 = gsr_lds128(park_w + rq * GSR_BR_ROW + c * 32 + 16);
-          sb[0] = gsr_add2(sb[0], gsr_pk(r0.x, r0.y)), sb[1] = gsr_add2(sb[1], gsr_pk(r0.z, r0.w));
-          sb[2] = gsr_add2(sb[2], gsr_pk(r1.x, r1.y)), sb[3] = gsr_add2(sb[3], gsr_pk(r1.z, r1.w));
-        }
-      }
-      __syncwarp();  // gathered: the rows may be overwritten
-    }
-    // ---- the chunk's sums -> the Gaussians' moment rows
-    if (mA.w != 0xffffffffu) {
-      float* mo = q.mom + (size_t)mA.w * 8;
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mo), "f"(gsr_lo(sa[0])), "f"(gsr_hi(sa[0])), "f"(gsr_lo(sa[1])), "f"(gsr_hi(sa[1])) : "memory");
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mo + 4), "f"(gsr_lo(sa[2])), "f"(gsr_hi(sa[2])), "f"(gsr_lo(sa[3])), "f"(gsr_hi(sa[3])) : "memory");
-    }
-    if (mB.z != 0xffffffffu) {
-      float* mo = q.mom + (size_t)mB.z * 8;
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mo), "f"(gsr_lo(sb[0])), "f"(gsr_hi(sb[0])), "f"(gsr_lo(sb[1])), "f"(gsr_hi(sb[1])) : "memory");
-      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mo + 4), "f"(gsr_lo(sb[2])), "f"(gsr_hi(sb[2])), "f"(gsr_lo(sb[3])), "f"(gsr_hi(sb[3])) : "memory");
     }
     cur ^= 1;
     ++ci;
-    trip = trip_n;
+    total = total_n;
     slow_ac = slow_an;
     slow_bc = slow_bn;
     if (!last) continue;
@@ -404,12 +372,9 @@ __global__ void __launch_bounds__(GSR_FR_THREADS, GSR_CFG_BR_MIN_CTAS) gsr_backw
     uC = take_unit();
     nC = count_of(uC);
     ci = 0;
-    nxA[0] = nxB[0], nxA[1] = nxB[1];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) nyA[r] = nyB[r];
-    coords_of(uB, nxB, nyB);
-    store_tile(gB);  // (every lane is past its last read of the tile: the gather's __syncwarp)
-    grads_of(uB, gB);
+    __syncwarp();  // every lane is past its last read of the unit's tile and coordinates
+    store_unit(gB, coordB);
+    fetch_unit(uB, gB, coordB);
     __syncwarp();
   }
   finish();
