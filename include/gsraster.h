@@ -114,6 +114,10 @@ int gsr_forward(const float* sigmas, const float* coords, const float* colors, f
                 int s, int h, int w, int c, float dmax, float ksigma, uint32_t flags,
                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* Gradients are ACCUMULATED into grads_* (the reference's atomicAdd contract, gs.cu:163-174).  flags:
+ * GSR_FLAG_CHW (grads is (3,h,w)); GSR_FLAG_DETERMINISTIC (the Gaussian-centric kernel: bit-reproducible, slower).
+ * Default: the backward over the region buckets -- its partial sums meet in fp32 REDs, so the last bits vary run
+ * to run, as the reference's do. */
 int gsr_backward(const float* sigmas, const float* coords, const float* colors,
                  const float* grads, float* grads_sigmas, float* grads_coords,
                  float* grads_colors, int s, int h, int w, int c, float dmax, float ksigma,
