@@ -2,7 +2,7 @@
 travels to the GPU box with the snapshot like the compiled reference kernels).  TEST INFRASTRUCTURE ONLY:
 used by the drop-in tests (the reference's gswrapper.py / gaussian_splatting.py running on top of this repo's
 `gscuda` module), by bench.py's cpu_baseline leg (rendering_python, the path BASELINE config 1 names) and by
-tools/train_step_c5.py (the Fea2GS_ROPE_AMP head of BASELINE config 5).  Nothing is copied into the repository's
+tests/report_train_step_c5.py (the Fea2GS_ROPE_AMP head of BASELINE config 5).  Nothing is copied into the repository's
 history; /root/reference is only read where it exists (this container), by stage().
 """
 from __future__ import annotations

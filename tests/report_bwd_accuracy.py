@@ -1,5 +1,5 @@
 """Error of the two backward kernels against the fp64 oracle (same field, same gradient image; lives under tests/ because it runs the oracle):
-   python tests/bwd_accuracy_report.py [C1|C2]      -> max |err| / max |gradient| per output, region vs Gaussian-centric."""
+   python tests/report_bwd_accuracy.py [C1|C2]      -> max |err| / max |gradient| per output, region vs Gaussian-centric."""
 import os, sys, json
 import numpy as np
 import torch

@@ -14,8 +14,8 @@ its share of the step.  Render variants: `reference-loop` = the reference's gene
 uniform-batch call of this library (one set-up + one raster launch each way); `batch-fused` = the same with the front
 end folded into the set-up kernel and the L1 loss + its gradient as one kernel (losses.l1_crop_loss_padded).
 
-    torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/train_step_c5.py [--ddp] [--steps 5]
-    python tools/train_step_c5.py --per-gpu 1 --depth tiny          (single GPU smoke run)
+    torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tests/report_train_step_c5.py [--ddp] [--steps 5]
+    python tests/report_train_step_c5.py --per-gpu 1 --depth tiny          (single GPU smoke run)
 """
 import argparse, json, os, sys, time
 import torch
