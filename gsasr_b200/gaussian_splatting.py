@@ -54,10 +54,13 @@ class _RenderCHW(Function):
         n = sigmas.shape[0]
         step = n if not buffer_size else int(buffer_size)
         first = True
+        # one chunk: its set-up (region buckets, records) serves the backward too (gscuda.set_reuse_setup)
+        keep = _gs.get_reuse_setup() and 0 < n <= step and any(ctx.needs_input_grad[:3])
+        ctx.ws = _gs.workspace(n, h, w, sigmas.device) if keep else None
         for a in range(0, max(n, 1), max(step, 1)):
             b = min(a + step, n)
             _gs.gs_render(sigmas[a:b], coords[a:b], colors[a:b], out, b - a, h, w, 3, dmax,
-                          flags=_CHW | (_OVER if first else 0))
+                          flags=_CHW | (_OVER if first else 0), workspace_buf=ctx.ws)
             first = False
         return out
 
@@ -70,6 +73,10 @@ class _RenderCHW(Function):
         gs, gc, gk = torch.zeros_like(sigmas), torch.zeros_like(coords), torch.zeros_like(colors)
         n = sigmas.shape[0]
         step = n if not buffer_size else int(buffer_size)
+        ws, ctx.ws = getattr(ctx, "ws", None), None
+        if ws is not None and _gs.get_reuse_setup():
+            _gs.gs_render_backward_prepared(sigmas, grad, gs, gc, gk, n, h, w, ws, flags=_CHW)
+            return gs, gc, gk, None, None, None, None
         for a in range(0, n, max(step, 1)):
             b = min(a + step, n)
             _gs.gs_render_backward(sigmas[a:b], coords[a:b], colors[a:b], grad, gs[a:b], gc[a:b],

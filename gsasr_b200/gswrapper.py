@@ -22,7 +22,11 @@ class GSCUDA(Function):
         ctx.dmax = dmax
         h, w, c = rendered_img.shape
         s = sigmas.shape[0]
-        GSWrapper.gs_render(sigmas, coords, colors, rendered_img, s, h, w, c, dmax)
+        # the set-up of this call (region buckets, records) serves the backward too: see gscuda.set_reuse_setup
+        keep = GSWrapper.get_reuse_setup() and c == 3 and s > 0 and any(ctx.needs_input_grad[:3])
+        ws = GSWrapper.workspace(s, h, w, sigmas.device) if keep else None
+        GSWrapper.gs_render(sigmas, coords, colors, rendered_img, s, h, w, c, dmax, workspace_buf=ws)
+        ctx.ws = ws
         return rendered_img
 
     @staticmethod
@@ -35,8 +39,13 @@ class GSCUDA(Function):
         grads_sigmas = torch.zeros_like(sigmas)
         grads_coords = torch.zeros_like(coords)
         grads_colors = torch.zeros_like(colors)
-        GSWrapper.gs_render_backward(sigmas, coords, colors, grad_output.contiguous(), grads_sigmas,
-                                     grads_coords, grads_colors, s, h, w, c, dmax)
+        ws, ctx.ws = getattr(ctx, "ws", None), None
+        if ws is not None and GSWrapper.get_reuse_setup():
+            GSWrapper.gs_render_backward_prepared(sigmas, grad_output.contiguous(), grads_sigmas, grads_coords,
+                                                  grads_colors, s, h, w, ws)
+        else:
+            GSWrapper.gs_render_backward(sigmas, coords, colors, grad_output.contiguous(), grads_sigmas,
+                                         grads_coords, grads_colors, s, h, w, c, dmax)
         return (grads_sigmas, grads_coords, grads_colors, None, None)
 
 

@@ -163,7 +163,10 @@ int gsr_forward_window(const float* sigmas, const float* coords, const float* co
  * sort by home bin) and leaves it in `workspace`; as long as the workspace is untouched and
  * (s, h, w, dmax, ksigma) are the same, any number of raster passes can reuse it -- a training
  * step prepares once and runs forward and backward (GSCUDA.forward / .backward,
- * gswrapper.py:25-44, see the same Gaussians). */
+ * gswrapper.py:25-44, see the same Gaussians).  A whole-image gsr_forward call leaves the same state behind
+ * as far as gsr_backward_prepared without GSR_FLAG_DETERMINISTIC needs it (region buckets; the home-bin arrays
+ * if a bucket overflowed): gsr_forward + gsr_backward_prepared on the same workspace is how this repo's autograd
+ * boundaries avoid the second set-up (gsasr_b200/gswrapper.py). */
 int gsr_prepare(const float* sigmas, const float* coords, const float* colors, int s, int h, int w,
                 float dmax, float ksigma, void* workspace, size_t workspace_bytes, void* stream);
 int gsr_forward_prepared(float* img, int s, int h, int w, float ksigma, uint32_t flags,

@@ -286,3 +286,39 @@ def test_calls_are_cuda_graph_capturable():
     for a, b, f in zip((gs, gc, gk), ws2, fast):
         assert torch.equal(a, b)               # (Gaussian-centric backward: one writer per output, fixed order)
         assert float((f - b).abs().max()) <= 2e-4 * float(b.abs().max()) + 1e-12  # region backward: summation order
+
+
+def test_autograd_backward_reuses_the_forward_setup():
+    """gswrapper.GSCUDA / gaussian_splatting.render_chw keep the forward's workspace and run gsr_backward_prepared on it
+    (gscuda.set_reuse_setup): same gradients as the full backward call, a second backward through a retained graph
+    (workspace already released) included; clustered field: the buckets overflow and both passes take the fallback."""
+    from gsasr_b200 import gaussian_splatting as gsp
+    from gsasr_b200.gswrapper import gaussiansplatting_render
+    rng = np.random.default_rng(11)
+    cases = [fields.make("C1", 4)[1:], None]
+    n, h, w = 4000, 128, 128   # every Gaussian near the centre: bucket overflow -> home-bin fallback both ways
+    cases[1] = (torch.tensor(np.stack([np.full(n, 0.02), np.full(n, 0.02), np.zeros(n)], 1), dtype=torch.float32),
+                torch.tensor(rng.normal(0, 0.01, (n, 2)), dtype=torch.float32), torch.rand(n, 3), h, w)
+    for s, c, k, h, w in cases:
+        wgt = torch.rand(h, w, 3, device=DEV)
+        grads = {}
+        for reuse in (True, False):
+            gscuda.set_reuse_setup(reuse)
+            try:
+                leaves = [t.to(DEV).requires_grad_(True) for t in (s, c, k)]
+                img = gaussiansplatting_render(*leaves, (h, w), 0.5)
+                (img * wgt).sum().backward(retain_graph=True)
+                first = [t.grad.clone() for t in leaves]
+                (img * wgt).sum().backward()   # accumulates: twice the gradient
+                for t, f in zip(leaves, first):
+                    assert float((t.grad - 2 * f).abs().max()) <= 2e-4 * float(f.abs().max()) + 1e-12
+                grads[reuse] = first
+                lv2 = [t.detach().clone().requires_grad_(True) for t in leaves]
+                (gsp.render_chw(*lv2, h, w, 0.5) * wgt.permute(2, 0, 1)).sum().backward()
+                for t, f in zip(lv2, first):
+                    assert float((t.grad - f).abs().max()) <= 2e-4 * float(f.abs().max()) + 1e-12
+            finally:
+                gscuda.set_reuse_setup(True)
+        for a, b in zip(grads[True], grads[False]):
+            assert float((a - b).abs().max()) <= 2e-4 * float(b.abs().max()) + 1e-12
+
