@@ -173,3 +173,31 @@ def test_inclusion_counts_bit_identical_at_4096(h, w, dmax):
     theirs = torch.round(ref[..., 0]).cpu().numpy().astype(np.int64)
     assert np.array_equal(theirs, cnt), "oracle inclusion set differs from the reference kernel"
     assert np.array_equal(ours, cnt), "inclusion set differs from the reference kernel"
+
+
+def test_more_gaussians_than_a_bucket_entry_can_index():
+    """Maximum sizes: bucket entries hold 23-bit Gaussian indices, so a call with more than 2^23 Gaussians takes the
+    home-bin path both ways (gsr_run_tiles raises the overflow flag itself; forward: the cooperative fallback kernel,
+    backward: the guarded Gaussian-centric kernel on its strided grid).  Checked through linearity: the render of all
+    Gaussians equals the two halves (each below the limit: region path) accumulated into one image, and the
+    gradients of the whole call are those of the halves side by side."""
+    n, h, w, dmax = (1 << 23) + 4097, 512, 512, 0.1
+    g = torch.Generator(DEV).manual_seed(7)
+    u = lambda lo, hi, *shape: torch.empty(*shape, device=DEV).uniform_(lo, hi, generator=g)
+    s = torch.cat([u(0.004, 0.02, n, 2), u(-0.6, 0.6, n, 1)], 1).contiguous()
+    c, k = u(-1.0, 1.0, n, 2), u(0.0, 1e-2, n, 3)
+    whole = torch.zeros(h, w, 3, device=DEV)
+    gscuda.gs_render(s, c, k, whole, n, h, w, 3, dmax)
+    halves = torch.zeros(h, w, 3, device=DEV)
+    m = n // 2
+    for a, b in ((0, m), (m, n)):   # accumulate contract (gs.cu:58-60)
+        gscuda.gs_render(s[a:b].contiguous(), c[a:b].contiguous(), k[a:b].contiguous(), halves, b - a, h, w, 3, dmax)
+    torch.cuda.synchronize()
+    assert float(halves.max()) > 1.0   # (hundreds of Gaussians per pixel)
+    assert float((whole - halves).abs().max()) <= FWD_TOL * float(halves.abs().max())
+    grd = u(0.0, 1.0, h, w, 3)
+    got = _bwd(s, c, k, grd, dmax)
+    for i, (a, b) in enumerate(((0, m), (m, n))):
+        part = _bwd(s[a:b].contiguous(), c[a:b].contiguous(), k[a:b].contiguous(), grd, dmax)
+        for x, y in zip(got, part):
+            assert float((x[a:b] - y).abs().max()) <= 2e-4 * float(y.abs().max())
