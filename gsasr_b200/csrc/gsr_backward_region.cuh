@@ -61,16 +61,17 @@ __device__ __forceinline__ void gsr_bwd_eval_cell(const float4 a0, const float4 
     float ea, eb, ec, ed;
     gsr_upk(e0, ea, eb);
     gsr_upk(e1, ec, ed);
-    float va = gsr_ex2(ea), vb = gsr_ex2(eb), vc = gsr_ex2(ec), vd = gsr_ex2(ed);
-    if (MASKED) {
-      const bool yr = (yin >> r) & 1u;
-      va = (yr && (xin & 1u)) ? va : 0.f;
-      vb = (yr && (xin & 2u)) ? vb : 0.f;
-      vc = (yr && (xin & 4u)) ? vc : 0.f;
-      vd = (yr && (xin & 8u)) ? vd : 0.f;
-    }
+    const float va = gsr_ex2(ea), vb = gsr_ex2(eb), vc = gsr_ex2(ec), vd = gsr_ex2(ed);
     const gsr_f2 v0 = gsr_pk(va, vb), v1 = gsr_pk(vc, vd);
-    const float4 gr = gt[r * 3 + 0], gg = gt[r * 3 + 1], gb = gt[r * 3 + 2];
+    float4 gr = gt[r * 3 + 0], gg = gt[r * 3 + 1], gb = gt[r * 3 + 2];
+    if (MASKED) {  // pixels outside the dmax window: their gradient is not seen at all (v stays finite: no 0 * inf)
+      const bool yr = (yin >> r) & 1u;
+      const bool m0 = yr && (xin & 1u), m1 = yr && (xin & 2u), m2 = yr && (xin & 4u), m3 = yr && (xin & 8u);
+      gr.x = m0 ? gr.x : 0.f, gg.x = m0 ? gg.x : 0.f, gb.x = m0 ? gb.x : 0.f;
+      gr.y = m1 ? gr.y : 0.f, gg.y = m1 ? gg.y : 0.f, gb.y = m1 ? gb.y : 0.f;
+      gr.z = m2 ? gr.z : 0.f, gg.z = m2 ? gg.z : 0.f, gb.z = m2 ? gb.z : 0.f;
+      gr.w = m3 ? gr.w : 0.f, gg.w = m3 ? gg.w : 0.f, gb.w = m3 ? gb.w : 0.f;
+    }
     const gsr_f2 gr0 = gsr_pk(gr.x, gr.y), gr1 = gsr_pk(gr.z, gr.w), gg0 = gsr_pk(gg.x, gg.y), gg1 = gsr_pk(gg.z, gg.w);
     const gsr_f2 gb0 = gsr_pk(gb.x, gb.y), gb1 = gsr_pk(gb.z, gb.w);
     const gsr_f2 u0 = gsr_mul2(v0, gsr_fma2(gr0, cr, gsr_fma2(gg0, cg, gsr_mul2(gb0, cb))));

@@ -322,3 +322,27 @@ def test_autograd_backward_reuses_the_forward_setup():
         for a, b in zip(grads[True], grads[False]):
             assert float((a - b).abs().max()) <= 2e-4 * float(b.abs().max()) + 1e-12
 
+
+
+@pytest.mark.parametrize("flags", [0, 0x20])
+def test_non_finite_gradient_pixel_stays_inside_its_dmax_windows(flags):
+    """One inf in dL/dimg (an AMP overflow step): the reference sums a Gaussian's gradient over its dmax window only
+    (gs.cu:112-131), so Gaussians whose window does not contain that pixel keep finite gradients.  Both backward
+    kernels evaluate pixels beyond the window (whole cells / whole patches) and must not turn 0 * inf into NaN."""
+    rng = np.random.default_rng(21)
+    n, h, w, dmax = 600, 64, 64, 0.12
+    s = torch.tensor(np.stack([rng.uniform(0.02, 0.2, n), rng.uniform(0.02, 0.2, n), rng.uniform(-0.7, 0.7, n)], 1),
+                     dtype=torch.float32, device=DEV)
+    c = torch.tensor(rng.uniform(-1, 1, (n, 2)), dtype=torch.float32, device=DEV)
+    k = torch.rand(n, 3, device=DEV)
+    g = torch.rand(h, w, 3, device=DEV)
+    py, px = 21, 38
+    g[py, px, 1] = float("inf")
+    out = [torch.zeros_like(s), torch.zeros_like(c), torch.zeros_like(k)]
+    gscuda.gs_render_backward(s, c, k, g, *out, n, h, w, 3, dmax, flags=flags)
+    torch.cuda.synchronize()
+    xs, ys = 2.0 * px / (w - 1) - 1.0, 2.0 * py / (h - 1) - 1.0   # pixel centre in the reference's coordinates
+    far = ((c[:, 0] - xs).abs() > dmax + 1e-3) | ((c[:, 1] - ys).abs() > dmax + 1e-3)
+    assert int(far.sum()) > n // 2 and int((~far).sum()) > 3
+    for t in out:
+        assert bool(torch.isfinite(t[far]).all())
