@@ -56,7 +56,7 @@ __device__ __forceinline__ void gsr_bwd_eval_cell(const float4 a0, const float4 
   for (int r = 0; r < 4; ++r) {
     const float dy = ny[r] + a0.y;
     const gsr_f2 dyb = gsr_pk(dy, dy);
-    const gsr_f2 t12 = gsr_mul2(b2, dyb), t02 = gsr_mul2(gsr_mul2(c2, dyb), dyb);
+    const gsr_f2 t12 = gsr_mul2(b2, dyb), t02 = gsr_mul2(gsr_mul2(c2, dyb), dyb);  // (scalar forms: same time)
     const gsr_f2 e0 = gsr_fma2(dx0, gsr_add2(ad0, t12), t02), e1 = gsr_fma2(dx1, gsr_add2(ad1, t12), t02);
     float ea, eb, ec, ed;
     gsr_upk(e0, ea, eb);
