@@ -261,10 +261,18 @@ def _gather_bands(full, bands, rank, group):
     return full
 
 
-def _band_backward_cuda(sigmas, coords, colors, grads_band, h, w, row0, rows, dmax):
+def _grad_views(sigmas, coords, colors):
+    """One flat fp32 buffer of 8 values per Gaussian and the three contiguous gradient arrays that live in it
+    ((N,3) | (N,2) | (N,3), one after the other): a single collective reduces all of them, no packing copies."""
+    n = sigmas.shape[0]
+    flat = torch.zeros(8 * n, device=sigmas.device, dtype=torch.float32)
+    return flat, flat[:3 * n].view(n, 3), flat[3 * n:5 * n].view(n, 2), flat[5 * n:].view(n, 3)
+
+
+def _band_backward_cuda(sigmas, coords, colors, grads_band, h, w, row0, rows, dmax, out=None):
     from . import gscuda
 
-    gs, gc, gk = torch.zeros_like(sigmas), torch.zeros_like(coords), torch.zeros_like(colors)
+    gs, gc, gk = out if out is not None else (torch.zeros_like(sigmas), torch.zeros_like(coords), torch.zeros_like(colors))
     gscuda.gs_render_backward_band(sigmas, coords, colors, grads_band.contiguous(), gs, gc, gk,
                                    sigmas.shape[0], h, w, 3, row0, rows, dmax)
     return gs, gc, gk
@@ -275,9 +283,17 @@ def backward_image_bands(sigmas, coords, colors, grads, h: int, w: int, dmax: fl
     """Gradients of render_image_bands: `grads` is the full (h,w,3) dL/dimg (every rank reads only
     its band of it).  Returns (grads_sigmas, grads_coords, grads_colors), identical on every rank
     after one all-reduce(sum) of 32 bytes per Gaussian."""
-    backward_band = backward_band or _band_backward_cuda
     rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
     row0, rows = band_rows(h, rank, world)
+    if backward_band is None and sigmas.is_cuda and sigmas.dtype == torch.float32:
+        # the three gradient arrays are views of ONE buffer: a single all-reduce, no packing or unpacking copies
+        flat, gs, gc, gk = _grad_views(sigmas, coords, colors)
+        if rows > 0:
+            _band_backward_cuda(sigmas, coords, colors, grads[row0:row0 + rows], h, w, row0, rows, dmax, out=(gs, gc, gk))
+        if world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        return gs, gc, gk
+    backward_band = backward_band or _band_backward_cuda
     if rows > 0:
         gs, gc, gk = backward_band(sigmas, coords, colors, grads[row0:row0 + rows], h, w, row0, rows, dmax)
     else:
