@@ -67,9 +67,29 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-def bind_to_gpu_numa(local: int):
+def numa_memory_policy(node):
+    """set_mempolicy(2) for the calling thread: MPOL_PREFERRED on `node` (None: back to MPOL_DEFAULT).  Placement of the
+    pinned staging buffers without touching any thread's CPU affinity.  Returns True if the kernel took it."""
+    try:
+        import ctypes, platform
+
+        nr = {"x86_64": 238, "aarch64": 237}.get(platform.machine())
+        if nr is None:
+            return False
+        libc = ctypes.CDLL(None, use_errno=True)
+        if node is None:
+            return libc.syscall(nr, 0, None, 0) == 0
+        mask = ctypes.c_ulong(1 << int(node))
+        return libc.syscall(nr, 1, ctypes.byref(mask), 64) == 0
+    except Exception:
+        return False
+
+
+def bind_to_gpu_numa(local: int, bind: bool = True):
     """Pin this rank's threads to the NUMA node its GPU hangs off, BEFORE the pinned host buffers are allocated
-    (first touch places them on that node).  Best effort: returns what was done for the JSON line."""
+    (first touch places them on that node).  bind=False (a single rank, whose CPU arms should keep every core): only
+    the memory policy of the calling thread prefers that node while the pinned buffers are allocated.
+    Best effort: returns what was done for the JSON line."""
     try:
         import pynvml
 
@@ -108,6 +128,10 @@ def bind_to_gpu_numa(local: int):
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             a, _, b = part.partition("-")
             cpus.update(range(int(a), int(b or a) + 1))
+        if not bind:
+            ok = numa_memory_policy(node)
+            return {"numa_node": node, "how": how, "threads": "not pinned",
+                    "memory_policy": "preferred on this node while the pinned buffers are allocated" if ok else "unchanged (set_mempolicy refused)"}
         allowed = cpus & set(os.sched_getaffinity(0))
         if allowed:
             os.sched_setaffinity(0, allowed)
@@ -408,7 +432,7 @@ def main():
         run_reference(args, rank)
         return
 
-    numa = bind_to_gpu_numa(local) if world > 1 or os.environ.get("GSR_BIND_NUMA") else {"numa_node": None, "note": "single rank: not bound"}
+    numa = bind_to_gpu_numa(local, bind=world > 1 or bool(os.environ.get("GSR_BIND_NUMA")))
 
     import torch
     import torch.distributed as dist
@@ -742,6 +766,7 @@ def main():
             out["gpu_reference"] = gpu_reference(dev)
             out["head_tail"] = head_tail_bench(dev)
         if not args.no_cpu_baseline and world == 1:
+            numa_memory_policy(None)  # the CPU arms place their memory as usual
             mps, cores, sample, _ = cpu_sample(args.workload)
             out["cpu_baseline"] = {"value": mps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
             out["cpu_reference_python"] = cpu_reference_python()
