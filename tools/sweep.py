@@ -11,7 +11,7 @@ VARIANTS = {
     # examples of what has been swept: GSR_CFG_FR_MIN_CTAS, GSR_CFG_FR_LW=4, GSR_CFG_FR_TAIL=0,
     # GSR_CFG_FR_UNROLL8=0, GSR_CFG_RB2_MIN_CTAS, GSR_CFG_MASK_PER_BAND=1, GSR_CFG_FALLBACK_COOP=0, GSH_CFG_EPI_PARTS=2
     "ws_sync_arrive": ["GSR_CFG_WS_SYNC_ARRIVE=1"],  # racecheck aid (profiles/r02_sanitizer.md)
-    "br_t16": ["GSR_CFG_BR_T=16"],   # region backward: 16 parked list positions, 4 CTAs per SM
+    "br_c4": ["GSR_CFG_BR_MIN_CTAS=4"],   # region backward: 4 CTAs per SM (121 registers): HL 654 vs 657 us, C2d 390 vs 345 us
 }
 if sys.argv[1] == "build":
     from gsasr_b200 import build
