@@ -199,3 +199,21 @@ def test_padded_batch_rescaling_algebra():
         assert np.isclose(b * sxy + 2 * a * sxx, bc * txy + 2 * ac * txx, rtol=1e-9, atol=1e-9)      # sigma_x term
         assert np.isclose(a * sxx + b * sxy + c * syy, ac * txx + bc * txy + cc * tyy, rtol=1e-9, atol=1e-9)  # Q
         assert np.isclose(sxy, txy * ax * ay, rtol=1e-9, atol=1e-9)
+
+
+def test_band_backward_gradient_views_share_one_buffer():
+    """sharding._grad_views: the three gradient arrays of the band backward are contiguous views of one flat buffer,
+    (N,3) | (N,2) | (N,3), so one all-reduce covers them and nothing is packed or unpacked."""
+    import torch
+    from gsasr_b200 import sharding
+
+    n = 37
+    s, c, k = torch.zeros(n, 3), torch.zeros(n, 2), torch.zeros(n, 3)
+    flat, gs, gc, gk = sharding._grad_views(s, c, k)
+    assert flat.shape == (8 * n,) and gs.shape == (n, 3) and gc.shape == (n, 2) and gk.shape == (n, 3)
+    assert gs.is_contiguous() and gc.is_contiguous() and gk.is_contiguous()
+    gs += 1.0
+    gc += 2.0
+    gk += 3.0
+    assert torch.equal(flat, torch.cat([torch.full((3 * n,), 1.0), torch.full((2 * n,), 2.0), torch.full((3 * n,), 3.0)]))
+    assert gs.data_ptr() == flat.data_ptr() and gk.data_ptr() == flat.data_ptr() + 4 * 5 * n
