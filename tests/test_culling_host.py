@@ -217,3 +217,29 @@ def test_band_backward_gradient_views_share_one_buffer():
     gk += 3.0
     assert torch.equal(flat, torch.cat([torch.full((3 * n,), 1.0), torch.full((2 * n,), 2.0), torch.full((3 * n,), 3.0)]))
     assert gs.data_ptr() == flat.data_ptr() and gk.data_ptr() == flat.data_ptr() + 4 * 5 * n
+
+
+@pytest.mark.parametrize("h,w,dmax", [(40, 72, 0.2), (97, 33, 0.08), (64, 64, np.inf)])
+def test_region_backward_exact_mode_sums_the_reference_window(h, w, dmax):
+    """The backward over the region buckets, ksigma=inf: the (Gaussian, cell) pairs the entries name -- clipped to the
+    cull box where the dmax window binds -- are exactly the pixels the reference's backward sums (gs.cu:112-131)."""
+    rng = np.random.default_rng(h * w + 7)
+    sig, xy, col = _random_field(rng, 120, 0.01, 0.4)
+    g = rng.uniform(0, 1, (h, w, 3)).astype(np.float32)
+    want = oracle.backward(sig, xy, col, g, dmax)
+    got = emulate.emulate_backward_cells(sig, xy, col, g, h, w, dmax, float("inf"))
+    for a, b in zip(got, want):
+        assert np.abs(a - b).max() <= 1e-9 * max(np.abs(b).max(), 1.0)
+
+
+@pytest.mark.parametrize("cfg,dmax", [("C1", 0.1), ("C1", 0.05)])
+def test_region_backward_default_ksigma_error_budget(cfg, dmax):
+    """Default k-sigma through the cell masks: the truncation moves no gradient by more than 1e-4 of the largest one
+    (tolerance of the backward parity tests: 1e-3)."""
+    _, s, c, k, h, w = fields.make(cfg)
+    s, c, k = s.numpy(), c.numpy(), k.numpy()
+    g = np.random.default_rng(3).uniform(0, 1, (h, w, 3)).astype(np.float32)
+    want = oracle.backward(s, c, k, g, dmax)
+    got = emulate.emulate_backward_cells(s, c, k, g, h, w, dmax, 0.0)
+    for a, b in zip(got, want):
+        assert np.abs(a - b).max() <= 1e-4 * np.abs(b).max()
